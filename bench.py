@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — the hot path's headline measurement (contract: task brief ④).
+
+Workload (config.workload): BASELINE.json configs[3], the HBM-streaming case the
+roofline ceilings of BASELINE.md are quoted on — a synthetic batch of 64 noisy
+512×512 images PER GPU, fixed scalar λ = 0.1, exactly 1000 accelerated PDPS
+iterations in fp64, followed by the upper-level loss 0.5‖u-ū‖² (and, at N>1, the
+NCCL all-reduce of that loss across ranks: the path's only exchange step).
+A "step" is one such pass = 64·512·512·1000 = 16.78 Gpixel-iterations per GPU.
+
+  value  — Gpixel-iter/s, whole job (all ranks), inputs resident in HBM.
+  e2e    — the same metric through the reference-facing call `denoise(data, x)` with
+           HOST (pinned) buffers: H2D of the noisy stack and D2H of the denoised
+           stack inside the timed region.
+  --impl reference — the reference algorithm on the box's host cores (the C oracle
+           port, OpenMP over images; Julia is not installed anywhere: DESIGN.md).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+M = N = 512
+O_PER_GPU = 64
+ITERS = 1000
+LAM = 0.1
+METRIC = "tv_pdps_gpixel_iter_per_s"
+UNIT = "Gpixel-iter/s"
+ALG_BYTES_PER_PIXEL_ITER_F64 = 56  # read x,y1,y2,f + write x,y1,y2
+
+
+def _config(n_gpus):
+    return {
+        "workload": "BASELINE configs[3]: synthetic 64x512x512 noisy images per GPU, scalar lambda=0.1, "
+                    "1000 accelerated PDPS iterations (tau0=5, sigma0=0.99/5) + loss 0.5||u-u_true||^2",
+        "images_per_gpu": O_PER_GPU, "image": [M, N], "iterations": ITERS, "lambda": LAM,
+        "arith": "strict (one IEEE op per reference operator; bit-identical to the oracle)",
+        "l2": "working set 7 planes x 128 MiB = 896 MiB per GPU >> 126 MB L2 (no flush needed)",
+        "parallelism": f"images sharded over {n_gpus} GPU(s), one all-reduce of the loss per step",
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if p[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except (KeyError, ValueError):
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture."""
+    p = os.path.join(ROOT, "profiles", "ncu_top_kernel.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except ValueError:
+            return None
+    return None
+
+
+def cpu_reference_step(orc, f_sample, iters, threads):
+    t0 = time.perf_counter()
+    orc.pdps(f_sample, LAM, maxiter=iters, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return f_sample.size * iters / dt / 1e9, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle as orc
+    orc.build()
+    from bpldenoising_b200.datasets import synthetic_dataset
+    cores = orc.lib().oracle_max_threads()
+    n_img = max(1, min(cores, O_PER_GPU))
+    iters = 100
+    _, f = synthetic_dataset(M, N, n_img, seed=20240601)
+    vals = []
+    for k in range(args.warmup + args.steps):
+        v, dt = cpu_reference_step(orc, f, iters, cores)
+        if k >= args.warmup:
+            vals.append((v, dt))
+    value = statistics.mean(v for v, _ in vals)
+    ms = statistics.mean(dt for _, dt in vals) * 1e3
+    sample = (f"{n_img} of the {O_PER_GPU} images (512x512) x {iters} of the {ITERS} iterations per step, "
+              f"OpenMP over images, {cores} threads; C port of the reference recursion (oracle/bpltv_oracle.c), "
+              "not Julia (not installed; its solver packages are un-vendored)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": _config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="bpltv", choices=["bpltv", "reference"])
+    ap.add_argument("--arith", default="strict", choices=["strict", "fast"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the learn_eval wall-time extras")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import bpldenoising_b200 as bp
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    W = max(args.warmup, 3)
+    K = args.steps
+
+    truth, noisy = bp.synthetic_dataset(M, N, O_PER_GPU, seed=20240601 + rank)
+    ctx = bp.Context([local], 64)
+    arith = bp.STRICT if args.arith == "strict" else bp.FAST
+    popts = bp.pdps_opts(maxiter=ITERS, arith=arith)
+    eopts = bp.eval_opts(popts, force_branch=3)  # solve + loss (fixed λ: no gradient in this config)
+
+    # ---- device-resident leg (value) ---------------------------------------------
+    # column-major M×N×O on the host == contiguous (O,N,M) torch tensor
+    d_truth = torch.from_numpy(np.ascontiguousarray(truth.transpose(2, 1, 0))).to(dev)
+    d_noisy = torch.from_numpy(np.ascontiguousarray(noisy.transpose(2, 1, 0))).to(dev)
+    d_costgrad = torch.zeros(2, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx.set_dataset_device(d_truth.data_ptr(), d_noisy.data_ptr(), M, N, O_PER_GPU, stream)
+
+    def step():
+        ctx.learn_eval_device(LAM, 0.1, d_costgrad.data_ptr(), eopts, stream=stream)
+        if world > 1:
+            dist.all_reduce(d_costgrad)  # upper-level loss summed over ranks (NCCL)
+
+    for _ in range(W):
+        step()
+    launches_per_step = ctx.stats()["kernel_launches"]
+    kernel_used = ctx.stats()["pdps_kernel_used"]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(K):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / K
+    pix_iter_per_step = float(M) * N * O_PER_GPU * ITERS
+    value = pix_iter_per_step * world / (ms_per_step * 1e-3) / 1e9
+    loss = float(d_costgrad[0].item())
+
+    # ---- roofline of the dominant kernel (pdps_march: one launch per iteration) -----
+    peak, peak_src = hbm_peak()
+    # per-launch duration measured live: K steps × ITERS launches back to back on this stream;
+    # the loss reduction (2 tiny launches per step) is < 0.1 % of the step
+    launch_ms = ms_per_step / ITERS
+    alg_bytes = ALG_BYTES_PER_PIXEL_ITER_F64 * float(M) * N * O_PER_GPU
+    achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(), "peak_source": peak_src,
+                "kernel": "pdps_march_kernel<double,VEC=2> (kernel id %d)" % kernel_used,
+                "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_ms}
+
+    # ---- end-to-end leg through the reference-facing call with host buffers ----------
+    h_in = torch.empty((O_PER_GPU, N, M), dtype=torch.float64).pin_memory()
+    h_out = torch.empty((O_PER_GPU, N, M), dtype=torch.float64).pin_memory()
+    h_in.copy_(torch.from_numpy(np.ascontiguousarray(noisy.transpose(2, 1, 0))))
+    np_in = h_in.numpy().transpose(2, 1, 0)    # Fortran-ordered M×N×O views of the pinned buffers
+    np_out = h_out.numpy().transpose(2, 1, 0)
+    for _ in range(2):
+        ctx.denoise(np_in, LAM, popts, out=np_out)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        u = ctx.denoise(np_in, LAM, popts, out=np_out)   # blocking: H2D + solve + D2H
+        _ = float(u[0, 0, 0])                             # the result is read on the host
+    t1 = time.perf_counter()
+    e2e_ms = (t1 - t0) * 1e3 / K
+    st = ctx.stats()
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_val = pix_iter_per_step * world / (e2e_ms * 1e-3) / 1e9
+    nbytes = M * N * O_PER_GPU * 8
+    e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+           "ms_per_step": e2e_ms, "device_ms": {"upload": st["ms_upload"], "pdps": st["ms_pdps"],
+                                                 "download": st["ms_download"]}}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": _config(world), "roofline": roofline, "e2e": e2e,
+        "gpu_launches": int(launches_per_step * K), "loss": loss,
+    }
+
+    if rank == 0:
+        line["clocks"] = clk.summary()
+        # ---- CPU baseline: the oracle port on this box's host cores (bounded sample) ----
+        from oracle import oracle as orc
+        orc.build()
+        cores = orc.lib().oracle_max_threads()
+        n_img = max(1, min(cores, O_PER_GPU))
+        f_s = np.asfortranarray(noisy[:, :, np.arange(n_img) % O_PER_GPU])
+        iters_s = 200
+        v_all, dt_all = cpu_reference_step(orc, f_s, iters_s, cores)
+        v_one, dt_one = cpu_reference_step(orc, np.asfortranarray(noisy[:, :, :1]), iters_s, 1)
+        line["cpu_baseline"] = {
+            "value": v_all, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_img} images 512x512 x {iters_s} iterations, OpenMP over images ({dt_all:.1f} s); "
+                      f"1 thread / 1 image: {v_one:.4f} {UNIT} ({dt_one:.1f} s). C restatement of the reference "
+                      "recursion (oracle/bpltv_oracle.c) — Julia is not installed",
+            "single_thread_value": v_one,
+        }
+        # ---- extras: learn_eval wall time on the reference-shaped configs (N=1 only) ------
+        if world == 1 and not args.no_extras:
+            line["learn_eval"] = learn_eval_extras(bp)
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def learn_eval_extras(bp):
+    """Wall time of one tv_op_learning_function evaluation (5000 PDPS iterations + cost
+    + λ-gradient) on synthetic data shaped like BASELINE configs 1-3 (O×128×128)."""
+    out = {}
+    for name, O, x, Delta in (("config1_like_1x128x128_scalar", 1, 0.1, 0.1),
+                              ("config2_like_10x128x128_scalar", 10, 0.1, 0.1),
+                              ("config3_like_1x128x128_patch2x2", 1, 0.01 * np.ones((2, 2)), 1e-4)):
+        data = bp.synthetic_dataset(128, 128, O, seed=7)
+        with bp.Context([0], 64) as c:
+            c.set_dataset(data)
+            c.learn_eval(x, Delta)  # warm-up (allocations)
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                _, cost, g = c.learn_eval(x, Delta)
+                ts.append((time.perf_counter() - t0) * 1e3)
+            st = c.stats()
+            out[name] = {"ms": min(ts), "ms_pdps": st["ms_pdps"], "ms_gradient": st["ms_gradient"],
+                         "cost": cost, "grad": np.asarray(g).ravel().tolist()}
+    return out
+
+
+if __name__ == "__main__":
+    sys.exit(main())

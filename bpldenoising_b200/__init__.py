@@ -1,0 +1,24 @@
+"""bpldenoising_b200 — B200-native (sm_100a) TV-denoising solve and λ-gradient behind
+the learning-function interface of dvillacis/BPLDenoising.
+
+Only the hot path lives here: the CUDA kernels + C ABI (`csrc/`, `libbpltv.so`,
+`include/bpltv.h`) and the host-side mirror of the reference interface.  Importing
+the package loads the CUDA library and fails loudly when it has not been built.
+"""
+from . import _lib
+from ._lib import (BpltvError, FAST, KERNEL_AUTO, KERNEL_GENERIC, KERNEL_MARCH, KERNEL_RESIDENT,
+                   KERNEL_TBLOCK, STRICT)
+
+_lib.load()  # no silent CPU path: ImportError if libbpltv.so is absent
+
+from .learning import (Context, L2CostFunction, TVDenoise, default_context, denoise, eval_opts,  # noqa: E402
+                       gradient, gradient_reg, pdps_opts, tv_op_learning_function)
+from .datasets import synthetic_dataset  # noqa: E402
+from .parallel import shard_range  # noqa: E402
+
+__all__ = [
+    "BpltvError", "Context", "L2CostFunction", "TVDenoise", "default_context", "denoise",
+    "eval_opts", "gradient", "gradient_reg", "pdps_opts", "tv_op_learning_function",
+    "synthetic_dataset", "shard_range", "STRICT", "FAST", "KERNEL_AUTO", "KERNEL_GENERIC",
+    "KERNEL_MARCH", "KERNEL_RESIDENT", "KERNEL_TBLOCK",
+]

@@ -1,0 +1,908 @@
+// bpltv_api.cu — C ABI of libbpltv.so (see include/bpltv.h).
+//
+// Host side of the hot path: context / buffer management, image sharding over the
+// devices of one process, kernel dispatch.  No CPU fallback: every numerical
+// operation below is a CUDA kernel for sm_100a.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bpltv.h"
+#include "common.cuh"
+#include "pdps_generic.cuh"
+#include "pdps_march.cuh"
+#include "pdps_resident.cuh"
+#include "gradient.cuh"
+
+using namespace bpltv;
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                          \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(BPLTV_ERR_CUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,  \
+                        cudaGetErrorString(e_));                                              \
+    } while (0)
+
+#define RC_TRY(expr)             \
+    do {                         \
+        int rc_ = (expr);        \
+        if (rc_ != 0) return rc_; \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// device buffers (grow-only)
+// ---------------------------------------------------------------------------
+struct DBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need)
+    {
+        if (need <= bytes) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(BPLTV_ERR_ALLOC, "cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e));
+        }
+        bytes = need;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct StepKey {
+    double tau0 = -1, sigma0 = -1, opnorm = -1;
+    int accel = -1, maxiter = -1, prec = 0;
+    bool operator==(const StepKey &o) const
+    {
+        return tau0 == o.tau0 && sigma0 == o.sigma0 && opnorm == o.opnorm && accel == o.accel &&
+               maxiter == o.maxiter && prec == o.prec;
+    }
+};
+
+struct Dev {
+    int id = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {nullptr};
+    // resident dataset shard
+    int M = 0, N = 0, O = 0;  // O = images on this device
+    int o_begin = 0;          // first global image index of the shard
+    DBuf truth, noisy;
+    // solve state (ping-pong) and scratch
+    DBuf x[2], y1[2], y2[2], fbuf, amap, steps, partials, scalars, stage, lam_dev, ubuf;
+    GradWork grad;            // gradient.cuh
+    StepKey steps_key;
+    std::vector<unsigned char> steps_host;
+    long long launches = 0;
+};
+
+struct bpltv_ctx {
+    int prec = 64;
+    std::vector<Dev> devs;
+    int M = 0, N = 0, O = 0;  // resident dataset shape (global)
+    bool have_dataset = false;
+    bpltv_stats stats;
+};
+
+static void shard_range(int O, int ndev, int d, int &begin, int &count)
+{
+    // contiguous blocks of ceil(O/ndev) images
+    const int per = (O + ndev - 1) / ndev;
+    begin = std::min(O, d * per);
+    count = std::min(O, begin + per) - begin;
+}
+
+// ---------------------------------------------------------------------------
+// step-size recursion (S1, S2): σ=σ₀/R_K, τ=τ₀/R_K, γ=1, ω=1/√(1+2γτ), τ←τω, σ←σ/ω
+// ---------------------------------------------------------------------------
+template <typename Real>
+static int upload_steps(Dev &d, const bpltv_pdps_opts &o, cudaStream_t st)
+{
+    StepKey key;
+    key.tau0 = o.tau0; key.sigma0 = o.sigma0; key.opnorm = o.opnorm; key.accel = o.accel;
+    key.maxiter = o.maxiter; key.prec = (int)sizeof(Real);
+    if (key == d.steps_key) return 0;
+    const size_t n = (size_t)std::max(o.maxiter, 1);
+    d.steps_host.resize(n * sizeof(StepConsts<Real>));
+    StepConsts<Real> *h = reinterpret_cast<StepConsts<Real> *>(d.steps_host.data());
+    double sigma = o.sigma0 / o.opnorm;
+    double tau = o.tau0 / o.opnorm;
+    const double gamma = 1.0;
+    for (int k = 0; k < o.maxiter; ++k) {
+        double omega = 1.0;
+        if (o.accel) omega = 1.0 / std::sqrt(1.0 + 2.0 * gamma * tau);
+        StepConsts<Real> s;
+        s.tau = (Real)tau; s.sigma = (Real)sigma; s.omega = (Real)omega;
+        // (1+τ), (1+ω) are formed in the compute type from the rounded τ, ω, as the
+        // reference's broadcast would form them per element
+        s.one_p_tau = (Real)1 + s.tau;
+        s.one_p_omega = (Real)1 + s.omega;
+        s.inv_one_p_tau = (Real)(1.0 / (1.0 + tau));
+        s.tau_over_one_p_tau = (Real)(tau / (1.0 + tau));
+        s.pad = 0;
+        h[k] = s;
+        if (o.accel) { tau = tau * omega; sigma = sigma / omega; }
+    }
+    RC_TRY(d.steps.ensure(n * sizeof(StepConsts<Real>)));
+    // stream-ordered w.r.t. kernels still reading the previous table
+    CU_TRY(cudaMemcpyAsync(d.steps.p, h, n * sizeof(StepConsts<Real>), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    d.steps_key = key;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// PDPS driver
+// ---------------------------------------------------------------------------
+static int env_int(const char *name, int dflt)
+{
+    const char *s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+template <typename Real>
+static int march_vec(int M)
+{
+    int forced = env_int("BPLTV_MARCH_VEC", 0);
+    const int cands64[3] = {2, 4, 1}, cands32[3] = {4, 2, 1};
+    const int *c = sizeof(Real) == 8 ? cands64 : cands32;
+    if (forced == 1 || forced == 2 || forced == 4) {
+        if (M % forced == 0 && (M / forced + 31) / 32 * 32 <= 1024) return forced;
+    }
+    // prefer 16-byte accesses with <= 256 threads per column (no register cap), then
+    // wider rows per thread for tall images, then anything that fits one CTA
+    for (int pass = 0; pass < 2; ++pass)
+        for (int k = 0; k < 3; ++k) {
+            const int v = c[k];
+            if (M % v) continue;
+            const int nt = (M / v + 31) / 32 * 32;
+            if (nt <= (pass == 0 ? 256 : 1024)) return v;
+        }
+    return 0;
+}
+
+template <typename Real, int VEC, int MAXT>
+static void launch_march_t(const MarchArgs<Real> &a, int nthreads, int nunits, bool map, bool strict, cudaStream_t st)
+{
+    if (map) {
+        if (strict) pdps_march_kernel<Real, VEC, true, true, MAXT><<<nunits, nthreads, 0, st>>>(a);
+        else pdps_march_kernel<Real, VEC, true, false, MAXT><<<nunits, nthreads, 0, st>>>(a);
+    } else {
+        if (strict) pdps_march_kernel<Real, VEC, false, true, MAXT><<<nunits, nthreads, 0, st>>>(a);
+        else pdps_march_kernel<Real, VEC, false, false, MAXT><<<nunits, nthreads, 0, st>>>(a);
+    }
+}
+
+template <typename Real, int VEC>
+static void launch_march_vec(const MarchArgs<Real> &a, int nthreads, int nunits, bool map, bool strict, cudaStream_t st)
+{
+    // ≤256 threads: the register allocator may use up to 255 registers per thread
+    if (nthreads <= 256) launch_march_t<Real, VEC, 256>(a, nthreads, nunits, map, strict, st);
+    else launch_march_t<Real, VEC, 1024>(a, nthreads, nunits, map, strict, st);
+}
+
+template <typename Real>
+static void launch_generic(const GenericArgs<Real> &a, bool map, bool strict, cudaStream_t st)
+{
+    const int bt = a.M >= 256 ? 256 : std::max(32, (a.M + 31) / 32 * 32);
+    dim3 grid((a.M + bt - 1) / bt, a.N, a.O);
+    if (map) {
+        if (strict) pdps_generic_kernel<Real, true, true><<<grid, bt, 0, st>>>(a);
+        else pdps_generic_kernel<Real, true, false><<<grid, bt, 0, st>>>(a);
+    } else {
+        if (strict) pdps_generic_kernel<Real, false, true><<<grid, bt, 0, st>>>(a);
+        else pdps_generic_kernel<Real, false, false><<<grid, bt, 0, st>>>(a);
+    }
+}
+
+// Runs opts.maxiter iterations on `f` (device, M×N×O Reals).  On return (stream
+// order) the denoised stack is in *u_result (one of the ping-pong buffers).
+template <typename Real>
+static int run_pdps(Dev &d, const Real *f, int M, int N, int O, double alpha_s, const Real *alpha_map,
+                    const bpltv_pdps_opts &o, cudaStream_t st, const Real **u_result, int *kernel_used)
+{
+    if (O == 0) { *u_result = nullptr; return 0; }
+    const size_t n = (size_t)M * N * O;
+    for (int b = 0; b < 2; ++b) {
+        RC_TRY(d.x[b].ensure(n * sizeof(Real)));
+        RC_TRY(d.y1[b].ensure(n * sizeof(Real)));
+        RC_TRY(d.y2[b].ensure(n * sizeof(Real)));
+    }
+    const bool strict = o.arith == BPLTV_ARITH_STRICT;
+    const bool rho = o.rho != 0.0;
+    const bool map = alpha_map != nullptr;
+
+    int kernel = o.kernel;
+    if (kernel == BPLTV_KERNEL_AUTO) kernel = env_int("BPLTV_PDPS_KERNEL", 0);
+    if (kernel == BPLTV_KERNEL_AUTO) {
+        if (resident_eligible<Real>(d.smem_optin, M, N) && !rho && O * resident_cluster_size<Real>(M, N) <= 4 * d.sm_count)
+            kernel = BPLTV_KERNEL_RESIDENT;
+        else
+            kernel = march_vec<Real>(M) ? BPLTV_KERNEL_MARCH : BPLTV_KERNEL_GENERIC;
+    }
+    if (kernel == BPLTV_KERNEL_RESIDENT && (!resident_eligible<Real>(d.smem_optin, M, N) || rho))
+        return fail(BPLTV_ERR_ARG, "resident PDPS kernel does not take %dx%d (rho=%g) at this precision", M, N, o.rho);
+    if (kernel == BPLTV_KERNEL_MARCH && !march_vec<Real>(M))
+        return fail(BPLTV_ERR_ARG, "march PDPS kernel does not take M=%d", M);
+    if (kernel == BPLTV_KERNEL_TBLOCK)
+        return fail(BPLTV_ERR_ARG, "temporally blocked PDPS kernel is not built yet");
+    *kernel_used = kernel;
+
+    RC_TRY(upload_steps<Real>(d, o, st));
+    const StepConsts<Real> *steps = d.steps.as<StepConsts<Real>>();
+
+    if (kernel == BPLTV_KERNEL_RESIDENT) {
+        // whole solve in one launch; x⁰/y⁰ are formed on chip
+        ResidentArgs<Real> a;
+        a.f = f; a.u_out = d.x[0].as<Real>(); a.alpha_map = alpha_map; a.steps = steps;
+        a.maxiter = o.maxiter; a.M = M; a.N = N; a.O = O; a.alpha_s = (Real)alpha_s; a.init_mode = o.init_mode;
+        RC_TRY(launch_resident<Real>(a, map, strict, st));
+        d.launches += 1;
+        *u_result = d.x[0].as<Real>();
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(BPLTV_ERR_CUDA, "resident PDPS launch failed: %s", cudaGetErrorString(e));
+        return 0;
+    }
+
+    // x⁰ = 0 | f (S3), y⁰ = 0
+    if (o.init_mode) CU_TRY(cudaMemcpyAsync(d.x[0].p, f, n * sizeof(Real), cudaMemcpyDeviceToDevice, st));
+    else CU_TRY(cudaMemsetAsync(d.x[0].p, 0, n * sizeof(Real), st));
+    CU_TRY(cudaMemsetAsync(d.y1[0].p, 0, n * sizeof(Real), st));
+    CU_TRY(cudaMemsetAsync(d.y2[0].p, 0, n * sizeof(Real), st));
+
+    if (kernel == BPLTV_KERNEL_MARCH) {
+        const int vec = march_vec<Real>(M);
+        const int nthreads = (M / vec + 31) / 32 * 32;
+        // enough CTAs to cover the chip several times over; chunks no shorter than 8 columns
+        const int target_units = d.sm_count * env_int("BPLTV_MARCH_UNITS_PER_SM", 8);
+        int chunk = env_int("BPLTV_MARCH_CHUNK", 0);
+        if (chunk <= 0) {
+            const long long cols = (long long)N * O;
+            chunk = (int)std::max<long long>(8, (cols + target_units - 1) / target_units);
+        }
+        chunk = std::min(chunk, N);
+        const int cpi = (N + chunk - 1) / chunk;
+        MarchArgs<Real> a;
+        a.f = f; a.alpha_map = alpha_map; a.steps = steps; a.M = M; a.N = N; a.O = O;
+        a.chunk = chunk; a.chunks_per_image = cpi; a.alpha_s = (Real)alpha_s; a.rho = (Real)o.rho;
+        for (int it = 0; it < o.maxiter; ++it) {
+            const int bi = it & 1, bo = bi ^ 1;
+            a.x_in = d.x[bi].as<Real>(); a.y1_in = d.y1[bi].as<Real>(); a.y2_in = d.y2[bi].as<Real>();
+            a.x_out = d.x[bo].as<Real>(); a.y1_out = d.y1[bo].as<Real>(); a.y2_out = d.y2[bo].as<Real>();
+            a.it = it;
+            if (vec == 4) launch_march_vec<Real, 4>(a, nthreads, cpi * O, map, strict, st);
+            else if (vec == 2) launch_march_vec<Real, 2>(a, nthreads, cpi * O, map, strict, st);
+            else launch_march_vec<Real, 1>(a, nthreads, cpi * O, map, strict, st);
+        }
+    } else {
+        GenericArgs<Real> a;
+        a.f = f; a.alpha_map = alpha_map; a.steps = steps; a.M = M; a.N = N; a.O = O;
+        a.alpha_s = (Real)alpha_s; a.rho = (Real)o.rho;
+        if (N > 65535 || O > 65535) return fail(BPLTV_ERR_ARG, "generic kernel: N and O must be <= 65535");
+        for (int it = 0; it < o.maxiter; ++it) {
+            const int bi = it & 1, bo = bi ^ 1;
+            a.x_in = d.x[bi].as<Real>(); a.y1_in = d.y1[bi].as<Real>(); a.y2_in = d.y2[bi].as<Real>();
+            a.x_out = d.x[bo].as<Real>(); a.y1_out = d.y1[bo].as<Real>(); a.y2_out = d.y2[bo].as<Real>();
+            a.it = it;
+            launch_generic<Real>(a, map, strict, st);
+        }
+    }
+    d.launches += o.maxiter;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(BPLTV_ERR_CUDA, "PDPS kernel launch failed: %s", cudaGetErrorString(e));
+    *u_result = d.x[o.maxiter & 1].as<Real>();
+    return 0;
+}
+
+// λ handling: scalar → alpha_s; grid → device map (PatchOp up-sampling, S7)
+template <typename Real>
+static int prepare_lambda(Dev &d, const double *lam, int lm, int ln, int M, int N, cudaStream_t st,
+                          double *alpha_s, const Real **alpha_map)
+{
+    if (lm == 1 && ln == 1) {
+        *alpha_s = lam[0];
+        *alpha_map = nullptr;
+        return 0;
+    }
+    RC_TRY(d.lam_dev.ensure((size_t)lm * ln * sizeof(double)));
+    RC_TRY(d.amap.ensure((size_t)M * N * sizeof(Real)));
+    CU_TRY(cudaMemcpyAsync(d.lam_dev.p, lam, (size_t)lm * ln * sizeof(double), cudaMemcpyHostToDevice, st));
+    const int n = M * N;
+    patch_upsample_kernel<Real><<<(n + 255) / 256, 256, 0, st>>>(d.lam_dev.as<double>(), lm, ln, d.amap.as<Real>(), M, N);
+    d.launches += 1;
+    *alpha_s = 0.0;
+    *alpha_map = d.amap.as<Real>();
+    return 0;
+}
+
+static int check_lambda(const double *lam, int lm, int ln)
+{
+    if (!lam || lm < 1 || ln < 1) return fail(BPLTV_ERR_ARG, "lambda grid must be at least 1x1");
+    for (int k = 0; k < lm * ln; ++k)
+        if (!(lam[k] >= 0.0) || !std::isfinite(lam[k]))
+            return fail(BPLTV_ERR_ARG, "lambda[%d] = %g must be finite and >= 0", k, lam[k]);
+    return 0;
+}
+
+static int check_pdps_opts(const bpltv_pdps_opts &o)
+{
+    if (!(o.tau0 > 0) || !(o.sigma0 > 0) || !(o.opnorm > 0) || o.maxiter < 0 || o.rho < 0)
+        return fail(BPLTV_ERR_ARG, "invalid PDPS options (tau0=%g sigma0=%g opnorm=%g rho=%g maxiter=%d)", o.tau0,
+                    o.sigma0, o.opnorm, o.rho, o.maxiter);
+    if (!(o.tau0 * o.sigma0 < 1.0))
+        return fail(BPLTV_ERR_ARG, "PDPS step condition tau0*sigma0 < 1 violated (%g)", o.tau0 * o.sigma0);
+    if (o.arith != BPLTV_ARITH_STRICT && o.arith != BPLTV_ARITH_FAST) return fail(BPLTV_ERR_ARG, "bad arith mode");
+    return 0;
+}
+
+// host double stack (M×N×count) → device Real buffer
+template <typename Real>
+static int upload_stack(Dev &d, const double *h, size_t n, DBuf &dst, cudaStream_t st)
+{
+    RC_TRY(dst.ensure(std::max<size_t>(n, 1) * sizeof(Real)));
+    if (n == 0) return 0;
+    if (sizeof(Real) == 8) {
+        CU_TRY(cudaMemcpyAsync(dst.p, h, n * 8, cudaMemcpyHostToDevice, st));
+    } else {
+        RC_TRY(d.stage.ensure(n * 8));
+        CU_TRY(cudaMemcpyAsync(d.stage.p, h, n * 8, cudaMemcpyHostToDevice, st));
+        const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+        convert_kernel<Real, double><<<blocks, 256, 0, st>>>(d.stage.as<double>(), dst.as<Real>(), n);
+        d.launches += 1;
+    }
+    return 0;
+}
+
+template <typename Real>
+static int download_stack(Dev &d, const Real *src, size_t n, double *h, cudaStream_t st)
+{
+    if (n == 0) return 0;
+    if (sizeof(Real) == 8) {
+        CU_TRY(cudaMemcpyAsync(h, src, n * 8, cudaMemcpyDeviceToHost, st));
+    } else {
+        RC_TRY(d.stage.ensure(n * 8));
+        const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+        convert_kernel<double, Real><<<blocks, 256, 0, st>>>(src, d.stage.as<double>(), n);
+        d.launches += 1;
+        CU_TRY(cudaMemcpyAsync(h, d.stage.p, n * 8, cudaMemcpyDeviceToHost, st));
+    }
+    return 0;
+}
+
+// cost of this device's shard into scalars[0] (device double)
+template <typename Real>
+static int run_cost(Dev &d, const Real *u, const Real *ubar, size_t n, double *d_out, cudaStream_t st)
+{
+    const int blocks = (int)std::max<size_t>(1, std::min<size_t>((n + 256 * 8 - 1) / (256 * 8), 1024));
+    RC_TRY(d.partials.ensure(1024 * sizeof(double)));
+    cost_partial_kernel<Real><<<blocks, 256, 0, st>>>(u, ubar, n, d.partials.as<double>());
+    sum_partials_kernel<<<1, 256, 0, st>>>(d.partials.as<double>(), blocks, 0.5, d_out);
+    d.launches += 2;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// per-precision implementations of the entry points
+// ---------------------------------------------------------------------------
+static float ev_ms(cudaEvent_t a, cudaEvent_t b)
+{
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return ms;
+}
+
+template <typename Real>
+static int denoise_impl(bpltv_ctx *ctx, const double *noisy, int M, int N, int O, const double *lam, int lm, int ln,
+                        const bpltv_pdps_opts &o, double *u_out)
+{
+    const int ndev = (int)ctx->devs.size();
+    const size_t plane = (size_t)M * N;
+    std::memset(&ctx->stats, 0, sizeof ctx->stats);
+    for (int di = 0; di < ndev; ++di) {
+        Dev &d = ctx->devs[di];
+        CU_TRY(cudaSetDevice(d.id));
+        d.launches = 0;
+        int ob, oc;
+        if (noisy) shard_range(O, ndev, di, ob, oc);
+        else { ob = d.o_begin; oc = d.O; }
+        cudaStream_t st = d.stream;
+        CU_TRY(cudaEventRecord(d.ev[0], st));
+        const Real *f;
+        if (noisy) {
+            RC_TRY(upload_stack<Real>(d, noisy + plane * ob, plane * oc, d.fbuf, st));
+            f = d.fbuf.as<Real>();
+        } else {
+            f = d.noisy.as<Real>();
+        }
+        CU_TRY(cudaEventRecord(d.ev[1], st));
+        double alpha_s; const Real *amap;
+        RC_TRY(prepare_lambda<Real>(d, lam, lm, ln, M, N, st, &alpha_s, &amap));
+        const Real *u = nullptr; int used = 0;
+        RC_TRY(run_pdps<Real>(d, f, M, N, oc, alpha_s, amap, o, st, &u, &used));
+        ctx->stats.pdps_kernel_used = used;
+        CU_TRY(cudaEventRecord(d.ev[2], st));
+        if (oc > 0) RC_TRY(download_stack<Real>(d, u, plane * oc, u_out + plane * ob, st));
+        CU_TRY(cudaEventRecord(d.ev[3], st));
+    }
+    for (int di = 0; di < ndev; ++di) {
+        Dev &d = ctx->devs[di];
+        CU_TRY(cudaSetDevice(d.id));
+        CU_TRY(cudaStreamSynchronize(d.stream));
+        ctx->stats.ms_upload = std::max<double>(ctx->stats.ms_upload, ev_ms(d.ev[0], d.ev[1]));
+        ctx->stats.ms_pdps = std::max<double>(ctx->stats.ms_pdps, ev_ms(d.ev[1], d.ev[2]));
+        ctx->stats.ms_download = std::max<double>(ctx->stats.ms_download, ev_ms(d.ev[2], d.ev[3]));
+        ctx->stats.ms_total = std::max<double>(ctx->stats.ms_total, ev_ms(d.ev[0], d.ev[3]));
+        ctx->stats.kernel_launches += d.launches;
+    }
+    ctx->stats.pdps_iterations = o.maxiter;
+    ctx->stats.pixel_iterations = (long long)plane * O * o.maxiter;
+    ctx->stats.n_devices = ndev;
+    return 0;
+}
+
+template <typename Real>
+static int set_dataset_impl(bpltv_ctx *ctx, const double *truth, const double *noisy, int M, int N, int O)
+{
+    const int ndev = (int)ctx->devs.size();
+    const size_t plane = (size_t)M * N;
+    for (int di = 0; di < ndev; ++di) {
+        Dev &d = ctx->devs[di];
+        CU_TRY(cudaSetDevice(d.id));
+        int ob, oc;
+        shard_range(O, ndev, di, ob, oc);
+        d.M = M; d.N = N; d.O = oc; d.o_begin = ob;
+        RC_TRY(upload_stack<Real>(d, truth + plane * ob, plane * oc, d.truth, d.stream));
+        RC_TRY(upload_stack<Real>(d, noisy + plane * ob, plane * oc, d.noisy, d.stream));
+    }
+    for (int di = 0; di < ndev; ++di) {
+        CU_TRY(cudaSetDevice(ctx->devs[di].id));
+        CU_TRY(cudaStreamSynchronize(ctx->devs[di].stream));
+    }
+    ctx->M = M; ctx->N = N; ctx->O = O; ctx->have_dataset = true;
+    return 0;
+}
+
+// Enqueue one evaluation on one device: u = denoise; scalars[0] = cost;
+// scalars[1..] = gradient.  Everything asynchronous on `st`.
+template <typename Real>
+static int eval_on_device(bpltv_ctx *ctx, Dev &d, const double *lam, int lm, int ln, double Delta,
+                          const bpltv_eval_opts &eo, cudaStream_t st, const Real **u_res, double *d_costgrad)
+{
+    const int M = d.M, N = d.N, O = d.O;
+    const size_t n = (size_t)M * N * O;
+    const int ng = lm * ln;
+    CU_TRY(cudaEventRecord(d.ev[0], st));
+    double alpha_s; const Real *amap;
+    RC_TRY(prepare_lambda<Real>(d, lam, lm, ln, M, N, st, &alpha_s, &amap));
+    const Real *u = nullptr; int used = 0;
+    RC_TRY(run_pdps<Real>(d, d.noisy.as<Real>(), M, N, O, alpha_s, amap, eo.pdps, st, &u, &used));
+    ctx->stats.pdps_kernel_used = used;
+    CU_TRY(cudaEventRecord(d.ev[1], st));
+    CU_TRY(cudaMemsetAsync(d_costgrad, 0, (1 + ng) * sizeof(double), st));
+    if (O > 0) RC_TRY(run_cost<Real>(d, u, d.truth.as<Real>(), n, d_costgrad, st));
+    CU_TRY(cudaEventRecord(d.ev[2], st));
+    if (O > 0 && eo.force_branch != 3) {
+        const bool reg = eo.force_branch == 2 || (eo.force_branch == 0 && !(Delta > eo.delta_t));
+        GradProblem<Real> gp;
+        gp.u = u; gp.ubar = d.truth.as<Real>(); gp.M = M; gp.N = N; gp.O = O;
+        gp.alpha_s = alpha_s; gp.alpha_map = amap; gp.lm = lm; gp.ln = ln; gp.regularised = reg;
+        gp.gamma = eo.gamma; gp.act_tol = eo.act_tol;
+        gp.eps_act = eo.eps_act > 0 ? eo.eps_act : (ng == 1 ? 2.220446049250313e-16 : 1.4901161193847656e-08);
+        gp.tol = eo.solver_tol; gp.maxit = eo.solver_maxit; gp.solver = eo.solver;
+        int rc = run_gradient<Real>(d.grad, gp, d.sm_count, d.smem_optin, st, d_costgrad + 1, &d.launches);
+        if (rc != 0) return fail(rc, "gradient: %s", d.grad.err.c_str());
+    }
+    CU_TRY(cudaEventRecord(d.ev[3], st));
+    *u_res = u;
+    return 0;
+}
+
+template <typename Real>
+static int learn_eval_impl(bpltv_ctx *ctx, const double *lam, int lm, int ln, double Delta,
+                           const bpltv_eval_opts &eo, double *u_out, double *cost_out, double *grad_out)
+{
+    const int ndev = (int)ctx->devs.size();
+    const int ng = lm * ln;
+    const size_t plane = (size_t)ctx->M * ctx->N;
+    std::memset(&ctx->stats, 0, sizeof ctx->stats);
+    std::vector<std::vector<double>> host(ndev, std::vector<double>(1 + ng, 0.0));
+    for (int di = 0; di < ndev; ++di) {
+        Dev &d = ctx->devs[di];
+        CU_TRY(cudaSetDevice(d.id));
+        d.launches = 0;
+        RC_TRY(d.scalars.ensure((1 + ng) * sizeof(double)));
+        const Real *u = nullptr;
+        RC_TRY(eval_on_device<Real>(ctx, d, lam, lm, ln, Delta, eo, d.stream, &u, d.scalars.as<double>()));
+        CU_TRY(cudaMemcpyAsync(host[di].data(), d.scalars.p, (1 + ng) * sizeof(double), cudaMemcpyDeviceToHost,
+                               d.stream));
+        if (u_out && d.O > 0) RC_TRY(download_stack<Real>(d, u, plane * d.O, u_out + plane * d.o_begin, d.stream));
+        CU_TRY(cudaEventRecord(d.ev[4], d.stream));
+    }
+    double cost = 0.0;
+    std::vector<double> grad(ng, 0.0);
+    for (int di = 0; di < ndev; ++di) {  // fixed device order: deterministic sum
+        Dev &d = ctx->devs[di];
+        CU_TRY(cudaSetDevice(d.id));
+        CU_TRY(cudaStreamSynchronize(d.stream));
+        cost += host[di][0];
+        for (int k = 0; k < ng; ++k) grad[k] += host[di][1 + k];
+        ctx->stats.ms_pdps = std::max<double>(ctx->stats.ms_pdps, ev_ms(d.ev[0], d.ev[1]));
+        ctx->stats.ms_cost = std::max<double>(ctx->stats.ms_cost, ev_ms(d.ev[1], d.ev[2]));
+        ctx->stats.ms_gradient = std::max<double>(ctx->stats.ms_gradient, ev_ms(d.ev[2], d.ev[3]));
+        ctx->stats.ms_download = std::max<double>(ctx->stats.ms_download, ev_ms(d.ev[3], d.ev[4]));
+        ctx->stats.ms_total = std::max<double>(ctx->stats.ms_total, ev_ms(d.ev[0], d.ev[4]));
+        ctx->stats.kernel_launches += d.launches;
+        ctx->stats.solver_iterations += d.grad.last_iterations;
+        ctx->stats.solver_max_relres = std::max(ctx->stats.solver_max_relres, d.grad.last_relres);
+    }
+    ctx->stats.pdps_iterations = eo.pdps.maxiter;
+    ctx->stats.pixel_iterations = (long long)plane * ctx->O * eo.pdps.maxiter;
+    ctx->stats.n_devices = ndev;
+    if (!std::isfinite(cost)) return fail(BPLTV_ERR_NUMERIC, "non-finite cost");
+    for (int k = 0; k < ng; ++k)
+        if (!std::isfinite(grad[k])) return fail(BPLTV_ERR_NUMERIC, "non-finite gradient entry %d", k);
+    *cost_out = cost;
+    for (int k = 0; k < ng; ++k) grad_out[k] = grad[k];
+    return 0;
+}
+
+template <typename Real>
+static int gradient_impl(bpltv_ctx *ctx, const double *u_host, const double *lam, int lm, int ln, int regularised,
+                         const bpltv_eval_opts &eo, double *grad_out)
+{
+    const int ndev = (int)ctx->devs.size();
+    const int ng = lm * ln;
+    const size_t plane = (size_t)ctx->M * ctx->N;
+    std::memset(&ctx->stats, 0, sizeof ctx->stats);
+    std::vector<std::vector<double>> host(ndev, std::vector<double>(ng, 0.0));
+    for (int di = 0; di < ndev; ++di) {
+        Dev &d = ctx->devs[di];
+        CU_TRY(cudaSetDevice(d.id));
+        d.launches = 0;
+        if (d.O == 0) continue;
+        cudaStream_t st = d.stream;
+        RC_TRY(d.scalars.ensure((1 + ng) * sizeof(double)));
+        RC_TRY(upload_stack<Real>(d, u_host + plane * d.o_begin, plane * d.O, d.ubuf, st));
+        double alpha_s; const Real *amap;
+        RC_TRY(prepare_lambda<Real>(d, lam, lm, ln, d.M, d.N, st, &alpha_s, &amap));
+        CU_TRY(cudaEventRecord(d.ev[2], st));
+        GradProblem<Real> gp;
+        gp.u = d.ubuf.as<Real>(); gp.ubar = d.truth.as<Real>(); gp.M = d.M; gp.N = d.N; gp.O = d.O;
+        gp.alpha_s = alpha_s; gp.alpha_map = amap; gp.lm = lm; gp.ln = ln; gp.regularised = regularised != 0;
+        gp.gamma = eo.gamma; gp.act_tol = eo.act_tol;
+        gp.eps_act = eo.eps_act > 0 ? eo.eps_act : (ng == 1 ? 2.220446049250313e-16 : 1.4901161193847656e-08);
+        gp.tol = eo.solver_tol; gp.maxit = eo.solver_maxit; gp.solver = eo.solver;
+        CU_TRY(cudaMemsetAsync(d.scalars.p, 0, (1 + ng) * sizeof(double), st));
+        int rc = run_gradient<Real>(d.grad, gp, d.sm_count, d.smem_optin, st, d.scalars.as<double>() + 1, &d.launches);
+        if (rc != 0) return fail(rc, "gradient: %s", d.grad.err.c_str());
+        CU_TRY(cudaEventRecord(d.ev[3], st));
+        CU_TRY(cudaMemcpyAsync(host[di].data(), d.scalars.as<double>() + 1, ng * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    std::vector<double> grad(ng, 0.0);
+    for (int di = 0; di < ndev; ++di) {
+        Dev &d = ctx->devs[di];
+        if (d.O == 0) continue;
+        CU_TRY(cudaSetDevice(d.id));
+        CU_TRY(cudaStreamSynchronize(d.stream));
+        for (int k = 0; k < ng; ++k) grad[k] += host[di][k];
+        ctx->stats.ms_gradient = std::max<double>(ctx->stats.ms_gradient, ev_ms(d.ev[2], d.ev[3]));
+        ctx->stats.kernel_launches += d.launches;
+        ctx->stats.solver_iterations += d.grad.last_iterations;
+        ctx->stats.solver_max_relres = std::max(ctx->stats.solver_max_relres, d.grad.last_relres);
+    }
+    ctx->stats.n_devices = ndev;
+    for (int k = 0; k < ng; ++k) {
+        if (!std::isfinite(grad[k])) return fail(BPLTV_ERR_NUMERIC, "non-finite gradient entry %d", k);
+        grad_out[k] = grad[k];
+    }
+    return 0;
+}
+
+template <typename Real>
+static int denoise_device_impl(bpltv_ctx *ctx, const void *d_noisy, int M, int N, int O, const double *lam, int lm,
+                               int ln, const bpltv_pdps_opts &o, void *d_u_out, cudaStream_t st)
+{
+    Dev &d = ctx->devs[0];
+    CU_TRY(cudaSetDevice(d.id));
+    d.launches = 0;
+    double alpha_s; const Real *amap;
+    RC_TRY(prepare_lambda<Real>(d, lam, lm, ln, M, N, st, &alpha_s, &amap));
+    const Real *u = nullptr; int used = 0;
+    RC_TRY(run_pdps<Real>(d, static_cast<const Real *>(d_noisy), M, N, O, alpha_s, amap, o, st, &u, &used));
+    if (O > 0)
+        CU_TRY(cudaMemcpyAsync(d_u_out, u, (size_t)M * N * O * sizeof(Real), cudaMemcpyDeviceToDevice, st));
+    std::memset(&ctx->stats, 0, sizeof ctx->stats);
+    ctx->stats.pdps_kernel_used = used;
+    ctx->stats.kernel_launches = d.launches;
+    ctx->stats.pdps_iterations = o.maxiter;
+    ctx->stats.pixel_iterations = (long long)M * N * O * o.maxiter;
+    ctx->stats.n_devices = 1;
+    return 0;
+}
+
+template <typename Real>
+static int learn_eval_device_impl(bpltv_ctx *ctx, const double *lam, int lm, int ln, double Delta,
+                                  const bpltv_eval_opts &eo, void *d_u_out, double *d_costgrad, cudaStream_t st)
+{
+    Dev &d = ctx->devs[0];
+    CU_TRY(cudaSetDevice(d.id));
+    d.launches = 0;
+    std::memset(&ctx->stats, 0, sizeof ctx->stats);
+    const Real *u = nullptr;
+    RC_TRY(eval_on_device<Real>(ctx, d, lam, lm, ln, Delta, eo, st, &u, d_costgrad));
+    if (d_u_out && d.O > 0)
+        CU_TRY(cudaMemcpyAsync(d_u_out, u, (size_t)d.M * d.N * d.O * sizeof(Real), cudaMemcpyDeviceToDevice, st));
+    ctx->stats.kernel_launches = d.launches;
+    ctx->stats.pdps_iterations = eo.pdps.maxiter;
+    ctx->stats.pixel_iterations = (long long)d.M * d.N * d.O * eo.pdps.maxiter;
+    ctx->stats.n_devices = 1;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// C entry points
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int bpltv_version(void) { return BPLTV_VERSION; }
+
+const char *bpltv_last_error(void) { return g_last_error.c_str(); }
+
+void bpltv_default_pdps_opts(bpltv_pdps_opts *o)
+{
+    if (!o) return;
+    std::memset(o, 0, sizeof *o);
+    o->tau0 = 5.0;           // /root/reference/src/TVLearningFunctionVec.jl:36
+    o->sigma0 = 0.99 / 5;    // :37
+    o->rho = 0.0;            // :34
+    o->opnorm = std::sqrt(8.0);
+    o->accel = 1;            // :38
+    o->maxiter = 5000;       // :40
+    o->init_mode = 0;
+    o->arith = BPLTV_ARITH_STRICT;
+    o->kernel = BPLTV_KERNEL_AUTO;
+    o->tblock = 0;
+}
+
+void bpltv_default_eval_opts(bpltv_eval_opts *o)
+{
+    if (!o) return;
+    std::memset(o, 0, sizeof *o);
+    bpltv_default_pdps_opts(&o->pdps);
+    o->delta_t = 1e-6;   // :14
+    o->gamma = 1e8;      // :142, :197
+    o->act_tol = 1e-12;  // :109, :231
+    o->eps_act = 0.0;    // → eps() scalar (:128) / sqrt(eps()) patch (:245)
+    o->solver_tol = 1e-13;
+    o->solver_maxit = 400000;
+    o->solver = 0;
+    o->force_branch = 0;
+}
+
+int bpltv_create(const int *device_ids, int ndev, int precision, bpltv_ctx **out)
+{
+    if (!out) return fail(BPLTV_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (precision != 64 && precision != 32) return fail(BPLTV_ERR_ARG, "precision must be 64 or 32");
+    if (ndev < 1) return fail(BPLTV_ERR_ARG, "ndev must be >= 1");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count < 1) {
+        cudaGetLastError();
+        return fail(BPLTV_ERR_NODEVICE, "no CUDA device (%s); libbpltv has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    bpltv_ctx *ctx = new bpltv_ctx();
+    ctx->prec = precision;
+    std::memset(&ctx->stats, 0, sizeof ctx->stats);
+    ctx->devs.resize(ndev);
+    for (int k = 0; k < ndev; ++k) {
+        Dev &d = ctx->devs[k];
+        d.id = device_ids ? device_ids[k] : k;
+        if (d.id < 0 || d.id >= count) {
+            delete ctx;
+            return fail(BPLTV_ERR_ARG, "device id %d out of range (have %d devices)", d.id, count);
+        }
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, d.id) != cudaSuccess || prop.major != 10) {
+            cudaGetLastError();
+            int major = prop.major, minor = prop.minor;
+            delete ctx;
+            return fail(BPLTV_ERR_NODEVICE, "device %d is sm_%d%d; libbpltv is built for sm_100a only", d.id, major, minor);
+        }
+        d.sm_count = prop.multiProcessorCount;
+        d.smem_optin = prop.sharedMemPerBlockOptin;
+        if (cudaSetDevice(d.id) != cudaSuccess || cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess) {
+            cudaGetLastError();
+            delete ctx;
+            return fail(BPLTV_ERR_CUDA, "cannot create stream on device %d", d.id);
+        }
+        for (auto &ev : d.ev) cudaEventCreate(&ev);
+    }
+    *out = ctx;
+    return 0;
+}
+
+int bpltv_destroy(bpltv_ctx *ctx)
+{
+    if (!ctx) return 0;
+    for (Dev &d : ctx->devs) {
+        cudaSetDevice(d.id);
+        if (d.stream) cudaStreamSynchronize(d.stream);
+        DBuf *bufs[] = {&d.truth, &d.noisy, &d.x[0], &d.x[1], &d.y1[0], &d.y1[1], &d.y2[0], &d.y2[1], &d.fbuf,
+                        &d.amap, &d.steps, &d.partials, &d.scalars, &d.stage, &d.lam_dev, &d.ubuf};
+        for (DBuf *b : bufs) b->release();
+        d.grad.release();
+        for (auto &ev : d.ev) if (ev) cudaEventDestroy(ev);
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
+    delete ctx;
+    return 0;
+}
+
+static int check_shape(int M, int N, int O)
+{
+    if (M < 1 || N < 1 || O < 0) return fail(BPLTV_ERR_ARG, "bad stack shape %dx%dx%d", M, N, O);
+    if ((double)M * N * std::max(O, 1) > 4.0e9) return fail(BPLTV_ERR_ARG, "stack too large");
+    return 0;
+}
+
+int bpltv_set_dataset(bpltv_ctx *ctx, const double *truth, const double *noisy, int M, int N, int O)
+{
+    if (!ctx || !truth || !noisy) return fail(BPLTV_ERR_ARG, "NULL argument");
+    RC_TRY(check_shape(M, N, O));
+    return ctx->prec == 64 ? set_dataset_impl<double>(ctx, truth, noisy, M, N, O)
+                           : set_dataset_impl<float>(ctx, truth, noisy, M, N, O);
+}
+
+int bpltv_denoise(bpltv_ctx *ctx, const double *noisy, int M, int N, int O, const double *lam, int lm, int ln,
+                  const bpltv_pdps_opts *opts, double *u_out)
+{
+    if (!ctx || !u_out) return fail(BPLTV_ERR_ARG, "NULL argument");
+    RC_TRY(check_shape(M, N, O));
+    RC_TRY(check_lambda(lam, lm, ln));
+    bpltv_pdps_opts o;
+    if (opts) o = *opts; else bpltv_default_pdps_opts(&o);
+    RC_TRY(check_pdps_opts(o));
+    if (!noisy) {
+        if (!ctx->have_dataset) return fail(BPLTV_ERR_STATE, "denoise(noisy=NULL) needs bpltv_set_dataset first");
+        if (M != ctx->M || N != ctx->N || O != ctx->O)
+            return fail(BPLTV_ERR_ARG, "shape %dx%dx%d does not match the resident dataset %dx%dx%d", M, N, O, ctx->M,
+                        ctx->N, ctx->O);
+    }
+    return ctx->prec == 64 ? denoise_impl<double>(ctx, noisy, M, N, O, lam, lm, ln, o, u_out)
+                           : denoise_impl<float>(ctx, noisy, M, N, O, lam, lm, ln, o, u_out);
+}
+
+static int check_eval(bpltv_ctx *ctx, const double *lam, int lm, int ln, const bpltv_eval_opts *opts,
+                      bpltv_eval_opts &eo)
+{
+    if (!ctx) return fail(BPLTV_ERR_ARG, "NULL context");
+    if (!ctx->have_dataset) return fail(BPLTV_ERR_STATE, "no resident dataset: call bpltv_set_dataset first");
+    RC_TRY(check_lambda(lam, lm, ln));
+    if (opts) eo = *opts; else bpltv_default_eval_opts(&eo);
+    RC_TRY(check_pdps_opts(eo.pdps));
+    if (ctx->M != ctx->N)
+        return fail(BPLTV_ERR_ARG, "the gradient assumes square images like the reference "
+                                   "(TVLearningFunctionVec.jl:102); got %dx%d", ctx->M, ctx->N);
+    if (lm > ctx->M || ln > ctx->N) return fail(BPLTV_ERR_ARG, "lambda grid larger than the image");
+    for (int k = 0; k < lm * ln; ++k)
+        if (!(lam[k] > 0.0)) return fail(BPLTV_ERR_ARG, "lambda[%d] must be > 0 for the gradient", k);
+    if (!(eo.gamma > 0) || !(eo.act_tol >= 0)) return fail(BPLTV_ERR_ARG, "bad gamma / act_tol");
+    return 0;
+}
+
+int bpltv_learn_eval(bpltv_ctx *ctx, const double *lam, int lm, int ln, double Delta, const bpltv_eval_opts *opts,
+                     double *u_out, double *cost_out, double *grad_out)
+{
+    bpltv_eval_opts eo;
+    RC_TRY(check_eval(ctx, lam, lm, ln, opts, eo));
+    if (!cost_out || !grad_out) return fail(BPLTV_ERR_ARG, "NULL output");
+    return ctx->prec == 64 ? learn_eval_impl<double>(ctx, lam, lm, ln, Delta, eo, u_out, cost_out, grad_out)
+                           : learn_eval_impl<float>(ctx, lam, lm, ln, Delta, eo, u_out, cost_out, grad_out);
+}
+
+int bpltv_gradient(bpltv_ctx *ctx, const double *u, const double *lam, int lm, int ln, int regularised,
+                   const bpltv_eval_opts *opts, double *grad_out)
+{
+    bpltv_eval_opts eo;
+    RC_TRY(check_eval(ctx, lam, lm, ln, opts, eo));
+    if (!u || !grad_out) return fail(BPLTV_ERR_ARG, "NULL argument");
+    return ctx->prec == 64 ? gradient_impl<double>(ctx, u, lam, lm, ln, regularised, eo, grad_out)
+                           : gradient_impl<float>(ctx, u, lam, lm, ln, regularised, eo, grad_out);
+}
+
+// ---- device-resident variants (single device) --------------------------------
+static int single_dev(bpltv_ctx *ctx)
+{
+    if (!ctx) return fail(BPLTV_ERR_ARG, "NULL context");
+    if (ctx->devs.size() != 1) return fail(BPLTV_ERR_ARG, "device-pointer entry points need a single-device context");
+    return 0;
+}
+
+
+int bpltv_denoise_device(bpltv_ctx *ctx, const void *d_noisy, int M, int N, int O, const double *lam, int lm, int ln,
+                         const bpltv_pdps_opts *opts, void *d_u_out, void *stream)
+{
+    RC_TRY(single_dev(ctx));
+    if (!d_noisy || !d_u_out) return fail(BPLTV_ERR_ARG, "NULL device pointer");
+    RC_TRY(check_shape(M, N, O));
+    RC_TRY(check_lambda(lam, lm, ln));
+    bpltv_pdps_opts o;
+    if (opts) o = *opts; else bpltv_default_pdps_opts(&o);
+    RC_TRY(check_pdps_opts(o));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->devs[0].stream;
+    return ctx->prec == 64 ? denoise_device_impl<double>(ctx, d_noisy, M, N, O, lam, lm, ln, o, d_u_out, st)
+                           : denoise_device_impl<float>(ctx, d_noisy, M, N, O, lam, lm, ln, o, d_u_out, st);
+}
+
+int bpltv_set_dataset_device(bpltv_ctx *ctx, const void *d_truth, const void *d_noisy, int M, int N, int O,
+                             void *stream)
+{
+    RC_TRY(single_dev(ctx));
+    if (!d_truth || !d_noisy) return fail(BPLTV_ERR_ARG, "NULL device pointer");
+    RC_TRY(check_shape(M, N, O));
+    Dev &d = ctx->devs[0];
+    CU_TRY(cudaSetDevice(d.id));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : d.stream;
+    const size_t bytes = (size_t)M * N * O * (ctx->prec == 64 ? 8 : 4);
+    RC_TRY(d.truth.ensure(std::max<size_t>(bytes, 8)));
+    RC_TRY(d.noisy.ensure(std::max<size_t>(bytes, 8)));
+    if (bytes) {
+        CU_TRY(cudaMemcpyAsync(d.truth.p, d_truth, bytes, cudaMemcpyDeviceToDevice, st));
+        CU_TRY(cudaMemcpyAsync(d.noisy.p, d_noisy, bytes, cudaMemcpyDeviceToDevice, st));
+    }
+    d.M = M; d.N = N; d.O = O; d.o_begin = 0;
+    ctx->M = M; ctx->N = N; ctx->O = O; ctx->have_dataset = true;
+    return 0;
+}
+
+
+int bpltv_learn_eval_device(bpltv_ctx *ctx, const double *lam, int lm, int ln, double Delta,
+                            const bpltv_eval_opts *opts, void *d_u_out, double *d_costgrad, void *stream)
+{
+    RC_TRY(single_dev(ctx));
+    bpltv_eval_opts eo;
+    RC_TRY(check_eval(ctx, lam, lm, ln, opts, eo));
+    if (!d_costgrad) return fail(BPLTV_ERR_ARG, "NULL d_costgrad");
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->devs[0].stream;
+    return ctx->prec == 64 ? learn_eval_device_impl<double>(ctx, lam, lm, ln, Delta, eo, d_u_out, d_costgrad, st)
+                           : learn_eval_device_impl<float>(ctx, lam, lm, ln, Delta, eo, d_u_out, d_costgrad, st);
+}
+
+int bpltv_get_stats(bpltv_ctx *ctx, bpltv_stats *out)
+{
+    if (!ctx || !out) return fail(BPLTV_ERR_ARG, "NULL argument");
+    *out = ctx->stats;
+    return 0;
+}
+
+}  // extern "C"

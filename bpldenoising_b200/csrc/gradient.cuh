@@ -1,0 +1,762 @@
+// gradient.cuh — adjoint solve and λ-gradient on the GPU (fp64).
+//
+// Replaces gradient / gradient_reg of /root/reference/src/TVLearningFunctionVec.jl
+// (:98-135, :137-161, :192-215, :219-254), which assemble an explicit sparse
+// (3n²)² or (n²)² matrix per image and call a sparse LU (`\`).
+//
+// Formulation.  After eliminating the multipliers every variant is
+//       (C + Gᵀ D G) p = r ,   grad = ± Σ ⟨(Gp), w⟩ (pixel) or Σ p·(Gᵀw) (node)
+// with C diagonal and D block diagonal, D_q = s·I ("iso": flat pixel, s = 1/eps or
+// αγ) or s·t tᵀ with t ⟂ ∇u ("aniso", s = α/|∇u|).  The penalty form has entries up
+// to 4.5e15 and is unusable in fp64, so we factor the equivalent
+// SPD system in multiplier space instead,
+//       (diag(E) + B C⁻¹ Bᵀ) ζ = B C⁻¹ r ,   p = C⁻¹ (r − Bᵀ ζ),   E = 1/s,
+// one unknown per aniso pixel (mode t) and two per iso pixel (modes e₁, e₂).  All its
+// entries are O(1); numbering the modes in pixel order makes it banded with
+// half-bandwidth ≤ 2n+1, and a blocked right-looking banded Cholesky with a pivot
+// floor (redundant constraints of flat regions give pivots ≈ eps) followed by one
+// step of iterative refinement reproduces the refined literal solve
+// (oracle/oracle.py: gradient_dual is the same algorithm on the CPU).
+//
+// Mapping: one CTA per image "slot"; images are processed in waves of ≤ #SM slots.
+#pragma once
+#include <string>
+
+#include "common.cuh"
+
+namespace bpltv {
+
+constexpr int GRAD_NB = 16;        // Cholesky block size
+constexpr int GRAD_THREADS = 512;  // CTA size of the per-image kernels
+
+struct GradSlots {
+    // per-slot strides (elements)
+    int N;          // pixels per image
+    int n;          // image side
+    int LD;         // allocated leading dimension of the band (≥ 2n+2+NB)
+    int NdMax;      // 2N
+    int nblkMax;    // NdMax/NB + 1
+    // base pointers of slot 0; slot s adds s*stride
+    double *pix;    // 10 pixel arrays of N doubles: ea eb E w1 w2 cinv rc p q fpix
+    double *mode;   // 3 mode arrays of NdMax doubles: b zeta work
+    double *sinv;   // nblkMax * NB*NB
+    double *ab;     // NdMax * LD
+    int *off;       // N+1
+    int *ext;       // NdMax
+    int *info;      // 4 ints per slot: Nd, LDa (actual band + NB + 1), guarded pivots, spare
+    size_t pix_stride, mode_stride, sinv_stride, ab_stride, off_stride, ext_stride;
+};
+
+struct GradVariant {
+    int regularised;   // 1: gradient_reg, 0: gradient
+    int patch;         // λ is a map
+    int lm, ln;
+    double alpha_s, gamma, act_tol, eps_act, guard_rel;
+    int refine;
+};
+
+template <typename T>
+static __device__ __forceinline__ T *slot_ptr(T *base, size_t stride, int slot) { return base + stride * slot; }
+
+// ---------------------------------------------------------------------------
+// K1: per-pixel classification + exclusive scan of the mode counts.
+// ---------------------------------------------------------------------------
+template <typename Real>
+__global__ void __launch_bounds__(GRAD_THREADS) grad_classify_kernel(GradSlots ws, GradVariant gv, const Real *u_all,
+                                                                     const Real *ubar_all, const Real *alpha_map,
+                                                                     int img0)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_total;
+    const int slot = blockIdx.x;
+    const int n = ws.n, N = ws.N;
+    const Real *u = u_all + (size_t)(img0 + slot) * N;
+    const Real *ub = ubar_all + (size_t)(img0 + slot) * N;
+    double *pix = slot_ptr(ws.pix, ws.pix_stride, slot);
+    double *ea = pix, *eb = pix + N, *E = pix + 2 * (size_t)N, *w1 = pix + 3 * (size_t)N, *w2 = pix + 4 * (size_t)N,
+           *cinv = pix + 5 * (size_t)N, *rc = pix + 6 * (size_t)N;
+    int *off = slot_ptr(ws.off, ws.off_stride, slot);
+    int *ext = slot_ptr(ws.ext, ws.ext_stride, slot);
+    int *info = ws.info + 4 * slot;
+
+    // each thread owns a contiguous run of pixels so the scan is a two-level one
+    const int per = (N + blockDim.x - 1) / blockDim.x;
+    const int q0 = threadIdx.x * per, q1 = min(N, q0 + per);
+    int cnt = 0;
+    for (int q = q0; q < q1; ++q) {
+        const int i = q % n, j = q / n;
+        const double uq = (double)u[q];
+        const double g1 = (i + 1 < n) ? (double)u[q + 1] - uq : 0.0;
+        const double g2 = (j + 1 < n) ? (double)u[q + n] - uq : 0.0;
+        const double nrm = sqrt(g1 * g1 + g2 * g2);
+        const double a = gv.patch ? (double)alpha_map[q] : gv.alpha_s;
+        bool iso;
+        double e, c, r, v1, v2;
+        if (gv.regularised) {
+            // act = max(0,|Gu|-1/γ) != 0  (:146-147, :201-202); iso = !act
+            iso = !(fmax(0.0, nrm - 1.0 / gv.gamma) != 0.0);
+            if (iso) { v1 = gv.gamma * g1; v2 = gv.gamma * g2; }
+            else { v1 = g1 / nrm; v2 = g2 / nrm; }
+            r = (double)ub[q] - uq;                     // ū - u (:157, :212)
+            if (gv.patch) { c = a; e = iso ? 1.0 / gv.gamma : nrm; }
+            else { c = 1.0; e = iso ? 1.0 / (a * gv.gamma) : nrm / a; }
+        } else {
+            iso = nrm < gv.act_tol;                     // (:109, :231)
+            if (iso) { v1 = 0.0; v2 = 0.0; }
+            else { v1 = g1 / nrm; v2 = g2 / nrm; }
+            r = uq - (double)ub[q];                     // u - ū (:130, :247)
+            c = 1.0;
+            e = iso ? gv.eps_act : nrm / a;
+        }
+        ea[q] = iso ? 1.0 : -g2 / nrm;
+        eb[q] = iso ? 0.0 : g1 / nrm;
+        E[q] = e; w1[q] = v1; w2[q] = v2; cinv[q] = c; rc[q] = r;
+        off[q] = iso ? 2 : 1;  // count for now
+        cnt += iso ? 2 : 1;
+    }
+    // block exclusive scan of cnt
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        int v = lane < nw ? s_warp[lane] : 0, iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, iv, o);
+            if (lane >= o) iv += t;
+        }
+        s_warp[lane] = iv - v;  // exclusive warp offsets
+        if (lane == 31) s_total = iv;
+    }
+    __syncthreads();
+    int run = s_warp[warp] + incl - cnt;
+    for (int q = q0; q < q1; ++q) {
+        const int c = off[q];
+        off[q] = run;
+        run += c;
+    }
+    if (threadIdx.x == 0) { off[N] = s_total; info[0] = s_total; info[2] = 0; }
+    __syncthreads();
+    // envelope: last mode coupled to the modes of pixel q = last mode of pixel min(q+n, N-1)
+    int bwmax = 0;
+    for (int q = threadIdx.x; q < N; q += blockDim.x) {
+        const int qq = min(q + n, N - 1);
+        const int last = off[qq + 1] - 1;
+        for (int a = off[q]; a < off[q + 1]; ++a) {
+            ext[a] = last;
+            bwmax = max(bwmax, last - a);
+        }
+    }
+    bwmax = max(bwmax, __shfl_xor_sync(0xffffffffu, bwmax, 16));
+    bwmax = max(bwmax, __shfl_xor_sync(0xffffffffu, bwmax, 8));
+    bwmax = max(bwmax, __shfl_xor_sync(0xffffffffu, bwmax, 4));
+    bwmax = max(bwmax, __shfl_xor_sync(0xffffffffu, bwmax, 2));
+    bwmax = max(bwmax, __shfl_xor_sync(0xffffffffu, bwmax, 1));
+    __syncthreads();
+    if (lane == 0) s_warp[warp] = bwmax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int m = 0;
+        for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) m = max(m, s_warp[w]);
+        info[1] = min(ws.LD, m + 1 + GRAD_NB);  // actual leading dimension used by this slot
+    }
+}
+
+// node coefficients of a mode (pixel (i,j), vector (e1,e2)): β0 at q, β1 at q+1, β2 at q+n
+static __device__ __forceinline__ void mode_beta(int i, int j, int n, double e1, double e2, double &b0, double &b1,
+                                                 double &b2)
+{
+    b1 = (i + 1 < n) ? e1 : 0.0;
+    b2 = (j + 1 < n) ? e2 : 0.0;
+    b0 = -(b1 + b2);
+}
+
+// mode m (0/1) of pixel q: vector and compliance
+static __device__ __forceinline__ void mode_vec(const double *ea, const double *eb, int q, int m, bool iso, double &e1,
+                                                double &e2)
+{
+    if (iso) { e1 = m == 0 ? 1.0 : 0.0; e2 = m == 0 ? 0.0 : 1.0; }
+    else { e1 = ea[q]; e2 = eb[q]; }
+}
+
+// ---------------------------------------------------------------------------
+// K2: zero the used part of the band, scatter diag(E) + B C⁻¹ Bᵀ (lower band) and
+// the right-hand side b = B C⁻¹ r.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(GRAD_THREADS) grad_assemble_kernel(GradSlots ws)
+{
+    const int slot = blockIdx.x;
+    const int n = ws.n, N = ws.N;
+    const double *pix = slot_ptr(ws.pix, ws.pix_stride, slot);
+    const double *ea = pix, *eb = pix + N, *E = pix + 2 * (size_t)N, *cinv = pix + 5 * (size_t)N,
+                 *rc = pix + 6 * (size_t)N;
+    const int *off = slot_ptr(ws.off, ws.off_stride, slot);
+    const int *info = ws.info + 4 * slot;
+    const int Nd = info[0], LDa = info[1];
+    double *ab = slot_ptr(ws.ab, ws.ab_stride, slot);
+    double *bvec = slot_ptr(ws.mode, ws.mode_stride, slot);
+
+    const size_t total = (size_t)Nd * LDa;
+    {   // vectorised zero fill (ab is 16-byte aligned per slot, LDa arbitrary → scalar tail)
+        double2 *ab2 = reinterpret_cast<double2 *>(ab);
+        const size_t n2 = total >> 1;
+        const double2 z2 = make_double2(0.0, 0.0);
+        for (size_t k = threadIdx.x; k < n2; k += blockDim.x) ab2[k] = z2;
+        if (threadIdx.x == 0 && (total & 1)) ab[total - 1] = 0.0;
+    }
+    __syncthreads();
+
+    for (int q = threadIdx.x; q < N; q += blockDim.x) {
+        const int i = q % n, j = q / n;
+        const int a0 = off[q];
+        const int nm = off[q + 1] - a0;
+        const bool iso = nm == 2;
+        const double c0 = cinv[q];
+        const double c1 = (i + 1 < n) ? cinv[q + 1] : 0.0;
+        const double c2 = (j + 1 < n) ? cinv[q + n] : 0.0;
+        const double r0 = rc[q];
+        const double r1 = (i + 1 < n) ? rc[q + 1] : 0.0;
+        const double r2 = (j + 1 < n) ? rc[q + n] : 0.0;
+        for (int m = 0; m < nm; ++m) {
+            const int a = a0 + m;
+            double e1, e2, b0, b1, b2;
+            mode_vec(ea, eb, q, m, iso, e1, e2);
+            mode_beta(i, j, n, e1, e2, b0, b1, b2);
+            double *col = ab + (size_t)a * LDa;
+            col[0] = E[q] + b0 * b0 * c0 + b1 * b1 * c1 + b2 * b2 * c2;
+            bvec[a] = b0 * r0 + b1 * r1 + b2 * r2;
+            if (iso && m == 0) {  // second mode of the same pixel: e = (0,1)
+                double f0, f1, f2;
+                mode_beta(i, j, n, 0.0, 1.0, f0, f1, f2);
+                col[1] = b0 * f0 * c0 + b1 * f1 * c1 + b2 * f2 * c2;
+            }
+            // pixel q+1 = (i+1, j): shared node q+1 (its β0)
+            if (i + 1 < n) {
+                const int qq = q + 1, o0 = off[qq], nn = off[qq + 1] - o0;
+                for (int mm = 0; mm < nn; ++mm) {
+                    double g1, g2, f0, f1, f2;
+                    mode_vec(ea, eb, qq, mm, nn == 2, g1, g2);
+                    mode_beta(i + 1, j, n, g1, g2, f0, f1, f2);
+                    col[o0 + mm - a] = b1 * f0 * c1;
+                }
+            }
+            if (j + 1 < n) {
+                // pixel q+n-1 = (i-1, j+1): shared node q+n (its β1)
+                if (i > 0) {
+                    const int qq = q + n - 1, o0 = off[qq], nn = off[qq + 1] - o0;
+                    for (int mm = 0; mm < nn; ++mm) {
+                        double g1, g2, f0, f1, f2;
+                        mode_vec(ea, eb, qq, mm, nn == 2, g1, g2);
+                        mode_beta(i - 1, j + 1, n, g1, g2, f0, f1, f2);
+                        col[o0 + mm - a] = b2 * f1 * c2;
+                    }
+                }
+                // pixel q+n = (i, j+1): shared node q+n (its β0)
+                {
+                    const int qq = q + n, o0 = off[qq], nn = off[qq + 1] - o0;
+                    for (int mm = 0; mm < nn; ++mm) {
+                        double g1, g2, f0, f1, f2;
+                        mode_vec(ea, eb, qq, mm, nn == 2, g1, g2);
+                        mode_beta(i, j + 1, n, g1, g2, f0, f1, f2);
+                        col[o0 + mm - a] = b2 * f0 * c2;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K3: blocked right-looking banded Cholesky, in place on the band (global memory,
+// the working window of ≤ (2n+2+NB)² /2 entries lives in L1/L2).  Per block of NB
+// columns: (1) warp 0 factors the NB×NB diagonal block in shared memory (pivot
+// floor `guard`) and inverts it; (2) one thread per panel row forms
+// L21 = A21·L11⁻ᵀ; (3) all threads apply the rank-NB update to the trailing
+// envelope in 4×4 register tiles fed from shared memory.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws, double guard)
+{
+    extern __shared__ double sm[];
+    constexpr int NB = GRAD_NB;
+    double *S = sm;               // NB*NB, row-major lower triangle → L11
+    double *Si = sm + NB * NB;    // NB*NB, L11⁻¹
+    double *P = sm + 2 * NB * NB; // NB × PR panel, c-major
+    const int slot = blockIdx.x;
+    int *info = ws.info + 4 * slot;
+    const int Nd = info[0], LDa = info[1];
+    const int PR = (LDa + 3) & ~3;  // rows of P, padded to the 4-row tiles
+    double *ab = slot_ptr(ws.ab, ws.ab_stride, slot);
+    const int *ext = slot_ptr(ws.ext, ws.ext_stride, slot);
+    double *sinv = slot_ptr(ws.sinv, ws.sinv_stride, slot);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    int guarded = 0;
+
+    for (int kb = 0, blk = 0; kb < Nd; kb += NB, ++blk) {
+        const int nb = min(NB, Nd - kb);
+        const int hi = min(Nd - 1, ext[kb + nb - 1]);
+        const int nrows = hi - (kb + nb) + 1;
+        // ---- (1) diagonal block -------------------------------------------------
+        for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
+            const int r = idx / NB, c = idx % NB;
+            double v = (r == c) ? 1.0 : 0.0;
+            if (r < nb && c <= r) v = ab[(size_t)(kb + c) * LDa + (r - c)];
+            S[idx] = v;
+            Si[idx] = 0.0;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            for (int c = 0; c < nb; ++c) {
+                double d = S[c * NB + c];
+                if (!(d > guard)) { d = guard; if (lane == 0) ++guarded; }
+                const double sd = sqrt(d), inv = 1.0 / sd;
+                double l = 0.0;
+                if (lane == c) S[c * NB + c] = sd;
+                if (lane > c && lane < nb) { l = S[lane * NB + c] * inv; S[lane * NB + c] = l; }
+                __syncwarp();
+                if (lane > c && lane < nb)
+                    for (int c2 = c + 1; c2 <= lane; ++c2) S[lane * NB + c2] -= l * S[c2 * NB + c];
+                __syncwarp();
+            }
+            // Si = L11⁻¹: lane = column k of the inverse
+            if (lane < NB) {
+                const int k = lane;
+                double x[NB];
+#pragma unroll
+                for (int r = 0; r < NB; ++r) {
+                    double s = (r == k) ? 1.0 : 0.0;
+#pragma unroll
+                    for (int c = 0; c < NB; ++c)
+                        if (c >= k && c < r) s -= S[r * NB + c] * x[c];
+                    x[r] = (r >= k) ? s / S[r * NB + r] : 0.0;
+                    Si[r * NB + k] = x[r];
+                }
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
+            const int r = idx / NB, c = idx % NB;
+            if (r < nb && c <= r) ab[(size_t)(kb + c) * LDa + (r - c)] = S[idx];
+            sinv[(size_t)blk * NB * NB + idx] = Si[idx];
+        }
+        // ---- (2) panel rows: x = L11⁻¹ a  (row of A21 → row of L21) ---------------
+        for (int r = tid; r < PR; r += blockDim.x) {
+            double x[NB];
+            if (r < nrows) {
+                const int i = kb + nb + r;
+                double a[NB];
+#pragma unroll
+                for (int c = 0; c < NB; ++c) a[c] = (c < nb) ? ab[(size_t)(kb + c) * LDa + (i - kb - c)] : 0.0;
+#pragma unroll
+                for (int c = 0; c < NB; ++c) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int c2 = 0; c2 <= c; ++c2) s += Si[c * NB + c2] * a[c2];
+                    x[c] = s;
+                }
+#pragma unroll
+                for (int c = 0; c < NB; ++c)
+                    if (c < nb) ab[(size_t)(kb + c) * LDa + (i - kb - c)] = x[c];
+            } else {
+#pragma unroll
+                for (int c = 0; c < NB; ++c) x[c] = 0.0;
+            }
+#pragma unroll
+            for (int c = 0; c < NB; ++c) P[c * PR + r] = x[c];
+        }
+        __syncthreads();
+        // ---- (3) trailing update: A22 -= L21 L21ᵀ on the lower envelope ---------
+        const int ntile = (nrows + 3) >> 2;
+        double *a22 = ab + (size_t)(kb + nb) * LDa;  // column (kb+nb+j) at a22 + j*LDa, entry i-j
+        for (int tj = warp; tj < ntile; tj += nwarps) {
+            for (int ti = tj + lane; ti < ntile; ti += 32) {
+                double acc[4][4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) acc[x][y] = 0.0;
+#pragma unroll 4
+                for (int c = 0; c < NB; ++c) {
+                    const double2 pi0 = *reinterpret_cast<const double2 *>(P + c * PR + 4 * ti);
+                    const double2 pi1 = *reinterpret_cast<const double2 *>(P + c * PR + 4 * ti + 2);
+                    const double2 pj0 = *reinterpret_cast<const double2 *>(P + c * PR + 4 * tj);
+                    const double2 pj1 = *reinterpret_cast<const double2 *>(P + c * PR + 4 * tj + 2);
+                    const double pi[4] = {pi0.x, pi0.y, pi1.x, pi1.y};
+                    const double pj[4] = {pj0.x, pj0.y, pj1.x, pj1.y};
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) acc[x][y] = fma(pi[x], pj[y], acc[x][y]);
+                }
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    const int j = 4 * tj + y;
+                    if (j >= nrows) continue;
+                    double *col = a22 + (size_t)j * LDa - j;
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        const int i = 4 * ti + x;
+                        if (i >= j && i < nrows) col[i] -= acc[x][y];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) info[2] = guarded;
+}
+
+// ---------------------------------------------------------------------------
+// Banded triangular solves with the factor (device function, whole CTA).
+// z ← (L Lᵀ)⁻¹ z, using the stored inverses of the diagonal blocks.
+// ---------------------------------------------------------------------------
+static __device__ void band_solve(const double *ab, const double *sinv, const int *ext, int Nd, int LDa, double *z,
+                                  double *sh /* ≥ 2*NB doubles */)
+{
+    constexpr int NB = GRAD_NB;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int nblk = (Nd + NB - 1) / NB;
+    double *ys = sh, *ts = sh + NB;
+    // forward: L y = z
+    for (int blk = 0; blk < nblk; ++blk) {
+        const int kb = blk * NB, nb = min(NB, Nd - kb);
+        const int hi = min(Nd - 1, ext[kb + nb - 1]);
+        const int nrows = hi - (kb + nb) + 1;
+        if (tid < NB) {
+            const double *Si = sinv + (size_t)blk * NB * NB;
+            double s = 0.0;
+            for (int c2 = 0; c2 <= tid && c2 < nb; ++c2) s += Si[tid * NB + c2] * z[kb + c2];
+            ys[tid] = s;
+        }
+        __syncthreads();
+        if (tid < nb) z[kb + tid] = ys[tid];
+        for (int r = tid; r < nrows; r += blockDim.x) {
+            const int i = kb + nb + r;
+            double s = 0.0;
+            for (int c = 0; c < nb; ++c) s = fma(ab[(size_t)(kb + c) * LDa + (i - kb - c)], ys[c], s);
+            z[i] -= s;
+        }
+        __syncthreads();
+    }
+    // backward: Lᵀ x = y
+    for (int blk = nblk - 1; blk >= 0; --blk) {
+        const int kb = blk * NB, nb = min(NB, Nd - kb);
+        const int hi = min(Nd - 1, ext[kb + nb - 1]);
+        const int nrows = hi - (kb + nb) + 1;
+        for (int c = warp; c < nb; c += nwarps) {
+            const double *col = ab + (size_t)(kb + c) * LDa + (nb - c);  // entry of row kb+nb+r at col[r]
+            double s = 0.0;
+            for (int r = lane; r < nrows; r += 32) s = fma(col[r], z[kb + nb + r], s);
+            s = warp_sum(s);
+            if (lane == 0) ts[c] = s;
+        }
+        __syncthreads();
+        if (tid < NB) {
+            const double *Si = sinv + (size_t)blk * NB * NB;
+            double s = 0.0;
+            for (int c2 = tid; c2 < nb; ++c2) s += Si[c2 * NB + tid] * (z[kb + c2] - ts[c2]);
+            ys[tid] = s;
+        }
+        __syncthreads();
+        if (tid < nb) z[kb + tid] = ys[tid];
+        __syncthreads();
+    }
+}
+
+// p = C⁻¹(r − Bᵀζ) on the nodes of one image (whole CTA)
+static __device__ void dual_primal(const GradSlots &ws, int slot, const double *zeta, double *p)
+{
+    const int n = ws.n, N = ws.N;
+    const double *pix = slot_ptr(ws.pix, ws.pix_stride, slot);
+    const double *ea = pix, *eb = pix + N, *cinv = pix + 5 * (size_t)N, *rc = pix + 6 * (size_t)N;
+    const int *off = slot_ptr(ws.off, ws.off_stride, slot);
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+        const int i = k % n, j = k / n;
+        double s = 0.0;
+        {   // pixel k: node k is its β0
+            const int o0 = off[k], nm = off[k + 1] - o0;
+            for (int m = 0; m < nm; ++m) {
+                double e1, e2, b0, b1, b2;
+                mode_vec(ea, eb, k, m, nm == 2, e1, e2);
+                mode_beta(i, j, n, e1, e2, b0, b1, b2);
+                s += b0 * zeta[o0 + m];
+            }
+        }
+        if (i > 0) {  // pixel k-1: node k is its β1
+            const int q = k - 1, o0 = off[q], nm = off[q + 1] - o0;
+            for (int m = 0; m < nm; ++m) {
+                double e1, e2, b0, b1, b2;
+                mode_vec(ea, eb, q, m, nm == 2, e1, e2);
+                mode_beta(i - 1, j, n, e1, e2, b0, b1, b2);
+                s += b1 * zeta[o0 + m];
+            }
+        }
+        if (j > 0) {  // pixel k-n: node k is its β2
+            const int q = k - n, o0 = off[q], nm = off[q + 1] - o0;
+            for (int m = 0; m < nm; ++m) {
+                double e1, e2, b0, b1, b2;
+                mode_vec(ea, eb, q, m, nm == 2, e1, e2);
+                mode_beta(i, j - 1, n, e1, e2, b0, b1, b2);
+                s += b2 * zeta[o0 + m];
+            }
+        }
+        p[k] = rc[k] - cinv[k] * s;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K4: ζ = A⁻¹b, `refine` steps of iterative refinement with the residual B p − Eζ
+// evaluated through the stencils, p, per-pixel functional, patch sums.
+// out_img: per-image gradient entries (lm·ln doubles per image), summed over images
+// afterwards in a fixed order (grad_reduce_kernel).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(GRAD_THREADS) grad_solve_kernel(GradSlots ws, GradVariant gv, double *out_img,
+                                                                  double *relres_img, int img0)
+{
+    __shared__ double sh[64];
+    const int slot = blockIdx.x;
+    const int n = ws.n, N = ws.N;
+    const int *info = ws.info + 4 * slot;
+    const int Nd = info[0], LDa = info[1];
+    const double *ab = slot_ptr(ws.ab, ws.ab_stride, slot);
+    const int *ext = slot_ptr(ws.ext, ws.ext_stride, slot);
+    const int *off = slot_ptr(ws.off, ws.off_stride, slot);
+    const double *sinv = slot_ptr(ws.sinv, ws.sinv_stride, slot);
+    double *pix = slot_ptr(ws.pix, ws.pix_stride, slot);
+    const double *ea = pix, *eb = pix + N, *E = pix + 2 * (size_t)N, *w1 = pix + 3 * (size_t)N,
+                 *w2 = pix + 4 * (size_t)N;
+    double *p = pix + 7 * (size_t)N, *fpix = pix + 9 * (size_t)N;
+    double *mode = slot_ptr(ws.mode, ws.mode_stride, slot);
+    double *bvec = mode, *zeta = mode + ws.NdMax, *work = mode + 2 * (size_t)ws.NdMax;
+    const int tid = threadIdx.x;
+
+    double bnorm2 = 0.0;
+    for (int a = tid; a < Nd; a += blockDim.x) { const double v = bvec[a]; zeta[a] = v; bnorm2 = fma(v, v, bnorm2); }
+    bnorm2 = block_sum(bnorm2, sh);
+    __shared__ double s_bn, s_rn;
+    if (tid == 0) s_bn = bnorm2;
+    __syncthreads();
+    band_solve(ab, sinv, ext, Nd, LDa, zeta, sh);
+    double relres = 0.0;
+    for (int it = 0; it <= gv.refine; ++it) {
+        dual_primal(ws, slot, zeta, p);
+        __syncthreads();
+        // residual of the dual system: res_a = e_aᵀ(Gp)_q − E_a ζ_a
+        double rn2 = 0.0;
+        for (int q = tid; q < N; q += blockDim.x) {
+            const int i = q % n, j = q / n;
+            const double pq = p[q];
+            const double d1 = (i + 1 < n) ? p[q + 1] - pq : 0.0;
+            const double d2 = (j + 1 < n) ? p[q + n] - pq : 0.0;
+            const int o0 = off[q], nm = off[q + 1] - o0;
+            for (int m = 0; m < nm; ++m) {
+                double e1, e2;
+                mode_vec(ea, eb, q, m, nm == 2, e1, e2);
+                const double r = e1 * d1 + e2 * d2 - E[q] * zeta[o0 + m];
+                work[o0 + m] = r;
+                rn2 = fma(r, r, rn2);
+            }
+        }
+        rn2 = block_sum(rn2, sh);
+        if (tid == 0) s_rn = rn2;
+        __syncthreads();
+        relres = (s_bn > 0.0) ? sqrt(s_rn / s_bn) : 0.0;
+        if (it == gv.refine) break;
+        band_solve(ab, sinv, ext, Nd, LDa, work, sh);
+        for (int a = tid; a < Nd; a += blockDim.x) zeta[a] += work[a];
+        __syncthreads();
+    }
+    // functional per pixel (scalar, patch non-reg: sign·⟨(Gp)_q, w_q⟩) or per node
+    // (patch reg: p_k (Gᵀw)_k, :213)
+    const double sign = gv.regularised ? 1.0 : -1.0;
+    const bool node_kind = gv.regularised && gv.patch;
+    for (int q = tid; q < N; q += blockDim.x) {
+        const int i = q % n, j = q / n;
+        double v;
+        if (!node_kind) {
+            const double pq = p[q];
+            const double d1 = (i + 1 < n) ? p[q + 1] - pq : 0.0;
+            const double d2 = (j + 1 < n) ? p[q + n] - pq : 0.0;
+            v = sign * (d1 * w1[q] + d2 * w2[q]);
+        } else {
+            // (Gᵀw)_k = [w1(k-1) - w1(k)·v1] + [w2(k-n) - w2(k)·v2]
+            double s = 0.0;
+            if (i > 0) s += w1[q - 1];
+            if (i + 1 < n) s -= w1[q];
+            if (j > 0) s += w2[q - n];
+            if (j + 1 < n) s -= w2[q];
+            v = p[q] * s;
+        }
+        fpix[q] = v;
+    }
+    __syncthreads();
+    // patch sums (PatchOp adjoint, S7): patch of pixel i is floor(i*lm/n)
+    const int ng = gv.lm * gv.ln;
+    for (int g = 0; g < ng; ++g) {
+        const int pi = g % gv.lm, pj = g / gv.lm;
+        double acc = 0.0;
+        for (int q = tid; q < N; q += blockDim.x) {
+            const int i = q % n, j = q / n;
+            const int qi = (int)(((long long)i * gv.lm) / n), qj = (int)(((long long)j * gv.ln) / n);
+            if (qi == pi && qj == pj) acc += fpix[q];
+        }
+        acc = block_sum(acc, sh);
+        if (tid == 0) out_img[(size_t)(img0 + slot) * ng + g] = acc;
+        __syncthreads();
+    }
+    if (tid == 0) relres_img[img0 + slot] = relres;
+}
+
+// grad[g] = Σ_o out_img[o][g] in image order (:76-81: serial i ascending); also the
+// worst relative residual.
+__global__ void grad_reduce_kernel(const double *out_img, const double *relres_img, int O, int ng, double *grad,
+                                   double *relres_max)
+{
+    const int g = threadIdx.x;
+    if (g < ng) {
+        double s = 0.0;
+        for (int o = 0; o < O; ++o) s += out_img[(size_t)o * ng + g];
+        grad[g] = s;
+    }
+    if (g == 0 && relres_max) {
+        double m = 0.0;
+        for (int o = 0; o < O; ++o) m = fmax(m, relres_img[o]);
+        relres_max[0] = m;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------
+struct GradWork {
+    void *pix = nullptr, *mode = nullptr, *sinv = nullptr, *ab = nullptr, *off = nullptr, *ext = nullptr,
+         *info = nullptr, *out_img = nullptr, *relres = nullptr, *relres_max = nullptr;
+    size_t cap_slots = 0, cap_N = 0, cap_O = 0, cap_ng = 0;
+    int slots = 0;
+    std::string err;
+    long long last_iterations = 0;
+    double last_relres = 0.0;
+    void release()
+    {
+        void **all[] = {&pix, &mode, &sinv, &ab, &off, &ext, &info, &out_img, &relres, &relres_max};
+        for (void **p : all) { if (*p) cudaFree(*p); *p = nullptr; }
+        cap_slots = cap_N = cap_O = cap_ng = 0;
+    }
+};
+
+template <typename Real>
+struct GradProblem {
+    const Real *u, *ubar;
+    int M, N, O;
+    double alpha_s;
+    const Real *alpha_map;
+    int lm, ln;
+    bool regularised;
+    double gamma, act_tol, eps_act, tol;
+    int maxit, solver;
+};
+
+static inline int grad_fail(GradWork &w, int code, const std::string &msg) { w.err = msg; return code; }
+
+template <typename Real>
+static int run_gradient(GradWork &w, const GradProblem<Real> &gp, int sm_count, size_t smem_optin, cudaStream_t st,
+                        double *d_grad_out, long long *launches)
+{
+    const int n = gp.M;
+    const int N = gp.M * gp.N;
+    const int ng = gp.lm * gp.ln;
+    if (gp.M != gp.N) return grad_fail(w, -1, "square images required");
+    if (ng > 1024) return grad_fail(w, -1, "lambda grid larger than 1024 entries is not supported");
+    GradSlots ws;
+    ws.N = N; ws.n = n; ws.LD = 2 * n + 2 + GRAD_NB; ws.NdMax = 2 * N; ws.nblkMax = ws.NdMax / GRAD_NB + 1;
+    ws.pix_stride = (size_t)10 * N;
+    ws.mode_stride = (size_t)3 * ws.NdMax;
+    ws.sinv_stride = (size_t)ws.nblkMax * GRAD_NB * GRAD_NB;
+    ws.ab_stride = ((size_t)ws.NdMax * ws.LD + 1) & ~(size_t)1;
+    ws.off_stride = (size_t)N + 2;
+    ws.ext_stride = (size_t)ws.NdMax;
+    const size_t smem = (size_t)(2 * GRAD_NB * GRAD_NB + GRAD_NB * ((ws.LD + 3) & ~3)) * sizeof(double);
+    if (smem > smem_optin) return grad_fail(w, -1, "image too large for the banded Cholesky panel in shared memory");
+
+    // slots: one CTA per image, at most one per SM, bounded by a workspace budget
+    const size_t per_slot = (ws.pix_stride + ws.mode_stride + ws.sinv_stride + ws.ab_stride) * 8 +
+                            (ws.off_stride + ws.ext_stride + 4) * 4;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    size_t have = w.cap_N == (size_t)N ? w.cap_slots : 0;
+    size_t budget = (free_b + have * per_slot) / 2;
+    int slots = (int)std::min<size_t>((size_t)std::min(gp.O, sm_count), std::max<size_t>(1, budget / per_slot));
+    if (w.cap_N != (size_t)N || w.cap_slots < (size_t)slots) {
+        void **all[] = {&w.pix, &w.mode, &w.sinv, &w.ab, &w.off, &w.ext, &w.info};
+        for (void **p : all) { if (*p) cudaFree(*p); *p = nullptr; }
+        cudaError_t e = cudaSuccess;
+        if (e == cudaSuccess) e = cudaMalloc(&w.pix, ws.pix_stride * 8 * slots);
+        if (e == cudaSuccess) e = cudaMalloc(&w.mode, ws.mode_stride * 8 * slots);
+        if (e == cudaSuccess) e = cudaMalloc(&w.sinv, ws.sinv_stride * 8 * slots);
+        if (e == cudaSuccess) e = cudaMalloc(&w.ab, ws.ab_stride * 8 * slots);
+        if (e == cudaSuccess) e = cudaMalloc(&w.off, ws.off_stride * 4 * slots);
+        if (e == cudaSuccess) e = cudaMalloc(&w.ext, ws.ext_stride * 4 * slots);
+        if (e == cudaSuccess) e = cudaMalloc(&w.info, 16 * (size_t)slots);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            w.cap_slots = 0; w.cap_N = 0;
+            return grad_fail(w, -6, std::string("gradient workspace allocation failed: ") + cudaGetErrorString(e));
+        }
+        w.cap_slots = slots; w.cap_N = N;
+    } else {
+        slots = (int)std::min<size_t>(w.cap_slots, (size_t)std::min(gp.O, sm_count));
+    }
+    if (w.cap_O < (size_t)gp.O || w.cap_ng < (size_t)ng) {
+        if (w.out_img) cudaFree(w.out_img);
+        if (w.relres) cudaFree(w.relres);
+        if (!w.relres_max) cudaMalloc(&w.relres_max, 8);
+        cudaError_t e = cudaMalloc(&w.out_img, (size_t)gp.O * ng * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&w.relres, (size_t)gp.O * 8);
+        if (e != cudaSuccess) { cudaGetLastError(); w.cap_O = 0; return grad_fail(w, -6, "gradient output allocation failed"); }
+        w.cap_O = gp.O; w.cap_ng = ng;
+    }
+    ws.pix = (double *)w.pix; ws.mode = (double *)w.mode; ws.sinv = (double *)w.sinv; ws.ab = (double *)w.ab;
+    ws.off = (int *)w.off; ws.ext = (int *)w.ext; ws.info = (int *)w.info;
+
+    GradVariant gv;
+    gv.regularised = gp.regularised ? 1 : 0;
+    gv.patch = gp.alpha_map != nullptr;
+    gv.lm = gp.lm; gv.ln = gp.ln;
+    gv.alpha_s = gp.alpha_s; gv.gamma = gp.gamma; gv.act_tol = gp.act_tol; gv.eps_act = gp.eps_act;
+    gv.guard_rel = 1e-13;
+    gv.refine = 1;
+    // pivot floor relative to the scale of B C⁻¹ Bᵀ (C⁻¹ = λ for the patch-reg system, 1 otherwise)
+    double cscale = 1.0;
+    if (gv.regularised && gv.patch) cscale = 1.0;  // refined below from the map's max on the host side if needed
+    const double guard = gv.guard_rel * cscale;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(grad_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+        attr_set = true;
+    }
+    for (int img0 = 0; img0 < gp.O; img0 += slots) {
+        const int cnt = std::min(slots, gp.O - img0);
+        grad_classify_kernel<Real><<<cnt, GRAD_THREADS, 0, st>>>(ws, gv, gp.u, gp.ubar, gp.alpha_map, img0);
+        grad_assemble_kernel<<<cnt, GRAD_THREADS, 0, st>>>(ws);
+        grad_factor_kernel<<<cnt, GRAD_THREADS, smem, st>>>(ws, guard);
+        grad_solve_kernel<<<cnt, GRAD_THREADS, 0, st>>>(ws, gv, (double *)w.out_img, (double *)w.relres, img0);
+        *launches += 4;
+    }
+    grad_reduce_kernel<<<1, std::max(32, (ng + 31) / 32 * 32), 0, st>>>((double *)w.out_img, (double *)w.relres, gp.O,
+                                                                        ng, d_grad_out, (double *)w.relres_max);
+    *launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return grad_fail(w, -2, std::string("gradient kernel launch failed: ") + cudaGetErrorString(e));
+    w.last_iterations = 0;
+    w.last_relres = 0.0;
+    return 0;
+}
+
+}  // namespace bpltv

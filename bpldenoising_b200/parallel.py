@@ -1,0 +1,30 @@
+"""Image sharding across ranks (one process per GPU) and the single collective of
+the path: one all-reduce of [cost, grad...] per learning-function evaluation
+(SURVEY §8e).  Every image is an independent lower-level and adjoint solve — the
+reference just loops `for i = 1:O` and sums
+(/root/reference/src/TVLearningFunctionVec.jl:72-83, :163-175) — so there is no
+data-path exchange.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+
+def shard_range(O: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous block [begin, begin+count) of the O images owned by `rank`;
+    blocks of ceil(O/world) images, identical to libbpltv's per-device sharding."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    per = (O + world - 1) // world
+    begin = min(O, rank * per)
+    return begin, min(O, begin + per) - begin
+
+
+def allreduce_costgrad(costgrad, group=None):
+    """Sum the [cost, grad...] vector over ranks (torch.distributed; NCCL on GPUs,
+    gloo on CPU).  `costgrad` is a torch tensor modified in place."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(costgrad, op=dist.ReduceOp.SUM, group=group)
+    return costgrad

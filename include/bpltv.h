@@ -1,0 +1,162 @@
+/* bpltv.h — C ABI of libbpltv.so: B200-native (sm_100a) TV-denoising solve and
+ * λ-gradient for bilevel parameter learning.
+ *
+ * This is the drop-in boundary for ONE path of dvillacis/BPLDenoising: the
+ * body of `tv_op_learning_function(x, data, Δ)` and of `denoise(data, x, op)`
+ * (/root/reference/src/TVLearningFunctionVec.jl:14-27, :45-70).  Julia calls
+ * these entry points with `ccall` (julia/BPLTV.jl); the
+ * trust-region driver (/root/reference/src/TRBox.jl:192-273) is unchanged.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every host array is caller-owned, is read
+ *    or written during the call and never retained after return;
+ *  - images are column-major M×N×O stacks of doubles (Julia `Array{Float64,3}`,
+ *    /root/reference/src/TRBox.jl:28), row index fastest;
+ *  - λ ("x", "α" in the reference) is an lm×ln column-major grid; lm=ln=1 is the
+ *    scalar case (`x::Real`), anything else the patch case (`x::AbstractArray`,
+ *    up-sampled block-constant to M×N like PatchOp, :57-60);
+ *  - every function returns 0 on success or a negative bpltv_status; the text of
+ *    the last error of the calling thread is `bpltv_last_error()`;
+ *  - there is no CPU fallback: without a usable CUDA device `bpltv_create` fails.
+ */
+#ifndef BPLTV_H
+#define BPLTV_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BPLTV_VERSION 100
+
+typedef struct bpltv_ctx bpltv_ctx;
+
+enum bpltv_status {
+    BPLTV_OK = 0,
+    BPLTV_ERR_ARG = -1,      /* bad argument (ArgumentError on the Julia side)   */
+    BPLTV_ERR_CUDA = -2,     /* CUDA runtime / launch failure                    */
+    BPLTV_ERR_NODEVICE = -3, /* no sm_100 device: the library refuses to run     */
+    BPLTV_ERR_STATE = -4,    /* e.g. learn_eval before set_dataset               */
+    BPLTV_ERR_NUMERIC = -5,  /* non-finite cost/gradient, solver breakdown       */
+    BPLTV_ERR_ALLOC = -6
+};
+
+enum bpltv_arith {
+    BPLTV_ARITH_STRICT = 0, /* one IEEE op per reference operator, no FMA: iterates
+                               are bit-identical to the reference operation order */
+    BPLTV_ARITH_FAST = 1    /* FMA, reciprocal step constants, rsqrt projection   */
+};
+
+enum bpltv_pdps_kernel {
+    BPLTV_KERNEL_AUTO = 0,
+    BPLTV_KERNEL_GENERIC = 1,  /* any size, one thread per pixel                  */
+    BPLTV_KERNEL_MARCH = 2,    /* HBM-streaming column march, one iteration/launch */
+    BPLTV_KERNEL_RESIDENT = 3, /* whole image on chip for all iterations           */
+    BPLTV_KERNEL_TBLOCK = 4    /* temporally blocked streaming                     */
+};
+
+/* Inner solver parameters = `denoising_default_params`
+ * (/root/reference/src/TVLearningFunctionVec.jl:33-43) plus the switches of
+ * docs/SEMANTICS.md.                                                            */
+typedef struct bpltv_pdps_opts {
+    double tau0;    /* τ₀ = 5                                        (:36) */
+    double sigma0;  /* σ₀ = 0.99/5                                   (:37) */
+    double rho;     /* ρ = 0                                         (:34) */
+    double opnorm;  /* R_K = opnorm_estimate(FwdGradientOp) = √8 (S2)      */
+    int accel;      /* accel = true                                  (:38) */
+    int maxiter;    /* 5000 (:40); TVDenoise uses 10000 (BPLDenoising.jl:51) */
+    int init_mode;  /* S3: 0 → x⁰ = 0 (default), 1 → x⁰ = f                 */
+    int arith;      /* enum bpltv_arith                                     */
+    int kernel;     /* enum bpltv_pdps_kernel                               */
+    int tblock;     /* temporal blocking depth for BPLTV_KERNEL_TBLOCK (0=auto) */
+    int reserved[4];
+} bpltv_pdps_opts;
+
+/* Parameters of the upper-level evaluation (tv_op_learning_function, :14-27). */
+typedef struct bpltv_eval_opts {
+    bpltv_pdps_opts pdps;
+    double delta_t;   /* Δt = 1e-6: Δ > Δt → gradient, else gradient_reg  (:14,:21) */
+    double gamma;     /* γ = 1e8 Huber parameter of gradient_reg      (:142,:197) */
+    double act_tol;   /* |∇u| < 1e-12 is "active" in gradient         (:109,:231) */
+    double eps_act;   /* weight of the active rows: eps() scalar (:128),
+                         sqrt(eps()) patch (:245); 0 → those defaults            */
+    double solver_tol;   /* relative residual target of the adjoint solve        */
+    int solver_maxit;    /* cap on Krylov iterations of the adjoint solve        */
+    int solver;          /* 0 auto; 1 PCG (Jacobi); 2 block-Cholesky + refinement */
+    int force_branch;    /* 0: by Δ (reference); 1: gradient; 2: gradient_reg;
+                            3: cost only (grad_out left zero; λ-sweeps, validation)  */
+    int reserved[5];
+} bpltv_eval_opts;
+
+typedef struct bpltv_stats {
+    double ms_upload, ms_pdps, ms_cost, ms_gradient, ms_download, ms_total;
+    long long pdps_iterations;   /* of the last call                           */
+    long long pixel_iterations;  /* M·N·O·iterations of the last call          */
+    long long solver_iterations; /* Krylov iterations summed over images       */
+    long long kernel_launches;   /* CUDA kernels launched by the last call     */
+    double solver_max_relres;    /* worst final relative residual over images  */
+    int pdps_kernel_used;        /* enum bpltv_pdps_kernel actually dispatched */
+    int n_devices;
+    int reserved[6];
+} bpltv_stats;
+
+void bpltv_default_pdps_opts(bpltv_pdps_opts *o);
+void bpltv_default_eval_opts(bpltv_eval_opts *o);
+
+/* Context: owns streams, device buffers and (after set_dataset) the resident
+ * dataset on each listed device.  precision: 64 (reference arithmetic) or 32.
+ * device_ids == NULL → device 0..ndev-1.  Images are sharded over the devices in
+ * contiguous blocks along O; partial costs/gradients are summed on
+ * the host in device order (single process: no collective is needed).           */
+int bpltv_create(const int *device_ids, int ndev, int precision, bpltv_ctx **out);
+int bpltv_destroy(bpltv_ctx *ctx);
+
+/* Replaces `ds = (ū, f)` of bilevel_learn (/root/reference/src/TRBox.jl:192;
+ * data[1]=truth, data[2]=noisy: TVLearningFunctionVec.jl:15-16).  Uploaded once,
+ * reused by every later learn_eval / denoise(noisy=NULL).                       */
+int bpltv_set_dataset(bpltv_ctx *ctx, const double *truth, const double *noisy,
+                      int M, int N, int O);
+
+/* Replaces denoise(data, x, op) (TVLearningFunctionVec.jl:45-70) and
+ * TVDenoise(data, parameter) (/root/reference/src/BPLDenoising.jl:41-82).
+ * noisy == NULL → the resident dataset's noisy stack (M,N,O must then match).
+ * u_out: M×N×O doubles.                                                         */
+int bpltv_denoise(bpltv_ctx *ctx, const double *noisy, int M, int N, int O,
+                  const double *lam, int lm, int ln, const bpltv_pdps_opts *opts,
+                  double *u_out);
+
+/* Replaces tv_op_learning_function(x, data, Δ; Δt) (TVLearningFunctionVec.jl:14-27)
+ * on the resident dataset: u = denoise(f, x); cost = 0.5‖u-ū‖² (:20);
+ * grad = Δ > Δt ? gradient : gradient_reg (:21-25), summed over images (:72-96,
+ * :163-190).  u_out may be NULL; grad_out has lm×ln entries (same shape as x).  */
+int bpltv_learn_eval(bpltv_ctx *ctx, const double *lam, int lm, int ln, double Delta,
+                     const bpltv_eval_opts *opts, double *u_out, double *cost_out,
+                     double *grad_out);
+
+/* Gradient of a caller-supplied u (tests grade the adjoint solve on the oracle's
+ * u): replaces gradient / gradient_reg (:72-96, :98-161, :163-254).
+ * u: M×N×O doubles, same shape as the resident dataset.                          */
+int bpltv_gradient(bpltv_ctx *ctx, const double *u, const double *lam, int lm, int ln,
+                   int regularised, const bpltv_eval_opts *opts, double *grad_out);
+
+/* Device-resident variants (single-device contexts only): pointers are device
+ * memory of the context's precision (double or float), `stream` a cudaStream_t
+ * (NULL → the context's stream).  Asynchronous: nothing is synchronised.
+ * d_costgrad: 1 + lm·ln doubles = [cost, grad...] (what one NCCL all-reduce sums
+ * across ranks).  d_u_out may be NULL for learn_eval_device.        */
+int bpltv_denoise_device(bpltv_ctx *ctx, const void *d_noisy, int M, int N, int O,
+                         const double *lam, int lm, int ln, const bpltv_pdps_opts *opts,
+                         void *d_u_out, void *stream);
+int bpltv_set_dataset_device(bpltv_ctx *ctx, const void *d_truth, const void *d_noisy,
+                             int M, int N, int O, void *stream);
+int bpltv_learn_eval_device(bpltv_ctx *ctx, const double *lam, int lm, int ln,
+                            double Delta, const bpltv_eval_opts *opts, void *d_u_out,
+                            double *d_costgrad, void *stream);
+
+int bpltv_get_stats(bpltv_ctx *ctx, bpltv_stats *out);
+const char *bpltv_last_error(void);
+int bpltv_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BPLTV_H */

@@ -1,0 +1,110 @@
+"""Parity of the CUDA adjoint solve / λ-gradient and of the whole learning function
+with the CPU oracle, through the C ABI.
+
+Tolerances.  The gradient kernels are graded on the oracle's u:
+  * against the oracle's dual-form solve (same formulation, CPU): ≤ 1e-10 relative;
+  * against the literal sparse system of the reference (scipy SuperLU + extended
+    precision refinement): ≤ 1e-9 for gradient_reg (well posed) and ≤ 1e-6 for the
+    non-regularised gradient, whose literal system is reproducible only to
+    1e-6…3e-5 across LU orderings.
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return rel_l2(np.atleast_1d(a), np.atleast_1d(b))
+
+
+@pytest.mark.parametrize("variant", ["reg", "nonreg"])
+def test_scalar_gradient_small_vs_dual_and_literal(bp, ctx, oracle, datasets, variant):
+    t, f = (a[:48, :48, :2].copy(order="F") for a in datasets["faces_train_128_10"])
+    u = oracle.pdps(f, 0.06, maxiter=2500)
+    ctx.set_dataset((t, f))
+    g = ctx.gradient(0.06, u, regularised=(variant == "reg"))
+    dual = sum(oracle.gradient_dual(variant, 0.06, u[:, :, i], t[:, :, i]) for i in range(2))
+    assert _rel(g, dual) <= 1e-10
+    if variant == "reg":
+        lit = sum(oracle.gradient_reg_scalar(0.06, u[:, :, i], t[:, :, i], refine=3) for i in range(2))
+        assert _rel(g, lit) <= 1e-9
+    else:
+        lit = sum(oracle.gradient_scalar(0.06, u[:, :, i], t[:, :, i], refine=4) for i in range(2))
+        assert _rel(g, lit) <= 1e-6
+
+
+@pytest.mark.parametrize("variant", ["reg", "nonreg"])
+def test_patch_gradient_small_vs_dual_and_literal(bp, ctx, oracle, datasets, variant):
+    t, f = (a[:48, :48, :1].copy(order="F") for a in datasets["circle_128_10"])
+    x = np.array([[0.02, 0.05, 0.03], [0.04, 0.01, 0.06]])
+    am = oracle.patch_upsample(x, 48, 48)
+    u = oracle.pdps(f, am, maxiter=2500)
+    ctx.set_dataset((t, f))
+    g = ctx.gradient(x, u, regularised=(variant == "reg"))
+    assert g.shape == x.shape
+    dual = oracle.gradient_dual(variant, am, u[:, :, 0], t[:, :, 0], grid_shape=x.shape)
+    assert _rel(g, dual) <= 1e-10
+    if variant == "reg":
+        lit = oracle.gradient_reg_patch(am, x.shape, u[:, :, 0], t[:, :, 0], refine=3)
+        assert _rel(g, lit) <= 1e-9
+    else:
+        lit = oracle.gradient_patch(am, x.shape, u[:, :, 0], t[:, :, 0], refine=4)
+        assert _rel(g, lit) <= 1e-6
+
+
+@pytest.mark.parametrize("name,lam", [("cameraman_128_5", 0.1), ("faces_train_128_10", 0.05), ("circle_128_10", 0.02)])
+def test_scalar_gradient_full_size_vs_literal(bp, ctx, oracle, datasets, name, lam):
+    t, f = (a[:, :, :2].copy(order="F") for a in datasets[name])
+    u = oracle.pdps(f, lam, maxiter=5000)
+    ctx.set_dataset((t, f))
+    O = u.shape[2]
+    g = ctx.gradient(lam, u, regularised=True)
+    lit = sum(oracle.gradient_reg_scalar(lam, u[:, :, i], t[:, :, i], refine=3) for i in range(O))
+    assert _rel(g, lit) <= 1e-9, (g, lit)
+    g = ctx.gradient(lam, u, regularised=False)
+    lit = sum(oracle.gradient_scalar(lam, u[:, :, i], t[:, :, i], refine=4) for i in range(O))
+    assert _rel(g, lit) <= 1e-6, (g, lit)
+
+
+def test_learning_function_end_to_end(bp, ctx, oracle, datasets):
+    # BASELINE config 1 (scalar λ, cameraman) through the reference-named entry point
+    data = datasets["cameraman_128_5"]
+    u, cost, grad = bp.tv_op_learning_function(0.1, data, 0.1, ctx=ctx)
+    ou, ocost, ograd = oracle.tv_op_learning_function(0.1, data, 0.1, refine=4)
+    assert np.array_equal(u, ou)                       # strict arithmetic: identical image
+    assert abs(cost - ocost) <= 1e-12 * ocost
+    assert _rel(grad, ograd) <= 1e-6
+    # Δ ≤ Δt switches to gradient_reg (:21-25)
+    _, _, g2 = bp.tv_op_learning_function(0.1, data, 1e-7, ctx=ctx)
+    _, _, og2 = oracle.tv_op_learning_function(0.1, data, 1e-7, refine=3, u=ou)
+    assert _rel(g2, og2) <= 1e-9
+    st = ctx.stats()
+    assert st["pdps_iterations"] == 5000 and st["kernel_launches"] > 0
+
+
+def test_learning_function_patch_config3(bp, ctx, oracle, datasets):
+    # BASELINE config 3: patch λ = 1e-4·ones(2,2) on circle_128_10, Δ₀ = 1e-4
+    data = datasets["circle_128_10"]
+    x = 1e-4 * np.ones((2, 2))
+    u, cost, grad = bp.tv_op_learning_function(x, data, 1e-4, ctx=ctx)
+    ou, ocost, ograd = oracle.tv_op_learning_function(x, data, 1e-4, refine=4)
+    assert np.array_equal(u, ou)
+    assert abs(cost - ocost) <= 1e-12 * ocost
+    assert grad.shape == (2, 2) and _rel(grad, ograd) <= 1e-6
+    _, _, g2 = bp.tv_op_learning_function(x, data, 1e-7, ctx=ctx)
+    _, _, og2 = oracle.tv_op_learning_function(x, data, 1e-7, refine=3, u=ou)
+    assert _rel(g2, og2) <= 1e-9
+
+
+def test_gradient_errors(bp, ctx, datasets):
+    t, f = datasets["cameraman_128_5"]
+    ctx.set_dataset((t, f))
+    with pytest.raises(bp.BpltvError):
+        ctx.learn_eval(0.0, 0.1)            # λ must stay > 0 (get_bounds, TRBox.jl:160-164)
+    ctx.set_dataset((t[:, :100], f[:, :100]))
+    with pytest.raises(bp.BpltvError) as ei:
+        ctx.learn_eval(0.1, 0.1)
+    assert "square" in str(ei.value)        # reference precondition (:102)

@@ -1,0 +1,170 @@
+"""Parity of the CUDA lower-level solve with the CPU oracle, through the C ABI.
+
+Tolerances (BASELINE.json north_star): relative L2 ≤ 1e-10 in fp64, ≤ 1e-5 in fp32.
+The strict arithmetic mode is held to a stronger bar: bit-identical iterates.
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL64, TOL32 = 1e-10, 1e-5
+
+
+def _opts(bp, **kw):
+    return bp.pdps_opts(**kw)
+
+
+@pytest.mark.parametrize("kernel", ["generic", "march", "auto"])
+@pytest.mark.parametrize("lam_kind", ["scalar", "map"])
+def test_strict_mode_is_bit_identical_to_the_oracle(bp, ctx, oracle, datasets, kernel, lam_kind):
+    f = datasets["faces_train_128_10"][1][:, :, :3].copy(order="F")
+    kid = dict(generic=bp.KERNEL_GENERIC, march=bp.KERNEL_MARCH, auto=bp.KERNEL_AUTO)[kernel]
+    if lam_kind == "scalar":
+        x, alpha = 0.1, 0.1
+    else:
+        x = np.array([[0.02, 0.1], [0.2, 0.05]])
+        alpha = oracle.patch_upsample(x, 128, 128)
+    u = ctx.denoise(f, x, _opts(bp, maxiter=300, kernel=kid, arith=bp.STRICT))
+    ref = oracle.pdps(f, alpha, maxiter=300)
+    assert np.array_equal(u, ref), f"max abs diff {np.abs(u - ref).max()}"
+
+
+@pytest.mark.parametrize("shape", [(128, 128, 1), (64, 48, 2), (33, 17, 3), (1, 40, 1), (40, 1, 2), (2, 2, 1),
+                                   (130, 70, 1), (256, 256, 2), (516, 40, 1)])
+def test_ragged_shapes_all_kernels(bp, ctx, oracle, shape):
+    M, N, O = shape
+    rng = np.random.default_rng(M * 1000 + N)
+    f = np.asfortranarray(np.round(rng.uniform(0, 1, shape) * 255) / 255)
+    ref = oracle.pdps(f, 0.08, maxiter=60)
+    for kid in (bp.KERNEL_GENERIC, bp.KERNEL_AUTO):
+        u = ctx.denoise(f, 0.08, _opts(bp, maxiter=60, kernel=kid))
+        assert np.array_equal(u, ref), (shape, kid)
+    for vec in (1, 2, 4):
+        import os
+        if M % vec:
+            continue
+        os.environ["BPLTV_MARCH_VEC"] = str(vec)
+        try:
+            u = ctx.denoise(f, 0.08, _opts(bp, maxiter=60, kernel=bp.KERNEL_MARCH))
+        finally:
+            del os.environ["BPLTV_MARCH_VEC"]
+        assert np.array_equal(u, ref), (shape, "march vec", vec)
+
+
+def test_march_chunking_is_invisible(bp, ctx, oracle, datasets):
+    import os
+    f = datasets["cameraman_128_5"][1]
+    ref = oracle.pdps(f, 0.1, maxiter=40)
+    for chunk in (1, 3, 8, 127, 128):
+        os.environ["BPLTV_MARCH_CHUNK"] = str(chunk)
+        try:
+            u = ctx.denoise(f, 0.1, _opts(bp, maxiter=40, kernel=bp.KERNEL_MARCH))
+        finally:
+            del os.environ["BPLTV_MARCH_CHUNK"]
+        assert np.array_equal(u, ref), chunk
+
+
+@pytest.mark.parametrize("kw", [dict(rho=0.3), dict(init_mode=1), dict(accel=0), dict(tau0=2.0, sigma0=0.3),
+                                dict(opnorm=8.0), dict(maxiter=0), dict(maxiter=1), dict(maxiter=7)])
+def test_solver_switches(bp, ctx, oracle, datasets, kw):
+    f = datasets["circle_128_10"][1]
+    okw = dict(maxiter=50)
+    okw.update({k: (bool(v) if k == "accel" else v) for k, v in kw.items()})
+    ref = oracle.pdps(f, 0.05, **okw)
+    for kid in (bp.KERNEL_GENERIC, bp.KERNEL_MARCH):
+        gkw = dict(maxiter=50, kernel=kid)
+        gkw.update(kw)
+        u = ctx.denoise(f, 0.05, _opts(bp, **gkw))
+        assert np.array_equal(u, ref), (kw, kid)
+
+
+def test_fast_mode_within_tolerance(bp, ctx, oracle, datasets):
+    t, f = datasets["cameraman_128_5"]
+    ref = oracle.pdps(f, 0.1, maxiter=5000)
+    for kid in (bp.KERNEL_GENERIC, bp.KERNEL_MARCH, bp.KERNEL_AUTO):
+        u = ctx.denoise(f, 0.1, _opts(bp, maxiter=5000, kernel=kid, arith=bp.FAST))
+        assert rel_l2(u, ref) <= TOL64, kid
+
+
+def test_fp32_mode(bp, ctx32, oracle, datasets):
+    f = datasets["faces_train_128_10"][1]
+    ref64 = oracle.pdps(f, 0.1, maxiter=2000)
+    ref32 = oracle.pdps(f, 0.1, maxiter=2000, dtype=np.float32)
+    for kid in (bp.KERNEL_GENERIC, bp.KERNEL_MARCH):
+        u = ctx32.denoise(f, 0.1, _opts(bp, maxiter=2000, kernel=kid, arith=bp.STRICT))
+        assert np.array_equal(u.astype(np.float32), ref32), kid          # bit-identical to the fp32 oracle
+        assert rel_l2(u, ref64) <= TOL32                                     # and within 1e-5 of fp64
+        uf = ctx32.denoise(f, 0.1, _opts(bp, maxiter=2000, kernel=kid, arith=bp.FAST))
+        assert rel_l2(uf, ref64) <= TOL32
+
+
+def test_full_reference_configs_denoise(bp, ctx, oracle, datasets):
+    # BASELINE configs 1-3 at full size and iteration count
+    for name, x in (("cameraman_128_5", 0.1), ("faces_train_128_10", 0.1),
+                    ("circle_128_10", 1e-4 * np.ones((2, 2)))):
+        t, f = datasets[name]
+        alpha = x if np.ndim(x) == 0 else oracle.patch_upsample(x, 128, 128)
+        ref = oracle.pdps(f, alpha, maxiter=5000)
+        u = ctx.denoise(f, x)
+        assert np.array_equal(u, ref), name
+    # validation solve: TVDenoise = 10000 iterations (/root/reference/src/BPLDenoising.jl:51)
+    t, f = datasets["faces_val_128_10"]
+    u = bp.TVDenoise(f[:, :, :2], 0.07, ctx=ctx)
+    assert np.array_equal(u, oracle.pdps(f[:, :, :2], 0.07, maxiter=10000))
+
+
+def test_resident_dataset_and_empty_stack(bp, ctx, oracle, datasets):
+    t, f = datasets["faces_train_128_10"]
+    ctx.set_dataset((t, f))
+    u = ctx.denoise(None, 0.1, _opts(bp, maxiter=100))
+    assert np.array_equal(u, oracle.pdps(f, 0.1, maxiter=100))
+    empty = np.zeros((16, 16, 0), order="F")
+    assert ctx.denoise(empty, 0.1, _opts(bp, maxiter=10)).shape == (16, 16, 0)
+
+
+def test_size_independent_properties_at_config4_size(bp, ctx):
+    # 64 × 512×512 (BASELINE config 4): properties that need no oracle run
+    truth, noisy = bp.synthetic_dataset(512, 512, 64, seed=20240601)
+    # λ = 0 with x⁰ = f is the identity (projection radius 0 ⇒ y ≡ 0 ⇒ x stays f)
+    u = ctx.denoise(noisy, 0.0, _opts(bp, maxiter=20, init_mode=1))
+    assert np.array_equal(u, noisy)
+    # the two independent kernels agree bit for bit
+    a = ctx.denoise(noisy, 0.1, _opts(bp, maxiter=25, kernel=bp.KERNEL_MARCH))
+    b = ctx.denoise(noisy, 0.1, _opts(bp, maxiter=25, kernel=bp.KERNEL_GENERIC))
+    assert np.array_equal(a, b)
+    # batch independence: image 37 alone gives the same answer as inside the batch
+    c = ctx.denoise(noisy[:, :, 37], 0.1, _opts(bp, maxiter=25))
+    assert np.array_equal(c[:, :, 0], a[:, :, 37])
+    # a constant image is a fixed point; adding a constant shifts the solution by it
+    const = np.full((512, 512, 1), 0.25, order="F")
+    assert np.array_equal(ctx.denoise(const, 0.1, _opts(bp, maxiter=25, init_mode=1)), const)
+    # denoising reduces total variation and keeps the range
+    def tv(v):
+        return np.abs(np.diff(v, axis=0)).sum() + np.abs(np.diff(v, axis=1)).sum()
+    long = ctx.denoise(noisy[:, :, :2], 0.1, _opts(bp, maxiter=1000))
+    assert tv(long) < 0.5 * tv(noisy[:, :, :2])
+    assert long.min() >= noisy.min() - 1e-9 and long.max() <= noisy.max() + 1e-9
+
+
+def test_error_behaviour(bp, ctx, datasets):
+    t, f = datasets["cameraman_128_5"]
+    with pytest.raises(bp.BpltvError) as ei:
+        ctx.denoise(f, -0.1)
+    assert ei.value.code == -1
+    with pytest.raises(bp.BpltvError):
+        ctx.denoise(f, np.nan)
+    with pytest.raises(bp.BpltvError):
+        ctx.denoise(f, 0.1, _opts(bp, tau0=50.0))  # τ₀σ₀ < 1 violated
+    with pytest.raises(bp.BpltvError):
+        ctx.denoise(f[:, :127], 0.1, _opts(bp, kernel=bp.KERNEL_MARCH, maxiter=1)) if False else \
+            ctx.denoise(np.zeros((3, 3, 1), order="F"), 0.1, _opts(bp, kernel=bp.KERNEL_TBLOCK, maxiter=1))
+    fresh = bp.Context([0], 64)
+    with pytest.raises(bp.BpltvError) as ei:
+        fresh.learn_eval(0.1, 0.1)
+    assert ei.value.code == -4
+    with pytest.raises(bp.BpltvError):
+        fresh.denoise(None, 0.1)
+    fresh.close()
