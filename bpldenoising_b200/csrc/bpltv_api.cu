@@ -147,7 +147,7 @@ static int upload_steps(Dev &d, const bpltv_pdps_opts &o, cudaStream_t st)
         s.one_p_omega = (Real)1 + s.omega;
         s.inv_one_p_tau = (Real)(1.0 / (1.0 + tau));
         s.tau_over_one_p_tau = (Real)(tau / (1.0 + tau));
-        s.pad = 0;
+        s.rcp_one_p_tau = (Real)1 / s.one_p_tau;  // correctly rounded in the compute type
         h[k] = s;
         if (o.accel) { tau = tau * omega; sigma = sigma / omega; }
     }
@@ -189,24 +189,37 @@ static int march_vec(int M)
     return 0;
 }
 
-template <typename Real, int VEC, int MAXT>
-static void launch_march_t(const MarchArgs<Real> &a, int nthreads, int nunits, bool map, bool strict, cudaStream_t st)
+// kernel pointer of one march instantiation
+template <typename Real>
+using MarchFn = void (*)(const MarchArgs<Real>);
+
+template <typename Real, int VEC, int MAXT, int MINB>
+static MarchFn<Real> march_fn_cfg(bool map, bool strict)
 {
-    if (map) {
-        if (strict) pdps_march_kernel<Real, VEC, true, true, MAXT><<<nunits, nthreads, 0, st>>>(a);
-        else pdps_march_kernel<Real, VEC, true, false, MAXT><<<nunits, nthreads, 0, st>>>(a);
-    } else {
-        if (strict) pdps_march_kernel<Real, VEC, false, true, MAXT><<<nunits, nthreads, 0, st>>>(a);
-        else pdps_march_kernel<Real, VEC, false, false, MAXT><<<nunits, nthreads, 0, st>>>(a);
-    }
+    if (map) return strict ? pdps_march_kernel<Real, VEC, true, true, MAXT, MINB>
+                           : pdps_march_kernel<Real, VEC, true, false, MAXT, MINB>;
+    return strict ? pdps_march_kernel<Real, VEC, false, true, MAXT, MINB>
+                  : pdps_march_kernel<Real, VEC, false, false, MAXT, MINB>;
 }
 
 template <typename Real, int VEC>
-static void launch_march_vec(const MarchArgs<Real> &a, int nthreads, int nunits, bool map, bool strict, cudaStream_t st)
+static MarchFn<Real> march_fn_vec(int nthreads, int minb, bool map, bool strict)
 {
-    // ≤256 threads: the register allocator may use up to 255 registers per thread
-    if (nthreads <= 256) launch_march_t<Real, VEC, 256>(a, nthreads, nunits, map, strict, st);
-    else launch_march_t<Real, VEC, 1024>(a, nthreads, nunits, map, strict, st);
+    // ≤256 threads: ask for `minb` resident CTAs per SM (register cap 65536/(256·minb))
+    if (nthreads <= 256) {
+        if (minb >= 4) return march_fn_cfg<Real, VEC, 256, 4>(map, strict);
+        if (minb == 3) return march_fn_cfg<Real, VEC, 256, 3>(map, strict);
+        return march_fn_cfg<Real, VEC, 256, 2>(map, strict);
+    }
+    return march_fn_cfg<Real, VEC, 1024, 1>(map, strict);
+}
+
+template <typename Real>
+static MarchFn<Real> march_fn(int vec, int nthreads, int minb, bool map, bool strict)
+{
+    if (vec == 4) return march_fn_vec<Real, 4>(nthreads, minb, map, strict);
+    if (vec == 2) return march_fn_vec<Real, 2>(nthreads, minb, map, strict);
+    return march_fn_vec<Real, 1>(nthreads, minb, map, strict);
 }
 
 template <typename Real>
@@ -243,7 +256,8 @@ static int run_pdps(Dev &d, const Real *f, int M, int N, int O, double alpha_s, 
     int kernel = o.kernel;
     if (kernel == BPLTV_KERNEL_AUTO) kernel = env_int("BPLTV_PDPS_KERNEL", 0);
     if (kernel == BPLTV_KERNEL_AUTO) {
-        if (resident_eligible<Real>(d.smem_optin, M, N) && !rho && O * resident_cluster_size<Real>(M, N) <= 4 * d.sm_count)
+        if (resident_eligible<Real>(d.smem_optin, M, N) && !rho &&
+            O * resident_cluster_size<Real>(d.smem_optin, M, N) <= env_int("BPLTV_RESIDENT_MAX_WAVES", 4) * d.sm_count)
             kernel = BPLTV_KERNEL_RESIDENT;
         else
             kernel = march_vec<Real>(M) ? BPLTV_KERNEL_MARCH : BPLTV_KERNEL_GENERIC;
@@ -263,12 +277,15 @@ static int run_pdps(Dev &d, const Real *f, int M, int N, int O, double alpha_s, 
         // whole solve in one launch; x⁰/y⁰ are formed on chip
         ResidentArgs<Real> a;
         a.f = f; a.u_out = d.x[0].as<Real>(); a.alpha_map = alpha_map; a.steps = steps;
-        a.maxiter = o.maxiter; a.M = M; a.N = N; a.O = O; a.alpha_s = (Real)alpha_s; a.init_mode = o.init_mode;
-        RC_TRY(launch_resident<Real>(a, map, strict, st));
+        a.maxiter = o.maxiter; a.M = M; a.N = N; a.O = O; a.NC = 0; a.alpha_s = (Real)alpha_s;
+        a.init_mode = o.init_mode;
+        cudaError_t e = launch_resident<Real>(a, d.smem_optin, map, strict, st);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(BPLTV_ERR_CUDA, "resident PDPS launch failed: %s", cudaGetErrorString(e));
+        }
         d.launches += 1;
         *u_result = d.x[0].as<Real>();
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return fail(BPLTV_ERR_CUDA, "resident PDPS launch failed: %s", cudaGetErrorString(e));
         return 0;
     }
 
@@ -281,26 +298,29 @@ static int run_pdps(Dev &d, const Real *f, int M, int N, int O, double alpha_s, 
     if (kernel == BPLTV_KERNEL_MARCH) {
         const int vec = march_vec<Real>(M);
         const int nthreads = (M / vec + 31) / 32 * 32;
-        // enough CTAs to cover the chip several times over; chunks no shorter than 8 columns
-        const int target_units = d.sm_count * env_int("BPLTV_MARCH_UNITS_PER_SM", 8);
-        int chunk = env_int("BPLTV_MARCH_CHUNK", 0);
-        if (chunk <= 0) {
-            const long long cols = (long long)N * O;
-            chunk = (int)std::max<long long>(8, (cols + target_units - 1) / target_units);
-        }
-        chunk = std::min(chunk, N);
-        const int cpi = (N + chunk - 1) / chunk;
+        const int minb = env_int("BPLTV_MARCH_MINB", 4);
+        MarchFn<Real> fn = march_fn<Real>(vec, nthreads, minb, map, strict);
+        // one balanced wave: grid = #SM × resident CTAs per SM, never more CTAs than columns
+        int per_sm = 0;
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, nthreads, 0));
+        per_sm = std::max(1, per_sm);
+        const long long cols = (long long)N * O;
+        long long grid = (long long)d.sm_count * per_sm;
+        const int min_cols = std::max(1, env_int("BPLTV_MARCH_MIN_COLS", 4));
+        grid = std::max<long long>(1, std::min<long long>(grid, (cols + min_cols - 1) / min_cols));
+        if (env_int("BPLTV_MARCH_CHUNK", 0) > 0)  // test hook: force a range length
+            grid = (cols + env_int("BPLTV_MARCH_CHUNK", 0) - 1) / env_int("BPLTV_MARCH_CHUNK", 0);
         MarchArgs<Real> a;
-        a.f = f; a.alpha_map = alpha_map; a.steps = steps; a.M = M; a.N = N; a.O = O;
-        a.chunk = chunk; a.chunks_per_image = cpi; a.alpha_s = (Real)alpha_s; a.rho = (Real)o.rho;
+        a.f = f; a.alpha_map = alpha_map; a.M = M; a.N = N; a.O = O; a.total_cols = cols;
+        a.prefetch_dist = env_int("BPLTV_MARCH_PREFETCH", 0);
+        a.alpha_s = (Real)alpha_s; a.rho = (Real)o.rho;
+        const StepConsts<Real> *hsteps = reinterpret_cast<const StepConsts<Real> *>(d.steps_host.data());
         for (int it = 0; it < o.maxiter; ++it) {
             const int bi = it & 1, bo = bi ^ 1;
             a.x_in = d.x[bi].as<Real>(); a.y1_in = d.y1[bi].as<Real>(); a.y2_in = d.y2[bi].as<Real>();
             a.x_out = d.x[bo].as<Real>(); a.y1_out = d.y1[bo].as<Real>(); a.y2_out = d.y2[bo].as<Real>();
-            a.it = it;
-            if (vec == 4) launch_march_vec<Real, 4>(a, nthreads, cpi * O, map, strict, st);
-            else if (vec == 2) launch_march_vec<Real, 2>(a, nthreads, cpi * O, map, strict, st);
-            else launch_march_vec<Real, 1>(a, nthreads, cpi * O, map, strict, st);
+            a.sc = hsteps[it];
+            fn<<<(unsigned)grid, nthreads, 0, st>>>(a);
         }
     } else {
         GenericArgs<Real> a;

@@ -1,9 +1,32 @@
-// pdps_resident.cuh — kernel B: whole image resident on chip for all iterations.
-// (interface; the kernel body lands after the streaming path is validated)
+// pdps_resident.cuh — kernel B: whole image resident on chip for ALL iterations.
+//
+// One launch = the complete lower-level solve.  One image per thread-block cluster
+// of CS CTAs; CTA `rank` owns the NC = ceil(N/CS) consecutive columns starting at
+// rank·NC (a contiguous slab of the column-major image).  Per pixel, x and f (and λ
+// for a map) live in REGISTERS of the owning thread for the whole solve; the dual
+// field y1, y2 and the over-relaxed x̄ live in SHARED MEMORY planes because their
+// row/column neighbours are read by other threads.  The two columns a CTA needs from
+// its neighbours — y2(:, c0-1) from the left, x̄(:, c0+NC) from the right — are
+// PUSHED by their owners into halo slots of the neighbour's planes through
+// distributed shared memory (remote stores, made visible by the cluster barrier), so
+// every read in the hot loop is a local shared-memory read.  HBM traffic: f once in,
+// u once out.  Two cluster barriers per iteration:
+//     phase A  primal prox + over-relaxation  (reads y planes, writes x̄ plane)
+//     barrier.cluster
+//     phase B  dual ascent + projection       (reads x̄ plane, writes y planes)
+//     barrier.cluster
+// The path is bounded by barrier latency + shared-memory bandwidth + fp64 issue, not
+// by HBM.  Same operation order as the other kernels: strict mode is bit-identical.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace bpltv {
+
+namespace cg = cooperative_groups;
+
+constexpr int RES_THREADS = 512;
 
 template <typename Real>
 struct ResidentArgs {
@@ -12,16 +35,201 @@ struct ResidentArgs {
     const Real *alpha_map;
     const StepConsts<Real> *steps;
     int maxiter, M, N, O, init_mode;
+    int NC;  // columns per CTA
     Real alpha_s;
 };
 
-template <typename Real>
-static inline bool resident_eligible(size_t /*smem_optin*/, int /*M*/, int /*N*/) { return false; }
+// KC = column slots per thread (each slot = 2 consecutive rows of one column)
+template <typename Real, int KC, bool MAP, bool STRICT>
+__global__ void __launch_bounds__(RES_THREADS, 1) pdps_resident_kernel(const ResidentArgs<Real> a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CS = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int o = blockIdx.x / CS;  // image
+    const int M = a.M, N = a.N, NC = a.NC;
+
+    // planes: y1[NC][M]; y2[1+NC][M] (slot 0 = left halo); xb[NC+1][M] (slot NC = right halo)
+    Real *y1p = reinterpret_cast<Real *>(smem_raw);
+    Real *y2p = y1p + (size_t)NC * M;
+    Real *xbp = y2p + (size_t)(NC + 1) * M;
+    const int plane_total = (3 * NC + 2) * M;
+    for (int k = threadIdx.x; k < plane_total; k += blockDim.x) y1p[k] = (Real)0;
+
+    // neighbours' planes through DSMEM
+    Real *xb_left = rank > 0 ? cluster.map_shared_rank(xbp, rank - 1) : nullptr;        // their right halo
+    Real *y2_right = rank + 1 < CS ? cluster.map_shared_rank(y2p, rank + 1) : nullptr;  // their left halo
+
+    const int tpc = M >> 1;                 // threads per column (2 rows each)
+    const int CG = blockDim.x / tpc;        // column groups
+    const int cgrp = threadIdx.x / tpc;
+    const int r0 = (threadIdx.x - cgrp * tpc) * 2;
+    const bool t_ok = cgrp < CG;            // threads beyond CG·tpc idle (still hit the barriers)
+    const int c_begin = rank * NC;
+    const size_t img = (size_t)o * M * N;
+
+    Real x[KC][2], f[KC][2], al[KC][2];
+    bool ok[KC];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        const int c = cgrp + CG * k;        // local column
+        const int jg = c_begin + c;         // image column
+        ok[k] = t_ok && c < NC && jg < N;
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            f[k][v] = 0; x[k][v] = 0; al[k][v] = a.alpha_s;
+            if (ok[k]) {
+                const size_t idx = (size_t)jg * M + r0 + v;
+                f[k][v] = a.f[img + idx];
+                if (MAP) al[k][v] = a.alpha_map[idx];
+                x[k][v] = a.init_mode ? f[k][v] : (Real)0;
+            }
+        }
+    }
+    cluster.sync();  // planes zeroed everywhere before anyone pushes into a halo
+
+    for (int it = 0; it < a.maxiter; ++it) {
+        const StepConsts<Real> sc = a.steps[it];
+        Real xb[KC][2], y1o[KC][2], y2o[KC][2];
+        // ---- phase A: x ← prox, x̄ ← over-relaxation ----------------------------------
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            if (!ok[k]) continue;
+            const int c = cgrp + CG * k;
+            const Real *py1 = y1p + (size_t)c * M + r0;
+            const Real *py2 = y2p + (size_t)(c + 1) * M + r0;  // own column (slot c+1), left = slot c
+            y1o[k][0] = py1[0]; y1o[k][1] = py1[1];
+            y2o[k][0] = py2[0]; y2o[k][1] = py2[1];
+            const Real up = r0 > 0 ? py1[-1] : (Real)0;
+            const Real l0 = py2[-M], l1 = py2[-M + 1];
+            const Real xn0 = primal_update<Real, STRICT>(x[k][0], f[k][0], up, y1o[k][0], l0, y2o[k][0], sc, xb[k][0]);
+            const Real xn1 = primal_update<Real, STRICT>(x[k][1], f[k][1], y1o[k][0], y1o[k][1], l1, y2o[k][1], sc, xb[k][1]);
+            x[k][0] = xn0; x[k][1] = xn1;
+            Real *pxb = xbp + (size_t)c * M + r0;
+            pxb[0] = xb[k][0]; pxb[1] = xb[k][1];
+            if (c == 0 && xb_left) {  // first local column: the left CTA needs it as x̄(:, its NC)
+                Real *q = xb_left + (size_t)NC * M + r0;
+                q[0] = xb[k][0]; q[1] = xb[k][1];
+            }
+        }
+        cluster.sync();
+        // ---- phase B: y ← P_λ(y + σ∇x̄) ---------------------------------------------------
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            if (!ok[k]) continue;
+            const int c = cgrp + CG * k;
+            const int jg = c_begin + c;
+            const Real *pxb = xbp + (size_t)c * M + r0;
+            const Real below = (r0 + 2 < M) ? pxb[2] : (Real)0;
+            Real d1_0, d1_1, d2_0 = 0, d2_1 = 0;
+            if (STRICT) {
+                d1_0 = StrictOps<Real>::sub(xb[k][1], xb[k][0]);
+                d1_1 = (r0 + 2 < M) ? StrictOps<Real>::sub(below, xb[k][1]) : (Real)0;
+            } else {
+                d1_0 = xb[k][1] - xb[k][0];
+                d1_1 = (r0 + 2 < M) ? below - xb[k][1] : (Real)0;
+            }
+            if (jg + 1 < N) {
+                const Real rt0 = pxb[M], rt1 = pxb[M + 1];  // column c+1 (slot NC = pushed halo)
+                if (STRICT) { d2_0 = StrictOps<Real>::sub(rt0, xb[k][0]); d2_1 = StrictOps<Real>::sub(rt1, xb[k][1]); }
+                else { d2_0 = rt0 - xb[k][0]; d2_1 = rt1 - xb[k][1]; }
+            }
+            Real v1 = y1o[k][0], v2 = y2o[k][0], w1 = y1o[k][1], w2 = y2o[k][1];
+            dual_update<Real, STRICT, false>(v1, v2, d1_0, d2_0, al[k][0], (Real)0, sc);
+            dual_update<Real, STRICT, false>(w1, w2, d1_1, d2_1, al[k][1], (Real)0, sc);
+            Real *py1 = y1p + (size_t)c * M + r0;
+            Real *py2 = y2p + (size_t)(c + 1) * M + r0;
+            py1[0] = v1; py1[1] = w1;
+            py2[0] = v2; py2[1] = w2;
+            if (c == NC - 1 && y2_right) {  // last local column: the right CTA needs it as y2(:, c0-1)
+                Real *q = y2_right + r0;
+                q[0] = v2; q[1] = w2;
+            }
+        }
+        cluster.sync();
+    }
+
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        if (!ok[k]) continue;
+        const int jg = c_begin + cgrp + CG * k;
+        const size_t idx = img + (size_t)jg * M + r0;
+        a.u_out[idx] = x[k][0];
+        a.u_out[idx + 1] = x[k][1];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side: shape → (cluster size, columns per CTA, slots per thread)
+// ---------------------------------------------------------------------------
+struct ResidentPlan {
+    bool ok = false;
+    int CS = 0, NC = 0, KC = 0;
+    size_t smem = 0;
+};
 
 template <typename Real>
-static inline int resident_cluster_size(int /*M*/, int /*N*/) { return 1; }
+static inline ResidentPlan resident_plan(size_t smem_optin, int M, int N)
+{
+    ResidentPlan p;
+    if (M < 2 || (M & 1) || (M / 2) > RES_THREADS || RES_THREADS % (M / 2) != 0) return p;
+    const int CG = RES_THREADS / (M / 2);
+    const int cs_cands[4] = {8, 4, 2, 1};
+    for (int ci = 0; ci < 4; ++ci) {
+        const int CS = cs_cands[ci];
+        if (CS > N) continue;
+        const int NC = (N + CS - 1) / CS;
+        if ((CS - 1) * NC >= N) continue;              // every rank must own at least one column
+        const int KC = (NC + CG - 1) / CG;
+        if (KC > 4) continue;
+        const size_t smem = (size_t)(3 * NC + 2) * M * sizeof(Real);
+        if (smem > smem_optin) continue;
+        p.ok = true; p.CS = CS; p.NC = NC; p.KC = KC <= 1 ? 1 : (KC <= 2 ? 2 : 4); p.smem = smem;
+        return p;
+    }
+    return p;
+}
 
 template <typename Real>
-static inline int launch_resident(const ResidentArgs<Real> &, bool /*map*/, bool /*strict*/, cudaStream_t) { return -1; }
+static inline bool resident_eligible(size_t smem_optin, int M, int N) { return resident_plan<Real>(smem_optin, M, N).ok; }
+
+template <typename Real>
+static inline int resident_cluster_size(size_t smem_optin, int M, int N) { return resident_plan<Real>(smem_optin, M, N).CS; }
+
+template <typename Real, int KC>
+static inline cudaError_t launch_resident_kc(const ResidentArgs<Real> &a, const ResidentPlan &p, bool map, bool strict,
+                                             cudaStream_t st)
+{
+    void (*fn)(const ResidentArgs<Real>);
+    if (map) fn = strict ? pdps_resident_kernel<Real, KC, true, true> : pdps_resident_kernel<Real, KC, true, false>;
+    else fn = strict ? pdps_resident_kernel<Real, KC, false, true> : pdps_resident_kernel<Real, KC, false, false>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(a.O * p.CS));
+    cfg.blockDim = dim3(RES_THREADS);
+    cfg.dynamicSmemBytes = p.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)p.CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, fn, a);
+}
+
+template <typename Real>
+static inline cudaError_t launch_resident(ResidentArgs<Real> a, size_t smem_optin, bool map, bool strict, cudaStream_t st)
+{
+    const ResidentPlan p = resident_plan<Real>(smem_optin, a.M, a.N);
+    if (!p.ok) return cudaErrorInvalidValue;
+    a.NC = p.NC;
+    if (p.KC == 1) return launch_resident_kc<Real, 1>(a, p, map, strict, st);
+    if (p.KC == 2) return launch_resident_kc<Real, 2>(a, p, map, strict, st);
+    return launch_resident_kc<Real, 4>(a, p, map, strict, st);
+}
 
 }  // namespace bpltv
