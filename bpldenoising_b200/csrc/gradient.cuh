@@ -20,6 +20,7 @@
 //
 // Mapping: one CTA per image "slot"; images are processed in waves of ≤ #SM slots.
 #pragma once
+#include <cstdlib>
 #include <string>
 
 #include "common.cuh"
@@ -274,91 +275,205 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_assemble_kernel(GradSlots w
 }
 
 // ---------------------------------------------------------------------------
-// K3: blocked right-looking banded Cholesky, in place on the band (global memory,
-// the working window of ≤ (2n+2+NB)² /2 entries lives in L1/L2).  Per block of NB
-// columns: (1) warp 0 factors the NB×NB diagonal block in shared memory (pivot
-// floor `guard`) and inverts it; (2) one thread per panel row forms
-// L21 = A21·L11⁻ᵀ; (3) all threads apply the rank-NB update to the trailing
-// envelope in 4×4 register tiles fed from shared memory.
+// K3: blocked right-looking banded Cholesky, in place on the band (global memory; the
+// working window of ≤ (2n+2+NB)²/2 entries lives in L1/L2).  Per block of NB columns:
+//   (1) panel: one thread per row forms L21 = A21·L11⁻ᵀ with the stored inverse of L11;
+//   (2) trailing update A22 -= L21·L21ᵀ on the envelope in 4×8 register tiles (band
+//       entries prefetched before the rank-NB loop, operands from shared memory);
+//   (3) LOOK-AHEAD: while warps 1..15 do (2), warp 0 updates only the next NB×NB
+//       diagonal block, factors it in registers (rows across lanes, columns through
+//       warp shuffles, pivot floor `guard`) and inverts it, so the serial part of the
+//       next step is already done when (2) finishes.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws, double guard)
+
+static __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc)
 {
-    extern __shared__ double sm[];
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gsrc));
+}
+
+// warp-level: S (NB×NB row-major, lower, identity padded) → L11 in S, 1/diag(L11) in dinv
+static __device__ __forceinline__ void diag_factor_warp(double *S, double *dinv, int nb, double guard, int lane,
+                                                        int &guarded)
+{
     constexpr int NB = GRAD_NB;
-    double *S = sm;               // NB*NB, row-major lower triangle → L11
-    double *Si = sm + NB * NB;    // NB*NB, L11⁻¹
-    double *P = sm + 2 * NB * NB; // NB × PR panel, c-major
+    double row[NB];
+    const int lr = lane < NB ? lane : NB - 1;
+#pragma unroll
+    for (int c = 0; c < NB; ++c) row[c] = S[lr * NB + c];
+    double dinv_own = 1.0;
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+        double d = __shfl_sync(0xffffffffu, row[c], c);
+        if (!(d > guard)) { d = guard; if (lane == 0 && c < nb) ++guarded; }
+        const double inv = rsqrt(d);
+        const double l = row[c] * inv;  // lane == c: d·rsqrt(d) = sqrt(d)
+        if (lane == c) { row[c] = d * inv; dinv_own = inv; }
+        else if (lane > c) row[c] = l;
+#pragma unroll
+        for (int c2 = c + 1; c2 < NB; ++c2) {
+            const double lc2 = __shfl_sync(0xffffffffu, l, c2);
+            if (lane >= c2) row[c2] = fma(-l, lc2, row[c2]);
+        }
+    }
+    if (lane < NB) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) S[lane * NB + c] = (c <= lane) ? row[c] : 0.0;
+        dinv[lane] = dinv_own;
+    }
+    __syncwarp();
+}
+
+// warp-level: L (NB×NB row-major lower, in shared memory) → Si = L⁻¹ (lane k = column k)
+static __device__ __forceinline__ void tri_inverse_warp(const double *L, double *Si, int lane)
+{
+    constexpr int NB = GRAD_NB;
+    double x[NB];
+#pragma unroll
+    for (int r = 0; r < NB; ++r) {
+        double s0 = (r == lane) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+        for (int c = 0; c < r; ++c) {
+            const double t = (c >= lane) ? L[r * NB + c] * x[c] : 0.0;
+            if (c & 1) s1 -= t; else s0 -= t;
+        }
+        x[r] = (r >= lane) ? (s0 + s1) / L[r * NB + r] : 0.0;
+    }
+    if (lane < NB) {
+#pragma unroll
+        for (int r = 0; r < NB; ++r) Si[r * NB + lane] = x[r];
+    }
+    __syncwarp();
+}
+
+// One 4(i)×8(j) tile of the trailing update A22 -= P Pᵀ.  FAST: every entry of the tile is
+// strictly inside the envelope (no predicates, affine addresses).  The tile's old band
+// entries are staged global→shared with cp.async while the rank-NB FMA loop runs.
+template <bool FAST>
+static __device__ __forceinline__ void tile_update(double *a22, int LDa, int nrows, const double *P, int PR, int i0,
+                                                   int j0, bool use_stage, double *stage, int nstage, int ut)
+{
+    constexpr int NB = GRAD_NB;
+    double *t00 = a22 + (size_t)j0 * LDa - j0 + i0;   // entry (x,y) at t00 + y·(LDa-1) + x
+    const size_t cstride = (size_t)LDa - 1;
+    if (use_stage) {
+#pragma unroll
+        for (int y = 0; y < 8; ++y)
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                if (FAST || (j0 + y < nrows && i0 + x >= j0 + y && i0 + x < nrows)) {
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + (size_t)(y * 4 + x) * nstage + ut);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(t00 + y * cstride + x));
+                }
+            }
+        asm volatile("cp.async.commit_group;");
+    }
+    double acc[4][8];
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 8; ++y) acc[x][y] = 0.0;
+#pragma unroll 2
+    for (int c = 0; c < NB; ++c) {
+        const double *pc = P + c * PR;
+        const double2 pi0 = *reinterpret_cast<const double2 *>(pc + i0);
+        const double2 pi1 = *reinterpret_cast<const double2 *>(pc + i0 + 2);
+        const double2 pj0 = *reinterpret_cast<const double2 *>(pc + j0);
+        const double2 pj1 = *reinterpret_cast<const double2 *>(pc + j0 + 2);
+        const double2 pj2 = *reinterpret_cast<const double2 *>(pc + j0 + 4);
+        const double2 pj3 = *reinterpret_cast<const double2 *>(pc + j0 + 6);
+        const double pi[4] = {pi0.x, pi0.y, pi1.x, pi1.y};
+        const double pj[8] = {pj0.x, pj0.y, pj1.x, pj1.y, pj2.x, pj2.y, pj3.x, pj3.y};
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 8; ++y) acc[x][y] = fma(pi[x], pj[y], acc[x][y]);
+    }
+    if (use_stage) asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+    for (int y = 0; y < 8; ++y)
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            if (FAST || (j0 + y < nrows && i0 + x >= j0 + y && i0 + x < nrows)) {
+                double *q = t00 + y * cstride + x;
+                const double old = use_stage ? stage[(size_t)(y * 4 + x) * nstage + ut] : *q;
+                *q = old - acc[x][y];
+            }
+        }
+}
+
+__global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws, double guard, int use_stage, int dbg)
+{
+    extern __shared__ __align__(16) double sm[];
+    constexpr int NB = GRAD_NB;
+    double *Sbuf = sm;                 // 2 × NB*NB: L11 of the current / next block
+    double *Dbuf = sm + 2 * NB * NB;   // 2 × NB: 1/diag of those; + NB*NB raw next diagonal block
+    double *Araw = sm + 3 * NB * NB;   // NB*NB: next diagonal block before its update (cp.async target)
+    double *P = sm + 4 * NB * NB;      // NB × PR panel, c-major
     const int slot = blockIdx.x;
     int *info = ws.info + 4 * slot;
     const int Nd = info[0], LDa = info[1];
-    const int PR = (LDa + 3) & ~3;  // rows of P, padded to the 4-row tiles
+    const int PR = (LDa + 7) & ~7;     // rows of P, padded to the 4×8 tiles
+    const int nstage = GRAD_THREADS - 32;                        // update threads
+    double *stage = P + (size_t)NB * ((ws.LD + 7) & ~7);         // 32 × nstage staging slots (if use_stage)
     double *ab = slot_ptr(ws.ab, ws.ab_stride, slot);
     const int *ext = slot_ptr(ws.ext, ws.ext_stride, slot);
     double *sinv = slot_ptr(ws.sinv, ws.sinv_stride, slot);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     int guarded = 0;
 
+    // prologue: first diagonal block straight from the band
+    if (warp == 0) {
+        const int nb0 = min(NB, Nd);
+        for (int idx = lane; idx < NB * NB; idx += 32) {
+            const int r = idx / NB, c = idx % NB;
+            double v = (r == c) ? 1.0 : 0.0;
+            if (r < nb0 && c <= r) v = ab[(size_t)c * LDa + (r - c)];
+            Sbuf[idx] = (c <= r) ? v : 0.0;
+        }
+        __syncwarp();
+        diag_factor_warp(Sbuf, Dbuf, nb0, guard, lane, guarded);
+    }
+    __syncthreads();
+
     for (int kb = 0, blk = 0; kb < Nd; kb += NB, ++blk) {
+        const int cur = blk & 1;
+        double *S = Sbuf + cur * NB * NB, *dinv = Dbuf + cur * NB;
+        double *Sn = Sbuf + (cur ^ 1) * NB * NB, *dinvn = Dbuf + (cur ^ 1) * NB;
         const int nb = min(NB, Nd - kb);
         const int hi = min(Nd - 1, ext[kb + nb - 1]);
         const int nrows = hi - (kb + nb) + 1;
-        // ---- (1) diagonal block -------------------------------------------------
-        for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
-            const int r = idx / NB, c = idx % NB;
-            double v = (r == c) ? 1.0 : 0.0;
-            if (r < nb && c <= r) v = ab[(size_t)(kb + c) * LDa + (r - c)];
-            S[idx] = v;
-            Si[idx] = 0.0;
-        }
-        __syncthreads();
-        if (warp == 0) {
-            for (int c = 0; c < nb; ++c) {
-                double d = S[c * NB + c];
-                if (!(d > guard)) { d = guard; if (lane == 0) ++guarded; }
-                const double sd = sqrt(d), inv = 1.0 / sd;
-                double l = 0.0;
-                if (lane == c) S[c * NB + c] = sd;
-                if (lane > c && lane < nb) { l = S[lane * NB + c] * inv; S[lane * NB + c] = l; }
-                __syncwarp();
-                if (lane > c && lane < nb)
-                    for (int c2 = c + 1; c2 <= lane; ++c2) S[lane * NB + c2] -= l * S[c2 * NB + c];
-                __syncwarp();
+        double *a22 = ab + (size_t)(kb + nb) * LDa;  // column (kb+nb+j) at a22 + j*LDa, entry i-j
+        // next diagonal block's current entries → shared memory (independent of this panel)
+        if (warp == 0 && nrows > 0) {
+            const int nb2 = min(NB, nrows);
+            for (int idx = lane; idx < NB * NB; idx += 32) {
+                const int r = idx / NB, c = idx % NB;
+                if (r < nb2 && c <= r) cp_async8(Araw + idx, a22 + (size_t)c * LDa + (r - c));
             }
-            // Si = L11⁻¹: lane = column k of the inverse
-            if (lane < NB) {
-                const int k = lane;
-                double x[NB];
-#pragma unroll
-                for (int r = 0; r < NB; ++r) {
-                    double s = (r == k) ? 1.0 : 0.0;
-#pragma unroll
-                    for (int c = 0; c < NB; ++c)
-                        if (c >= k && c < r) s -= S[r * NB + c] * x[c];
-                    x[r] = (r >= k) ? s / S[r * NB + r] : 0.0;
-                    Si[r * NB + k] = x[r];
-                }
-            }
+            asm volatile("cp.async.commit_group;");
         }
-        __syncthreads();
+        // ---- store L11; (1) panel rows by forward substitution: x L11ᵀ = a ---------------
         for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
             const int r = idx / NB, c = idx % NB;
             if (r < nb && c <= r) ab[(size_t)(kb + c) * LDa + (r - c)] = S[idx];
-            sinv[(size_t)blk * NB * NB + idx] = Si[idx];
         }
-        // ---- (2) panel rows: x = L11⁻¹ a  (row of A21 → row of L21) ---------------
         for (int r = tid; r < PR; r += blockDim.x) {
             double x[NB];
-            if (r < nrows) {
+            if (r < nrows && !(dbg & 4)) {
                 const int i = kb + nb + r;
                 double a[NB];
 #pragma unroll
                 for (int c = 0; c < NB; ++c) a[c] = (c < nb) ? ab[(size_t)(kb + c) * LDa + (i - kb - c)] : 0.0;
 #pragma unroll
                 for (int c = 0; c < NB; ++c) {
-                    double s = 0.0;
+                    double s0 = a[c], s1 = 0.0;
 #pragma unroll
-                    for (int c2 = 0; c2 <= c; ++c2) s += Si[c * NB + c2] * a[c2];
-                    x[c] = s;
+                    for (int c2 = 0; c2 < c; ++c2) {
+                        if (c2 & 1) s1 = fma(-S[c * NB + c2], x[c2], s1);
+                        else s0 = fma(-S[c * NB + c2], x[c2], s0);
+                    }
+                    x[c] = (s0 + s1) * dinv[c];
                 }
 #pragma unroll
                 for (int c = 0; c < NB; ++c)
@@ -370,102 +485,207 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws,
 #pragma unroll
             for (int c = 0; c < NB; ++c) P[c * PR + r] = x[c];
         }
+        if (warp == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        // ---- (3) trailing update: A22 -= L21 L21ᵀ on the lower envelope ---------
-        const int ntile = (nrows + 3) >> 2;
-        double *a22 = ab + (size_t)(kb + nb) * LDa;  // column (kb+nb+j) at a22 + j*LDa, entry i-j
-        for (int tj = warp; tj < ntile; tj += nwarps) {
-            for (int ti = tj + lane; ti < ntile; ti += 32) {
-                double acc[4][4];
+        if (nrows <= 0) break;
+        if (warp == 0) {
+            // ---- (3) look-ahead: next diagonal block = A22[0:NB,0:NB] - P Pᵀ, factor ----------
+            const int nb2 = min(NB, nrows);
+            for (int idx = lane; idx < NB * NB; idx += 32) {
+                const int r = idx / NB, c = idx % NB;
+                double v = (r == c) ? 1.0 : 0.0;
+                if (r < nb2 && c <= r) {
+                    double s0 = Araw[idx], s1 = 0.0;
 #pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) acc[x][y] = 0.0;
-#pragma unroll 4
-                for (int c = 0; c < NB; ++c) {
-                    const double2 pi0 = *reinterpret_cast<const double2 *>(P + c * PR + 4 * ti);
-                    const double2 pi1 = *reinterpret_cast<const double2 *>(P + c * PR + 4 * ti + 2);
-                    const double2 pj0 = *reinterpret_cast<const double2 *>(P + c * PR + 4 * tj);
-                    const double2 pj1 = *reinterpret_cast<const double2 *>(P + c * PR + 4 * tj + 2);
-                    const double pi[4] = {pi0.x, pi0.y, pi1.x, pi1.y};
-                    const double pj[4] = {pj0.x, pj0.y, pj1.x, pj1.y};
-#pragma unroll
-                    for (int x = 0; x < 4; ++x)
-#pragma unroll
-                        for (int y = 0; y < 4; ++y) acc[x][y] = fma(pi[x], pj[y], acc[x][y]);
-                }
-#pragma unroll
-                for (int y = 0; y < 4; ++y) {
-                    const int j = 4 * tj + y;
-                    if (j >= nrows) continue;
-                    double *col = a22 + (size_t)j * LDa - j;
-#pragma unroll
-                    for (int x = 0; x < 4; ++x) {
-                        const int i = 4 * ti + x;
-                        if (i >= j && i < nrows) col[i] -= acc[x][y];
+                    for (int k = 0; k < NB; k += 2) {
+                        s0 = fma(-P[k * PR + r], P[k * PR + c], s0);
+                        s1 = fma(-P[(k + 1) * PR + r], P[(k + 1) * PR + c], s1);
                     }
+                    v = s0 + s1;
                 }
+                Sn[idx] = (c <= r) ? v : 0.0;
+            }
+            __syncwarp();
+            if (!(dbg & 2)) diag_factor_warp(Sn, dinvn, nb2, guard, lane, guarded);
+        } else if (!(dbg & 1)) {
+            // ---- (2) trailing update on 4(i)×8(j) tiles, skipping the look-ahead block -------
+            // Work items are dealt round-robin to the 15 update warps so that every warp runs
+            // the same number of rounds (±1).  Interior rounds (tile rows 2tj+2 … nfull-1 of tile
+            // column tj: all 32 entries valid) take the predicate-free path; the tiles that
+            // cross the diagonal (rows 2tj, 2tj+1) or hang over the last row are gathered into
+            // separate boundary rounds, so no warp executes both paths for one item.
+            const int nti = (nrows + 3) >> 2, ntj = (nrows + 7) >> 3, nfull = nrows >> 2;
+            const int uw = warp - 1, nuw = nwarps - 1;
+            const int ut = tid - 32;               // index among the update threads
+            int item = 0;
+            for (int tj = 0; tj < ntj; ++tj) {
+                for (int tbase = 2 * tj + 2; tbase < nfull; tbase += 32, ++item) {
+                    if (item % nuw != uw) continue;
+                    const int ti = tbase + lane;
+                    if (ti < nfull && !(ti < 4 && tj < 2))   // (ti<4,tj<2): next diagonal block (warp 0)
+                        tile_update<true>(a22, LDa, nrows, P, PR, 4 * ti, 8 * tj, use_stage != 0, stage, nstage, ut);
+                }
+            }
+            const int nbound = 3 * ntj;            // (tj, kind): kind 0,1 → rows 2tj, 2tj+1; kind 2 → partial last row
+            for (int bbase = 0; bbase < nbound; bbase += 32, ++item) {
+                if (item % nuw != uw) continue;
+                const int b = bbase + lane;
+                if (b >= nbound) continue;
+                const int tj = b / 3, kind = b - 3 * tj;
+                int ti = 2 * tj + kind;
+                if (kind == 2) { ti = nti - 1; if (nti == nfull || ti <= 2 * tj + 1) continue; }
+                if (ti >= nti || (ti < 4 && tj < 2)) continue;
+                tile_update<false>(a22, LDa, nrows, P, PR, 4 * ti, 8 * tj, use_stage != 0, stage, nstage, ut);
             }
         }
         __syncthreads();
     }
     if (tid == 0) info[2] = guarded;
+    __syncthreads();
+    // ---- all L11⁻¹ (used by the triangular solves) in one parallel pass: warp per block ----
+    {
+        double *Lw = P + warp * 2 * NB * NB, *Siw = Lw + NB * NB;  // per-warp scratch (P is free now)
+        const int nblk = (Nd + NB - 1) / NB;
+        for (int blk = warp; blk < nblk; blk += nwarps) {
+            const int kb = blk * NB, nb = min(NB, Nd - kb);
+            for (int idx = lane; idx < NB * NB; idx += 32) {
+                const int r = idx / NB, c = idx % NB;
+                double v = (r == c) ? 1.0 : 0.0;
+                if (r < nb && c <= r) v = ab[(size_t)(kb + c) * LDa + (r - c)];
+                Lw[idx] = (c <= r) ? v : 0.0;
+            }
+            __syncwarp();
+            tri_inverse_warp(Lw, Siw, lane);
+            for (int idx = lane; idx < NB * NB; idx += 32) sinv[(size_t)blk * NB * NB + idx] = Siw[idx];
+            __syncwarp();
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
 // Banded triangular solves with the factor (device function, whole CTA).
-// z ← (L Lᵀ)⁻¹ z, using the stored inverses of the diagonal blocks.
+// z ← (L Lᵀ)⁻¹ z, using the stored inverses of the diagonal blocks.  `z` may point
+// to shared memory (the caller stages the vector there when it fits).  The factor is
+// read-only here, so its panel entries are loaded through the read-only path.
 // ---------------------------------------------------------------------------
-static __device__ void band_solve(const double *ab, const double *sinv, const int *ext, int Nd, int LDa, double *z,
-                                  double *sh /* ≥ 2*NB doubles */)
+constexpr int GRAD_BK = 10;  // backward solve: panel entries per lane held in registers (covers bands ≤ 320)
+
+static __device__ void band_solve(const double *__restrict__ ab, const double *__restrict__ sinv,
+                                  const unsigned short *nr /* rows below each block (shared memory) */, int Nd,
+                                  int LDa, double *z, double *sh /* ≥ 2*NB + 2*NB*NB doubles */)
 {
     constexpr int NB = GRAD_NB;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int nblk = (Nd + NB - 1) / NB;
-    double *ys = sh, *ts = sh + NB;
-    // forward: L y = z
-    for (int blk = 0; blk < nblk; ++blk) {
-        const int kb = blk * NB, nb = min(NB, Nd - kb);
-        const int hi = min(Nd - 1, ext[kb + nb - 1]);
-        const int nrows = hi - (kb + nb) + 1;
-        if (tid < NB) {
-            const double *Si = sinv + (size_t)blk * NB * NB;
-            double s = 0.0;
-            for (int c2 = 0; c2 <= tid && c2 < nb; ++c2) s += Si[tid * NB + c2] * z[kb + c2];
-            ys[tid] = s;
-        }
-        __syncthreads();
-        if (tid < nb) z[kb + tid] = ys[tid];
-        for (int r = tid; r < nrows; r += blockDim.x) {
-            const int i = kb + nb + r;
-            double s = 0.0;
-            for (int c = 0; c < nb; ++c) s = fma(ab[(size_t)(kb + c) * LDa + (i - kb - c)], ys[c], s);
-            z[i] -= s;
+    double *ys = sh, *ts = sh + NB, *sib = sh + 2 * NB;  // sib: 2 × NB*NB, inverse of the current / next block
+    auto block_rows = [&](int blk) { return (int)nr[blk]; };
+    auto fetch_si = [&](int blk, int buf) {   // everything the dependent part needs, one block ahead
+        if (tid < NB * NB) cp_async8(sib + buf * NB * NB + tid, sinv + (size_t)blk * NB * NB + tid);
+        asm volatile("cp.async.commit_group;");
+    };
+    // ---- forward: L y = z.  Thread r owns panel row r of the block ----------------------
+    {
+        double lcur[NB];
+        auto fetch_l = [&](int blk, int nrows, double(&l)[NB]) {
+            const int kb = blk * NB, nb = min(NB, Nd - kb);
+#pragma unroll
+            for (int c = 0; c < NB; ++c)
+                l[c] = (tid < nrows && c < nb) ? __ldg(ab + (size_t)(kb + c) * LDa + (nb + tid - c)) : 0.0;
+        };
+        int nrows = nblk > 0 ? block_rows(0) : 0, nrows_n = 0;
+        if (nblk > 0) { fetch_l(0, nrows, lcur); fetch_si(0, 0); }
+        for (int blk = 0; blk < nblk; ++blk) {
+            const int kb = blk * NB, nb = min(NB, Nd - kb);
+            const double *Si = sib + (blk & 1) * NB * NB;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();                       // Si(blk) staged; previous step's z updates visible
+            if (blk + 1 < nblk) { nrows_n = block_rows(blk + 1); fetch_si(blk + 1, (blk + 1) & 1); }
+            if (tid < NB) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int c2 = 0; c2 < NB; c2 += 2) {
+                    if (c2 <= tid && c2 < nb) s0 = fma(Si[tid * NB + c2], z[kb + c2], s0);
+                    if (c2 + 1 <= tid && c2 + 1 < nb) s1 = fma(Si[tid * NB + c2 + 1], z[kb + c2 + 1], s1);
+                }
+                ys[tid] = s0 + s1;
+            }
+            __syncthreads();
+            if (tid < nb) z[kb + tid] = ys[tid];
+            if (tid < nrows) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int c = 0; c < NB; c += 2) { s0 = fma(lcur[c], ys[c], s0); s1 = fma(lcur[c + 1], ys[c + 1], s1); }
+                z[kb + nb + tid] -= s0 + s1;
+            }
+            // rows beyond blockDim.x (only when the band is wider than the CTA)
+            for (int r = tid + blockDim.x; r < nrows; r += blockDim.x) {
+                double s = 0.0;
+                for (int c = 0; c < nb; ++c) s = fma(__ldg(ab + (size_t)(kb + c) * LDa + (nb + r - c)), ys[c], s);
+                z[kb + nb + r] -= s;
+            }
+            // this row's factor entries for the next block: issued now, consumed two barriers later
+            if (blk + 1 < nblk) fetch_l(blk + 1, nrows_n, lcur);
+            nrows = nrows_n;
         }
         __syncthreads();
     }
-    // backward: Lᵀ x = y
-    for (int blk = nblk - 1; blk >= 0; --blk) {
-        const int kb = blk * NB, nb = min(NB, Nd - kb);
-        const int hi = min(Nd - 1, ext[kb + nb - 1]);
-        const int nrows = hi - (kb + nb) + 1;
-        for (int c = warp; c < nb; c += nwarps) {
-            const double *col = ab + (size_t)(kb + c) * LDa + (nb - c);  // entry of row kb+nb+r at col[r]
-            double s = 0.0;
-            for (int r = lane; r < nrows; r += 32) s = fma(col[r], z[kb + nb + r], s);
-            s = warp_sum(s);
-            if (lane == 0) ts[c] = s;
+    // ---- backward: Lᵀ x = y.  One warp per column of the block; lanes stride the rows ----
+    {
+        double lb[GRAD_BK], lbn[GRAD_BK];
+        auto fetch_lb = [&](int blk, int nrows, double(&l)[GRAD_BK]) {
+            const int kb = blk * NB, nb = min(NB, Nd - kb);
+            const double *col = ab + (size_t)(kb + warp) * LDa + (nb - warp);
+#pragma unroll
+            for (int k = 0; k < GRAD_BK; ++k) {
+                const int r = lane + 32 * k;
+                l[k] = (warp < nb && r < nrows) ? __ldg(col + r) : 0.0;
+            }
+        };
+        int nrows = nblk > 0 ? block_rows(nblk - 1) : 0, nrows_n = 0;
+        if (nblk > 0) { fetch_lb(nblk - 1, nrows, lb); fetch_si(nblk - 1, (nblk - 1) & 1); }
+        for (int blk = nblk - 1; blk >= 0; --blk) {
+            const int kb = blk * NB, nb = min(NB, Nd - kb);
+            const double *Si = sib + (blk & 1) * NB * NB;
+            if (blk > 0) { nrows_n = block_rows(blk - 1); fetch_lb(blk - 1, nrows_n, lbn); }
+            if (warp < nb) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int k = 0; k < GRAD_BK; k += 2) {
+                    const int r = lane + 32 * k;
+                    if (r < nrows) s0 = fma(lb[k], z[kb + nb + r], s0);
+                    if (r + 32 < nrows) s1 = fma(lb[k + 1], z[kb + nb + r + 32], s1);
+                }
+                const double *col = ab + (size_t)(kb + warp) * LDa + (nb - warp);
+                for (int r = lane + 32 * GRAD_BK; r < nrows; r += 32) s0 = fma(__ldg(col + r), z[kb + nb + r], s0);
+                const double s = warp_sum(s0 + s1);
+                if (lane == 0) ts[warp] = s;
+            }
+            for (int c = warp + nwarps; c < nb; c += nwarps) {  // only if the CTA has fewer than NB warps
+                const double *col = ab + (size_t)(kb + c) * LDa + (nb - c);
+                double s = 0.0;
+                for (int r = lane; r < nrows; r += 32) s = fma(__ldg(col + r), z[kb + nb + r], s);
+                s = warp_sum(s);
+                if (lane == 0) ts[c] = s;
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();                       // ts complete, Si(blk) staged
+            if (blk > 0) fetch_si(blk - 1, (blk - 1) & 1);
+            if (tid < NB) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int c2 = 0; c2 < NB; c2 += 2) {
+                    if (c2 >= tid && c2 < nb) s0 = fma(Si[c2 * NB + tid], z[kb + c2] - ts[c2], s0);
+                    if (c2 + 1 >= tid && c2 + 1 < nb) s1 = fma(Si[(c2 + 1) * NB + tid], z[kb + c2 + 1] - ts[c2 + 1], s1);
+                }
+                ys[tid] = s0 + s1;
+            }
+            __syncthreads();
+            if (tid < nb) z[kb + tid] = ys[tid];
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < GRAD_BK; ++k) lb[k] = lbn[k];
+            nrows = nrows_n;
         }
-        __syncthreads();
-        if (tid < NB) {
-            const double *Si = sinv + (size_t)blk * NB * NB;
-            double s = 0.0;
-            for (int c2 = tid; c2 < nb; ++c2) s += Si[c2 * NB + tid] * (z[kb + c2] - ts[c2]);
-            ys[tid] = s;
-        }
-        __syncthreads();
-        if (tid < nb) z[kb + tid] = ys[tid];
-        __syncthreads();
     }
 }
 
@@ -517,9 +737,13 @@ static __device__ void dual_primal(const GradSlots &ws, int slot, const double *
 // afterwards in a fixed order (grad_reduce_kernel).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(GRAD_THREADS) grad_solve_kernel(GradSlots ws, GradVariant gv, double *out_img,
-                                                                  double *relres_img, int img0)
+                                                                  double *relres_img, int img0, int zs_cap)
 {
-    __shared__ double sh[64];
+    extern __shared__ __align__(16) unsigned char dyn[];
+    // [per-block row counts (nblkMax u16, 16-byte padded)] [zs_cap doubles: the solve vector, if it fits]
+    unsigned short *s_nr = reinterpret_cast<unsigned short *>(dyn);
+    double *zs = reinterpret_cast<double *>(dyn + (((size_t)ws.nblkMax * 2 + 15) & ~(size_t)15));
+    __shared__ double sh[2 * GRAD_NB + 2 * GRAD_NB * GRAD_NB + 32];
     const int slot = blockIdx.x;
     const int n = ws.n, N = ws.N;
     const int *info = ws.info + 4 * slot;
@@ -542,7 +766,28 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_solve_kernel(GradSlots ws, 
     __shared__ double s_bn, s_rn;
     if (tid == 0) s_bn = bnorm2;
     __syncthreads();
-    band_solve(ab, sinv, ext, Nd, LDa, zeta, sh);
+    {
+        const int nblk = (Nd + GRAD_NB - 1) / GRAD_NB;
+        for (int blk = tid; blk < nblk; blk += blockDim.x) {
+            const int kb = blk * GRAD_NB, nb = min(GRAD_NB, Nd - kb);
+            s_nr[blk] = (unsigned short)(min(Nd - 1, ext[kb + nb - 1]) - (kb + nb) + 1);
+        }
+        __syncthreads();
+    }
+    const bool in_smem = Nd <= zs_cap;
+    // solve `vec` in place; staged through shared memory when it fits
+    auto solve = [&](double *vec) {
+        if (in_smem) {
+            for (int a = tid; a < Nd; a += blockDim.x) zs[a] = vec[a];
+            __syncthreads();
+            band_solve(ab, sinv, s_nr, Nd, LDa, zs, sh);
+            for (int a = tid; a < Nd; a += blockDim.x) vec[a] = zs[a];
+            __syncthreads();
+        } else {
+            band_solve(ab, sinv, s_nr, Nd, LDa, vec, sh);
+        }
+    };
+    solve(zeta);
     double relres = 0.0;
     for (int it = 0; it <= gv.refine; ++it) {
         dual_primal(ws, slot, zeta, p);
@@ -568,7 +813,7 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_solve_kernel(GradSlots ws, 
         __syncthreads();
         relres = (s_bn > 0.0) ? sqrt(s_rn / s_bn) : 0.0;
         if (it == gv.refine) break;
-        band_solve(ab, sinv, ext, Nd, LDa, work, sh);
+        solve(work);
         for (int a = tid; a < Nd; a += blockDim.x) zeta[a] += work[a];
         __syncthreads();
     }
@@ -681,7 +926,11 @@ static int run_gradient(GradWork &w, const GradProblem<Real> &gp, int sm_count, 
     ws.ab_stride = ((size_t)ws.NdMax * ws.LD + 1) & ~(size_t)1;
     ws.off_stride = (size_t)N + 2;
     ws.ext_stride = (size_t)ws.NdMax;
-    const size_t smem = (size_t)(2 * GRAD_NB * GRAD_NB + GRAD_NB * ((ws.LD + 3) & ~3)) * sizeof(double);
+    size_t smem = (size_t)(4 * GRAD_NB * GRAD_NB + GRAD_NB * ((ws.LD + 7) & ~7)) * sizeof(double);
+    const size_t stage_bytes = (size_t)32 * (GRAD_THREADS - 32) * sizeof(double);
+    const int use_stage = smem + stage_bytes <= smem_optin ? 1 : 0;
+    if (use_stage) smem += stage_bytes;
+    smem = std::max<size_t>(smem, (size_t)(4 * GRAD_NB * GRAD_NB + 32 * GRAD_NB * GRAD_NB) * sizeof(double));  // inverse pass scratch
     if (smem > smem_optin) return grad_fail(w, -1, "image too large for the banded Cholesky panel in shared memory");
 
     // slots: one CTA per image, at most one per SM, bounded by a workspace budget
@@ -736,17 +985,21 @@ static int run_gradient(GradWork &w, const GradProblem<Real> &gp, int sm_count, 
     if (gv.regularised && gv.patch) cscale = 1.0;  // refined below from the map's max on the host side if needed
     const double guard = gv.guard_rel * cscale;
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(grad_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
-        attr_set = true;
-    }
+    cudaFuncSetAttribute(grad_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // solve vector in shared memory when it fits next to the static arrays
+    const size_t nr_bytes = ((size_t)ws.nblkMax * 2 + 15) & ~(size_t)15;
+    if (nr_bytes + 8192 + 4096 > smem_optin) return grad_fail(w, -1, "image too large for the solve kernel's block table");
+    const size_t zs_only = std::min<size_t>((size_t)ws.NdMax * 8, smem_optin - 8192 - nr_bytes);
+    const int zs_cap = (int)(zs_only / 8);
+    const size_t zs_bytes = nr_bytes + zs_only;
+    cudaFuncSetAttribute(grad_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs_bytes);
     for (int img0 = 0; img0 < gp.O; img0 += slots) {
         const int cnt = std::min(slots, gp.O - img0);
         grad_classify_kernel<Real><<<cnt, GRAD_THREADS, 0, st>>>(ws, gv, gp.u, gp.ubar, gp.alpha_map, img0);
         grad_assemble_kernel<<<cnt, GRAD_THREADS, 0, st>>>(ws);
-        grad_factor_kernel<<<cnt, GRAD_THREADS, smem, st>>>(ws, guard);
-        grad_solve_kernel<<<cnt, GRAD_THREADS, 0, st>>>(ws, gv, (double *)w.out_img, (double *)w.relres, img0);
+        grad_factor_kernel<<<cnt, GRAD_THREADS, smem, st>>>(ws, guard, use_stage, getenv("BPLTV_GRAD_DBG") ? atoi(getenv("BPLTV_GRAD_DBG")) : 0);
+        grad_solve_kernel<<<cnt, GRAD_THREADS, zs_bytes, st>>>(ws, gv, (double *)w.out_img, (double *)w.relres, img0,
+                                                                zs_cap);
         *launches += 4;
     }
     grad_reduce_kernel<<<1, std::max(32, (ng + 31) / 32 * 32), 0, st>>>((double *)w.out_img, (double *)w.relres, gp.O,
