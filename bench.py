@@ -46,7 +46,7 @@ def _config(n_gpus):
         "workload": "BASELINE configs[3]: synthetic 64x512x512 noisy images per GPU, scalar lambda=0.1, "
                     "1000 accelerated PDPS iterations (tau0=5, sigma0=0.99/5) + loss 0.5||u-u_true||^2",
         "images_per_gpu": O_PER_GPU, "image": [M, N], "iterations": ITERS, "lambda": LAM,
-        "arith": "strict (one IEEE op per reference operator; bit-identical to the oracle)",
+        "arith": "strict (one IEEE op per reference operator; bit-identical to the oracle) unless --arith fast",
         "l2": "working set 7 planes x 128 MiB = 896 MiB per GPU >> 126 MB L2 (no flush needed)",
         "parallelism": f"images sharded over {n_gpus} GPU(s), one all-reduce of the loss per step",
     }
@@ -128,6 +128,13 @@ def ncu_traffic():
     return None
 
 
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference_step(orc, f_sample, iters, threads):
     t0 = time.perf_counter()
     orc.pdps(f_sample, LAM, maxiter=iters, nthreads=threads)
@@ -142,7 +149,7 @@ def run_reference(args):
     from oracle import oracle as orc
     orc.build()
     from bpldenoising_b200.datasets import synthetic_dataset
-    cores = orc.lib().oracle_max_threads()
+    cores = host_threads()   # torchrun exports OMP_NUM_THREADS=1: ask for the cores explicitly
     n_img = max(1, min(cores, O_PER_GPU))
     iters = 100
     _, f = synthetic_dataset(M, N, n_img, seed=20240601)
@@ -208,7 +215,14 @@ def main():
     d_truth = torch.from_numpy(np.ascontiguousarray(truth.transpose(2, 1, 0))).to(dev)
     d_noisy = torch.from_numpy(np.ascontiguousarray(noisy.transpose(2, 1, 0))).to(dev)
     d_costgrad = torch.zeros(2, dtype=torch.float64, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    # ONE explicit stream carries the kernels, the timing events and the NCCL all-reduce.  (The
+    # legacy default stream has handle 0, which the C ABI reads as "use the context's own stream":
+    # events recorded on it would not see the kernels.)
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
     ctx.set_dataset_device(d_truth.data_ptr(), d_noisy.data_ptr(), M, N, O_PER_GPU, stream)
 
     def step():
@@ -226,10 +240,10 @@ def main():
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
-        e0.record()
+        e0.record(tstream)
         for _ in range(K):
             step()
-        e1.record()
+        e1.record(tstream)
         torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -242,7 +256,23 @@ def main():
     ms_per_step = ms_total / K
     pix_iter_per_step = float(M) * N * O_PER_GPU * ITERS
     value = pix_iter_per_step * world / (ms_per_step * 1e-3) / 1e9
-    loss = float(d_costgrad[0].item())
+    loss = float(d_costgrad[0].item())   # after the all-reduce: the loss of the whole job
+
+    # ---- the same leg in the fast arithmetic mode (FMA, rsqrt; within 1e-10 of the oracle) ----
+    value_other = None
+    if not args.no_extras:
+        other = bp.FAST if arith == bp.STRICT else bp.STRICT
+        eo2 = bp.eval_opts(bp.pdps_opts(maxiter=ITERS, arith=other), force_branch=3)
+        for _ in range(2):
+            ctx.learn_eval_device(LAM, 0.1, d_costgrad.data_ptr(), eo2, stream=stream)
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(tstream)
+        for _ in range(3):
+            ctx.learn_eval_device(LAM, 0.1, d_costgrad.data_ptr(), eo2, stream=stream)
+        f1.record(tstream)
+        torch.cuda.synchronize()
+        value_other = pix_iter_per_step / (f0.elapsed_time(f1) / 3 * 1e-3) / 1e9  # per GPU
 
     # ---- roofline of the dominant kernel (pdps_march: one launch per iteration) -----
     peak, peak_src = hbm_peak()
@@ -290,13 +320,16 @@ def main():
         "dtype": "f64", "data": "synthetic", "config": _config(world), "roofline": roofline, "e2e": e2e,
         "gpu_launches": int(launches_per_step * K), "loss": loss,
     }
+    if value_other is not None:
+        line["per_gpu_value_other_arith"] = {"arith": "fast" if arith == bp.STRICT else "strict", "value": value_other,
+                                              "unit": UNIT, "frac_of_hbm_peak": value_other * 1e9 * ALG_BYTES_PER_PIXEL_ITER_F64 / 1e9 / peak}
 
     if rank == 0:
         line["clocks"] = clk.summary()
         # ---- CPU baseline: the oracle port on this box's host cores (bounded sample) ----
         from oracle import oracle as orc
         orc.build()
-        cores = orc.lib().oracle_max_threads()
+        cores = host_threads()
         n_img = max(1, min(cores, O_PER_GPU))
         f_s = np.asfortranarray(noisy[:, :, np.arange(n_img) % O_PER_GPU])
         iters_s = 200

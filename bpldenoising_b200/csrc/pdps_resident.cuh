@@ -39,6 +39,22 @@ struct ResidentArgs {
     Real alpha_s;
 };
 
+template <typename Real> struct Vec2T;
+template <> struct Vec2T<double> { typedef double2 type; };
+template <> struct Vec2T<float> { typedef float2 type; };
+template <typename Real>
+static __device__ __forceinline__ void ld2(const Real *p, Real &a, Real &b)
+{
+    const typename Vec2T<Real>::type v = *reinterpret_cast<const typename Vec2T<Real>::type *>(p);
+    a = v.x; b = v.y;
+}
+template <typename Real>
+static __device__ __forceinline__ void st2(Real *p, Real a, Real b)
+{
+    typename Vec2T<Real>::type v; v.x = a; v.y = b;
+    *reinterpret_cast<typename Vec2T<Real>::type *>(p) = v;
+}
+
 // KC = column slots per thread (each slot = 2 consecutive rows of one column)
 template <typename Real, int KC, bool MAP, bool STRICT>
 __global__ void __launch_bounds__(RES_THREADS, 1) pdps_resident_kernel(const ResidentArgs<Real> a)
@@ -69,13 +85,15 @@ __global__ void __launch_bounds__(RES_THREADS, 1) pdps_resident_kernel(const Res
     const int c_begin = rank * NC;
     const size_t img = (size_t)o * M * N;
 
+    const int lane = threadIdx.x & 31;
     Real x[KC][2], f[KC][2], al[KC][2];
-    bool ok[KC];
+    bool ok[KC], okw[KC];
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
         const int c = cgrp + CG * k;        // local column
         const int jg = c_begin + c;         // image column
         ok[k] = t_ok && c < NC && jg < N;
+        okw[k] = __any_sync(0xffffffffu, ok[k]);
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
             f[k][v] = 0; x[k][v] = 0; al[k][v] = a.alpha_s;
@@ -95,33 +113,43 @@ __global__ void __launch_bounds__(RES_THREADS, 1) pdps_resident_kernel(const Res
         // ---- phase A: x ← prox, x̄ ← over-relaxation ----------------------------------
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
-            if (!ok[k]) continue;
+            if (!okw[k]) continue;              // warp-uniform: whole warp in or out (shuffles below)
             const int c = cgrp + CG * k;
             const Real *py1 = y1p + (size_t)c * M + r0;
             const Real *py2 = y2p + (size_t)(c + 1) * M + r0;  // own column (slot c+1), left = slot c
-            y1o[k][0] = py1[0]; y1o[k][1] = py1[1];
-            y2o[k][0] = py2[0]; y2o[k][1] = py2[1];
-            const Real up = r0 > 0 ? py1[-1] : (Real)0;
-            const Real l0 = py2[-M], l1 = py2[-M + 1];
+            const bool valid = ok[k];           // lanes of a mixed warp (M < 64) may sit on a dead slot
+            Real l0 = 0, l1 = 0;
+            y1o[k][0] = y1o[k][1] = y2o[k][0] = y2o[k][1] = 0;
+            if (valid) {
+                ld2(py1, y1o[k][0], y1o[k][1]); // one 2-element vector access per plane: conflict-free
+                ld2(py2, y2o[k][0], y2o[k][1]);
+                ld2(py2 - M, l0, l1);
+            }
+            // row above: the previous lane's second row (same column); lane 0 reads the plane
+            Real up = __shfl_up_sync(0xffffffffu, y1o[k][1], 1);
+            if (valid && lane == 0 && r0 > 0) up = py1[-1];
+            if (r0 == 0) up = (Real)0;
             const Real xn0 = primal_update<Real, STRICT>(x[k][0], f[k][0], up, y1o[k][0], l0, y2o[k][0], sc, xb[k][0]);
             const Real xn1 = primal_update<Real, STRICT>(x[k][1], f[k][1], y1o[k][0], y1o[k][1], l1, y2o[k][1], sc, xb[k][1]);
             x[k][0] = xn0; x[k][1] = xn1;
-            Real *pxb = xbp + (size_t)c * M + r0;
-            pxb[0] = xb[k][0]; pxb[1] = xb[k][1];
-            if (c == 0 && xb_left) {  // first local column: the left CTA needs it as x̄(:, its NC)
-                Real *q = xb_left + (size_t)NC * M + r0;
-                q[0] = xb[k][0]; q[1] = xb[k][1];
+            if (valid) {
+                st2(xbp + (size_t)c * M + r0, xb[k][0], xb[k][1]);
+                if (c == 0 && xb_left)    // first local column: the left CTA needs it as x̄(:, its NC)
+                    st2(xb_left + (size_t)NC * M + r0, xb[k][0], xb[k][1]);
             }
         }
         cluster.sync();
         // ---- phase B: y ← P_λ(y + σ∇x̄) ---------------------------------------------------
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
-            if (!ok[k]) continue;
+            if (!okw[k]) continue;
             const int c = cgrp + CG * k;
             const int jg = c_begin + c;
             const Real *pxb = xbp + (size_t)c * M + r0;
-            const Real below = (r0 + 2 < M) ? pxb[2] : (Real)0;
+            // row below: the next lane's first row (same column); lane 31 reads the plane
+            Real below = __shfl_down_sync(0xffffffffu, xb[k][0], 1);
+            const bool valid = ok[k];
+            if (valid && lane == 31 && r0 + 2 < M) below = pxb[2];
             Real d1_0, d1_1, d2_0 = 0, d2_1 = 0;
             if (STRICT) {
                 d1_0 = StrictOps<Real>::sub(xb[k][1], xb[k][0]);
@@ -130,8 +158,9 @@ __global__ void __launch_bounds__(RES_THREADS, 1) pdps_resident_kernel(const Res
                 d1_0 = xb[k][1] - xb[k][0];
                 d1_1 = (r0 + 2 < M) ? below - xb[k][1] : (Real)0;
             }
-            if (jg + 1 < N) {
-                const Real rt0 = pxb[M], rt1 = pxb[M + 1];  // column c+1 (slot NC = pushed halo)
+            if (valid && jg + 1 < N) {
+                Real rt0, rt1;
+                ld2(pxb + M, rt0, rt1);                     // column c+1 (slot NC = pushed halo)
                 if (STRICT) { d2_0 = StrictOps<Real>::sub(rt0, xb[k][0]); d2_1 = StrictOps<Real>::sub(rt1, xb[k][1]); }
                 else { d2_0 = rt0 - xb[k][0]; d2_1 = rt1 - xb[k][1]; }
             }
@@ -140,11 +169,11 @@ __global__ void __launch_bounds__(RES_THREADS, 1) pdps_resident_kernel(const Res
             dual_update<Real, STRICT, false>(w1, w2, d1_1, d2_1, al[k][1], (Real)0, sc);
             Real *py1 = y1p + (size_t)c * M + r0;
             Real *py2 = y2p + (size_t)(c + 1) * M + r0;
-            py1[0] = v1; py1[1] = w1;
-            py2[0] = v2; py2[1] = w2;
-            if (c == NC - 1 && y2_right) {  // last local column: the right CTA needs it as y2(:, c0-1)
-                Real *q = y2_right + r0;
-                q[0] = v2; q[1] = w2;
+            if (valid) {
+                st2(py1, v1, w1);
+                st2(py2, v2, w2);
+                if (c == NC - 1 && y2_right)    // last local column: the right CTA needs it as y2(:, c0-1)
+                    st2(y2_right + r0, v2, w2);
             }
         }
         cluster.sync();

@@ -108,3 +108,38 @@ def test_gradient_errors(bp, ctx, datasets):
     with pytest.raises(bp.BpltvError) as ei:
         ctx.learn_eval(0.1, 0.1)
     assert "square" in str(ei.value)        # reference precondition (:102)
+
+
+def test_gradient_256_config5_shape(bp, ctx, oracle):
+    # BASELINE config 5 image size (256×256 synthetic): band solver with the solve vector in
+    # global memory (it no longer fits in shared memory), both branches, against the literal solve
+    t, f = bp.synthetic_dataset(256, 256, 2, seed=20240602)
+    u = ctx.denoise(f, 0.1, bp.pdps_opts(maxiter=1500))
+    assert np.array_equal(u, oracle.pdps(f, 0.1, maxiter=1500))
+    ctx.set_dataset((t, f))
+    g = ctx.gradient(0.1, u, regularised=True)
+    lit = sum(oracle.gradient_reg_scalar(0.1, u[:, :, i], t[:, :, i], refine=3) for i in range(2))
+    assert _rel(g, lit) <= 1e-9, (g, lit)
+    g = ctx.gradient(0.1, u, regularised=False)
+    lit = sum(oracle.gradient_scalar(0.1, u[:, :, i], t[:, :, i], refine=4) for i in range(2))
+    assert _rel(g, lit) <= 1e-6, (g, lit)
+
+
+def test_single_process_multi_device_context(bp, oracle, datasets):
+    """bpltv_create with several device ids shards the images inside the library and sums
+    [cost, grad] on the host (INTEGRATION.md §2 set_devices!).  Needs ≥ 2 GPUs."""
+    import ctypes
+    cuda = ctypes.CDLL("libcuda.so.1")
+    n = ctypes.c_int(0)
+    cuda.cuInit(0); cuda.cuDeviceGetCount(ctypes.byref(n))
+    if n.value < 2:
+        pytest.skip("needs 2 GPUs")
+    t, f = (a[:, :, :5].copy(order="F") for a in datasets["faces_train_128_10"])
+    with bp.Context([0], 64) as c1, bp.Context([0, 1], 64) as c2:
+        c1.set_dataset((t, f)); c2.set_dataset((t, f))
+        eo = bp.eval_opts(bp.pdps_opts(maxiter=600))
+        u1, cost1, g1 = c1.learn_eval(0.07, 0.1, eo)
+        u2, cost2, g2 = c2.learn_eval(0.07, 0.1, eo)
+        assert np.array_equal(u1, u2)
+        assert abs(cost1 - cost2) <= 1e-13 * cost1 and abs(g1 - g2) <= 1e-12 * abs(g1)
+        assert c2.stats()["n_devices"] == 2
