@@ -371,6 +371,14 @@ def learn_eval_extras(bp):
             st = c.stats()
             out[name] = {"ms": min(ts), "ms_pdps": st["ms_pdps"], "ms_gradient": st["ms_gradient"],
                          "cost": cost, "grad": np.asarray(g).ravel().tolist()}
+            # full bilevel learn run (1 + ≤20 evaluations) through the host restatement of the
+            # reference's trust-region driver (bpldenoising_b200/trbox.py ← TRBox.jl:192-273)
+            from bpldenoising_b200 import trbox
+            res = trbox.bilevel_learn(data, lambda xx, ds, D: bp.tv_op_learning_function(xx, ds, D, ctx=c), x,
+                                      dict(Delta0=Delta))
+            out[name]["learn_run"] = {"seconds": res.seconds, "evaluations": res.evaluations,
+                                      "final_cost": res.log[-1].function_value,
+                                      "x": np.asarray(res.x).ravel().tolist()}
     return out
 
 

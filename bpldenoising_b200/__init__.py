@@ -15,6 +15,7 @@ from .learning import (Context, L2CostFunction, TVDenoise, default_context, deno
                        gradient, gradient_reg, pdps_opts, tv_op_learning_function)
 from .datasets import synthetic_dataset  # noqa: E402
 from .parallel import shard_range  # noqa: E402
+from . import trbox  # noqa: E402,F401
 
 __all__ = [
     "BpltvError", "Context", "L2CostFunction", "TVDenoise", "default_context", "denoise",

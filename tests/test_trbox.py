@@ -1,0 +1,83 @@
+"""Host restatement of the trust-region driver (bpldenoising_b200/trbox.py ←
+/root/reference/src/TRBox.jl): the scalar control flow and its quirks, on cheap synthetic
+learning functions (no GPU), plus one end-to-end learn run on the GPU."""
+import numpy as np
+import pytest
+
+from bpldenoising_b200 import trbox
+
+
+def quad(x0):
+    def lf(x, ds, Delta):
+        x = np.asarray(x, dtype=np.float64)
+        f = float(np.sum((x - x0) ** 2))
+        g = 2 * (x - x0)
+        return np.zeros((2, 2, 1)), f, (float(g) if g.ndim == 0 else g)
+    return lf
+
+
+def test_bounds_and_steps():
+    lb, ub = trbox.get_bounds(0.05, 0.1)                      # TRBox.jl:160-164
+    assert lb == max(-0.1, trbox.EPS - 0.05) and ub == 0.1
+    assert trbox.in_bounds(lb, 0.1, 0.1) and not trbox.in_bounds(lb, 0.1, -0.06)
+    # QUIRK (:149-152): element-wise max of both ratios
+    assert trbox.step_to_bound(-1.0, -0.05, 0.1) == 0.05 and trbox.step_to_bound(1.0, -0.05, 0.1) == 0.1
+    # scalar dogleg with B = 0.1: gx > 0 → Cauchy step leaves the box → scaled to the bound,
+    # limited by positivity x + p ≥ eps
+    assert trbox.dogleg_box(0.5, 300.0, 0.1, 0.1) == pytest.approx(-0.1)
+    assert trbox.dogleg_box(0.05, 300.0, 0.1, 0.1) == pytest.approx(-(0.05 - trbox.EPS))
+    assert trbox.dogleg_box(0.5, -300.0, 0.1, 0.1) == pytest.approx(0.1)
+    # QUIRK (:63): tiny gradient → the "Newton" step +gx/B is taken as is (uphill)
+    assert trbox.dogleg_box(0.5, 1e-3, 0.1, 0.1) == pytest.approx(1e-2)
+    assert trbox.pred(0.1, -0.1, 300.0) == pytest.approx(30.0 - 0.5 * 0.1 * 0.01)
+    # QUIRK (:181-186): the scalar BFGS update is lost
+    assert trbox.update_bfgs(0.1, 5.0, 0.2) == 0.1
+
+
+def test_scalar_learn_on_a_quadratic():
+    res = trbox.bilevel_learn(None, quad(0.3), 0.1, dict(maxiter=40, tol=1e-9))
+    assert res.evaluations == len(res.log) + 1
+    assert abs(res.x - 0.3) < 0.02
+    fs = [e.function_value for e in res.log]
+    assert all(b <= a + 1e-15 for a, b in zip(fs, fs[1:]))    # only ρ > 0 steps are accepted
+    # radius: grows ×1.9 on very successful full steps, shrinks ×0.25 on failures
+    r = [0.1] + [e.radius for e in res.log]
+    ratios = {round(b / a, 6) for a, b in zip(r, r[1:])}
+    assert ratios <= {1.0, 1.9, 0.25, round(0.25 * 0.25, 6), round(1.9 * 0.25, 6)}
+    # stop rule: a logged iteration saw Δ < tol, or maxiter was reached
+    res2 = trbox.bilevel_learn(None, quad(0.3), 0.1, dict(maxiter=200, tol=1e-2))
+    assert res2.log[-1].radius < 1e-2 and len(res2.log) < 200
+
+
+def test_lbfgs_operator_is_spd_and_secant():
+    rng = np.random.default_rng(0)
+    B = trbox.LBFGSOperator(4)
+    A = np.diag([1.0, 2.0, 5.0, 10.0])
+    for _ in range(7):
+        s = rng.standard_normal(4)
+        B.push(s, A @ s)
+    D = B.dense()
+    assert np.allclose(D, D.T, atol=1e-10) and np.all(np.linalg.eigvalsh(D) > 0)
+    assert np.allclose(B.mul(B.s[-1]), B.y[-1], rtol=1e-10)   # secant equation for the newest pair
+    assert len(B.s) == 5
+
+
+def test_patch_learn_on_a_quadratic():
+    x0 = np.array([[2e-4, 5e-5], [1.5e-4, 3e-4]])
+    res = trbox.bilevel_learn(None, quad(x0), 1e-4 * np.ones((2, 2)), dict(maxiter=60, tol=1e-12))
+    assert res.x.shape == (2, 2) and np.all(res.x > 0)
+    f0 = float(np.sum((1e-4 - x0) ** 2))
+    assert res.log[-1].function_value < 0.5 * f0
+
+
+@pytest.mark.gpu
+def test_learn_run_end_to_end_on_gpu(bp, ctx, datasets):
+    # BASELINE config 1 end to end: 1 + ≤20 evaluations of the CUDA learning function
+    data = datasets["cameraman_128_5"]
+    res = trbox.scalar_bilevel_tv_learn(data, ctx=ctx)
+    assert 2 <= res.evaluations <= 21 and res.u.shape == (128, 128, 1)
+    f0 = bp.tv_op_learning_function(0.1, data, 0.1, ctx=ctx)[1]
+    assert res.log[-1].function_value < f0            # the learned λ beats λ₀ = 0.1
+    assert 0 < res.x < 0.1
+    resp = trbox.patch_bilevel_tv_learn(datasets["circle_128_10"], ctx=ctx, maxiter=4)
+    assert resp.x.shape == (2, 2) and resp.evaluations == 5
