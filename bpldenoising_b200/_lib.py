@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbpltv.so")
+LIB_PATH = os.environ.get("BPLTV_LIB", os.path.join(_HERE, "libbpltv.so"))
 
 STRICT, FAST = 0, 1
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_MARCH, KERNEL_RESIDENT, KERNEL_TBLOCK = 0, 1, 2, 3, 4

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256) pdps_generic_kernel(const GenericArgs<Rea
     }
     Real v1 = __ldg(y1 + k), v2 = __ldg(y2 + k);
     const Real al = MAP ? __ldg(a.alpha_map + k) : a.alpha_s;
-    if (a.rho != (Real)0) dual_update<Real, STRICT, true>(v1, v2, d1, d2, al, a.rho, sc);
+    if (a.rho != (Real)0) dual_update_rho<Real, STRICT>(v1, v2, d1, d2, al, a.rho, sc);
     else dual_update<Real, STRICT, false>(v1, v2, d1, d2, al, a.rho, sc);
     a.x_out[img + k] = xn;
     a.y1_out[img + k] = v1;

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(MAXT, MINB) pdps_march_kernel(const MarchArgs<
                     const Real d2 = STRICT ? StrictOps<Real>::sub(xb_c[v], xb_p[v]) : xb_c[v] - xb_p[v];
                     o1[v] = y1_p[v]; o2[v] = y2_p[v];
                     const Real al = MAP ? al_p[v] : a.alpha_s;
-                    if (has_rho) dual_update<Real, STRICT, true>(o1[v], o2[v], d1_p[v], d2, al, a.rho, sc);
+                    if (has_rho) dual_update_rho<Real, STRICT>(o1[v], o2[v], d1_p[v], d2, al, a.rho, sc);
                     else dual_update<Real, STRICT, false>(o1[v], o2[v], d1_p[v], d2, al, a.rho, sc);
                 }
                 if (rows_ok) {
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(MAXT, MINB) pdps_march_kernel(const MarchArgs<
             for (int v = 0; v < VEC; ++v) {
                 o1[v] = y1_p[v]; o2[v] = y2_p[v];
                 const Real al = MAP ? al_p[v] : a.alpha_s;
-                if (has_rho) dual_update<Real, STRICT, true>(o1[v], o2[v], d1_p[v], (Real)0, al, a.rho, sc);
+                if (has_rho) dual_update_rho<Real, STRICT>(o1[v], o2[v], d1_p[v], (Real)0, al, a.rho, sc);
                 else dual_update<Real, STRICT, false>(o1[v], o2[v], d1_p[v], (Real)0, al, a.rho, sc);
             }
             if (rows_ok) {

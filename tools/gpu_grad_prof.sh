@@ -1,3 +1,6 @@
-python tools/profile_case.py grad 5000 > gpurun_out/plain_grad.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:grad_ -c 5 -o gpurun_out/prof_grad3 python tools/profile_case.py grad 5000 > gpurun_out/ncu_grad3.log 2>&1
-tail -n 2 gpurun_out/plain_grad.log
+for d in 0 8 0 8; do
+  export BPLTV_GRAD_DBG=$d
+  python tools/profile_case.py grad 5000 > gpurun_out/plain_grad.log 2>&1
+  ncu --metrics gpu__time_duration.sum --clock-control none -k regex:grad_factor --csv --log-file gpurun_out/grad_times.csv python tools/profile_case.py grad 5000 > gpurun_out/ncu_grad4.log 2>&1
+  echo "DBG=$d"; grep -E "grad_" gpurun_out/grad_times.csv | awk -F'","' '{print substr($5,1,40), $(NF)}' | head -3
+done
