@@ -274,6 +274,25 @@ def main():
         torch.cuda.synchronize()
         value_other = pix_iter_per_step / (f0.elapsed_time(f1) / 3 * 1e-3) / 1e9  # per GPU
 
+    # ---- fp32 build-only mode: same workload, float planes (28 B per pixel-iteration) -----
+    value_f32 = None
+    if not args.no_extras:
+        c32 = bp.Context([local], 32)
+        d_t32, d_n32 = d_truth.float(), d_noisy.float()
+        c32.set_dataset_device(d_t32.data_ptr(), d_n32.data_ptr(), M, N, O_PER_GPU, stream)
+        for _ in range(2):
+            c32.learn_eval_device(LAM, 0.1, d_costgrad.data_ptr(), eopts, stream=stream)
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(tstream)
+        for _ in range(3):
+            c32.learn_eval_device(LAM, 0.1, d_costgrad.data_ptr(), eopts, stream=stream)
+        f1.record(tstream)
+        torch.cuda.synchronize()
+        value_f32 = pix_iter_per_step / (f0.elapsed_time(f1) / 3 * 1e-3) / 1e9
+        c32.close()
+        del d_t32, d_n32
+
     # ---- roofline of the dominant kernel (pdps_march: one launch per iteration) -----
     peak, peak_src = hbm_peak()
     # per-launch duration measured live: K steps × ITERS launches back to back on this stream;
@@ -320,6 +339,9 @@ def main():
         "dtype": "f64", "data": "synthetic", "config": _config(world), "roofline": roofline, "e2e": e2e,
         "gpu_launches": int(launches_per_step * K), "loss": loss,
     }
+    if value_f32 is not None:
+        line["per_gpu_value_fp32"] = {"value": value_f32, "unit": UNIT, "arith": args.arith,
+                                      "frac_of_hbm_peak": value_f32 * 28.0 / peak}
     if value_other is not None:
         line["per_gpu_value_other_arith"] = {"arith": "fast" if arith == bp.STRICT else "strict", "value": value_other,
                                               "unit": UNIT, "frac_of_hbm_peak": value_other * 1e9 * ALG_BYTES_PER_PIXEL_ITER_F64 / 1e9 / peak}
