@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "pdps_generic.cuh"
 #include "pdps_march.cuh"
+#include "pdps_tblock.cuh"
 #include "pdps_resident.cuh"
 #include "gradient.cuh"
 
@@ -236,6 +237,89 @@ static void launch_generic(const GenericArgs<Real> &a, bool map, bool strict, cu
     }
 }
 
+// ---- temporally blocked march (kernel C): T iterations per launch ---------------------
+template <typename Real, int T>
+using TBlockFn = void (*)(const TBlockArgs<Real, T>);
+
+template <typename Real, int VEC, int T>
+static TBlockFn<Real, T> tblock_fn_vec(bool map, bool strict)
+{
+    // register budget: T=2 keeps two 256-thread CTAs per SM, deeper pipelines one
+    constexpr int MINB = T <= 2 ? 2 : 1;
+    if (map) return strict ? pdps_tblock_kernel<Real, VEC, T, true, true, 256, MINB>
+                           : pdps_tblock_kernel<Real, VEC, T, true, false, 256, MINB>;
+    return strict ? pdps_tblock_kernel<Real, VEC, T, false, true, 256, MINB>
+                  : pdps_tblock_kernel<Real, VEC, T, false, false, 256, MINB>;
+}
+
+template <int T> static TBlockFn<double, T> tblock_fn(double, int vec, bool map, bool strict)
+{
+    if (vec == 2) return tblock_fn_vec<double, 2, T>(map, strict);
+    if (vec == 1) return tblock_fn_vec<double, 1, T>(map, strict);
+    return nullptr;
+}
+template <int T> static TBlockFn<float, T> tblock_fn(float, int vec, bool map, bool strict)
+{
+    if (vec == 4) return tblock_fn_vec<float, 4, T>(map, strict);
+    if (vec == 2) return tblock_fn_vec<float, 2, T>(map, strict);
+    if (vec == 1) return tblock_fn_vec<float, 1, T>(map, strict);
+    return nullptr;
+}
+
+// vector width of the temporally blocked kernel for column height M (0 = shape not taken):
+// 16-byte accesses when M allows, one column per CTA of at most 256 threads
+template <typename Real>
+static int tblock_vec(int M)
+{
+    const int forced = env_int("BPLTV_MARCH_VEC", 0);
+    const int cands64[2] = {2, 1}, cands32[3] = {4, 2, 1};
+    const int *c = sizeof(Real) == 8 ? cands64 : cands32;
+    const int nc = sizeof(Real) == 8 ? 2 : 3;
+    for (int k = 0; k < nc; ++k) {
+        const int v = c[k];
+        if (forced && v != forced) continue;
+        if (M % v) continue;
+        if ((M / v + 31) / 32 * 32 <= 256) return v;
+    }
+    return 0;
+}
+
+// Launches floor(iters/T) T-iteration passes starting at iteration `it0`; returns the number
+// of iterations done (the caller finishes the remainder with kernel A).
+template <typename Real, int T>
+static int run_tblock_passes(Dev &d, const Real *f, int M, int N, int O, Real alpha_s, const Real *alpha_map,
+                             bool strict, int it0, int iters, cudaStream_t st, int *buf)
+{
+    const int vec = tblock_vec<Real>(M);
+    const int nthreads = (M / vec + 31) / 32 * 32;
+    TBlockFn<Real, T> fn = tblock_fn<T>(Real(), vec, alpha_map != nullptr, strict);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, nthreads, 0) != cudaSuccess) return -1;
+    per_sm = std::max(1, per_sm);
+    const long long cols = (long long)N * O;
+    long long grid = (long long)d.sm_count * per_sm;
+    // a range shorter than the 2(T-1) halo columns it recomputes is not worth a CTA
+    const int min_cols = std::max(1, env_int("BPLTV_TBLOCK_MIN_COLS", 4 * T));
+    grid = std::max<long long>(1, std::min<long long>(grid, (cols + min_cols - 1) / min_cols));
+    if (env_int("BPLTV_MARCH_CHUNK", 0) > 0)  // test hook: force a range length
+        grid = (cols + env_int("BPLTV_MARCH_CHUNK", 0) - 1) / env_int("BPLTV_MARCH_CHUNK", 0);
+    TBlockArgs<Real, T> a;
+    a.f = f; a.alpha_map = alpha_map; a.M = M; a.N = N; a.O = O; a.total_cols = cols; a.alpha_s = alpha_s;
+    const StepConsts<Real> *hsteps = reinterpret_cast<const StepConsts<Real> *>(d.steps_host.data());
+    int done = 0;
+    for (int it = it0; it + T <= it0 + iters; it += T) {
+        const int bi = *buf, bo = bi ^ 1;
+        a.x_in = d.x[bi].as<Real>(); a.y1_in = d.y1[bi].as<Real>(); a.y2_in = d.y2[bi].as<Real>();
+        a.x_out = d.x[bo].as<Real>(); a.y1_out = d.y1[bo].as<Real>(); a.y2_out = d.y2[bo].as<Real>();
+        for (int s = 0; s < T; ++s) a.sc[s] = hsteps[it + s];
+        fn<<<(unsigned)grid, nthreads, 0, st>>>(a);
+        *buf = bo;
+        done += T;
+        d.launches += 1;
+    }
+    return done;
+}
+
 // Runs opts.maxiter iterations on `f` (device, M×N×O Reals).  On return (stream
 // order) the denoised stack is in *u_result (one of the ping-pong buffers).
 template <typename Real>
@@ -266,8 +350,13 @@ static int run_pdps(Dev &d, const Real *f, int M, int N, int O, double alpha_s, 
         return fail(BPLTV_ERR_ARG, "resident PDPS kernel does not take %dx%d (rho=%g) at this precision", M, N, o.rho);
     if (kernel == BPLTV_KERNEL_MARCH && !march_vec<Real>(M))
         return fail(BPLTV_ERR_ARG, "march PDPS kernel does not take M=%d", M);
-    if (kernel == BPLTV_KERNEL_TBLOCK)
-        return fail(BPLTV_ERR_ARG, "temporally blocked PDPS kernel is not built yet");
+    int tdepth = 1;
+    if (kernel == BPLTV_KERNEL_TBLOCK) {
+        tdepth = o.tblock > 0 ? o.tblock : env_int("BPLTV_TBLOCK_T", 2);
+        if (tdepth < 1 || tdepth > 4) return fail(BPLTV_ERR_ARG, "temporal blocking depth must be 1..4 (got %d)", tdepth);
+        if (!tblock_vec<Real>(M) || rho)
+            return fail(BPLTV_ERR_ARG, "temporally blocked PDPS kernel does not take M=%d (rho=%g)", M, o.rho);
+    }
     *kernel_used = kernel;
 
     RC_TRY(upload_steps<Real>(d, o, st));
@@ -295,7 +384,18 @@ static int run_pdps(Dev &d, const Real *f, int M, int N, int O, double alpha_s, 
     CU_TRY(cudaMemsetAsync(d.y1[0].p, 0, n * sizeof(Real), st));
     CU_TRY(cudaMemsetAsync(d.y2[0].p, 0, n * sizeof(Real), st));
 
-    if (kernel == BPLTV_KERNEL_MARCH) {
+    int buf = 0;       // ping-pong buffer holding the current state
+    int it_begin = 0;  // iterations already done
+    if (kernel == BPLTV_KERNEL_TBLOCK && tdepth > 1) {
+        int done = 0;
+        if (tdepth == 2) done = run_tblock_passes<Real, 2>(d, f, M, N, O, (Real)alpha_s, alpha_map, strict, 0, o.maxiter, st, &buf);
+        else if (tdepth == 3) done = run_tblock_passes<Real, 3>(d, f, M, N, O, (Real)alpha_s, alpha_map, strict, 0, o.maxiter, st, &buf);
+        else done = run_tblock_passes<Real, 4>(d, f, M, N, O, (Real)alpha_s, alpha_map, strict, 0, o.maxiter, st, &buf);
+        if (done < 0) { cudaGetLastError(); return fail(BPLTV_ERR_CUDA, "temporally blocked PDPS kernel: occupancy query failed"); }
+        it_begin = done;  // the remainder (< T iterations) runs as single-iteration passes below
+    }
+
+    if (kernel == BPLTV_KERNEL_MARCH || kernel == BPLTV_KERNEL_TBLOCK) {
         const int vec = march_vec<Real>(M);
         const int nthreads = (M / vec + 31) / 32 * 32;
         const int minb = env_int("BPLTV_MARCH_MINB", 4);
@@ -315,13 +415,15 @@ static int run_pdps(Dev &d, const Real *f, int M, int N, int O, double alpha_s, 
         a.prefetch_dist = env_int("BPLTV_MARCH_PREFETCH", 0);
         a.alpha_s = (Real)alpha_s; a.rho = (Real)o.rho;
         const StepConsts<Real> *hsteps = reinterpret_cast<const StepConsts<Real> *>(d.steps_host.data());
-        for (int it = 0; it < o.maxiter; ++it) {
-            const int bi = it & 1, bo = bi ^ 1;
+        for (int it = it_begin; it < o.maxiter; ++it) {
+            const int bi = buf, bo = bi ^ 1;
             a.x_in = d.x[bi].as<Real>(); a.y1_in = d.y1[bi].as<Real>(); a.y2_in = d.y2[bi].as<Real>();
             a.x_out = d.x[bo].as<Real>(); a.y1_out = d.y1[bo].as<Real>(); a.y2_out = d.y2[bo].as<Real>();
             a.sc = hsteps[it];
             fn<<<(unsigned)grid, nthreads, 0, st>>>(a);
+            buf = bo;
         }
+        d.launches += o.maxiter - it_begin;
     } else {
         GenericArgs<Real> a;
         a.f = f; a.alpha_map = alpha_map; a.steps = steps; a.M = M; a.N = N; a.O = O;
@@ -334,11 +436,12 @@ static int run_pdps(Dev &d, const Real *f, int M, int N, int O, double alpha_s, 
             a.it = it;
             launch_generic<Real>(a, map, strict, st);
         }
+        buf = o.maxiter & 1;
+        d.launches += o.maxiter;
     }
-    d.launches += o.maxiter;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(BPLTV_ERR_CUDA, "PDPS kernel launch failed: %s", cudaGetErrorString(e));
-    *u_result = d.x[o.maxiter & 1].as<Real>();
+    *u_result = d.x[buf].as<Real>();
     return 0;
 }
 

@@ -190,8 +190,9 @@ def test_error_behaviour(bp, ctx, datasets):
     with pytest.raises(bp.BpltvError):
         ctx.denoise(f, 0.1, _opts(bp, tau0=50.0))  # τ₀σ₀ < 1 violated
     with pytest.raises(bp.BpltvError):
-        ctx.denoise(f[:, :127], 0.1, _opts(bp, kernel=bp.KERNEL_MARCH, maxiter=1)) if False else \
-            ctx.denoise(np.zeros((3, 3, 1), order="F"), 0.1, _opts(bp, kernel=bp.KERNEL_TBLOCK, maxiter=1))
+        ctx.denoise(np.zeros((4, 4, 1), order="F"), 0.1, _opts(bp, kernel=bp.KERNEL_TBLOCK, tblock=9, maxiter=1))
+    with pytest.raises(bp.BpltvError):   # the pipelined march has no ρ path
+        ctx.denoise(np.zeros((4, 4, 1), order="F"), 0.1, _opts(bp, kernel=bp.KERNEL_TBLOCK, rho=0.2, maxiter=1))
     fresh = bp.Context([0], 64)
     with pytest.raises(bp.BpltvError) as ei:
         fresh.learn_eval(0.1, 0.1)
@@ -199,3 +200,84 @@ def test_error_behaviour(bp, ctx, datasets):
     with pytest.raises(bp.BpltvError):
         fresh.denoise(None, 0.1)
     fresh.close()
+
+
+# ---- kernel C: temporally blocked (pipelined) march --------------------------------------
+@pytest.mark.parametrize("depth", [2, 3, 4])
+@pytest.mark.parametrize("lam_kind", ["scalar", "map"])
+def test_tblock_is_bit_identical_to_the_oracle(bp, ctx, oracle, datasets, depth, lam_kind):
+    f = datasets["faces_train_128_10"][1][:, :, :3].copy(order="F")
+    if lam_kind == "scalar":
+        x, alpha = 0.1, 0.1
+    else:
+        x = np.array([[0.02, 0.1], [0.2, 0.05]])
+        alpha = oracle.patch_upsample(x, 128, 128)
+    for maxiter in (301, 24):   # remainders 1 / 1 / 1 and 0 / 0 / 0 of the T-iteration passes
+        u = ctx.denoise(f, x, _opts(bp, maxiter=maxiter, kernel=bp.KERNEL_TBLOCK, tblock=depth))
+        assert ctx.stats()["pdps_kernel_used"] == bp.KERNEL_TBLOCK
+        assert ctx.stats()["kernel_launches"] <= maxiter // depth + maxiter % depth + 2
+        ref = oracle.pdps(f, alpha, maxiter=maxiter)
+        assert np.array_equal(u, ref), (depth, maxiter, np.abs(u - ref).max())
+
+
+@pytest.mark.parametrize("depth", [2, 3, 4])
+def test_tblock_range_ends_are_invisible(bp, ctx, oracle, datasets, depth):
+    """Column ranges shorter than, equal to and longer than the T-1 halo, ranges that
+    straddle two images and ranges ending one column before the image edge."""
+    import os
+    f = np.asfortranarray(datasets["faces_train_128_10"][1][:64, :37, :3])
+    ref = oracle.pdps(f, 0.1, maxiter=12 + depth - 1)
+    for chunk in (1, 2, 3, 4, 5, 9, 36, 37, 38, 50, 111):
+        os.environ["BPLTV_MARCH_CHUNK"] = str(chunk)
+        try:
+            u = ctx.denoise(f, 0.1, _opts(bp, maxiter=12 + depth - 1, kernel=bp.KERNEL_TBLOCK, tblock=depth))
+        finally:
+            del os.environ["BPLTV_MARCH_CHUNK"]
+        assert np.array_equal(u, ref), (depth, chunk, np.abs(u - ref).max())
+
+
+@pytest.mark.parametrize("shape", [(128, 128, 1), (64, 48, 2), (33, 17, 3), (1, 40, 1), (40, 1, 2), (2, 2, 1),
+                                   (130, 70, 1), (256, 256, 2), (512, 40, 1), (6, 3, 5)])
+def test_tblock_ragged_shapes_and_precisions(bp, ctx, ctx32, oracle, shape):
+    import os
+    M, N, O = shape
+    rng = np.random.default_rng(M * 977 + N)
+    f = np.asfortranarray(np.round(rng.uniform(0, 1, shape) * 255) / 255)
+    ref = oracle.pdps(f, 0.08, maxiter=30)
+    ref32 = oracle.pdps(f, 0.08, maxiter=30, dtype=np.float32)
+    for depth in (2, 3, 4):
+        for vec in (1, 2, 4):
+            if M % vec:
+                continue
+            os.environ["BPLTV_MARCH_VEC"] = str(vec)
+            try:
+                if vec <= 2 and M // vec <= 256:
+                    u = ctx.denoise(f, 0.08, _opts(bp, maxiter=30, kernel=bp.KERNEL_TBLOCK, tblock=depth))
+                    assert np.array_equal(u, ref), (shape, depth, vec)
+                if M // vec <= 256:
+                    u32 = ctx32.denoise(f, 0.08, _opts(bp, maxiter=30, kernel=bp.KERNEL_TBLOCK, tblock=depth))
+                    assert np.array_equal(u32.astype(np.float32), ref32), (shape, depth, vec, "fp32")
+            finally:
+                del os.environ["BPLTV_MARCH_VEC"]
+
+
+def test_tblock_fast_mode_and_switches(bp, ctx, oracle, datasets):
+    t, f = datasets["cameraman_128_5"]
+    ref = oracle.pdps(f, 0.1, maxiter=2000)
+    for depth in (2, 4):
+        u = ctx.denoise(f, 0.1, _opts(bp, maxiter=2000, kernel=bp.KERNEL_TBLOCK, tblock=depth, arith=bp.FAST))
+        assert rel_l2(u, ref) <= TOL64, depth
+    for kw in (dict(init_mode=1), dict(accel=0), dict(tau0=2.0, sigma0=0.3), dict(maxiter=1), dict(maxiter=0)):
+        okw = dict(maxiter=51)
+        okw.update({k: (bool(v) if k == "accel" else v) for k, v in kw.items()})
+        gkw = dict(maxiter=51, kernel=bp.KERNEL_TBLOCK, tblock=3)
+        gkw.update(kw)
+        assert np.array_equal(ctx.denoise(f, 0.05, _opts(bp, **gkw)), oracle.pdps(f, 0.05, **okw)), kw
+
+
+def test_tblock_at_config4_size_matches_the_single_pass_kernel(bp, ctx):
+    truth, noisy = bp.synthetic_dataset(512, 512, 64, seed=20240601)
+    a = ctx.denoise(noisy, 0.1, _opts(bp, maxiter=25, kernel=bp.KERNEL_MARCH))
+    for depth in (2, 3, 4):
+        b = ctx.denoise(noisy, 0.1, _opts(bp, maxiter=25, kernel=bp.KERNEL_TBLOCK, tblock=depth))
+        assert np.array_equal(a, b), depth
