@@ -16,6 +16,11 @@ with bp.Context([0], int(os.environ.get("BPLTV_PREC", "64"))) as ctx:
         t, f = bp.synthetic_dataset(512, 512, 64, seed=20240601)
         u = ctx.denoise(f, 0.1, bp.pdps_opts(maxiter=iters, kernel=bp.KERNEL_MARCH, arith=arith))
         print("pdps ok", float(u.mean()), ctx.stats()["ms_pdps"])
+    elif case == "tblock":  # same shape through the temporally blocked kernel (depth from BPLTV_TBLOCK_T)
+        t, f = bp.synthetic_dataset(512, 512, 64, seed=20240601)
+        u = ctx.denoise(f, 0.1, bp.pdps_opts(maxiter=iters, kernel=bp.KERNEL_TBLOCK, arith=arith,
+                                             tblock=int(os.environ.get("BPLTV_TBLOCK_T", "2"))))
+        print("tblock ok", float(u.mean()), ctx.stats()["ms_pdps"])
     elif case == "resident":
         t, f = bp.synthetic_dataset(128, 128, 10, seed=7)
         u = ctx.denoise(f, 0.1, bp.pdps_opts(maxiter=iters, kernel=bp.KERNEL_RESIDENT, arith=arith))
