@@ -244,12 +244,14 @@ using TBlockFn = void (*)(const TBlockArgs<Real, T>);
 template <typename Real, int VEC, int T>
 static TBlockFn<Real, T> tblock_fn_vec(bool map, bool strict)
 {
-    // register budget: T=2 keeps two 256-thread CTAs per SM, deeper pipelines one
+    // register budget: T=2 keeps two 256-thread CTAs per SM, deeper pipelines one.
+    // 16-byte vectors (whole columns are then 16-byte multiples) take the TMA prefetch ring.
     constexpr int MINB = T <= 2 ? 2 : 1;
-    if (map) return strict ? pdps_tblock_kernel<Real, VEC, T, true, true, 256, MINB>
-                           : pdps_tblock_kernel<Real, VEC, T, true, false, 256, MINB>;
-    return strict ? pdps_tblock_kernel<Real, VEC, T, false, true, 256, MINB>
-                  : pdps_tblock_kernel<Real, VEC, T, false, false, 256, MINB>;
+    constexpr bool RING = VEC * sizeof(Real) == 16;
+    if (map) return strict ? pdps_tblock_kernel<Real, VEC, T, true, true, RING, 256, MINB>
+                           : pdps_tblock_kernel<Real, VEC, T, true, false, RING, 256, MINB>;
+    return strict ? pdps_tblock_kernel<Real, VEC, T, false, true, RING, 256, MINB>
+                  : pdps_tblock_kernel<Real, VEC, T, false, false, RING, 256, MINB>;
 }
 
 template <int T> static TBlockFn<double, T> tblock_fn(double, int vec, bool map, bool strict)
@@ -293,8 +295,11 @@ static int run_tblock_passes(Dev &d, const Real *f, int M, int N, int O, Real al
     const int vec = tblock_vec<Real>(M);
     const int nthreads = (M / vec + 31) / 32 * 32;
     TBlockFn<Real, T> fn = tblock_fn<T>(Real(), vec, alpha_map != nullptr, strict);
+    const size_t smem = (vec * sizeof(Real) == 16) ? tblock_ring_bytes<Real, T>(M) : 0;
+    if (smem > d.smem_optin) return -1;
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, nthreads, 0) != cudaSuccess) return -1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, nthreads, smem) != cudaSuccess) return -1;
     per_sm = std::max(1, per_sm);
     const long long cols = (long long)N * O;
     long long grid = (long long)d.sm_count * per_sm;
@@ -312,7 +317,7 @@ static int run_tblock_passes(Dev &d, const Real *f, int M, int N, int O, Real al
         a.x_in = d.x[bi].as<Real>(); a.y1_in = d.y1[bi].as<Real>(); a.y2_in = d.y2[bi].as<Real>();
         a.x_out = d.x[bo].as<Real>(); a.y1_out = d.y1[bo].as<Real>(); a.y2_out = d.y2[bo].as<Real>();
         for (int s = 0; s < T; ++s) a.sc[s] = hsteps[it + s];
-        fn<<<(unsigned)grid, nthreads, 0, st>>>(a);
+        fn<<<(unsigned)grid, nthreads, smem, st>>>(a);
         *buf = bo;
         done += T;
         d.launches += 1;

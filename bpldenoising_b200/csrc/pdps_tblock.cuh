@@ -35,6 +35,41 @@
 
 namespace bpltv {
 
+// ---- 1-D bulk TMA + mbarrier (column prefetch ring) -------------------------------------
+constexpr int TB_PF = 2;             // columns in flight ahead of the march front
+constexpr int TB_R = TB_PF + 1;      // ring slots of the x / y1 / y2 planes
+
+static __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+static __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+static __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+static __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TB_DONE;\n"
+        "bra TB_WAIT;\n"
+        "TB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global → shared copy of `bytes` (multiple of 16, both addresses 16-byte aligned) by the TMA
+// engine; completion is counted in bytes on `bar`
+static __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 template <typename Real, int T>
 struct TBlockArgs {
     const Real *x_in, *y1_in, *y2_in, *f;
@@ -62,11 +97,48 @@ struct TBSeg {
     int M, N, c0, c1, cs, r0, lane, warp;
     bool rows_ok, multi_warp;
     Real alpha_s;
+    // column prefetch ring (RING kernels): TB_R slots of {x, y1, y2}, TB_R + 2(T-1) slots of f
+    // (later stages re-read f from it); column c of the segment is load number k0 + (c - cs)
+    Real *ring, *fring;
+    unsigned long long *bars;
+    int k0, cl;
 };
+
+// thread 0: start the TMA copies of image column `col` (load number kk)
+template <typename Real, int T>
+static __device__ __forceinline__ void tb_issue(const TBSeg<Real> &g, int kk, int col)
+{
+    constexpr int RF = TB_R + 2 * (T - 1);
+    const unsigned bytes = (unsigned)(g.M * sizeof(Real));
+    unsigned long long *bar = g.bars + kk % TB_R;
+    Real *sx = g.ring + (size_t)(kk % TB_R) * 3 * g.M;
+    const size_t off = (size_t)col * g.M;
+    mbar_expect_tx(bar, 4 * bytes);
+    tma_load_1d(sx, g.xin + off, bytes, bar);
+    tma_load_1d(sx + g.M, g.y1in + off, bytes, bar);
+    tma_load_1d(sx + 2 * g.M, g.y2in + off, bytes, bar);
+    tma_load_1d(g.fring + (size_t)(kk % RF) * g.M, g.fin + off, bytes, bar);
+}
+
+template <typename Real, int VEC>
+static __device__ __forceinline__ void lds_vec(const Real *p, Real (&v)[VEC])
+{
+    if (VEC * sizeof(Real) == 16) {
+        const double2 t = *reinterpret_cast<const double2 *>(p);
+        if (sizeof(Real) == 8) { v[0] = (Real)t.x; v[VEC - 1] = (Real)t.y; }
+        else {
+            const float4 q = *reinterpret_cast<const float4 *>(&t);
+            v[0] = (Real)q.x; v[1 % VEC] = (Real)q.y; v[2 % VEC] = (Real)q.z; v[3 % VEC] = (Real)q.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v[k] = p[k];
+    }
+}
 
 // One march step.  Reads the state of the previous step from P (and, for x/f, the values
 // stage s-1 left in C two steps ago), writes the new state to C.
-template <typename Real, int VEC, int T, bool MAP, bool STRICT, bool STEADY>
+template <typename Real, int VEC, int T, bool MAP, bool STRICT, bool RING, bool STEADY>
 static __device__ __forceinline__ void tblock_step(const int c, const TBStage<Real, VEC> (&P)[T],
                                                    TBStage<Real, VEC> (&C)[T], const TBSeg<Real> &g,
                                                    const StepConsts<Real> (&scs)[T], Real (&s_dn)[T][33],
@@ -89,8 +161,23 @@ static __device__ __forceinline__ void tblock_step(const int c, const TBStage<Re
         Real x_c[VEC], f_c[VEC], up_c = 0;
 #pragma unroll
         for (int v = 0; v < VEC; ++v) { x_c[v] = f_c[v] = y1_c[s][v] = y2_c[s][v] = 0; }
+        constexpr int RF = TB_R + 2 * (T - 1);
+        const int k = g.k0 + (p - g.cs);                          // load number of column p (RING)
         if (s == 0) {
-            if (do_primal[0] && g.rows_ok) {
+            if (RING) {
+                if (do_primal[0]) {
+                    if (threadIdx.x == 0 && p + TB_PF <= g.cl) tb_issue<Real, T>(g, k + TB_PF, p + TB_PF);
+                    if (g.rows_ok) {
+                        mbar_wait(g.bars + k % TB_R, (unsigned)(k / TB_R) & 1u);
+                        const Real *sx = g.ring + (size_t)(k % TB_R) * 3 * M + r0;
+                        lds_vec<Real, VEC>(sx, x_c);
+                        lds_vec<Real, VEC>(sx + M, y1_c[0]);
+                        lds_vec<Real, VEC>(sx + 2 * M, y2_c[0]);
+                        lds_vec<Real, VEC>(g.fring + (size_t)(k % RF) * M + r0, f_c);
+                        if (lane == 0 && r0 > 0) up_c = sx[M - 1];  // y1 of the row above
+                    }
+                }
+            } else if (do_primal[0] && g.rows_ok) {
                 const size_t off = (size_t)p * M + r0;
                 IO::ld(g.xin + off, x_c);
                 IO::ld(g.fin + off, f_c);
@@ -101,9 +188,11 @@ static __device__ __forceinline__ void tblock_step(const int c, const TBStage<Re
         } else {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                x_c[v] = C[s - 1].xn[v]; f_c[v] = C[s - 1].f[v];          // from two steps ago
+                x_c[v] = C[s - 1].xn[v];                                   // from two steps ago
+                if (!RING) f_c[v] = C[s - 1].f[v];
                 y1_c[s][v] = P[s - 1].o1[v]; y2_c[s][v] = P[s - 1].o2[v];  // from the previous step
             }
+            if (RING && do_primal[s] && g.rows_ok) lds_vec<Real, VEC>(g.fring + (size_t)(k % RF) * M + r0, f_c);
             if (g.multi_warp && lane == 0 && warp > 0) up_c = s_up[s][warp];
         }
         if (do_primal[s]) {
@@ -120,7 +209,7 @@ static __device__ __forceinline__ void tblock_step(const int c, const TBStage<Re
                 if (g.rows_ok && p >= g.c0 && p < g.c1) IO::st(g.xout + (size_t)p * M + r0, xn_c);
             } else {
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) { C[s].xn[v] = xn_c[v]; C[s].f[v] = f_c[v]; }
+                for (int v = 0; v < VEC; ++v) { C[s].xn[v] = xn_c[v]; if (!RING) C[s].f[v] = f_c[v]; }
             }
             if (g.multi_warp && lane == 0) s_dn[s][warp] = xb_c[s][0];
         } else {
@@ -181,10 +270,16 @@ static __device__ __forceinline__ void tblock_step(const int c, const TBStage<Re
     if (g.multi_warp) __syncthreads();
 }
 
-template <typename Real, int VEC, int T, bool MAP, bool STRICT, int MAXT, int MINB>
+// dynamic shared memory of a RING kernel for column height M
+template <typename Real, int T>
+static inline size_t tblock_ring_bytes(int M) { return (size_t)(3 * TB_R + TB_R + 2 * (T - 1)) * M * sizeof(Real); }
+
+template <typename Real, int VEC, int T, bool MAP, bool STRICT, bool RING, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) pdps_tblock_kernel(const TBlockArgs<Real, T> a)
 {
     typedef VecIO<Real, VEC> IO;
+    extern __shared__ __align__(128) unsigned char tb_smem[];
+    __shared__ unsigned long long s_bars[TB_R];
     // slot [warp] of s_dn: x̄ of the warp's first row (read by the warp above it);
     // slot [warp+1] of s_up: the finished y1 of the warp's last row (read by the warp below)
     __shared__ Real s_dn[T][33];
@@ -197,6 +292,18 @@ __global__ void __launch_bounds__(MAXT, MINB) pdps_tblock_kernel(const TBlockArg
     g.lane = threadIdx.x & 31; g.warp = threadIdx.x >> 5;
     g.multi_warp = blockDim.x > 32;
     const int M = a.M, N = a.N;
+    g.ring = reinterpret_cast<Real *>(tb_smem);
+    g.fring = g.ring + (size_t)3 * TB_R * M;
+    g.bars = s_bars;
+    g.k0 = 0; g.cl = 0;
+    if (RING) {
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int i = 0; i < TB_R; ++i) mbar_init(&s_bars[i], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
 
     const long long per = (a.total_cols + gridDim.x - 1) / gridDim.x;
     long long gc = (long long)blockIdx.x * per;
@@ -226,11 +333,17 @@ __global__ void __launch_bounds__(MAXT, MINB) pdps_tblock_kernel(const TBlockArg
             B[s] = A[s];
         }
         if (g.rows_ok && cs > 0) IO::ld(g.y2in + (size_t)(cs - 1) * M + g.r0, A[0].y2);
+        g.cl = c_hi;                                                   // last column loaded
+        if (RING && threadIdx.x == 0) {
+#pragma unroll
+            for (int i = 0; i < TB_PF; ++i)
+                if (cs + i <= c_hi) tb_issue<Real, T>(g, g.k0 + i, cs + i);
+        }
 
         int c = cs;
         // fill (and everything, for ranges too short to reach the steady state)
         for (; c <= c_end && c < c_lo; ++c) {
-            tblock_step<Real, VEC, T, MAP, STRICT, false>(c, A, B, g, a.sc, s_dn, s_up);
+            tblock_step<Real, VEC, T, MAP, STRICT, RING, false>(c, A, B, g, a.sc, s_dn, s_up);
 #pragma unroll
             for (int s = 0; s < T; ++s) {
                 // B holds the new state; A keeps the two-steps-ago x/f until the next step reads them
@@ -239,17 +352,18 @@ __global__ void __launch_bounds__(MAXT, MINB) pdps_tblock_kernel(const TBlockArg
         }
         // steady state, two steps per trip: the register sets swap roles
         for (; c + 1 <= c_hi; c += 2) {
-            tblock_step<Real, VEC, T, MAP, STRICT, true>(c, A, B, g, a.sc, s_dn, s_up);
-            tblock_step<Real, VEC, T, MAP, STRICT, true>(c + 1, B, A, g, a.sc, s_dn, s_up);
+            tblock_step<Real, VEC, T, MAP, STRICT, RING, true>(c, A, B, g, a.sc, s_dn, s_up);
+            tblock_step<Real, VEC, T, MAP, STRICT, RING, true>(c + 1, B, A, g, a.sc, s_dn, s_up);
         }
         // drain
         for (; c <= c_end; ++c) {
-            tblock_step<Real, VEC, T, MAP, STRICT, false>(c, A, B, g, a.sc, s_dn, s_up);
+            tblock_step<Real, VEC, T, MAP, STRICT, RING, false>(c, A, B, g, a.sc, s_dn, s_up);
 #pragma unroll
             for (int s = 0; s < T; ++s) {
                 TBStage<Real, VEC> t = A[s]; A[s] = B[s]; B[s] = t;
             }
         }
+        g.k0 += c_hi - cs + 1;
     }
 }
 
