@@ -14,12 +14,18 @@
 // reading the duals stage s-1 finished in the PREVIOUS step and the x it formed two steps
 // ago.  Because every stage works on data of earlier steps, the T stages of one step are
 // independent instruction streams (the dependent chain of one iteration — prox, shuffle,
-// gradient, dual ascent, √ and ÷ of the projection — is what limits a single stage) and a
-// step needs two CTA barriers whatever T is: one after the P-phase (x̄ of the first row of
-// each warp → the warp above), one after the D-phase (the finished y1 of the last row of
-// each warp → the warp below).  Only stage 0 reads state from memory, only stage T-1
-// writes it.  The march loop is unrolled by two with the carried state in two register
+// gradient, dual ascent, √ and ÷ of the projection — is what limits a single stage; the
+// projections of all stages and rows of a thread are issued together for the same reason)
+// and a step needs two CTA barriers whatever T is: one after the P-phase (x̄ of the first
+// row of each warp → the warp above), one after the D-phase (the finished y1 of the last
+// row of each warp → the warp below).  Only stage 0 reads state from memory, only stage
+// T-1 writes it.  The march loop is unrolled by two with the carried state in two register
 // sets that swap roles, so nothing is copied from step to step.
+//
+// Loads: with 16-byte vectors a column is a 16-byte multiple, and stage 0's input columns
+// {x, y1, y2, f} arrive through a shared-memory ring filled by the TMA engine (1-D
+// cp.async.bulk, one mbarrier per slot, TB_PF columns ahead of the march front), so no
+// thread ever waits on an HBM load; later stages re-read f from the same ring.
 //
 // Range ends: a range [c0,c1) of an image starts marching at cs = c0-(T-1) and loads up to
 // c1+T-1 (clipped to the image), recomputing the T-1 halo columns on each side; stage s is
@@ -28,27 +34,29 @@
 // the dual of column N-1 with Δy2 = 0, as kernel A does.  The pipeline fill and drain
 // steps run the same code with per-stage activity flags (template STEADY = false).
 //
-// The arithmetic is common.cuh's primal_update / dual_update in the same order per pixel
-// and iteration, so strict mode stays bit-identical to the oracle.
+// The arithmetic is common.cuh's primal_update / dual ascent / projection in the same order
+// per pixel and iteration, so strict mode stays bit-identical to the oracle.
 #pragma once
 #include "common.cuh"
 
 namespace bpltv {
 
-// ---- 1-D bulk TMA + mbarrier (column prefetch ring) -------------------------------------
-constexpr int TB_PF = 2;             // columns in flight ahead of the march front
-constexpr int TB_R = TB_PF + 1;      // ring slots of the x / y1 / y2 planes
+// ---- 1-D bulk TMA + mbarrier (column prefetch ring), 32-bit shared addresses -------------
+constexpr int TB_R = 4;              // ring slots of the x / y1 / y2 planes (power of two)
+constexpr int TB_PF = TB_R - 1;      // columns in flight ahead of the march front
+// ring slots of f: later stages read f of column c-2s (power of two ≥ TB_R + 2(T-1))
+template <int T> struct TBRingF { static constexpr int value = (TB_R + 2 * (T - 1)) <= 8 ? 8 : 16; };
 
 static __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-static __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+static __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-static __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+static __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
 {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-static __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+static __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 {
     asm volatile(
         "{\n"
@@ -58,16 +66,34 @@ static __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsign
         "@p bra TB_DONE;\n"
         "bra TB_WAIT;\n"
         "TB_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 // global → shared copy of `bytes` (multiple of 16, both addresses 16-byte aligned) by the TMA
-// engine; completion is counted in bytes on `bar`
-static __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+// engine; completion is counted in bytes on the mbarrier `bar`
+static __device__ __forceinline__ void tma_load_1d(unsigned dst, const void *src, unsigned bytes, unsigned bar)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
+}
+// 16-byte shared-memory load of VEC Reals
+static __device__ __forceinline__ void lds16(unsigned addr, double (&v)[2])
+{
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(addr));
+}
+static __device__ __forceinline__ void lds16(unsigned addr, float (&v)[4])
+{
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+}
+template <typename Real, int VEC>
+static __device__ __forceinline__ void lds16(unsigned, Real (&)[VEC]) {}  // never called (RING ⇒ 16-byte vectors)
+static __device__ __forceinline__ double lds1(unsigned addr, double)
+{
+    double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr)); return v;
+}
+static __device__ __forceinline__ float lds1(unsigned addr, float)
+{
+    float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v;
 }
 
 template <typename Real, int T>
@@ -94,46 +120,30 @@ template <typename Real>
 struct TBSeg {
     const Real *xin, *y1in, *y2in, *fin, *amap;
     Real *xout, *y1out, *y2out;
-    int M, N, c0, c1, cs, r0, lane, warp;
-    bool rows_ok, multi_warp;
+    int M, N, c0, c1, cs, cl, lane, warp;
+    int r0;            // first row of this thread (clamped into the image for threads beyond it)
+    bool st_ok;        // this thread owns rows (threads beyond the column compute a copy, store nothing)
+    bool multi_warp;
     Real alpha_s;
-    // column prefetch ring (RING kernels): TB_R slots of {x, y1, y2}, TB_R + 2(T-1) slots of f
-    // (later stages re-read f from it); column c of the segment is load number k0 + (c - cs)
-    Real *ring, *fring;
-    unsigned long long *bars;
-    int k0, cl;
+    // column prefetch ring (RING kernels), shared-window byte addresses of this thread's rows:
+    // slot i of {x,y1,y2} at ring_t + i·3·colb (planes colb apart), slot j of f at fring_t + j·colb;
+    // image column c of the segment is load number k0 + (c - cs)
+    unsigned ring_t, fring_t, ring0, fring0, bars, colb;
+    int k0;
 };
 
 // thread 0: start the TMA copies of image column `col` (load number kk)
 template <typename Real, int T>
 static __device__ __forceinline__ void tb_issue(const TBSeg<Real> &g, int kk, int col)
 {
-    constexpr int RF = TB_R + 2 * (T - 1);
-    const unsigned bytes = (unsigned)(g.M * sizeof(Real));
-    unsigned long long *bar = g.bars + kk % TB_R;
-    Real *sx = g.ring + (size_t)(kk % TB_R) * 3 * g.M;
+    const unsigned bar = g.bars + 8u * (unsigned)(kk & (TB_R - 1));
+    const unsigned sx = g.ring0 + (unsigned)(kk & (TB_R - 1)) * 3u * g.colb;
     const size_t off = (size_t)col * g.M;
-    mbar_expect_tx(bar, 4 * bytes);
-    tma_load_1d(sx, g.xin + off, bytes, bar);
-    tma_load_1d(sx + g.M, g.y1in + off, bytes, bar);
-    tma_load_1d(sx + 2 * g.M, g.y2in + off, bytes, bar);
-    tma_load_1d(g.fring + (size_t)(kk % RF) * g.M, g.fin + off, bytes, bar);
-}
-
-template <typename Real, int VEC>
-static __device__ __forceinline__ void lds_vec(const Real *p, Real (&v)[VEC])
-{
-    if (VEC * sizeof(Real) == 16) {
-        const double2 t = *reinterpret_cast<const double2 *>(p);
-        if (sizeof(Real) == 8) { v[0] = (Real)t.x; v[VEC - 1] = (Real)t.y; }
-        else {
-            const float4 q = *reinterpret_cast<const float4 *>(&t);
-            v[0] = (Real)q.x; v[1 % VEC] = (Real)q.y; v[2 % VEC] = (Real)q.z; v[3 % VEC] = (Real)q.w;
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) v[k] = p[k];
-    }
+    mbar_expect_tx(bar, 4 * g.colb);
+    tma_load_1d(sx, g.xin + off, g.colb, bar);
+    tma_load_1d(sx + g.colb, g.y1in + off, g.colb, bar);
+    tma_load_1d(sx + 2 * g.colb, g.y2in + off, g.colb, bar);
+    tma_load_1d(g.fring0 + (unsigned)(kk & (TBRingF<T>::value - 1)) * g.colb, g.fin + off, g.colb, bar);
 }
 
 // One march step.  Reads the state of the previous step from P (and, for x/f, the values
@@ -145,6 +155,8 @@ static __device__ __forceinline__ void tblock_step(const int c, const TBStage<Re
                                                    Real (&s_up)[T][34])
 {
     typedef VecIO<Real, VEC> IO;
+    typedef StrictOps<Real> A;
+    constexpr int RF = TBRingF<T>::value;
     const int M = g.M, N = g.N, r0 = g.r0, lane = g.lane, warp = g.warp;
     bool do_primal[T], do_dual[T], do_flush[T];
     Real xb_c[T][VEC], y1_c[T][VEC], y2_c[T][VEC];
@@ -158,26 +170,24 @@ static __device__ __forceinline__ void tblock_step(const int c, const TBStage<Re
         do_primal[s] = STEADY || (p >= g.cs && p <= pl);         // CTA-uniform
         do_dual[s] = STEADY || (p - 1 >= g.cs && p <= pl);
         do_flush[s] = !STEADY && (p == N && pl == N - 1);
-        Real x_c[VEC], f_c[VEC], up_c = 0;
+        if (!do_primal[s]) {
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) { x_c[v] = f_c[v] = y1_c[s][v] = y2_c[s][v] = 0; }
-        constexpr int RF = TB_R + 2 * (T - 1);
+            for (int v = 0; v < VEC; ++v) xb_c[s][v] = y1_c[s][v] = y2_c[s][v] = 0;
+            continue;
+        }
+        Real x_c[VEC], f_c[VEC], up_c = 0;
         const int k = g.k0 + (p - g.cs);                          // load number of column p (RING)
         if (s == 0) {
             if (RING) {
-                if (do_primal[0]) {
-                    if (threadIdx.x == 0 && p + TB_PF <= g.cl) tb_issue<Real, T>(g, k + TB_PF, p + TB_PF);
-                    if (g.rows_ok) {
-                        mbar_wait(g.bars + k % TB_R, (unsigned)(k / TB_R) & 1u);
-                        const Real *sx = g.ring + (size_t)(k % TB_R) * 3 * M + r0;
-                        lds_vec<Real, VEC>(sx, x_c);
-                        lds_vec<Real, VEC>(sx + M, y1_c[0]);
-                        lds_vec<Real, VEC>(sx + 2 * M, y2_c[0]);
-                        lds_vec<Real, VEC>(g.fring + (size_t)(k % RF) * M + r0, f_c);
-                        if (lane == 0 && r0 > 0) up_c = sx[M - 1];  // y1 of the row above
-                    }
-                }
-            } else if (do_primal[0] && g.rows_ok) {
+                if (threadIdx.x == 0 && p + TB_PF <= g.cl) tb_issue<Real, T>(g, k + TB_PF, p + TB_PF);
+                mbar_wait(g.bars + 8u * (unsigned)(k & (TB_R - 1)), ((unsigned)k / TB_R) & 1u);
+                const unsigned sx = g.ring_t + (unsigned)(k & (TB_R - 1)) * 3u * g.colb;
+                lds16(sx, x_c);
+                lds16(sx + g.colb, y1_c[0]);
+                lds16(sx + 2 * g.colb, y2_c[0]);
+                lds16(g.fring_t + (unsigned)(k & (RF - 1)) * g.colb, f_c);
+                if (lane == 0 && r0 > 0) up_c = lds1(sx + g.colb - (unsigned)sizeof(Real), Real());  // y1 of the row above
+            } else {
                 const size_t off = (size_t)p * M + r0;
                 IO::ld(g.xin + off, x_c);
                 IO::ld(g.fin + off, f_c);
@@ -192,34 +202,32 @@ static __device__ __forceinline__ void tblock_step(const int c, const TBStage<Re
                 if (!RING) f_c[v] = C[s - 1].f[v];
                 y1_c[s][v] = P[s - 1].o1[v]; y2_c[s][v] = P[s - 1].o2[v];  // from the previous step
             }
-            if (RING && do_primal[s] && g.rows_ok) lds_vec<Real, VEC>(g.fring + (size_t)(k % RF) * M + r0, f_c);
+            if (RING) lds16(g.fring_t + (unsigned)(k & (RF - 1)) * g.colb, f_c);
             if (g.multi_warp && lane == 0 && warp > 0) up_c = s_up[s][warp];
         }
-        if (do_primal[s]) {
-            Real up = __shfl_up_sync(0xffffffffu, y1_c[s][VEC - 1], 1);
-            if (lane == 0) up = up_c;  // 0 at the top row
-            Real xn_c[VEC];
+        Real up = __shfl_up_sync(0xffffffffu, y1_c[s][VEC - 1], 1);
+        if (lane == 0) up = up_c;  // 0 at the top row
+        Real xn_c[VEC];
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                const Real y1up = (v == 0) ? up : y1_c[s][v - 1];
-                xn_c[v] = primal_update<Real, STRICT>(x_c[v], f_c[v], y1up, y1_c[s][v], P[s].y2[v], y2_c[s][v], scs[s],
-                                                      xb_c[s][v]);
-            }
-            if (s == T - 1) {
-                if (g.rows_ok && p >= g.c0 && p < g.c1) IO::st(g.xout + (size_t)p * M + r0, xn_c);
-            } else {
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) { C[s].xn[v] = xn_c[v]; if (!RING) C[s].f[v] = f_c[v]; }
-            }
-            if (g.multi_warp && lane == 0) s_dn[s][warp] = xb_c[s][0];
+        for (int v = 0; v < VEC; ++v) {
+            const Real y1up = (v == 0) ? up : y1_c[s][v - 1];
+            xn_c[v] = primal_update<Real, STRICT>(x_c[v], f_c[v], y1up, y1_c[s][v], P[s].y2[v], y2_c[s][v], scs[s],
+                                                  xb_c[s][v]);
+        }
+        if (s == T - 1) {
+            if (g.st_ok && p >= g.c0 && p < g.c1) IO::st(g.xout + (size_t)p * M + r0, xn_c);
         } else {
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) xb_c[s][v] = 0;
+            for (int v = 0; v < VEC; ++v) { C[s].xn[v] = xn_c[v]; if (!RING) C[s].f[v] = f_c[v]; }
         }
+        if (g.multi_warp && lane == 0) s_dn[s][warp] = xb_c[s][0];
     }
     if (g.multi_warp) __syncthreads();
 
     // ---------------- D-phase ---------------------------------------------------------------
+    // Δy1 of the new column; dual ascent v = y + σ∇x̄ of column p-1 for every active stage
+    Real v1[T][VEC], v2[T][VEC], n2[T][VEC], al[T][VEC];
+    bool outside = false;
 #pragma unroll
     for (int s = 0; s < T; ++s) {
         const int p = c - 2 * s;
@@ -230,30 +238,64 @@ static __device__ __forceinline__ void tblock_step(const int c, const TBStage<Re
             for (int v = 0; v < VEC; ++v) {
                 const Real nxt = (v == VEC - 1) ? dn : xb_c[s][v + 1];
                 const bool last_row = (r0 + v == M - 1);
-                C[s].d1[v] = last_row ? (Real)0 : (STRICT ? StrictOps<Real>::sub(nxt, xb_c[s][v]) : nxt - xb_c[s][v]);
+                C[s].d1[v] = last_row ? (Real)0 : (STRICT ? A::sub(nxt, xb_c[s][v]) : nxt - xb_c[s][v]);
             }
         }
-        if (do_dual[s] || do_flush[s]) {
-            Real o1[VEC], o2[VEC], al[VEC];
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) al[v] = g.alpha_s;
-            if (MAP && g.rows_ok) IO::ld(g.amap + (size_t)(p - 1) * M + r0, al);
+        for (int v = 0; v < VEC; ++v) { v1[s][v] = v2[s][v] = n2[s][v] = 0; al[s][v] = g.alpha_s; }
+        if (do_dual[s] || do_flush[s]) {
+            if (MAP) IO::ld(g.amap + (size_t)(p - 1) * M + r0, al[s]);
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
                 Real d2 = (Real)0;
-                if (do_dual[s]) d2 = STRICT ? StrictOps<Real>::sub(xb_c[s][v], P[s].xb[v]) : xb_c[s][v] - P[s].xb[v];
-                o1[v] = P[s].y1[v]; o2[v] = P[s].y2[v];
-                dual_update<Real, STRICT, false>(o1[v], o2[v], P[s].d1[v], d2, al[v], (Real)0, scs[s]);
+                if (STRICT) {
+                    if (do_dual[s]) d2 = A::sub(xb_c[s][v], P[s].xb[v]);
+                    v1[s][v] = A::add(P[s].y1[v], A::mul(scs[s].sigma, P[s].d1[v]));
+                    v2[s][v] = A::add(P[s].y2[v], A::mul(scs[s].sigma, d2));
+                    n2[s][v] = A::add(A::mul(v1[s][v], v1[s][v]), A::mul(v2[s][v], v2[s][v]));
+                    outside |= n2[s][v] > A::mul(al[s][v], al[s][v]);
+                } else {
+                    if (do_dual[s]) d2 = xb_c[s][v] - P[s].xb[v];
+                    v1[s][v] = fma_(scs[s].sigma, P[s].d1[v], P[s].y1[v]);
+                    v2[s][v] = fma_(scs[s].sigma, d2, P[s].y2[v]);
+                    n2[s][v] = fma_(v1[s][v], v1[s][v], v2[s][v] * v2[s][v]);
+                    outside |= n2[s][v] > al[s][v] * al[s][v];
+                }
             }
+        }
+    }
+    // projection onto the λ-ball, `if n² > α²` as in the reference: all of the thread's pixels
+    // that left the ball are scaled in one block so that their √ and ÷ chains overlap (a
+    // thread none of whose pixels left the ball skips it entirely)
+    if (outside) {
+#pragma unroll
+        for (int s = 0; s < T; ++s)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                if (STRICT) {
+                    const bool out = n2[s][v] > A::mul(al[s][v], al[s][v]);
+                    const Real sc = A::div(al[s][v], A::sqrt(out ? n2[s][v] : (Real)1));
+                    if (out) { v1[s][v] = A::mul(v1[s][v], sc); v2[s][v] = A::mul(v2[s][v], sc); }
+                } else {
+                    const bool out = n2[s][v] > al[s][v] * al[s][v];
+                    const Real sc = al[s][v] * rsqrt_(out ? n2[s][v] : (Real)1);
+                    if (out) { v1[s][v] *= sc; v2[s][v] *= sc; }
+                }
+            }
+    }
+#pragma unroll
+    for (int s = 0; s < T; ++s) {
+        const int p = c - 2 * s;
+        if (do_dual[s] || do_flush[s]) {
             if (s == T - 1) {
-                if (g.rows_ok && p - 1 >= g.c0 && p - 1 < g.c1) {
-                    IO::st(g.y1out + (size_t)(p - 1) * M + r0, o1);
-                    IO::st(g.y2out + (size_t)(p - 1) * M + r0, o2);
+                if (g.st_ok && p - 1 >= g.c0 && p - 1 < g.c1) {
+                    IO::st(g.y1out + (size_t)(p - 1) * M + r0, v1[s]);
+                    IO::st(g.y2out + (size_t)(p - 1) * M + r0, v2[s]);
                 }
             } else {
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) { C[s].o1[v] = o1[v]; C[s].o2[v] = o2[v]; }
-                if (g.multi_warp && lane == 31) s_up[s + 1][warp + 1] = o1[VEC - 1];
+                for (int v = 0; v < VEC; ++v) { C[s].o1[v] = v1[s][v]; C[s].o2[v] = v2[s][v]; }
+                if (g.multi_warp && lane == 31) s_up[s + 1][warp + 1] = v1[s][VEC - 1];
             }
         }
         // carried column of this stage
@@ -272,7 +314,7 @@ static __device__ __forceinline__ void tblock_step(const int c, const TBStage<Re
 
 // dynamic shared memory of a RING kernel for column height M
 template <typename Real, int T>
-static inline size_t tblock_ring_bytes(int M) { return (size_t)(3 * TB_R + TB_R + 2 * (T - 1)) * M * sizeof(Real); }
+static inline size_t tblock_ring_bytes(int M) { return (size_t)(3 * TB_R + TBRingF<T>::value) * M * sizeof(Real); }
 
 template <typename Real, int VEC, int T, bool MAP, bool STRICT, bool RING, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) pdps_tblock_kernel(const TBlockArgs<Real, T> a)
@@ -285,21 +327,24 @@ __global__ void __launch_bounds__(MAXT, MINB) pdps_tblock_kernel(const TBlockArg
     __shared__ Real s_dn[T][33];
     __shared__ Real s_up[T][34];
 
+    const int M = a.M, N = a.N;
     TBSeg<Real> g;
-    g.M = a.M; g.N = a.N; g.amap = a.alpha_map; g.alpha_s = a.alpha_s;
-    g.r0 = threadIdx.x * VEC;
-    g.rows_ok = g.r0 < a.M;          // M % VEC == 0 → all VEC rows valid together
+    g.M = M; g.N = N; g.amap = a.alpha_map; g.alpha_s = a.alpha_s;
+    g.st_ok = (int)threadIdx.x * VEC < M;                 // M % VEC == 0 → all VEC rows valid together
+    g.r0 = min((int)threadIdx.x * VEC, M - VEC);          // threads beyond the column shadow its last rows
     g.lane = threadIdx.x & 31; g.warp = threadIdx.x >> 5;
     g.multi_warp = blockDim.x > 32;
-    const int M = a.M, N = a.N;
-    g.ring = reinterpret_cast<Real *>(tb_smem);
-    g.fring = g.ring + (size_t)3 * TB_R * M;
-    g.bars = s_bars;
+    g.colb = (unsigned)(M * sizeof(Real));
+    g.ring0 = smem_u32(tb_smem);
+    g.fring0 = g.ring0 + 3u * TB_R * g.colb;
+    g.ring_t = g.ring0 + (unsigned)(g.r0 * sizeof(Real));
+    g.fring_t = g.fring0 + (unsigned)(g.r0 * sizeof(Real));
+    g.bars = smem_u32(s_bars);
     g.k0 = 0; g.cl = 0;
     if (RING) {
         if (threadIdx.x == 0) {
 #pragma unroll
-            for (int i = 0; i < TB_R; ++i) mbar_init(&s_bars[i], 1);
+            for (int i = 0; i < TB_R; ++i) mbar_init(g.bars + 8u * i, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
@@ -323,6 +368,7 @@ __global__ void __launch_bounds__(MAXT, MINB) pdps_tblock_kernel(const TBlockArg
         const int c_end = ((c1 == N) ? N : c1) + 2 * (T - 1);          // last march step
         const int c_lo = cs + 1 + 2 * (T - 1);                         // steady state: every stage forms
         const int c_hi = min(c1 + T - 1, N - 1);                       // and finishes a column per step
+        g.cl = c_hi;                                                   // last column loaded
 
         TBStage<Real, VEC> A[T], B[T];
 #pragma unroll
@@ -332,8 +378,7 @@ __global__ void __launch_bounds__(MAXT, MINB) pdps_tblock_kernel(const TBlockArg
                 A[s].xb[v] = A[s].d1[v] = A[s].y1[v] = A[s].y2[v] = A[s].xn[v] = A[s].f[v] = A[s].o1[v] = A[s].o2[v] = 0;
             B[s] = A[s];
         }
-        if (g.rows_ok && cs > 0) IO::ld(g.y2in + (size_t)(cs - 1) * M + g.r0, A[0].y2);
-        g.cl = c_hi;                                                   // last column loaded
+        if (cs > 0) IO::ld(g.y2in + (size_t)(cs - 1) * M + g.r0, A[0].y2);
         if (RING && threadIdx.x == 0) {
 #pragma unroll
             for (int i = 0; i < TB_PF; ++i)
