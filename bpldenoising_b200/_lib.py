@@ -32,7 +32,7 @@ class Stats(C.Structure):
                 ("pdps_iterations", C.c_longlong), ("pixel_iterations", C.c_longlong),
                 ("solver_iterations", C.c_longlong), ("kernel_launches", C.c_longlong),
                 ("solver_max_relres", C.c_double), ("pdps_kernel_used", C.c_int),
-                ("n_devices", C.c_int), ("reserved", C.c_int * 6)]
+                ("n_devices", C.c_int), ("tblock_depth", C.c_int), ("reserved", C.c_int * 5)]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}

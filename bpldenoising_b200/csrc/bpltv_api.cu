@@ -329,7 +329,8 @@ static int run_tblock_passes(Dev &d, const Real *f, int M, int N, int O, Real al
 // order) the denoised stack is in *u_result (one of the ping-pong buffers).
 template <typename Real>
 static int run_pdps(Dev &d, const Real *f, int M, int N, int O, double alpha_s, const Real *alpha_map,
-                    const bpltv_pdps_opts &o, cudaStream_t st, const Real **u_result, int *kernel_used)
+                    const bpltv_pdps_opts &o, cudaStream_t st, const Real **u_result, int *kernel_used,
+                    int *depth_used = nullptr)
 {
     if (O == 0) { *u_result = nullptr; return 0; }
     const size_t n = (size_t)M * N * O;
@@ -348,6 +349,8 @@ static int run_pdps(Dev &d, const Real *f, int M, int N, int O, double alpha_s, 
         if (resident_eligible<Real>(d.smem_optin, M, N) && !rho &&
             O * resident_cluster_size<Real>(d.smem_optin, M, N) <= env_int("BPLTV_RESIDENT_MAX_WAVES", 4) * d.sm_count)
             kernel = BPLTV_KERNEL_RESIDENT;
+        else if (tblock_vec<Real>(M) && !rho && o.maxiter >= 2 && env_int("BPLTV_AUTO_TBLOCK", 1))
+            kernel = BPLTV_KERNEL_TBLOCK;   // streaming, T iterations per HBM pass
         else
             kernel = march_vec<Real>(M) ? BPLTV_KERNEL_MARCH : BPLTV_KERNEL_GENERIC;
     }
@@ -357,12 +360,13 @@ static int run_pdps(Dev &d, const Real *f, int M, int N, int O, double alpha_s, 
         return fail(BPLTV_ERR_ARG, "march PDPS kernel does not take M=%d", M);
     int tdepth = 1;
     if (kernel == BPLTV_KERNEL_TBLOCK) {
-        tdepth = o.tblock > 0 ? o.tblock : env_int("BPLTV_TBLOCK_T", 2);
+        tdepth = o.tblock > 0 ? o.tblock : env_int("BPLTV_TBLOCK_T", strict ? 2 : 4);
         if (tdepth < 1 || tdepth > 4) return fail(BPLTV_ERR_ARG, "temporal blocking depth must be 1..4 (got %d)", tdepth);
         if (!tblock_vec<Real>(M) || rho)
             return fail(BPLTV_ERR_ARG, "temporally blocked PDPS kernel does not take M=%d (rho=%g)", M, o.rho);
     }
     *kernel_used = kernel;
+    if (depth_used) *depth_used = tdepth;
 
     RC_TRY(upload_steps<Real>(d, o, st));
     const StepConsts<Real> *steps = d.steps.as<StepConsts<Real>>();
@@ -573,9 +577,10 @@ static int denoise_impl(bpltv_ctx *ctx, const double *noisy, int M, int N, int O
         CU_TRY(cudaEventRecord(d.ev[1], st));
         double alpha_s; const Real *amap;
         RC_TRY(prepare_lambda<Real>(d, lam, lm, ln, M, N, st, &alpha_s, &amap));
-        const Real *u = nullptr; int used = 0;
-        RC_TRY(run_pdps<Real>(d, f, M, N, oc, alpha_s, amap, o, st, &u, &used));
+        const Real *u = nullptr; int used = 0, depth = 1;
+        RC_TRY(run_pdps<Real>(d, f, M, N, oc, alpha_s, amap, o, st, &u, &used, &depth));
         ctx->stats.pdps_kernel_used = used;
+        ctx->stats.tblock_depth = depth;
         CU_TRY(cudaEventRecord(d.ev[2], st));
         if (oc > 0) RC_TRY(download_stack<Real>(d, u, plane * oc, u_out + plane * ob, st));
         CU_TRY(cudaEventRecord(d.ev[3], st));
@@ -630,9 +635,10 @@ static int eval_on_device(bpltv_ctx *ctx, Dev &d, const double *lam, int lm, int
     CU_TRY(cudaEventRecord(d.ev[0], st));
     double alpha_s; const Real *amap;
     RC_TRY(prepare_lambda<Real>(d, lam, lm, ln, M, N, st, &alpha_s, &amap));
-    const Real *u = nullptr; int used = 0;
-    RC_TRY(run_pdps<Real>(d, d.noisy.as<Real>(), M, N, O, alpha_s, amap, eo.pdps, st, &u, &used));
+    const Real *u = nullptr; int used = 0, depth = 1;
+    RC_TRY(run_pdps<Real>(d, d.noisy.as<Real>(), M, N, O, alpha_s, amap, eo.pdps, st, &u, &used, &depth));
     ctx->stats.pdps_kernel_used = used;
+    ctx->stats.tblock_depth = depth;
     CU_TRY(cudaEventRecord(d.ev[1], st));
     CU_TRY(cudaMemsetAsync(d_costgrad, 0, (1 + ng) * sizeof(double), st));
     if (O > 0) RC_TRY(run_cost<Real>(d, u, d.truth.as<Real>(), n, d_costgrad, st));
@@ -763,12 +769,13 @@ static int denoise_device_impl(bpltv_ctx *ctx, const void *d_noisy, int M, int N
     d.launches = 0;
     double alpha_s; const Real *amap;
     RC_TRY(prepare_lambda<Real>(d, lam, lm, ln, M, N, st, &alpha_s, &amap));
-    const Real *u = nullptr; int used = 0;
-    RC_TRY(run_pdps<Real>(d, static_cast<const Real *>(d_noisy), M, N, O, alpha_s, amap, o, st, &u, &used));
+    const Real *u = nullptr; int used = 0, depth = 1;
+    RC_TRY(run_pdps<Real>(d, static_cast<const Real *>(d_noisy), M, N, O, alpha_s, amap, o, st, &u, &used, &depth));
     if (O > 0)
         CU_TRY(cudaMemcpyAsync(d_u_out, u, (size_t)M * N * O * sizeof(Real), cudaMemcpyDeviceToDevice, st));
     std::memset(&ctx->stats, 0, sizeof ctx->stats);
     ctx->stats.pdps_kernel_used = used;
+    ctx->stats.tblock_depth = depth;
     ctx->stats.kernel_launches = d.launches;
     ctx->stats.pdps_iterations = o.maxiter;
     ctx->stats.pixel_iterations = (long long)M * N * O * o.maxiter;

@@ -51,7 +51,8 @@ enum bpltv_pdps_kernel {
     BPLTV_KERNEL_GENERIC = 1,  /* any size, one thread per pixel                  */
     BPLTV_KERNEL_MARCH = 2,    /* HBM-streaming column march, one iteration/launch */
     BPLTV_KERNEL_RESIDENT = 3, /* whole image on chip for all iterations           */
-    BPLTV_KERNEL_TBLOCK = 4    /* temporally blocked streaming                     */
+    BPLTV_KERNEL_TBLOCK = 4    /* temporally blocked streaming: T iterations per HBM
+                                  pass, software-pipelined along the column march   */
 };
 
 /* Inner solver parameters = `denoising_default_params`
@@ -67,7 +68,8 @@ typedef struct bpltv_pdps_opts {
     int init_mode;  /* S3: 0 → x⁰ = 0 (default), 1 → x⁰ = f                 */
     int arith;      /* enum bpltv_arith                                     */
     int kernel;     /* enum bpltv_pdps_kernel                               */
-    int tblock;     /* temporal blocking depth for BPLTV_KERNEL_TBLOCK (0=auto) */
+    int tblock;     /* temporal blocking depth T of BPLTV_KERNEL_TBLOCK, 2..4
+                       (0 = auto: 2 in strict, 4 in fast arithmetic)          */
     int reserved[4];
 } bpltv_pdps_opts;
 
@@ -96,7 +98,8 @@ typedef struct bpltv_stats {
     double solver_max_relres;    /* worst final relative residual over images  */
     int pdps_kernel_used;        /* enum bpltv_pdps_kernel actually dispatched */
     int n_devices;
-    int reserved[6];
+    int tblock_depth;            /* PDPS iterations per HBM pass of that kernel (1 unless TBLOCK) */
+    int reserved[5];
 } bpltv_stats;
 
 void bpltv_default_pdps_opts(bpltv_pdps_opts *o);
