@@ -290,7 +290,7 @@ static int tblock_vec(int M)
 // of iterations done (the caller finishes the remainder with kernel A).
 template <typename Real, int T>
 static int run_tblock_passes(Dev &d, const Real *f, int M, int N, int O, Real alpha_s, const Real *alpha_map,
-                             bool strict, int it0, int iters, cudaStream_t st, int *buf)
+                             bool strict, int it0, int iters, cudaStream_t st, int *buf, const BatchMap<Real> &bm)
 {
     const int vec = tblock_vec<Real>(M);
     const int nthreads = (M / vec + 31) / 32 * 32;
@@ -309,7 +309,7 @@ static int run_tblock_passes(Dev &d, const Real *f, int M, int N, int O, Real al
     if (env_int("BPLTV_MARCH_CHUNK", 0) > 0)  // test hook: force a range length
         grid = (cols + env_int("BPLTV_MARCH_CHUNK", 0) - 1) / env_int("BPLTV_MARCH_CHUNK", 0);
     TBlockArgs<Real, T> a;
-    a.f = f; a.alpha_map = alpha_map; a.M = M; a.N = N; a.O = O; a.total_cols = cols; a.alpha_s = alpha_s;
+    a.f = f; a.alpha_map = alpha_map; a.M = M; a.N = N; a.O = O; a.total_cols = cols; a.alpha_s = alpha_s; a.bm = bm;
     const StepConsts<Real> *hsteps = reinterpret_cast<const StepConsts<Real> *>(d.steps_host.data());
     int done = 0;
     for (int it = it0; it + T <= it0 + iters; it += T) {
@@ -330,7 +330,7 @@ static int run_tblock_passes(Dev &d, const Real *f, int M, int N, int O, Real al
 template <typename Real>
 static int run_pdps(Dev &d, const Real *f, int M, int N, int O, double alpha_s, const Real *alpha_map,
                     const bpltv_pdps_opts &o, cudaStream_t st, const Real **u_result, int *kernel_used,
-                    int *depth_used = nullptr)
+                    int *depth_used = nullptr, const BatchMap<Real> *bmap = nullptr)
 {
     if (O == 0) { *u_result = nullptr; return 0; }
     const size_t n = (size_t)M * N * O;
@@ -342,6 +342,7 @@ static int run_pdps(Dev &d, const Real *f, int M, int N, int O, double alpha_s, 
     const bool strict = o.arith == BPLTV_ARITH_STRICT;
     const bool rho = o.rho != 0.0;
     const bool map = alpha_map != nullptr;
+    const BatchMap<Real> bm = bmap ? *bmap : BatchMap<Real>();
 
     int kernel = o.kernel;
     if (kernel == BPLTV_KERNEL_AUTO) kernel = env_int("BPLTV_PDPS_KERNEL", 0);
@@ -376,7 +377,7 @@ static int run_pdps(Dev &d, const Real *f, int M, int N, int O, double alpha_s, 
         ResidentArgs<Real> a;
         a.f = f; a.u_out = d.x[0].as<Real>(); a.alpha_map = alpha_map; a.steps = steps;
         a.maxiter = o.maxiter; a.M = M; a.N = N; a.O = O; a.NC = 0; a.alpha_s = (Real)alpha_s;
-        a.init_mode = o.init_mode;
+        a.init_mode = o.init_mode; a.bm = bm;
         cudaError_t e = launch_resident<Real>(a, d.smem_optin, map, strict, st);
         if (e != cudaSuccess) {
             cudaGetLastError();
@@ -388,8 +389,12 @@ static int run_pdps(Dev &d, const Real *f, int M, int N, int O, double alpha_s, 
     }
 
     // x⁰ = 0 | f (S3), y⁰ = 0
-    if (o.init_mode) CU_TRY(cudaMemcpyAsync(d.x[0].p, f, n * sizeof(Real), cudaMemcpyDeviceToDevice, st));
-    else CU_TRY(cudaMemsetAsync(d.x[0].p, 0, n * sizeof(Real), st));
+    if (o.init_mode) {
+        const int Of = bm.f_mod ? bm.f_mod : O;   // a sweep's virtual stack repeats the Of images of f
+        for (int v0 = 0; v0 < O; v0 += Of)
+            CU_TRY(cudaMemcpyAsync(d.x[0].as<Real>() + (size_t)v0 * M * N, f,
+                                   (size_t)std::min(Of, O - v0) * M * N * sizeof(Real), cudaMemcpyDeviceToDevice, st));
+    } else CU_TRY(cudaMemsetAsync(d.x[0].p, 0, n * sizeof(Real), st));
     CU_TRY(cudaMemsetAsync(d.y1[0].p, 0, n * sizeof(Real), st));
     CU_TRY(cudaMemsetAsync(d.y2[0].p, 0, n * sizeof(Real), st));
 
@@ -397,9 +402,9 @@ static int run_pdps(Dev &d, const Real *f, int M, int N, int O, double alpha_s, 
     int it_begin = 0;  // iterations already done
     if (kernel == BPLTV_KERNEL_TBLOCK && tdepth > 1) {
         int done = 0;
-        if (tdepth == 2) done = run_tblock_passes<Real, 2>(d, f, M, N, O, (Real)alpha_s, alpha_map, strict, 0, o.maxiter, st, &buf);
-        else if (tdepth == 3) done = run_tblock_passes<Real, 3>(d, f, M, N, O, (Real)alpha_s, alpha_map, strict, 0, o.maxiter, st, &buf);
-        else done = run_tblock_passes<Real, 4>(d, f, M, N, O, (Real)alpha_s, alpha_map, strict, 0, o.maxiter, st, &buf);
+        if (tdepth == 2) done = run_tblock_passes<Real, 2>(d, f, M, N, O, (Real)alpha_s, alpha_map, strict, 0, o.maxiter, st, &buf, bm);
+        else if (tdepth == 3) done = run_tblock_passes<Real, 3>(d, f, M, N, O, (Real)alpha_s, alpha_map, strict, 0, o.maxiter, st, &buf, bm);
+        else done = run_tblock_passes<Real, 4>(d, f, M, N, O, (Real)alpha_s, alpha_map, strict, 0, o.maxiter, st, &buf, bm);
         if (done < 0) { cudaGetLastError(); return fail(BPLTV_ERR_CUDA, "temporally blocked PDPS kernel: occupancy query failed"); }
         it_begin = done;  // the remainder (< T iterations) runs as single-iteration passes below
     }
@@ -422,7 +427,7 @@ static int run_pdps(Dev &d, const Real *f, int M, int N, int O, double alpha_s, 
         MarchArgs<Real> a;
         a.f = f; a.alpha_map = alpha_map; a.M = M; a.N = N; a.O = O; a.total_cols = cols;
         a.prefetch_dist = env_int("BPLTV_MARCH_PREFETCH", 0);
-        a.alpha_s = (Real)alpha_s; a.rho = (Real)o.rho;
+        a.alpha_s = (Real)alpha_s; a.rho = (Real)o.rho; a.bm = bm;
         const StepConsts<Real> *hsteps = reinterpret_cast<const StepConsts<Real> *>(d.steps_host.data());
         for (int it = it_begin; it < o.maxiter; ++it) {
             const int bi = buf, bo = bi ^ 1;
@@ -436,7 +441,7 @@ static int run_pdps(Dev &d, const Real *f, int M, int N, int O, double alpha_s, 
     } else {
         GenericArgs<Real> a;
         a.f = f; a.alpha_map = alpha_map; a.steps = steps; a.M = M; a.N = N; a.O = O;
-        a.alpha_s = (Real)alpha_s; a.rho = (Real)o.rho;
+        a.alpha_s = (Real)alpha_s; a.rho = (Real)o.rho; a.bm = bm;
         if (N > 65535 || O > 65535) return fail(BPLTV_ERR_ARG, "generic kernel: N and O must be <= 65535");
         for (int it = 0; it < o.maxiter; ++it) {
             const int bi = it & 1, bo = bi ^ 1;
@@ -708,6 +713,91 @@ static int learn_eval_impl(bpltv_ctx *ctx, const double *lam, int lm, int ln, do
     return 0;
 }
 
+// λ-sweep: L parameter sets × the resident images as ONE batch of independent solves
+// (virtual image v = l·O_dev + o on each device), then 0.5‖u-ū‖² per set.
+template <typename Real>
+static int sweep_impl(bpltv_ctx *ctx, const double *lams, int L, int lm, int ln, const bpltv_pdps_opts &o,
+                      double *cost_out, double *sqerr_out, double *u_out)
+{
+    const int ndev = (int)ctx->devs.size();
+    const int M = ctx->M, N = ctx->N, O = ctx->O, ng = lm * ln;
+    const size_t plane = (size_t)M * N;
+    const bool scalar = ng == 1;
+    std::memset(&ctx->stats, 0, sizeof ctx->stats);
+    std::vector<std::vector<double>> host(ndev);
+    for (int di = 0; di < ndev; ++di) {
+        Dev &d = ctx->devs[di];
+        CU_TRY(cudaSetDevice(d.id));
+        d.launches = 0;
+        const int V = L * d.O;
+        host[di].assign((size_t)std::max(V, 1), 0.0);
+        if (V == 0) continue;
+        cudaStream_t st = d.stream;
+        CU_TRY(cudaEventRecord(d.ev[0], st));
+        RC_TRY(d.lam_dev.ensure((size_t)L * ng * sizeof(double)));
+        CU_TRY(cudaMemcpyAsync(d.lam_dev.p, lams, (size_t)L * ng * sizeof(double), cudaMemcpyHostToDevice, st));
+        BatchMap<Real> bm;
+        bm.f_mod = d.O; bm.lam_div = d.O;
+        const Real *amap = nullptr;
+        if (scalar) {
+            RC_TRY(d.amap.ensure((size_t)L * sizeof(Real)));
+            convert_kernel<Real, double><<<(L + 255) / 256, 256, 0, st>>>(d.lam_dev.as<double>(), d.amap.as<Real>(), (size_t)L);
+            bm.alpha_vec = d.amap.as<Real>();
+        } else {
+            RC_TRY(d.amap.ensure((size_t)L * plane * sizeof(Real)));
+            const size_t tot = (size_t)L * plane;
+            patch_upsample_sets_kernel<Real><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d.lam_dev.as<double>(), L, lm, ln,
+                                                                                        d.amap.as<Real>(), M, N);
+            bm.map_stride = (long long)plane;
+            amap = d.amap.as<Real>();
+        }
+        d.launches += 1;
+        CU_TRY(cudaEventRecord(d.ev[1], st));
+        const Real *u = nullptr; int used = 0, depth = 1;
+        RC_TRY(run_pdps<Real>(d, d.noisy.as<Real>(), M, N, V, 0.0, amap, o, st, &u, &used, &depth, &bm));
+        ctx->stats.pdps_kernel_used = used;
+        ctx->stats.tblock_depth = depth;
+        CU_TRY(cudaEventRecord(d.ev[2], st));
+        RC_TRY(d.partials.ensure(std::max<size_t>((size_t)V, 1024) * sizeof(double)));
+        sqerr_image_kernel<Real><<<V, 256, 0, st>>>(u, d.truth.as<Real>(), (int)plane, d.O, d.partials.as<double>());
+        d.launches += 1;
+        CU_TRY(cudaMemcpyAsync(host[di].data(), d.partials.p, (size_t)V * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaEventRecord(d.ev[3], st));
+        if (u_out)
+            for (int l = 0; l < L; ++l)
+                RC_TRY(download_stack<Real>(d, u + (size_t)l * d.O * plane, plane * d.O,
+                                            u_out + ((size_t)l * O + d.o_begin) * plane, st));
+        CU_TRY(cudaEventRecord(d.ev[4], st));
+    }
+    for (int l = 0; l < L; ++l) cost_out[l] = 0.0;
+    for (int di = 0; di < ndev; ++di) {  // fixed device and image order: deterministic sums
+        Dev &d = ctx->devs[di];
+        if (L * d.O == 0) continue;
+        CU_TRY(cudaSetDevice(d.id));
+        CU_TRY(cudaStreamSynchronize(d.stream));
+        for (int l = 0; l < L; ++l)
+            for (int oo = 0; oo < d.O; ++oo) {
+                const double v = host[di][(size_t)l * d.O + oo];
+                cost_out[l] += v;
+                if (sqerr_out) sqerr_out[(size_t)l * O + d.o_begin + oo] = v;
+            }
+        ctx->stats.ms_upload = std::max<double>(ctx->stats.ms_upload, ev_ms(d.ev[0], d.ev[1]));
+        ctx->stats.ms_pdps = std::max<double>(ctx->stats.ms_pdps, ev_ms(d.ev[1], d.ev[2]));
+        ctx->stats.ms_cost = std::max<double>(ctx->stats.ms_cost, ev_ms(d.ev[2], d.ev[3]));
+        ctx->stats.ms_download = std::max<double>(ctx->stats.ms_download, ev_ms(d.ev[3], d.ev[4]));
+        ctx->stats.ms_total = std::max<double>(ctx->stats.ms_total, ev_ms(d.ev[0], d.ev[4]));
+        ctx->stats.kernel_launches += d.launches;
+    }
+    for (int l = 0; l < L; ++l) {
+        cost_out[l] *= 0.5;
+        if (!std::isfinite(cost_out[l])) return fail(BPLTV_ERR_NUMERIC, "non-finite cost for parameter set %d", l);
+    }
+    ctx->stats.pdps_iterations = o.maxiter;
+    ctx->stats.pixel_iterations = (long long)plane * O * L * o.maxiter;
+    ctx->stats.n_devices = ndev;
+    return 0;
+}
+
 template <typename Real>
 static int gradient_impl(bpltv_ctx *ctx, const double *u_host, const double *lam, int lm, int ln, int regularised,
                          const bpltv_eval_opts &eo, double *grad_out)
@@ -973,6 +1063,22 @@ int bpltv_gradient(bpltv_ctx *ctx, const double *u, const double *lam, int lm, i
     if (!u || !grad_out) return fail(BPLTV_ERR_ARG, "NULL argument");
     return ctx->prec == 64 ? gradient_impl<double>(ctx, u, lam, lm, ln, regularised, eo, grad_out)
                            : gradient_impl<float>(ctx, u, lam, lm, ln, regularised, eo, grad_out);
+}
+
+int bpltv_sweep(bpltv_ctx *ctx, const double *lams, int L, int lm, int ln, const bpltv_pdps_opts *opts,
+                double *cost_out, double *sqerr_out, double *u_out)
+{
+    if (!ctx || !lams || !cost_out) return fail(BPLTV_ERR_ARG, "NULL argument");
+    if (!ctx->have_dataset) return fail(BPLTV_ERR_STATE, "no resident dataset: call bpltv_set_dataset first");
+    if (L < 1) return fail(BPLTV_ERR_ARG, "need at least one parameter set");
+    for (int l = 0; l < L; ++l) RC_TRY(check_lambda(lams + (size_t)l * lm * ln, lm, ln));
+    if (lm > ctx->M || ln > ctx->N) return fail(BPLTV_ERR_ARG, "lambda grid larger than the image");
+    bpltv_pdps_opts o;
+    if (opts) o = *opts; else bpltv_default_pdps_opts(&o);
+    RC_TRY(check_pdps_opts(o));
+    if ((double)ctx->M * ctx->N * std::max(ctx->O, 1) * L > 4.0e9) return fail(BPLTV_ERR_ARG, "sweep too large: split the parameter range");
+    return ctx->prec == 64 ? sweep_impl<double>(ctx, lams, L, lm, ln, o, cost_out, sqerr_out, u_out)
+                           : sweep_impl<float>(ctx, lams, L, lm, ln, o, cost_out, sqerr_out, u_out);
 }
 
 // ---- device-resident variants (single device) --------------------------------

@@ -17,6 +17,7 @@ struct GenericArgs {
     int it;
     int M, N, O;
     Real alpha_s, rho;
+    BatchMap<Real> bm;
 };
 
 // x̄ at pixel (i,j) of image base pointers; also returns x_new through xn.
@@ -41,7 +42,7 @@ __global__ void __launch_bounds__(256) pdps_generic_kernel(const GenericArgs<Rea
     const int o = blockIdx.z;
     if (i >= M) return;
     const size_t img = (size_t)o * M * N;
-    const Real *x = a.x_in + img, *f = a.f + img, *y1 = a.y1_in + img, *y2 = a.y2_in + img;
+    const Real *x = a.x_in + img, *f = a.f + (size_t)a.bm.f_image(o) * M * N, *y1 = a.y1_in + img, *y2 = a.y2_in + img;
     const StepConsts<Real> sc = a.steps[a.it];
     const size_t k = (size_t)j * M + i;
 
@@ -57,7 +58,7 @@ __global__ void __launch_bounds__(256) pdps_generic_kernel(const GenericArgs<Rea
         d2 = STRICT ? StrictOps<Real>::sub(xb2, xb) : xb2 - xb;
     }
     Real v1 = __ldg(y1 + k), v2 = __ldg(y2 + k);
-    const Real al = MAP ? __ldg(a.alpha_map + k) : a.alpha_s;
+    const Real al = MAP ? __ldg(a.alpha_map + (size_t)a.bm.lam_set(o) * a.bm.map_stride + k) : a.bm.scalar(o, a.alpha_s);
     if (a.rho != (Real)0) dual_update_rho<Real, STRICT>(v1, v2, d1, d2, al, a.rho, sc);
     else dual_update<Real, STRICT, false>(v1, v2, d1, d2, al, a.rho, sc);
     a.x_out[img + k] = xn;
@@ -75,6 +76,38 @@ __global__ void patch_upsample_kernel(const double *lam, int lm, int ln, Real *m
     const int i = k % M, j = k / M;
     const int pi = (int)(((long long)i * lm) / M), pj = (int)(((long long)j * ln) / N);
     map[k] = (Real)lam[pi + (size_t)lm * pj];
+}
+
+// L parameter sets at once: set l → map + l·M·N (λ-sweeps over patch grids)
+template <typename Real>
+__global__ void patch_upsample_sets_kernel(const double *lam, int L, int lm, int ln, Real *map, int M, int N)
+{
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t plane = (size_t)M * N;
+    if (k >= plane * L) return;
+    const int l = (int)(k / plane);
+    const int q = (int)(k - (size_t)l * plane);
+    const int i = q % M, j = q / M;
+    const int pi = (int)(((long long)i * lm) / M), pj = (int)(((long long)j * ln) / N);
+    map[k] = (Real)lam[(size_t)l * lm * ln + pi + (size_t)lm * pj];
+}
+
+// Σ (u_v - ū_{v % f_mod})² of virtual image v = blockIdx.x (deterministic per image)
+template <typename Real>
+__global__ void __launch_bounds__(256) sqerr_image_kernel(const Real *u, const Real *ubar, int plane, int f_mod,
+                                                         double *out)
+{
+    __shared__ double smem[32];
+    const int v = blockIdx.x;
+    const Real *uv = u + (size_t)v * plane;
+    const Real *ub = ubar + (size_t)(f_mod ? v % f_mod : v) * plane;
+    double acc = 0.0;
+    for (int k = threadIdx.x; k < plane; k += blockDim.x) {
+        const double d = (double)uv[k] - (double)ub[k];
+        acc = fma(d, d, acc);
+    }
+    const double s = block_sum(acc, smem);
+    if (threadIdx.x == 0) out[v] = s;
 }
 
 template <typename Dst, typename Src>

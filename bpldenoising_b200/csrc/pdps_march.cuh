@@ -35,6 +35,7 @@ struct MarchArgs {
     long long total_cols;             // N·O
     int prefetch_dist;                // columns of L2 look-ahead (0 = off)
     Real alpha_s, rho;
+    BatchMap<Real> bm;
 };
 
 static __device__ __forceinline__ void prefetch_l2(const void *p)
@@ -68,13 +69,16 @@ __global__ void __launch_bounds__(MAXT, MINB) pdps_march_kernel(const MarchArgs<
         const int c1 = (int)min((long long)N, (long long)c0 + (g_end - g));  // exclusive
         g += c1 - c0;
         const size_t img = (size_t)o * M * N;
-        const Real *xin = a.x_in + img, *y1in = a.y1_in + img, *y2in = a.y2_in + img, *fin = a.f + img;
+        const Real *xin = a.x_in + img, *y1in = a.y1_in + img, *y2in = a.y2_in + img;
+        const Real *fin = a.f + (size_t)a.bm.f_image(o) * M * N;
+        const Real *amap = MAP ? a.alpha_map + (size_t)a.bm.lam_set(o) * a.bm.map_stride : nullptr;
+        const Real alpha_s = a.bm.scalar(o, a.alpha_s);
         Real *xout = a.x_out + img, *y1out = a.y1_out + img, *y2out = a.y2_out + img;
 
         // state of the previous column (c-1): x̄, Δy1 = x̄(i+1)-x̄(i), old duals, λ
         Real xb_p[VEC], d1_p[VEC], y1_p[VEC], y2_p[VEC], al_p[VEC];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) { xb_p[v] = d1_p[v] = y1_p[v] = y2_p[v] = 0; al_p[v] = a.alpha_s; }
+        for (int v = 0; v < VEC; ++v) { xb_p[v] = d1_p[v] = y1_p[v] = y2_p[v] = 0; al_p[v] = alpha_s; }
         // y2 of column c0-1 (zero left of the image)
         if (rows_ok && c0 > 0) IO::ld(y2in + (size_t)(c0 - 1) * M + r0, y2_p);
 
@@ -83,14 +87,14 @@ __global__ void __launch_bounds__(MAXT, MINB) pdps_march_kernel(const MarchArgs<
         for (int c = c0; c <= c_last; ++c) {
             Real x_c[VEC], f_c[VEC], y1_c[VEC], y2_c[VEC], al_c[VEC], up_c = 0;
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) { x_c[v] = f_c[v] = y1_c[v] = y2_c[v] = 0; al_c[v] = a.alpha_s; }
+            for (int v = 0; v < VEC; ++v) { x_c[v] = f_c[v] = y1_c[v] = y2_c[v] = 0; al_c[v] = alpha_s; }
             if (rows_ok) {
                 const size_t off = (size_t)c * M + r0;
                 IO::ld(xin + off, x_c);
                 IO::ld(fin + off, f_c);
                 IO::ld(y1in + off, y1_c);
                 IO::ld(y2in + off, y2_c);
-                if (MAP) IO::ld(a.alpha_map + off, al_c);
+                if (MAP) IO::ld(amap + off, al_c);
                 // y1 of the row above this warp's first row belongs to another warp: read it from
                 // memory (it is an input of this launch, so any copy is current)
                 if (lane == 0 && r0 > 0) up_c = __ldg(y1in + off - 1);
@@ -136,7 +140,7 @@ __global__ void __launch_bounds__(MAXT, MINB) pdps_march_kernel(const MarchArgs<
                 for (int v = 0; v < VEC; ++v) {
                     const Real d2 = STRICT ? StrictOps<Real>::sub(xb_c[v], xb_p[v]) : xb_c[v] - xb_p[v];
                     o1[v] = y1_p[v]; o2[v] = y2_p[v];
-                    const Real al = MAP ? al_p[v] : a.alpha_s;
+                    const Real al = MAP ? al_p[v] : alpha_s;
                     if (has_rho) dual_update_rho<Real, STRICT>(o1[v], o2[v], d1_p[v], d2, al, a.rho, sc);
                     else dual_update<Real, STRICT, false>(o1[v], o2[v], d1_p[v], d2, al, a.rho, sc);
                 }
@@ -159,7 +163,7 @@ __global__ void __launch_bounds__(MAXT, MINB) pdps_march_kernel(const MarchArgs<
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
                 o1[v] = y1_p[v]; o2[v] = y2_p[v];
-                const Real al = MAP ? al_p[v] : a.alpha_s;
+                const Real al = MAP ? al_p[v] : alpha_s;
                 if (has_rho) dual_update_rho<Real, STRICT>(o1[v], o2[v], d1_p[v], (Real)0, al, a.rho, sc);
                 else dual_update<Real, STRICT, false>(o1[v], o2[v], d1_p[v], (Real)0, al, a.rho, sc);
             }

@@ -37,6 +37,7 @@ struct ResidentArgs {
     int maxiter, M, N, O, init_mode;
     int NC;  // columns per CTA
     Real alpha_s;
+    BatchMap<Real> bm;
 };
 
 template <typename Real> struct Vec2T;
@@ -84,6 +85,9 @@ __global__ void __launch_bounds__(RES_THREADS, 1) pdps_resident_kernel(const Res
     const bool t_ok = cgrp < CG;            // threads beyond CG·tpc idle (still hit the barriers)
     const int c_begin = rank * NC;
     const size_t img = (size_t)o * M * N;
+    const size_t fimg = (size_t)a.bm.f_image(o) * M * N;
+    const Real *amap = MAP ? a.alpha_map + (size_t)a.bm.lam_set(o) * a.bm.map_stride : nullptr;
+    const Real alpha_s = a.bm.scalar(o, a.alpha_s);
 
     const int lane = threadIdx.x & 31;
     Real x[KC][2], f[KC][2], al[KC][2];
@@ -96,11 +100,11 @@ __global__ void __launch_bounds__(RES_THREADS, 1) pdps_resident_kernel(const Res
         okw[k] = __any_sync(0xffffffffu, ok[k]);
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
-            f[k][v] = 0; x[k][v] = 0; al[k][v] = a.alpha_s;
+            f[k][v] = 0; x[k][v] = 0; al[k][v] = alpha_s;
             if (ok[k]) {
                 const size_t idx = (size_t)jg * M + r0 + v;
-                f[k][v] = a.f[img + idx];
-                if (MAP) al[k][v] = a.alpha_map[idx];
+                f[k][v] = a.f[fimg + idx];
+                if (MAP) al[k][v] = amap[idx];
                 x[k][v] = a.init_mode ? f[k][v] : (Real)0;
             }
         }

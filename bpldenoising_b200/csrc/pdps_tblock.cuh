@@ -105,6 +105,7 @@ struct TBlockArgs {
     int M, N, O;
     long long total_cols;             // N·O
     Real alpha_s;
+    BatchMap<Real> bm;
 };
 
 // What one pipeline stage keeps from step to step (registers).
@@ -360,7 +361,10 @@ __global__ void __launch_bounds__(MAXT, MINB) pdps_tblock_kernel(const TBlockArg
         const int c1 = (int)min((long long)N, (long long)c0 + (g_end - gc));  // exclusive
         gc += c1 - c0;
         const size_t img = (size_t)o * M * N;
-        g.xin = a.x_in + img; g.y1in = a.y1_in + img; g.y2in = a.y2_in + img; g.fin = a.f + img;
+        g.xin = a.x_in + img; g.y1in = a.y1_in + img; g.y2in = a.y2_in + img;
+        g.fin = a.f + (size_t)a.bm.f_image(o) * M * N;
+        if (MAP) g.amap = a.alpha_map + (size_t)a.bm.lam_set(o) * a.bm.map_stride;
+        g.alpha_s = a.bm.scalar(o, a.alpha_s);
         g.xout = a.x_out + img; g.y1out = a.y1_out + img; g.y2out = a.y2_out + img;
         g.c0 = c0; g.c1 = c1;
         const int cs = max(0, c0 - (T - 1));                           // first marched column

@@ -7,7 +7,51 @@ datasets (/root/reference/src/Datasets.jl:54-65).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
+
+# /root/reference/src/Datasets.jl:11-17
+remotedatasets = ["cameraman_128_5", "cameraman_128_10", "faces_train_128_10", "faces_val_128_10", "circle_128_10"]
+
+
+def full_datasetname(datasetname: str) -> str:
+    """First known dataset whose name starts with `datasetname` (Datasets.jl:27-49); the
+    reference falls back to a fuzzy match and otherwise throws ArgumentError — here ValueError."""
+    for name in remotedatasets:
+        if name.startswith(datasetname):
+            return name
+    raise ValueError(f'"{datasetname}" not found in remotedatasets {remotedatasets}')
+
+
+def load_dataset(datasetfiles: str):
+    """load_dataset (Datasets.jl:54-65): `filelist.txt` holds one `true.png,data.png` pair per
+    line; 8-bit grey PNGs become k/255 in M×N×O Float64 stacks (column-major).  → (true, data)."""
+    from PIL import Image
+    with open(os.path.join(datasetfiles, "filelist.txt")) as fh:
+        pairs = [ln.strip() for ln in fh if ln.strip()]
+
+    def read(name):
+        im = Image.open(os.path.join(datasetfiles, name))
+        if im.mode == "1":                      # circle truth: 1-bit → {0, 1}
+            return np.asarray(im, dtype=np.float64)
+        return np.asarray(im.convert("L"), dtype=np.float64) / 255.0
+
+    first = read(pairs[0].split(",")[0])
+    M, N = first.shape
+    true_images = np.zeros((M, N, len(pairs)), order="F")
+    data_images = np.zeros((M, N, len(pairs)), order="F")
+    for i, pair in enumerate(pairs):
+        t, d = pair.split(",")[:2]
+        true_images[:, :, i] = read(t)
+        data_images[:, :, i] = read(d)
+    return true_images, data_images
+
+
+def testdataset(datasetname: str, dataset_dir: str = "BPLDenoising/datasets/"):
+    """testdataset(datasetname) (Datasets.jl:19-25); the reference resolves `dataset_dir`
+    relative to the current working directory (Datasets.jl:9)."""
+    return load_dataset(os.path.join(dataset_dir, full_datasetname(datasetname)))
 
 
 def synthetic_dataset(M: int, N: int, O: int, seed: int = 20240601, noise: float = 0.1):

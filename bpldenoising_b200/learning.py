@@ -160,6 +160,41 @@ class Context:
                                      int(bool(regularised)), C.byref(o), _ptr(grad)))
         return float(grad[0, 0]) if scalar else grad
 
+    # ---- λ-sweeps (cost curves, validation) ------------------------------------------
+    def sweep(self, parameters, opts: Optional[PdpsOpts] = None, return_u: bool = False,
+              return_sqerr: bool = False):
+        """All parameter sets × the resident images as ONE batch of independent solves.
+        `parameters`: sequence of L scalars, or of L equally shaped 2-D grids.  Returns
+        costs (L,), and optionally per-image squared errors (O, L) and u (M, N, O, L)."""
+        if self.shape is None:
+            raise _lib.BpltvError(-4, "no resident dataset: call set_dataset first")
+        ps = [np.asarray(p, dtype=np.float64) for p in parameters]
+        if not ps:
+            raise ValueError("empty parameter range")
+        if ps[0].ndim == 0:
+            lm = ln = 1
+        elif ps[0].ndim == 2:
+            lm, ln = ps[0].shape
+        else:
+            raise ValueError("parameters must be scalars or 2-D grids")
+        if any(p.shape != ps[0].shape for p in ps):
+            raise ValueError("all parameter sets must have the same shape")
+        L = len(ps)
+        lams = np.ascontiguousarray(np.stack([np.asfortranarray(p.reshape(lm, ln)).ravel(order="F") for p in ps]))
+        o = opts if opts is not None else pdps_opts()
+        M, N, O = self.shape
+        costs = np.zeros(L)
+        sq = np.zeros((O, L), order="F") if return_sqerr else None
+        u = np.zeros((M, N, O, L), order="F") if return_u else None
+        check(self._L.bpltv_sweep(self._h, _ptr(lams), L, lm, ln, C.byref(o), _ptr(costs),
+                                  _ptr(sq) if return_sqerr else None, _ptr(u) if return_u else None))
+        out = [costs]
+        if return_sqerr:
+            out.append(sq)
+        if return_u:
+            out.append(u)
+        return out[0] if len(out) == 1 else tuple(out)
+
     def stats(self) -> dict:
         s = Stats()
         check(self._L.bpltv_get_stats(self._h, C.byref(s)))
@@ -256,3 +291,64 @@ def gradient_reg(α, op, u, ū, ctx: Optional[Context] = None):
     ctx = ctx or default_context()
     _ensure_resident(ctx, (ū, ū))
     return ctx.gradient(α, u, regularised=True)
+
+
+# ------------------------------------------------------------------------------
+# λ-sweeps and validation (/root/reference/src/BPLDenoising.jl:92-111, :128-158, :176-178, :381-415)
+# ------------------------------------------------------------------------------
+def generate_cost(data, parameter_range, num_samples: Optional[int] = None, ctx: Optional[Context] = None,
+                  **kwargs) -> np.ndarray:
+    """generate_cost(dataset, parameter_range, L2CostFunction, TVDenoise; num_samples) (:92-111)
+    for a dataset already in memory: costs[i] = 0.5‖TVDenoise(data, parameter_range[i]) - true‖².
+    The reference loops over the range; here the whole range is one batched launch."""
+    ctx = ctx or default_context()
+    truth, noisy = _stack(data[0]), _stack(data[1])
+    if num_samples is not None:
+        truth, noisy = np.asfortranarray(truth[:, :, :num_samples]), np.asfortranarray(noisy[:, :, :num_samples])
+    ctx.set_dataset((truth, noisy))
+    global _resident_key
+    _resident_key = None
+    kwargs.setdefault("maxiter", 10000)   # TVDenoise (:51)
+    return ctx.sweep(list(parameter_range), pdps_opts(**kwargs))
+
+
+def generate_scalar_tv_cost(data, parameter_range, num_samples: int = 1, ctx: Optional[Context] = None, **kwargs):
+    """generate_scalar_tv_cost(dataset, parameter_range; num_samples=1) (:128-130)."""
+    return generate_cost(data, parameter_range, num_samples=num_samples, ctx=ctx, **kwargs)
+
+
+def generate_2d_tv_cost(data, parameter_range_1, parameter_range_2, num_samples: int = 1,
+                        ctx: Optional[Context] = None, **kwargs) -> np.ndarray:
+    """generate_2d_tv_cost (:136-158, :176-178): costs[i, j] for the 2×1 patch parameter
+    α = [range_1[i]; range_2[j]] .* ones(2,1)."""
+    grids = [np.array([[a], [b]], dtype=np.float64) for a in parameter_range_1 for b in parameter_range_2]
+    costs = generate_cost(data, grids, num_samples=num_samples, ctx=ctx, **kwargs)
+    return costs.reshape(len(parameter_range_1), len(parameter_range_2))
+
+
+def validate_tv_parameter(parameter, data, ctx: Optional[Context] = None, **kwargs) -> dict:
+    """validate_tv_parameter(parameter; dataset_name) (:381-415) for a dataset in memory:
+    u = TVDenoise(noisy, parameter); cost; the per-image quality table (orig/out SSIM and
+    PSNR) and its means.  PSNR comes from the device-side per-image squared errors."""
+    from . import quality
+    ctx = ctx or default_context()
+    truth, noisy = _stack(data[0]), _stack(data[1])
+    ctx.set_dataset((truth, noisy))
+    global _resident_key
+    _resident_key = None
+    kwargs.setdefault("maxiter", 10000)
+    costs, sq, u = ctx.sweep([parameter], pdps_opts(**kwargs), return_u=True, return_sqerr=True)
+    u = np.asfortranarray(u[:, :, :, 0])
+    M, N, O = truth.shape
+    rows = []
+    for i in range(O):
+        rows.append({
+            "img_num": i + 1,
+            "orig_ssim": quality.assess_ssim(truth[:, :, i], noisy[:, :, i]),
+            "orig_psnr": quality.assess_psnr(truth[:, :, i], noisy[:, :, i]),
+            "out_ssim": quality.assess_ssim(truth[:, :, i], u[:, :, i]),
+            "out_psnr": quality.psnr_from_sqerr(sq[i, 0], M * N),
+        })
+    return {"u": u, "cost": float(costs[0]), "table": rows,
+            "mean_ssim": float(np.mean([r["out_ssim"] for r in rows])),
+            "mean_psnr": float(np.mean([r["out_psnr"] for r in rows]))}

@@ -141,6 +141,17 @@ int bpltv_learn_eval(bpltv_ctx *ctx, const double *lam, int lm, int ln, double D
 int bpltv_gradient(bpltv_ctx *ctx, const double *u, const double *lam, int lm, int ln,
                    int regularised, const bpltv_eval_opts *opts, double *grad_out);
 
+/* λ-sweep on the resident dataset: replaces the loops `for i: u = denoise_function(data,
+ * parameter_range[i]); costs[i] = cost_function(u, true_)` of generate_cost / generate_2d_cost
+ * (/root/reference/src/BPLDenoising.jl:92-111, :136-158; the reference passes TVDenoise, i.e.
+ * opts->maxiter = 10000, :51).  All L parameter sets × O images are solved as ONE batch of
+ * independent problems.  lams: L consecutive lm×ln column-major grids (lm = ln = 1: scalars).
+ * cost_out[l] = 0.5‖u_l - ū‖² over the whole stack (L2CostFunction, :84-86);
+ * sqerr_out (may be NULL): O×L, ‖u_l[:,:,o] - ū[:,:,o]‖² per image (PSNR of validate_tv_parameter,
+ * :381-415); u_out (may be NULL): M×N×O×L.                                                        */
+int bpltv_sweep(bpltv_ctx *ctx, const double *lams, int L, int lm, int ln,
+                const bpltv_pdps_opts *opts, double *cost_out, double *sqerr_out, double *u_out);
+
 /* Device-resident variants (single-device contexts only): pointers are device
  * memory of the context's precision (double or float), `stream` a cudaStream_t
  * (NULL → the context's stream).  Asynchronous: nothing is synchronised.
