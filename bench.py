@@ -417,6 +417,23 @@ def learn_eval_extras(bp):
             out[name]["learn_run"] = {"seconds": res.seconds, "evaluations": res.evaluations,
                                       "final_cost": res.log[-1].function_value,
                                       "x": np.asarray(res.x).ravel().tolist()}
+    # λ-sweep (generate_scalar_tv_cost, /root/reference/src/BPLDenoising.jl:92-130): 64 parameters ×
+    # 1 image 128×128 × 10000 iterations, batched into one launch vs the reference's loop of solves
+    data = bp.synthetic_dataset(128, 128, 1, seed=7)
+    rng_ = np.geomspace(0.005, 0.5, 64)
+    with bp.Context([0], 64) as c:
+        bp.generate_scalar_tv_cost(data, rng_[:2], ctx=c)
+        t0 = time.perf_counter()
+        costs = bp.generate_scalar_tv_cost(data, rng_, ctx=c)
+        t_batched = time.perf_counter() - t0
+        st = c.stats()
+        t0 = time.perf_counter()
+        for lam_ in rng_[:8]:
+            c.sweep([float(lam_)], bp.pdps_opts(maxiter=10000))
+        t_loop = (time.perf_counter() - t0) * 8
+        out["cost_curve_64x1x128x128_10000its"] = {
+            "seconds_batched": t_batched, "seconds_looped_estimate": t_loop, "kernel": st["pdps_kernel_used"],
+            "gpixel_iter_per_s": 64 * 16384 * 10000 / t_batched / 1e9, "argmin_lambda": float(rng_[int(np.argmin(costs))])}
     return out
 
 

@@ -12,7 +12,7 @@
 # by the equivalent ctypes binding (bpldenoising_b200/_lib.py), which calls the same symbols.
 module BPLTV
 
-export tv_op_learning_function, denoise, TVDenoise, bpltv_context, set_devices!
+export tv_op_learning_function, denoise, TVDenoise, generate_cost, bpltv_context, set_devices!
 
 const lib = get(ENV, "BPLTV_LIB", joinpath(@__DIR__, "..", "bpldenoising_b200", "libbpltv.so"))
 
@@ -102,6 +102,25 @@ function tv_op_learning_function(x, data, Δ; Δt=1e-6, kwargs...)
                 (Ptr{Cvoid}, Ptr{Cdouble}, Cint, Cint, Cdouble, Ref{EvalOpts}, Ptr{Cdouble}, Ref{Cdouble}, Ptr{Cdouble}),
                 h, l, lm, ln, Δ, eo, u, cost, grad))
     return u, cost[], (x isa Real ? grad[1] : grad)   # grad has the shape of x (src/TRBox.jl:63,237)
+end
+
+"""
+generate_cost(true_, data, parameter_range) — the loop of src/BPLDenoising.jl:92-111 / :136-158
+(`u = TVDenoise(data, parameter_range[i]); costs[i] = L2CostFunction(u, true_)`) as ONE batched call:
+all parameter sets × images are independent solves.  `parameter_range`: reals or equally sized matrices.
+"""
+function generate_cost(true_::AbstractArray{<:Real,3}, data::AbstractArray{<:Real,3}, parameter_range; kwargs...)
+    M, N, O = size(data); h = bpltv_context()
+    check(ccall((:bpltv_set_dataset, lib), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cint, Cint),
+                h, Array{Float64,3}(true_), Array{Float64,3}(data), M, N, O))
+    resident[] = nothing
+    ps = [lam(p) for p in parameter_range]; lm, ln = ps[1][2], ps[1][3]
+    lams = reduce(vcat, [vec(p[1]) for p in ps]); L = length(ps)
+    o = Ref(pdps_from((; maxiter=10000, kwargs...))); costs = zeros(L)
+    check(ccall((:bpltv_sweep, lib), Cint,
+                (Ptr{Cvoid}, Ptr{Cdouble}, Cint, Cint, Cint, Ref{PdpsOpts}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                h, lams, L, lm, ln, o, costs, C_NULL, C_NULL))
+    costs
 end
 
 end # module
