@@ -281,3 +281,24 @@ def test_tblock_at_config4_size_matches_the_single_pass_kernel(bp, ctx):
     for depth in (2, 3, 4):
         b = ctx.denoise(noisy, 0.1, _opts(bp, maxiter=25, kernel=bp.KERNEL_TBLOCK, tblock=depth))
         assert np.array_equal(a, b), depth
+
+
+def test_config4_full_size_is_bit_identical_to_the_oracle_pins(bp, ctx, ctx32):
+    """BASELINE config 4 at FULL size (64 × 512×512, 1000 iterations) through the default (AUTO)
+    dispatch: every denoised image hashes to the oracle's (tests/golden/config4_pins.json, written
+    by tools/make_config4_pins.py), in fp64 and in fp32, and so does the loss."""
+    import hashlib
+    import json
+    import os
+    from conftest import ROOT
+    pins = json.load(open(os.path.join(ROOT, "tests", "golden", "config4_pins.json")))
+    truth, noisy = bp.synthetic_dataset(pins["M"], pins["N"], pins["O"], seed=pins["seed"])
+    assert hashlib.sha256(noisy.tobytes(order="F")).hexdigest() == pins["noisy_sha256"]
+    for c, key, dt in ((ctx, "f64", np.float64), (ctx32, "f32", np.float32)):
+        c.set_dataset((truth, noisy))
+        u, cost, _ = c.learn_eval(pins["lambda"], 0.1, bp.eval_opts(bp.pdps_opts(maxiter=pins["iterations"]), force_branch=3))
+        assert c.stats()["pdps_kernel_used"] == bp.KERNEL_TBLOCK and c.stats()["tblock_depth"] == 2
+        got = [hashlib.sha256(np.ascontiguousarray(u[:, :, o].astype(dt).T).tobytes()).hexdigest()
+               for o in range(pins["O"])]
+        assert got == pins[key]["u_sha256"], key
+        assert abs(cost - pins[key]["cost"]) <= 1e-12 * cost, (key, cost)
