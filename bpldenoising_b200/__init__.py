@@ -15,7 +15,7 @@ from .learning import (Context, L2CostFunction, TVDenoise, default_context, deno
                        generate_2d_tv_cost, generate_cost, generate_scalar_tv_cost, gradient, gradient_reg,
                        pdps_opts, tv_op_learning_function, validate_tv_parameter)
 from .datasets import load_dataset, synthetic_dataset, testdataset  # noqa: E402
-from . import quality  # noqa: E402,F401
+from . import quality, results  # noqa: E402,F401
 from .parallel import shard_range  # noqa: E402
 from . import trbox  # noqa: E402,F401
 

@@ -1,0 +1,85 @@
+"""On-disk artefacts of an experiment: `save_results`
+(/root/reference/src/BPLDenoising.jl:185-299) — the optimiser log, the per-image quality table
+(`img_num / orig_ssim / orig_psnr / out_ssim / out_psnr` + means) and the true / data / reco PNGs,
+plus the up-sampled, linearly stretched parameter map for patch parameters (:252-257).
+
+Host-side IO around the hot path; nothing here touches the GPU.  `write_log` belongs to the
+un-vendored AlgTools package: the log is written as a `#` comment line followed by tab-separated
+`iter time function_value gradient_norm radius residual` rows (the fields of `BilevelLogEntry`,
+/root/reference/src/BilevelVisualise.jl:39-46).
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import numpy as np
+
+from . import quality
+
+default_save_prefix = "output"   # BPLDenoising.jl:39
+
+
+def linear_stretch(a: np.ndarray) -> np.ndarray:
+    """adjust_histogram!(img, LinearStretching()) (:337-339): affine map of [min, max] onto [0, 1]."""
+    a = np.asarray(a, dtype=np.float64)
+    lo, hi = float(a.min()), float(a.max())
+    return np.zeros_like(a) if hi == lo else (a - lo) / (hi - lo)
+
+
+def _save_png(path: str, img: np.ndarray) -> None:
+    from PIL import Image
+    Image.fromarray(np.round(np.clip(img, 0.0, 1.0) * 255.0).astype(np.uint8)).save(path)   # grayimg → 8-bit
+
+
+def write_log(path: str, log, comment: str) -> None:
+    with open(path, "w") as io:
+        io.write(comment if comment.endswith("\n") else comment + "\n")
+        io.write("iter\ttime\tfunction_value\tgradient_norm\tradius\tresidual\n")
+        for e in log:
+            io.write(f"{e.iter}\t{e.time}\t{e.function_value}\t{e.gradient_norm}\t{e.radius}\t{e.residual}\n")
+
+
+def quality_table(b, b_data, opt_img):
+    """Rows of the quality file and the means of the output columns (:196-214)."""
+    O = b.shape[2]
+    rows = []
+    for i in range(O):
+        rows.append((i + 1,
+                     quality.assess_ssim(b[:, :, i], b_data[:, :, i]), quality.assess_psnr(b[:, :, i], b_data[:, :, i]),
+                     quality.assess_ssim(b[:, :, i], opt_img[:, :, i]), quality.assess_psnr(b[:, :, i], opt_img[:, :, i])))
+    return rows, float(np.mean([r[3] for r in rows])), float(np.mean([r[4] for r in rows]))
+
+
+def save_results(params: dict, b, b_data, x, opt_img, log, out_root: Optional[str] = None) -> dict:
+    """save_results(params, b, b_data, x, opt_img, st) for scalar (:185-217) and patch (:220-258)
+    parameters.  `params` needs `dataset_name` and `save_prefix`; nothing is written when
+    `params["save_results"]` is false (:186).  Returns the paths it wrote."""
+    if not params.get("save_results", True):
+        return {}
+    b, b_data, opt_img = (np.asarray(a, dtype=np.float64) for a in (b, b_data, opt_img))
+    out_path = os.path.join(out_root or default_save_prefix, params["dataset_name"])
+    os.makedirs(out_path, exist_ok=True)
+    stem = os.path.join(out_path, params["save_prefix"])
+    written = {"log": stem + ".txt", "quality": stem + "_quality.txt", "png": []}
+    write_log(written["log"], log, f"# params = {params}, x = {np.asarray(x).tolist()}")
+    rows, mean_ssim, mean_psnr = quality_table(b, b_data, opt_img)
+    with open(written["quality"], "w") as io:
+        io.write("img_num \t orig_ssim \t orig_psnr \t out_ssim \t out_psnr\n")
+        for i, ns, npn, os_, op in rows:
+            io.write(f"{i}\t {ns} \t {npn} \t {os_} \t {op}\n")
+            for tag, img in (("true", b), ("data", b_data), ("reco", opt_img)):
+                p = f"{stem}_{tag}_{i}.png"
+                _save_png(p, img[:, :, i - 1])
+                written["png"].append(p)
+        io.write(f"\t\t\t\t\t {mean_ssim}\t {mean_psnr}\n")
+    xa = np.asarray(x, dtype=np.float64)
+    if xa.ndim == 2:   # patch parameter: block-constant up-sampling (PatchOp, S7), stretched, as PNG (:252-257)
+        M, N = b.shape[:2]
+        ii = (np.arange(M) * xa.shape[0]) // M
+        jj = (np.arange(N) * xa.shape[1]) // N
+        p = stem + "_par.png"
+        _save_png(p, linear_stretch(xa[np.ix_(ii, jj)]))
+        written["png"].append(p)
+    written["mean_ssim"], written["mean_psnr"] = mean_ssim, mean_psnr
+    return written

@@ -67,3 +67,28 @@ def test_quality_indexes(bp, datasets):
     rng = np.random.default_rng(0)
     c = np.clip(a + 0.2 * rng.standard_normal(a.shape), 0, 1)
     assert q.assess_ssim(a, c) < s and q.assess_psnr(a, c) < q.assess_psnr(a, b)
+
+
+def test_save_results_writes_the_reference_artefacts(bp, datasets, tmp_path):
+    """save_results (/root/reference/src/BPLDenoising.jl:185-258): log, quality table, PNGs, parameter map."""
+    from PIL import Image
+    from bpldenoising_b200 import results, trbox
+    t, d = datasets["faces_val_128_10"]
+    t, d = t[:, :, :2], d[:, :, :2]
+    reco = 0.5 * (t + d)
+    log = [trbox.LogEntry(1, 0.1, 3.0, 2.0, 0.1, 0.0), trbox.LogEntry(2, 0.2, 2.5, 1.0, 0.05, 0.0)]
+    prm = dict(dataset_name="faces_val_128_10", save_prefix="tv_optimal_parameter_scalar_faces_val_128_10", save_results=True)
+    w = results.save_results(prm, t, d, 0.07, reco, log, out_root=str(tmp_path))
+    lines = open(w["quality"]).read().splitlines()
+    assert lines[0].split() == ["img_num", "orig_ssim", "orig_psnr", "out_ssim", "out_psnr"] and len(lines) == 4
+    r1 = [float(v) for v in lines[1].split()]
+    assert r1[0] == 1 and abs(r1[2] - bp.quality.assess_psnr(t[:, :, 0], d[:, :, 0])) < 1e-12 and r1[4] > r1[2]
+    assert abs(float(lines[3].split()[1]) - w["mean_psnr"]) < 1e-12
+    assert len(w["png"]) == 6 and open(w["log"]).read().count("\n") == 4
+    back = np.asarray(Image.open([p for p in w["png"] if p.endswith("_true_2.png")][0]), dtype=np.float64) / 255.0
+    assert np.array_equal(back, t[:, :, 1])                      # 8-bit round trip of k/255 data
+    w2 = results.save_results(dict(prm, save_prefix="patch"), t, d, np.array([[0.1, 0.2], [0.3, 0.5]]), reco, log,
+                              out_root=str(tmp_path))
+    par = np.asarray(Image.open([p for p in w2["png"] if p.endswith("_par.png")][0]))
+    assert par.shape == (128, 128) and par[0, 0] == 0 and par[127, 127] == 255 and par[0, 127] == 64
+    assert results.save_results(dict(prm, save_results=False), t, d, 0.07, reco, log, out_root=str(tmp_path)) == {}
