@@ -390,14 +390,31 @@ def main():
     return 0
 
 
-def learn_eval_extras(bp):
-    """Wall time of one tv_op_learning_function evaluation (5000 PDPS iterations + cost
-    + λ-gradient) on synthetic data shaped like BASELINE configs 1-3 (O×128×128)."""
+def _reference_datasets():
+    """The reference's own datasets (packed from its PNGs into tests/golden/datasets.npz by
+    tools/make_dataset_fixtures.py; /root/reference does not exist on the GPU box)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "datasets.npz"))
     out = {}
-    for name, O, x, Delta in (("config1_like_1x128x128_scalar", 1, 0.1, 0.1),
-                              ("config2_like_10x128x128_scalar", 10, 0.1, 0.1),
-                              ("config3_like_1x128x128_patch2x2", 1, 0.01 * np.ones((2, 2)), 1e-4)):
-        data = bp.synthetic_dataset(128, 128, O, seed=7)
+    for key in z.files:
+        if key.endswith("/true"):
+            name = key[:-5]
+            out[name] = (np.asfortranarray(z[name + "/true"].astype(np.float64) / z[name + "/true_div"]),
+                         np.asfortranarray(z[name + "/data"].astype(np.float64) / z[name + "/data_div"]))
+    return out
+
+
+def learn_eval_extras(bp):
+    """BASELINE configs 1-3 on the reference's own datasets: wall time of one
+    tv_op_learning_function evaluation (5000 PDPS iterations + cost + λ-gradient) and of the full
+    bilevel learn run through the host restatement of the reference's trust-region driver
+    (bpldenoising_b200/trbox.py ← TRBox.jl:192-273); config 2's validation solve."""
+    from bpldenoising_b200 import trbox
+    ds = _reference_datasets()
+    out = {}
+    for name, dsname, x, Delta in (("config1_cameraman_128_5_scalar", "cameraman_128_5", 0.1, 0.1),
+                                   ("config2_faces_train_128_10_scalar", "faces_train_128_10", 0.1, 0.1),
+                                   ("config3_circle_128_10_patch2x2", "circle_128_10", 1e-4 * np.ones((2, 2)), 1e-4)):
+        data = ds[dsname]
         with bp.Context([0], 64) as c:
             c.set_dataset(data)
             c.learn_eval(x, Delta)  # warm-up (allocations)
@@ -407,16 +424,18 @@ def learn_eval_extras(bp):
                 _, cost, g = c.learn_eval(x, Delta)
                 ts.append((time.perf_counter() - t0) * 1e3)
             st = c.stats()
-            out[name] = {"ms": min(ts), "ms_pdps": st["ms_pdps"], "ms_gradient": st["ms_gradient"],
-                         "cost": cost, "grad": np.asarray(g).ravel().tolist()}
-            # full bilevel learn run (1 + ≤20 evaluations) through the host restatement of the
-            # reference's trust-region driver (bpldenoising_b200/trbox.py ← TRBox.jl:192-273)
-            from bpldenoising_b200 import trbox
-            res = trbox.bilevel_learn(data, lambda xx, ds, D: bp.tv_op_learning_function(xx, ds, D, ctx=c), x,
+            out[name] = {"images": int(data[0].shape[2]), "ms": min(ts), "ms_pdps": st["ms_pdps"],
+                         "ms_gradient": st["ms_gradient"], "cost": cost, "grad": np.asarray(g).ravel().tolist()}
+            res = trbox.bilevel_learn(data, lambda xx, d_, D: bp.tv_op_learning_function(xx, d_, D, ctx=c), x,
                                       dict(Delta0=Delta))
             out[name]["learn_run"] = {"seconds": res.seconds, "evaluations": res.evaluations,
                                       "final_cost": res.log[-1].function_value,
                                       "x": np.asarray(res.x).ravel().tolist()}
+            if dsname == "faces_train_128_10":   # "validated on faces_val_128_10": TVDenoise = 10000 iterations
+                t0 = time.perf_counter()
+                val = bp.validate_tv_parameter(float(res.x), ds["faces_val_128_10"], ctx=c)
+                out[name]["validation"] = {"seconds": time.perf_counter() - t0, "cost": val["cost"],
+                                           "mean_psnr": val["mean_psnr"], "mean_ssim": val["mean_ssim"]}
     # λ-sweep (generate_scalar_tv_cost, /root/reference/src/BPLDenoising.jl:92-130): 64 parameters ×
     # 1 image 128×128 × 10000 iterations, batched into one launch vs the reference's loop of solves
     data = bp.synthetic_dataset(128, 128, 1, seed=7)
