@@ -41,7 +41,8 @@ class Stats(C.Structure):
 # every symbol include/bpltv.h declares
 EXPORTS = [
     "bpltv_default_pdps_opts", "bpltv_default_eval_opts", "bpltv_create", "bpltv_destroy",
-    "bpltv_set_dataset", "bpltv_denoise", "bpltv_learn_eval", "bpltv_gradient", "bpltv_sweep",
+    "bpltv_set_dataset", "bpltv_denoise", "bpltv_learn_eval", "bpltv_gradient", "bpltv_sweep", "bpltv_default_sumregs_eval_opts",
+    "bpltv_sumregs_denoise",
     "bpltv_denoise_device", "bpltv_set_dataset_device", "bpltv_learn_eval_device",
     "bpltv_get_stats", "bpltv_last_error", "bpltv_version",
 ]
@@ -78,6 +79,10 @@ def load() -> C.CDLL:
                                    dp, dp, dp]
     L.bpltv_gradient.argtypes = [vp, dp, dp, C.c_int, C.c_int, C.c_int, C.POINTER(EvalOpts), dp]
     L.bpltv_sweep.argtypes = [vp, dp, C.c_int, C.c_int, C.c_int, C.POINTER(PdpsOpts), dp, dp, dp]
+    L.bpltv_default_sumregs_eval_opts.argtypes = [C.POINTER(EvalOpts)]
+    L.bpltv_default_sumregs_eval_opts.restype = None
+    L.bpltv_sumregs_denoise.argtypes = [vp, dp, C.c_int, C.c_int, C.c_int, dp, C.c_int, C.c_int,
+                                        C.POINTER(PdpsOpts), dp]
     L.bpltv_denoise_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, dp, C.c_int, C.c_int,
                                        C.POINTER(PdpsOpts), vp, vp]
     L.bpltv_set_dataset_device.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
@@ -87,7 +92,8 @@ def load() -> C.CDLL:
     L.bpltv_last_error.restype = C.c_char_p
     L.bpltv_version.restype = C.c_int
     for name in EXPORTS:
-        if name not in ("bpltv_default_pdps_opts", "bpltv_default_eval_opts", "bpltv_last_error"):
+        if name not in ("bpltv_default_pdps_opts", "bpltv_default_eval_opts", "bpltv_default_sumregs_eval_opts",
+                        "bpltv_last_error"):
             getattr(L, name).restype = C.c_int
     _lib = L
     return L

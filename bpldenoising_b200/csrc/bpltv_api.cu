@@ -20,6 +20,7 @@
 #include "pdps_march.cuh"
 #include "pdps_tblock.cuh"
 #include "pdps_resident.cuh"
+#include "pdps_sumregs.cuh"
 #include "gradient.cuh"
 
 using namespace bpltv;
@@ -98,7 +99,7 @@ struct Dev {
     int o_begin = 0;          // first global image index of the shard
     DBuf truth, noisy;
     // solve state (ping-pong) and scratch
-    DBuf x[2], y1[2], y2[2], fbuf, amap, steps, partials, scalars, stage, lam_dev, ubuf;
+    DBuf x[2], y1[2], y2[2], fbuf, amap, steps, partials, scalars, stage, lam_dev, ubuf, sry;
     GradWork grad;            // gradient.cuh
     StepKey steps_key;
     std::vector<unsigned char> steps_host;
@@ -606,6 +607,122 @@ static int denoise_impl(bpltv_ctx *ctx, const double *noisy, int M, int N, int O
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// sum-of-regularisers path (SumRegsLearningFunction.jl): lower-level solve
+// ---------------------------------------------------------------------------
+// λ handling: lm = ln = 1 → three scalars; otherwise lm×ln×3 grids up-sampled to three M×N maps
+template <typename Real>
+static int prepare_lambda3(Dev &d, const double *lam, int lm, int ln, int M, int N, cudaStream_t st, Real (&alpha)[3],
+                           const Real **amap)
+{
+    if (lm == 1 && ln == 1) {
+        for (int k = 0; k < 3; ++k) alpha[k] = (Real)lam[k];
+        *amap = nullptr;
+        return 0;
+    }
+    const size_t ng = (size_t)lm * ln;
+    RC_TRY(d.lam_dev.ensure(3 * ng * sizeof(double)));
+    RC_TRY(d.amap.ensure((size_t)3 * M * N * sizeof(Real)));
+    CU_TRY(cudaMemcpyAsync(d.lam_dev.p, lam, 3 * ng * sizeof(double), cudaMemcpyHostToDevice, st));
+    const size_t tot = (size_t)3 * M * N;
+    patch_upsample_sets_kernel<Real><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d.lam_dev.as<double>(), 3, lm, ln,
+                                                                                d.amap.as<Real>(), M, N);
+    d.launches += 1;
+    for (int k = 0; k < 3; ++k) alpha[k] = 0;
+    *amap = d.amap.as<Real>();
+    return 0;
+}
+
+// Runs o.maxiter iterations of the three-operator PDPS on `f`; the result is d.x[0].
+template <typename Real>
+static int run_sumregs_pdps(Dev &d, const Real *f, int M, int N, int O, const Real (&alpha)[3], const Real *amap,
+                            const bpltv_pdps_opts &o, cudaStream_t st, const Real **u_result)
+{
+    if (O == 0) { *u_result = nullptr; return 0; }
+    if (o.rho != 0.0) return fail(BPLTV_ERR_ARG, "the sum-of-regularisers solve has no rho path (the reference fixes rho = 0)");
+    const size_t n = (size_t)M * N * O;
+    RC_TRY(d.x[0].ensure(n * sizeof(Real)));
+    RC_TRY(d.x[1].ensure(n * sizeof(Real)));
+    RC_TRY(d.sry.ensure(6 * n * sizeof(Real)));
+    RC_TRY(upload_steps<Real>(d, o, st));
+    if (o.init_mode) CU_TRY(cudaMemcpyAsync(d.x[0].p, f, n * sizeof(Real), cudaMemcpyDeviceToDevice, st));
+    else CU_TRY(cudaMemsetAsync(d.x[0].p, 0, n * sizeof(Real), st));
+    CU_TRY(cudaMemsetAsync(d.sry.p, 0, 6 * n * sizeof(Real), st));
+    SumRegsArgs<Real> a;
+    a.x = d.x[0].as<Real>(); a.xb = d.x[1].as<Real>(); a.f = f; a.y = d.sry.as<Real>(); a.amap = amap;
+    for (int k = 0; k < 3; ++k) a.alpha[k] = alpha[k];
+    a.M = M; a.N = N; a.O = O;
+    const bool strict = o.arith == BPLTV_ARITH_STRICT;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    const StepConsts<Real> *hsteps = reinterpret_cast<const StepConsts<Real> *>(d.steps_host.data());
+    for (int it = 0; it < o.maxiter; ++it) {
+        a.sc = hsteps[it];
+        if (strict) sumregs_primal_kernel<Real, true><<<grid, 256, 0, st>>>(a);
+        else sumregs_primal_kernel<Real, false><<<grid, 256, 0, st>>>(a);
+        if (amap) {
+            if (strict) sumregs_dual_kernel<Real, true, true><<<grid, 256, 0, st>>>(a);
+            else sumregs_dual_kernel<Real, true, false><<<grid, 256, 0, st>>>(a);
+        } else {
+            if (strict) sumregs_dual_kernel<Real, false, true><<<grid, 256, 0, st>>>(a);
+            else sumregs_dual_kernel<Real, false, false><<<grid, 256, 0, st>>>(a);
+        }
+    }
+    d.launches += 2LL * o.maxiter;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(BPLTV_ERR_CUDA, "sumregs PDPS kernel launch failed: %s", cudaGetErrorString(e));
+    *u_result = d.x[0].as<Real>();
+    return 0;
+}
+
+template <typename Real>
+static int sumregs_denoise_impl(bpltv_ctx *ctx, const double *noisy, int M, int N, int O, const double *lam, int lm,
+                                int ln, const bpltv_pdps_opts &o, double *u_out)
+{
+    const int ndev = (int)ctx->devs.size();
+    const size_t plane = (size_t)M * N;
+    std::memset(&ctx->stats, 0, sizeof ctx->stats);
+    for (int di = 0; di < ndev; ++di) {
+        Dev &d = ctx->devs[di];
+        CU_TRY(cudaSetDevice(d.id));
+        d.launches = 0;
+        int ob, oc;
+        if (noisy) shard_range(O, ndev, di, ob, oc);
+        else { ob = d.o_begin; oc = d.O; }
+        cudaStream_t st = d.stream;
+        CU_TRY(cudaEventRecord(d.ev[0], st));
+        const Real *f;
+        if (noisy) {
+            RC_TRY(upload_stack<Real>(d, noisy + plane * ob, plane * oc, d.fbuf, st));
+            f = d.fbuf.as<Real>();
+        } else {
+            f = d.noisy.as<Real>();
+        }
+        CU_TRY(cudaEventRecord(d.ev[1], st));
+        Real alpha[3]; const Real *amap;
+        RC_TRY(prepare_lambda3<Real>(d, lam, lm, ln, M, N, st, alpha, &amap));
+        const Real *u = nullptr;
+        RC_TRY(run_sumregs_pdps<Real>(d, f, M, N, oc, alpha, amap, o, st, &u));
+        CU_TRY(cudaEventRecord(d.ev[2], st));
+        if (oc > 0) RC_TRY(download_stack<Real>(d, u, plane * oc, u_out + plane * ob, st));
+        CU_TRY(cudaEventRecord(d.ev[3], st));
+    }
+    for (int di = 0; di < ndev; ++di) {
+        Dev &d = ctx->devs[di];
+        CU_TRY(cudaSetDevice(d.id));
+        CU_TRY(cudaStreamSynchronize(d.stream));
+        ctx->stats.ms_upload = std::max<double>(ctx->stats.ms_upload, ev_ms(d.ev[0], d.ev[1]));
+        ctx->stats.ms_pdps = std::max<double>(ctx->stats.ms_pdps, ev_ms(d.ev[1], d.ev[2]));
+        ctx->stats.ms_download = std::max<double>(ctx->stats.ms_download, ev_ms(d.ev[2], d.ev[3]));
+        ctx->stats.ms_total = std::max<double>(ctx->stats.ms_total, ev_ms(d.ev[0], d.ev[3]));
+        ctx->stats.kernel_launches += d.launches;
+    }
+    ctx->stats.pdps_iterations = o.maxiter;
+    ctx->stats.pixel_iterations = (long long)plane * O * o.maxiter;
+    ctx->stats.n_devices = ndev;
+    ctx->stats.tblock_depth = 1;
+    return 0;
+}
+
 template <typename Real>
 static int set_dataset_impl(bpltv_ctx *ctx, const double *truth, const double *noisy, int M, int N, int O)
 {
@@ -983,7 +1100,7 @@ int bpltv_destroy(bpltv_ctx *ctx)
         cudaSetDevice(d.id);
         if (d.stream) cudaStreamSynchronize(d.stream);
         DBuf *bufs[] = {&d.truth, &d.noisy, &d.x[0], &d.x[1], &d.y1[0], &d.y1[1], &d.y2[0], &d.y2[1], &d.fbuf,
-                        &d.amap, &d.steps, &d.partials, &d.scalars, &d.stage, &d.lam_dev, &d.ubuf};
+                        &d.amap, &d.steps, &d.partials, &d.scalars, &d.stage, &d.lam_dev, &d.ubuf, &d.sry};
         for (DBuf *b : bufs) b->release();
         d.grad.release();
         for (auto &ev : d.ev) if (ev) cudaEventDestroy(ev);
@@ -1079,6 +1196,36 @@ int bpltv_sweep(bpltv_ctx *ctx, const double *lams, int L, int lm, int ln, const
     if ((double)ctx->M * ctx->N * std::max(ctx->O, 1) * L > 4.0e9) return fail(BPLTV_ERR_ARG, "sweep too large: split the parameter range");
     return ctx->prec == 64 ? sweep_impl<double>(ctx, lams, L, lm, ln, o, cost_out, sqerr_out, u_out)
                            : sweep_impl<float>(ctx, lams, L, lm, ln, o, cost_out, sqerr_out, u_out);
+}
+
+void bpltv_default_sumregs_eval_opts(bpltv_eval_opts *o)
+{
+    if (!o) return;
+    bpltv_default_eval_opts(o);
+    o->pdps.opnorm = std::sqrt(18.0);   // S12: R_K of (∇ᶠ; ∇ᵇ; ∇ᶜ)
+    o->delta_t = 1e-3;                  // /root/reference/src/SumRegsLearningFunction.jl:8
+    o->gamma = 1e3;                     // :117 (scalar sumregs_gradient_reg)
+}
+
+int bpltv_sumregs_denoise(bpltv_ctx *ctx, const double *noisy, int M, int N, int O, const double *lam, int lm, int ln,
+                          const bpltv_pdps_opts *opts, double *u_out)
+{
+    if (!ctx || !u_out) return fail(BPLTV_ERR_ARG, "NULL argument");
+    RC_TRY(check_shape(M, N, O));
+    if (!lam || lm < 1 || ln < 1) return fail(BPLTV_ERR_ARG, "lambda grid must be at least 1x1(x3)");
+    for (int k = 0; k < 3; ++k) RC_TRY(check_lambda(lam + (size_t)k * lm * ln, lm, ln));
+    bpltv_pdps_opts o;
+    if (opts) o = *opts;
+    else { bpltv_eval_opts e; bpltv_default_sumregs_eval_opts(&e); o = e.pdps; }
+    RC_TRY(check_pdps_opts(o));
+    if (!noisy) {
+        if (!ctx->have_dataset) return fail(BPLTV_ERR_STATE, "denoise(noisy=NULL) needs bpltv_set_dataset first");
+        if (M != ctx->M || N != ctx->N || O != ctx->O)
+            return fail(BPLTV_ERR_ARG, "shape %dx%dx%d does not match the resident dataset %dx%dx%d", M, N, O, ctx->M,
+                        ctx->N, ctx->O);
+    }
+    return ctx->prec == 64 ? sumregs_denoise_impl<double>(ctx, noisy, M, N, O, lam, lm, ln, o, u_out)
+                           : sumregs_denoise_impl<float>(ctx, noisy, M, N, O, lam, lm, ln, o, u_out);
 }
 
 // ---- device-resident variants (single device) --------------------------------

@@ -40,6 +40,16 @@ def _lam(x):
     return np.asfortranarray(xa), False
 
 
+def _lam3(x):
+    """Sum-of-regularisers parameter: a 3-vector (`x::AbstractVector{Float64}`) or an m×n×3 array."""
+    xa = np.asarray(x, dtype=np.float64)
+    if xa.shape == (3,):
+        return np.ascontiguousarray(xa), 1, 1
+    if xa.ndim == 3 and xa.shape[2] == 3:
+        return np.asfortranarray(xa), xa.shape[0], xa.shape[1]
+    raise ValueError("the sum-of-regularisers parameter is a 3-vector or an m×n×3 array")
+
+
 def _ptr(a: np.ndarray):
     return a.ctypes.data_as(_DP)
 
@@ -70,6 +80,31 @@ def eval_opts(pdps: Optional[PdpsOpts] = None, **kw) -> EvalOpts:
         k = alias.get(k, k)
         if not hasattr(o, k) or k in ("reserved", "pdps"):
             raise TypeError(f"unknown evaluation option {k!r}")
+        setattr(o, k, type(getattr(o, k))(v))
+    return o
+
+
+def sumregs_eval_opts(pdps: Optional[PdpsOpts] = None, **kw) -> EvalOpts:
+    """Defaults of the sum-of-regularisers path: opnorm √18 (S12), Δt = 1e-3, γ = 1e3
+    (/root/reference/src/SumRegsLearningFunction.jl:8, :117)."""
+    o = EvalOpts()
+    _lib.load().bpltv_default_sumregs_eval_opts(C.byref(o))
+    if pdps is not None:
+        o.pdps = pdps
+    alias = {"Δt": "delta_t", "γ": "gamma"}
+    for k, v in kw.items():
+        k = alias.get(k, k)
+        if not hasattr(o, k) or k in ("reserved", "pdps"):
+            raise TypeError(f"unknown evaluation option {k!r}")
+        setattr(o, k, type(getattr(o, k))(v))
+    return o
+
+
+def sumregs_pdps_opts(**kw) -> PdpsOpts:
+    o = sumregs_eval_opts().pdps
+    for k, v in kw.items():
+        if not hasattr(o, k) or k == "reserved":
+            raise TypeError(f"unknown PDPS option {k!r}")
         setattr(o, k, type(getattr(o, k))(v))
     return o
 
@@ -159,6 +194,23 @@ class Context:
         check(self._L.bpltv_gradient(self._h, _ptr(us), _ptr(lam), lam.shape[0], lam.shape[1],
                                      int(bool(regularised)), C.byref(o), _ptr(grad)))
         return float(grad[0, 0]) if scalar else grad
+
+    # ---- sum-of-regularisers interface (SumRegsLearningFunction.jl) ---------------------
+    def sumregs_denoise(self, data, x, opts: Optional[PdpsOpts] = None) -> np.ndarray:
+        lam, lm, ln = _lam3(x)
+        o = opts if opts is not None else sumregs_eval_opts().pdps
+        if data is None:
+            if self.shape is None:
+                raise _lib.BpltvError(-4, "no resident dataset")
+            M, N, O = self.shape
+            fptr = None
+        else:
+            f = _stack(data)
+            M, N, O = f.shape
+            fptr = _ptr(f)
+        u = np.zeros((M, N, O), order="F")
+        check(self._L.bpltv_sumregs_denoise(self._h, fptr, M, N, O, _ptr(lam), lm, ln, C.byref(o), _ptr(u)))
+        return u
 
     # ---- λ-sweeps (cost curves, validation) ------------------------------------------
     def sweep(self, parameters, opts: Optional[PdpsOpts] = None, return_u: bool = False,
@@ -352,3 +404,13 @@ def validate_tv_parameter(parameter, data, ctx: Optional[Context] = None, **kwar
     return {"u": u, "cost": float(costs[0]), "table": rows,
             "mean_ssim": float(np.mean([r["out_ssim"] for r in rows])),
             "mean_psnr": float(np.mean([r["out_psnr"] for r in rows]))}
+
+
+# ------------------------------------------------------------------------------
+# sum-of-regularisers interface (/root/reference/src/SumRegsLearningFunction.jl)
+# ------------------------------------------------------------------------------
+def sumregs_denoise(data, x, op1=None, op2=None, op3=None, pOp=None, ctx: Optional[Context] = None, **kwargs):
+    """sumregs_denoise(data, x, op₁, op₂, op₃[, pOp]) (:38-85); the operator arguments are accepted
+    for signature parity (the reference always passes Fwd/Bwd/CenteredGradientOp, :9-11)."""
+    ctx = ctx or default_context()
+    return ctx.sumregs_denoise(data, x, sumregs_pdps_opts(**kwargs))

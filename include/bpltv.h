@@ -152,6 +152,22 @@ int bpltv_gradient(bpltv_ctx *ctx, const double *u, const double *lam, int lm, i
 int bpltv_sweep(bpltv_ctx *ctx, const double *lams, int L, int lm, int ln,
                 const bpltv_pdps_opts *opts, double *cost_out, double *sqerr_out, double *u_out);
 
+/* ---- sum-of-regularisers interface (/root/reference/src/SumRegsLearningFunction.jl) ----------
+ * Three TV-type regularisers: forward, backward and centred differences (op₁, op₂, op₃, :9-11).
+ * λ is a 3-vector (lm = ln = 1; `x::AbstractVector{Float64}`, :8) or an lm×ln×3 column-major array
+ * (`x::AbstractArray{T,3}`, :22), each layer up-sampled like PatchOp.  Semantics of the un-vendored
+ * operators and solver: docs/SEMANTICS.md S10-S13.                                             */
+
+/* bpltv_default_eval_opts with the sum-of-regularisers constants: pdps.opnorm = √18 (S12),
+ * Δt = 1e-3 (:8), γ = 1e3 (:117).                                                             */
+void bpltv_default_sumregs_eval_opts(bpltv_eval_opts *o);
+
+/* Replaces sumregs_denoise(data, x, op₁, op₂, op₃[, pOp]) (:38-85).  opts == NULL → the defaults
+ * above.  noisy == NULL → the resident dataset's noisy stack.                                  */
+int bpltv_sumregs_denoise(bpltv_ctx *ctx, const double *noisy, int M, int N, int O,
+                          const double *lam, int lm, int ln, const bpltv_pdps_opts *opts,
+                          double *u_out);
+
 /* Device-resident variants (single-device contexts only): pointers are device
  * memory of the context's precision (double or float), `stream` a cudaStream_t
  * (NULL → the context's stream).  Asynchronous: nothing is synchronised.
