@@ -42,7 +42,7 @@ class Stats(C.Structure):
 EXPORTS = [
     "bpltv_default_pdps_opts", "bpltv_default_eval_opts", "bpltv_create", "bpltv_destroy",
     "bpltv_set_dataset", "bpltv_denoise", "bpltv_learn_eval", "bpltv_gradient", "bpltv_sweep", "bpltv_default_sumregs_eval_opts",
-    "bpltv_sumregs_denoise",
+    "bpltv_sumregs_denoise", "bpltv_sumregs_learn_eval", "bpltv_sumregs_gradient",
     "bpltv_denoise_device", "bpltv_set_dataset_device", "bpltv_learn_eval_device",
     "bpltv_get_stats", "bpltv_last_error", "bpltv_version",
 ]
@@ -83,6 +83,8 @@ def load() -> C.CDLL:
     L.bpltv_default_sumregs_eval_opts.restype = None
     L.bpltv_sumregs_denoise.argtypes = [vp, dp, C.c_int, C.c_int, C.c_int, dp, C.c_int, C.c_int,
                                         C.POINTER(PdpsOpts), dp]
+    L.bpltv_sumregs_learn_eval.argtypes = [vp, dp, C.c_int, C.c_int, C.c_double, C.POINTER(EvalOpts), dp, dp, dp]
+    L.bpltv_sumregs_gradient.argtypes = [vp, dp, dp, C.c_int, C.c_int, C.c_int, C.POINTER(EvalOpts), dp]
     L.bpltv_denoise_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, dp, C.c_int, C.c_int,
                                        C.POINTER(PdpsOpts), vp, vp]
     L.bpltv_set_dataset_device.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]

@@ -22,6 +22,7 @@
 #include "pdps_resident.cuh"
 #include "pdps_sumregs.cuh"
 #include "gradient.cuh"
+#include "gradient_sumregs.cuh"
 
 using namespace bpltv;
 
@@ -101,6 +102,7 @@ struct Dev {
     // solve state (ping-pong) and scratch
     DBuf x[2], y1[2], y2[2], fbuf, amap, steps, partials, scalars, stage, lam_dev, ubuf, sry;
     GradWork grad;            // gradient.cuh
+    GradWork grad3;           // gradient_sumregs.cuh
     StepKey steps_key;
     std::vector<unsigned char> steps_host;
     long long launches = 0;
@@ -723,6 +725,94 @@ static int sumregs_denoise_impl(bpltv_ctx *ctx, const double *noisy, int M, int 
     return 0;
 }
 
+// one sum-of-regularisers evaluation on one device: u, scalars[0] = cost, scalars[1..3·ng] = gradient
+template <typename Real>
+static int sumregs_eval_on_device(bpltv_ctx *ctx, Dev &d, const double *lam, int lm, int ln, double Delta,
+                                  const bpltv_eval_opts &eo, const Real *u_given, cudaStream_t st, const Real **u_res,
+                                  double *d_costgrad)
+{
+    const int M = d.M, N = d.N, O = d.O;
+    const size_t n = (size_t)M * N * O;
+    const int ng = lm * ln;
+    CU_TRY(cudaEventRecord(d.ev[0], st));
+    Real alpha[3]; const Real *amap;
+    RC_TRY(prepare_lambda3<Real>(d, lam, lm, ln, M, N, st, alpha, &amap));
+    const Real *u = u_given;
+    if (!u) RC_TRY(run_sumregs_pdps<Real>(d, d.noisy.as<Real>(), M, N, O, alpha, amap, eo.pdps, st, &u));
+    CU_TRY(cudaEventRecord(d.ev[1], st));
+    CU_TRY(cudaMemsetAsync(d_costgrad, 0, (1 + 3 * ng) * sizeof(double), st));
+    if (O > 0) RC_TRY(run_cost<Real>(d, u, d.truth.as<Real>(), n, d_costgrad, st));
+    CU_TRY(cudaEventRecord(d.ev[2], st));
+    if (O > 0 && eo.force_branch != 3) {
+        Grad3Problem<Real> gp;
+        gp.u = u; gp.ubar = d.truth.as<Real>(); gp.M = M; gp.N = N; gp.O = O;
+        for (int k = 0; k < 3; ++k) gp.alpha[k] = ng == 1 ? lam[k] : 0.0;
+        gp.alpha_maps = amap; gp.lm = lm; gp.ln = ln;
+        gp.regularised = eo.force_branch == 2 || (eo.force_branch == 0 && !(Delta > eo.delta_t));
+        gp.gamma = eo.gamma; gp.act_tol = eo.act_tol;
+        gp.eps_act = eo.eps_act > 0 ? eo.eps_act : 2.220446049250313e-16;   // eps() in both variants (:318-320, :387-389)
+        int rc = run_gradient3<Real>(d.grad3, gp, d.sm_count, d.smem_optin, st, d_costgrad + 1, &d.launches);
+        if (rc != 0) return fail(rc == -1 ? BPLTV_ERR_ARG : rc, "sumregs gradient: %s", d.grad3.err.c_str());
+    }
+    CU_TRY(cudaEventRecord(d.ev[3], st));
+    *u_res = u;
+    return 0;
+}
+
+// u_host != NULL: gradient of the caller's u (no solve); else the full learning function
+template <typename Real>
+static int sumregs_learn_eval_impl(bpltv_ctx *ctx, const double *lam, int lm, int ln, double Delta,
+                                   const bpltv_eval_opts &eo, const double *u_host, double *u_out, double *cost_out,
+                                   double *grad_out)
+{
+    const int ndev = (int)ctx->devs.size();
+    const int ng = 3 * lm * ln;
+    const size_t plane = (size_t)ctx->M * ctx->N;
+    std::memset(&ctx->stats, 0, sizeof ctx->stats);
+    std::vector<std::vector<double>> host(ndev, std::vector<double>(1 + ng, 0.0));
+    for (int di = 0; di < ndev; ++di) {
+        Dev &d = ctx->devs[di];
+        CU_TRY(cudaSetDevice(d.id));
+        d.launches = 0;
+        RC_TRY(d.scalars.ensure((1 + ng) * sizeof(double)));
+        const Real *ug = nullptr;
+        if (u_host) {
+            RC_TRY(upload_stack<Real>(d, u_host + plane * d.o_begin, plane * d.O, d.ubuf, d.stream));
+            ug = d.ubuf.as<Real>();
+        }
+        const Real *u = nullptr;
+        RC_TRY(sumregs_eval_on_device<Real>(ctx, d, lam, lm, ln, Delta, eo, ug, d.stream, &u, d.scalars.as<double>()));
+        CU_TRY(cudaMemcpyAsync(host[di].data(), d.scalars.p, (1 + ng) * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
+        if (u_out && d.O > 0) RC_TRY(download_stack<Real>(d, u, plane * d.O, u_out + plane * d.o_begin, d.stream));
+        CU_TRY(cudaEventRecord(d.ev[4], d.stream));
+    }
+    double cost = 0.0;
+    std::vector<double> grad(ng, 0.0);
+    for (int di = 0; di < ndev; ++di) {
+        Dev &d = ctx->devs[di];
+        CU_TRY(cudaSetDevice(d.id));
+        CU_TRY(cudaStreamSynchronize(d.stream));
+        cost += host[di][0];
+        for (int k = 0; k < ng; ++k) grad[k] += host[di][1 + k];
+        ctx->stats.ms_pdps = std::max<double>(ctx->stats.ms_pdps, ev_ms(d.ev[0], d.ev[1]));
+        ctx->stats.ms_cost = std::max<double>(ctx->stats.ms_cost, ev_ms(d.ev[1], d.ev[2]));
+        ctx->stats.ms_gradient = std::max<double>(ctx->stats.ms_gradient, ev_ms(d.ev[2], d.ev[3]));
+        ctx->stats.ms_download = std::max<double>(ctx->stats.ms_download, ev_ms(d.ev[3], d.ev[4]));
+        ctx->stats.ms_total = std::max<double>(ctx->stats.ms_total, ev_ms(d.ev[0], d.ev[4]));
+        ctx->stats.kernel_launches += d.launches;
+    }
+    ctx->stats.pdps_iterations = u_host ? 0 : eo.pdps.maxiter;
+    ctx->stats.pixel_iterations = u_host ? 0 : (long long)plane * ctx->O * eo.pdps.maxiter;
+    ctx->stats.n_devices = ndev;
+    ctx->stats.tblock_depth = 1;
+    if (!std::isfinite(cost)) return fail(BPLTV_ERR_NUMERIC, "non-finite cost");
+    for (int k = 0; k < ng; ++k)
+        if (!std::isfinite(grad[k])) return fail(BPLTV_ERR_NUMERIC, "non-finite gradient entry %d", k);
+    if (cost_out) *cost_out = cost;
+    for (int k = 0; k < ng; ++k) grad_out[k] = grad[k];
+    return 0;
+}
+
 template <typename Real>
 static int set_dataset_impl(bpltv_ctx *ctx, const double *truth, const double *noisy, int M, int N, int O)
 {
@@ -1103,6 +1193,7 @@ int bpltv_destroy(bpltv_ctx *ctx)
                         &d.amap, &d.steps, &d.partials, &d.scalars, &d.stage, &d.lam_dev, &d.ubuf, &d.sry};
         for (DBuf *b : bufs) b->release();
         d.grad.release();
+        d.grad3.release();
         for (auto &ev : d.ev) if (ev) cudaEventDestroy(ev);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
@@ -1226,6 +1317,49 @@ int bpltv_sumregs_denoise(bpltv_ctx *ctx, const double *noisy, int M, int N, int
     }
     return ctx->prec == 64 ? sumregs_denoise_impl<double>(ctx, noisy, M, N, O, lam, lm, ln, o, u_out)
                            : sumregs_denoise_impl<float>(ctx, noisy, M, N, O, lam, lm, ln, o, u_out);
+}
+
+static int check_sumregs_eval(bpltv_ctx *ctx, const double *lam, int lm, int ln, const bpltv_eval_opts *opts,
+                              bpltv_eval_opts &eo)
+{
+    if (!ctx) return fail(BPLTV_ERR_ARG, "NULL context");
+    if (!ctx->have_dataset) return fail(BPLTV_ERR_STATE, "no resident dataset: call bpltv_set_dataset first");
+    if (!lam || lm < 1 || ln < 1) return fail(BPLTV_ERR_ARG, "lambda grid must be at least 1x1(x3)");
+    for (int k = 0; k < 3; ++k) RC_TRY(check_lambda(lam + (size_t)k * lm * ln, lm, ln));
+    if (opts) eo = *opts; else bpltv_default_sumregs_eval_opts(&eo);
+    RC_TRY(check_pdps_opts(eo.pdps));
+    if (ctx->M != ctx->N)
+        return fail(BPLTV_ERR_ARG, "the gradient assumes square images like the reference "
+                                   "(SumRegsLearningFunction.jl:116); got %dx%d", ctx->M, ctx->N);
+    if (lm > ctx->M || ln > ctx->N) return fail(BPLTV_ERR_ARG, "lambda grid larger than the image");
+    if (eo.force_branch != 3)
+        for (int k = 0; k < 3 * lm * ln; ++k)
+            if (!(lam[k] > 0.0)) return fail(BPLTV_ERR_ARG, "lambda[%d] must be > 0 for the gradient", k);
+    if (!(eo.gamma > 0) || !(eo.act_tol >= 0)) return fail(BPLTV_ERR_ARG, "bad gamma / act_tol");
+    return 0;
+}
+
+int bpltv_sumregs_learn_eval(bpltv_ctx *ctx, const double *lam, int lm, int ln, double Delta,
+                             const bpltv_eval_opts *opts, double *u_out, double *cost_out, double *grad_out)
+{
+    bpltv_eval_opts eo;
+    RC_TRY(check_sumregs_eval(ctx, lam, lm, ln, opts, eo));
+    if (!cost_out || !grad_out) return fail(BPLTV_ERR_ARG, "NULL output");
+    return ctx->prec == 64
+               ? sumregs_learn_eval_impl<double>(ctx, lam, lm, ln, Delta, eo, nullptr, u_out, cost_out, grad_out)
+               : sumregs_learn_eval_impl<float>(ctx, lam, lm, ln, Delta, eo, nullptr, u_out, cost_out, grad_out);
+}
+
+int bpltv_sumregs_gradient(bpltv_ctx *ctx, const double *u, const double *lam, int lm, int ln, int regularised,
+                           const bpltv_eval_opts *opts, double *grad_out)
+{
+    bpltv_eval_opts eo;
+    RC_TRY(check_sumregs_eval(ctx, lam, lm, ln, opts, eo));
+    if (!u || !grad_out) return fail(BPLTV_ERR_ARG, "NULL argument");
+    eo.force_branch = regularised ? 2 : 1;
+    return ctx->prec == 64
+               ? sumregs_learn_eval_impl<double>(ctx, lam, lm, ln, 0.0, eo, u, nullptr, nullptr, grad_out)
+               : sumregs_learn_eval_impl<float>(ctx, lam, lm, ln, 0.0, eo, u, nullptr, nullptr, grad_out);
 }
 
 // ---- device-resident variants (single device) --------------------------------

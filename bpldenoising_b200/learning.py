@@ -212,6 +212,30 @@ class Context:
         check(self._L.bpltv_sumregs_denoise(self._h, fptr, M, N, O, _ptr(lam), lm, ln, C.byref(o), _ptr(u)))
         return u
 
+    def sumregs_learn_eval(self, x, Delta, opts: Optional[EvalOpts] = None, return_u: bool = True):
+        if self.shape is None:
+            raise _lib.BpltvError(-4, "no resident dataset: call set_dataset first")
+        lam, lm, ln = _lam3(x)
+        o = opts if opts is not None else sumregs_eval_opts()
+        M, N, O = self.shape
+        u = np.zeros((M, N, O), order="F") if return_u else None
+        cost = C.c_double()
+        grad = np.zeros(np.asarray(x).shape, order="F")
+        check(self._L.bpltv_sumregs_learn_eval(self._h, _ptr(lam), lm, ln, float(Delta), C.byref(o),
+                                               _ptr(u) if return_u else None, C.byref(cost), _ptr(grad)))
+        return u, cost.value, grad
+
+    def sumregs_gradient(self, x, u, regularised: bool, opts: Optional[EvalOpts] = None):
+        lam, lm, ln = _lam3(x)
+        o = opts if opts is not None else sumregs_eval_opts()
+        us = _stack(u)
+        if self.shape is None or us.shape != self.shape:
+            raise ValueError("u must have the shape of the resident dataset")
+        grad = np.zeros(np.asarray(x).shape, order="F")
+        check(self._L.bpltv_sumregs_gradient(self._h, _ptr(us), _ptr(lam), lm, ln, int(bool(regularised)),
+                                             C.byref(o), _ptr(grad)))
+        return grad
+
     # ---- λ-sweeps (cost curves, validation) ------------------------------------------
     def sweep(self, parameters, opts: Optional[PdpsOpts] = None, return_u: bool = False,
               return_sqerr: bool = False):
@@ -414,3 +438,11 @@ def sumregs_denoise(data, x, op1=None, op2=None, op3=None, pOp=None, ctx: Option
     for signature parity (the reference always passes Fwd/Bwd/CenteredGradientOp, :9-11)."""
     ctx = ctx or default_context()
     return ctx.sumregs_denoise(data, x, sumregs_pdps_opts(**kwargs))
+
+
+def sumregs_learning_function(x, data, Δ, Δt: float = 1e-3, ctx: Optional[Context] = None, **kwargs):
+    """sumregs_learning_function(x, data, Δ; Δt=1e-3) → (u, cost, grad) (:8-36); x a 3-vector or m×n×3."""
+    ctx = ctx or default_context()
+    _ensure_resident(ctx, data)
+    eo = sumregs_eval_opts(sumregs_pdps_opts(**kwargs), delta_t=Δt)
+    return ctx.sumregs_learn_eval(x, Δ, eo)

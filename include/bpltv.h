@@ -168,6 +168,20 @@ int bpltv_sumregs_denoise(bpltv_ctx *ctx, const double *noisy, int M, int N, int
                           const double *lam, int lm, int ln, const bpltv_pdps_opts *opts,
                           double *u_out);
 
+/* Replaces sumregs_learning_function(x, data, Δ; Δt=1e-3) (:8-36) on the resident dataset:
+ * u = sumregs_denoise(f, x); cost = 0.5‖u-ū‖²; grad = Δ > Δt ? sumregs_gradient (:264-327, :330-407)
+ * : sumregs_gradient_reg (:112-167), summed over images (:87-110, :169-193).  grad_out has the shape
+ * of x: 3 (lm = ln = 1) or lm×ln×3 entries.  The patch variant of sumregs_gradient_reg (:195-262) is
+ * not built (its row-scaled system has no symmetric form): BPLTV_ERR_ARG.  opts == NULL → the
+ * sum-of-regularisers defaults.                                                              */
+int bpltv_sumregs_learn_eval(bpltv_ctx *ctx, const double *lam, int lm, int ln, double Delta,
+                             const bpltv_eval_opts *opts, double *u_out, double *cost_out,
+                             double *grad_out);
+
+/* Gradient of a caller-supplied u (the tests grade the adjoint solve on the oracle's u).     */
+int bpltv_sumregs_gradient(bpltv_ctx *ctx, const double *u, const double *lam, int lm, int ln,
+                           int regularised, const bpltv_eval_opts *opts, double *grad_out);
+
 /* Device-resident variants (single-device contexts only): pointers are device
  * memory of the context's precision (double or float), `stream` a cudaStream_t
  * (NULL → the context's stream).  Asynchronous: nothing is synchronised.

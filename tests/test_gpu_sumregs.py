@@ -59,3 +59,74 @@ def test_sumregs_denoise_on_the_reference_dataset(bp, ctx, sr, datasets):
         ctx.sumregs_denoise(f, np.array([0.1, -0.1, 0.1]))
     with pytest.raises(bp.BpltvError):
         ctx.sumregs_denoise(f, x0, bp.sumregs_pdps_opts(rho=0.5, maxiter=2))
+
+
+# ---- adjoint solve / λ-gradient -------------------------------------------------------------
+def _crop(datasets, name, n, k=1, off=40):
+    t, f = datasets[name]
+    return (np.asfortranarray(t[off:off + n, off:off + n, :k]), np.asfortranarray(f[off:off + n, off:off + n, :k]))
+
+
+@pytest.mark.parametrize("variant", ["reg", "nonreg"])
+@pytest.mark.parametrize("n", [16, 33, 48])
+def test_sumregs_gradient_on_the_oracles_u(bp, ctx, sr, datasets, variant, n):
+    """Scalar sumregs_gradient (:264-327) / sumregs_gradient_reg (:112-167) on the ORACLE's u: ≤ 1e-10 against
+    the compliance-form CPU checker (same algorithm), ≤ 1e-9 (reg) / 1e-6 (non-reg) against the refined literal
+    sparse solve — the bars of the TV path."""
+    t, f = _crop(datasets, "faces_train_128_10", n, k=2, off=30)
+    x = np.array([0.03, 0.02, 0.04])
+    u = sr.sumregs_pdps(f, list(x), maxiter=400)
+    ctx.set_dataset((t, f))
+    g = ctx.sumregs_gradient(x, u, regularised=(variant == "reg"))
+    assert g.shape == (3,)
+    du = sum(sr.sumregs_gradient_dual(variant, x, u[:, :, i], t[:, :, i]) for i in range(2))
+    assert np.all(np.abs(g - du) <= 1e-10 * np.abs(du)), (g, du)
+    if variant == "reg":
+        lit = sum(sr.sumregs_gradient_reg(x, u[:, :, i], t[:, :, i], refine=3) for i in range(2))
+        assert np.all(np.abs(g - lit) <= 1e-9 * np.abs(lit)), (g, lit)
+    else:
+        lit = sum(sr.sumregs_gradient(x, u[:, :, i], t[:, :, i], refine=3) for i in range(2))
+        assert np.all(np.abs(g - lit) <= 1e-6 * np.abs(lit)), (g, lit)
+
+
+def test_sumregs_gradient_with_flat_regions_and_patch_parameters(bp, ctx, sr, datasets):
+    from oracle import oracle as orc
+    # the circle truth is piecewise constant: its denoised image has exactly flat pixels (active sets)
+    t, f = _crop(datasets, "circle_128_10", 32, off=48)
+    x = np.array([0.05, 0.04, 0.06])
+    u = sr.sumregs_pdps(f, list(x), maxiter=600)
+    u[:8, :8, 0] = u[0, 0, 0]                         # force an exactly flat block (|∇_k u| = 0 for all k)
+    ctx.set_dataset((t, f))
+    for variant in ("reg", "nonreg"):
+        g = ctx.sumregs_gradient(x, u, regularised=(variant == "reg"))
+        du = sr.sumregs_gradient_dual(variant, x, u[:, :, 0], t[:, :, 0])
+        assert np.all(np.abs(g - du) <= 1e-9 * np.abs(du).max()), (variant, g, du)
+    # patch parameter, non-regularised branch (:330-407)
+    xp = np.stack([np.array([[0.03, 0.05], [0.02, 0.04]]) * s for s in (1.0, 0.7, 1.3)], axis=2)
+    maps = [orc.patch_upsample(xp[:, :, k], 32, 32) for k in range(3)]
+    gp = ctx.sumregs_gradient(xp, u, regularised=False)
+    dp = sr.sumregs_gradient_dual("nonreg", maps, u[:, :, 0], t[:, :, 0], grid_shape=(2, 2))
+    assert gp.shape == (2, 2, 3) and np.all(np.abs(gp - dp) <= 1e-9 * np.abs(dp).max()), (gp, dp)
+    # patch regularised branch (:195-262): refused, with the reason
+    with pytest.raises(bp.BpltvError) as ei:
+        ctx.sumregs_gradient(xp, u, regularised=True)
+    assert "row-scaled" in str(ei.value)
+
+
+def test_sumregs_learning_function_end_to_end(bp, ctx, sr, datasets):
+    """sumregs_learning_function(x, data, Δ) (:8-20) on the reference's cameraman dataset at α₀ (BPLDenoising.jl:429)."""
+    from oracle import oracle as orc
+    t, f = datasets["cameraman_128_5"]
+    x0 = np.array([0.001, 0.001, 0.001])
+    u, cost, g = bp.sumregs_learning_function(x0, (t, f), 0.01, ctx=ctx, maxiter=300)     # Δ₀ = 0.01 > Δt
+    ref = sr.sumregs_pdps(f, list(x0), maxiter=300)
+    assert np.array_equal(u, ref) and abs(cost - orc.cost(ref, t)) <= 1e-12 * cost
+    assert g.shape == (3,) and np.all(np.isfinite(g))
+    st = ctx.stats()
+    assert st["ms_gradient"] > 0 and st["kernel_launches"] == 2 * 300 + 2 + 5
+    u2, cost2, g2 = bp.sumregs_learning_function(x0, (t, f), 1e-4, ctx=ctx, maxiter=300)  # Δ ≤ Δt: regularised
+    assert np.array_equal(u2, u) and cost2 == cost and not np.allclose(g, g2)
+    lit = sr.sumregs_gradient_reg(x0, ref[:, :, 0], t[:, :, 0], refine=3)
+    assert np.all(np.abs(g2 - lit) <= 1e-9 * np.abs(lit)), (g2, lit)
+    with pytest.raises(bp.BpltvError):
+        ctx.sumregs_learn_eval(np.array([0.1, 0.0, 0.1]), 0.1)          # λ must be > 0 for the gradient
