@@ -436,6 +436,22 @@ def learn_eval_extras(bp):
                 val = bp.validate_tv_parameter(float(res.x), ds["faces_val_128_10"], ctx=c)
                 out[name]["validation"] = {"seconds": time.perf_counter() - t0, "cost": val["cost"],
                                            "mean_psnr": val["mean_psnr"], "mean_ssim": val["mean_ssim"]}
+    # sum-of-regularisers interface: one sumregs_learning_function evaluation on the
+    # reference's cameraman dataset at α₀ = [0.001, 0.001, 0.001], both gradient branches
+    data = ds["cameraman_128_5"]
+    with bp.Context([0], 64) as c:
+        c.set_dataset(data)
+        x0 = np.array([0.001, 0.001, 0.001])
+        c.sumregs_learn_eval(x0, 0.01)
+        rec = {}
+        for name, Delta in (("sumregs_gradient", 0.01), ("sumregs_gradient_reg", 1e-4)):
+            t0 = time.perf_counter()
+            _, cost, g = c.sumregs_learn_eval(x0, Delta)
+            st = c.stats()
+            rec[name] = {"ms": (time.perf_counter() - t0) * 1e3, "ms_pdps": st["ms_pdps"], "ms_gradient": st["ms_gradient"],
+                         "cost": cost, "grad": np.asarray(g).ravel().tolist()}
+        out["sumregs_cameraman_128_5"] = rec
+
     # λ-sweep (generate_scalar_tv_cost, /root/reference/src/BPLDenoising.jl:92-130): 64 parameters ×
     # 1 image 128×128 × 10000 iterations, batched into one launch vs the reference's loop of solves
     data = bp.synthetic_dataset(128, 128, 1, seed=7)

@@ -36,6 +36,9 @@ EPS = float(np.finfo(np.float64).eps)
 # /root/reference/src/BPLDenoising.jl:306-323 (scalar) and :350-357 (patch)
 DEFAULT_PARAMS = dict(verbose_iter=1, maxiter=20, tol=1e-5)
 BILEVEL_PARAMS = dict(eta1=0.25, eta2=0.75, beta1=0.25, beta2=1.9, Delta0=0.1, alpha0=0.1)
+# /root/reference/src/BPLDenoising.jl:423-430 (scalar sum-of-regularisers experiment)
+SUMREGS_BILEVEL_PARAMS = dict(eta1=0.25, eta2=0.75, beta1=0.25, beta2=1.9, Delta0=0.01,
+                              alpha0=np.array([0.001, 0.001, 0.001]))
 PATCH_BILEVEL_PARAMS = dict(eta1=0.25, eta2=0.75, beta1=0.25, beta2=1.9, Delta0=1e-4,
                             alpha0=1e-4 * np.ones((2, 2)))
 
@@ -221,4 +224,14 @@ def patch_bilevel_tv_learn(data, ctx=None, **kwargs) -> LearnResult:
 
     prm = dict(PATCH_BILEVEL_PARAMS); prm.update(kwargs)
     return bilevel_learn(data, lambda x, ds, D: tv_op_learning_function(x, ds, D, ctx=ctx),
+                         prm.pop("alpha0"), prm)
+
+
+def scalar_bilevel_sumregs_learn(data, ctx=None, **kwargs) -> LearnResult:
+    """scalar_bilevel_sumregs_learn (BPLDenoising.jl:432-451) without IO/visualisation: the
+    3-vector parameter takes the driver's array path (L-BFGS model, TRBox.jl:50, :99-114)."""
+    from .learning import sumregs_learning_function
+
+    prm = dict(SUMREGS_BILEVEL_PARAMS); prm.update(kwargs)
+    return bilevel_learn(data, lambda x, ds, D: sumregs_learning_function(x, ds, D, ctx=ctx),
                          prm.pop("alpha0"), prm)

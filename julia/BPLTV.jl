@@ -12,7 +12,7 @@
 # by the equivalent ctypes binding (bpldenoising_b200/_lib.py), which calls the same symbols.
 module BPLTV
 
-export tv_op_learning_function, denoise, TVDenoise, generate_cost, bpltv_context, set_devices!
+export tv_op_learning_function, sumregs_learning_function, sumregs_denoise, denoise, TVDenoise, generate_cost, bpltv_context, set_devices!
 
 const lib = get(ENV, "BPLTV_LIB", joinpath(@__DIR__, "..", "bpldenoising_b200", "libbpltv.so"))
 
@@ -102,6 +102,44 @@ function tv_op_learning_function(x, data, Δ; Δt=1e-6, kwargs...)
                 (Ptr{Cvoid}, Ptr{Cdouble}, Cint, Cint, Cdouble, Ref{EvalOpts}, Ptr{Cdouble}, Ref{Cdouble}, Ptr{Cdouble}),
                 h, l, lm, ln, Δ, eo, u, cost, grad))
     return u, cost[], (x isa Real ? grad[1] : grad)   # grad has the shape of x (src/TRBox.jl:63,237)
+end
+
+# ---- sum-of-regularisers interface (src/SumRegsLearningFunction.jl) -------------------------------
+lam3(x::AbstractVector) = (Vector{Float64}(x), 1, 1)
+lam3(x::AbstractArray{<:Real,3}) = (Array{Float64,3}(x), size(x, 1), size(x, 2))
+function default_sumregs_eval()
+    r = Ref{EvalOpts}()
+    ccall((:bpltv_default_sumregs_eval_opts, lib), Cvoid, (Ref{EvalOpts},), r)
+    r[]
+end
+
+"sumregs_denoise(data, x, op₁, op₂, op₃[, pOp]) — src/SumRegsLearningFunction.jl:38-85"
+function sumregs_denoise(data::AbstractArray{<:Real,3}, x, ops...; kwargs...)
+    f = Array{Float64,3}(data); M, N, O = size(f)
+    l, lm, ln = lam3(x); o = Ref(with(default_sumregs_eval().pdps; kwargs...)); u = similar(f)
+    check(ccall((:bpltv_sumregs_denoise, lib), Cint,
+                (Ptr{Cvoid}, Ptr{Cdouble}, Cint, Cint, Cint, Ptr{Cdouble}, Cint, Cint, Ref{PdpsOpts}, Ptr{Cdouble}),
+                bpltv_context(), f, M, N, O, l, lm, ln, o, u))
+    u
+end
+
+"sumregs_learning_function(x, data, Δ; Δt=1e-3) → (u, cost, grad) — src/SumRegsLearningFunction.jl:8-36"
+function sumregs_learning_function(x, data, Δ; Δt=1e-3)
+    ū, f = data[1], data[2]
+    M, N, O = size(f)
+    h = bpltv_context()
+    if resident[] !== data
+        check(ccall((:bpltv_set_dataset, lib), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cint, Cint),
+                    h, Array{Float64,3}(ū), Array{Float64,3}(f), M, N, O))
+        resident[] = data
+    end
+    l, lm, ln = lam3(x)
+    eo = Ref(with(default_sumregs_eval(); delta_t=Δt))
+    u = Array{Float64,3}(undef, M, N, O); cost = Ref{Cdouble}(0); grad = zeros(size(x))
+    check(ccall((:bpltv_sumregs_learn_eval, lib), Cint,
+                (Ptr{Cvoid}, Ptr{Cdouble}, Cint, Cint, Cdouble, Ref{EvalOpts}, Ptr{Cdouble}, Ref{Cdouble}, Ptr{Cdouble}),
+                h, l, lm, ln, Δ, eo, u, cost, grad))
+    return u, cost[], grad                       # grad has the shape of x (3-vector or m×n×3)
 end
 
 """

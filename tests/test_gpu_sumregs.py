@@ -130,3 +130,15 @@ def test_sumregs_learning_function_end_to_end(bp, ctx, sr, datasets):
     assert np.all(np.abs(g2 - lit) <= 1e-9 * np.abs(lit)), (g2, lit)
     with pytest.raises(bp.BpltvError):
         ctx.sumregs_learn_eval(np.array([0.1, 0.0, 0.1]), 0.1)          # λ must be > 0 for the gradient
+
+
+def test_scalar_bilevel_sumregs_learn_run(bp, ctx, datasets):
+    """scalar_bilevel_sumregs_learn (BPLDenoising.jl:432-451) through the host restatement of the trust-region
+    driver: the learned 3-vector stays positive and lowers the upper-level cost."""
+    from bpldenoising_b200 import trbox
+    t, f = _crop(datasets, "cameraman_128_5", 64, off=32)
+    res = trbox.scalar_bilevel_sumregs_learn((t, f), ctx=ctx, maxiter=6)
+    assert np.shape(res.x) == (3,) and np.all(np.asarray(res.x) > 0)
+    assert res.evaluations == len(res.log) + 1
+    c0 = bp.sumregs_learning_function(np.array([0.001, 0.001, 0.001]), (t, f), 0.01, ctx=ctx)[1]
+    assert res.log[-1].function_value <= c0
