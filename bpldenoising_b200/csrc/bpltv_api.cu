@@ -244,30 +244,39 @@ static void launch_generic(const GenericArgs<Real> &a, bool map, bool strict, cu
 template <typename Real, int T>
 using TBlockFn = void (*)(const TBlockArgs<Real, T>);
 
-template <typename Real, int VEC, int T>
-static TBlockFn<Real, T> tblock_fn_vec(bool map, bool strict)
+template <typename Real, int VEC, int T, bool BATCH>
+static TBlockFn<Real, T> tblock_fn_cfg(bool map, bool strict)
 {
     // register budget: T=2 keeps two 256-thread CTAs per SM, deeper pipelines one.
     // 16-byte vectors (whole columns are then 16-byte multiples) take the TMA prefetch ring.
     constexpr int MINB = T <= 2 ? 2 : 1;
     constexpr bool RING = VEC * sizeof(Real) == 16;
-    if (map) return strict ? pdps_tblock_kernel<Real, VEC, T, true, true, RING, 256, MINB>
-                           : pdps_tblock_kernel<Real, VEC, T, true, false, RING, 256, MINB>;
-    return strict ? pdps_tblock_kernel<Real, VEC, T, false, true, RING, 256, MINB>
-                  : pdps_tblock_kernel<Real, VEC, T, false, false, RING, 256, MINB>;
+    if (map) return strict ? pdps_tblock_kernel<Real, VEC, T, true, true, RING, BATCH, 256, MINB>
+                           : pdps_tblock_kernel<Real, VEC, T, true, false, RING, BATCH, 256, MINB>;
+    return strict ? pdps_tblock_kernel<Real, VEC, T, false, true, RING, BATCH, 256, MINB>
+                  : pdps_tblock_kernel<Real, VEC, T, false, false, RING, BATCH, 256, MINB>;
 }
 
-template <int T> static TBlockFn<double, T> tblock_fn(double, int vec, bool map, bool strict)
+// λ-sweeps (batch = true) are built for the depths AUTO uses (T = 2, 4) only
+template <typename Real, int VEC, int T>
+static TBlockFn<Real, T> tblock_fn_vec(bool map, bool strict, bool batch)
 {
-    if (vec == 2) return tblock_fn_vec<double, 2, T>(map, strict);
-    if (vec == 1) return tblock_fn_vec<double, 1, T>(map, strict);
+    if (!batch) return tblock_fn_cfg<Real, VEC, T, false>(map, strict);
+    if constexpr (T == 3) return nullptr;
+    else return tblock_fn_cfg<Real, VEC, T, true>(map, strict);
+}
+
+template <int T> static TBlockFn<double, T> tblock_fn(double, int vec, bool map, bool strict, bool batch)
+{
+    if (vec == 2) return tblock_fn_vec<double, 2, T>(map, strict, batch);
+    if (vec == 1) return tblock_fn_vec<double, 1, T>(map, strict, batch);
     return nullptr;
 }
-template <int T> static TBlockFn<float, T> tblock_fn(float, int vec, bool map, bool strict)
+template <int T> static TBlockFn<float, T> tblock_fn(float, int vec, bool map, bool strict, bool batch)
 {
-    if (vec == 4) return tblock_fn_vec<float, 4, T>(map, strict);
-    if (vec == 2) return tblock_fn_vec<float, 2, T>(map, strict);
-    if (vec == 1) return tblock_fn_vec<float, 1, T>(map, strict);
+    if (vec == 4) return tblock_fn_vec<float, 4, T>(map, strict, batch);
+    if (vec == 2) return tblock_fn_vec<float, 2, T>(map, strict, batch);
+    if (vec == 1) return tblock_fn_vec<float, 1, T>(map, strict, batch);
     return nullptr;
 }
 
@@ -297,7 +306,9 @@ static int run_tblock_passes(Dev &d, const Real *f, int M, int N, int O, Real al
 {
     const int vec = tblock_vec<Real>(M);
     const int nthreads = (M / vec + 31) / 32 * 32;
-    TBlockFn<Real, T> fn = tblock_fn<T>(Real(), vec, alpha_map != nullptr, strict);
+    const bool batch = bm.alpha_vec != nullptr || bm.f_mod != 0 || bm.lam_div != 0;
+    TBlockFn<Real, T> fn = tblock_fn<T>(Real(), vec, alpha_map != nullptr, strict, batch);
+    if (!fn) return -2;
     const size_t smem = (vec * sizeof(Real) == 16) ? tblock_ring_bytes<Real, T>(M) : 0;
     if (smem > d.smem_optin) return -1;
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
@@ -408,6 +419,7 @@ static int run_pdps(Dev &d, const Real *f, int M, int N, int O, double alpha_s, 
         if (tdepth == 2) done = run_tblock_passes<Real, 2>(d, f, M, N, O, (Real)alpha_s, alpha_map, strict, 0, o.maxiter, st, &buf, bm);
         else if (tdepth == 3) done = run_tblock_passes<Real, 3>(d, f, M, N, O, (Real)alpha_s, alpha_map, strict, 0, o.maxiter, st, &buf, bm);
         else done = run_tblock_passes<Real, 4>(d, f, M, N, O, (Real)alpha_s, alpha_map, strict, 0, o.maxiter, st, &buf, bm);
+        if (done == -2) return fail(BPLTV_ERR_ARG, "λ-sweeps through the temporally blocked kernel are built for depths 2 and 4 only");
         if (done < 0) { cudaGetLastError(); return fail(BPLTV_ERR_CUDA, "temporally blocked PDPS kernel: occupancy query failed"); }
         it_begin = done;  // the remainder (< T iterations) runs as single-iteration passes below
     }

@@ -317,7 +317,9 @@ static __device__ __forceinline__ void tblock_step(const int c, const TBStage<Re
 template <typename Real, int T>
 static inline size_t tblock_ring_bytes(int M) { return (size_t)(3 * TB_R + TBRingF<T>::value) * M * sizeof(Real); }
 
-template <typename Real, int VEC, int T, bool MAP, bool STRICT, bool RING, int MAXT, int MINB>
+// BATCH: the stack is a λ-sweep's virtual stack (BatchMap: per-image λ, shared f); kept out of the plain
+// instantiation because its per-segment values cost registers the T = 2 kernel does not have to spare
+template <typename Real, int VEC, int T, bool MAP, bool STRICT, bool RING, bool BATCH, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) pdps_tblock_kernel(const TBlockArgs<Real, T> a)
 {
     typedef VecIO<Real, VEC> IO;
@@ -362,9 +364,13 @@ __global__ void __launch_bounds__(MAXT, MINB) pdps_tblock_kernel(const TBlockArg
         gc += c1 - c0;
         const size_t img = (size_t)o * M * N;
         g.xin = a.x_in + img; g.y1in = a.y1_in + img; g.y2in = a.y2_in + img;
-        g.fin = a.f + (size_t)a.bm.f_image(o) * M * N;
-        if (MAP) g.amap = a.alpha_map + (size_t)a.bm.lam_set(o) * a.bm.map_stride;
-        g.alpha_s = a.bm.scalar(o, a.alpha_s);
+        if (BATCH) {
+            g.fin = a.f + (size_t)a.bm.f_image(o) * M * N;
+            if (MAP) g.amap = a.alpha_map + (size_t)a.bm.lam_set(o) * a.bm.map_stride;
+            g.alpha_s = a.bm.scalar(o, a.alpha_s);
+        } else {
+            g.fin = a.f + img;
+        }
         g.xout = a.x_out + img; g.y1out = a.y1_out + img; g.y2out = a.y2_out + img;
         g.c0 = c0; g.c1 = c1;
         const int cs = max(0, c0 - (T - 1));                           // first marched column

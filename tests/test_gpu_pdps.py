@@ -301,4 +301,5 @@ def test_config4_full_size_is_bit_identical_to_the_oracle_pins(bp, ctx, ctx32):
         got = [hashlib.sha256(np.ascontiguousarray(u[:, :, o].astype(dt).T).tobytes()).hexdigest()
                for o in range(pins["O"])]
         assert got == pins[key]["u_sha256"], key
-        assert abs(cost - pins[key]["cost"]) <= 1e-12 * cost, (key, cost)
+        # an fp32 context also holds ū in fp32 (k/255 rounded), so its loss differs from the fp64 one in the 8th digit
+        assert abs(cost - pins[key]["cost"]) <= (1e-12 if key == "f64" else 1e-6) * cost, (key, cost)
