@@ -20,6 +20,8 @@
 //
 // Mapping: one CTA per image "slot"; images are processed in waves of ≤ #SM slots.
 #pragma once
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 #include <string>
 
@@ -402,15 +404,27 @@ static __device__ __forceinline__ void tile_update(double *a22, int LDa, int nro
         }
 }
 
+// CL: the image is factorised by a thread-block CLUSTER (csize CTAs, one SM each).  Every CTA forms the
+// (cheap) panel and the look-ahead block redundantly in its own shared memory; the tiles of the trailing
+// update — where the flops are — are dealt round-robin over all update warps of the cluster, and one
+// cluster barrier per block step publishes them (global memory, release/acquire at cluster scope).
+// Only rank 0 writes L11 and the panel back to the band; the panel write-back is deferred by one step
+// because the other CTAs are still reading those entries while they form their own copy.
+template <bool CL>
 __global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws, double guard, int use_stage, int dbg)
 {
     extern __shared__ __align__(16) double sm[];
     constexpr int NB = GRAD_NB;
+    int crank = 0, csize = 1;
+    if (CL) {
+        cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+        crank = (int)cluster.block_rank(); csize = (int)cluster.num_blocks();
+    }
     double *Sbuf = sm;                 // 2 × NB*NB: L11 of the current / next block
     double *Dbuf = sm + 2 * NB * NB;   // 2 × NB: 1/diag of those; + NB*NB raw next diagonal block
     double *Araw = sm + 3 * NB * NB;   // NB*NB: next diagonal block before its update (cp.async target)
     double *P = sm + 4 * NB * NB;      // NB × PR panel, c-major
-    const int slot = blockIdx.x;
+    const int slot = CL ? (int)blockIdx.x / csize : (int)blockIdx.x;
     int *info = ws.info + 4 * slot;
     const int Nd = info[0], LDa = info[1];
     const int PR = (LDa + 7) & ~7;     // rows of P, padded to the 4×8 tiles
@@ -436,8 +450,20 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws,
     }
     __syncthreads();
 
+    int wb_kb = -1, wb_nb = 0, wb_rows = 0;   // CL: panel of the previous step, still to be written back
+    auto write_back = [&]() {
+        if (CL && crank == 0 && wb_kb >= 0)
+            for (int r = tid; r < wb_rows; r += blockDim.x) {
+                const int i = wb_kb + wb_nb + r;
+#pragma unroll
+                for (int c = 0; c < NB; ++c)
+                    if (c < wb_nb) ab[(size_t)(wb_kb + c) * LDa + (i - wb_kb - c)] = P[c * PR + r];
+            }
+        wb_kb = -1;
+    };
     for (int kb = 0, blk = 0; kb < Nd; kb += NB, ++blk) {
         const int cur = blk & 1;
+        write_back();                            // same thread ↔ row mapping as the panel loop below
         double *S = Sbuf + cur * NB * NB, *dinv = Dbuf + cur * NB;
         double *Sn = Sbuf + (cur ^ 1) * NB * NB, *dinvn = Dbuf + (cur ^ 1) * NB;
         const int nb = min(NB, Nd - kb);
@@ -454,10 +480,11 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws,
             asm volatile("cp.async.commit_group;");
         }
         // ---- store L11; (1) panel rows by forward substitution: x L11ᵀ = a ---------------
-        for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
-            const int r = idx / NB, c = idx % NB;
-            if (r < nb && c <= r) ab[(size_t)(kb + c) * LDa + (r - c)] = S[idx];
-        }
+        if (!CL || crank == 0)
+            for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
+                const int r = idx / NB, c = idx % NB;
+                if (r < nb && c <= r) ab[(size_t)(kb + c) * LDa + (r - c)] = S[idx];
+            }
         for (int r = tid; r < PR; r += blockDim.x) {
             double x[NB];
             if (r < nrows && !(dbg & 4)) {
@@ -475,9 +502,11 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws,
                     }
                     x[c] = (s0 + s1) * dinv[c];
                 }
+                if (!CL) {
 #pragma unroll
-                for (int c = 0; c < NB; ++c)
-                    if (c < nb) ab[(size_t)(kb + c) * LDa + (i - kb - c)] = x[c];
+                    for (int c = 0; c < NB; ++c)
+                        if (c < nb) ab[(size_t)(kb + c) * LDa + (i - kb - c)] = x[c];
+                }
             } else {
 #pragma unroll
                 for (int c = 0; c < NB; ++c) x[c] = 0.0;
@@ -487,6 +516,7 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws,
         }
         if (warp == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
+        if (CL) { wb_kb = kb; wb_nb = nb; wb_rows = max(nrows, 0); }
         if (nrows <= 0) break;
         if (warp == 0) {
             // ---- (3) look-ahead: next diagonal block = A22[0:NB,0:NB] - P Pᵀ, factor ----------
@@ -515,21 +545,25 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws,
             // cross the diagonal (rows 2tj, 2tj+1) or hang over the last row are gathered into
             // separate boundary rounds, so no warp executes both paths for one item.
             const int nti = (nrows + 3) >> 2, ntj = (nrows + 7) >> 3, nfull = nrows >> 2;
-            const int uw = warp - 1, nuw = nwarps - 1;
+            const int uw = (warp - 1) + (nwarps - 1) * crank, nuw = (nwarps - 1) * csize;   // update warps of the cluster
             const int ut = tid - 32;               // index among the update threads
-            int item = 0;
+            // item k of the step belongs to update warp k mod nuw; `skip` = items between here and this
+            // warp's next one, carried across tile columns so that no division or per-item scan is needed
+            int skip = uw;
             for (int tj = 0; tj < ntj; ++tj) {
-                for (int tbase = 2 * tj + 2; tbase < nfull; tbase += 32, ++item) {
-                    if (item % nuw != uw) continue;
-                    const int ti = tbase + lane;
+                const int first = 2 * tj + 2;
+                const int cj = nfull > first ? (nfull - first + 31) >> 5 : 0;   // interior items of this column
+                int k = skip;
+                for (; k < cj; k += nuw) {
+                    const int ti = first + 32 * k + lane;
                     if (ti < nfull && !(ti < 4 && tj < 2))   // (ti<4,tj<2): next diagonal block (warp 0)
                         tile_update<true>(a22, LDa, nrows, P, PR, 4 * ti, 8 * tj, use_stage != 0, stage, nstage, ut);
                 }
+                skip = k - cj;
             }
             const int nbound = 3 * ntj;            // (tj, kind): kind 0,1 → rows 2tj, 2tj+1; kind 2 → partial last row
-            for (int bbase = 0; bbase < nbound; bbase += 32, ++item) {
-                if (item % nuw != uw) continue;
-                const int b = bbase + lane;
+            for (int k = skip; 32 * k < nbound; k += nuw) {
+                const int b = 32 * k + lane;
                 if (b >= nbound) continue;
                 const int tj = b / 3, kind = b - 3 * tj;
                 int ti = 2 * tj + kind;
@@ -538,15 +572,16 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws,
                 tile_update<false>(a22, LDa, nrows, P, PR, 4 * ti, 8 * tj, use_stage != 0, stage, nstage, ut);
             }
         }
-        __syncthreads();
+        if (CL) cooperative_groups::this_cluster().sync(); else __syncthreads();
     }
-    if (tid == 0) info[2] = guarded;
-    __syncthreads();
+    write_back();
+    if (tid == 0 && crank == 0) info[2] = guarded;
+    if (CL) cooperative_groups::this_cluster().sync(); else __syncthreads();
     // ---- all L11⁻¹ (used by the triangular solves) in one parallel pass: warp per block ----
     {
         double *Lw = P + warp * 2 * NB * NB, *Siw = Lw + NB * NB;  // per-warp scratch (P is free now)
         const int nblk = (Nd + NB - 1) / NB;
-        for (int blk = warp; blk < nblk; blk += nwarps) {
+        for (int blk = warp + nwarps * crank; blk < nblk; blk += nwarps * csize) {
             const int kb = blk * NB, nb = min(NB, Nd - kb);
             for (int idx = lane; idx < NB * NB; idx += 32) {
                 const int r = idx / NB, c = idx % NB;
@@ -879,6 +914,43 @@ __global__ void grad_reduce_kernel(const double *out_img, const double *relres_i
 // ---------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------
+// launches the factorisation of `cnt` slots, `C` CTAs (one cluster) per slot
+static inline cudaError_t launch_factor(const GradSlots &ws, double guard, int use_stage, int dbg, int cnt, int C,
+                                        size_t smem, cudaStream_t st)
+{
+    if (C <= 1) {
+        cudaError_t e = cudaFuncSetAttribute(grad_factor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        grad_factor_kernel<false><<<cnt, GRAD_THREADS, smem, st>>>(ws, guard, use_stage, dbg);
+        return cudaGetLastError();
+    }
+    cudaError_t e = cudaFuncSetAttribute(grad_factor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(cnt * C));
+    cfg.blockDim = dim3(GRAD_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, grad_factor_kernel<true>, ws, guard, use_stage, dbg);
+}
+
+// CTAs per image for the factorisation: as many as leave every image of the wave its own cluster
+static inline int factor_cluster_size(int images_in_wave, int sm_count)
+{
+    const char *env = getenv("BPLTV_GRAD_CLUSTER");
+    if (env && *env) { const int c = atoi(env); if (c == 1 || c == 2 || c == 4 || c == 8) return c; }
+    int C = 1;
+    while (C < 8 && 2 * C * images_in_wave <= sm_count) C *= 2;
+    return C;
+}
+
 struct GradWork {
     void *pix = nullptr, *mode = nullptr, *sinv = nullptr, *ab = nullptr, *off = nullptr, *ext = nullptr,
          *info = nullptr, *out_img = nullptr, *relres = nullptr, *relres_max = nullptr;
@@ -985,7 +1057,6 @@ static int run_gradient(GradWork &w, const GradProblem<Real> &gp, int sm_count, 
     if (gv.regularised && gv.patch) cscale = 1.0;  // refined below from the map's max on the host side if needed
     const double guard = gv.guard_rel * cscale;
 
-    cudaFuncSetAttribute(grad_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     // solve vector in shared memory when it fits next to the static arrays
     const size_t nr_bytes = ((size_t)ws.nblkMax * 2 + 15) & ~(size_t)15;
     if (nr_bytes + 8192 + 4096 > smem_optin) return grad_fail(w, -1, "image too large for the solve kernel's block table");
@@ -997,7 +1068,11 @@ static int run_gradient(GradWork &w, const GradProblem<Real> &gp, int sm_count, 
         const int cnt = std::min(slots, gp.O - img0);
         grad_classify_kernel<Real><<<cnt, GRAD_THREADS, 0, st>>>(ws, gv, gp.u, gp.ubar, gp.alpha_map, img0);
         grad_assemble_kernel<<<cnt, GRAD_THREADS, 0, st>>>(ws);
-        grad_factor_kernel<<<cnt, GRAD_THREADS, smem, st>>>(ws, guard, use_stage, getenv("BPLTV_GRAD_DBG") ? atoi(getenv("BPLTV_GRAD_DBG")) : 0);
+        {
+            cudaError_t fe = launch_factor(ws, guard, use_stage, getenv("BPLTV_GRAD_DBG") ? atoi(getenv("BPLTV_GRAD_DBG")) : 0, cnt,
+                                           factor_cluster_size(cnt, sm_count), smem, st);
+            if (fe != cudaSuccess) { cudaGetLastError(); return grad_fail(w, -2, std::string("factor launch failed: ") + cudaGetErrorString(fe)); }
+        }
         grad_solve_kernel<<<cnt, GRAD_THREADS, zs_bytes, st>>>(ws, gv, (double *)w.out_img, (double *)w.relres, img0,
                                                                 zs_cap);
         *launches += 4;

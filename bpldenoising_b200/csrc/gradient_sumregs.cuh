@@ -468,7 +468,6 @@ static int run_gradient3(GradWork &w, const Grad3Problem<Real> &gp, int sm_count
     gv.refine = 1;
     const double guard = 1e-13;
 
-    cudaFuncSetAttribute(grad_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const size_t nr_bytes = ((size_t)ws.nblkMax * 2 + 15) & ~(size_t)15;
     if (nr_bytes + 8192 + 4096 > smem_optin) return grad_fail(w, -1, "image too large for the solve kernel's block table");
     const size_t zs_only = std::min<size_t>((size_t)ws.NdMax * 8, smem_optin - 8192 - nr_bytes);
@@ -479,7 +478,10 @@ static int run_gradient3(GradWork &w, const Grad3Problem<Real> &gp, int sm_count
         const int cnt = std::min(slots, gp.O - img0);
         grad3_classify_kernel<Real><<<cnt, GRAD_THREADS, 0, st>>>(ws, gv, gp.u, gp.ubar, gp.alpha_maps, img0);
         grad3_assemble_kernel<<<cnt, GRAD_THREADS, 0, st>>>(ws);
-        grad_factor_kernel<<<cnt, GRAD_THREADS, smem, st>>>(ws, guard, use_stage, 0);
+        {
+            cudaError_t fe = launch_factor(ws, guard, use_stage, 0, cnt, factor_cluster_size(cnt, sm_count), smem, st);
+            if (fe != cudaSuccess) { cudaGetLastError(); return grad_fail(w, -2, std::string("factor launch failed: ") + cudaGetErrorString(fe)); }
+        }
         grad3_solve_kernel<<<cnt, GRAD_THREADS, zs_bytes, st>>>(ws, gv, (double *)w.out_img, (double *)w.relres, img0, zs_cap);
         *launches += 4;
     }
