@@ -451,19 +451,19 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws,
     __syncthreads();
 
     int wb_kb = -1, wb_nb = 0, wb_rows = 0;   // CL: panel of the previous step, still to be written back
-    auto write_back = [&]() {
-        if (CL && crank == 0 && wb_kb >= 0)
-            for (int r = tid; r < wb_rows; r += blockDim.x) {
-                const int i = wb_kb + wb_nb + r;
-#pragma unroll
-                for (int c = 0; c < NB; ++c)
-                    if (c < wb_nb) ab[(size_t)(wb_kb + c) * LDa + (i - wb_kb - c)] = P[c * PR + r];
-            }
-        wb_kb = -1;
-    };
+// (same thread ↔ row mapping as the panel loop, so no barrier is needed between the two)
+#define BPLTV_FACTOR_WRITE_BACK()                                                                        \
+    if (CL) {                                                                                            \
+        if (crank == 0 && wb_kb >= 0)                                                                    \
+            for (int r = tid; r < wb_rows; r += blockDim.x) {                                            \
+                const int i_ = wb_kb + wb_nb + r;                                                        \
+                for (int c = 0; c < wb_nb; ++c) ab[(size_t)(wb_kb + c) * LDa + (i_ - wb_kb - c)] = P[c * PR + r]; \
+            }                                                                                            \
+        wb_kb = -1;                                                                                      \
+    }
     for (int kb = 0, blk = 0; kb < Nd; kb += NB, ++blk) {
         const int cur = blk & 1;
-        write_back();                            // same thread ↔ row mapping as the panel loop below
+        BPLTV_FACTOR_WRITE_BACK()
         double *S = Sbuf + cur * NB * NB, *dinv = Dbuf + cur * NB;
         double *Sn = Sbuf + (cur ^ 1) * NB * NB, *dinvn = Dbuf + (cur ^ 1) * NB;
         const int nb = min(NB, Nd - kb);
@@ -574,7 +574,8 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws,
         }
         if (CL) cooperative_groups::this_cluster().sync(); else __syncthreads();
     }
-    write_back();
+    BPLTV_FACTOR_WRITE_BACK()
+#undef BPLTV_FACTOR_WRITE_BACK
     if (tid == 0 && crank == 0) info[2] = guarded;
     if (CL) cooperative_groups::this_cluster().sync(); else __syncthreads();
     // ---- all L11⁻¹ (used by the triangular solves) in one parallel pass: warp per block ----
@@ -941,11 +942,15 @@ static inline cudaError_t launch_factor(const GradSlots &ws, double guard, int u
     return cudaLaunchKernelEx(&cfg, grad_factor_kernel<true>, ws, guard, use_stage, dbg);
 }
 
-// CTAs per image for the factorisation: as many as leave every image of the wave its own cluster
-static inline int factor_cluster_size(int images_in_wave, int sm_count)
+// CTAs per image for the factorisation: as many as leave every image of the wave its own cluster.
+// Only wide bands have enough trailing-update tiles per block step to share (sum-of-regularisers:
+// ≥ 771 rows); the TV band (≈ 130-260 rows at 128²) is bound by the per-step latency chain (panel →
+// look-ahead pivots → barrier), which a cluster barrier only lengthens (measured: 24 ms with 1 or 8 CTAs).
+static inline int factor_cluster_size(int images_in_wave, int sm_count, int max_band)
 {
     const char *env = getenv("BPLTV_GRAD_CLUSTER");
     if (env && *env) { const int c = atoi(env); if (c == 1 || c == 2 || c == 4 || c == 8) return c; }
+    if (max_band < 600) return 1;
     int C = 1;
     while (C < 8 && 2 * C * images_in_wave <= sm_count) C *= 2;
     return C;
@@ -1070,7 +1075,7 @@ static int run_gradient(GradWork &w, const GradProblem<Real> &gp, int sm_count, 
         grad_assemble_kernel<<<cnt, GRAD_THREADS, 0, st>>>(ws);
         {
             cudaError_t fe = launch_factor(ws, guard, use_stage, getenv("BPLTV_GRAD_DBG") ? atoi(getenv("BPLTV_GRAD_DBG")) : 0, cnt,
-                                           factor_cluster_size(cnt, sm_count), smem, st);
+                                           factor_cluster_size(cnt, sm_count, ws.LD), smem, st);
             if (fe != cudaSuccess) { cudaGetLastError(); return grad_fail(w, -2, std::string("factor launch failed: ") + cudaGetErrorString(fe)); }
         }
         grad_solve_kernel<<<cnt, GRAD_THREADS, zs_bytes, st>>>(ws, gv, (double *)w.out_img, (double *)w.relres, img0,

@@ -142,3 +142,28 @@ def test_scalar_bilevel_sumregs_learn_run(bp, ctx, datasets):
     assert res.evaluations == len(res.log) + 1
     c0 = bp.sumregs_learning_function(np.array([0.001, 0.001, 0.001]), (t, f), 0.01, ctx=ctx)[1]
     assert res.log[-1].function_value <= c0
+
+
+def test_cluster_factorisation_is_invisible(bp, ctx, sr, datasets):
+    """The banded Cholesky shared by a thread-block cluster (2, 4, 8 CTAs per image) gives bit-identical
+    gradients to the single-CTA factorisation, for the TV and the sum-of-regularisers systems."""
+    import os
+    t, f = _crop(datasets, "faces_train_128_10", 40, k=3, off=20)
+    ctx.set_dataset((t, f))
+    x3 = np.array([0.03, 0.02, 0.04])
+    u3 = sr.sumregs_pdps(f, list(x3), maxiter=200)
+    utv = ctx.denoise(f, 0.07, bp.pdps_opts(maxiter=300))
+    ref = {}
+    for C in ("1", "2", "4", "8"):
+        os.environ["BPLTV_GRAD_CLUSTER"] = C
+        try:
+            got = (ctx.gradient(0.07, utv, False), ctx.gradient(0.07, utv, True),
+                   ctx.sumregs_gradient(x3, u3, False), ctx.sumregs_gradient(x3, u3, True))
+        finally:
+            del os.environ["BPLTV_GRAD_CLUSTER"]
+        if C == "1":
+            ref = got
+        else:
+            assert got[0] == ref[0] and got[1] == ref[1], C
+            # the sum-of-regularisers assembly adds with atomics: equal up to summation order
+            assert np.allclose(got[2], ref[2], rtol=1e-11, atol=0) and np.allclose(got[3], ref[3], rtol=1e-11, atol=0), C
