@@ -547,8 +547,32 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws,
             const int nti = (nrows + 3) >> 2, ntj = (nrows + 7) >> 3, nfull = nrows >> 2;
             const int uw = (warp - 1) + (nwarps - 1) * crank, nuw = (nwarps - 1) * csize;   // update warps of the cluster
             const int ut = tid - 32;               // index among the update threads
-            // item k of the step belongs to update warp k mod nuw; `skip` = items between here and this
-            // warp's next one, carried across tile columns so that no division or per-item scan is needed
+            // item k of the step belongs to update warp k mod nuw.
+            if (nrows < 400) {
+                // narrow band (TV): a few dozen items per step — the plain scan is the faster code (A/B on B200)
+                int item = 0;
+                for (int tj = 0; tj < ntj; ++tj) {
+                    for (int tbase = 2 * tj + 2; tbase < nfull; tbase += 32, ++item) {
+                        if (item % nuw != uw) continue;
+                        const int ti = tbase + lane;
+                        if (ti < nfull && !(ti < 4 && tj < 2))   // (ti<4,tj<2): next diagonal block (warp 0)
+                            tile_update<true>(a22, LDa, nrows, P, PR, 4 * ti, 8 * tj, use_stage != 0, stage, nstage, ut);
+                    }
+                }
+                const int nbound = 3 * ntj;        // (tj, kind): kind 0,1 → rows 2tj, 2tj+1; kind 2 → partial last row
+                for (int bbase = 0; bbase < nbound; bbase += 32, ++item) {
+                    if (item % nuw != uw) continue;
+                    const int b = bbase + lane;
+                    if (b >= nbound) continue;
+                    const int tj = b / 3, kind = b - 3 * tj;
+                    int ti = 2 * tj + kind;
+                    if (kind == 2) { ti = nti - 1; if (nti == nfull || ti <= 2 * tj + 1) continue; }
+                    if (ti >= nti || (ti < 4 && tj < 2)) continue;
+                    tile_update<false>(a22, LDa, nrows, P, PR, 4 * ti, 8 * tj, use_stage != 0, stage, nstage, ut);
+                }
+            } else {
+            // wide band (sum-of-regularisers): hundreds of items per step — `skip` = items between here and
+            // this warp's next one, carried across tile columns so that no division or per-item scan is needed
             int skip = uw;
             for (int tj = 0; tj < ntj; ++tj) {
                 const int first = 2 * tj + 2;
@@ -570,6 +594,7 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws,
                 if (kind == 2) { ti = nti - 1; if (nti == nfull || ti <= 2 * tj + 1) continue; }
                 if (ti >= nti || (ti < 4 && tj < 2)) continue;
                 tile_update<false>(a22, LDa, nrows, P, PR, 4 * ti, 8 * tj, use_stage != 0, stage, nstage, ut);
+            }
             }
         }
         if (CL) cooperative_groups::this_cluster().sync(); else __syncthreads();

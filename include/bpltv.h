@@ -3,9 +3,12 @@
  *
  * This is the drop-in boundary for ONE path of dvillacis/BPLDenoising: the
  * body of `tv_op_learning_function(x, data, Δ)` and of `denoise(data, x, op)`
- * (/root/reference/src/TVLearningFunctionVec.jl:14-27, :45-70).  Julia calls
- * these entry points with `ccall` (julia/BPLTV.jl); the
- * trust-region driver (/root/reference/src/TRBox.jl:192-273) is unchanged.
+ * (/root/reference/src/TVLearningFunctionVec.jl:14-27, :45-70), widened to its
+ * direct callers: the λ-sweeps / validation solves of src/BPLDenoising.jl
+ * (bpltv_sweep) and the sum-of-regularisers learning function of
+ * src/SumRegsLearningFunction.jl (bpltv_sumregs_*).  Julia calls these entry
+ * points with `ccall` (julia/BPLTV.jl); the trust-region
+ * driver (/root/reference/src/TRBox.jl:192-273) is unchanged.
  *
  * Conventions
  *  - plain pointers and sizes only; every host array is caller-owned, is read
