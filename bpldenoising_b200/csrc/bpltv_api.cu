@@ -18,7 +18,7 @@
 #include "common.cuh"
 #include "pdps_generic.cuh"
 #include "pdps_march.cuh"
-#include "pdps_tblock.cuh"
+#include "tblock_kernels.h"
 #include "pdps_resident.cuh"
 #include "pdps_sumregs.cuh"
 #include "gradient.cuh"
@@ -241,45 +241,7 @@ static void launch_generic(const GenericArgs<Real> &a, bool map, bool strict, cu
 }
 
 // ---- temporally blocked march (kernel C): T iterations per launch ---------------------
-template <typename Real, int T>
-using TBlockFn = void (*)(const TBlockArgs<Real, T>);
-
-template <typename Real, int VEC, int T, bool BATCH>
-static TBlockFn<Real, T> tblock_fn_cfg(bool map, bool strict)
-{
-    // register budget: T=2 keeps two 256-thread CTAs per SM, deeper pipelines one.
-    // 16-byte vectors (whole columns are then 16-byte multiples) take the TMA prefetch ring.
-    constexpr int MINB = T <= 2 ? 2 : 1;
-    constexpr bool RING = VEC * sizeof(Real) == 16;
-    if (map) return strict ? pdps_tblock_kernel<Real, VEC, T, true, true, RING, BATCH, 256, MINB>
-                           : pdps_tblock_kernel<Real, VEC, T, true, false, RING, BATCH, 256, MINB>;
-    return strict ? pdps_tblock_kernel<Real, VEC, T, false, true, RING, BATCH, 256, MINB>
-                  : pdps_tblock_kernel<Real, VEC, T, false, false, RING, BATCH, 256, MINB>;
-}
-
-// λ-sweeps (batch = true) are built for the depths AUTO uses (T = 2, 4) only
-template <typename Real, int VEC, int T>
-static TBlockFn<Real, T> tblock_fn_vec(bool map, bool strict, bool batch)
-{
-    if (!batch) return tblock_fn_cfg<Real, VEC, T, false>(map, strict);
-    if constexpr (T == 3) return nullptr;
-    else return tblock_fn_cfg<Real, VEC, T, true>(map, strict);
-}
-
-template <int T> static TBlockFn<double, T> tblock_fn(double, int vec, bool map, bool strict, bool batch)
-{
-    if (vec == 2) return tblock_fn_vec<double, 2, T>(map, strict, batch);
-    if (vec == 1) return tblock_fn_vec<double, 1, T>(map, strict, batch);
-    return nullptr;
-}
-template <int T> static TBlockFn<float, T> tblock_fn(float, int vec, bool map, bool strict, bool batch)
-{
-    if (vec == 4) return tblock_fn_vec<float, 4, T>(map, strict, batch);
-    if (vec == 2) return tblock_fn_vec<float, 2, T>(map, strict, batch);
-    if (vec == 1) return tblock_fn_vec<float, 1, T>(map, strict, batch);
-    return nullptr;
-}
-
+// (the kernels are instantiated in tblock_f{64,32}_t{2,3,4}.cu so that they compile in parallel)
 // vector width of the temporally blocked kernel for column height M (0 = shape not taken):
 // 16-byte accesses when M allows, one column per CTA of at most 256 threads
 template <typename Real>
@@ -307,7 +269,7 @@ static int run_tblock_passes(Dev &d, const Real *f, int M, int N, int O, Real al
     const int vec = tblock_vec<Real>(M);
     const int nthreads = (M / vec + 31) / 32 * 32;
     const bool batch = bm.alpha_vec != nullptr || bm.f_mod != 0 || bm.lam_div != 0;
-    TBlockFn<Real, T> fn = tblock_fn<T>(Real(), vec, alpha_map != nullptr, strict, batch);
+    TBlockFn<Real, T> fn = tblock_kernel<Real, T>(vec, alpha_map != nullptr, strict, batch);
     if (!fn) return -2;
     const size_t smem = (vec * sizeof(Real) == 16) ? tblock_ring_bytes<Real, T>(M) : 0;
     if (smem > d.smem_optin) return -1;
