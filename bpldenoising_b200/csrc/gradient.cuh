@@ -873,7 +873,10 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_solve_kernel(GradSlots ws, 
         if (tid == 0) s_rn = rn2;
         __syncthreads();
         relres = (s_bn > 0.0) ? sqrt(s_rn / s_bn) : 0.0;
-        if (it == gv.refine) break;
+        // refinement is skipped when the factorisation already solved the system to rounding level (the
+        // well-conditioned regularised systems: measured change of the gradient ≤ 1e-14); the
+        // non-regularised systems (compliances down to eps()) need the step (1e-9 → 1e-12)
+        if (it == gv.refine || relres <= 1e-14) break;
         solve(work);
         for (int a = tid; a < Nd; a += blockDim.x) zeta[a] += work[a];
         __syncthreads();
@@ -1081,7 +1084,7 @@ static int run_gradient(GradWork &w, const GradProblem<Real> &gp, int sm_count, 
     gv.lm = gp.lm; gv.ln = gp.ln;
     gv.alpha_s = gp.alpha_s; gv.gamma = gp.gamma; gv.act_tol = gp.act_tol; gv.eps_act = gp.eps_act;
     gv.guard_rel = 1e-13;
-    gv.refine = 1;
+    gv.refine = getenv("BPLTV_GRAD_REFINE") ? atoi(getenv("BPLTV_GRAD_REFINE")) : 1;
     // pivot floor relative to the scale of B C⁻¹ Bᵀ (C⁻¹ = λ for the patch-reg system, 1 otherwise)
     double cscale = 1.0;
     if (gv.regularised && gv.patch) cscale = 1.0;  // refined below from the map's max on the host side if needed

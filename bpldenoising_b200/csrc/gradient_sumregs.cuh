@@ -333,7 +333,10 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad3_solve_kernel(GradSlots ws,
         if (tid == 0) s_rn = rn2;
         __syncthreads();
         relres = (s_bn > 0.0) ? sqrt(s_rn / s_bn) : 0.0;
-        if (it == gv.refine) break;
+        // refinement is skipped when the factorisation already solved the system to rounding level (the
+        // well-conditioned regularised systems: measured change of the gradient ≤ 1e-14); the
+        // non-regularised systems (compliances down to eps()) need the step (1e-9 → 1e-12)
+        if (it == gv.refine || relres <= 1e-14) break;
         solve(work);
         for (int a = tid; a < Nd; a += blockDim.x) zeta[a] += work[a];
         __syncthreads();
