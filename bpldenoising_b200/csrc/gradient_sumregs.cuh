@@ -482,7 +482,7 @@ static int run_gradient3(GradWork &w, const Grad3Problem<Real> &gp, int sm_count
         grad3_classify_kernel<Real><<<cnt, GRAD_THREADS, 0, st>>>(ws, gv, gp.u, gp.ubar, gp.alpha_maps, img0);
         grad3_assemble_kernel<<<cnt, GRAD_THREADS, 0, st>>>(ws);
         {
-            cudaError_t fe = launch_factor(ws, guard, use_stage, 0, cnt, factor_cluster_size(cnt, sm_count, ws.LD), smem, st);
+            cudaError_t fe = launch_factor(ws, guard, use_stage, getenv("BPLTV_GRAD_DBG") ? atoi(getenv("BPLTV_GRAD_DBG")) : 0, cnt, factor_cluster_size(cnt, sm_count, ws.LD), smem, st);
             if (fe != cudaSuccess) { cudaGetLastError(); return grad_fail(w, -2, std::string("factor launch failed: ") + cudaGetErrorString(fe)); }
         }
         grad3_solve_kernel<<<cnt, GRAD_THREADS, zs_bytes, st>>>(ws, gv, (double *)w.out_img, (double *)w.relres, img0, zs_cap);
