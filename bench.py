@@ -436,6 +436,19 @@ def learn_eval_extras(bp):
                 val = bp.validate_tv_parameter(float(res.x), ds["faces_val_128_10"], ctx=c)
                 out[name]["validation"] = {"seconds": time.perf_counter() - t0, "cost": val["cost"],
                                            "mean_psnr": val["mean_psnr"], "mean_ssim": val["mean_ssim"]}
+    # the reference-form gradient on the host cores in the same run: the literal sparse systems of
+    # TVLearningFunctionVec.jl:98-161 through SciPy's SuperLU (oracle/oracle.py), one image, one thread
+    from oracle import oracle as orc
+    t1, f1 = ds["cameraman_128_5"]
+    with bp.Context([0], 64) as c:
+        u1 = c.denoise(f1, 0.1)
+    cpu = {}
+    for name, fn in (("gradient", orc.gradient_scalar), ("gradient_reg", orc.gradient_reg_scalar)):
+        t0 = time.perf_counter()
+        gval = fn(0.1, u1[:, :, 0], t1[:, :, 0])
+        cpu[name] = {"seconds_per_image": time.perf_counter() - t0, "grad": float(gval)}
+    out["cpu_port_gradient_cameraman_128_5"] = cpu
+
     # sum-of-regularisers interface: one sumregs_learning_function evaluation on the
     # reference's cameraman dataset at α₀ = [0.001, 0.001, 0.001], both gradient branches
     data = ds["cameraman_128_5"]

@@ -167,3 +167,26 @@ def test_cluster_factorisation_is_invisible(bp, ctx, sr, datasets):
             assert got[0] == ref[0] and got[1] == ref[1], C
             # the sum-of-regularisers assembly adds with atomics: equal up to summation order
             assert np.allclose(got[2], ref[2], rtol=1e-11, atol=0) and np.allclose(got[3], ref[3], rtol=1e-11, atol=0), C
+
+
+def test_sumregs_single_process_multi_device_context(bp, datasets):
+    """The sum-of-regularisers evaluation shards over the devices of a multi-device context like the TV one
+    (images in contiguous blocks, [cost, grad] summed on the host in device order).  Needs ≥ 2 GPUs."""
+    import ctypes
+    cuda = ctypes.CDLL("libcuda.so.1")
+    n = ctypes.c_int(0)
+    cuda.cuInit(0); cuda.cuDeviceGetCount(ctypes.byref(n))
+    if n.value < 2:
+        pytest.skip("needs 2 GPUs")
+    t, f = _crop(datasets, "faces_train_128_10", 32, k=3, off=24)
+    x = np.array([0.02, 0.03, 0.01])
+    with bp.Context([0], 64) as c1, bp.Context([0, 1], 64) as c2:
+        c1.set_dataset((t, f)); c2.set_dataset((t, f))
+        eo = bp.sumregs_eval_opts(bp.sumregs_pdps_opts(maxiter=200))
+        for Delta in (0.01, 1e-4):
+            u1, cost1, g1 = c1.sumregs_learn_eval(x, Delta, eo)
+            u2, cost2, g2 = c2.sumregs_learn_eval(x, Delta, eo)
+            assert np.array_equal(u1, u2) and abs(cost1 - cost2) <= 1e-13 * cost1
+            assert np.allclose(g1, g2, rtol=1e-11, atol=0)
+        assert c2.stats()["n_devices"] == 2
+        assert np.array_equal(c2.sumregs_denoise(f, x, eo.pdps), u1)
