@@ -382,7 +382,10 @@ def main():
         }
         # ---- extras: learn_eval wall time on the reference-shaped configs (N=1 only) ------
         if world == 1 and not args.no_extras:
-            line["learn_eval"] = learn_eval_extras(bp)
+            try:
+                line["learn_eval"] = learn_eval_extras(bp)
+            except Exception as e:   # the extras must never cost the headline line
+                line["learn_eval"] = {"error": f"{type(e).__name__}: {e}"}
         print(json.dumps(line))
     ctx.close()
     if world > 1:
