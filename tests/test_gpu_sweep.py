@@ -127,3 +127,25 @@ def test_sweep_on_all_devices(bp, oracle, datasets):
         assert np.array_equal(u[:, :, :, l], ref)
         assert abs(costs[l] - oracle.cost(ref, t)) <= 1e-12 * costs[l]
     c2.close()
+
+
+def test_sweep_through_the_streaming_kernels_in_fast_and_fp32_modes(bp, ctx, ctx32, oracle):
+    """The λ-sweep instantiations of the temporally blocked kernel (T = 2 and T = 4, BATCH = true), in fast
+    arithmetic and in fp32; T = 3 is not built for sweeps and says so."""
+    rng = np.random.default_rng(11)
+    t = np.asfortranarray(np.round(rng.uniform(0, 1, (64, 50, 3)) * 255) / 255)
+    f = np.asfortranarray(np.clip(t + 0.1 * rng.standard_normal(t.shape), 0, 1))
+    params = [0.03, 0.08, 0.2]
+    refs = [oracle.pdps(f, p, maxiter=81) for p in params]
+    ctx.set_dataset((t, f)); ctx32.set_dataset((t, f))
+    for depth in (2, 4):
+        for arith, tol in ((bp.STRICT, 0.0), (bp.FAST, 1e-10)):
+            c, u = ctx.sweep(params, bp.pdps_opts(maxiter=81, kernel=bp.KERNEL_TBLOCK, tblock=depth, arith=arith), return_u=True)
+            for l in range(3):
+                assert rel_l2(u[:, :, :, l], refs[l]) <= tol, (depth, arith, l)
+    c32, u32 = ctx32.sweep(params, bp.pdps_opts(maxiter=81, kernel=bp.KERNEL_TBLOCK), return_u=True)
+    for l, p in enumerate(params):
+        assert np.array_equal(u32[:, :, :, l].astype(np.float32), oracle.pdps(f, p, maxiter=81, dtype=np.float32))
+    with pytest.raises(bp.BpltvError) as ei:
+        ctx.sweep(params, bp.pdps_opts(maxiter=9, kernel=bp.KERNEL_TBLOCK, tblock=3))
+    assert "depths 2 and 4" in str(ei.value)
