@@ -955,6 +955,19 @@ static inline cudaError_t launch_factor(const GradSlots &ws, double guard, int u
     }
     cudaError_t e = cudaFuncSetAttribute(grad_factor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    {   // a cluster of C CTAs with this much shared memory must be co-schedulable; otherwise halve it
+        cudaLaunchConfig_t q = {};
+        q.gridDim = dim3((unsigned)C); q.blockDim = dim3(GRAD_THREADS); q.dynamicSmemBytes = smem;
+        cudaLaunchAttribute qa[1];
+        qa[0].id = cudaLaunchAttributeClusterDimension;
+        qa[0].val.clusterDim.x = (unsigned)C; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+        q.attrs = qa; q.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, grad_factor_kernel<true>, &q) != cudaSuccess || nclusters < 1) {
+            cudaGetLastError();
+            return launch_factor(ws, guard, use_stage, dbg, cnt, C / 2, smem, st);
+        }
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(cnt * C));
     cfg.blockDim = dim3(GRAD_THREADS);
