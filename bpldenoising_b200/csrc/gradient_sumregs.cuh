@@ -12,8 +12,9 @@
 // operator-minor, which makes the matrix banded with half-bandwidth ≤ the modes of 2n+1 pixels.  The
 // band is factorised by gradient.cuh's blocked Cholesky (grad_factor_kernel) and solved by its
 // band_solve; this file adds the three-operator classification, the assembly and the functional.
-// The assembly accumulates node contributions with atomicAdd (summation order, hence the last bits
-// of the result, may vary from run to run; the TV path is deterministic).
+// The assembly accumulates the off-diagonal node contributions with atomicAdd; every such entry has at
+// most two contributions (addition of two numbers is commutative), the diagonal and the right-hand side
+// are summed in a fixed order, so the result is deterministic like the TV path.
 //
 // Not built: the patch variant of sumregs_gradient_reg (:195-262) — its system is row-scaled by a
 // different λ-map per operator, cannot be symmetrised, and so has no SPD compliance form.
@@ -68,6 +69,28 @@ static __device__ __forceinline__ void visit_node(int i, int j, int n, F &&fn)
     if (i + 1 <= n - 2) fn(v + 1, 2, -0.5, 0.0);      // pixel row i+1 ≥ 1 always
     if (j - 1 >= 1) fn(v - n, 2, 0.0, 0.5);
     if (j + 1 <= n - 2) fn(v + n, 2, 0.0, -0.5);
+}
+
+// The nodes of the stencil of (pixel (i,j), operator k), with the coefficients of components 1 and 2:
+// fn(node, c1, c2), in a fixed order.
+template <typename F>
+static __device__ __forceinline__ void visit_stencil(int k, int i, int j, int n, F &&fn)
+{
+    const int q = j * n + i;
+    if (k == 0) {
+        const double c1 = (i + 1 < n) ? -1.0 : 0.0, c2 = (j + 1 < n) ? -1.0 : 0.0;
+        if (c1 != 0.0 || c2 != 0.0) fn(q, c1, c2);
+        if (i + 1 < n) fn(q + 1, 1.0, 0.0);
+        if (j + 1 < n) fn(q + n, 0.0, 1.0);
+    } else if (k == 1) {
+        const double c1 = (i >= 1) ? 1.0 : 0.0, c2 = (j >= 1) ? 1.0 : 0.0;
+        if (c1 != 0.0 || c2 != 0.0) fn(q, c1, c2);
+        if (i >= 1) fn(q - 1, -1.0, 0.0);
+        if (j >= 1) fn(q - n, 0.0, -1.0);
+    } else {
+        if (i >= 1 && i <= n - 2) { fn(q - 1, -0.5, 0.0); fn(q + 1, 0.5, 0.0); }
+        if (j >= 1 && j <= n - 2) { fn(q - n, 0.0, -0.5); fn(q + n, 0.0, 0.5); }
+    }
 }
 
 // per-slot layout of GradSlots::pix for this path (N = n² doubles each):
@@ -207,14 +230,26 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad3_assemble_kernel(GradSlots 
         const double2 z2 = make_double2(0.0, 0.0);
         for (size_t k = threadIdx.x; k < n2; k += blockDim.x) ab2[k] = z2;
         if (threadIdx.x == 0 && (total & 1)) ab[total - 1] = 0.0;
-        for (int a = threadIdx.x; a < Nd; a += blockDim.x) bvec[a] = 0.0;
     }
     __syncthreads();
-    // diagonal compliances
+    // diagonal E + Σ β² and right-hand side Σ β r of every mode, over the nodes of its own stencil in a
+    // fixed order (these sums have up to four terms; the off-diagonal entries below have at most two —
+    // two different stencils share at most two nodes — so their atomic accumulation is order-independent
+    // and the whole assembly is deterministic)
     for (int e = threadIdx.x; e < 3 * N; e += blockDim.x) {
-        const int q = e / 3, k = e - 3 * q;
+        const int q = e / 3, k = e - 3 * q, i = q % n, j = q / n;
         const double E = g3_plane(pix, N, 5 * k + 2)[q];
-        for (int a = off[e]; a < off[e + 1]; ++a) ab[(size_t)a * LDa] = E;
+        const int a0 = off[e], nm = off[e + 1] - a0;
+        for (int m = 0; m < nm; ++m) {
+            double d = E, bsum = 0.0;
+            visit_stencil(k, i, j, n, [&](int node, double c1, double c2) {
+                const double b = g3_beta(pix, N, q, k, m, nm == 2, c1, c2);
+                d += b * b;
+                bsum += b * rc[node];
+            });
+            ab[(size_t)(a0 + m) * LDa] = d;
+            bvec[a0 + m] = bsum;
+        }
     }
     __syncthreads();
     // node contributions β_a β_a' (C = I)
@@ -231,14 +266,11 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad3_assemble_kernel(GradSlots 
                 if (b != 0.0) { ma[cnt] = a0 + m; mb[cnt] = b; ++cnt; }
             }
         });
-        const double r = rc[v];
-        for (int x = 0; x < cnt; ++x) {
-            atomicAdd(&bvec[ma[x]], mb[x] * r);
-            for (int y = x; y < cnt; ++y) {
+        for (int x = 0; x < cnt; ++x)
+            for (int y = x + 1; y < cnt; ++y) {
                 const int lo = min(ma[x], ma[y]), hi = max(ma[x], ma[y]);
                 atomicAdd(&ab[(size_t)lo * LDa + (hi - lo)], mb[x] * mb[y]);
             }
-        }
     }
 }
 

@@ -165,8 +165,8 @@ def test_cluster_factorisation_is_invisible(bp, ctx, sr, datasets):
             ref = got
         else:
             assert got[0] == ref[0] and got[1] == ref[1], C
-            # the sum-of-regularisers assembly adds with atomics: equal up to summation order
-            assert np.allclose(got[2], ref[2], rtol=1e-11, atol=0) and np.allclose(got[3], ref[3], rtol=1e-11, atol=0), C
+            # the sum-of-regularisers assembly is deterministic too (its atomics add at most two terms per entry)
+            assert np.array_equal(got[2], ref[2]) and np.array_equal(got[3], ref[3]), C
 
 
 def test_sumregs_single_process_multi_device_context(bp, datasets):
@@ -187,6 +187,6 @@ def test_sumregs_single_process_multi_device_context(bp, datasets):
             u1, cost1, g1 = c1.sumregs_learn_eval(x, Delta, eo)
             u2, cost2, g2 = c2.sumregs_learn_eval(x, Delta, eo)
             assert np.array_equal(u1, u2) and abs(cost1 - cost2) <= 1e-13 * cost1
-            assert np.allclose(g1, g2, rtol=1e-11, atol=0)
+            assert np.allclose(g1, g2, rtol=1e-12, atol=0)   # host sum over devices vs one in-order device sum
         assert c2.stats()["n_devices"] == 2
         assert np.array_equal(c2.sumregs_denoise(f, x, eo.pdps), u1)
