@@ -81,3 +81,30 @@ def test_learn_run_end_to_end_on_gpu(bp, ctx, datasets):
     assert 0 < res.x < 0.1
     resp = trbox.patch_bilevel_tv_learn(datasets["circle_128_10"], ctx=ctx, maxiter=4)
     assert resp.x.shape == (2, 2) and resp.evaluations == 5
+
+
+@pytest.mark.gpu
+def test_run_experiment_cli_reproduces_the_artefacts(tmp_path, datasets):
+    """tools/run_experiment.py: dataset directory in the reference's format → learn run → log, quality
+    table and PNGs under <output>/<dataset_name>/ (BPLDenoising.jl:325-344, :185-217)."""
+    import os
+    import subprocess
+    import sys
+    from PIL import Image
+    from conftest import ROOT
+    t, d = datasets["cameraman_128_5"]
+    root = tmp_path / "BPLDenoising" / "datasets" / "cameraman_128_5"
+    root.mkdir(parents=True)
+    Image.fromarray(np.round(t[:, :, 0] * 255).astype(np.uint8)).save(root / "cameraman_128_5_true_1.png")
+    Image.fromarray(np.round(d[:, :, 0] * 255).astype(np.uint8)).save(root / "cameraman_128_5_data_1.png")
+    (root / "filelist.txt").write_text("cameraman_128_5_true_1.png,cameraman_128_5_data_1.png\n")
+    out = tmp_path / "output"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "run_experiment.py"), "scalar_bilevel_tv_learn",
+                        "--dataset_name", "cameraman", "--datasets_dir", str(tmp_path / "BPLDenoising" / "datasets"),
+                        "--maxiter", "4", "--output", str(out)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    files = sorted(os.listdir(out / "cameraman_128_5"))
+    stem = "tv_optimal_parameter_scalar_cameraman_128_5"
+    assert f"{stem}.txt" in files and f"{stem}_quality.txt" in files and f"{stem}_reco_1.png" in files
+    q = open(out / "cameraman_128_5" / f"{stem}_quality.txt").read().splitlines()
+    assert len(q) == 3 and float(q[1].split()[4]) > float(q[1].split()[2])    # out_psnr > orig_psnr
