@@ -410,7 +410,10 @@ static __device__ __forceinline__ void tile_update(double *a22, int LDa, int nro
 // cluster barrier per block step publishes them (global memory, release/acquire at cluster scope).
 // Only rank 0 writes L11 and the panel back to the band; the panel write-back is deferred by one step
 // because the other CTAs are still reading those entries while they form their own copy.
-template <bool CL>
+// PLA: the look-ahead (update + factorisation of the next diagonal block) is done by warps 0-3 together
+// (one entry pair per thread, column exchange through shared memory, one named barrier per pivot)
+// instead of by warp 0 alone with shuffles; same operations per entry, hence the same bits.
+template <bool CL, bool PLA>
 __global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws, double guard, int use_stage, int dbg)
 {
     extern __shared__ __align__(16) double sm[];
@@ -518,7 +521,57 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws,
         __syncthreads();
         if (CL) { wb_kb = kb; wb_nb = nb; wb_rows = max(nrows, 0); }
         if (nrows <= 0) break;
+        if (PLA && warp < 4) {
+            // ---- (3') look-ahead shared by warps 0-3 -----------------------------------------
+            const int nb2 = min(NB, nrows);
+            double e[2];
+            int er[2], ec[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int idx = tid + 128 * h, r = idx / NB, c = idx % NB;
+                er[h] = r; ec[h] = c;
+                double v = (r == c) ? 1.0 : 0.0;
+                if (r < nb2 && c <= r) {
+                    double s0 = Araw[idx], s1 = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NB; k += 2) {
+                        s0 = fma(-P[k * PR + r], P[k * PR + c], s0);
+                        s1 = fma(-P[(k + 1) * PR + r], P[(k + 1) * PR + c], s1);
+                    }
+                    v = s0 + s1;
+                }
+                e[h] = (c <= r) ? v : 0.0;
+            }
+            if (!(dbg & 2)) {
+#pragma unroll 1
+                for (int c = 0; c < NB; ++c) {
+                    // the owners of column c publish its current entries (final after update c-1)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        if (ec[h] == c && er[h] >= c) Sn[er[h] * NB + c] = e[h];
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    double d = Sn[c * NB + c];
+                    if (!(d > guard)) { d = guard; if (tid == 0 && c < nb2) ++guarded; }
+                    const double inv = rsqrt(d);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int r = er[h], c2 = ec[h];
+                        if (c2 == c) {
+                            if (r == c) { e[h] = d * inv; dinvn[c] = inv; }
+                            else if (r > c) e[h] = e[h] * inv;
+                        } else if (c2 > c && r >= c2) {
+                            const double lr = Sn[r * NB + c] * inv, lc2 = Sn[c2 * NB + c] * inv;
+                            e[h] = fma(-lr, lc2, e[h]);
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");   // all column reads done before L overwrites them
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) Sn[tid + 128 * h] = (ec[h] <= er[h]) ? e[h] : 0.0;
+        }
         if (warp == 0) {
+            if (!PLA) {
             // ---- (3) look-ahead: next diagonal block = A22[0:NB,0:NB] - P Pᵀ, factor ----------
             const int nb2 = min(NB, nrows);
             for (int idx = lane; idx < NB * NB; idx += 32) {
@@ -537,6 +590,7 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws,
             }
             __syncwarp();
             if (!(dbg & 2)) diag_factor_warp(Sn, dinvn, nb2, guard, lane, guarded);
+            }
         } else if (!(dbg & 1)) {
             // ---- (2) trailing update on 4(i)×8(j) tiles, skipping the look-ahead block -------
             // Work items are dealt round-robin to the 15 update warps so that every warp runs
@@ -545,7 +599,8 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws,
             // cross the diagonal (rows 2tj, 2tj+1) or hang over the last row are gathered into
             // separate boundary rounds, so no warp executes both paths for one item.
             const int nti = (nrows + 3) >> 2, ntj = (nrows + 7) >> 3, nfull = nrows >> 2;
-            const int uw = (warp - 1) + (nwarps - 1) * crank, nuw = (nwarps - 1) * csize;   // update warps of the cluster
+            // update warps of the cluster; with PLA warps 1-3 join late, so they take the last item slots
+            const int uw = (PLA ? (warp + nwarps - 5) % (nwarps - 1) : warp - 1) + (nwarps - 1) * crank, nuw = (nwarps - 1) * csize;
             const int ut = tid - 32;               // index among the update threads
             // item k of the step belongs to update warp k mod nuw.
             if (nrows < 640) {
@@ -948,12 +1003,22 @@ static inline cudaError_t launch_factor(const GradSlots &ws, double guard, int u
                                         size_t smem, cudaStream_t st)
 {
     if (C <= 1) {
-        cudaError_t e = cudaFuncSetAttribute(grad_factor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // shared look-ahead: A/B on B200 — no gain at 128x128 (23.8 vs 24.1 ms), 4-9 % at 256x256
+        // (165 -> 155 ms, 174 -> 158 ms for 32 images); bit-identical results either way
+        const char *pla_env = getenv("BPLTV_GRAD_PLA");
+        const bool pla = pla_env && *pla_env ? atoi(pla_env) != 0 : ws.LD >= 400;
+        if (pla) {
+            cudaError_t e = cudaFuncSetAttribute(grad_factor_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            grad_factor_kernel<false, true><<<cnt, GRAD_THREADS, smem, st>>>(ws, guard, use_stage, dbg);
+            return cudaGetLastError();
+        }
+        cudaError_t e = cudaFuncSetAttribute(grad_factor_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        grad_factor_kernel<false><<<cnt, GRAD_THREADS, smem, st>>>(ws, guard, use_stage, dbg);
+        grad_factor_kernel<false, false><<<cnt, GRAD_THREADS, smem, st>>>(ws, guard, use_stage, dbg);
         return cudaGetLastError();
     }
-    cudaError_t e = cudaFuncSetAttribute(grad_factor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(grad_factor_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     {   // a cluster of C CTAs with this much shared memory must be co-schedulable; otherwise halve it
         cudaLaunchConfig_t q = {};
@@ -963,7 +1028,7 @@ static inline cudaError_t launch_factor(const GradSlots &ws, double guard, int u
         qa[0].val.clusterDim.x = (unsigned)C; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
         q.attrs = qa; q.numAttrs = 1;
         int nclusters = 0;
-        if (cudaOccupancyMaxActiveClusters(&nclusters, grad_factor_kernel<true>, &q) != cudaSuccess || nclusters < 1) {
+        if (cudaOccupancyMaxActiveClusters(&nclusters, grad_factor_kernel<true, false>, &q) != cudaSuccess || nclusters < 1) {
             cudaGetLastError();
             return launch_factor(ws, guard, use_stage, dbg, cnt, C / 2, smem, st);
         }
@@ -980,7 +1045,7 @@ static inline cudaError_t launch_factor(const GradSlots &ws, double guard, int u
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, grad_factor_kernel<true>, ws, guard, use_stage, dbg);
+    return cudaLaunchKernelEx(&cfg, grad_factor_kernel<true, false>, ws, guard, use_stage, dbg);
 }
 
 // CTAs per image for the factorisation: as many as leave every image of the wave its own cluster.
