@@ -20,6 +20,9 @@
 #pragma once
 #include <cooperative_groups.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace bpltv {
@@ -203,14 +206,15 @@ struct ResidentPlan {
 };
 
 template <typename Real>
-static inline ResidentPlan resident_plan(size_t smem_optin, int M, int N)
+static inline ResidentPlan resident_plan(size_t smem_optin, int M, int N, int cs_max = 8)
 {
     ResidentPlan p;
     if (M < 2 || (M & 1) || (M / 2) > RES_THREADS || RES_THREADS % (M / 2) != 0) return p;
     const int CG = RES_THREADS / (M / 2);
-    const int cs_cands[4] = {8, 4, 2, 1};
-    for (int ci = 0; ci < 4; ++ci) {
+    const int cs_cands[5] = {16, 8, 4, 2, 1};   // 16 = non-portable cluster size (launch_resident decides)
+    for (int ci = 0; ci < 5; ++ci) {
         const int CS = cs_cands[ci];
+        if (CS > cs_max) continue;
         if (CS > N) continue;
         const int NC = (N + CS - 1) / CS;
         if ((CS - 1) * NC >= N) continue;              // every rank must own at least one column
@@ -239,6 +243,10 @@ static inline cudaError_t launch_resident_kc(const ResidentArgs<Real> &a, const 
     else fn = strict ? pdps_resident_kernel<Real, KC, false, true> : pdps_resident_kernel<Real, KC, false, false>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return e;
+    if (p.CS > 8) {
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(a.O * p.CS));
     cfg.blockDim = dim3(RES_THREADS);
@@ -251,13 +259,37 @@ static inline cudaError_t launch_resident_kc(const ResidentArgs<Real> &a, const 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (p.CS > 8) {   // all clusters of the batch must be co-resident (≈ one 16-CTA cluster per GPC)
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg) != cudaSuccess || nclusters < a.O) {
+            cudaGetLastError();
+            return cudaErrorLaunchOutOfResources;
+        }
+    }
     return cudaLaunchKernelEx(&cfg, fn, a);
 }
 
 template <typename Real>
 static inline cudaError_t launch_resident(ResidentArgs<Real> a, size_t smem_optin, bool map, bool strict, cudaStream_t st)
 {
-    const ResidentPlan p = resident_plan<Real>(smem_optin, a.M, a.N);
+    // Few images: 16-CTA clusters (non-portable size) halve the columns per CTA — 5000 iterations of one
+    // 128×128 image in 8.0 ms instead of 11.9 ms; they fit about one per GPC, so larger batches (10 images:
+    // 16.0 vs 11.9 ms) keep the 8-CTA plan.  BPLTV_RESIDENT_CS caps the cluster size.
+    const char *cs_env = getenv("BPLTV_RESIDENT_CS");
+    const int cs_cap = cs_env && *cs_env ? atoi(cs_env) : 16;
+    if (cs_cap >= 16) {
+        const ResidentPlan p16 = resident_plan<Real>(smem_optin, a.M, a.N, 16);
+        if (p16.ok && p16.CS == 16) {
+            ResidentArgs<Real> a16 = a;
+            a16.NC = p16.NC;
+            cudaError_t e16 = p16.KC == 1 ? launch_resident_kc<Real, 1>(a16, p16, map, strict, st)
+                              : p16.KC == 2 ? launch_resident_kc<Real, 2>(a16, p16, map, strict, st)
+                                            : launch_resident_kc<Real, 4>(a16, p16, map, strict, st);
+            if (e16 == cudaSuccess) return e16;
+            cudaGetLastError();   // not co-resident (or refused): the portable plan below
+        }
+    }
+    const ResidentPlan p = resident_plan<Real>(smem_optin, a.M, a.N, std::min(cs_cap, 8));
     if (!p.ok) return cudaErrorInvalidValue;
     a.NC = p.NC;
     if (p.KC == 1) return launch_resident_kc<Real, 1>(a, p, map, strict, st);
