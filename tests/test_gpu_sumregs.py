@@ -154,7 +154,7 @@ def test_cluster_factorisation_is_invisible(bp, ctx, sr, datasets):
     u3 = sr.sumregs_pdps(f, list(x3), maxiter=200)
     utv = ctx.denoise(f, 0.07, bp.pdps_opts(maxiter=300))
     ref = {}
-    for C in ("1", "2", "4", "8"):
+    for C in ("1", "2", "4", "8", "16"):
         os.environ["BPLTV_GRAD_CLUSTER"] = C
         try:
             got = (ctx.gradient(0.07, utv, False), ctx.gradient(0.07, utv, True),
