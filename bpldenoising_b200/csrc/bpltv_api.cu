@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1350,6 +1351,8 @@ int bpltv_denoise_device(bpltv_ctx *ctx, const void *d_noisy, int M, int N, int 
 {
     RC_TRY(single_dev(ctx));
     if (!d_noisy || !d_u_out) return fail(BPLTV_ERR_ARG, "NULL device pointer");
+    if (((uintptr_t)d_noisy | (uintptr_t)d_u_out) & 15)
+        return fail(BPLTV_ERR_ARG, "device pointers must be 16-byte aligned (vector and TMA accesses)");
     RC_TRY(check_shape(M, N, O));
     RC_TRY(check_lambda(lam, lm, ln));
     bpltv_pdps_opts o;
@@ -1365,6 +1368,8 @@ int bpltv_set_dataset_device(bpltv_ctx *ctx, const void *d_truth, const void *d_
 {
     RC_TRY(single_dev(ctx));
     if (!d_truth || !d_noisy) return fail(BPLTV_ERR_ARG, "NULL device pointer");
+    if (((uintptr_t)d_truth | (uintptr_t)d_noisy) & 15)
+        return fail(BPLTV_ERR_ARG, "device pointers must be 16-byte aligned (vector and TMA accesses)");
     RC_TRY(check_shape(M, N, O));
     Dev &d = ctx->devs[0];
     CU_TRY(cudaSetDevice(d.id));
