@@ -24,7 +24,23 @@ def _load(path_u):
     return u, float(meta[3]), meta[5:5 + ng]
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(JDIR, "*.u.f64"))))
+SUMREGS = {"sumregs_nonreg": 0.01, "sumregs_reg": 1e-4}
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(JDIR, "*_sumregs_*.u.f64"))))
+def test_sumregs_oracle_against_julia(datasets, path):
+    """Checks assumptions S10-S13 (backward / centred operators, R_K = √18) against the real thing."""
+    from oracle import sumregs as sr
+    base = os.path.basename(path)[:-6]
+    name, tag = base.rsplit("_sumregs_", 1)[0], "sumregs_" + base.rsplit("_sumregs_", 1)[1]
+    u, cost, grad = _load(path)
+    ou, ocost, ograd = sr.sumregs_learning_function(np.array([0.001] * 3), datasets[name], SUMREGS[tag], refine=3)
+    assert rel_l2(ou, u) <= 1e-10
+    assert abs(ocost - cost) <= 1e-10 * abs(cost)
+    assert rel_l2(np.ravel(ograd), grad) <= (1e-9 if tag.endswith("_reg") else 1e-4)
+
+
+@pytest.mark.parametrize("path", sorted(p for p in glob.glob(os.path.join(JDIR, "*.u.f64")) if "_sumregs_" not in p))
 def test_oracle_against_julia(oracle, datasets, path):
     name, tag = os.path.basename(path)[:-6].rsplit("_", 2)[0], "_".join(os.path.basename(path)[:-6].rsplit("_", 2)[1:])
     x, Delta = CASES[tag]
