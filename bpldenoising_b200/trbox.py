@@ -39,6 +39,9 @@ BILEVEL_PARAMS = dict(eta1=0.25, eta2=0.75, beta1=0.25, beta2=1.9, Delta0=0.1, a
 # /root/reference/src/BPLDenoising.jl:423-430 (scalar sum-of-regularisers experiment)
 SUMREGS_BILEVEL_PARAMS = dict(eta1=0.25, eta2=0.75, beta1=0.25, beta2=1.9, Delta0=0.01,
                               alpha0=np.array([0.001, 0.001, 0.001]))
+# /root/reference/src/BPLDenoising.jl:455-462 (patch sum-of-regularisers experiment)
+PATCH_SUMREGS_BILEVEL_PARAMS = dict(eta1=0.25, eta2=0.75, beta1=0.25, beta2=1.5, Delta0=0.1,
+                                    alpha0=0.001 * np.ones((2, 2, 3)))
 PATCH_BILEVEL_PARAMS = dict(eta1=0.25, eta2=0.75, beta1=0.25, beta2=1.9, Delta0=1e-4,
                             alpha0=1e-4 * np.ones((2, 2)))
 
@@ -235,3 +238,28 @@ def scalar_bilevel_sumregs_learn(data, ctx=None, **kwargs) -> LearnResult:
     prm = dict(SUMREGS_BILEVEL_PARAMS); prm.update(kwargs)
     return bilevel_learn(data, lambda x, ds, D: sumregs_learning_function(x, ds, D, ctx=ctx),
                          prm.pop("alpha0"), prm)
+
+
+class RegularisedPatchBranch(RuntimeError):
+    """The trust region shrank below Δt = 1e-3, where the reference switches to the patch variant of
+    sumregs_gradient_reg (SumRegsLearningFunction.jl:195-262) — the one system libbpltv does not build
+    (row-scaled by a different λ-map per operator: no symmetric form, docs/SEMANTICS.md)."""
+
+
+def patch_bilevel_sumregs_learn(data, ctx=None, **kwargs) -> LearnResult:
+    """patch_bilevel_sumregs_learn (BPLDenoising.jl:464-481) without IO/visualisation, for as long as the
+    run stays in the non-regularised branch (Δ > Δt); raises RegularisedPatchBranch otherwise."""
+    from . import _lib
+    from .learning import sumregs_learning_function
+
+    prm = dict(PATCH_SUMREGS_BILEVEL_PARAMS); prm.update(kwargs)
+
+    def lf(x, ds, D):
+        try:
+            return sumregs_learning_function(x, ds, D, ctx=ctx)
+        except _lib.BpltvError as e:
+            if "row-scaled" in str(e):
+                raise RegularisedPatchBranch(f"Δ = {D:g} ≤ Δt: {e}") from e
+            raise
+
+    return bilevel_learn(data, lf, prm.pop("alpha0"), prm)

@@ -190,3 +190,14 @@ def test_sumregs_single_process_multi_device_context(bp, datasets):
             assert np.allclose(g1, g2, rtol=1e-12, atol=0)   # host sum over devices vs one in-order device sum
         assert c2.stats()["n_devices"] == 2
         assert np.array_equal(c2.sumregs_denoise(f, x, eo.pdps), u1)
+
+
+def test_patch_bilevel_sumregs_learn_runs_in_the_non_regularised_branch(bp, ctx, datasets):
+    """patch_bilevel_sumregs_learn (BPLDenoising.jl:464-481): m×n×3 parameter through the L-BFGS path of the
+    driver; the regularised patch branch (Δ ≤ 1e-3) is the one system that is not built and says so."""
+    from bpldenoising_b200 import trbox
+    t, f = _crop(datasets, "circle_128_10", 32, off=48)
+    res = trbox.patch_bilevel_sumregs_learn((t, f), ctx=ctx, maxiter=3)
+    assert np.shape(res.x) == (2, 2, 3) and np.all(np.asarray(res.x) > 0) and res.evaluations == 4
+    with pytest.raises(trbox.RegularisedPatchBranch):
+        trbox.patch_bilevel_sumregs_learn((t, f), ctx=ctx, maxiter=2, Delta0=5e-4)
