@@ -22,6 +22,7 @@
 #pragma once
 #include <cooperative_groups.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <string>
 
@@ -464,8 +465,19 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws,
             }                                                                                            \
         wb_kb = -1;                                                                                      \
     }
+#ifdef BPLTV_FACTOR_TIMING
+    // cycle attribution per phase (developer build only: tools/factor_timing.sh); lane 0 of warps 0, 1, 15
+    long long tm_panel = 0, tm_syncA = 0, tm_work = 0, tm_syncB = 0, tm_t0 = 0, tm_items = 0;
+    auto tm_clock = []() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory"); return t; };
+#define TM_NOW() tm_clock()
+#else
+#define TM_NOW() 0LL
+#endif
     for (int kb = 0, blk = 0; kb < Nd; kb += NB, ++blk) {
         const int cur = blk & 1;
+#ifdef BPLTV_FACTOR_TIMING
+        tm_t0 = TM_NOW();
+#endif
         BPLTV_FACTOR_WRITE_BACK()
         double *S = Sbuf + cur * NB * NB, *dinv = Dbuf + cur * NB;
         double *Sn = Sbuf + (cur ^ 1) * NB * NB, *dinvn = Dbuf + (cur ^ 1) * NB;
@@ -518,7 +530,13 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws,
             for (int c = 0; c < NB; ++c) P[c * PR + r] = x[c];
         }
         if (warp == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+#ifdef BPLTV_FACTOR_TIMING
+        { const long long t = TM_NOW(); tm_panel += t - tm_t0; tm_t0 = t; }
+#endif
         __syncthreads();
+#ifdef BPLTV_FACTOR_TIMING
+        { const long long t = TM_NOW(); tm_syncA += t - tm_t0; tm_t0 = t; }
+#endif
         if (CL) { wb_kb = kb; wb_nb = nb; wb_rows = max(nrows, 0); }
         if (nrows <= 0) break;
         if (PLA && warp < 4) {
@@ -605,10 +623,15 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws,
             // item k of the step belongs to update warp k mod nuw.
             if (nrows < 640) {
                 // narrow band (TV up to 256x256): the plain scan is the faster code (A/B on B200: 0.84 vs 0.90 s at config 5)
+                // PLA: warps 1-3 arrive late from the shared look-ahead (≈ 1.3 items' worth of cycles, measured
+                // with tools/factor_timing.py), so they take one item per round of 27 and warps 4-15 two
+                const int slot_a = PLA ? (warp >= 4 ? warp - 4 : 23 + warp) : uw;
+                const int slot_b = PLA ? (warp >= 4 ? warp + 8 : -1) : -1;
+                const int nslot = PLA ? 27 : nuw;
                 int item = 0;
                 for (int tj = 0; tj < ntj; ++tj) {
                     for (int tbase = 2 * tj + 2; tbase < nfull; tbase += 32, ++item) {
-                        if (item % nuw != uw) continue;
+                        { const int sl = item % nslot; if (sl != slot_a && sl != slot_b) continue; }
                         const int ti = tbase + lane;
                         if (ti < nfull && !(ti < 4 && tj < 2))   // (ti<4,tj<2): next diagonal block (warp 0)
                             tile_update<true>(a22, LDa, nrows, P, PR, 4 * ti, 8 * tj, use_stage != 0, stage, nstage, ut);
@@ -616,7 +639,7 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws,
                 }
                 const int nbound = 3 * ntj;        // (tj, kind): kind 0,1 → rows 2tj, 2tj+1; kind 2 → partial last row
                 for (int bbase = 0; bbase < nbound; bbase += 32, ++item) {
-                    if (item % nuw != uw) continue;
+                    { const int sl = item % nslot; if (sl != slot_a && sl != slot_b) continue; }
                     const int b = bbase + lane;
                     if (b >= nbound) continue;
                     const int tj = b / 3, kind = b - 3 * tj;
@@ -652,8 +675,19 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws,
             }
             }
         }
+#ifdef BPLTV_FACTOR_TIMING
+        { const long long t = TM_NOW(); tm_work += t - tm_t0; tm_t0 = t; }
+#endif
         if (CL) cooperative_groups::this_cluster().sync(); else __syncthreads();
+#ifdef BPLTV_FACTOR_TIMING
+        { const long long t = TM_NOW(); tm_syncB += t - tm_t0; tm_t0 = t; tm_items += 1; }
+#endif
     }
+#ifdef BPLTV_FACTOR_TIMING
+    if (lane == 0 && (warp == 0 || warp == 1 || warp == 4 || warp == 15) && blockIdx.x == 0)
+        printf("factor timing warp %2d: steps %lld  cycles/step: panel %.0f  syncA %.0f  work %.0f  syncB %.0f\n", warp, tm_items,
+               (double)tm_panel / tm_items, (double)tm_syncA / tm_items, (double)tm_work / tm_items, (double)tm_syncB / tm_items);
+#endif
     BPLTV_FACTOR_WRITE_BACK()
 #undef BPLTV_FACTOR_WRITE_BACK
     if (tid == 0 && crank == 0) info[2] = guarded;
@@ -1003,10 +1037,11 @@ static inline cudaError_t launch_factor(const GradSlots &ws, double guard, int u
                                         size_t smem, cudaStream_t st)
 {
     if (C <= 1) {
-        // shared look-ahead: A/B on B200 — no gain at 128x128 (23.8 vs 24.1 ms), 4-9 % at 256x256
-        // (165 -> 155 ms, 174 -> 158 ms for 32 images); bit-identical results either way
+        // shared look-ahead with the weighted tile distribution: A/B on B200 — 23.8 -> 22.1 ms (cameraman),
+        // 27.7 -> 25.3 ms (10 faces), 20.6 -> 18.5 ms (circle, patch), 165 -> 140 ms (32 images of 256x256);
+        // bit-identical results either way
         const char *pla_env = getenv("BPLTV_GRAD_PLA");
-        const bool pla = pla_env && *pla_env ? atoi(pla_env) != 0 : ws.LD >= 400;
+        const bool pla = pla_env && *pla_env ? atoi(pla_env) != 0 : true;
         if (pla) {
             cudaError_t e = cudaFuncSetAttribute(grad_factor_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
