@@ -625,9 +625,9 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws,
                 // narrow band (TV up to 256x256): the plain scan is the faster code (A/B on B200: 0.84 vs 0.90 s at config 5)
                 // PLA: warps 1-3 arrive late from the shared look-ahead (≈ 1.3 items' worth of cycles, measured
                 // with tools/factor_timing.py), so they take one item per round of 27 and warps 4-15 two
-                const int slot_a = PLA ? (warp >= 4 ? warp - 4 : 23 + warp) : uw;
-                const int slot_b = PLA ? (warp >= 4 ? warp + 8 : -1) : -1;
-                const int nslot = PLA ? 27 : nuw;
+                const int slot_a = PLA ? 27 * crank + (warp >= 4 ? warp - 4 : 23 + warp) : uw;
+                const int slot_b = PLA ? (warp >= 4 ? 27 * crank + warp + 8 : -1) : -1;
+                const int nslot = PLA ? 27 * csize : nuw;
                 int item = 0;
                 for (int tj = 0; tj < ntj; ++tj) {
                     for (int tbase = 2 * tj + 2; tbase < nfull; tbase += 32, ++item) {
