@@ -539,14 +539,16 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws,
 #endif
         if (CL) { wb_kb = kb; wb_nb = nb; wb_rows = max(nrows, 0); }
         if (nrows <= 0) break;
-        if (PLA && warp < 4) {
-            // ---- (3') look-ahead shared by warps 0-3 -----------------------------------------
+        if (PLA && (warp & 3) == 0) {
+            // ---- (3') look-ahead shared by warps 0, 4, 8, 12: the four warps of ONE scheduler, so that the
+            // pivot chain does not compete for issue slots with the tile warps of the other three ---------
             const int nb2 = min(NB, nrows);
+            const int lt = (warp >> 2) * 32 + lane;      // 0..127 within the look-ahead group
             double e[2];
             int er[2], ec[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int idx = tid + 128 * h, r = idx / NB, c = idx % NB;
+                const int idx = lt + 128 * h, r = idx / NB, c = idx % NB;
                 er[h] = r; ec[h] = c;
                 double v = (r == c) ? 1.0 : 0.0;
                 if (r < nb2 && c <= r) {
@@ -569,7 +571,7 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws,
                         if (ec[h] == c && er[h] >= c) Sn[er[h] * NB + c] = e[h];
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                     double d = Sn[c * NB + c];
-                    if (!(d > guard)) { d = guard; if (tid == 0 && c < nb2) ++guarded; }
+                    if (!(d > guard)) { d = guard; if (tid == 0 && c < nb2) ++guarded; }   // tid 0 is in the group
                     const double inv = rsqrt(d);
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
@@ -586,7 +588,7 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws,
                 asm volatile("bar.sync 1, 128;" ::: "memory");   // all column reads done before L overwrites them
             }
 #pragma unroll
-            for (int h = 0; h < 2; ++h) Sn[tid + 128 * h] = (ec[h] <= er[h]) ? e[h] : 0.0;
+            for (int h = 0; h < 2; ++h) Sn[lt + 128 * h] = (ec[h] <= er[h]) ? e[h] : 0.0;
         }
         if (warp == 0) {
             if (!PLA) {
@@ -617,16 +619,19 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws,
             // cross the diagonal (rows 2tj, 2tj+1) or hang over the last row are gathered into
             // separate boundary rounds, so no warp executes both paths for one item.
             const int nti = (nrows + 3) >> 2, ntj = (nrows + 7) >> 3, nfull = nrows >> 2;
-            // update warps of the cluster; with PLA warps 1-3 join late, so they take the last item slots
-            const int uw = (PLA ? (warp + nwarps - 5) % (nwarps - 1) : warp - 1) + (nwarps - 1) * crank, nuw = (nwarps - 1) * csize;
+            // update warps of the cluster; with PLA the look-ahead warps join late, so they take the last item slots
+            const bool la_warp = (warp & 3) == 0;                            // (PLA) warps 4, 8, 12 come late from the look-ahead
+            const int nidx = (warp >> 2) * 3 + (warp & 3) - 1;               // 0..11 among the twelve other update warps
+            const int uw = (PLA ? (la_warp ? 11 + (warp >> 2) : nidx) : warp - 1) + (nwarps - 1) * crank, nuw = (nwarps - 1) * csize;
             const int ut = tid - 32;               // index among the update threads
             // item k of the step belongs to update warp k mod nuw.
             if (nrows < 640) {
                 // narrow band (TV up to 256x256): the plain scan is the faster code (A/B on B200: 0.84 vs 0.90 s at config 5)
-                // PLA: warps 1-3 arrive late from the shared look-ahead (≈ 1.3 items' worth of cycles, measured
-                // with tools/factor_timing.py), so they take one item per round of 27 and warps 4-15 two
-                const int slot_a = PLA ? 27 * crank + (warp >= 4 ? warp - 4 : 23 + warp) : uw;
-                const int slot_b = PLA ? (warp >= 4 ? 27 * crank + warp + 8 : -1) : -1;
+                // PLA: the look-ahead warps arrive late (≈ 1.3-2 items' worth of cycles, measured with
+                // tools/factor_timing.py), so they take one item per round of 27 and the others two
+                // (warps 4, 8, 12: one item per round of 27; the twelve others two)
+                const int slot_a = PLA ? 27 * crank + (la_warp ? 23 + (warp >> 2) : nidx) : uw;
+                const int slot_b = PLA ? (la_warp ? -1 : 27 * crank + nidx + 12) : -1;
                 const int nslot = PLA ? 27 * csize : nuw;
                 int item = 0;
                 for (int tj = 0; tj < ntj; ++tj) {
