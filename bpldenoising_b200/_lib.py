@@ -23,7 +23,7 @@ class EvalOpts(C.Structure):
     _fields_ = [("pdps", PdpsOpts), ("delta_t", C.c_double), ("gamma", C.c_double),
                 ("act_tol", C.c_double), ("eps_act", C.c_double), ("solver_tol", C.c_double),
                 ("solver_maxit", C.c_int), ("solver", C.c_int), ("force_branch", C.c_int),
-                ("reserved", C.c_int * 5)]
+                ("reserved0", C.c_int), ("gamma_patch", C.c_double), ("reserved", C.c_int * 2)]
 
 
 class Stats(C.Structure):
@@ -35,7 +35,7 @@ class Stats(C.Structure):
                 ("n_devices", C.c_int), ("tblock_depth", C.c_int), ("reserved", C.c_int * 5)]
 
     def asdict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+        return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("reserved")}
 
 
 # every symbol include/bpltv.h declares

@@ -724,7 +724,8 @@ static int sumregs_eval_on_device(bpltv_ctx *ctx, Dev &d, const double *lam, int
         for (int k = 0; k < 3; ++k) gp.alpha[k] = ng == 1 ? lam[k] : 0.0;
         gp.alpha_maps = amap; gp.lm = lm; gp.ln = ln;
         gp.regularised = eo.force_branch == 2 || (eo.force_branch == 0 && !(Delta > eo.delta_t));
-        gp.gamma = eo.gamma; gp.act_tol = eo.act_tol;
+        gp.gamma = (gp.regularised && amap && eo.gamma_patch > 0) ? eo.gamma_patch : eo.gamma;   // :200 vs :117
+        gp.act_tol = eo.act_tol;
         gp.eps_act = eo.eps_act > 0 ? eo.eps_act : 2.220446049250313e-16;   // eps() in both variants (:318-320, :387-389)
         int rc = run_gradient3<Real>(d.grad3, gp, d.sm_count, d.smem_optin, st, d_costgrad + 1, &d.launches);
         if (rc != 0) return fail(rc == -1 ? BPLTV_ERR_ARG : rc, "sumregs gradient: %s", d.grad3.err.c_str());
@@ -1271,6 +1272,7 @@ void bpltv_default_sumregs_eval_opts(bpltv_eval_opts *o)
     o->pdps.opnorm = std::sqrt(18.0);   // S12: R_K of (∇ᶠ; ∇ᵇ; ∇ᶜ)
     o->delta_t = 1e-3;                  // /root/reference/src/SumRegsLearningFunction.jl:8
     o->gamma = 1e3;                     // :117 (scalar sumregs_gradient_reg)
+    o->gamma_patch = 1e8;               // :200 (patch sumregs_gradient_reg)
 }
 
 int bpltv_sumregs_denoise(bpltv_ctx *ctx, const double *noisy, int M, int N, int O, const double *lam, int lm, int ln,

@@ -1113,15 +1113,19 @@ struct GradWork {
     void *pix = nullptr, *mode = nullptr, *sinv = nullptr, *ab = nullptr, *off = nullptr, *ext = nullptr,
          *info = nullptr, *out_img = nullptr, *relres = nullptr, *relres_max = nullptr;
     size_t cap_slots = 0, cap_N = 0, cap_O = 0, cap_ng = 0;
+    void *lu_ab = nullptr, *lu_pix = nullptr, *lu_info = nullptr;   // node-space band LU (lu_band.cuh)
+    size_t lu_cap_slots = 0, lu_cap_N = 0;
     int slots = 0;
     std::string err;
     long long last_iterations = 0;
     double last_relres = 0.0;
     void release()
     {
-        void **all[] = {&pix, &mode, &sinv, &ab, &off, &ext, &info, &out_img, &relres, &relres_max};
+        void **all[] = {&pix, &mode, &sinv, &ab, &off, &ext, &info, &out_img, &relres, &relres_max,
+                        &lu_ab, &lu_pix, &lu_info};
         for (void **p : all) { if (*p) cudaFree(*p); *p = nullptr; }
         cap_slots = cap_N = cap_O = cap_ng = 0;
+        lu_cap_slots = lu_cap_N = 0;
     }
 };
 

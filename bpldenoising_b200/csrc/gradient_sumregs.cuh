@@ -16,10 +16,13 @@
 // most two contributions (addition of two numbers is commutative), the diagonal and the right-hand side
 // are summed in a fixed order, so the result is deterministic like the TV path.
 //
-// Not built: the patch variant of sumregs_gradient_reg (:195-262) — its system is row-scaled by a
-// different λ-map per operator, cannot be symmetrised, and so has no SPD compliance form.
+// The patch variant of sumregs_gradient_reg (:195-262) is row-scaled by a different λ-map per operator,
+// cannot be symmetrised and so has no SPD compliance form: it is solved in node space by the band LU of
+// lu_band.cuh (run_gradient3_lu below).
 #pragma once
 #include "gradient.cuh"
+#include "sumregs_stencils.cuh"
+#include "lu_band.cuh"
 
 namespace bpltv {
 
@@ -28,70 +31,6 @@ struct Grad3Variant {
     double alpha[3], gamma, act_tol, eps_act;
     int refine;
 };
-
-// (G_k p)(q): forward (k=0, S4), backward (k=1, S10), centred (k=2, S11) differences
-template <typename T>
-static __device__ __forceinline__ void op_apply(int k, int i, int j, int n, const T *p, int q, double &d1, double &d2)
-{
-    d1 = 0.0; d2 = 0.0;
-    if (k == 0) {
-        if (i + 1 < n) d1 = (double)p[q + 1] - (double)p[q];
-        if (j + 1 < n) d2 = (double)p[q + n] - (double)p[q];
-    } else if (k == 1) {
-        if (i >= 1) d1 = (double)p[q] - (double)p[q - 1];
-        if (j >= 1) d2 = (double)p[q] - (double)p[q - n];
-    } else {
-        if (i >= 1 && i <= n - 2) d1 = 0.5 * ((double)p[q + 1] - (double)p[q - 1]);
-        if (j >= 1 && j <= n - 2) d2 = 0.5 * ((double)p[q + n] - (double)p[q - n]);
-    }
-}
-
-// Every (pixel q, operator k) whose stencil touches node (i,j), with the coefficients c1, c2 that
-// components 1 and 2 of (G_k ·)(q) put on that node: fn(q, k, c1, c2).
-template <typename F>
-static __device__ __forceinline__ void visit_node(int i, int j, int n, F &&fn)
-{
-    const int v = j * n + i;
-    {   // forward differences
-        const double c1 = (i + 1 < n) ? -1.0 : 0.0, c2 = (j + 1 < n) ? -1.0 : 0.0;
-        if (c1 != 0.0 || c2 != 0.0) fn(v, 0, c1, c2);
-        if (i > 0) fn(v - 1, 0, 1.0, 0.0);
-        if (j > 0) fn(v - n, 0, 0.0, 1.0);
-    }
-    {   // backward differences
-        const double c1 = (i >= 1) ? 1.0 : 0.0, c2 = (j >= 1) ? 1.0 : 0.0;
-        if (c1 != 0.0 || c2 != 0.0) fn(v, 1, c1, c2);
-        if (i + 1 < n) fn(v + 1, 1, -1.0, 0.0);
-        if (j + 1 < n) fn(v + n, 1, 0.0, -1.0);
-    }
-    // centred differences (rows / columns 1..n-2 only)
-    if (i - 1 >= 1) fn(v - 1, 2, 0.5, 0.0);           // pixel row i-1 ≤ n-2 always
-    if (i + 1 <= n - 2) fn(v + 1, 2, -0.5, 0.0);      // pixel row i+1 ≥ 1 always
-    if (j - 1 >= 1) fn(v - n, 2, 0.0, 0.5);
-    if (j + 1 <= n - 2) fn(v + n, 2, 0.0, -0.5);
-}
-
-// The nodes of the stencil of (pixel (i,j), operator k), with the coefficients of components 1 and 2:
-// fn(node, c1, c2), in a fixed order.
-template <typename F>
-static __device__ __forceinline__ void visit_stencil(int k, int i, int j, int n, F &&fn)
-{
-    const int q = j * n + i;
-    if (k == 0) {
-        const double c1 = (i + 1 < n) ? -1.0 : 0.0, c2 = (j + 1 < n) ? -1.0 : 0.0;
-        if (c1 != 0.0 || c2 != 0.0) fn(q, c1, c2);
-        if (i + 1 < n) fn(q + 1, 1.0, 0.0);
-        if (j + 1 < n) fn(q + n, 0.0, 1.0);
-    } else if (k == 1) {
-        const double c1 = (i >= 1) ? 1.0 : 0.0, c2 = (j >= 1) ? 1.0 : 0.0;
-        if (c1 != 0.0 || c2 != 0.0) fn(q, c1, c2);
-        if (i >= 1) fn(q - 1, -1.0, 0.0);
-        if (j >= 1) fn(q - n, 0.0, -1.0);
-    } else {
-        if (i >= 1 && i <= n - 2) { fn(q - 1, -0.5, 0.0); fn(q + 1, 0.5, 0.0); }
-        if (j >= 1 && j <= n - 2) { fn(q - n, 0.0, -0.5); fn(q + n, 0.0, 0.5); }
-    }
-}
 
 // per-slot layout of GradSlots::pix for this path (N = n² doubles each):
 //   [5k+0..5k+4] ea, eb, E, w1, w2 of operator k;  [15] r;  [16] p;  [17..19] per-node functional of operator k
@@ -424,6 +363,84 @@ struct Grad3Problem {
     double gamma, act_tol, eps_act;
 };
 
+// ---------------------------------------------------------------------------
+// host driver of the node-space LU path (patch sumregs_gradient_reg, :195-262)
+// ---------------------------------------------------------------------------
+template <typename Real>
+static int run_gradient3_lu(GradWork &w, const Grad3Problem<Real> &gp, int sm_count, size_t smem_optin, cudaStream_t st,
+                            double *d_grad_out, long long *launches)
+{
+    const int n = gp.M, N = gp.M * gp.N, ng = gp.lm * gp.ln;
+    if (n < 4) return grad_fail(w, -1, "images smaller than 4x4 are not supported by the band LU");
+    LuSlots ws;
+    ws.n = n; ws.N = N; ws.bw = std::min(2 * n, N - 1); ws.bwx = ws.bw + LU_NB; ws.LD = (2 * ws.bwx + 1 + 1) & ~1;
+    ws.ab_stride = (size_t)N * ws.LD;
+    ws.pix_stride = (size_t)LU_PLANES * N;
+    const size_t fsmem = lu_factor_smem(ws.bw);
+    if (fsmem > smem_optin) return grad_fail(w, -1, "image too large for the band-LU panels in shared memory (n <= 430)");
+    const bool vec_in_smem = lu_solve_smem(N, true) + 1024 <= smem_optin;
+    const size_t ssmem = lu_solve_smem(N, vec_in_smem);
+
+    const size_t per_slot = (ws.ab_stride + ws.pix_stride) * 8 + 16;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const size_t have = w.lu_cap_N == (size_t)N ? w.lu_cap_slots : 0;
+    const size_t budget = (free_b + have * per_slot) / 2;
+    int slots = (int)std::min<size_t>((size_t)std::min(gp.O, sm_count), std::max<size_t>(1, budget / per_slot));
+    if (w.lu_cap_N != (size_t)N || w.lu_cap_slots < (size_t)slots) {
+        void **all[] = {&w.lu_ab, &w.lu_pix, &w.lu_info};
+        for (void **p : all) { if (*p) cudaFree(*p); *p = nullptr; }
+        cudaError_t e = cudaMalloc(&w.lu_ab, ws.ab_stride * 8 * slots);
+        if (e == cudaSuccess) e = cudaMalloc(&w.lu_pix, ws.pix_stride * 8 * slots);
+        if (e == cudaSuccess) e = cudaMalloc(&w.lu_info, 16 * (size_t)slots);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            w.lu_cap_slots = 0; w.lu_cap_N = 0;
+            return grad_fail(w, -6, std::string("band-LU workspace allocation failed: ") + cudaGetErrorString(e));
+        }
+        w.lu_cap_slots = slots; w.lu_cap_N = N;
+    } else {
+        slots = (int)std::min<size_t>(w.lu_cap_slots, (size_t)std::min(gp.O, sm_count));
+    }
+    if (w.cap_O < (size_t)gp.O || w.cap_ng < (size_t)(3 * ng)) {
+        if (w.out_img) cudaFree(w.out_img);
+        if (w.relres) cudaFree(w.relres);
+        if (!w.relres_max) cudaMalloc(&w.relres_max, 8);
+        cudaError_t e = cudaMalloc(&w.out_img, (size_t)gp.O * 3 * ng * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&w.relres, (size_t)gp.O * 8);
+        if (e != cudaSuccess) { cudaGetLastError(); w.cap_O = 0; return grad_fail(w, -6, "gradient output allocation failed"); }
+        w.cap_O = gp.O; w.cap_ng = 3 * ng;
+    }
+    ws.ab = (double *)w.lu_ab; ws.pix = (double *)w.lu_pix; ws.info = (int *)w.lu_info;
+
+    Lu3Params pr;
+    for (int k = 0; k < 3; ++k) pr.alpha[k] = gp.alpha[k];
+    pr.gamma = gp.gamma; pr.lm = gp.lm; pr.ln = gp.ln;
+    pr.refine = 3;
+    cudaError_t e = cudaFuncSetAttribute(lu_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(lu3_solve_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem);
+    if (e != cudaSuccess) { cudaGetLastError(); return grad_fail(w, -2, std::string("band-LU kernel attributes: ") + cudaGetErrorString(e)); }
+    const int chunks = std::max(1, std::min(64, (N + 255) / 256));
+    for (int img0 = 0; img0 < gp.O; img0 += slots) {
+        const int cnt = std::min(slots, gp.O - img0);
+        cudaMemsetAsync(ws.ab, 0, ws.ab_stride * 8 * cnt, st);
+        lu3_classify_kernel<Real><<<dim3(cnt, chunks), 256, 0, st>>>(ws, pr.gamma, gp.u, gp.ubar, img0);
+        lu3_assemble_kernel<Real><<<dim3(cnt, chunks), 256, 0, st>>>(ws, pr, gp.alpha_maps);
+        lu_factor_kernel<<<cnt, LU_THREADS, fsmem, st>>>(ws);
+        lu3_solve_kernel<Real><<<cnt, LU_THREADS, ssmem, st>>>(ws, pr, gp.alpha_maps, (double *)w.out_img,
+                                                              (double *)w.relres, img0, vec_in_smem ? 1 : 0);
+        *launches += 4;
+    }
+    const int nout = 3 * ng;
+    grad_reduce_kernel<<<1, std::max(32, (nout + 31) / 32 * 32), 0, st>>>((double *)w.out_img, (double *)w.relres, gp.O,
+                                                                          nout, d_grad_out, (double *)w.relres_max);
+    *launches += 1;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return grad_fail(w, -2, std::string("band-LU kernel launch failed: ") + cudaGetErrorString(e));
+    return 0;
+}
+
 template <typename Real>
 static int run_gradient3(GradWork &w, const Grad3Problem<Real> &gp, int sm_count, size_t smem_optin, cudaStream_t st,
                          double *d_grad_out, long long *launches)
@@ -433,9 +450,8 @@ static int run_gradient3(GradWork &w, const Grad3Problem<Real> &gp, int sm_count
     const int ng = gp.lm * gp.ln;
     if (gp.M != gp.N) return grad_fail(w, -1, "square images required");
     if (3 * ng > 1024) return grad_fail(w, -1, "lambda grid larger than 341 entries per operator is not supported");
-    if (gp.regularised && gp.alpha_maps)
-        return grad_fail(w, -1, "patch sumregs_gradient_reg is not built: its row-scaled system (one λ-map per "
-                                "operator, SumRegsLearningFunction.jl:246) has no symmetric compliance form");
+    if (gp.regularised && gp.alpha_maps)   // row-scaled, non-symmetric (:246): node-space band LU
+        return run_gradient3_lu<Real>(w, gp, sm_count, smem_optin, st, d_grad_out, launches);
     GradSlots ws;
     ws.N = N; ws.n = n;
     ws.NdMax = 6 * N;

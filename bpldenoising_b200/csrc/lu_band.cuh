@@ -1,0 +1,497 @@
+// lu_band.cuh — node-space adjoint solve of the ROW-SCALED regularised sum-of-regularisers system (fp64).
+//
+// Replaces the patch variant of sumregs_gradient_reg, /root/reference/src/SumRegsLearningFunction.jl:195-262:
+//     p = (I + x₁[:] .* G₁ᵀ(B₁−C₁)G₁ + x₂[:] .* G₂ᵀ(B₂−C₂)G₂ + x₃[:] .* G₃ᵀ(B₃−C₃)G₃) \ (ū − u)       (:246)
+//     g_k = p ⊙ G_kᵀ(Act_k Den_k G_k u + γ Inact_k G_k u),   gx[:,:,k] = calc_adjoint(pOp, g_k)          (:247-259)
+// `x_k[:] .*` scales the ROWS of each term by a different λ-map, so the matrix is not symmetric and has
+// no compliance (Cholesky) form.  It is a banded n²×n² matrix on the column-major nodes, though: the
+// stencils of G_kᵀ T G_k reach ±2 rows and ±2 columns, half-bandwidth 2n.  Per image (one CTA each):
+//   lu3_classify   per (pixel, operator): the 2×2 tensor T = B − C and the functional weights
+//   lu3_assemble   one thread per matrix row, 13 stencil offsets, fixed summation order (deterministic)
+//   lu_factor      blocked right-looking band LU without pivoting, NB = 16: diagonal block in one warp,
+//                  L21 rows / U12 columns by substitution (one thread each, panels kept in shared memory),
+//                  rank-16 update of the bw×bw trailing window in 8×4 register tiles
+//   lu3_solve      blocked forward / backward substitution with the vector in shared memory, iterative
+//                  refinement against the MATRIX-FREE residual (stencils + tensors, independent of the
+//                  assembled band), functional, PatchOp-adjoint sums
+// No pivoting: every term is (positive diagonal)·(PSD); for equal maps the matrix is D·SPD, whose LU needs
+// none.  A vanished pivot, or a solve whose normwise backward error stays above 1e-11 after refinement,
+// poisons the output with NaN, which the API reports as BPLTV_ERR_NUMERIC — no silent wrong answer.
+// Band storage: row i holds columns i−bwx … i+bwx at ab[i·LD + (j−i+bwx)], bwx = bw + NB, so that every
+// index a block step forms is inside the row's storage (entries outside the true band stay exactly zero).
+//
+// This header holds device code only and depends on sumregs_stencils.cuh alone: tests/emu/ compiles it with
+// g++ and runs the kernels on OS threads (CPU check of the index arithmetic and barriers; no GPU needed).
+#pragma once
+#include "sumregs_stencils.cuh"
+
+namespace bpltv {
+
+constexpr int LU_NB = 16;
+constexpr int LU_DP = LU_NB + 1;        // padded row length of the 16×16 blocks and of the L panel
+#ifndef LU_THREADS
+#define LU_THREADS 512
+#endif
+constexpr int LU_PLANES = 22;
+// per-slot planes (N doubles each): [6k+0..3] T11 T12 T21 T22, [6k+4..5] w1 w2 of operator k;
+// [18] r = ū − u; [19] p; [20] residual / correction; [21] per-node functional
+constexpr int LU_PL_R = 18, LU_PL_P = 19, LU_PL_WORK = 20, LU_PL_F = 21;
+
+struct LuSlots {
+    double *ab;   size_t ab_stride;     // per slot: N rows × LD doubles
+    double *pix;  size_t pix_stride;    // per slot: LU_PLANES planes
+    int *info;                          // per slot: 4 ints, [0] ≠ 0 → a pivot vanished
+    int n, N, bw, bwx, LD;
+};
+
+struct Lu3Params {
+    double alpha[3];     // scalar parameters when alpha_maps == nullptr
+    double gamma;
+    int lm, ln, refine;
+};
+
+static __device__ __forceinline__ double lu_warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// sum over the CTA, valid in every thread; `red` = 33 doubles of shared memory
+static __device__ double lu_block_sum(double v, double *red)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    v = lu_warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        double r = lane < nwarps ? red[lane] : 0.0;
+        r = lu_warp_sum(r);
+        if (lane == 0) red[32] = r;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+// max over the CTA, valid in every thread
+static __device__ double lu_block_max(double v, double *red)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        double r = lane < nwarps ? red[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
+        if (lane == 0) red[32] = r;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+// ---------------------------------------------------------------------------
+// K1: T_kq = B − C and w_kq of every (pixel, operator); r = ū − u     (:203-241, :246)
+// ---------------------------------------------------------------------------
+template <typename Real>
+__global__ void __launch_bounds__(256) lu3_classify_kernel(LuSlots ws, double gamma, const Real *u_all,
+                                                           const Real *ubar_all, int img0)
+{
+    const int slot = blockIdx.x;
+    const int n = ws.n, N = ws.N;
+    const Real *u = u_all + (size_t)(img0 + slot) * N;
+    const Real *ub = ubar_all + (size_t)(img0 + slot) * N;
+    double *pix = ws.pix + ws.pix_stride * slot;
+    for (int q = blockIdx.y * blockDim.x + threadIdx.x; q < N; q += gridDim.y * blockDim.x) {
+        const int i = q % n, j = q / n;
+        pix[(size_t)LU_PL_R * N + q] = (double)ub[q] - (double)u[q];
+        for (int k = 0; k < 3; ++k) {
+            double g1, g2;
+            op_apply<Real>(k, i, j, n, u, q, g1, g2);
+            const double nrm = sqrt(g1 * g1 + g2 * g2);
+            const bool act = fmax(0.0, nrm - 1.0 / gamma) != 0.0;     // :207-208
+            double t11, t12, t21, t22, w1, w2;
+            if (act) {   // −C = Den − prodesc(Gu/den³, Gu) (:211-215); w = Den·Gu
+                const double den = nrm, id = 1.0 / den, d3 = den * den * den;
+                const double a1 = g1 / d3, a2 = g2 / d3;
+                t11 = id - a1 * g1; t12 = -(a1 * g2); t21 = -(a2 * g1); t22 = id - a2 * g2;
+                w1 = id * g1; w2 = id * g2;
+            } else {     // B = γ·Inact; w = γ·Gu
+                t11 = gamma; t12 = 0.0; t21 = 0.0; t22 = gamma;
+                w1 = gamma * g1; w2 = gamma * g2;
+            }
+            double *pk = pix + (size_t)(6 * k) * N;
+            pk[q] = t11; pk[(size_t)N + q] = t12; pk[(size_t)2 * N + q] = t21; pk[(size_t)3 * N + q] = t22;
+            pk[(size_t)4 * N + q] = w1; pk[(size_t)5 * N + q] = w2;
+        }
+    }
+}
+
+template <typename Real>
+static __device__ __forceinline__ double lu3_alpha(const Real *alpha_maps, const Lu3Params &pr, int N, int k, int v)
+{
+    return alpha_maps ? (double)alpha_maps[(size_t)k * N + v] : pr.alpha[k];
+}
+
+// ---------------------------------------------------------------------------
+// K2: row v of  I + Σ_k diag(α_k) G_kᵀ T_k G_k  (the band must be zero on entry)
+// ---------------------------------------------------------------------------
+template <typename Real>
+__global__ void __launch_bounds__(256) lu3_assemble_kernel(LuSlots ws, Lu3Params pr, const Real *alpha_maps)
+{
+    const int slot = blockIdx.x;
+    const int n = ws.n, N = ws.N;
+    const double *pix = ws.pix + ws.pix_stride * slot;
+    double *ab = ws.ab + ws.ab_stride * slot;
+    if (blockIdx.y == 0 && threadIdx.x == 0) ws.info[4 * slot] = 0;
+    const int offs[13] = {-2 * n, -n - 1, -n, -n + 1, -2, -1, 0, 1, 2, n - 1, n, n + 1, 2 * n};   // distinct for n ≥ 4
+    for (int v = blockIdx.y * blockDim.x + threadIdx.x; v < N; v += gridDim.y * blockDim.x) {
+        const int i = v % n, j = v / n;
+        double acc[13];
+#pragma unroll
+        for (int s = 0; s < 13; ++s) acc[s] = 0.0;
+        acc[6] = 1.0;
+        visit_node(i, j, n, [&](int q, int k, double c1, double c2) {
+            const double *tk = pix + (size_t)(6 * k) * N;
+            const double a = lu3_alpha<Real>(alpha_maps, pr, N, k, v);
+            const double v1 = c1 * tk[q] + c2 * tk[(size_t)2 * N + q];                  // (c1 c2)·T
+            const double v2 = c1 * tk[(size_t)N + q] + c2 * tk[(size_t)3 * N + q];
+            visit_stencil(k, q % n, q / n, n, [&](int node, double e1, double e2) {
+                const double val = a * (v1 * e1 + v2 * e2);
+                const int d = node - v;
+#pragma unroll
+                for (int s = 0; s < 13; ++s)
+                    if (offs[s] == d) { acc[s] += val; break; }
+            });
+        });
+        double *row = ab + (size_t)v * ws.LD + ws.bwx;
+#pragma unroll
+        for (int s = 0; s < 13; ++s) {
+            const int col = v + offs[s];
+            if (col >= 0 && col < N) row[offs[s]] = acc[s];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K3: in-place band LU, no pivoting.  Dynamic shared memory (doubles):
+//   D[NB·DP] diagonal block | rD[NB] reciprocal pivots | Ls[(bw+8)·DP] L panel | Us[NB·bwp] U panel
+// ---------------------------------------------------------------------------
+static inline size_t lu_factor_smem(int bw)
+{
+    const int bwp = (bw + 3) & ~3;
+    return (size_t)(LU_NB * LU_DP + LU_NB + (bw + 8) * LU_DP + 1 + LU_NB * bwp) * sizeof(double);
+}
+
+__global__ void __launch_bounds__(LU_THREADS, 1) lu_factor_kernel(LuSlots ws)
+{
+    extern __shared__ __align__(16) double lu_fsm[];
+    constexpr int NB = LU_NB, DP = LU_DP;
+    const int slot = blockIdx.x;
+    const int N = ws.N, bw = ws.bw, bwx = ws.bwx, LD = ws.LD;
+    double *ab = ws.ab + ws.ab_stride * slot;
+    const int bwp = (bw + 3) & ~3;
+    double *D = lu_fsm;
+    double *rD = D + NB * DP;
+    double *Ls = rD + NB;
+    double *Us = Ls + (((bw + 8) * DP + 1) & ~1);     // even offset: 16-byte aligned for the double2 reads
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    bool bad = false;
+
+    for (int k0 = 0; k0 < N; k0 += NB) {
+        const int nb = min(NB, N - k0);
+        const int R = min(bw, N - k0 - nb);       // rows below / columns right of the block inside the band
+        // ---- diagonal block: load, factor in warp 0 (identity padding for a short last block) ----
+        if (tid < NB * NB) {
+            const int r = tid / NB, c = tid - r * NB;
+            D[r * DP + c] = (r < nb && c < nb) ? ab[(size_t)(k0 + r) * LD + (c - r + bwx)] : (r == c ? 1.0 : 0.0);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const int r = lane & 15, h = lane >> 4;   // row r, columns 8h … 8h+7
+            for (int pv = 0; pv < NB; ++pv) {
+                const double piv = D[pv * DP + pv];
+                if (!(fabs(piv) > 0.0)) bad = true;
+                const double l = r > pv ? D[r * DP + pv] * (1.0 / piv) : 0.0;
+                __syncwarp();
+                if (r > pv) {
+                    if (h == (pv >> 3)) D[r * DP + pv] = l;
+#pragma unroll
+                    for (int cc = 0; cc < 8; ++cc) {
+                        const int c = 8 * h + cc;
+                        if (c > pv) D[r * DP + c] -= l * D[pv * DP + c];
+                    }
+                }
+                __syncwarp();
+            }
+            if (lane < NB) rD[lane] = 1.0 / D[lane * DP + lane];
+        }
+        __syncthreads();
+        if (tid < NB * NB) {   // the factored block back to the band
+            const int r = tid / NB, c = tid - r * NB;
+            if (r < nb && c < nb) ab[(size_t)(k0 + r) * LD + (c - r + bwx)] = D[r * DP + c];
+        }
+        // ---- L21 = A21 U11⁻¹ (one thread per row), U12 = L11⁻¹ A12 (one thread per column) ----
+        for (int t = tid; t < 2 * R; t += blockDim.x) {
+            if (t < R) {
+                const int gr = k0 + nb + t;
+                double *rowp = ab + (size_t)gr * LD + (k0 - gr + bwx);        // entry (gr, k0+c) at rowp[c]
+                double x[NB];
+#pragma unroll
+                for (int c = 0; c < NB; ++c) x[c] = rowp[c];
+#pragma unroll
+                for (int c = 0; c < NB; ++c) {
+                    double s = x[c];
+#pragma unroll
+                    for (int m = 0; m < c; ++m) s -= x[m] * D[m * DP + c];
+                    x[c] = s * rD[c];
+                }
+#pragma unroll
+                for (int c = 0; c < NB; ++c) { rowp[c] = x[c]; Ls[t * DP + c] = x[c]; }
+            } else {
+                const int tt = t - R, gj = k0 + nb + tt;
+                double *colp = ab + (size_t)k0 * LD + (gj - k0 + bwx);        // entry (k0+r, gj) at colp[r·(LD−1)]
+                double y[NB];
+#pragma unroll
+                for (int r = 0; r < NB; ++r) y[r] = colp[(size_t)r * (LD - 1)];
+#pragma unroll
+                for (int r = 0; r < NB; ++r) {
+                    double s = y[r];
+#pragma unroll
+                    for (int m = 0; m < r; ++m) s -= D[r * DP + m] * y[m];
+                    y[r] = s;
+                }
+#pragma unroll
+                for (int r = 0; r < NB; ++r) { colp[(size_t)r * (LD - 1)] = y[r]; Us[r * bwp + tt] = y[r]; }
+            }
+        }
+        __syncthreads();
+        // ---- trailing window A22 −= L21·U12: warp tiles of 8 rows × 128 columns, 8×4 per thread ----
+        const int ct = (R + 127) >> 7, ntile = ((R + 7) >> 3) * ct;
+        const int g0 = k0 + nb;
+        for (int wt = warp; wt < ntile; wt += nwarps) {
+            const int tr = wt / ct, tc = wt - tr * ct;
+            const int r0 = tr * 8, j0 = tc * 128 + lane * 4;
+            if (j0 < R) {
+                double acc[8][4];
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    const int rr = r0 + a;
+                    const double *pp = ab + (size_t)(g0 + rr) * LD + (j0 - rr + bwx);
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] = (rr < R && j0 + b < R) ? pp[b] : 0.0;
+                }
+#pragma unroll
+                for (int c = 0; c < NB; ++c) {
+                    const double2 u01 = *reinterpret_cast<const double2 *>(Us + c * bwp + j0);
+                    const double2 u23 = *reinterpret_cast<const double2 *>(Us + c * bwp + j0 + 2);
+#pragma unroll
+                    for (int a = 0; a < 8; ++a) {
+                        const double l = Ls[(r0 + a) * DP + c];
+                        acc[a][0] = fma(-l, u01.x, acc[a][0]);
+                        acc[a][1] = fma(-l, u01.y, acc[a][1]);
+                        acc[a][2] = fma(-l, u23.x, acc[a][2]);
+                        acc[a][3] = fma(-l, u23.y, acc[a][3]);
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    const int rr = r0 + a;
+                    double *pp = ab + (size_t)(g0 + rr) * LD + (j0 - rr + bwx);
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (rr < R && j0 + b < R) pp[b] = acc[a][b];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (bad && tid == 0) ws.info[4 * slot] = 1;
+}
+
+// ---------------------------------------------------------------------------
+// blocked substitution with the factors of lu_factor_kernel; `vec` (N doubles, shared or global memory)
+// is solved in place.  D: NB·DP doubles, rhs: NB doubles of shared memory.  Ends with a barrier.
+// ---------------------------------------------------------------------------
+static __device__ void lu_band_solve(const double *ab, int N, int bw, int bwx, int LD, double *vec, double *D,
+                                     double *rhs)
+{
+    constexpr int NB = LU_NB, DP = LU_DP;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    // forward: L y = b, L unit lower
+    for (int k0 = 0; k0 < N; k0 += NB) {
+        const int nb = min(NB, N - k0);
+        const int R = min(bw, N - k0 - nb);
+        if (tid < NB * NB) {
+            const int r = tid / NB, c = tid - r * NB;
+            D[r * DP + c] = (r < nb && c < r) ? ab[(size_t)(k0 + r) * LD + (c - r + bwx)] : 0.0;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double y = lane < nb ? vec[k0 + lane] : 0.0;
+#pragma unroll
+            for (int m = 0; m < NB; ++m) {
+                const double ym = __shfl_sync(0xffffffffu, y, m);
+                if (lane > m && lane < NB) y -= D[lane * DP + m] * ym;
+            }
+            if (lane < nb) vec[k0 + lane] = y;
+        }
+        __syncthreads();
+        for (int t = tid; t < R; t += blockDim.x) {     // R > 0 implies a full block (nb = NB)
+            const int gr = k0 + nb + t;
+            const double *rowp = ab + (size_t)gr * LD + (k0 - gr + bwx);
+            double s = 0.0;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) s = fma(rowp[c], vec[k0 + c], s);
+            vec[gr] -= s;
+        }
+        __syncthreads();
+    }
+    // backward: U x = y
+    const int nblk = (N + NB - 1) / NB;
+    for (int kb = nblk - 1; kb >= 0; --kb) {
+        const int k0 = kb * NB;
+        const int nb = min(NB, N - k0);
+        const int R = min(bw, N - k0 - nb);
+        if (tid < NB * NB) {
+            const int r = tid / NB, c = tid - r * NB;
+            D[r * DP + c] = (r < nb && c < nb && c >= r) ? ab[(size_t)(k0 + r) * LD + (c - r + bwx)] : (r == c ? 1.0 : 0.0);
+        }
+        for (int r = warp; r < nb; r += nwarps) {
+            const double *rowp = ab + (size_t)(k0 + r) * LD + (nb - r + bwx);   // entry (k0+r, k0+nb+j) at rowp[j]
+            double s = 0.0;
+            for (int j = lane; j < R; j += 32) s = fma(rowp[j], vec[k0 + nb + j], s);
+            s = lu_warp_sum(s);
+            if (lane == 0) rhs[r] = vec[k0 + r] - s;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double x = lane < nb ? rhs[lane] : 0.0;
+#pragma unroll
+            for (int m = NB - 1; m >= 0; --m) {
+                const double xm = __shfl_sync(0xffffffffu, x, m) / D[m * DP + m];
+                if (lane == m) x = xm;
+                if (lane < m) x -= D[lane * DP + m] * xm;
+            }
+            if (lane < nb) vec[k0 + lane] = x;
+        }
+        __syncthreads();
+    }
+}
+
+// (M p)(v), matrix-free: p_v + Σ_k α_k(v) (G_kᵀ T_k G_k p)(v)
+template <typename Real>
+static __device__ __forceinline__ double lu3_apply(const double *pix, int n, int N, const Real *alpha_maps,
+                                                   const Lu3Params &pr, const double *p, int v)
+{
+    double sk[3] = {0.0, 0.0, 0.0};
+    visit_node(v % n, v / n, n, [&](int q, int k, double c1, double c2) {
+        double d1, d2;
+        op_apply<double>(k, q % n, q / n, n, p, q, d1, d2);
+        const double *tk = pix + (size_t)(6 * k) * N;
+        const double z1 = tk[q] * d1 + tk[(size_t)N + q] * d2;
+        const double z2 = tk[(size_t)2 * N + q] * d1 + tk[(size_t)3 * N + q] * d2;
+        sk[k] += c1 * z1 + c2 * z2;
+    });
+    double s = p[v];
+    for (int k = 0; k < 3; ++k) s += lu3_alpha<Real>(alpha_maps, pr, N, k, v) * sk[k];
+    return s;
+}
+
+// ---------------------------------------------------------------------------
+// K4: p = M⁻¹ r with refinement, g_k = p ⊙ G_kᵀ w_k, patch sums (or plain sums for a scalar parameter).
+// Dynamic shared memory: D[NB·DP] | rhs[NB] | red[33+] | vec[N] when vec_in_smem.
+// out_img: 3·lm·ln doubles per image, layout [operator][patch] like the m×n×3 array.
+// ---------------------------------------------------------------------------
+static inline size_t lu_solve_smem(int N, bool vec_in_smem)
+{
+    return (size_t)(LU_NB * LU_DP + LU_NB + 40 + (vec_in_smem ? N : 0)) * sizeof(double);
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(LU_THREADS, 1) lu3_solve_kernel(LuSlots ws, Lu3Params pr, const Real *alpha_maps,
+                                                                  double *out_img, double *relres_img, int img0,
+                                                                  int vec_in_smem)
+{
+    extern __shared__ __align__(16) double lu_ssm[];
+    const int slot = blockIdx.x;
+    const int n = ws.n, N = ws.N;
+    const double *ab = ws.ab + ws.ab_stride * slot;
+    double *pix = ws.pix + ws.pix_stride * slot;
+    const double *r = pix + (size_t)LU_PL_R * N;
+    double *p = pix + (size_t)LU_PL_P * N, *work = pix + (size_t)LU_PL_WORK * N, *fk = pix + (size_t)LU_PL_F * N;
+    double *D = lu_ssm, *rhs = D + LU_NB * LU_DP, *red = rhs + LU_NB;
+    double *vec = vec_in_smem ? red + 40 : work;
+    const int tid = threadIdx.x;
+
+    double bn2 = 0.0;
+    for (int v = tid; v < N; v += blockDim.x) { const double x = r[v]; vec[v] = x; bn2 = fma(x, x, bn2); }
+    bn2 = lu_block_sum(bn2, red);
+    lu_band_solve(ab, N, ws.bw, ws.bwx, ws.LD, vec, D, rhs);
+    for (int v = tid; v < N; v += blockDim.x) p[v] = vec[v];
+    __syncthreads();
+    double relres = 0.0, prev = 1e300, rn2_last = 0.0;
+    for (int it = 0;; ++it) {
+        double rn2 = 0.0;
+        for (int v = tid; v < N; v += blockDim.x) {
+            const double res = r[v] - lu3_apply<Real>(pix, n, N, alpha_maps, pr, p, v);
+            work[v] = res;
+            rn2 = fma(res, res, rn2);
+        }
+        rn2 = lu_block_sum(rn2, red);
+        rn2_last = rn2;
+        relres = bn2 > 0.0 ? sqrt(rn2 / bn2) : 0.0;
+        // stop at rounding level, or when a step no longer gains a factor 4 (the residual itself is only
+        // accurate to eps·‖M‖‖p‖: ≈ 1e-10·‖r‖ at γ = 1e8)
+        if (it >= pr.refine || relres <= 1e-14 || !(relres <= 0.25 * prev)) break;
+        prev = relres;
+        if (vec != work) {
+            for (int v = tid; v < N; v += blockDim.x) vec[v] = work[v];
+            __syncthreads();
+        }
+        lu_band_solve(ab, N, ws.bw, ws.bwx, ws.LD, vec, D, rhs);
+        for (int v = tid; v < N; v += blockDim.x) p[v] += vec[v];
+        __syncthreads();
+    }
+    // a vanished pivot or an unconverged solve must not pass as a gradient: normwise backward error
+    // ‖r − Mp‖ / (‖M‖‖p‖ + ‖r‖) with the bound ‖M‖ ≤ 1 + (8 + 8 + 2)·γ·max α
+    double pn2 = 0.0, amax = 0.0;
+    for (int v = tid; v < N; v += blockDim.x) {
+        pn2 = fma(p[v], p[v], pn2);
+        for (int k = 0; k < 3; ++k) amax = fmax(amax, lu3_alpha<Real>(alpha_maps, pr, N, k, v));
+    }
+    pn2 = lu_block_sum(pn2, red);
+    amax = lu_block_max(amax, red);
+    const double berr = sqrt(rn2_last) / ((1.0 + 18.0 * pr.gamma * amax) * sqrt(pn2) + sqrt(bn2) + 1e-300);
+    const bool failed = ws.info[4 * slot] != 0 || !(berr <= 1e-11);
+    const int ng = pr.lm * pr.ln;
+    for (int k = 0; k < 3; ++k) {
+        const double *w1 = pix + (size_t)(6 * k + 4) * N, *w2 = pix + (size_t)(6 * k + 5) * N;
+        for (int v = tid; v < N; v += blockDim.x) {
+            double s = 0.0;
+            visit_node(v % n, v / n, n, [&](int q, int kk, double c1, double c2) {
+                if (kk == k) s += c1 * w1[q] + c2 * w2[q];
+            });
+            fk[v] = p[v] * s;                                   // p ⊙ G_kᵀ w_k (:247-249; p'·G_kᵀw_k :166)
+        }
+        __syncthreads();
+        for (int g = 0; g < ng; ++g) {
+            const int pi = g % pr.lm, pj = g / pr.lm;
+            double acc = 0.0;
+            for (int v = tid; v < N; v += blockDim.x) {
+                const int i = v % n, j = v / n;
+                const int qi = (int)(((long long)i * pr.lm) / n), qj = (int)(((long long)j * pr.ln) / n);
+                if (qi == pi && qj == pj) acc += fk[v];
+            }
+            acc = lu_block_sum(acc, red);
+            if (tid == 0) out_img[((size_t)(img0 + slot) * 3 + k) * ng + g] = failed ? nan("") : acc;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) relres_img[img0 + slot] = relres;
+}
+
+}  // namespace bpltv

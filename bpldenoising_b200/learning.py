@@ -78,7 +78,7 @@ def eval_opts(pdps: Optional[PdpsOpts] = None, **kw) -> EvalOpts:
     alias = {"Δt": "delta_t", "γ": "gamma"}
     for k, v in kw.items():
         k = alias.get(k, k)
-        if not hasattr(o, k) or k in ("reserved", "pdps"):
+        if not hasattr(o, k) or k in ("reserved", "reserved0", "pdps"):
             raise TypeError(f"unknown evaluation option {k!r}")
         setattr(o, k, type(getattr(o, k))(v))
     return o
@@ -94,7 +94,7 @@ def sumregs_eval_opts(pdps: Optional[PdpsOpts] = None, **kw) -> EvalOpts:
     alias = {"Δt": "delta_t", "γ": "gamma"}
     for k, v in kw.items():
         k = alias.get(k, k)
-        if not hasattr(o, k) or k in ("reserved", "pdps"):
+        if not hasattr(o, k) or k in ("reserved", "reserved0", "pdps"):
             raise TypeError(f"unknown evaluation option {k!r}")
         setattr(o, k, type(getattr(o, k))(v))
     return o

@@ -89,7 +89,11 @@ typedef struct bpltv_eval_opts {
     int solver;          /* 0 auto; 1 PCG (Jacobi); 2 block-Cholesky + refinement */
     int force_branch;    /* 0: by Δ (reference); 1: gradient; 2: gradient_reg;
                             3: cost only (grad_out left zero; λ-sweeps, validation)  */
-    int reserved[5];
+    int reserved0;
+    double gamma_patch;  /* γ of the PATCH variant of sumregs_gradient_reg, 1e8
+                            (SumRegsLearningFunction.jl:200; the scalar variant uses
+                            `gamma` = 1e3, :117); 0 → `gamma`.  Unused by the TV path.  */
+    int reserved[2];
 } bpltv_eval_opts;
 
 typedef struct bpltv_stats {
@@ -174,8 +178,9 @@ int bpltv_sumregs_denoise(bpltv_ctx *ctx, const double *noisy, int M, int N, int
 /* Replaces sumregs_learning_function(x, data, Δ; Δt=1e-3) (:8-36) on the resident dataset:
  * u = sumregs_denoise(f, x); cost = 0.5‖u-ū‖²; grad = Δ > Δt ? sumregs_gradient (:264-327, :330-407)
  * : sumregs_gradient_reg (:112-167), summed over images (:87-110, :169-193).  grad_out has the shape
- * of x: 3 (lm = ln = 1) or lm×ln×3 entries.  The patch variant of sumregs_gradient_reg (:195-262) is
- * not built (its row-scaled system has no symmetric form): BPLTV_ERR_ARG.  opts == NULL → the
+ * of x: 3 (lm = ln = 1) or lm×ln×3 entries.  The patch variant of sumregs_gradient_reg (:195-262),
+ * whose system is row-scaled by a different λ-map per operator and therefore not symmetric, is
+ * solved by a banded LU in node space (γ = opts->gamma_patch).  opts == NULL → the
  * sum-of-regularisers defaults.                                                              */
 int bpltv_sumregs_learn_eval(bpltv_ctx *ctx, const double *lam, int lm, int ln, double Delta,
                              const bpltv_eval_opts *opts, double *u_out, double *cost_out,

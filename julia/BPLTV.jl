@@ -26,7 +26,8 @@ struct EvalOpts
     pdps::PdpsOpts
     delta_t::Cdouble; gamma::Cdouble; act_tol::Cdouble; eps_act::Cdouble; solver_tol::Cdouble
     solver_maxit::Cint; solver::Cint; force_branch::Cint
-    reserved::NTuple{5,Cint}
+    reserved0::Cint; gamma_patch::Cdouble
+    reserved::NTuple{2,Cint}
 end
 
 lasterr() = unsafe_string(ccall((:bpltv_last_error, lib), Cstring, ()))

@@ -1,0 +1,84 @@
+// emu_cuda.h — TEST INFRASTRUCTURE: just enough of the CUDA execution model on OS threads to run the
+// device code of bpldenoising_b200/csrc/lu_band.cuh on a CPU (one std::thread per CUDA thread, CTA and
+// warp barriers, warp shuffles through a per-warp exchange buffer).  It checks index arithmetic and
+// barrier placement where no GPU exists; it is never part of the product (nothing under
+// bpldenoising_b200/ includes it) and says nothing about performance.
+#pragma once
+#include <algorithm>
+#include <barrier>
+#include <cmath>
+#include <cstddef>
+#include <memory>
+#include <thread>
+#include <vector>
+
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+struct double2 { double x, y; };
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __shared__
+#define __align__(x)
+
+namespace emu {
+struct Warp {
+    std::barrier<> bar;
+    double xch[32];
+    Warp() : bar(32) {}
+};
+struct Cta {
+    std::barrier<> bar;
+    std::vector<std::unique_ptr<Warp>> warps;
+    explicit Cta(int threads) : bar(threads)
+    {
+        for (int w = 0; w < (threads + 31) / 32; ++w) warps.emplace_back(new Warp());
+    }
+};
+inline thread_local Cta *cta = nullptr;
+inline thread_local Warp *warp = nullptr;
+}  // namespace emu
+
+inline thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
+
+inline void __syncthreads() { emu::cta->bar.arrive_and_wait(); }
+inline void __syncwarp() { emu::warp->bar.arrive_and_wait(); }
+inline double __shfl_sync(unsigned, double v, int src)
+{
+    emu::Warp &w = *emu::warp;
+    w.xch[threadIdx.x & 31] = v;
+    w.bar.arrive_and_wait();
+    const double r = w.xch[src & 31];
+    w.bar.arrive_and_wait();
+    return r;
+}
+inline double __shfl_xor_sync(unsigned m, double v, int o) { return __shfl_sync(m, v, (int)(threadIdx.x & 31) ^ o); }
+
+using std::max;
+using std::min;
+
+namespace emu {
+// kernel<<<grid, threads>>>(args...): blocks run one after the other, the threads of a block concurrently
+// (threads must be a multiple of 32: every warp barrier expects 32 arrivals)
+template <typename F>
+void launch(dim3 grid, int threads, F &&body)
+{
+    for (unsigned by = 0; by < grid.y; ++by)
+        for (unsigned bx = 0; bx < grid.x; ++bx) {
+            Cta c(threads);
+            std::vector<std::thread> ts;
+            for (int t = 0; t < threads; ++t)
+                ts.emplace_back([&, t] {
+                    threadIdx = dim3((unsigned)t); blockIdx = dim3(bx, by); blockDim = dim3((unsigned)threads); gridDim = grid;
+                    cta = &c; warp = c.warps[t / 32].get();
+                    body();
+                });
+            for (auto &th : ts) th.join();
+        }
+}
+}  // namespace emu

@@ -1,0 +1,103 @@
+"""CPU check of the band-LU gradient kernels (bpldenoising_b200/csrc/lu_band.cuh) where no GPU exists:
+the device code is compiled with g++ against tests/emu/emu_cuda.h (one OS thread per CUDA thread, CTA /
+warp barriers, shuffles) and run for one image, then compared with the oracle's literal row-scaled system
+(`sumregs_gradient_reg`, patch variant, /root/reference/src/SumRegsLearningFunction.jl:195-262).  The
+emulation checks index arithmetic and barrier placement, not performance; the GPU parity test proper is
+tests/test_gpu_sumregs.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import oracle as orc
+from oracle import sumregs as sr
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, "emu")
+
+
+def _build(threads):
+    out = os.path.join(EMU, "_build", f"libemu_lu_{threads}.so")
+    srcs = [os.path.join(EMU, "emu_lu.cpp"), os.path.join(EMU, "emu_cuda.h"),
+            os.path.join(HERE, "..", "bpldenoising_b200", "csrc", "lu_band.cuh"),
+            os.path.join(HERE, "..", "bpldenoising_b200", "csrc", "sumregs_stencils.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-fPIC", "-shared", f"-DLU_THREADS={threads}",
+                        "-o", out, srcs[0]], check=True)
+    lib = C.CDLL(out)
+    lib.emu_lu_gradient.restype = C.c_int
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _case(n, seed):
+    rng = np.random.default_rng(seed)
+    t = np.round(rng.random((n, n)) * 255) / 255
+    u = np.asfortranarray(t + 0.05 * rng.standard_normal((n, n)))
+    u[:3, :3] = u[0, 0]                      # an exactly flat block: |∇_k u| = 0, the γ·I tensors
+    return np.asfortranarray(t), u
+
+
+def _run(lib, n, u, t, maps, alpha3, gamma, grid, vec_in_smem, want_band=False):
+    N = n * n
+    bw = min(2 * n, N - 1)
+    LD = (2 * (bw + 16) + 2) & ~1
+    out = np.zeros(3 * grid[0] * grid[1])
+    band = np.zeros(N * LD) if want_band else None
+    rr, pf, ld = C.c_double(), C.c_int(), C.c_int()
+    am = None if maps is None else np.concatenate([m.flatten(order="F") for m in maps])
+    a3 = None if alpha3 is None else np.asarray(alpha3, dtype=np.float64)
+    rc = lib.emu_lu_gradient(n, _ptr(u.flatten(order="F")), _ptr(t.flatten(order="F")), _ptr(am), _ptr(a3),
+                             C.c_double(gamma), grid[0], grid[1], 3, int(vec_in_smem), _ptr(out), C.byref(rr),
+                             C.byref(pf), _ptr(band), C.byref(ld))
+    assert rc == 0 and ld.value == LD and pf.value == 0
+    got = out.reshape(3, grid[1], grid[0]).transpose(2, 1, 0)      # [operator][patch] → (pi, pj, operator)
+    return got, rr.value, (None if band is None else band.reshape(N, LD)), bw + 16
+
+
+@pytest.mark.parametrize("n,threads,vec_in_smem", [(8, 256, 1), (12, 256, 0), (16, 512, 1)])
+def test_band_lu_patch_reg_gradient_on_the_thread_emulation(n, threads, vec_in_smem):
+    lib = _build(threads)
+    t, u = _case(n, 100 + n)
+    xp = np.stack([np.array([[0.03, 0.05], [0.02, 0.04]]) * s for s in (1.0, 0.7, 1.3)], axis=2)
+    maps = [np.asfortranarray(orc.patch_upsample(xp[:, :, k], n, n)) for k in range(3)]
+    gamma = 1e8                                                   # :200
+    got, relres, band, bwx = _run(lib, n, u, t, maps, None, gamma, (2, 2), vec_in_smem, want_band=True)
+    # the assembled band = the oracle's literal matrix (:246), entry by entry
+    N = n * n
+    uf = u.flatten(order="F")
+    A = sp.identity(N, format="csr")
+    for k, kind in enumerate(sr.KINDS):
+        G = sr.op_matrix(kind, n)
+        BmC, _ = sr._sets_reg(G, uf, gamma)
+        A = A + sp.diags(maps[k].flatten(order="F")) @ (G.T @ BmC @ G)
+    A = A.toarray()
+    Ab = np.zeros((N, N))
+    for i in range(N):
+        lo, hi = max(0, i - bwx), min(N, i + bwx + 1)
+        Ab[i, lo:hi] = band[i, lo - i + bwx:hi - i + bwx]
+    assert np.abs(Ab - A).max() <= 1e-15 * np.abs(A).max()
+    # the gradient = the refined literal solve; tolerance 1e-9 (the system's entries span 1 … αγ ≈ 1e7, the
+    # same bar as the other regularised variants)
+    lit = sr.sumregs_gradient_reg(maps, u, t, grid_shape=(2, 2), gamma=gamma, refine=3)
+    assert np.all(np.abs(got - lit) <= 1e-9 * np.abs(lit).max()), (got, lit)
+    assert relres <= 1e-8
+
+
+def test_band_lu_scalar_parameter_on_the_thread_emulation():
+    """The same kernels with a scalar 3-vector (alpha_maps == NULL): scalar sumregs_gradient_reg (:112-167, γ = 1e3)."""
+    lib = _build(256)
+    n = 10
+    t, u = _case(n, 7)
+    x = np.array([0.05, 0.04, 0.06])
+    got, relres, _, _ = _run(lib, n, u, t, None, x, 1e3, (1, 1), 1)
+    lit = sr.sumregs_gradient_reg(x, u, t, refine=3)
+    assert np.all(np.abs(got.ravel() - lit) <= 1e-12 * np.abs(lit).max()), (got, lit)
+    assert relres <= 1e-13
