@@ -24,6 +24,7 @@
 #include "pdps_sumregs.cuh"
 #include "gradient.cuh"
 #include "gradient_sumregs.cuh"
+#include "gradient_lu.cuh"
 
 using namespace bpltv;
 
@@ -813,6 +814,29 @@ static int set_dataset_impl(bpltv_ctx *ctx, const double *truth, const double *n
 
 // Enqueue one evaluation on one device: u = denoise; scalars[0] = cost;
 // scalars[1..] = gradient.  Everything asynchronous on `st`.
+
+// gradient / gradient_reg of the TV learning function.  The regularised branch has two implementations:
+// the multiplier-space banded Cholesky of gradient.cuh and the node-space band LU of lu_band.cuh
+// (n² unknowns with half-bandwidth n instead of ≤ 2n² modes with half-bandwidth ≤ 2n+1);
+// BPLTV_GRAD_REG_LU=0/1 selects, default BPLTV_GRAD_REG_LU_DEFAULT.
+#ifndef BPLTV_GRAD_REG_LU_DEFAULT
+#define BPLTV_GRAD_REG_LU_DEFAULT false
+#endif
+template <typename Real>
+static int run_tv_gradient(Dev &d, const GradProblem<Real> &gp, cudaStream_t st, double *d_grad_out)
+{
+    const char *lu_env = getenv("BPLTV_GRAD_REG_LU");
+    const bool lu = lu_env && *lu_env ? atoi(lu_env) != 0 : BPLTV_GRAD_REG_LU_DEFAULT;
+    if (gp.regularised && lu && gp.M == gp.N && gp.M >= 4) {
+        LuProblem<Real> lp;
+        lp.u = gp.u; lp.ubar = gp.ubar; lp.M = gp.M; lp.N = gp.N; lp.O = gp.O;
+        lp.alpha[0] = gp.alpha_s; lp.alpha[1] = lp.alpha[2] = 0.0;
+        lp.alpha_maps = gp.alpha_map; lp.lm = gp.lm; lp.ln = gp.ln; lp.gamma = gp.gamma; lp.nops = 1;
+        return run_gradient_lu<Real>(d.grad, lp, d.sm_count, d.smem_optin, st, d_grad_out, &d.launches);
+    }
+    return run_gradient<Real>(d.grad, gp, d.sm_count, d.smem_optin, st, d_grad_out, &d.launches);
+}
+
 template <typename Real>
 static int eval_on_device(bpltv_ctx *ctx, Dev &d, const double *lam, int lm, int ln, double Delta,
                           const bpltv_eval_opts &eo, cudaStream_t st, const Real **u_res, double *d_costgrad)
@@ -839,7 +863,7 @@ static int eval_on_device(bpltv_ctx *ctx, Dev &d, const double *lam, int lm, int
         gp.gamma = eo.gamma; gp.act_tol = eo.act_tol;
         gp.eps_act = eo.eps_act > 0 ? eo.eps_act : (ng == 1 ? 2.220446049250313e-16 : 1.4901161193847656e-08);
         gp.tol = eo.solver_tol; gp.maxit = eo.solver_maxit; gp.solver = eo.solver;
-        int rc = run_gradient<Real>(d.grad, gp, d.sm_count, d.smem_optin, st, d_costgrad + 1, &d.launches);
+        int rc = run_tv_gradient<Real>(d, gp, st, d_costgrad + 1);
         if (rc != 0) return fail(rc, "gradient: %s", d.grad.err.c_str());
     }
     CU_TRY(cudaEventRecord(d.ev[3], st));
@@ -1008,7 +1032,7 @@ static int gradient_impl(bpltv_ctx *ctx, const double *u_host, const double *lam
         gp.eps_act = eo.eps_act > 0 ? eo.eps_act : (ng == 1 ? 2.220446049250313e-16 : 1.4901161193847656e-08);
         gp.tol = eo.solver_tol; gp.maxit = eo.solver_maxit; gp.solver = eo.solver;
         CU_TRY(cudaMemsetAsync(d.scalars.p, 0, (1 + ng) * sizeof(double), st));
-        int rc = run_gradient<Real>(d.grad, gp, d.sm_count, d.smem_optin, st, d.scalars.as<double>() + 1, &d.launches);
+        int rc = run_tv_gradient<Real>(d, gp, st, d.scalars.as<double>() + 1);
         if (rc != 0) return fail(rc, "gradient: %s", d.grad.err.c_str());
         CU_TRY(cudaEventRecord(d.ev[3], st));
         CU_TRY(cudaMemcpyAsync(host[di].data(), d.scalars.as<double>() + 1, ng * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -42,6 +42,7 @@ struct LuSlots {
     double *pix;  size_t pix_stride;    // per slot: LU_PLANES planes
     int *info;                          // per slot: 4 ints, [0] ≠ 0 → a pivot vanished
     int n, N, bw, bwx, LD;
+    int nops;                           // 3: forward, backward, centred (sum of regularisers); 1: forward only (TV)
 };
 
 struct Lu3Params {
@@ -49,6 +50,13 @@ struct Lu3Params {
     double gamma;
     int lm, ln, refine;
 };
+
+// 16-byte accesses: the thread emulation (tests/emu, -DBPLTV_EMU) checks the alignment the GPU requires
+#ifdef BPLTV_EMU
+#define LU_A16(p) (emu::check_aligned16(p), (p))
+#else
+#define LU_A16(p) (p)
+#endif
 
 static __device__ __forceinline__ double lu_warp_sum(double v)
 {
@@ -108,7 +116,7 @@ __global__ void __launch_bounds__(256) lu3_classify_kernel(LuSlots ws, double ga
     for (int q = blockIdx.y * blockDim.x + threadIdx.x; q < N; q += gridDim.y * blockDim.x) {
         const int i = q % n, j = q / n;
         pix[(size_t)LU_PL_R * N + q] = (double)ub[q] - (double)u[q];
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < ws.nops; ++k) {
             double g1, g2;
             op_apply<Real>(k, i, j, n, u, q, g1, g2);
             const double nrm = sqrt(g1 * g1 + g2 * g2);
@@ -155,6 +163,7 @@ __global__ void __launch_bounds__(256) lu3_assemble_kernel(LuSlots ws, Lu3Params
         for (int s = 0; s < 13; ++s) acc[s] = 0.0;
         acc[6] = 1.0;
         visit_node(i, j, n, [&](int q, int k, double c1, double c2) {
+            if (k >= ws.nops) return;
             const double *tk = pix + (size_t)(6 * k) * N;
             const double a = lu3_alpha<Real>(alpha_maps, pr, N, k, v);
             const double v1 = c1 * tk[q] + c2 * tk[(size_t)2 * N + q];                  // (c1 c2)·T
@@ -178,12 +187,15 @@ __global__ void __launch_bounds__(256) lu3_assemble_kernel(LuSlots ws, Lu3Params
 
 // ---------------------------------------------------------------------------
 // K3: in-place band LU, no pivoting.  Dynamic shared memory (doubles):
-//   D[NB·DP] diagonal block | rD[NB] reciprocal pivots | Ls[(bw+8)·DP] L panel | Us[NB·bwp] U panel
+//   D[NB·DP] diagonal block | rD[NB] reciprocal pivots | Lt[NB·lsp] L panel, TRANSPOSED (column c of the
+//   panel contiguous over the rows) | Us[NB·bwp] U panel (row c contiguous over the columns)
+// LD is odd (≡ 1 mod 4), so (row·LD + col − row) has the parity of col: every row segment that starts at an
+// even column of the window is 16-byte aligned and moves as double2.
 // ---------------------------------------------------------------------------
+static inline int lu_panel_pitch(int bw) { return (bw + 32 + 3) & ~3; }
 static inline size_t lu_factor_smem(int bw)
 {
-    const int bwp = (bw + 3) & ~3;
-    return (size_t)(LU_NB * LU_DP + LU_NB + (bw + 8) * LU_DP + 1 + LU_NB * bwp) * sizeof(double);
+    return (size_t)(LU_NB * LU_DP + LU_NB + 2 * LU_NB * lu_panel_pitch(bw)) * sizeof(double);
 }
 
 __global__ void __launch_bounds__(LU_THREADS, 1) lu_factor_kernel(LuSlots ws)
@@ -193,12 +205,13 @@ __global__ void __launch_bounds__(LU_THREADS, 1) lu_factor_kernel(LuSlots ws)
     const int slot = blockIdx.x;
     const int N = ws.N, bw = ws.bw, bwx = ws.bwx, LD = ws.LD;
     double *ab = ws.ab + ws.ab_stride * slot;
-    const int bwp = (bw + 3) & ~3;
+    const int lsp = (bw + 32 + 3) & ~3;           // pitch of both panels (32 spare entries: ragged tiles read, never use them)
     double *D = lu_fsm;
-    double *rD = D + NB * DP;
-    double *Ls = rD + NB;
-    double *Us = Ls + (((bw + 8) * DP + 1) & ~1);     // even offset: 16-byte aligned for the double2 reads
+    double *rD = D + NB * DP;                     // NB·DP = 272 and NB are even: the panels are 16-byte aligned
+    double *Lt = rD + NB;
+    double *Us = Lt + NB * lsp;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int rg = lane >> 3, cg = lane & 7;      // trailing update: 4 row groups × 8 column groups per warp
     bool bad = false;
 
     for (int k0 = 0; k0 < N; k0 += NB) {
@@ -238,10 +251,13 @@ __global__ void __launch_bounds__(LU_THREADS, 1) lu_factor_kernel(LuSlots ws)
         for (int t = tid; t < 2 * R; t += blockDim.x) {
             if (t < R) {
                 const int gr = k0 + nb + t;
-                double *rowp = ab + (size_t)gr * LD + (k0 - gr + bwx);        // entry (gr, k0+c) at rowp[c]
+                double *rowp = ab + (size_t)gr * LD + (k0 - gr + bwx);        // entry (gr, k0+c) at rowp[c]; 16-byte aligned
                 double x[NB];
 #pragma unroll
-                for (int c = 0; c < NB; ++c) x[c] = rowp[c];
+                for (int c = 0; c < NB; c += 2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(LU_A16(rowp + c));
+                    x[c] = v.x; x[c + 1] = v.y;
+                }
 #pragma unroll
                 for (int c = 0; c < NB; ++c) {
                     double s = x[c];
@@ -250,7 +266,10 @@ __global__ void __launch_bounds__(LU_THREADS, 1) lu_factor_kernel(LuSlots ws)
                     x[c] = s * rD[c];
                 }
 #pragma unroll
-                for (int c = 0; c < NB; ++c) { rowp[c] = x[c]; Ls[t * DP + c] = x[c]; }
+                for (int c = 0; c < NB; c += 2) {
+                    *reinterpret_cast<double2 *>(LU_A16(rowp + c)) = make_double2(x[c], x[c + 1]);
+                    Lt[c * lsp + t] = x[c]; Lt[(c + 1) * lsp + t] = x[c + 1];
+                }
             } else {
                 const int tt = t - R, gj = k0 + nb + tt;
                 double *colp = ab + (size_t)k0 * LD + (gj - k0 + bwx);        // entry (k0+r, gj) at colp[r·(LD−1)]
@@ -265,18 +284,29 @@ __global__ void __launch_bounds__(LU_THREADS, 1) lu_factor_kernel(LuSlots ws)
                     y[r] = s;
                 }
 #pragma unroll
-                for (int r = 0; r < NB; ++r) { colp[(size_t)r * (LD - 1)] = y[r]; Us[r * bwp + tt] = y[r]; }
+                for (int r = 0; r < NB; ++r) { colp[(size_t)r * (LD - 1)] = y[r]; Us[r * lsp + tt] = y[r]; }
             }
         }
         __syncthreads();
-        // ---- trailing window A22 −= L21·U12: warp tiles of 8 rows × 128 columns, 8×4 per thread ----
-        const int ct = (R + 127) >> 7, ntile = ((R + 7) >> 3) * ct;
+        // ---- trailing window A22 −= L21·U12: warp tiles of 32 rows × 32 columns, 8×4 per thread; per rank
+        //      the thread reads 8 panel entries of Lt and 4 of Us as six 16-byte shared-memory loads ----
+        const int ct = (R + 31) >> 5, ntile = ct * ct;
         const int g0 = k0 + nb;
         for (int wt = warp; wt < ntile; wt += nwarps) {
             const int tr = wt / ct, tc = wt - tr * ct;
-            const int r0 = tr * 8, j0 = tc * 128 + lane * 4;
-            if (j0 < R) {
-                double acc[8][4];
+            const int r0 = tr * 32 + rg * 8, j0 = tc * 32 + cg * 4;
+            if (r0 >= R || j0 >= R) continue;
+            const bool full = r0 + 8 <= R && j0 + 4 <= R;
+            double acc[8][4];
+            if (full) {
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    const double *pp = ab + (size_t)(g0 + r0 + a) * LD + (j0 - r0 - a + bwx);
+                    const double2 v0 = *reinterpret_cast<const double2 *>(LU_A16(pp));
+                    const double2 v1 = *reinterpret_cast<const double2 *>(LU_A16(pp + 2));
+                    acc[a][0] = v0.x; acc[a][1] = v0.y; acc[a][2] = v1.x; acc[a][3] = v1.y;
+                }
+            } else {
 #pragma unroll
                 for (int a = 0; a < 8; ++a) {
                     const int rr = r0 + a;
@@ -284,19 +314,33 @@ __global__ void __launch_bounds__(LU_THREADS, 1) lu_factor_kernel(LuSlots ws)
 #pragma unroll
                     for (int b = 0; b < 4; ++b) acc[a][b] = (rr < R && j0 + b < R) ? pp[b] : 0.0;
                 }
+            }
+#pragma unroll 4
+            for (int c = 0; c < NB; ++c) {
+                const double2 u01 = *reinterpret_cast<const double2 *>(LU_A16(Us + c * lsp + j0));
+                const double2 u23 = *reinterpret_cast<const double2 *>(LU_A16(Us + c * lsp + j0 + 2));
+                double l[8];
 #pragma unroll
-                for (int c = 0; c < NB; ++c) {
-                    const double2 u01 = *reinterpret_cast<const double2 *>(Us + c * bwp + j0);
-                    const double2 u23 = *reinterpret_cast<const double2 *>(Us + c * bwp + j0 + 2);
-#pragma unroll
-                    for (int a = 0; a < 8; ++a) {
-                        const double l = Ls[(r0 + a) * DP + c];
-                        acc[a][0] = fma(-l, u01.x, acc[a][0]);
-                        acc[a][1] = fma(-l, u01.y, acc[a][1]);
-                        acc[a][2] = fma(-l, u23.x, acc[a][2]);
-                        acc[a][3] = fma(-l, u23.y, acc[a][3]);
-                    }
+                for (int a = 0; a < 8; a += 2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(LU_A16(Lt + c * lsp + r0 + a));
+                    l[a] = v.x; l[a + 1] = v.y;
                 }
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    acc[a][0] = fma(-l[a], u01.x, acc[a][0]);
+                    acc[a][1] = fma(-l[a], u01.y, acc[a][1]);
+                    acc[a][2] = fma(-l[a], u23.x, acc[a][2]);
+                    acc[a][3] = fma(-l[a], u23.y, acc[a][3]);
+                }
+            }
+            if (full) {
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    double *pp = ab + (size_t)(g0 + r0 + a) * LD + (j0 - r0 - a + bwx);
+                    *reinterpret_cast<double2 *>(LU_A16(pp)) = make_double2(acc[a][0], acc[a][1]);
+                    *reinterpret_cast<double2 *>(LU_A16(pp + 2)) = make_double2(acc[a][2], acc[a][3]);
+                }
+            } else {
 #pragma unroll
                 for (int a = 0; a < 8; ++a) {
                     const int rr = r0 + a;
@@ -384,11 +428,12 @@ static __device__ void lu_band_solve(const double *ab, int N, int bw, int bwx, i
 
 // (M p)(v), matrix-free: p_v + Σ_k α_k(v) (G_kᵀ T_k G_k p)(v)
 template <typename Real>
-static __device__ __forceinline__ double lu3_apply(const double *pix, int n, int N, const Real *alpha_maps,
+static __device__ __forceinline__ double lu3_apply(const double *pix, int n, int N, int nops, const Real *alpha_maps,
                                                    const Lu3Params &pr, const double *p, int v)
 {
     double sk[3] = {0.0, 0.0, 0.0};
     visit_node(v % n, v / n, n, [&](int q, int k, double c1, double c2) {
+        if (k >= nops) return;
         double d1, d2;
         op_apply<double>(k, q % n, q / n, n, p, q, d1, d2);
         const double *tk = pix + (size_t)(6 * k) * N;
@@ -397,14 +442,14 @@ static __device__ __forceinline__ double lu3_apply(const double *pix, int n, int
         sk[k] += c1 * z1 + c2 * z2;
     });
     double s = p[v];
-    for (int k = 0; k < 3; ++k) s += lu3_alpha<Real>(alpha_maps, pr, N, k, v) * sk[k];
+    for (int k = 0; k < nops; ++k) s += lu3_alpha<Real>(alpha_maps, pr, N, k, v) * sk[k];
     return s;
 }
 
 // ---------------------------------------------------------------------------
 // K4: p = M⁻¹ r with refinement, g_k = p ⊙ G_kᵀ w_k, patch sums (or plain sums for a scalar parameter).
 // Dynamic shared memory: D[NB·DP] | rhs[NB] | red[33+] | vec[N] when vec_in_smem.
-// out_img: 3·lm·ln doubles per image, layout [operator][patch] like the m×n×3 array.
+// out_img: nops·lm·ln doubles per image, layout [operator][patch] like the m×n×3 array.
 // ---------------------------------------------------------------------------
 static inline size_t lu_solve_smem(int N, bool vec_in_smem)
 {
@@ -437,7 +482,7 @@ __global__ void __launch_bounds__(LU_THREADS, 1) lu3_solve_kernel(LuSlots ws, Lu
     for (int it = 0;; ++it) {
         double rn2 = 0.0;
         for (int v = tid; v < N; v += blockDim.x) {
-            const double res = r[v] - lu3_apply<Real>(pix, n, N, alpha_maps, pr, p, v);
+            const double res = r[v] - lu3_apply<Real>(pix, n, N, ws.nops, alpha_maps, pr, p, v);
             work[v] = res;
             rn2 = fma(res, res, rn2);
         }
@@ -461,14 +506,14 @@ __global__ void __launch_bounds__(LU_THREADS, 1) lu3_solve_kernel(LuSlots ws, Lu
     double pn2 = 0.0, amax = 0.0;
     for (int v = tid; v < N; v += blockDim.x) {
         pn2 = fma(p[v], p[v], pn2);
-        for (int k = 0; k < 3; ++k) amax = fmax(amax, lu3_alpha<Real>(alpha_maps, pr, N, k, v));
+        for (int k = 0; k < ws.nops; ++k) amax = fmax(amax, lu3_alpha<Real>(alpha_maps, pr, N, k, v));
     }
     pn2 = lu_block_sum(pn2, red);
     amax = lu_block_max(amax, red);
     const double berr = sqrt(rn2_last) / ((1.0 + 18.0 * pr.gamma * amax) * sqrt(pn2) + sqrt(bn2) + 1e-300);
     const bool failed = ws.info[4 * slot] != 0 || !(berr <= 1e-11);
     const int ng = pr.lm * pr.ln;
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < ws.nops; ++k) {
         const double *w1 = pix + (size_t)(6 * k + 4) * N, *w2 = pix + (size_t)(6 * k + 5) * N;
         for (int v = tid; v < N; v += blockDim.x) {
             double s = 0.0;
@@ -487,7 +532,7 @@ __global__ void __launch_bounds__(LU_THREADS, 1) lu3_solve_kernel(LuSlots ws, Lu
                 if (qi == pi && qj == pj) acc += fk[v];
             }
             acc = lu_block_sum(acc, red);
-            if (tid == 0) out_img[((size_t)(img0 + slot) * 3 + k) * ng + g] = failed ? nan("") : acc;
+            if (tid == 0) out_img[((size_t)(img0 + slot) * ws.nops + k) * ng + g] = failed ? nan("") : acc;
         }
         __syncthreads();
     }

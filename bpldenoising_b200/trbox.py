@@ -240,26 +240,12 @@ def scalar_bilevel_sumregs_learn(data, ctx=None, **kwargs) -> LearnResult:
                          prm.pop("alpha0"), prm)
 
 
-class RegularisedPatchBranch(RuntimeError):
-    """The trust region shrank below Δt = 1e-3, where the reference switches to the patch variant of
-    sumregs_gradient_reg (SumRegsLearningFunction.jl:195-262) — the one system libbpltv does not build
-    (row-scaled by a different λ-map per operator: no symmetric form, docs/SEMANTICS.md)."""
-
-
 def patch_bilevel_sumregs_learn(data, ctx=None, **kwargs) -> LearnResult:
-    """patch_bilevel_sumregs_learn (BPLDenoising.jl:464-481) without IO/visualisation, for as long as the
-    run stays in the non-regularised branch (Δ > Δt); raises RegularisedPatchBranch otherwise."""
-    from . import _lib
+    """patch_bilevel_sumregs_learn (BPLDenoising.jl:464-481) without IO/visualisation.  Once the trust
+    region shrinks below Δt = 1e-3 the learning function switches to the patch variant of
+    sumregs_gradient_reg (SumRegsLearningFunction.jl:195-262), which libbpltv solves with its band LU."""
     from .learning import sumregs_learning_function
 
     prm = dict(PATCH_SUMREGS_BILEVEL_PARAMS); prm.update(kwargs)
-
-    def lf(x, ds, D):
-        try:
-            return sumregs_learning_function(x, ds, D, ctx=ctx)
-        except _lib.BpltvError as e:
-            if "row-scaled" in str(e):
-                raise RegularisedPatchBranch(f"Δ = {D:g} ≤ Δt: {e}") from e
-            raise
-
-    return bilevel_learn(data, lf, prm.pop("alpha0"), prm)
+    return bilevel_learn(data, lambda x, ds, D: sumregs_learning_function(x, ds, D, ctx=ctx),
+                         prm.pop("alpha0"), prm)

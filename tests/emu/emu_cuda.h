@@ -17,6 +17,7 @@ struct dim3 {
     dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
 struct double2 { double x, y; };
+inline double2 make_double2(double a, double b) { return double2{a, b}; }
 
 #define __global__
 #define __device__
@@ -26,7 +27,14 @@ struct double2 { double x, y; };
 #define __shared__
 #define __align__(x)
 
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 namespace emu {
+inline void check_aligned16(const void *p)
+{
+    if (reinterpret_cast<std::uintptr_t>(p) & 15) { std::fprintf(stderr, "emu: misaligned 16-byte access %p\n", p); std::abort(); }
+}
 struct Warp {
     std::barrier<> bar;
     double xch[32];

@@ -15,29 +15,30 @@ alignas(16) double lu_ssm[1 << 17];
 using namespace bpltv;
 
 // returns 0, or -1 when the problem does not fit the emulation's shared-memory arrays
-extern "C" int emu_lu_gradient(int n, const double *u, const double *ubar, const double *alpha_maps, const double *alpha3,
+extern "C" int emu_lu_gradient(int nops, int n, const double *u, const double *ubar, const double *alpha_maps, const double *alpha3,
                                double gamma, int lm, int ln, int refine, int vec_in_smem, double *out, double *relres,
                                int *pivot_flag, double *band_out /* N·LD or NULL: the assembled (unfactored) band */,
                                int *ld_out)
 {
     const int N = n * n;
     LuSlots ws;
-    ws.n = n; ws.N = N; ws.bw = std::min(2 * n, N - 1); ws.bwx = ws.bw + LU_NB; ws.LD = (2 * ws.bwx + 1 + 1) & ~1;
-    ws.ab_stride = (size_t)N * ws.LD; ws.pix_stride = (size_t)LU_PLANES * N;
+    ws.n = n; ws.N = N; ws.nops = nops; ws.bw = std::min(nops == 1 ? n : 2 * n, N - 1); ws.bwx = ws.bw + LU_NB; ws.LD = 2 * ws.bwx + 1;
+    ws.ab_stride = ((size_t)N * ws.LD + 3) & ~(size_t)3; ws.pix_stride = (size_t)LU_PLANES * N;
     if (ld_out) *ld_out = ws.LD;
     if (lu_factor_smem(ws.bw) > sizeof lu_fsm || lu_solve_smem(N, vec_in_smem != 0) > sizeof lu_ssm) return -1;
-    std::vector<double> ab(ws.ab_stride, 0.0), pix(ws.pix_stride, 0.0);
+    std::vector<double> ab_store(ws.ab_stride + 2, 0.0), pix(ws.pix_stride, 0.0);
     int info[4] = {0, 0, 0, 0};
-    ws.ab = ab.data(); ws.pix = pix.data(); ws.info = info;
+    double *abp = ab_store.data(); if (reinterpret_cast<std::uintptr_t>(abp) & 15) ++abp;   // 16-byte aligned like cudaMalloc
+    ws.ab = abp; ws.pix = pix.data(); ws.info = info;
     Lu3Params pr;
     for (int k = 0; k < 3; ++k) pr.alpha[k] = alpha3 ? alpha3[k] : 0.0;
     pr.gamma = gamma; pr.lm = lm; pr.ln = ln; pr.refine = refine;
     const int chunks = std::max(1, std::min(64, (N + 255) / 256));
     emu::launch(dim3(1, chunks), 256, [&] { lu3_classify_kernel<double>(ws, gamma, u, ubar, 0); });
     emu::launch(dim3(1, chunks), 256, [&] { lu3_assemble_kernel<double>(ws, pr, alpha_maps); });
-    if (band_out) std::memcpy(band_out, ab.data(), ab.size() * sizeof(double));
+    if (band_out) std::memcpy(band_out, abp, ws.ab_stride * sizeof(double));
     emu::launch(dim3(1), LU_THREADS, [&] { lu_factor_kernel(ws); });
-    std::vector<double> out_img(3 * lm * ln, 0.0);
+    std::vector<double> out_img(nops * lm * ln, 0.0);
     double rr = -1.0;
     emu::launch(dim3(1), LU_THREADS, [&] { lu3_solve_kernel<double>(ws, pr, alpha_maps, out_img.data(), &rr, 0, vec_in_smem); });
     std::memcpy(out, out_img.data(), out_img.size() * sizeof(double));

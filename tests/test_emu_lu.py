@@ -26,7 +26,7 @@ def _build(threads):
             os.path.join(HERE, "..", "bpldenoising_b200", "csrc", "sumregs_stencils.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         os.makedirs(os.path.dirname(out), exist_ok=True)
-        subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-fPIC", "-shared", f"-DLU_THREADS={threads}",
+        subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-fPIC", "-shared", f"-DLU_THREADS={threads}", "-DBPLTV_EMU",
                         "-o", out, srcs[0]], check=True)
     lib = C.CDLL(out)
     lib.emu_lu_gradient.restype = C.c_int
@@ -45,21 +45,21 @@ def _case(n, seed):
     return np.asfortranarray(t), u
 
 
-def _run(lib, n, u, t, maps, alpha3, gamma, grid, vec_in_smem, want_band=False):
+def _run(lib, n, u, t, maps, alpha3, gamma, grid, vec_in_smem, want_band=False, nops=3):
     N = n * n
-    bw = min(2 * n, N - 1)
-    LD = (2 * (bw + 16) + 2) & ~1
-    out = np.zeros(3 * grid[0] * grid[1])
-    band = np.zeros(N * LD) if want_band else None
+    bw = min(n if nops == 1 else 2 * n, N - 1)
+    LD = 2 * (bw + 16) + 1
+    out = np.zeros(nops * grid[0] * grid[1])
+    band = np.zeros((N * LD + 3) & ~3) if want_band else None
     rr, pf, ld = C.c_double(), C.c_int(), C.c_int()
     am = None if maps is None else np.concatenate([m.flatten(order="F") for m in maps])
     a3 = None if alpha3 is None else np.asarray(alpha3, dtype=np.float64)
-    rc = lib.emu_lu_gradient(n, _ptr(u.flatten(order="F")), _ptr(t.flatten(order="F")), _ptr(am), _ptr(a3),
+    rc = lib.emu_lu_gradient(nops, n, _ptr(u.flatten(order="F")), _ptr(t.flatten(order="F")), _ptr(am), _ptr(a3),
                              C.c_double(gamma), grid[0], grid[1], 3, int(vec_in_smem), _ptr(out), C.byref(rr),
                              C.byref(pf), _ptr(band), C.byref(ld))
     assert rc == 0 and ld.value == LD and pf.value == 0
-    got = out.reshape(3, grid[1], grid[0]).transpose(2, 1, 0)      # [operator][patch] → (pi, pj, operator)
-    return got, rr.value, (None if band is None else band.reshape(N, LD)), bw + 16
+    got = out.reshape(nops, grid[1], grid[0]).transpose(2, 1, 0)      # [operator][patch] → (pi, pj, operator)
+    return got, rr.value, (None if band is None else band[:N * LD].reshape(N, LD)), bw + 16
 
 
 @pytest.mark.parametrize("n,threads,vec_in_smem", [(8, 256, 1), (12, 256, 0), (16, 512, 1)])
@@ -101,3 +101,19 @@ def test_band_lu_scalar_parameter_on_the_thread_emulation():
     lit = sr.sumregs_gradient_reg(x, u, t, refine=3)
     assert np.all(np.abs(got.ravel() - lit) <= 1e-12 * np.abs(lit).max()), (got, lit)
     assert relres <= 1e-13
+
+
+def test_band_lu_tv_gradient_reg_on_the_thread_emulation():
+    """nops = 1: gradient_reg of the TV learning function, scalar (/root/reference/src/TVLearningFunctionVec.jl:137-161)
+    and patch (:192-215, row-scaled), forward differences only, half-bandwidth n, γ = 1e8."""
+    lib = _build(256)
+    n = 12
+    t, u = _case(n, 11)
+    got, relres, _, _ = _run(lib, n, u, t, None, np.array([0.1, 0.0, 0.0]), 1e8, (1, 1), 1, nops=1)
+    lit = orc.gradient_reg_scalar(0.1, u, t, refine=3)
+    assert abs(got.ravel()[0] - lit) <= 1e-9 * abs(lit), (got, lit)
+    x = np.array([[0.05, 0.1], [0.08, 0.02]])
+    amap = np.asfortranarray(orc.patch_upsample(x, n, n))
+    gotp, relres, _, _ = _run(lib, n, u, t, [amap], None, 1e8, (2, 2), 0, nops=1)
+    litp = orc.gradient_reg_patch(amap, (2, 2), u, t, refine=3)
+    assert np.all(np.abs(gotp[:, :, 0] - litp) <= 1e-9 * np.abs(litp).max()), (gotp, litp)

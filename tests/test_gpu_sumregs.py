@@ -107,10 +107,70 @@ def test_sumregs_gradient_with_flat_regions_and_patch_parameters(bp, ctx, sr, da
     gp = ctx.sumregs_gradient(xp, u, regularised=False)
     dp = sr.sumregs_gradient_dual("nonreg", maps, u[:, :, 0], t[:, :, 0], grid_shape=(2, 2))
     assert gp.shape == (2, 2, 3) and np.all(np.abs(gp - dp) <= 1e-9 * np.abs(dp).max()), (gp, dp)
-    # patch regularised branch (:195-262): refused, with the reason
-    with pytest.raises(bp.BpltvError) as ei:
-        ctx.sumregs_gradient(xp, u, regularised=True)
-    assert "row-scaled" in str(ei.value)
+    # patch regularised branch (:195-262, γ = 1e8): the row-scaled, non-symmetric system, solved by the
+    # node-space band LU (lu_band.cuh); against the refined literal sparse solve, the 1e-9 bar of the other
+    # regularised variants
+    gr = ctx.sumregs_gradient(xp, u, regularised=True)
+    lr = sr.sumregs_gradient_reg(maps, u[:, :, 0], t[:, :, 0], grid_shape=(2, 2), refine=3)
+    assert gr.shape == (2, 2, 3) and np.all(np.abs(gr - lr) <= 1e-9 * np.abs(lr).max()), (gr, lr)
+
+
+def test_patch_sumregs_gradient_reg_band_lu(bp, ctx, sr, datasets):
+    """Patch variant of sumregs_gradient_reg (:195-262) through the band LU: several images per call (one
+    CTA each, summed in image order, :183-191), odd size (short last block, ragged tiles), a 3×2 grid whose
+    patches do not divide the image, γ override, fp32 context, and the full 128×128 dataset size."""
+    from oracle import oracle as orc
+    # three images, 40×40, 2×2 grid
+    t, f = _crop(datasets, "faces_train_128_10", 40, k=3, off=30)
+    xp = np.stack([np.array([[0.03, 0.05], [0.02, 0.04]]) * s for s in (1.0, 0.7, 1.3)], axis=2)
+    maps = [orc.patch_upsample(xp[:, :, k], 40, 40) for k in range(3)]
+    u = sr.sumregs_pdps(f, maps, maxiter=300)
+    ctx.set_dataset((t, f))
+    g = ctx.sumregs_gradient(xp, u, regularised=True)
+    lit = sum(sr.sumregs_gradient_reg(maps, u[:, :, i], t[:, :, i], grid_shape=(2, 2), refine=3) for i in range(3))
+    assert np.all(np.abs(g - lit) <= 1e-9 * np.abs(lit).max()), (g, lit)
+    # the learning function takes this branch for Δ ≤ Δt = 1e-3 (:29-33)
+    u2, cost2, g2 = bp.sumregs_learning_function(xp, (t, f), 5e-4, ctx=ctx, maxiter=300)
+    assert np.array_equal(u2, u) and np.allclose(g2, g, rtol=1e-13, atol=0)
+    # γ through the options (1e3 makes the system benign: 1e-12)
+    g3 = ctx.sumregs_gradient(xp, u, regularised=True, opts=bp.sumregs_eval_opts(gamma_patch=1e3))
+    lit3 = sum(sr.sumregs_gradient_reg(maps, u[:, :, i], t[:, :, i], grid_shape=(2, 2), gamma=1e3, refine=3)
+               for i in range(3))
+    assert np.all(np.abs(g3 - lit3) <= 1e-12 * np.abs(lit3).max()), (g3, lit3)
+    # odd size, 3×2 grid
+    t, f = _crop(datasets, "cameraman_128_5", 37, off=40)
+    xq = np.stack([np.array([[0.03, 0.05], [0.02, 0.04], [0.06, 0.01]]) * s for s in (1.0, 0.7, 1.3)], axis=2)
+    mq = [orc.patch_upsample(xq[:, :, k], 37, 37) for k in range(3)]
+    uq = sr.sumregs_pdps(f, mq, maxiter=300)
+    ctx.set_dataset((t, f))
+    gq = ctx.sumregs_gradient(xq, uq, regularised=True)
+    lq = sr.sumregs_gradient_reg(mq, uq[:, :, 0], t[:, :, 0], grid_shape=(3, 2), refine=3)
+    assert gq.shape == (3, 2, 3) and np.all(np.abs(gq - lq) <= 1e-9 * np.abs(lq).max()), (gq, lq)
+    # fp32 context: the solve runs in fp32, the gradient in fp64 on the fp32 u (its own oracle input)
+    with bp.Context([0], 32) as c32:
+        c32.set_dataset((t, f))
+        u32 = c32.sumregs_denoise(f, xq, bp.sumregs_pdps_opts(maxiter=300))
+        g32 = c32.sumregs_gradient(xq, u32, regularised=True)
+        t32 = t.astype(np.float32).astype(np.float64)
+        m32 = [m.astype(np.float32).astype(np.float64) for m in mq]
+        l32 = sr.sumregs_gradient_reg(m32, u32[:, :, 0].astype(np.float64), t32[:, :, 0], grid_shape=(3, 2), refine=3)
+        assert np.all(np.abs(g32 - l32) <= 1e-9 * np.abs(l32).max()), (g32, l32)
+
+
+def test_patch_sumregs_gradient_reg_at_dataset_size(bp, ctx, sr, datasets):
+    """128×128 (the reference's dataset size; 16 384 unknowns, half-bandwidth 256) at α₀ (BPLDenoising.jl:462)."""
+    from oracle import oracle as orc
+    t, f = datasets["circle_128_10"]
+    x0 = 0.001 * np.ones((2, 2, 3)); x0[1, 0, :] *= 1.5; x0[0, 1, 2] *= 0.5
+    maps = [orc.patch_upsample(x0[:, :, k], 128, 128) for k in range(3)]
+    ctx.set_dataset((t, f))
+    u = ctx.sumregs_denoise(f, x0, bp.sumregs_pdps_opts(maxiter=500))
+    g = ctx.sumregs_gradient(x0, u, regularised=True)
+    st = ctx.stats()
+    lit = sr.sumregs_gradient_reg(maps, u[:, :, 0], t[:, :, 0], grid_shape=(2, 2), refine=3)
+    assert np.all(np.abs(g - lit) <= 1e-9 * np.abs(lit).max()), (g, lit)
+    assert st["ms_gradient"] > 0
+    print("patch sumregs_gradient_reg 128x128: %.1f ms" % st["ms_gradient"])
 
 
 def test_sumregs_learning_function_end_to_end(bp, ctx, sr, datasets):
@@ -192,12 +252,13 @@ def test_sumregs_single_process_multi_device_context(bp, datasets):
         assert np.array_equal(c2.sumregs_denoise(f, x, eo.pdps), u1)
 
 
-def test_patch_bilevel_sumregs_learn_runs_in_the_non_regularised_branch(bp, ctx, datasets):
+def test_patch_bilevel_sumregs_learn_runs_through_both_branches(bp, ctx, datasets):
     """patch_bilevel_sumregs_learn (BPLDenoising.jl:464-481): m×n×3 parameter through the L-BFGS path of the
-    driver; the regularised patch branch (Δ ≤ 1e-3) is the one system that is not built and says so."""
+    driver, in the non-regularised branch (Δ₀ = 0.1 > Δt) and, started below Δt = 1e-3, in the regularised
+    patch branch (band LU)."""
     from bpldenoising_b200 import trbox
     t, f = _crop(datasets, "circle_128_10", 32, off=48)
     res = trbox.patch_bilevel_sumregs_learn((t, f), ctx=ctx, maxiter=3)
     assert np.shape(res.x) == (2, 2, 3) and np.all(np.asarray(res.x) > 0) and res.evaluations == 4
-    with pytest.raises(trbox.RegularisedPatchBranch):
-        trbox.patch_bilevel_sumregs_learn((t, f), ctx=ctx, maxiter=2, Delta0=5e-4)
+    res2 = trbox.patch_bilevel_sumregs_learn((t, f), ctx=ctx, maxiter=2, Delta0=5e-4)
+    assert np.shape(res2.x) == (2, 2, 3) and np.all(np.asarray(res2.x) > 0) and np.all(np.isfinite(res2.x))

@@ -1,0 +1,51 @@
+"""Wall time of the sum-of-regularisers gradients on the reference's datasets (ms, device events):
+scalar sumregs_gradient_reg through the multiplier-space Cholesky vs the node-space band LU
+(BPLTV_SUMREGS_REG_LU), the patch variant (band LU only), and the non-regularised branch."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bpldenoising_b200 as bp  # noqa: E402
+
+z = np.load(os.path.join(ROOT, "tests", "golden", "datasets.npz"))
+
+
+def data(name, k):
+    return (np.asfortranarray(z[name + "/true"][:, :, :k] / 255.0), np.asfortranarray(z[name + "/data"][:, :, :k] / 255.0))
+
+
+def timed(c, x, reg, u, reps=3):
+    best, g = 1e30, None
+    for _ in range(reps):
+        g = c.sumregs_gradient(x, u, regularised=reg)
+        best = min(best, c.stats()["ms_gradient"])
+    return best, g
+
+
+for name, k in (("cameraman_128_5", 1), ("faces_train_128_10", 10)):
+    t, f = data(name, k)
+    with bp.Context([0], 64) as c:
+        c.set_dataset((t, f))
+        xs = np.array([0.001, 0.001, 0.001])
+        xp = 0.001 * np.ones((2, 2, 3)); xp[1, 0, :] *= 1.5
+        us = c.sumregs_denoise(None, xs, bp.sumregs_pdps_opts(maxiter=2000))
+        up = c.sumregs_denoise(None, xp, bp.sumregs_pdps_opts(maxiter=2000))
+        os.environ["BPLTV_SUMREGS_REG_LU"] = "0"
+        ms_c, g_c = timed(c, xs, True, us)
+        os.environ["BPLTV_SUMREGS_REG_LU"] = "1"
+        ms_l, g_l = timed(c, xs, True, us)
+        os.environ.pop("BPLTV_SUMREGS_REG_LU")
+        print("%s x%d scalar reg: Cholesky %.1f ms, band LU %.1f ms, rel diff %.2e" %
+              (name, k, ms_c, ms_l, np.abs(g_c - g_l).max() / np.abs(g_c).max()), flush=True)
+        ms_p, g_p = timed(c, xp, True, up)
+        print("%s x%d patch reg (band LU): %.1f ms" % (name, k, ms_p), flush=True)
+        ms_n, _ = timed(c, xs, False, us)
+        ms_pn, _ = timed(c, xp, False, up)
+        print("%s x%d non-reg: scalar %.1f ms, patch %.1f ms" % (name, k, ms_n, ms_pn), flush=True)
+t, f = bp.synthetic_dataset(256, 256, 2, seed=20240602)
+with bp.Context([0], 64) as c:
+    c.set_dataset((t, f))
+    xp = 0.01 * np.ones((2, 2, 3)); xp[1, 0, :] *= 1.5
+    up = c.sumregs_denoise(None, xp, bp.sumregs_pdps_opts(maxiter=500))
+    ms_p, g_p = timed(c, xp, True, up, reps=2)
+    print("synthetic 256x256 x2 patch reg (band LU): %.1f ms, finite %s" % (ms_p, bool(np.all(np.isfinite(g_p)))), flush=True)
