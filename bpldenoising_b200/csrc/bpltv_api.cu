@@ -623,6 +623,29 @@ static int run_sumregs_pdps(Dev &d, const Real *f, int M, int N, int O, const Re
     RC_TRY(d.x[1].ensure(n * sizeof(Real)));
     RC_TRY(d.sry.ensure(6 * n * sizeof(Real)));
     RC_TRY(upload_steps<Real>(d, o, st));
+    const bool strict = o.arith == BPLTV_ARITH_STRICT;
+    // Few images of a size that fits on chip: the whole solve in ONE launch, one image per thread-block
+    // cluster (sumregs_resident_kernel); otherwise two streaming launches per iteration.  o.kernel:
+    // GENERIC / MARCH force the streaming pair, RESIDENT requires the resident kernel, AUTO decides.
+    int kern = o.kernel;
+    if (kern == BPLTV_KERNEL_AUTO) kern = env_int("BPLTV_PDPS_KERNEL", 0);
+    const bool want_res = kern == BPLTV_KERNEL_RESIDENT ||
+                          (kern == BPLTV_KERNEL_AUTO && (long long)O * 8 <= (long long)env_int("BPLTV_RESIDENT_MAX_WAVES", 4) * d.sm_count);
+    if (want_res && o.maxiter > 0) {
+        SumRegsResArgs<Real> ra;
+        ra.f = f; ra.u_out = d.x[0].as<Real>(); ra.amap = amap; ra.steps = d.steps.as<StepConsts<Real>>();
+        for (int k = 0; k < 3; ++k) ra.alpha[k] = alpha[k];
+        ra.maxiter = o.maxiter; ra.M = M; ra.N = N; ra.O = O; ra.init_mode = o.init_mode; ra.NC = 0;
+        cudaError_t re = launch_sumregs_resident<Real>(ra, d.smem_optin, amap != nullptr, strict, st);
+        if (re == cudaSuccess) {
+            d.launches += 1;
+            *u_result = d.x[0].as<Real>();
+            return 0;
+        }
+        cudaGetLastError();
+        if (kern == BPLTV_KERNEL_RESIDENT)
+            return fail(BPLTV_ERR_ARG, "the resident sum-of-regularisers kernel does not take this shape: %s", cudaGetErrorString(re));
+    }
     if (o.init_mode) CU_TRY(cudaMemcpyAsync(d.x[0].p, f, n * sizeof(Real), cudaMemcpyDeviceToDevice, st));
     else CU_TRY(cudaMemsetAsync(d.x[0].p, 0, n * sizeof(Real), st));
     CU_TRY(cudaMemsetAsync(d.sry.p, 0, 6 * n * sizeof(Real), st));
@@ -630,7 +653,6 @@ static int run_sumregs_pdps(Dev &d, const Real *f, int M, int N, int O, const Re
     a.x = d.x[0].as<Real>(); a.xb = d.x[1].as<Real>(); a.f = f; a.y = d.sry.as<Real>(); a.amap = amap;
     for (int k = 0; k < 3; ++k) a.alpha[k] = alpha[k];
     a.M = M; a.N = N; a.O = O;
-    const bool strict = o.arith == BPLTV_ARITH_STRICT;
     const unsigned grid = (unsigned)((n + 255) / 256);
     const StepConsts<Real> *hsteps = reinterpret_cast<const StepConsts<Real> *>(d.steps_host.data());
     for (int it = 0; it < o.maxiter; ++it) {

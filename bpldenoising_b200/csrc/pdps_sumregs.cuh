@@ -12,6 +12,11 @@
 // One IEEE operation per operator of the reference expression in strict mode (bit-identical to
 // oracle/sumregs.py), FMA / rsqrt in fast mode.
 #pragma once
+#include <cooperative_groups.h>
+
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace bpltv {
@@ -98,6 +103,245 @@ __global__ void __launch_bounds__(256) sumregs_dual_kernel(const SumRegsArgs<Rea
         dual_update<Real, STRICT, false>(v1, v2, d1[op], d2[op], al, (Real)0, a.sc);
         *p1 = v1; *p2 = v2;
     }
+}
+
+// ---------------------------------------------------------------------------
+// Resident variant: one launch = the complete solve, one image per thread-block cluster (the
+// sum-of-regularisers counterpart of pdps_resident.cuh; at the reference's 128×128 the streaming pair above
+// is launch-bound: 10 000 launches ≈ 41 ms for 5000 iterations).  CTA `rank` owns NC consecutive columns;
+// x and f (and the three λ values of a map) stay in registers, x̄ and the six dual planes in shared memory
+// with the halo columns their stencils need: x̄ ±1 column, y[1] (forward, component 2) one to the left,
+// y[3] (backward, component 2) one to the right, y[5] (centred, component 2) both.  Owners PUSH their
+// boundary columns into the neighbours' halo slots through distributed shared memory; two cluster
+// barriers per iteration order the pushes against the reads (primal phase reads y / writes x̄, dual phase
+// reads x̄ / writes y).  Same operations in the same order as the streaming kernels: bit-identical.
+// ---------------------------------------------------------------------------
+constexpr int SRR_THREADS = 512;
+
+template <typename Real>
+struct SumRegsResArgs {
+    const Real *f;
+    Real *u_out;
+    const Real *amap;            // 3 maps of M·N or nullptr
+    const StepConsts<Real> *steps;
+    Real alpha[3];
+    int maxiter, M, N, O, init_mode, NC;
+};
+
+template <typename Real, int KP, bool MAP, bool STRICT>
+__global__ void __launch_bounds__(SRR_THREADS, 1) sumregs_resident_kernel(const SumRegsResArgs<Real> a)
+{
+    namespace cg = cooperative_groups;
+    typedef Ar<Real, STRICT> A;
+    extern __shared__ __align__(16) unsigned char srr_smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CS = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int o = blockIdx.x / CS;
+    const int M = a.M, N = a.N, NC = a.NC;
+    const int c_begin = rank * NC;
+    const int nc = min(NC, N - c_begin);          // ≥ 1 by the plan
+    // planes (column pitch M): xb NC+2 columns (slot = local column + 1), y0 NC, y1 NC+1 (slot = c + 1),
+    // y2 NC, y3 NC+1 (slot = c), y4 NC, y5 NC+2 (slot = c + 1)
+    Real *xb = reinterpret_cast<Real *>(srr_smem);
+    Real *y0 = xb + (size_t)(NC + 2) * M;
+    Real *y1 = y0 + (size_t)NC * M;
+    Real *y2 = y1 + (size_t)(NC + 1) * M;
+    Real *y3 = y2 + (size_t)NC * M;
+    Real *y4 = y3 + (size_t)(NC + 1) * M;
+    Real *y5 = y4 + (size_t)NC * M;
+    const int total = (7 * NC + 6) * M;
+    for (int k = threadIdx.x; k < total; k += blockDim.x) xb[k] = (Real)0;
+    // the neighbours' planes (a left neighbour is never the last rank, so its column count is NC)
+    Real *xb_l = rank > 0 ? cluster.map_shared_rank(xb, rank - 1) : nullptr;
+    Real *xb_r = rank + 1 < CS ? cluster.map_shared_rank(xb, rank + 1) : nullptr;
+    Real *y1_r = rank + 1 < CS ? cluster.map_shared_rank(y1, rank + 1) : nullptr;
+    Real *y3_l = rank > 0 ? cluster.map_shared_rank(y3, rank - 1) : nullptr;
+    Real *y5_l = rank > 0 ? cluster.map_shared_rank(y5, rank - 1) : nullptr;
+    Real *y5_r = rank + 1 < CS ? cluster.map_shared_rank(y5, rank + 1) : nullptr;
+
+    const size_t plane = (size_t)M * N;
+    const size_t img = (size_t)o * plane;
+    const int npix = nc * M;
+    Real x[KP], f[KP], al[KP][3];
+    int pos[KP];          // c·M + i of the thread's k-th pixel
+    unsigned flg[KP];     // 1 valid, 2 up, 4 down, 8 left, 16 right, 32 first local column, 64 last local column
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        const int l = threadIdx.x + k * blockDim.x;
+        x[k] = f[k] = (Real)0;
+        al[k][0] = a.alpha[0]; al[k][1] = a.alpha[1]; al[k][2] = a.alpha[2];
+        pos[k] = 0; flg[k] = 0;
+        if (l < npix) {
+            const int c = l / M, i = l - c * M, jg = c_begin + c;
+            pos[k] = l;
+            flg[k] = 1u | (i > 0 ? 2u : 0u) | (i + 1 < M ? 4u : 0u) | (jg > 0 ? 8u : 0u) | (jg + 1 < N ? 16u : 0u) |
+                     (c == 0 ? 32u : 0u) | (c == nc - 1 ? 64u : 0u);
+            const size_t q = (size_t)c_begin * M + l;           // pixel index inside the image
+            f[k] = a.f[img + q];
+            x[k] = a.init_mode ? f[k] : (Real)0;
+            if (MAP) { al[k][0] = a.amap[q]; al[k][1] = a.amap[plane + q]; al[k][2] = a.amap[2 * plane + q]; }
+        }
+    }
+    cluster.sync();   // planes zeroed everywhere before anyone pushes into a halo
+
+    const Real z = (Real)0, half = (Real)0.5;
+    for (int it = 0; it < a.maxiter; ++it) {
+        const StepConsts<Real> sc = a.steps[it];
+        // ---- primal: x ← prox, x̄ ← over-relaxation (reads the duals, writes x̄) ----
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            const unsigned fl = flg[k];
+            if (!(fl & 1u)) continue;
+            const bool up = fl & 2u, dn = fl & 4u, lf = fl & 8u, rt = fl & 16u, first = fl & 32u, last = fl & 64u;
+            const int p0 = pos[k], p1 = p0 + M;
+            const Real tF = A::add(A::sub(up ? y0[p0 - 1] : z, y0[p0]), A::sub(lf ? y1[p0] : z, y1[p1]));
+            const Real tB = A::add(A::sub(y2[p0], dn ? y2[p0 + 1] : z), A::sub(y3[p0], rt ? y3[p1] : z));
+            const Real tC = A::add(A::mul(half, A::sub(up ? y4[p0 - 1] : z, dn ? y4[p0 + 1] : z)),
+                                   A::mul(half, A::sub(lf ? y5[p0] : z, rt ? y5[p1 + M] : z)));
+            const Real dx = A::add(A::add(tF, tB), tC);
+            const Real xo = x[k];
+            Real xn, xbar;
+            if (STRICT) {
+                Real t = A::sub(dx, f[k]);
+                t = A::mul(sc.tau, t);
+                t = A::sub(xo, t);
+                xn = div_by_const<Real>(t, sc.one_p_tau, sc.rcp_one_p_tau);
+                xbar = A::sub(A::mul(sc.one_p_omega, xn), A::mul(sc.omega, xo));
+            } else {
+                xn = fma_(xo, sc.inv_one_p_tau, -sc.tau_over_one_p_tau * (dx - f[k]));
+                xbar = fma_(sc.one_p_omega, xn, -sc.omega * xo);
+            }
+            x[k] = xn;
+            xb[p1] = xbar;
+            if (first && xb_l) xb_l[(NC + 1) * M + p0] = xbar;        // the left CTA's right halo (first column: p0 = row)
+            if (last && xb_r) xb_r[p0 - (nc - 1) * M] = xbar;         // the right CTA's left halo
+        }
+        cluster.sync();
+        // ---- dual: y_k ← P_{α_k}(y_k + σ∇_k x̄) (reads x̄, writes the duals) ----
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            const unsigned fl = flg[k];
+            if (!(fl & 1u)) continue;
+            const bool up = fl & 2u, dn = fl & 4u, lf = fl & 8u, rt = fl & 16u, first = fl & 32u, last = fl & 64u;
+            const int p0 = pos[k], p1 = p0 + M;
+            const Real cc = xb[p1];
+            const Real xu = up ? xb[p1 - 1] : z, xd = dn ? xb[p1 + 1] : z;
+            const Real xl = lf ? xb[p0] : z, xr = rt ? xb[p1 + M] : z;
+            Real d1[3], d2[3];
+            d1[0] = dn ? A::sub(xd, cc) : z;                               // ∇ᶠ (S4)
+            d2[0] = rt ? A::sub(xr, cc) : z;
+            d1[1] = up ? A::sub(cc, xu) : z;                               // ∇ᵇ (S10)
+            d2[1] = lf ? A::sub(cc, xl) : z;
+            d1[2] = (up && dn) ? A::mul(half, A::sub(xd, xu)) : z;         // ∇ᶜ (S11)
+            d2[2] = (lf && rt) ? A::mul(half, A::sub(xr, xl)) : z;
+            Real v1, v2;
+            v1 = y0[p0]; v2 = y1[p1];
+            dual_update<Real, STRICT, false>(v1, v2, d1[0], d2[0], al[k][0], (Real)0, sc);
+            y0[p0] = v1; y1[p1] = v2;
+            if (last && y1_r) y1_r[p0 - (nc - 1) * M] = v2;                       // forward, component 2: the right CTA reads column c0−1
+            v1 = y2[p0]; v2 = y3[p0];
+            dual_update<Real, STRICT, false>(v1, v2, d1[1], d2[1], al[k][1], (Real)0, sc);
+            y2[p0] = v1; y3[p0] = v2;
+            if (first && y3_l) y3_l[NC * M + p0] = v2;                   // backward, component 2: the left CTA reads column c0+NC
+            v1 = y4[p0]; v2 = y5[p1];
+            dual_update<Real, STRICT, false>(v1, v2, d1[2], d2[2], al[k][2], (Real)0, sc);
+            y4[p0] = v1; y5[p1] = v2;
+            if (first && y5_l) y5_l[(NC + 1) * M + p0] = v2;             // centred, component 2: both neighbours
+            if (last && y5_r) y5_r[p0 - (nc - 1) * M] = v2;
+        }
+        cluster.sync();
+    }
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        const int l = threadIdx.x + k * blockDim.x;
+        if (l < npix) a.u_out[img + (size_t)c_begin * M + l] = x[k];
+    }
+}
+
+struct SumRegsResPlan {
+    bool ok = false;
+    int CS = 0, NC = 0, KP = 0;
+    size_t smem = 0;
+};
+
+template <typename Real>
+static inline SumRegsResPlan sumregs_resident_plan(size_t smem_optin, int M, int N, int cs_max)
+{
+    SumRegsResPlan p;
+    const int cs_cands[5] = {16, 8, 4, 2, 1};
+    for (int ci = 0; ci < 5; ++ci) {
+        const int CS = cs_cands[ci];
+        if (CS > cs_max || CS > N) continue;
+        const int NC = (N + CS - 1) / CS;
+        if ((CS - 1) * NC >= N) continue;                 // every rank owns at least one column
+        const int KP = (NC * M + SRR_THREADS - 1) / SRR_THREADS;
+        if (KP > 8) continue;
+        const size_t smem = (size_t)(7 * NC + 6) * M * sizeof(Real);
+        if (smem > smem_optin) continue;
+        p.ok = true; p.CS = CS; p.NC = NC; p.KP = KP <= 1 ? 1 : (KP <= 2 ? 2 : (KP <= 4 ? 4 : 8)); p.smem = smem;
+        return p;
+    }
+    return p;
+}
+
+template <typename Real, int KP>
+static inline cudaError_t launch_sumregs_resident_kp(const SumRegsResArgs<Real> &a, const SumRegsResPlan &p, bool map,
+                                                     bool strict, cudaStream_t st)
+{
+    void (*fn)(const SumRegsResArgs<Real>);
+    if (map) fn = strict ? sumregs_resident_kernel<Real, KP, true, true> : sumregs_resident_kernel<Real, KP, true, false>;
+    else fn = strict ? sumregs_resident_kernel<Real, KP, false, true> : sumregs_resident_kernel<Real, KP, false, false>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    if (e != cudaSuccess) return e;
+    if (p.CS > 8) {
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(a.O * p.CS));
+    cfg.blockDim = dim3(SRR_THREADS);
+    cfg.dynamicSmemBytes = p.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)p.CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg) != cudaSuccess || nclusters < 1 ||
+        (p.CS > 8 && nclusters < a.O)) {     // 16-CTA clusters only when the whole batch is co-resident
+        cudaGetLastError();
+        return cudaErrorLaunchOutOfResources;
+    }
+    return cudaLaunchKernelEx(&cfg, fn, a);
+}
+
+// cudaSuccess: launched.  cudaErrorInvalidValue / cudaErrorLaunchOutOfResources: not eligible (stream instead).
+template <typename Real>
+static inline cudaError_t launch_sumregs_resident(SumRegsResArgs<Real> a, size_t smem_optin, bool map, bool strict,
+                                                  cudaStream_t st)
+{
+    const char *cs_env = getenv("BPLTV_RESIDENT_CS");
+    const int cs_cap = cs_env && *cs_env ? atoi(cs_env) : 16;
+    const int caps[2] = {std::min(cs_cap, 16), std::min(cs_cap, 8)};
+    cudaError_t last = cudaErrorInvalidValue;
+    for (int t = 0; t < 2; ++t) {
+        if (t == 1 && caps[1] == caps[0]) break;
+        const SumRegsResPlan p = sumregs_resident_plan<Real>(smem_optin, a.M, a.N, caps[t]);
+        if (!p.ok) continue;
+        if (t == 1 && p.CS > 8) continue;
+        a.NC = p.NC;
+        last = p.KP == 1 ? launch_sumregs_resident_kp<Real, 1>(a, p, map, strict, st)
+             : p.KP == 2 ? launch_sumregs_resident_kp<Real, 2>(a, p, map, strict, st)
+             : p.KP == 4 ? launch_sumregs_resident_kp<Real, 4>(a, p, map, strict, st)
+                         : launch_sumregs_resident_kp<Real, 8>(a, p, map, strict, st);
+        if (last == cudaSuccess) return last;
+        cudaGetLastError();
+    }
+    return last;
 }
 
 }  // namespace bpltv

@@ -36,6 +36,41 @@ def test_sumregs_denoise_is_bit_identical_to_the_oracle(bp, ctx, ctx32, sr, shap
     assert np.array_equal(up, sr.sumregs_pdps(f, maps, maxiter=40)), shape
 
 
+def test_sumregs_resident_and_streaming_kernels_agree(bp, ctx, ctx32, sr, monkeypatch):
+    """The cluster-resident solve (one launch, one image per thread-block cluster, halo columns pushed through
+    distributed shared memory) against the streaming pair (two launches per iteration) and the oracle: bit-identical
+    for every cluster size, with ragged column splits, a λ-map, fp32 and fast arithmetic."""
+    from oracle import oracle as orc
+    M, N, O = 40, 37, 3
+    rng = np.random.default_rng(5)
+    f = np.asfortranarray(np.round(rng.uniform(0, 1, (M, N, O)) * 255) / 255)
+    x = np.array([0.03, 0.012, 0.05])
+    xp = rng.uniform(0.005, 0.08, (2, 3, 3))
+    maps = [orc.patch_upsample(xp[:, :, k], M, N) for k in range(3)]
+    ref = sr.sumregs_pdps(f, list(x), maxiter=50)
+    refp = sr.sumregs_pdps(f, maps, maxiter=50)
+    ref32 = sr.sumregs_pdps(f, list(x), maxiter=50, dtype=np.float32)
+    stream = ctx.sumregs_denoise(f, x, bp.sumregs_pdps_opts(maxiter=50, kernel=bp.KERNEL_GENERIC))
+    assert np.array_equal(stream, ref) and ctx.stats()["kernel_launches"] == 2 * 50
+    for cs in (1, 2, 4, 8, 16):
+        monkeypatch.setenv("BPLTV_RESIDENT_CS", str(cs))
+        u = ctx.sumregs_denoise(f, x, bp.sumregs_pdps_opts(maxiter=50, kernel=bp.KERNEL_RESIDENT))
+        assert np.array_equal(u, ref) and ctx.stats()["kernel_launches"] == 1, cs
+        up = ctx.sumregs_denoise(f, xp, bp.sumregs_pdps_opts(maxiter=50, kernel=bp.KERNEL_RESIDENT))
+        assert np.array_equal(up, refp), cs
+        u32 = ctx32.sumregs_denoise(f, x, bp.sumregs_pdps_opts(maxiter=50, kernel=bp.KERNEL_RESIDENT))
+        assert np.array_equal(u32.astype(np.float32), ref32), cs
+        uf = ctx.sumregs_denoise(f, x, bp.sumregs_pdps_opts(maxiter=50, kernel=bp.KERNEL_RESIDENT, arith=bp.FAST))
+        assert rel_l2(uf, ref) <= 1e-10, cs
+    monkeypatch.delenv("BPLTV_RESIDENT_CS")
+    # a shape that does not fit on chip streams under AUTO and is refused under RESIDENT
+    big = np.asfortranarray(np.round(rng.uniform(0, 1, (600, 600, 1)) * 255) / 255)
+    ub = ctx.sumregs_denoise(big, x, bp.sumregs_pdps_opts(maxiter=3))
+    assert ctx.stats()["kernel_launches"] == 6 and np.array_equal(ub, sr.sumregs_pdps(big, list(x), maxiter=3))
+    with pytest.raises(bp.BpltvError):
+        ctx.sumregs_denoise(big, x, bp.sumregs_pdps_opts(maxiter=3, kernel=bp.KERNEL_RESIDENT))
+
+
 def test_sumregs_denoise_on_the_reference_dataset(bp, ctx, sr, datasets):
     t, f = datasets["cameraman_128_5"]
     x0 = np.array([0.001, 0.001, 0.001])       # α₀ of scalar_bilevel_sumregs_learn (BPLDenoising.jl:429)
@@ -183,7 +218,7 @@ def test_sumregs_learning_function_end_to_end(bp, ctx, sr, datasets):
     assert np.array_equal(u, ref) and abs(cost - orc.cost(ref, t)) <= 1e-12 * cost
     assert g.shape == (3,) and np.all(np.isfinite(g))
     st = ctx.stats()
-    assert st["ms_gradient"] > 0 and st["kernel_launches"] == 2 * 300 + 2 + 5
+    assert st["ms_gradient"] > 0 and st["kernel_launches"] == 1 + 2 + 5      # resident solve, cost, gradient
     u2, cost2, g2 = bp.sumregs_learning_function(x0, (t, f), 1e-4, ctx=ctx, maxiter=300)  # Δ ≤ Δt: regularised
     assert np.array_equal(u2, u) and cost2 == cost and not np.allclose(g, g2)
     lit = sr.sumregs_gradient_reg(x0, ref[:, :, 0], t[:, :, 0], refine=3)

@@ -1,7 +1,6 @@
 set -x
 mkdir -p gpurun_out
-L=gpurun_out/lu_check2.log
-( timeout 900 python -m pytest tests/test_gpu_sumregs.py -x -q 2>&1 | tail -5
-  BPLTV_GRAD_REG_LU=1 timeout 900 python -m pytest tests/test_gpu_gradient.py -x -q 2>&1 | tail -8
-  timeout 900 python tools/time_tv_grad_reg.py 2>&1 | tail -20 ) > $L 2>&1
+L=gpurun_out/srr_check.log
+( timeout 900 python -m pytest tests/test_gpu_sumregs.py -x -q 2>&1 | tail -25
+  timeout 600 python tools/time_sumregs_pdps128.py 2>&1 | tail -20 ) > $L 2>&1
 tail -60 $L
