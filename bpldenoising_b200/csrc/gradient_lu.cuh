@@ -25,6 +25,51 @@ struct LuProblem {
 // ---------------------------------------------------------------------------
 // host driver of the node-space band LU
 // ---------------------------------------------------------------------------
+// CTAs per image of the LU factorisation: as many (power of two, ≤ 8) as leave every image of the wave its own
+// cluster; one when the trailing window has too few 32×32 tiles to share.  BPLTV_LU_CLUSTER overrides.
+static inline int lu_cluster_ctas(int images_in_wave, int sm_count, int bw)
+{
+    const char *env = getenv("BPLTV_LU_CLUSTER");
+    if (env && *env) { const int c = atoi(env); if (c == 1 || c == 2 || c == 4 || c == 8 || c == 16) return c; }
+    if (bw < 200) return 1;
+    int C = 1;
+    while (C < 8 && 2 * C * images_in_wave <= sm_count) C *= 2;
+    return C;
+}
+
+static inline cudaError_t launch_lu_factor(const LuSlots &ws, int cnt, int C, size_t smem, cudaStream_t st)
+{
+    while (C > 1) {
+        cudaError_t e = cudaFuncSetAttribute(lu_factor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess && C > 8)
+            e = cudaFuncSetAttribute(lu_factor_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(cnt * C));
+        cfg.blockDim = dim3(LU_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)C;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int nclusters = 0;
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&nclusters, lu_factor_kernel<true>, &cfg);
+        if (e == cudaSuccess && nclusters >= 1 && (C <= 8 || nclusters >= cnt)) {
+            e = cudaLaunchKernelEx(&cfg, lu_factor_kernel<true>, ws);
+            if (e == cudaSuccess) return e;
+        }
+        cudaGetLastError();
+        C /= 2;      // not schedulable as asked: smaller clusters, finally the single-CTA kernel
+    }
+    cudaError_t e = cudaFuncSetAttribute(lu_factor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    lu_factor_kernel<false><<<cnt, LU_THREADS, smem, st>>>(ws);
+    return cudaGetLastError();
+}
+
 template <typename Real>
 static int run_gradient_lu(GradWork &w, const LuProblem<Real> &gp, int sm_count, size_t smem_optin, cudaStream_t st,
                             double *d_grad_out, long long *launches)
@@ -78,9 +123,7 @@ static int run_gradient_lu(GradWork &w, const LuProblem<Real> &gp, int sm_count,
     for (int k = 0; k < 3; ++k) pr.alpha[k] = gp.alpha[k];
     pr.gamma = gp.gamma; pr.lm = gp.lm; pr.ln = gp.ln;
     pr.refine = 3;
-    cudaError_t e = cudaFuncSetAttribute(lu_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(lu3_solve_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem);
+    cudaError_t e = cudaFuncSetAttribute(lu3_solve_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem);
     if (e != cudaSuccess) { cudaGetLastError(); return grad_fail(w, -2, std::string("band-LU kernel attributes: ") + cudaGetErrorString(e)); }
     const int chunks = std::max(1, std::min(64, (N + 255) / 256));
     for (int img0 = 0; img0 < gp.O; img0 += slots) {
@@ -88,7 +131,8 @@ static int run_gradient_lu(GradWork &w, const LuProblem<Real> &gp, int sm_count,
         cudaMemsetAsync(ws.ab, 0, ws.ab_stride * 8 * cnt, st);
         lu3_classify_kernel<Real><<<dim3(cnt, chunks), 256, 0, st>>>(ws, pr.gamma, gp.u, gp.ubar, img0);
         lu3_assemble_kernel<Real><<<dim3(cnt, chunks), 256, 0, st>>>(ws, pr, gp.alpha_maps);
-        lu_factor_kernel<<<cnt, LU_THREADS, fsmem, st>>>(ws);
+        e = launch_lu_factor(ws, cnt, lu_cluster_ctas(cnt, sm_count, ws.bw), fsmem, st);
+        if (e != cudaSuccess) { cudaGetLastError(); return grad_fail(w, -2, std::string("band-LU factor launch failed: ") + cudaGetErrorString(e)); }
         lu3_solve_kernel<Real><<<cnt, LU_THREADS, ssmem, st>>>(ws, pr, gp.alpha_maps, (double *)w.out_img,
                                                               (double *)w.relres, img0, vec_in_smem ? 1 : 0);
         *launches += 4;

@@ -23,6 +23,10 @@
 // This header holds device code only and depends on sumregs_stencils.cuh alone: tests/emu/ compiles it with
 // g++ and runs the kernels on OS threads (CPU check of the index arithmetic and barriers; no GPU needed).
 #pragma once
+#ifndef BPLTV_EMU
+#include <cooperative_groups.h>
+#endif
+
 #include "sumregs_stencils.cuh"
 
 namespace bpltv {
@@ -56,6 +60,19 @@ struct Lu3Params {
 #define LU_A16(p) (emu::check_aligned16(p), (p))
 #else
 #define LU_A16(p) (p)
+#endif
+
+// dynamic shared memory and the thread-block cluster, as the GPU or as the thread emulation provides them
+#ifdef BPLTV_EMU
+#define LU_DYN_SMEM(name) double *name = emu::dyn_smem()
+static inline int lu_cluster_rank() { return emu::cluster_rank(); }
+static inline int lu_cluster_size() { return emu::cluster_size(); }
+static inline void lu_cluster_sync() { emu::cluster_sync(); }
+#else
+#define LU_DYN_SMEM(name) extern __shared__ __align__(16) double name[]
+static __device__ __forceinline__ int lu_cluster_rank() { return (int)cooperative_groups::this_cluster().block_rank(); }
+static __device__ __forceinline__ int lu_cluster_size() { return (int)cooperative_groups::this_cluster().num_blocks(); }
+static __device__ __forceinline__ void lu_cluster_sync() { cooperative_groups::this_cluster().sync(); }
 #endif
 
 static __device__ __forceinline__ double lu_warp_sum(double v)
@@ -198,11 +215,19 @@ static inline size_t lu_factor_smem(int bw)
     return (size_t)(LU_NB * LU_DP + LU_NB + 2 * LU_NB * lu_panel_pitch(bw)) * sizeof(double);
 }
 
+// CL: the image is factorised by a thread-block CLUSTER of csize CTAs (one SM each).  Every CTA forms the
+// diagonal block and both panels redundantly in its own shared memory (cheap), the 32×32 tiles of the
+// trailing window are dealt over all warps of the cluster, and two cluster barriers per block step order the
+// traffic through global memory: one after every CTA has READ the step's inputs (then rank 0 alone writes the
+// factored block and panels back in place), one after the trailing update.  Same operations per entry as the
+// single-CTA kernel: identical bits for every cluster size.
+template <bool CL>
 __global__ void __launch_bounds__(LU_THREADS, 1) lu_factor_kernel(LuSlots ws)
 {
-    extern __shared__ __align__(16) double lu_fsm[];
+    LU_DYN_SMEM(lu_fsm);
     constexpr int NB = LU_NB, DP = LU_DP;
-    const int slot = blockIdx.x;
+    const int crank = CL ? lu_cluster_rank() : 0, csize = CL ? lu_cluster_size() : 1;
+    const int slot = CL ? (int)blockIdx.x / csize : (int)blockIdx.x;
     const int N = ws.N, bw = ws.bw, bwx = ws.bwx, LD = ws.LD;
     double *ab = ws.ab + ws.ab_stride * slot;
     const int lsp = (bw + 32 + 3) & ~3;           // pitch of both panels (32 spare entries: ragged tiles read, never use them)
@@ -218,8 +243,8 @@ __global__ void __launch_bounds__(LU_THREADS, 1) lu_factor_kernel(LuSlots ws)
         const int nb = min(NB, N - k0);
         const int R = min(bw, N - k0 - nb);       // rows below / columns right of the block inside the band
         // ---- diagonal block: load, factor in warp 0 (identity padding for a short last block) ----
-        if (tid < NB * NB) {
-            const int r = tid / NB, c = tid - r * NB;
+        for (int e = tid; e < NB * NB; e += blockDim.x) {
+            const int r = e / NB, c = e - r * NB;
             D[r * DP + c] = (r < nb && c < nb) ? ab[(size_t)(k0 + r) * LD + (c - r + bwx)] : (r == c ? 1.0 : 0.0);
         }
         __syncthreads();
@@ -243,8 +268,8 @@ __global__ void __launch_bounds__(LU_THREADS, 1) lu_factor_kernel(LuSlots ws)
             if (lane < NB) rD[lane] = 1.0 / D[lane * DP + lane];
         }
         __syncthreads();
-        if (tid < NB * NB) {   // the factored block back to the band
-            const int r = tid / NB, c = tid - r * NB;
+        if (!CL) for (int e = tid; e < NB * NB; e += blockDim.x) {   // the factored block back to the band (cluster: after the read barrier below)
+            const int r = e / NB, c = e - r * NB;
             if (r < nb && c < nb) ab[(size_t)(k0 + r) * LD + (c - r + bwx)] = D[r * DP + c];
         }
         // ---- L21 = A21 U11⁻¹ (one thread per row), U12 = L11⁻¹ A12 (one thread per column) ----
@@ -267,7 +292,7 @@ __global__ void __launch_bounds__(LU_THREADS, 1) lu_factor_kernel(LuSlots ws)
                 }
 #pragma unroll
                 for (int c = 0; c < NB; c += 2) {
-                    *reinterpret_cast<double2 *>(LU_A16(rowp + c)) = make_double2(x[c], x[c + 1]);
+                    if (!CL) *reinterpret_cast<double2 *>(LU_A16(rowp + c)) = make_double2(x[c], x[c + 1]);
                     Lt[c * lsp + t] = x[c]; Lt[(c + 1) * lsp + t] = x[c + 1];
                 }
             } else {
@@ -284,15 +309,42 @@ __global__ void __launch_bounds__(LU_THREADS, 1) lu_factor_kernel(LuSlots ws)
                     y[r] = s;
                 }
 #pragma unroll
-                for (int r = 0; r < NB; ++r) { colp[(size_t)r * (LD - 1)] = y[r]; Us[r * lsp + tt] = y[r]; }
+                for (int r = 0; r < NB; ++r) {
+                    if (!CL) colp[(size_t)r * (LD - 1)] = y[r];
+                    Us[r * lsp + tt] = y[r];
+                }
             }
         }
-        __syncthreads();
+        if (CL) {
+            lu_cluster_sync();     // every CTA of the cluster has read this step's block and panels
+            if (crank == 0) {      // one writer: the factored block and panels, from shared memory
+                for (int e = tid; e < NB * NB; e += blockDim.x) {
+                    const int r = e / NB, c = e - r * NB;
+                    if (r < nb && c < nb) ab[(size_t)(k0 + r) * LD + (c - r + bwx)] = D[r * DP + c];
+                }
+                for (int t = tid; t < 2 * R; t += blockDim.x) {
+                    if (t < R) {
+                        const int gr = k0 + nb + t;
+                        double *rowp = ab + (size_t)gr * LD + (k0 - gr + bwx);
+#pragma unroll
+                        for (int c = 0; c < NB; c += 2)
+                            *reinterpret_cast<double2 *>(LU_A16(rowp + c)) = make_double2(Lt[c * lsp + t], Lt[(c + 1) * lsp + t]);
+                    } else {
+                        const int tt = t - R, gj = k0 + nb + tt;
+                        double *colp = ab + (size_t)k0 * LD + (gj - k0 + bwx);
+#pragma unroll
+                        for (int r = 0; r < NB; ++r) colp[(size_t)r * (LD - 1)] = Us[r * lsp + tt];
+                    }
+                }
+            }
+        } else {
+            __syncthreads();
+        }
         // ---- trailing window A22 −= L21·U12: warp tiles of 32 rows × 32 columns, 8×4 per thread; per rank
         //      the thread reads 8 panel entries of Lt and 4 of Us as six 16-byte shared-memory loads ----
         const int ct = (R + 31) >> 5, ntile = ct * ct;
         const int g0 = k0 + nb;
-        for (int wt = warp; wt < ntile; wt += nwarps) {
+        for (int wt = crank * nwarps + warp; wt < ntile; wt += csize * nwarps) {
             const int tr = wt / ct, tc = wt - tr * ct;
             const int r0 = tr * 32 + rg * 8, j0 = tc * 32 + cg * 4;
             if (r0 >= R || j0 >= R) continue;
@@ -351,9 +403,9 @@ __global__ void __launch_bounds__(LU_THREADS, 1) lu_factor_kernel(LuSlots ws)
                 }
             }
         }
-        __syncthreads();
+        if (CL) lu_cluster_sync(); else __syncthreads();
     }
-    if (bad && tid == 0) ws.info[4 * slot] = 1;
+    if (bad && tid == 0 && crank == 0) ws.info[4 * slot] = 1;
 }
 
 // ---------------------------------------------------------------------------
@@ -369,8 +421,8 @@ static __device__ void lu_band_solve(const double *ab, int N, int bw, int bwx, i
     for (int k0 = 0; k0 < N; k0 += NB) {
         const int nb = min(NB, N - k0);
         const int R = min(bw, N - k0 - nb);
-        if (tid < NB * NB) {
-            const int r = tid / NB, c = tid - r * NB;
+        for (int e = tid; e < NB * NB; e += blockDim.x) {
+            const int r = e / NB, c = e - r * NB;
             D[r * DP + c] = (r < nb && c < r) ? ab[(size_t)(k0 + r) * LD + (c - r + bwx)] : 0.0;
         }
         __syncthreads();
@@ -400,8 +452,8 @@ static __device__ void lu_band_solve(const double *ab, int N, int bw, int bwx, i
         const int k0 = kb * NB;
         const int nb = min(NB, N - k0);
         const int R = min(bw, N - k0 - nb);
-        if (tid < NB * NB) {
-            const int r = tid / NB, c = tid - r * NB;
+        for (int e = tid; e < NB * NB; e += blockDim.x) {
+            const int r = e / NB, c = e - r * NB;
             D[r * DP + c] = (r < nb && c < nb && c >= r) ? ab[(size_t)(k0 + r) * LD + (c - r + bwx)] : (r == c ? 1.0 : 0.0);
         }
         for (int r = warp; r < nb; r += nwarps) {
@@ -461,7 +513,7 @@ __global__ void __launch_bounds__(LU_THREADS, 1) lu3_solve_kernel(LuSlots ws, Lu
                                                                   double *out_img, double *relres_img, int img0,
                                                                   int vec_in_smem)
 {
-    extern __shared__ __align__(16) double lu_ssm[];
+    LU_DYN_SMEM(lu_ssm);
     const int slot = blockIdx.x;
     const int n = ws.n, N = ws.N;
     const double *ab = ws.ab + ws.ab_stride * slot;

@@ -40,16 +40,32 @@ struct Warp {
     double xch[32];
     Warp() : bar(32) {}
 };
+struct Cluster {
+    std::barrier<> bar;
+    int size;
+    Cluster(int ctas, int threads) : bar((std::ptrdiff_t)ctas * threads), size(ctas) {}
+};
 struct Cta {
     std::barrier<> bar;
     std::vector<std::unique_ptr<Warp>> warps;
-    explicit Cta(int threads) : bar(threads)
+    std::vector<double> smem;      // dynamic shared memory of this CTA
+    Cluster *cluster = nullptr;
+    int rank = 0;
+    Cta(int threads, size_t smem_doubles) : bar(threads), smem(smem_doubles + 2, 0.0)
     {
         for (int w = 0; w < (threads + 31) / 32; ++w) warps.emplace_back(new Warp());
     }
 };
 inline thread_local Cta *cta = nullptr;
 inline thread_local Warp *warp = nullptr;
+inline double *dyn_smem()
+{
+    double *p = cta->smem.data();
+    return (reinterpret_cast<std::uintptr_t>(p) & 15) ? p + 1 : p;     // 16-byte aligned like the GPU's
+}
+inline int cluster_rank() { return cta->rank; }
+inline int cluster_size() { return cta->cluster ? cta->cluster->size : 1; }
+inline void cluster_sync() { if (cta->cluster) cta->cluster->bar.arrive_and_wait(); else cta->bar.arrive_and_wait(); }
 }  // namespace emu
 
 inline thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
@@ -73,19 +89,28 @@ using std::min;
 namespace emu {
 // kernel<<<grid, threads>>>(args...): blocks run one after the other, the threads of a block concurrently
 // (threads must be a multiple of 32: every warp barrier expects 32 arrivals)
+// `csize` consecutive blocks (in x) form a cluster and run concurrently; clusters run one after the other.
 template <typename F>
-void launch(dim3 grid, int threads, F &&body)
+void launch(dim3 grid, int threads, F &&body, size_t smem_doubles = 0, int csize = 1)
 {
     for (unsigned by = 0; by < grid.y; ++by)
-        for (unsigned bx = 0; bx < grid.x; ++bx) {
-            Cta c(threads);
+        for (unsigned bx0 = 0; bx0 < grid.x; bx0 += (unsigned)csize) {
+            Cluster cl(csize, threads);
+            std::vector<std::unique_ptr<Cta>> ctas;
+            for (int r = 0; r < csize; ++r) {
+                ctas.emplace_back(new Cta(threads, smem_doubles));
+                ctas.back()->rank = r;
+                ctas.back()->cluster = csize > 1 ? &cl : nullptr;
+            }
             std::vector<std::thread> ts;
-            for (int t = 0; t < threads; ++t)
-                ts.emplace_back([&, t] {
-                    threadIdx = dim3((unsigned)t); blockIdx = dim3(bx, by); blockDim = dim3((unsigned)threads); gridDim = grid;
-                    cta = &c; warp = c.warps[t / 32].get();
-                    body();
-                });
+            for (int r = 0; r < csize; ++r)
+                for (int t = 0; t < threads; ++t)
+                    ts.emplace_back([&, r, t] {
+                        threadIdx = dim3((unsigned)t); blockIdx = dim3(bx0 + (unsigned)r, by);
+                        blockDim = dim3((unsigned)threads); gridDim = grid;
+                        cta = ctas[r].get(); warp = cta->warps[t / 32].get();
+                        body();
+                    });
             for (auto &th : ts) th.join();
         }
 }

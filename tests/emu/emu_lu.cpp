@@ -7,15 +7,9 @@
 
 #include "../../bpldenoising_b200/csrc/lu_band.cuh"
 
-namespace bpltv {
-alignas(16) double lu_fsm[1 << 17];
-alignas(16) double lu_ssm[1 << 17];
-}  // namespace bpltv
-
 using namespace bpltv;
 
-// returns 0, or -1 when the problem does not fit the emulation's shared-memory arrays
-extern "C" int emu_lu_gradient(int nops, int n, const double *u, const double *ubar, const double *alpha_maps, const double *alpha3,
+extern "C" int emu_lu_gradient(int csize, int nops, int n, const double *u, const double *ubar, const double *alpha_maps, const double *alpha3,
                                double gamma, int lm, int ln, int refine, int vec_in_smem, double *out, double *relres,
                                int *pivot_flag, double *band_out /* N·LD or NULL: the assembled (unfactored) band */,
                                int *ld_out)
@@ -25,7 +19,6 @@ extern "C" int emu_lu_gradient(int nops, int n, const double *u, const double *u
     ws.n = n; ws.N = N; ws.nops = nops; ws.bw = std::min(nops == 1 ? n : 2 * n, N - 1); ws.bwx = ws.bw + LU_NB; ws.LD = 2 * ws.bwx + 1;
     ws.ab_stride = ((size_t)N * ws.LD + 3) & ~(size_t)3; ws.pix_stride = (size_t)LU_PLANES * N;
     if (ld_out) *ld_out = ws.LD;
-    if (lu_factor_smem(ws.bw) > sizeof lu_fsm || lu_solve_smem(N, vec_in_smem != 0) > sizeof lu_ssm) return -1;
     std::vector<double> ab_store(ws.ab_stride + 2, 0.0), pix(ws.pix_stride, 0.0);
     int info[4] = {0, 0, 0, 0};
     double *abp = ab_store.data(); if (reinterpret_cast<std::uintptr_t>(abp) & 15) ++abp;   // 16-byte aligned like cudaMalloc
@@ -37,10 +30,12 @@ extern "C" int emu_lu_gradient(int nops, int n, const double *u, const double *u
     emu::launch(dim3(1, chunks), 256, [&] { lu3_classify_kernel<double>(ws, gamma, u, ubar, 0); });
     emu::launch(dim3(1, chunks), 256, [&] { lu3_assemble_kernel<double>(ws, pr, alpha_maps); });
     if (band_out) std::memcpy(band_out, abp, ws.ab_stride * sizeof(double));
-    emu::launch(dim3(1), LU_THREADS, [&] { lu_factor_kernel(ws); });
+    if (csize > 1) emu::launch(dim3(csize), LU_THREADS, [&] { lu_factor_kernel<true>(ws); }, lu_factor_smem(ws.bw) / 8, csize);
+    else emu::launch(dim3(1), LU_THREADS, [&] { lu_factor_kernel<false>(ws); }, lu_factor_smem(ws.bw) / 8);
     std::vector<double> out_img(nops * lm * ln, 0.0);
     double rr = -1.0;
-    emu::launch(dim3(1), LU_THREADS, [&] { lu3_solve_kernel<double>(ws, pr, alpha_maps, out_img.data(), &rr, 0, vec_in_smem); });
+    emu::launch(dim3(1), LU_THREADS, [&] { lu3_solve_kernel<double>(ws, pr, alpha_maps, out_img.data(), &rr, 0, vec_in_smem); },
+                lu_solve_smem(N, vec_in_smem != 0) / 8);
     std::memcpy(out, out_img.data(), out_img.size() * sizeof(double));
     *relres = rr;
     *pivot_flag = info[0];

@@ -45,7 +45,7 @@ def _case(n, seed):
     return np.asfortranarray(t), u
 
 
-def _run(lib, n, u, t, maps, alpha3, gamma, grid, vec_in_smem, want_band=False, nops=3):
+def _run(lib, n, u, t, maps, alpha3, gamma, grid, vec_in_smem, want_band=False, nops=3, csize=1):
     N = n * n
     bw = min(n if nops == 1 else 2 * n, N - 1)
     LD = 2 * (bw + 16) + 1
@@ -54,7 +54,7 @@ def _run(lib, n, u, t, maps, alpha3, gamma, grid, vec_in_smem, want_band=False, 
     rr, pf, ld = C.c_double(), C.c_int(), C.c_int()
     am = None if maps is None else np.concatenate([m.flatten(order="F") for m in maps])
     a3 = None if alpha3 is None else np.asarray(alpha3, dtype=np.float64)
-    rc = lib.emu_lu_gradient(nops, n, _ptr(u.flatten(order="F")), _ptr(t.flatten(order="F")), _ptr(am), _ptr(a3),
+    rc = lib.emu_lu_gradient(csize, nops, n, _ptr(u.flatten(order="F")), _ptr(t.flatten(order="F")), _ptr(am), _ptr(a3),
                              C.c_double(gamma), grid[0], grid[1], 3, int(vec_in_smem), _ptr(out), C.byref(rr),
                              C.byref(pf), _ptr(band), C.byref(ld))
     assert rc == 0 and ld.value == LD and pf.value == 0
@@ -117,3 +117,17 @@ def test_band_lu_tv_gradient_reg_on_the_thread_emulation():
     gotp, relres, _, _ = _run(lib, n, u, t, [amap], None, 1e8, (2, 2), 0, nops=1)
     litp = orc.gradient_reg_patch(amap, (2, 2), u, t, refine=3)
     assert np.all(np.abs(gotp[:, :, 0] - litp) <= 1e-9 * np.abs(litp).max()), (gotp, litp)
+
+
+def test_band_lu_cluster_factorisation_is_invisible_on_the_thread_emulation():
+    """lu_factor_kernel<CL = true>: the trailing tiles dealt over a cluster of CTAs, two cluster barriers per block
+    step, one writer — the same bits as the single-CTA kernel (n = 20: 2×2 warp tiles of 32×32 per step)."""
+    lib = _build(64)
+    n = 20
+    t, u = _case(n, 3)
+    xp = np.stack([np.array([[0.03, 0.05], [0.02, 0.04]]) * s for s in (1.0, 0.7, 1.3)], axis=2)
+    maps = [np.asfortranarray(orc.patch_upsample(xp[:, :, k], n, n)) for k in range(3)]
+    one, rr1, _, _ = _run(lib, n, u, t, maps, None, 1e8, (2, 2), 1)
+    for cs in (2, 3):
+        many, rr, _, _ = _run(lib, n, u, t, maps, None, 1e8, (2, 2), 1, csize=cs)
+        assert np.array_equal(one, many) and rr == rr1, cs
