@@ -25,15 +25,15 @@ struct LuProblem {
 // ---------------------------------------------------------------------------
 // host driver of the node-space band LU
 // ---------------------------------------------------------------------------
-// CTAs per image of the LU factorisation: as many (power of two, ≤ 8) as leave every image of the wave its own
-// cluster; one when the trailing window has too few 32×32 tiles to share.  BPLTV_LU_CLUSTER overrides.
+// CTAs per image of the LU factorisation: as many (power of two, ≤ 4: measured no gain beyond — the block step is
+// then its panel chain) as leave every image of the wave its own cluster; one when the trailing window has too few 32×32 tiles to share.  BPLTV_LU_CLUSTER overrides.
 static inline int lu_cluster_ctas(int images_in_wave, int sm_count, int bw)
 {
     const char *env = getenv("BPLTV_LU_CLUSTER");
     if (env && *env) { const int c = atoi(env); if (c == 1 || c == 2 || c == 4 || c == 8 || c == 16) return c; }
     if (bw < 200) return 1;
     int C = 1;
-    while (C < 8 && 2 * C * images_in_wave <= sm_count) C *= 2;
+    while (C < 4 && 2 * C * images_in_wave <= sm_count) C *= 2;
     return C;
 }
 

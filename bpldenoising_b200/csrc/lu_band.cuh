@@ -215,11 +215,48 @@ static inline size_t lu_factor_smem(int bw)
     return (size_t)(LU_NB * LU_DP + LU_NB + 2 * LU_NB * lu_panel_pitch(bw)) * sizeof(double);
 }
 
+// 16×16 LU without pivoting of the block in D (row pitch LU_DP), by ONE warp, in registers: lane c (< 16;
+// lanes 16-31 mirror it) holds column c; per pivot the multipliers of column pv come out of lane pv by
+// shuffle — no shared-memory round trip on the chain.  Writes the factors back to D and the reciprocal
+// pivots to rD; returns true when a pivot vanished (or is NaN).  Its own function so that its 16 column
+// registers do not weigh on the register allocation of the trailing update.
+#ifndef BPLTV_EMU
+__noinline__
+#endif
+static __device__ bool lu16_warp(double *D, double *rD)
+{
+    constexpr int NB = LU_NB, DP = LU_DP;
+    const int lane = threadIdx.x & 31, cl = lane & 15;
+    bool bad = false;
+    double acol[NB];
+#pragma unroll
+    for (int r = 0; r < NB; ++r) acol[r] = D[r * DP + cl];
+#pragma unroll
+    for (int pv = 0; pv < NB; ++pv) {
+        const double piv = __shfl_sync(0xffffffffu, acol[pv], pv);
+        if (!(fabs(piv) > 0.0)) bad = true;
+        const double rp = 1.0 / piv;
+#pragma unroll
+        for (int r = pv + 1; r < NB; ++r) {
+            const double l = __shfl_sync(0xffffffffu, acol[r], pv) * rp;
+            if (cl > pv) acol[r] -= l * acol[pv];
+            else if (cl == pv) acol[r] = l;
+        }
+    }
+    if (lane < NB) {
+#pragma unroll
+        for (int r = 0; r < NB; ++r) D[r * DP + lane] = acol[r];
+    }
+    __syncwarp();
+    if (lane < NB) rD[lane] = 1.0 / D[lane * DP + lane];
+    return bad;
+}
+
 // CL: the image is factorised by a thread-block CLUSTER of csize CTAs (one SM each).  Every CTA forms the
 // diagonal block and both panels redundantly in its own shared memory (cheap), the 32×32 tiles of the
 // trailing window are dealt over all warps of the cluster, and two cluster barriers per block step order the
-// traffic through global memory: one after every CTA has READ the step's inputs (then rank 0 alone writes the
-// factored block and panels back in place), one after the trailing update.  Same operations per entry as the
+// traffic through global memory: one after every CTA has READ the step's inputs (then the
+// factored block and panels are written back in place, each entry by one CTA), one after the trailing update.  Same operations per entry as the
 // single-CTA kernel: identical bits for every cluster size.
 template <bool CL>
 __global__ void __launch_bounds__(LU_THREADS, 1) lu_factor_kernel(LuSlots ws)
@@ -242,99 +279,99 @@ __global__ void __launch_bounds__(LU_THREADS, 1) lu_factor_kernel(LuSlots ws)
     for (int k0 = 0; k0 < N; k0 += NB) {
         const int nb = min(NB, N - k0);
         const int R = min(bw, N - k0 - nb);       // rows below / columns right of the block inside the band
+        // item t of the panels: t < R → row k0+nb+t of A21, else column k0+nb+(t−R) of A12
+        auto panel_load = [&](int t, double (&v)[NB]) {
+            if (t < R) {
+                const int gr = k0 + nb + t;
+                const double *rowp = ab + (size_t)gr * LD + (k0 - gr + bwx);     // entry (gr, k0+c) at rowp[c]; 16-byte aligned
+#pragma unroll
+                for (int c = 0; c < NB; c += 2) {
+                    const double2 w = *reinterpret_cast<const double2 *>(LU_A16(rowp + c));
+                    v[c] = w.x; v[c + 1] = w.y;
+                }
+            } else {
+                const int gj = k0 + nb + (t - R);
+                const double *colp = ab + (size_t)k0 * LD + (gj - k0 + bwx);     // entry (k0+r, gj) at colp[r·(LD−1)]
+#pragma unroll
+                for (int r = 0; r < NB; ++r) v[r] = colp[(size_t)r * (LD - 1)];
+            }
+        };
+        auto panel_solve = [&](int t, double (&v)[NB]) {
+            if (t < R) {
+                const int gr = k0 + nb + t;
+                double *rowp = ab + (size_t)gr * LD + (k0 - gr + bwx);
+#pragma unroll
+                for (int c = 0; c < NB; ++c) {
+                    double s = v[c];
+#pragma unroll
+                    for (int m = 0; m < c; ++m) s -= v[m] * D[m * DP + c];
+                    v[c] = s * rD[c];
+                }
+#pragma unroll
+                for (int c = 0; c < NB; c += 2) {
+                    if (!CL) *reinterpret_cast<double2 *>(LU_A16(rowp + c)) = make_double2(v[c], v[c + 1]);
+                    Lt[c * lsp + t] = v[c]; Lt[(c + 1) * lsp + t] = v[c + 1];
+                }
+            } else {
+                const int tt = t - R, gj = k0 + nb + tt;
+                double *colp = ab + (size_t)k0 * LD + (gj - k0 + bwx);
+#pragma unroll
+                for (int r = 0; r < NB; ++r) {
+                    double s = v[r];
+#pragma unroll
+                    for (int m = 0; m < r; ++m) s -= D[r * DP + m] * v[m];
+                    v[r] = s;
+                }
+#pragma unroll
+                for (int r = 0; r < NB; ++r) {
+                    if (!CL) colp[(size_t)r * (LD - 1)] = v[r];
+                    Us[r * lsp + tt] = v[r];
+                }
+            }
+        };
+        double pin[NB];
+        if (tid < 2 * R) panel_load(tid, pin);
         // ---- diagonal block: load, factor in warp 0 (identity padding for a short last block) ----
         for (int e = tid; e < NB * NB; e += blockDim.x) {
             const int r = e / NB, c = e - r * NB;
             D[r * DP + c] = (r < nb && c < nb) ? ab[(size_t)(k0 + r) * LD + (c - r + bwx)] : (r == c ? 1.0 : 0.0);
         }
         __syncthreads();
-        if (warp == 0) {
-            const int r = lane & 15, h = lane >> 4;   // row r, columns 8h … 8h+7
-            for (int pv = 0; pv < NB; ++pv) {
-                const double piv = D[pv * DP + pv];
-                if (!(fabs(piv) > 0.0)) bad = true;
-                const double l = r > pv ? D[r * DP + pv] * (1.0 / piv) : 0.0;
-                __syncwarp();
-                if (r > pv) {
-                    if (h == (pv >> 3)) D[r * DP + pv] = l;
-#pragma unroll
-                    for (int cc = 0; cc < 8; ++cc) {
-                        const int c = 8 * h + cc;
-                        if (c > pv) D[r * DP + c] -= l * D[pv * DP + c];
-                    }
-                }
-                __syncwarp();
-            }
-            if (lane < NB) rD[lane] = 1.0 / D[lane * DP + lane];
-        }
+        if (warp == 0 && lu16_warp(D, rD)) bad = true;
         __syncthreads();
         if (!CL) for (int e = tid; e < NB * NB; e += blockDim.x) {   // the factored block back to the band (cluster: after the read barrier below)
             const int r = e / NB, c = e - r * NB;
             if (r < nb && c < nb) ab[(size_t)(k0 + r) * LD + (c - r + bwx)] = D[r * DP + c];
         }
-        // ---- L21 = A21 U11⁻¹ (one thread per row), U12 = L11⁻¹ A12 (one thread per column) ----
-        for (int t = tid; t < 2 * R; t += blockDim.x) {
-            if (t < R) {
-                const int gr = k0 + nb + t;
-                double *rowp = ab + (size_t)gr * LD + (k0 - gr + bwx);        // entry (gr, k0+c) at rowp[c]; 16-byte aligned
-                double x[NB];
-#pragma unroll
-                for (int c = 0; c < NB; c += 2) {
-                    const double2 v = *reinterpret_cast<const double2 *>(LU_A16(rowp + c));
-                    x[c] = v.x; x[c + 1] = v.y;
-                }
-#pragma unroll
-                for (int c = 0; c < NB; ++c) {
-                    double s = x[c];
-#pragma unroll
-                    for (int m = 0; m < c; ++m) s -= x[m] * D[m * DP + c];
-                    x[c] = s * rD[c];
-                }
-#pragma unroll
-                for (int c = 0; c < NB; c += 2) {
-                    if (!CL) *reinterpret_cast<double2 *>(LU_A16(rowp + c)) = make_double2(x[c], x[c + 1]);
-                    Lt[c * lsp + t] = x[c]; Lt[(c + 1) * lsp + t] = x[c + 1];
-                }
-            } else {
-                const int tt = t - R, gj = k0 + nb + tt;
-                double *colp = ab + (size_t)k0 * LD + (gj - k0 + bwx);        // entry (k0+r, gj) at colp[r·(LD−1)]
-                double y[NB];
-#pragma unroll
-                for (int r = 0; r < NB; ++r) y[r] = colp[(size_t)r * (LD - 1)];
-#pragma unroll
-                for (int r = 0; r < NB; ++r) {
-                    double s = y[r];
-#pragma unroll
-                    for (int m = 0; m < r; ++m) s -= D[r * DP + m] * y[m];
-                    y[r] = s;
-                }
-#pragma unroll
-                for (int r = 0; r < NB; ++r) {
-                    if (!CL) colp[(size_t)r * (LD - 1)] = y[r];
-                    Us[r * lsp + tt] = y[r];
-                }
-            }
+        // ---- L21 = A21 U11⁻¹ (one thread per row), U12 = L11⁻¹ A12 (one thread per column); the inputs of a
+        //      thread's first item were loaded before the diagonal block was factored ----
+        if (tid < 2 * R) panel_solve(tid, pin);
+        for (int t = tid + blockDim.x; t < 2 * R; t += blockDim.x) {
+            double v[NB];
+            panel_load(t, v);
+            panel_solve(t, v);
         }
         if (CL) {
             lu_cluster_sync();     // every CTA of the cluster has read this step's block and panels
-            if (crank == 0) {      // one writer: the factored block and panels, from shared memory
+            // the factored block (rank 0) and panels (items dealt round-robin over the ranks: every CTA holds
+            // the complete panels) back to the band, from shared memory
+            if (crank == 0)
                 for (int e = tid; e < NB * NB; e += blockDim.x) {
                     const int r = e / NB, c = e - r * NB;
                     if (r < nb && c < nb) ab[(size_t)(k0 + r) * LD + (c - r + bwx)] = D[r * DP + c];
                 }
-                for (int t = tid; t < 2 * R; t += blockDim.x) {
-                    if (t < R) {
-                        const int gr = k0 + nb + t;
-                        double *rowp = ab + (size_t)gr * LD + (k0 - gr + bwx);
+            for (int t = tid * csize + crank; t < 2 * R; t += blockDim.x * csize) {
+                if (t < R) {
+                    const int gr = k0 + nb + t;
+                    double *rowp = ab + (size_t)gr * LD + (k0 - gr + bwx);
 #pragma unroll
-                        for (int c = 0; c < NB; c += 2)
-                            *reinterpret_cast<double2 *>(LU_A16(rowp + c)) = make_double2(Lt[c * lsp + t], Lt[(c + 1) * lsp + t]);
-                    } else {
-                        const int tt = t - R, gj = k0 + nb + tt;
-                        double *colp = ab + (size_t)k0 * LD + (gj - k0 + bwx);
+                    for (int c = 0; c < NB; c += 2)
+                        *reinterpret_cast<double2 *>(LU_A16(rowp + c)) = make_double2(Lt[c * lsp + t], Lt[(c + 1) * lsp + t]);
+                } else {
+                    const int tt = t - R, gj = k0 + nb + tt;
+                    double *colp = ab + (size_t)k0 * LD + (gj - k0 + bwx);
 #pragma unroll
-                        for (int r = 0; r < NB; ++r) colp[(size_t)r * (LD - 1)] = Us[r * lsp + tt];
-                    }
+                    for (int r = 0; r < NB; ++r) colp[(size_t)r * (LD - 1)] = Us[r * lsp + tt];
                 }
             }
         } else {
@@ -410,33 +447,65 @@ __global__ void __launch_bounds__(LU_THREADS, 1) lu_factor_kernel(LuSlots ws)
 
 // ---------------------------------------------------------------------------
 // blocked substitution with the factors of lu_factor_kernel; `vec` (N doubles, shared or global memory)
-// is solved in place.  D: NB·DP doubles, rhs: NB doubles of shared memory.  Ends with a barrier.
+// is solved in place.  D: 2·NB·DP doubles (double buffer), rhs: NB doubles of shared memory.  The factor
+// entries a block step needs do not depend on the vector, so they are PREFETCHED one step ahead (the 16 L21
+// entries of a thread's row / the 8 U12 entries of a lane's columns into registers, the diagonal block into
+// the other half of D): the critical path of a step is the 16-step triangular solve in warp 0 plus one
+// register-fed update, not a global-memory round trip.  Ends with a barrier.
 // ---------------------------------------------------------------------------
 static __device__ void lu_band_solve(const double *ab, int N, int bw, int bwx, int LD, double *vec, double *D,
                                      double *rhs)
 {
     constexpr int NB = LU_NB, DP = LU_DP;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    // forward: L y = b, L unit lower
-    for (int k0 = 0; k0 < N; k0 += NB) {
-        const int nb = min(NB, N - k0);
-        const int R = min(bw, N - k0 - nb);
+    const int nblk = (N + NB - 1) / NB;
+    // ---- forward: L y = b, L unit lower ----
+    auto fwd_block = [&](int kb, double *Dd) {      // strictly lower part of diagonal block kb
+        const int k0 = kb * NB, nb = min(NB, N - k0);
         for (int e = tid; e < NB * NB; e += blockDim.x) {
             const int r = e / NB, c = e - r * NB;
-            D[r * DP + c] = (r < nb && c < r) ? ab[(size_t)(k0 + r) * LD + (c - r + bwx)] : 0.0;
+            Dd[r * DP + c] = (r < nb && c < r) ? ab[(size_t)(k0 + r) * LD + (c - r + bwx)] : 0.0;
         }
-        __syncthreads();
+    };
+    auto fwd_row = [&](int kb, double (&l)[NB]) {   // L21 entries of this thread's row below block kb
+        const int k0 = kb * NB, nb = min(NB, N - k0), R = min(bw, N - k0 - nb);
+        if (tid < R) {
+            const int gr = k0 + nb + tid;
+            const double *rowp = ab + (size_t)gr * LD + (k0 - gr + bwx);
+#pragma unroll
+            for (int c = 0; c < NB; c += 2) {
+                const double2 v = *reinterpret_cast<const double2 *>(LU_A16(rowp + c));
+                l[c] = v.x; l[c + 1] = v.y;
+            }
+        }
+    };
+    double lcur[NB], lnext[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) lcur[c] = lnext[c] = 0.0;
+    fwd_block(0, D);
+    fwd_row(0, lcur);
+    __syncthreads();
+    for (int kb = 0; kb < nblk; ++kb) {
+        const int k0 = kb * NB, nb = min(NB, N - k0), R = min(bw, N - k0 - nb);
+        double *Dc = D + (kb & 1) * NB * DP;
+        if (kb + 1 < nblk) { fwd_block(kb + 1, D + ((kb + 1) & 1) * NB * DP); fwd_row(kb + 1, lnext); }
         if (warp == 0) {
             double y = lane < nb ? vec[k0 + lane] : 0.0;
 #pragma unroll
             for (int m = 0; m < NB; ++m) {
                 const double ym = __shfl_sync(0xffffffffu, y, m);
-                if (lane > m && lane < NB) y -= D[lane * DP + m] * ym;
+                if (lane > m && lane < NB) y -= Dc[lane * DP + m] * ym;
             }
             if (lane < nb) vec[k0 + lane] = y;
         }
         __syncthreads();
-        for (int t = tid; t < R; t += blockDim.x) {     // R > 0 implies a full block (nb = NB)
+        if (tid < R) {                                  // R > 0 implies a full block (nb = NB)
+            double s = 0.0;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) s = fma(lcur[c], vec[k0 + c], s);
+            vec[k0 + nb + tid] -= s;
+        }
+        for (int t = tid + blockDim.x; t < R; t += blockDim.x) {   // bands wider than the CTA: not prefetched
             const int gr = k0 + nb + t;
             const double *rowp = ab + (size_t)gr * LD + (k0 - gr + bwx);
             double s = 0.0;
@@ -445,21 +514,47 @@ static __device__ void lu_band_solve(const double *ab, int N, int bw, int bwx, i
             vec[gr] -= s;
         }
         __syncthreads();
+#pragma unroll
+        for (int c = 0; c < NB; ++c) lcur[c] = lnext[c];
     }
-    // backward: U x = y
-    const int nblk = (N + NB - 1) / NB;
-    for (int kb = nblk - 1; kb >= 0; --kb) {
-        const int k0 = kb * NB;
-        const int nb = min(NB, N - k0);
-        const int R = min(bw, N - k0 - nb);
+    // ---- backward: U x = y ----
+    constexpr int UM = 8;                               // prefetched U12 entries per lane (columns lane + 32·m)
+    auto bwd_block = [&](int kb, double *Dd) {          // upper part of diagonal block kb, identity padding
+        const int k0 = kb * NB, nb = min(NB, N - k0);
         for (int e = tid; e < NB * NB; e += blockDim.x) {
             const int r = e / NB, c = e - r * NB;
-            D[r * DP + c] = (r < nb && c < nb && c >= r) ? ab[(size_t)(k0 + r) * LD + (c - r + bwx)] : (r == c ? 1.0 : 0.0);
+            Dd[r * DP + c] = (r < nb && c < nb && c >= r) ? ab[(size_t)(k0 + r) * LD + (c - r + bwx)] : (r == c ? 1.0 : 0.0);
         }
+    };
+    auto bwd_row = [&](int kb, double (&u)[UM]) {       // U12 entries of row `warp` of block kb (rows ≥ nwarps: not prefetched)
+        const int k0 = kb * NB, nb = min(NB, N - k0), R = min(bw, N - k0 - nb);
+        if (warp < nb) {
+            const double *rowp = ab + (size_t)(k0 + warp) * LD + (nb - warp + bwx);   // entry (k0+r, k0+nb+j) at rowp[j]
+#pragma unroll
+            for (int m = 0; m < UM; ++m) u[m] = (lane + 32 * m < R) ? rowp[lane + 32 * m] : 0.0;
+        }
+    };
+    double ucur[UM], unext[UM];
+#pragma unroll
+    for (int m = 0; m < UM; ++m) ucur[m] = unext[m] = 0.0;
+    bwd_block(nblk - 1, D + ((nblk - 1) & 1) * NB * DP);
+    bwd_row(nblk - 1, ucur);
+    __syncthreads();
+    for (int kb = nblk - 1; kb >= 0; --kb) {
+        const int k0 = kb * NB, nb = min(NB, N - k0), R = min(bw, N - k0 - nb);
+        double *Dc = D + (kb & 1) * NB * DP;
+        if (kb > 0) { bwd_block(kb - 1, D + ((kb - 1) & 1) * NB * DP); bwd_row(kb - 1, unext); }
         for (int r = warp; r < nb; r += nwarps) {
-            const double *rowp = ab + (size_t)(k0 + r) * LD + (nb - r + bwx);   // entry (k0+r, k0+nb+j) at rowp[j]
+            const double *rowp = ab + (size_t)(k0 + r) * LD + (nb - r + bwx);
             double s = 0.0;
-            for (int j = lane; j < R; j += 32) s = fma(rowp[j], vec[k0 + nb + j], s);
+            if (r == warp) {
+#pragma unroll
+                for (int m = 0; m < UM; ++m)
+                    if (lane + 32 * m < R) s = fma(ucur[m], vec[k0 + nb + lane + 32 * m], s);
+                for (int j = lane + 32 * UM; j < R; j += 32) s = fma(rowp[j], vec[k0 + nb + j], s);
+            } else {
+                for (int j = lane; j < R; j += 32) s = fma(rowp[j], vec[k0 + nb + j], s);
+            }
             s = lu_warp_sum(s);
             if (lane == 0) rhs[r] = vec[k0 + r] - s;
         }
@@ -468,13 +563,15 @@ static __device__ void lu_band_solve(const double *ab, int N, int bw, int bwx, i
             double x = lane < nb ? rhs[lane] : 0.0;
 #pragma unroll
             for (int m = NB - 1; m >= 0; --m) {
-                const double xm = __shfl_sync(0xffffffffu, x, m) / D[m * DP + m];
+                const double xm = __shfl_sync(0xffffffffu, x, m) / Dc[m * DP + m];
                 if (lane == m) x = xm;
-                if (lane < m) x -= D[lane * DP + m] * xm;
+                if (lane < m) x -= Dc[lane * DP + m] * xm;
             }
             if (lane < nb) vec[k0 + lane] = x;
         }
         __syncthreads();
+#pragma unroll
+        for (int m = 0; m < UM; ++m) ucur[m] = unext[m];
     }
 }
 
@@ -500,12 +597,12 @@ static __device__ __forceinline__ double lu3_apply(const double *pix, int n, int
 
 // ---------------------------------------------------------------------------
 // K4: p = M⁻¹ r with refinement, g_k = p ⊙ G_kᵀ w_k, patch sums (or plain sums for a scalar parameter).
-// Dynamic shared memory: D[NB·DP] | rhs[NB] | red[33+] | vec[N] when vec_in_smem.
+// Dynamic shared memory: D[2·NB·DP] | rhs[NB] | red[40] | vec[N] when vec_in_smem.
 // out_img: nops·lm·ln doubles per image, layout [operator][patch] like the m×n×3 array.
 // ---------------------------------------------------------------------------
 static inline size_t lu_solve_smem(int N, bool vec_in_smem)
 {
-    return (size_t)(LU_NB * LU_DP + LU_NB + 40 + (vec_in_smem ? N : 0)) * sizeof(double);
+    return (size_t)(2 * LU_NB * LU_DP + LU_NB + 40 + (vec_in_smem ? N : 0)) * sizeof(double);
 }
 
 template <typename Real>
@@ -520,7 +617,7 @@ __global__ void __launch_bounds__(LU_THREADS, 1) lu3_solve_kernel(LuSlots ws, Lu
     double *pix = ws.pix + ws.pix_stride * slot;
     const double *r = pix + (size_t)LU_PL_R * N;
     double *p = pix + (size_t)LU_PL_P * N, *work = pix + (size_t)LU_PL_WORK * N, *fk = pix + (size_t)LU_PL_F * N;
-    double *D = lu_ssm, *rhs = D + LU_NB * LU_DP, *red = rhs + LU_NB;
+    double *D = lu_ssm, *rhs = D + 2 * LU_NB * LU_DP, *red = rhs + LU_NB;
     double *vec = vec_in_smem ? red + 40 : work;
     const int tid = threadIdx.x;
 
