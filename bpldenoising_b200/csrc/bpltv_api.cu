@@ -839,16 +839,16 @@ static int set_dataset_impl(bpltv_ctx *ctx, const double *truth, const double *n
 
 // gradient / gradient_reg of the TV learning function.  The regularised branch has two implementations:
 // the multiplier-space banded Cholesky of gradient.cuh and the node-space band LU of lu_band.cuh
-// (n² unknowns with half-bandwidth n instead of ≤ 2n² modes with half-bandwidth ≤ 2n+1);
-// BPLTV_GRAD_REG_LU=0/1 selects, default BPLTV_GRAD_REG_LU_DEFAULT.
-#ifndef BPLTV_GRAD_REG_LU_DEFAULT
-#define BPLTV_GRAD_REG_LU_DEFAULT false
-#endif
+// (n² unknowns with half-bandwidth n instead of ≤ 2n² modes with half-bandwidth ≤ 2n+1).  Measured on B200
+// (tools/time_tv_grad_reg.py), LU vs Cholesky: 25.4 vs 34.6 ms (1 image 128²), 29.6 vs 38.2 (10), 31.6 vs 37.0
+// (148), 25.5 vs 25.5 / 29.7 vs 35.1 (2×2 patch parameter, 1 / 10 images), 144 vs 337 (32 images of 256², 4-CTA
+// clusters), but 236 vs 217 for 128 images of 256² (one CTA each).  Hence: LU up to 128×128, and beyond when the
+// batch leaves every image a cluster; BPLTV_GRAD_REG_LU=0/1 overrides.
 template <typename Real>
 static int run_tv_gradient(Dev &d, const GradProblem<Real> &gp, cudaStream_t st, double *d_grad_out)
 {
     const char *lu_env = getenv("BPLTV_GRAD_REG_LU");
-    const bool lu = lu_env && *lu_env ? atoi(lu_env) != 0 : BPLTV_GRAD_REG_LU_DEFAULT;
+    const bool lu = lu_env && *lu_env ? atoi(lu_env) != 0 : (gp.M <= 128 || 2 * gp.O <= d.sm_count);
     if (gp.regularised && lu && gp.M == gp.N && gp.M >= 4) {
         LuProblem<Real> lp;
         lp.u = gp.u; lp.ubar = gp.ubar; lp.M = gp.M; lp.N = gp.N; lp.O = gp.O;

@@ -82,7 +82,8 @@ static int run_gradient_lu(GradWork &w, const LuProblem<Real> &gp, int sm_count,
     ws.n = n; ws.N = N; ws.nops = nops; ws.bw = std::min(nops == 1 ? n : 2 * n, N - 1); ws.bwx = ws.bw + LU_NB; ws.LD = 2 * ws.bwx + 1;
     ws.ab_stride = ((size_t)N * ws.LD + 3) & ~(size_t)3;
     ws.pix_stride = (size_t)LU_PLANES * N;
-    const size_t fsmem = lu_factor_smem(ws.bw);
+    ws.use_pin = (2 * ws.bw <= LU_THREADS && lu_factor_smem(ws.bw, true) <= smem_optin) ? 1 : 0;
+    const size_t fsmem = lu_factor_smem(ws.bw, ws.use_pin != 0);
     if (fsmem > smem_optin) return grad_fail(w, -1, "image too large for the band-LU panels in shared memory (n <= 430)");
     const bool vec_in_smem = lu_solve_smem(N, true) + 1024 <= smem_optin;
     const size_t ssmem = lu_solve_smem(N, vec_in_smem);

@@ -25,6 +25,7 @@
 #pragma once
 #ifndef BPLTV_EMU
 #include <cooperative_groups.h>
+#include <cuda_pipeline.h>
 #endif
 
 #include "sumregs_stencils.cuh"
@@ -46,6 +47,7 @@ struct LuSlots {
     double *pix;  size_t pix_stride;    // per slot: LU_PLANES planes
     int *info;                          // per slot: 4 ints, [0] ≠ 0 → a pivot vanished
     int n, N, bw, bwx, LD;
+    int use_pin;                        // lu_factor: stage the panel inputs in shared memory with cp.async
     int nops;                           // 3: forward, backward, centred (sum of regularisers); 1: forward only (TV)
 };
 
@@ -73,6 +75,33 @@ static inline void lu_cluster_sync() { emu::cluster_sync(); }
 static __device__ __forceinline__ int lu_cluster_rank() { return (int)cooperative_groups::this_cluster().block_rank(); }
 static __device__ __forceinline__ int lu_cluster_size() { return (int)cooperative_groups::this_cluster().num_blocks(); }
 static __device__ __forceinline__ void lu_cluster_sync() { cooperative_groups::this_cluster().sync(); }
+#endif
+
+// asynchronous global → shared copies (cp.async: no registers held while the data is in flight) and a fast
+// reciprocal for the pivot chain (hardware seed + two Newton steps: ≤ 1 ulp, deterministic)
+#ifdef BPLTV_EMU
+static inline void lu_cp_async16(double *dst, const double *src) { emu::check_aligned16(dst); emu::check_aligned16(src); dst[0] = src[0]; dst[1] = src[1]; }
+static inline void lu_cp_async8(double *dst, const double *src) { dst[0] = src[0]; }
+static inline void lu_cp_async_commit() {}
+static inline void lu_cp_async_wait() {}
+static inline double lu_rcp(double a) { return 1.0 / a; }
+#else
+static __device__ __forceinline__ void lu_cp_async16(double *dst, const double *src) { __pipeline_memcpy_async(dst, src, 16); }
+static __device__ __forceinline__ void lu_cp_async8(double *dst, const double *src) { __pipeline_memcpy_async(dst, src, 8); }
+static __device__ __forceinline__ void lu_cp_async_commit() { __pipeline_commit(); }
+static __device__ __forceinline__ void lu_cp_async_wait() { __pipeline_wait_prior(0); }
+static __device__ __forceinline__ double lu_rcp(double a)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    if (!(fabs(r) > 0.0) || !(fabs(r) < 1e300)) return 1.0 / a;     // 0, inf, NaN, denormal: the IEEE path
+    double e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-a, r, 1.0);
+    return fma(r, e, r);
+}
 #endif
 
 static __device__ __forceinline__ double lu_warp_sum(double v)
@@ -210,9 +239,10 @@ __global__ void __launch_bounds__(256) lu3_assemble_kernel(LuSlots ws, Lu3Params
 // even column of the window is 16-byte aligned and moves as double2.
 // ---------------------------------------------------------------------------
 static inline int lu_panel_pitch(int bw) { return (bw + 32 + 3) & ~3; }
-static inline size_t lu_factor_smem(int bw)
+constexpr int LU_PINP = LU_NB + 2;      // pitch of a staged panel item: 16-byte aligned, conflict-free 16-byte reads
+static inline size_t lu_factor_smem(int bw, bool use_pin)
 {
-    return (size_t)(LU_NB * LU_DP + LU_NB + 2 * LU_NB * lu_panel_pitch(bw)) * sizeof(double);
+    return (size_t)(LU_NB * LU_DP + LU_NB + 2 * LU_NB * lu_panel_pitch(bw) + (use_pin ? 2 * bw * LU_PINP : 0)) * sizeof(double);
 }
 
 // 16×16 LU without pivoting of the block in D (row pitch LU_DP), by ONE warp, in registers: lane c (< 16;
@@ -235,7 +265,7 @@ static __device__ bool lu16_warp(double *D, double *rD)
     for (int pv = 0; pv < NB; ++pv) {
         const double piv = __shfl_sync(0xffffffffu, acol[pv], pv);
         if (!(fabs(piv) > 0.0)) bad = true;
-        const double rp = 1.0 / piv;
+        const double rp = lu_rcp(piv);
 #pragma unroll
         for (int r = pv + 1; r < NB; ++r) {
             const double l = __shfl_sync(0xffffffffu, acol[r], pv) * rp;
@@ -272,6 +302,8 @@ __global__ void __launch_bounds__(LU_THREADS, 1) lu_factor_kernel(LuSlots ws)
     double *rD = D + NB * DP;                     // NB·DP = 272 and NB are even: the panels are 16-byte aligned
     double *Lt = rD + NB;
     double *Us = Lt + NB * lsp;
+    double *Pin = Us + NB * lsp;                  // staged panel inputs (use_pin): item t at Pin[t·LU_PINP …]
+    const bool use_pin = ws.use_pin != 0;         // host guarantees 2·bw ≤ blockDim.x then
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int rg = lane >> 3, cg = lane & 7;      // trailing update: 4 row groups × 8 column groups per warp
     bool bad = false;
@@ -329,8 +361,22 @@ __global__ void __launch_bounds__(LU_THREADS, 1) lu_factor_kernel(LuSlots ws)
                 }
             }
         };
-        double pin[NB];
-        if (tid < 2 * R) panel_load(tid, pin);
+        // the inputs of the thread's panel item start travelling now and arrive under the factorisation of the
+        // diagonal block: cp.async into shared memory, so no register is held across it
+        if (use_pin && tid < 2 * R) {
+            double *dst = Pin + tid * LU_PINP;
+            if (tid < R) {
+                const int gr = k0 + nb + tid;
+                const double *rowp = ab + (size_t)gr * LD + (k0 - gr + bwx);
+#pragma unroll
+                for (int c = 0; c < NB; c += 2) lu_cp_async16(dst + c, rowp + c);
+            } else {
+                const double *colp = ab + (size_t)k0 * LD + (nb + (tid - R) + bwx);
+#pragma unroll
+                for (int r = 0; r < NB; ++r) lu_cp_async8(dst + r, colp + (size_t)r * (LD - 1));
+            }
+            lu_cp_async_commit();
+        }
         // ---- diagonal block: load, factor in warp 0 (identity padding for a short last block) ----
         for (int e = tid; e < NB * NB; e += blockDim.x) {
             const int r = e / NB, c = e - r * NB;
@@ -343,13 +389,25 @@ __global__ void __launch_bounds__(LU_THREADS, 1) lu_factor_kernel(LuSlots ws)
             const int r = e / NB, c = e - r * NB;
             if (r < nb && c < nb) ab[(size_t)(k0 + r) * LD + (c - r + bwx)] = D[r * DP + c];
         }
-        // ---- L21 = A21 U11⁻¹ (one thread per row), U12 = L11⁻¹ A12 (one thread per column); the inputs of a
-        //      thread's first item were loaded before the diagonal block was factored ----
-        if (tid < 2 * R) panel_solve(tid, pin);
-        for (int t = tid + blockDim.x; t < 2 * R; t += blockDim.x) {
-            double v[NB];
-            panel_load(t, v);
-            panel_solve(t, v);
+        // ---- L21 = A21 U11⁻¹ (one thread per row), U12 = L11⁻¹ A12 (one thread per column) ----
+        if (use_pin) {
+            if (tid < 2 * R) {
+                lu_cp_async_wait();
+                const double *src = Pin + tid * LU_PINP;
+                double v[NB];
+#pragma unroll
+                for (int c = 0; c < NB; c += 2) {
+                    const double2 w = *reinterpret_cast<const double2 *>(LU_A16(src + c));
+                    v[c] = w.x; v[c + 1] = w.y;
+                }
+                panel_solve(tid, v);
+            }
+        } else {
+            for (int t = tid; t < 2 * R; t += blockDim.x) {
+                double v[NB];
+                panel_load(t, v);
+                panel_solve(t, v);
+            }
         }
         if (CL) {
             lu_cluster_sync();     // every CTA of the cluster has read this step's block and panels
@@ -523,7 +581,9 @@ static __device__ void lu_band_solve(const double *ab, int N, int bw, int bwx, i
         const int k0 = kb * NB, nb = min(NB, N - k0);
         for (int e = tid; e < NB * NB; e += blockDim.x) {
             const int r = e / NB, c = e - r * NB;
-            Dd[r * DP + c] = (r < nb && c < nb && c >= r) ? ab[(size_t)(k0 + r) * LD + (c - r + bwx)] : (r == c ? 1.0 : 0.0);
+            double v = (r < nb && c < nb && c >= r) ? ab[(size_t)(k0 + r) * LD + (c - r + bwx)] : (r == c ? 1.0 : 0.0);
+            if (r == c) v = 1.0 / v;          // reciprocal pivot, formed off the critical path
+            Dd[r * DP + c] = v;
         }
     };
     auto bwd_row = [&](int kb, double (&u)[UM]) {       // U12 entries of row `warp` of block kb (rows ≥ nwarps: not prefetched)
@@ -563,7 +623,7 @@ static __device__ void lu_band_solve(const double *ab, int N, int bw, int bwx, i
             double x = lane < nb ? rhs[lane] : 0.0;
 #pragma unroll
             for (int m = NB - 1; m >= 0; --m) {
-                const double xm = __shfl_sync(0xffffffffu, x, m) / Dc[m * DP + m];
+                const double xm = __shfl_sync(0xffffffffu, x, m) * Dc[m * DP + m];
                 if (lane == m) x = xm;
                 if (lane < m) x -= Dc[lane * DP + m] * xm;
             }

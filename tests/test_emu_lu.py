@@ -45,7 +45,7 @@ def _case(n, seed):
     return np.asfortranarray(t), u
 
 
-def _run(lib, n, u, t, maps, alpha3, gamma, grid, vec_in_smem, want_band=False, nops=3, csize=1):
+def _run(lib, n, u, t, maps, alpha3, gamma, grid, vec_in_smem, want_band=False, nops=3, csize=1, use_pin=1):
     N = n * n
     bw = min(n if nops == 1 else 2 * n, N - 1)
     LD = 2 * (bw + 16) + 1
@@ -54,7 +54,7 @@ def _run(lib, n, u, t, maps, alpha3, gamma, grid, vec_in_smem, want_band=False, 
     rr, pf, ld = C.c_double(), C.c_int(), C.c_int()
     am = None if maps is None else np.concatenate([m.flatten(order="F") for m in maps])
     a3 = None if alpha3 is None else np.asarray(alpha3, dtype=np.float64)
-    rc = lib.emu_lu_gradient(csize, nops, n, _ptr(u.flatten(order="F")), _ptr(t.flatten(order="F")), _ptr(am), _ptr(a3),
+    rc = lib.emu_lu_gradient(use_pin, csize, nops, n, _ptr(u.flatten(order="F")), _ptr(t.flatten(order="F")), _ptr(am), _ptr(a3),
                              C.c_double(gamma), grid[0], grid[1], 3, int(vec_in_smem), _ptr(out), C.byref(rr),
                              C.byref(pf), _ptr(band), C.byref(ld))
     assert rc == 0 and ld.value == LD and pf.value == 0
@@ -131,3 +131,9 @@ def test_band_lu_cluster_factorisation_is_invisible_on_the_thread_emulation():
     for cs in (2, 3):
         many, rr, _, _ = _run(lib, n, u, t, maps, None, 1e8, (2, 2), 1, csize=cs)
         assert np.array_equal(one, many) and rr == rr1, cs
+    # the cp.async staging of the panel inputs (needs 2·bw = 80 ≤ threads: on with 128 threads, off with 64 above)
+    # and its absence give the same bits; a different CTA size only reorders the block sums of the functional
+    lib128 = _build(128)
+    a, _, _, _ = _run(lib128, n, u, t, maps, None, 1e8, (2, 2), 1, use_pin=1)
+    b, _, _, _ = _run(lib128, n, u, t, maps, None, 1e8, (2, 2), 1, use_pin=0)
+    assert np.array_equal(a, b) and np.allclose(a, one, rtol=1e-12, atol=0)

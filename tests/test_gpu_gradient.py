@@ -55,6 +55,31 @@ def test_patch_gradient_small_vs_dual_and_literal(bp, ctx, oracle, datasets, var
         assert _rel(g, lit) <= 1e-6
 
 
+def test_gradient_reg_by_both_solvers(bp, ctx, oracle, datasets, monkeypatch):
+    """gradient_reg has two implementations — the multiplier-space banded Cholesky and the node-space band LU
+    (default up to 128×128, BPLTV_GRAD_REG_LU overrides): both within the bars of the dual-form checker and the
+    refined literal solve, scalar and patch (the patch system is row-scaled as the reference writes it, :210)."""
+    t, f = (a[:40, :40, :3].copy(order="F") for a in datasets["faces_train_128_10"])
+    x = np.array([[0.02, 0.05], [0.04, 0.06]])
+    am = oracle.patch_upsample(x, 40, 40)
+    us = oracle.pdps(f, 0.06, maxiter=1500)
+    up = oracle.pdps(f, am, maxiter=1500)
+    ctx.set_dataset((t, f))
+    dual_s = sum(oracle.gradient_dual("reg", 0.06, us[:, :, i], t[:, :, i]) for i in range(3))
+    dual_p = sum(oracle.gradient_dual("reg", am, up[:, :, i], t[:, :, i], grid_shape=x.shape) for i in range(3))
+    lit_s = sum(oracle.gradient_reg_scalar(0.06, us[:, :, i], t[:, :, i], refine=3) for i in range(3))
+    lit_p = sum(oracle.gradient_reg_patch(am, x.shape, up[:, :, i], t[:, :, i], refine=3) for i in range(3))
+    got = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("BPLTV_GRAD_REG_LU", mode)
+        gs = ctx.gradient(0.06, us, regularised=True)
+        gp = ctx.gradient(x, up, regularised=True)
+        assert _rel(gs, dual_s) <= 1e-10 and _rel(gp, dual_p) <= 1e-10, mode
+        assert _rel(gs, lit_s) <= 1e-9 and _rel(gp, lit_p) <= 1e-9, mode
+        got[mode] = (gs, gp)
+    assert _rel(got["0"][0], got["1"][0]) <= 1e-11 and _rel(got["0"][1], got["1"][1]) <= 1e-11
+
+
 @pytest.mark.parametrize("name,lam", [("cameraman_128_5", 0.1), ("faces_train_128_10", 0.05), ("circle_128_10", 0.02)])
 def test_scalar_gradient_full_size_vs_literal(bp, ctx, oracle, datasets, name, lam):
     t, f = (a[:, :, :2].copy(order="F") for a in datasets[name])

@@ -8,6 +8,7 @@ import bpldenoising_b200 as bp  # noqa: E402
 
 cases = (("1x128 scalar", 128, 1, 0.1, 5000), ("10x128 scalar", 128, 10, 0.1, 5000),
          ("1x128 patch", 128, 1, np.array([[0.05, 0.1], [0.08, 0.02]]), 5000),
+         ("10x128 patch", 128, 10, np.array([[0.05, 0.1], [0.08, 0.02]]), 5000), ("148x128 scalar", 128, 148, 0.1, 1000),
          ("32x256 scalar", 256, 32, 0.1, 1000), ("128x256 scalar", 256, 128, 0.1, 500))
 for name, n, O, x, its in cases:
     data = bp.synthetic_dataset(n, n, O, seed=7)
