@@ -725,6 +725,11 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_factor_kernel(GradSlots ws,
 // ---------------------------------------------------------------------------
 constexpr int GRAD_BK = 10;  // backward solve: panel entries per lane held in registers (covers bands ≤ 320)
 
+// BK: as GRAD_BK.  WIDE: bands wider than the CTA (the sum-of-regularisers system: ≈ 770 rows below a block at
+// 128×128, up to 1559) — the forward solve prefetches a second panel row per thread (rows up to 2·blockDim) and
+// the backward solve refills its single register set right after use instead of double-buffering it, so that
+// BK = 26 (bands ≤ 832) fits in registers; without it those rows were loaded on the critical path.
+template <int BK, bool WIDE>
 static __device__ void band_solve(const double *__restrict__ ab, const double *__restrict__ sinv,
                                   const unsigned short *nr /* rows below each block (shared memory) */, int Nd,
                                   int LDa, double *z, double *sh /* ≥ 2*NB + 2*NB*NB doubles */)
@@ -740,12 +745,17 @@ static __device__ void band_solve(const double *__restrict__ ab, const double *_
     };
     // ---- forward: L y = z.  Thread r owns panel row r of the block ----------------------
     {
-        double lcur[NB];
-        auto fetch_l = [&](int blk, int nrows, double(&l)[NB]) {
+        double lcur[NB], lcur2[WIDE ? NB : 1];
+        const int tid2 = tid + (int)blockDim.x;
+        auto fetch_row = [&](int blk, int nrows, int row, double(&l)[NB]) {
             const int kb = blk * NB, nb = min(NB, Nd - kb);
 #pragma unroll
             for (int c = 0; c < NB; ++c)
-                l[c] = (tid < nrows && c < nb) ? __ldg(ab + (size_t)(kb + c) * LDa + (nb + tid - c)) : 0.0;
+                l[c] = (row < nrows && c < nb) ? __ldg(ab + (size_t)(kb + c) * LDa + (nb + row - c)) : 0.0;
+        };
+        auto fetch_l = [&](int blk, int nrows, double(&l)[NB]) {
+            fetch_row(blk, nrows, tid, l);
+            if constexpr (WIDE) fetch_row(blk, nrows, tid2, lcur2);
         };
         int nrows = nblk > 0 ? block_rows(0) : 0, nrows_n = 0;
         if (nblk > 0) { fetch_l(0, nrows, lcur); fetch_si(0, 0); }
@@ -772,8 +782,16 @@ static __device__ void band_solve(const double *__restrict__ ab, const double *_
                 for (int c = 0; c < NB; c += 2) { s0 = fma(lcur[c], ys[c], s0); s1 = fma(lcur[c + 1], ys[c + 1], s1); }
                 z[kb + nb + tid] -= s0 + s1;
             }
-            // rows beyond blockDim.x (only when the band is wider than the CTA)
-            for (int r = tid + blockDim.x; r < nrows; r += blockDim.x) {
+            if constexpr (WIDE) {
+                if (tid2 < nrows) {
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int c = 0; c < NB; c += 2) { s0 = fma(lcur2[c], ys[c], s0); s1 = fma(lcur2[c + 1], ys[c + 1], s1); }
+                    z[kb + nb + tid2] -= s0 + s1;
+                }
+            }
+            // rows beyond the prefetched ones (only when the band is wider than that)
+            for (int r = tid + (WIDE ? 2 : 1) * blockDim.x; r < nrows; r += blockDim.x) {
                 double s = 0.0;
                 for (int c = 0; c < nb; ++c) s = fma(__ldg(ab + (size_t)(kb + c) * LDa + (nb + r - c)), ys[c], s);
                 z[kb + nb + r] -= s;
@@ -786,12 +804,12 @@ static __device__ void band_solve(const double *__restrict__ ab, const double *_
     }
     // ---- backward: Lᵀ x = y.  One warp per column of the block; lanes stride the rows ----
     {
-        double lb[GRAD_BK], lbn[GRAD_BK];
-        auto fetch_lb = [&](int blk, int nrows, double(&l)[GRAD_BK]) {
+        double lb[BK], lbn[WIDE ? 1 : BK];
+        auto fetch_lb = [&](int blk, int nrows, double(&l)[BK]) {
             const int kb = blk * NB, nb = min(NB, Nd - kb);
             const double *col = ab + (size_t)(kb + warp) * LDa + (nb - warp);
 #pragma unroll
-            for (int k = 0; k < GRAD_BK; ++k) {
+            for (int k = 0; k < BK; ++k) {
                 const int r = lane + 32 * k;
                 l[k] = (warp < nb && r < nrows) ? __ldg(col + r) : 0.0;
             }
@@ -801,19 +819,25 @@ static __device__ void band_solve(const double *__restrict__ ab, const double *_
         for (int blk = nblk - 1; blk >= 0; --blk) {
             const int kb = blk * NB, nb = min(NB, Nd - kb);
             const double *Si = sib + (blk & 1) * NB * NB;
-            if (blk > 0) { nrows_n = block_rows(blk - 1); fetch_lb(blk - 1, nrows_n, lbn); }
+            if (blk > 0) {
+                nrows_n = block_rows(blk - 1);
+                if constexpr (!WIDE) fetch_lb(blk - 1, nrows_n, lbn);
+            }
             if (warp < nb) {
                 double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-                for (int k = 0; k < GRAD_BK; k += 2) {
+                for (int k = 0; k < BK; k += 2) {
                     const int r = lane + 32 * k;
                     if (r < nrows) s0 = fma(lb[k], z[kb + nb + r], s0);
                     if (r + 32 < nrows) s1 = fma(lb[k + 1], z[kb + nb + r + 32], s1);
                 }
                 const double *col = ab + (size_t)(kb + warp) * LDa + (nb - warp);
-                for (int r = lane + 32 * GRAD_BK; r < nrows; r += 32) s0 = fma(__ldg(col + r), z[kb + nb + r], s0);
+                for (int r = lane + 32 * BK; r < nrows; r += 32) s0 = fma(__ldg(col + r), z[kb + nb + r], s0);
                 const double s = warp_sum(s0 + s1);
                 if (lane == 0) ts[warp] = s;
+            }
+            if constexpr (WIDE) {   // the register set is free again: the next block's entries travel under the rest of the step
+                if (blk > 0) fetch_lb(blk - 1, nrows_n, lb);
             }
             for (int c = warp + nwarps; c < nb; c += nwarps) {  // only if the CTA has fewer than NB warps
                 const double *col = ab + (size_t)(kb + c) * LDa + (nb - c);
@@ -837,8 +861,10 @@ static __device__ void band_solve(const double *__restrict__ ab, const double *_
             __syncthreads();
             if (tid < nb) z[kb + tid] = ys[tid];
             __syncthreads();
+            if constexpr (!WIDE) {
 #pragma unroll
-            for (int k = 0; k < GRAD_BK; ++k) lb[k] = lbn[k];
+                for (int k = 0; k < BK; ++k) lb[k] = lbn[k];
+            }
             nrows = nrows_n;
         }
     }
@@ -935,11 +961,11 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_solve_kernel(GradSlots ws, 
         if (in_smem) {
             for (int a = tid; a < Nd; a += blockDim.x) zs[a] = vec[a];
             __syncthreads();
-            band_solve(ab, sinv, s_nr, Nd, LDa, zs, sh);
+            band_solve<GRAD_BK, false>(ab, sinv, s_nr, Nd, LDa, zs, sh);
             for (int a = tid; a < Nd; a += blockDim.x) vec[a] = zs[a];
             __syncthreads();
         } else {
-            band_solve(ab, sinv, s_nr, Nd, LDa, vec, sh);
+            band_solve<GRAD_BK, false>(ab, sinv, s_nr, Nd, LDa, vec, sh);
         }
     };
     solve(zeta);

@@ -279,11 +279,11 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad3_solve_kernel(GradSlots ws,
         if (in_smem) {
             for (int a = tid; a < Nd; a += blockDim.x) zs[a] = vec[a];
             __syncthreads();
-            band_solve(ab, sinv, s_nr, Nd, LDa, zs, sh);
+            band_solve<26, true>(ab, sinv, s_nr, Nd, LDa, zs, sh);
             for (int a = tid; a < Nd; a += blockDim.x) vec[a] = zs[a];
             __syncthreads();
         } else {
-            band_solve(ab, sinv, s_nr, Nd, LDa, vec, sh);
+            band_solve<26, true>(ab, sinv, s_nr, Nd, LDa, vec, sh);
         }
     };
     solve(zeta);
