@@ -52,8 +52,8 @@ def quality_table(b, b_data, opt_img):
 
 
 def save_results(params: dict, b, b_data, x, opt_img, log, out_root: Optional[str] = None) -> dict:
-    """save_results(params, b, b_data, x, opt_img, st) for scalar (:185-217) and patch (:220-258)
-    parameters.  `params` needs `dataset_name` and `save_prefix`; nothing is written when
+    """save_results(params, b, b_data, x, opt_img, st) for scalar (:185-217), patch (:220-258) and
+    m×n×3 sum-of-regularisers (:260-299) parameters.  `params` needs `dataset_name` and `save_prefix`; nothing is written when
     `params["save_results"]` is false (:186).  Returns the paths it wrote."""
     if not params.get("save_results", True):
         return {}
@@ -72,8 +72,19 @@ def save_results(params: dict, b, b_data, x, opt_img, log, out_root: Optional[st
                 p = f"{stem}_{tag}_{i}.png"
                 _save_png(p, img[:, :, i - 1])
                 written["png"].append(p)
-        io.write(f"\t\t\t\t\t {mean_ssim}\t {mean_psnr}\n")
+        # the m×n×3 method accumulates `mean_psnr += mean_psnr` (:282): the file's last PSNR field is 0.0 there
+        file_psnr = 0.0 if np.ndim(x) == 3 else mean_psnr
+        io.write(f"\t\t\t\t\t {mean_ssim}\t {file_psnr}\n")
     xa = np.asarray(x, dtype=np.float64)
+    if xa.ndim == 3:   # three patch parameters: up-sampled, stretched JOINTLY (adjust_histogram! on the M×N×3 array), one PNG each (:291-297)
+        M, N = b.shape[:2]
+        ii = (np.arange(M) * xa.shape[0]) // M
+        jj = (np.arange(N) * xa.shape[1]) // N
+        xbar = linear_stretch(np.stack([xa[:, :, k][np.ix_(ii, jj)] for k in range(xa.shape[2])], axis=2))
+        for k in range(xa.shape[2]):
+            p = f"{stem}_par_{k + 1}.png"
+            _save_png(p, xbar[:, :, k])
+            written["png"].append(p)
     if xa.ndim == 2:   # patch parameter: block-constant up-sampling (PatchOp, S7), stretched, as PNG (:252-257)
         M, N = b.shape[:2]
         ii = (np.arange(M) * xa.shape[0]) // M

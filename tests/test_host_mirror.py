@@ -92,3 +92,9 @@ def test_save_results_writes_the_reference_artefacts(bp, datasets, tmp_path):
     par = np.asarray(Image.open([p for p in w2["png"] if p.endswith("_par.png")][0]))
     assert par.shape == (128, 128) and par[0, 0] == 0 and par[127, 127] == 255 and par[0, 127] == 64
     assert results.save_results(dict(prm, save_results=False), t, d, 0.07, reco, log, out_root=str(tmp_path)) == {}
+    # m×n×3 parameter (:260-299): three jointly stretched maps; the file's mean PSNR is the reference's 0.0 (:282)
+    x3 = np.stack([np.array([[0.1, 0.2], [0.3, 0.5]]) * s for s in (1.0, 0.5, 2.0)], axis=2)
+    w3 = results.save_results(dict(prm, save_prefix="sumregs_patch"), t, d, x3, reco, log, out_root=str(tmp_path))
+    pars = [np.asarray(Image.open(p)) for p in w3["png"] if "_par_" in p]
+    assert len(pars) == 3 and pars[2][127, 127] == 255 and pars[1][0, 0] == 0 and pars[0][127, 127] < 255
+    assert float(open(w3["quality"]).read().splitlines()[3].split()[1]) == 0.0 and w3["mean_psnr"] > 0

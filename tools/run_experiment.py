@@ -4,9 +4,10 @@
     python tools/run_experiment.py scalar_bilevel_tv_learn   --dataset_name cameraman_128_5 --datasets_dir BPLDenoising/datasets
     python tools/run_experiment.py patch_bilevel_tv_learn    --dataset_name circle_128_10
     python tools/run_experiment.py scalar_bilevel_sumregs_learn --dataset_name cameraman_128_5
+    python tools/run_experiment.py patch_bilevel_sumregs_learn  --dataset_name cameraman_128_5
     python tools/run_experiment.py validate_tv_parameter --parameter 0.07 --dataset_name faces_val_128_10
 
-Each follows /root/reference/src/BPLDenoising.jl (:325-344, :359-376, :432-451, :381-415): load the
+Each follows /root/reference/src/BPLDenoising.jl (:325-344, :359-376, :432-451, :464-481, :381-415): load the
 dataset (filelist.txt + PNG pairs, Datasets.jl:54-65), take `num_samples` images, run the trust-region
 driver with the library-backed learning function, stretch and save the artefacts (`save_results`,
 :185-258) under <output>/<dataset_name>/.  Everything numerical happens in libbpltv on the GPU.
@@ -26,7 +27,8 @@ from bpldenoising_b200 import results, trbox  # noqa: E402
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("experiment", choices=["scalar_bilevel_tv_learn", "patch_bilevel_tv_learn",
-                                           "scalar_bilevel_sumregs_learn", "validate_tv_parameter"])
+                                           "scalar_bilevel_sumregs_learn", "patch_bilevel_sumregs_learn",
+                                           "validate_tv_parameter"])
     ap.add_argument("--dataset_name", default="cameraman_128_5")          # default_params (:306-314)
     ap.add_argument("--datasets_dir", default="BPLDenoising/datasets/")   # Datasets.jl:9
     ap.add_argument("--num_samples", type=int, default=1)
@@ -50,14 +52,16 @@ def main(argv=None):
         data = (np.asfortranarray(b[:, :, :k]), np.asfortranarray(b_noisy[:, :, :k]))
         run = {"scalar_bilevel_tv_learn": (trbox.scalar_bilevel_tv_learn, "tv_optimal_parameter_scalar_"),
                "patch_bilevel_tv_learn": (trbox.patch_bilevel_tv_learn, "tv_optimal_parameter_(2, 2)_"),
-               "scalar_bilevel_sumregs_learn": (trbox.scalar_bilevel_sumregs_learn, "sumregs_optimal_parameter_scalar_")}
+               "scalar_bilevel_sumregs_learn": (trbox.scalar_bilevel_sumregs_learn, "sumregs_optimal_parameter_scalar_"),
+               # "sumregs_optimal_parameter_patch_$(size(params.α₀))" * dataset_name (:467): no separator
+               "patch_bilevel_sumregs_learn": (trbox.patch_bilevel_sumregs_learn, "sumregs_optimal_parameter_patch_(2, 2, 3)")}
         fn, prefix = run[a.experiment]
         res = fn(data, ctx=ctx, maxiter=a.maxiter, tol=a.tol)
         prm = dict(dataset_name=name, save_prefix=prefix + name, save_results=True, maxiter=a.maxiter, tol=a.tol,
                    num_samples=k)
         # adjust_histogram!(…, LinearStretching()) on u (and, for the TV experiments, on b and b_noisy) (:337-339)
         u = results.linear_stretch(res.u)
-        if a.experiment != "scalar_bilevel_sumregs_learn":
+        if "sumregs" not in a.experiment:
             data = (results.linear_stretch(data[0]), results.linear_stretch(data[1]))
         w = results.save_results(prm, data[0], data[1], res.x, u, res.log, out_root=a.output)
         print(f"x = {np.asarray(res.x).tolist()}, {res.evaluations} evaluations in {res.seconds:.2f} s, "
