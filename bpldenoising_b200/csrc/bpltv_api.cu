@@ -839,22 +839,24 @@ static int set_dataset_impl(bpltv_ctx *ctx, const double *truth, const double *n
 
 // gradient / gradient_reg of the TV learning function.  The regularised branch has two implementations:
 // the multiplier-space banded Cholesky of gradient.cuh and the node-space band LU of lu_band.cuh
-// (n² unknowns with half-bandwidth n instead of ≤ 2n² modes with half-bandwidth ≤ 2n+1).  Measured on B200
-// (tools/time_tv_grad_reg.py), LU vs Cholesky: 25.4 vs 34.6 ms (1 image 128²), 29.6 vs 38.2 (10), 31.6 vs 37.0
-// (148), 25.5 vs 25.5 / 29.7 vs 35.1 (2×2 patch parameter, 1 / 10 images), 144 vs 337 (32 images of 256², 4-CTA
-// clusters), but 236 vs 217 for 128 images of 256² (one CTA each).  Hence: LU up to 128×128, and beyond when the
-// batch leaves every image a cluster; BPLTV_GRAD_REG_LU=0/1 overrides.
+// (n² unknowns with half-bandwidth n instead of ≤ 2n² modes with half-bandwidth ≤ 2n+1; its cost does not grow
+// with the number of flat pixels, each of which is two modes of the multiplier form).  Measured on B200
+// (tools/time_tv_grad_reg.py, tools/time_c5_reg.py), LU vs Cholesky: 25.4 vs 34.6 ms (1 image 128²), 29.6 vs 38.2
+// (10), 31.6 vs 37.0 (148), 25.5 vs 25.5 / 29.7 vs 35.1 (2×2 patch parameter, 1 / 10 images), 144 vs 337 (32 images
+// of 256², 4-CTA clusters), 253 vs 590 (BASELINE config 5's share of one GPU: 128 images of 256², 5000 inner
+// iterations).  Hence the LU whenever it takes the shape; BPLTV_GRAD_REG_LU=0/1 overrides.
 template <typename Real>
 static int run_tv_gradient(Dev &d, const GradProblem<Real> &gp, cudaStream_t st, double *d_grad_out)
 {
     const char *lu_env = getenv("BPLTV_GRAD_REG_LU");
-    const bool lu = lu_env && *lu_env ? atoi(lu_env) != 0 : (gp.M <= 128 || 2 * gp.O <= d.sm_count);
+    const bool lu = lu_env && *lu_env ? atoi(lu_env) != 0 : true;
     if (gp.regularised && lu && gp.M == gp.N && gp.M >= 4) {
         LuProblem<Real> lp;
         lp.u = gp.u; lp.ubar = gp.ubar; lp.M = gp.M; lp.N = gp.N; lp.O = gp.O;
         lp.alpha[0] = gp.alpha_s; lp.alpha[1] = lp.alpha[2] = 0.0;
         lp.alpha_maps = gp.alpha_map; lp.lm = gp.lm; lp.ln = gp.ln; lp.gamma = gp.gamma; lp.nops = 1;
-        return run_gradient_lu<Real>(d.grad, lp, d.sm_count, d.smem_optin, st, d_grad_out, &d.launches);
+        const int rc = run_gradient_lu<Real>(d.grad, lp, d.sm_count, d.smem_optin, st, d_grad_out, &d.launches);
+        if (rc != -1) return rc;      // -1: the LU does not take this shape (panels beyond shared memory): Cholesky
     }
     return run_gradient<Real>(d.grad, gp, d.sm_count, d.smem_optin, st, d_grad_out, &d.launches);
 }
