@@ -471,11 +471,16 @@ def learn_eval_extras(bp):
         xp = 0.001 * np.ones((2, 2, 3))
         c.sumregs_learn_eval(xp, 1e-4)
         for name, Delta in (("patch_sumregs_gradient", 0.1), ("patch_sumregs_gradient_reg", 1e-4)):
-            t0 = time.perf_counter()
-            _, cost, g = c.sumregs_learn_eval(xp, Delta)
-            st = c.stats()
-            rec[name] = {"ms": (time.perf_counter() - t0) * 1e3, "ms_pdps": st["ms_pdps"], "ms_gradient": st["ms_gradient"],
-                         "cost": cost, "grad": np.asarray(g).ravel().tolist()}
+            best = None
+            for rep in range(3):     # best of 3: the first evaluation after a change of branch has been seen to take twice as long
+                t0 = time.perf_counter()
+                _, cost, g = c.sumregs_learn_eval(xp, Delta)
+                st = c.stats()
+                r = {"ms": (time.perf_counter() - t0) * 1e3, "ms_pdps": st["ms_pdps"], "ms_gradient": st["ms_gradient"],
+                     "cost": cost, "grad": np.asarray(g).ravel().tolist(), "best_of": 3}
+                if best is None or r["ms"] < best["ms"]:
+                    best = r
+            rec[name] = best
         out["sumregs_cameraman_128_5"] = rec
 
     # λ-sweep (generate_scalar_tv_cost, /root/reference/src/BPLDenoising.jl:92-130): 64 parameters ×
