@@ -89,25 +89,33 @@ static int run_gradient_lu(GradWork &w, const LuProblem<Real> &gp, int sm_count,
     const size_t ssmem = lu_solve_smem(N, vec_in_smem);
 
     const size_t per_slot = (ws.ab_stride + ws.pix_stride) * 8 + 16;
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
-    const size_t have = w.lu_cap_N == (size_t)N ? w.lu_cap_slots : 0;
-    const size_t budget = (free_b + have * per_slot) / 2;
-    int slots = (int)std::min<size_t>((size_t)std::min(gp.O, sm_count), std::max<size_t>(1, budget / per_slot));
-    if (w.lu_cap_N != (size_t)N || w.lu_cap_slots < (size_t)slots) {
-        void **all[] = {&w.lu_ab, &w.lu_pix, &w.lu_info};
-        for (void **p : all) { if (*p) cudaFree(*p); *p = nullptr; }
-        cudaError_t e = cudaMalloc(&w.lu_ab, ws.ab_stride * 8 * slots);
-        if (e == cudaSuccess) e = cudaMalloc(&w.lu_pix, ws.pix_stride * 8 * slots);
-        if (e == cudaSuccess) e = cudaMalloc(&w.lu_info, 16 * (size_t)slots);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            w.lu_cap_slots = 0; w.lu_cap_N = 0;
-            return grad_fail(w, -6, std::string("band-LU workspace allocation failed: ") + cudaGetErrorString(e));
-        }
-        w.lu_cap_slots = slots; w.lu_cap_N = N;
+    // workspace: kept across calls; the driver is asked about free memory only when it has to grow
+    const size_t key = (size_t)N * 4096 + (size_t)ws.LD;      // image size and band pitch (TV: n+…, sum of regularisers: 2n+…)
+    const int want = std::min(gp.O, sm_count);
+    int slots;
+    if (w.lu_cap_N == key && w.lu_cap_slots >= (size_t)want) {
+        slots = want;
     } else {
-        slots = (int)std::min<size_t>(w.lu_cap_slots, (size_t)std::min(gp.O, sm_count));
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const size_t have = w.lu_cap_N == key ? w.lu_cap_slots : 0;
+        const size_t budget = (free_b + have * per_slot) / 2;
+        slots = (int)std::min<size_t>((size_t)want, std::max<size_t>(1, budget / per_slot));
+        if (w.lu_cap_N != key || w.lu_cap_slots < (size_t)slots) {
+            void **all[] = {&w.lu_ab, &w.lu_pix, &w.lu_info};
+            for (void **p : all) { if (*p) cudaFree(*p); *p = nullptr; }
+            cudaError_t e = cudaMalloc(&w.lu_ab, ws.ab_stride * 8 * slots);
+            if (e == cudaSuccess) e = cudaMalloc(&w.lu_pix, ws.pix_stride * 8 * slots);
+            if (e == cudaSuccess) e = cudaMalloc(&w.lu_info, 16 * (size_t)slots);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                w.lu_cap_slots = 0; w.lu_cap_N = 0;
+                return grad_fail(w, -6, std::string("band-LU workspace allocation failed: ") + cudaGetErrorString(e));
+            }
+            w.lu_cap_slots = slots; w.lu_cap_N = key;
+        } else {
+            slots = (int)std::min<size_t>(w.lu_cap_slots, (size_t)want);
+        }
     }
     if (w.cap_O < (size_t)gp.O || w.cap_ng < (size_t)(nops * ng)) {
         if (w.out_img) cudaFree(w.out_img);

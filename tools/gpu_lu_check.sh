@@ -1,6 +1,5 @@
 set -x
 mkdir -p gpurun_out
-L=gpurun_out/wide_solve.log
-( timeout 900 python -m pytest tests/test_gpu_sumregs.py tests/test_gpu_gradient.py -x -q 2>&1 | tail -5
-  timeout 900 python tools/time_sumregs_grad.py 2>&1 | tail -20 ) > $L 2>&1
-tail -60 $L
+( timeout 900 python -m pytest tests/test_gpu_sumregs.py tests/test_gpu_gradient.py -x -q 2>&1 | tail -4
+  timeout 300 python tools/_probe2.py 2>&1 | tail -12 ) > gpurun_out/probe2.log 2>&1
+tail -30 gpurun_out/probe2.log
