@@ -1196,11 +1196,17 @@ static int run_gradient(GradWork &w, const GradProblem<Real> &gp, int sm_count, 
     // slots: one CTA per image, at most one per SM, bounded by a workspace budget
     const size_t per_slot = (ws.pix_stride + ws.mode_stride + ws.sinv_stride + ws.ab_stride) * 8 +
                             (ws.off_stride + ws.ext_stride + 4) * 4;
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
-    size_t have = w.cap_N == (size_t)N ? w.cap_slots : 0;
-    size_t budget = (free_b + have * per_slot) / 2;
-    int slots = (int)std::min<size_t>((size_t)std::min(gp.O, sm_count), std::max<size_t>(1, budget / per_slot));
+    // the driver is asked about free memory only when the workspace has to grow (the query costs host time
+    // inside the timed gradient phase)
+    const int want_slots = std::min(gp.O, sm_count);
+    int slots = want_slots;
+    if (w.cap_N != (size_t)N || w.cap_slots < (size_t)want_slots) {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        size_t have = w.cap_N == (size_t)N ? w.cap_slots : 0;
+        size_t budget = (free_b + have * per_slot) / 2;
+        slots = (int)std::min<size_t>((size_t)want_slots, std::max<size_t>(1, budget / per_slot));
+    }
     if (w.cap_N != (size_t)N || w.cap_slots < (size_t)slots) {
         void **all[] = {&w.pix, &w.mode, &w.sinv, &w.ab, &w.off, &w.ext, &w.info};
         for (void **p : all) { if (*p) cudaFree(*p); *p = nullptr; }

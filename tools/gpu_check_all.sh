@@ -4,4 +4,3 @@ mkdir -p gpurun_out
 python __graft_entry__.py smoke 2>&1 | tail -2
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r1.json 2> gpurun_out/bench_r1.err; tail -c 600 gpurun_out/bench_r1.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r1_reference.json 2>> gpurun_out/bench_r1.err
-python tools/config5.py 128 5000 > gpurun_out/config5_share128.json 2> gpurun_out/config5_share128.err; tail -n 1 gpurun_out/config5_share128.json; tail -c 300 gpurun_out/config5_share128.err
