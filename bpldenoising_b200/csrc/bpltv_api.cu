@@ -15,6 +15,8 @@
 #include <string>
 #include <vector>
 
+#include <cstddef>
+
 #include "../../include/bpltv.h"
 #include "common.cuh"
 #include "pdps_generic.cuh"
@@ -25,6 +27,11 @@
 #include "gradient.cuh"
 #include "gradient_sumregs.cuh"
 #include "gradient_lu.cuh"
+
+// the option structs are mirrored field by field in bpldenoising_b200/_lib.py (ctypes) and julia/BPLTV.jl
+static_assert(sizeof(bpltv_pdps_opts) == 72, "bpltv_pdps_opts layout");
+static_assert(sizeof(bpltv_eval_opts) == 144 && offsetof(bpltv_eval_opts, gamma_patch) == 128, "bpltv_eval_opts layout");
+static_assert(sizeof(bpltv_stats) == 120, "bpltv_stats layout");
 
 using namespace bpltv;
 

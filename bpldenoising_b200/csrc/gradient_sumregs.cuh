@@ -388,7 +388,10 @@ static int run_gradient3(GradWork &w, const Grad3Problem<Real> &gp, int sm_count
         // instead of ≤ 6n² modes with half-bandwidth ≤ 6(2n+1) in multiplier space.  BPLTV_SUMREGS_REG_LU=0/1.
         const char *lu_env = getenv("BPLTV_SUMREGS_REG_LU");
         const bool lu = lu_env && *lu_env ? atoi(lu_env) != 0 : BPLTV_SUMREGS_REG_LU_DEFAULT;
-        if (gp.regularised && lu) return band_lu();
+        if (gp.regularised && lu) {
+            const int rc = band_lu();
+            if (rc != -1) return rc;      // -1: the LU does not take this shape; the compliance form below may
+        }
     }
     GradSlots ws;
     ws.N = N; ws.n = n;

@@ -38,7 +38,8 @@ def test_defaults_are_the_reference_parameters(bp):
 def test_struct_layout_matches_c(bp):
     # sizes the C compiler computes for the header's structs (natural alignment)
     assert C.sizeof(bp._lib.PdpsOpts) == 4 * 8 + 10 * 4
-    assert C.sizeof(bp._lib.EvalOpts) == C.sizeof(bp._lib.PdpsOpts) + 5 * 8 + 8 * 4
+    assert C.sizeof(bp._lib.EvalOpts) == C.sizeof(bp._lib.PdpsOpts) + 5 * 8 + 8 * 4 == 144
+    assert bp._lib.EvalOpts.gamma_patch.offset == 128      # static_assert'ed on the C side (bpltv_api.cu)
     assert C.sizeof(bp._lib.Stats) == 6 * 8 + 4 * 8 + 8 + 8 * 4
 
 
