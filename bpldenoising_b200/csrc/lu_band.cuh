@@ -1,27 +1,35 @@
-// lu_band.cuh — node-space adjoint solve of the ROW-SCALED regularised sum-of-regularisers system (fp64).
+// lu_band.cuh — node-space band LU for the regularised adjoint systems (fp64).
 //
-// Replaces the patch variant of sumregs_gradient_reg, /root/reference/src/SumRegsLearningFunction.jl:195-262:
+// Written for the patch variant of sumregs_gradient_reg, /root/reference/src/SumRegsLearningFunction.jl:195-262:
 //     p = (I + x₁[:] .* G₁ᵀ(B₁−C₁)G₁ + x₂[:] .* G₂ᵀ(B₂−C₂)G₂ + x₃[:] .* G₃ᵀ(B₃−C₃)G₃) \ (ū − u)       (:246)
 //     g_k = p ⊙ G_kᵀ(Act_k Den_k G_k u + γ Inact_k G_k u),   gx[:,:,k] = calc_adjoint(pOp, g_k)          (:247-259)
 // `x_k[:] .*` scales the ROWS of each term by a different λ-map, so the matrix is not symmetric and has
 // no compliance (Cholesky) form.  It is a banded n²×n² matrix on the column-major nodes, though: the
-// stencils of G_kᵀ T G_k reach ±2 rows and ±2 columns, half-bandwidth 2n.  Per image (one CTA each):
+// stencils of G_kᵀ T G_k reach ±2 rows and ±2 columns, half-bandwidth 2n.  The same kernels carry the scalar
+// sumregs_gradient_reg (:112-167) and, with the forward operator alone (nops = 1, half-bandwidth n), gradient_reg
+// of the TV learning function (/root/reference/src/TVLearningFunctionVec.jl:137-161, :192-215); see gradient_lu.cuh.
+// Per image, one CTA or one thread-block cluster:
 //   lu3_classify   per (pixel, operator): the 2×2 tensor T = B − C and the functional weights
 //   lu3_assemble   one thread per matrix row, 13 stencil offsets, fixed summation order (deterministic)
-//   lu_factor      blocked right-looking band LU without pivoting, NB = 16: diagonal block in one warp,
-//                  L21 rows / U12 columns by substitution (one thread each, panels kept in shared memory),
-//                  rank-16 update of the bw×bw trailing window in 8×4 register tiles
-//   lu3_solve      blocked forward / backward substitution with the vector in shared memory, iterative
-//                  refinement against the MATRIX-FREE residual (stencils + tensors, independent of the
-//                  assembled band), functional, PatchOp-adjoint sums
+//   lu_factor      blocked right-looking band LU without pivoting, NB = 16: the 16×16 diagonal block in one
+//                  warp's registers (shuffles, Newton reciprocal of the pivots), L21 rows / U12 columns by
+//                  substitution (one thread each; inputs staged with cp.async under the diagonal block's
+//                  factorisation, panels kept in shared memory, L21 transposed), rank-16 update of the bw×bw
+//                  trailing window in 32×32 warp tiles (8×4 per thread), optionally dealt over a cluster
+//   lu3_solve      blocked forward / backward substitution with the vector in shared memory and the factor
+//                  entries prefetched one block step ahead, iterative refinement against the MATRIX-FREE
+//                  residual (stencils + tensors, independent of the assembled band), functional,
+//                  PatchOp-adjoint sums
 // No pivoting: every term is (positive diagonal)·(PSD); for equal maps the matrix is D·SPD, whose LU needs
 // none.  A vanished pivot, or a solve whose normwise backward error stays above 1e-11 after refinement,
 // poisons the output with NaN, which the API reports as BPLTV_ERR_NUMERIC — no silent wrong answer.
 // Band storage: row i holds columns i−bwx … i+bwx at ab[i·LD + (j−i+bwx)], bwx = bw + NB, so that every
-// index a block step forms is inside the row's storage (entries outside the true band stay exactly zero).
+// index a block step forms is inside the row's storage (entries outside the true band stay exactly zero);
+// LD = 2·bwx + 1 is odd, which makes every window segment that starts at an even column 16-byte aligned.
 //
 // This header holds device code only and depends on sumregs_stencils.cuh alone: tests/emu/ compiles it with
-// g++ and runs the kernels on OS threads (CPU check of the index arithmetic and barriers; no GPU needed).
+// g++ and runs the kernels on OS threads (CPU check of the index arithmetic, the barriers and the 16-byte
+// alignment of every vector access; no GPU needed).
 #pragma once
 #ifndef BPLTV_EMU
 #include <cooperative_groups.h>
