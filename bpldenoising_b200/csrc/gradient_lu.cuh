@@ -12,6 +12,10 @@
 
 namespace bpltv {
 
+// half-bandwidth of the node-space system: n (forward differences alone) or 2n (with the centred ones), rounded up
+// to EVEN — the 16-byte alignment of the kernels' vector accesses rests on it (n ≥ 4, so it stays below n² − 1)
+static inline int lu_band_halfwidth(int nops, int n) { return ((nops == 1 ? n : 2 * n) + 1) & ~1; }
+
 template <typename Real>
 struct LuProblem {
     const Real *u, *ubar;
@@ -79,7 +83,7 @@ static int run_gradient_lu(GradWork &w, const LuProblem<Real> &gp, int sm_count,
     if (nops * ng > 1024) return grad_fail(w, -1, "lambda grid larger than 1024 entries is not supported");
     if (n < 4) return grad_fail(w, -1, "images smaller than 4x4 are not supported by the band LU");
     LuSlots ws;
-    ws.n = n; ws.N = N; ws.nops = nops; ws.bw = std::min(nops == 1 ? n : 2 * n, N - 1); ws.bwx = ws.bw + LU_NB; ws.LD = 2 * ws.bwx + 1;
+    ws.n = n; ws.N = N; ws.nops = nops; ws.bw = lu_band_halfwidth(nops, n); ws.bwx = ws.bw + LU_NB; ws.LD = 2 * ws.bwx + 1;
     ws.ab_stride = ((size_t)N * ws.LD + 3) & ~(size_t)3;
     ws.pix_stride = (size_t)LU_PLANES * N;
     ws.use_pin = (2 * ws.bw <= LU_THREADS && lu_factor_smem(ws.bw, true) <= smem_optin) ? 1 : 0;

@@ -16,7 +16,7 @@ extern "C" int emu_lu_gradient(int use_pin, int csize, int nops, int n, const do
 {
     const int N = n * n;
     LuSlots ws;
-    ws.n = n; ws.N = N; ws.nops = nops; ws.use_pin = (use_pin && 2 * std::min(nops == 1 ? n : 2 * n, N - 1) <= LU_THREADS) ? 1 : 0; ws.bw = std::min(nops == 1 ? n : 2 * n, N - 1); ws.bwx = ws.bw + LU_NB; ws.LD = 2 * ws.bwx + 1;
+    ws.n = n; ws.N = N; ws.nops = nops; ws.use_pin = (use_pin && 2 * (((nops == 1 ? n : 2 * n) + 1) & ~1) <= LU_THREADS) ? 1 : 0; ws.bw = ((nops == 1 ? n : 2 * n) + 1) & ~1; /* = lu_band_halfwidth (gradient_lu.cuh) */ ws.bwx = ws.bw + LU_NB; ws.LD = 2 * ws.bwx + 1;
     ws.ab_stride = ((size_t)N * ws.LD + 3) & ~(size_t)3; ws.pix_stride = (size_t)LU_PLANES * N;
     if (ld_out) *ld_out = ws.LD;
     std::vector<double> ab_store(ws.ab_stride + 2, 0.0), pix(ws.pix_stride, 0.0);

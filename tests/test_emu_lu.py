@@ -47,7 +47,7 @@ def _case(n, seed):
 
 def _run(lib, n, u, t, maps, alpha3, gamma, grid, vec_in_smem, want_band=False, nops=3, csize=1, use_pin=1):
     N = n * n
-    bw = min(n if nops == 1 else 2 * n, N - 1)
+    bw = ((n if nops == 1 else 2 * n) + 1) & ~1          # lu_band_halfwidth (gradient_lu.cuh): even
     LD = 2 * (bw + 16) + 1
     out = np.zeros(nops * grid[0] * grid[1])
     band = np.zeros((N * LD + 3) & ~3) if want_band else None
@@ -137,3 +137,22 @@ def test_band_lu_cluster_factorisation_is_invisible_on_the_thread_emulation():
     a, _, _, _ = _run(lib128, n, u, t, maps, None, 1e8, (2, 2), 1, use_pin=1)
     b, _, _, _ = _run(lib128, n, u, t, maps, None, 1e8, (2, 2), 1, use_pin=0)
     assert np.array_equal(a, b) and np.allclose(a, one, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("threads,n,nops,cs,pin", [(128, 9, 3, 2, 1), (128, 13, 1, 3, 1), (64, 11, 3, 1, 0), (256, 17, 1, 2, 1)])
+def test_band_lu_odd_sizes_clusters_and_staging_on_the_thread_emulation(threads, n, nops, cs, pin):
+    """Odd image sizes (the forward-only band has half-width n: rounded up to even for the 16-byte accesses, which
+    the emulation checks), short last blocks, clusters and the cp.async staging together."""
+    lib = _build(threads)
+    t, u = _case(n, n)
+    if nops == 3:
+        xp = np.stack([np.array([[0.03, 0.05], [0.02, 0.04]]) * s for s in (1.0, 0.7, 1.3)], axis=2)
+        maps = [np.asfortranarray(orc.patch_upsample(xp[:, :, k], n, n)) for k in range(3)]
+        got, _, _, _ = _run(lib, n, u, t, maps, None, 1e8, (2, 2), 1, nops=3, csize=cs, use_pin=pin)
+        lit = sr.sumregs_gradient_reg(maps, u, t, grid_shape=(2, 2), gamma=1e8, refine=3)
+    else:
+        x = np.array([[0.05, 0.1], [0.08, 0.02]])
+        amap = np.asfortranarray(orc.patch_upsample(x, n, n))
+        got, _, _, _ = _run(lib, n, u, t, [amap], None, 1e8, (2, 2), 1, nops=1, csize=cs, use_pin=pin)
+        got, lit = got[:, :, 0], orc.gradient_reg_patch(amap, (2, 2), u, t, refine=3)
+    assert np.all(np.abs(got - lit) <= 2e-9 * np.abs(lit).max()), (got, lit)

@@ -78,6 +78,15 @@ def test_gradient_reg_by_both_solvers(bp, ctx, oracle, datasets, monkeypatch):
         assert _rel(gs, lit_s) <= 1e-9 and _rel(gp, lit_p) <= 1e-9, mode
         got[mode] = (gs, gp)
     assert _rel(got["0"][0], got["1"][0]) <= 1e-11 and _rel(got["0"][1], got["1"][1]) <= 1e-11
+    # odd image size: the forward-only band has half-width n, which the LU rounds up to even for its 16-byte accesses
+    t, f = (a[10:47, 20:57, :1] for a in datasets["cameraman_128_5"])
+    t, f = (np.concatenate([a, a[::-1, :, :]], axis=2).copy(order="F") for a in (t, f))     # two 37×37 images
+    u = oracle.pdps(f, 0.08, maxiter=800)
+    ctx.set_dataset((t, f))
+    monkeypatch.setenv("BPLTV_GRAD_REG_LU", "1")
+    g = ctx.gradient(0.08, u, regularised=True)
+    dual = sum(oracle.gradient_dual("reg", 0.08, u[:, :, i], t[:, :, i]) for i in range(2))
+    assert _rel(g, dual) <= 1e-10
 
 
 @pytest.mark.parametrize("name,lam", [("cameraman_128_5", 0.1), ("faces_train_128_10", 0.05), ("circle_128_10", 0.02)])
