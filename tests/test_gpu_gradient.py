@@ -87,6 +87,10 @@ def test_gradient_reg_by_both_solvers(bp, ctx, oracle, datasets, monkeypatch):
     g = ctx.gradient(0.08, u, regularised=True)
     dual = sum(oracle.gradient_dual("reg", 0.08, u[:, :, i], t[:, :, i]) for i in range(2))
     assert _rel(g, dual) <= 1e-10
+    monkeypatch.setenv("BPLTV_GRAD_REG_LU", "0")
+    assert _rel(ctx.gradient(0.08, u, regularised=True), dual) <= 1e-10           # the Cholesky at the odd size
+    dual_n = sum(oracle.gradient_dual("nonreg", 0.08, u[:, :, i], t[:, :, i]) for i in range(2))
+    assert _rel(ctx.gradient(0.08, u, regularised=False), dual_n) <= 1e-10        # and the non-regularised branch
 
 
 @pytest.mark.parametrize("name,lam", [("cameraman_128_5", 0.1), ("faces_train_128_10", 0.05), ("circle_128_10", 0.02)])
