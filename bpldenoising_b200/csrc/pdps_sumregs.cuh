@@ -12,7 +12,9 @@
 // One IEEE operation per operator of the reference expression in strict mode (bit-identical to
 // oracle/sumregs.py), FMA / rsqrt in fast mode.
 #pragma once
+#ifndef BPLTV_EMU      // tests/emu/emu_cuda.h supplies cooperative_groups::this_cluster() on OS threads
 #include <cooperative_groups.h>
+#endif
 
 #include <algorithm>
 #include <cstdlib>
@@ -133,7 +135,11 @@ __global__ void __launch_bounds__(SRR_THREADS, 1) sumregs_resident_kernel(const 
 {
     namespace cg = cooperative_groups;
     typedef Ar<Real, STRICT> A;
+#ifdef BPLTV_EMU
+    unsigned char *srr_smem = reinterpret_cast<unsigned char *>(emu::dyn_smem());
+#else
     extern __shared__ __align__(16) unsigned char srr_smem[];
+#endif
     cg::cluster_group cluster = cg::this_cluster();
     const int CS = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
@@ -285,6 +291,7 @@ static inline SumRegsResPlan sumregs_resident_plan(size_t smem_optin, int M, int
     return p;
 }
 
+#ifndef BPLTV_EMU      // host-side launch (CUDA runtime)
 template <typename Real, int KP>
 static inline cudaError_t launch_sumregs_resident_kp(const SumRegsResArgs<Real> &a, const SumRegsResPlan &p, bool map,
                                                      bool strict, cudaStream_t st)
@@ -343,5 +350,6 @@ static inline cudaError_t launch_sumregs_resident(SumRegsResArgs<Real> a, size_t
     }
     return last;
 }
+#endif  // BPLTV_EMU
 
 }  // namespace bpltv

@@ -17,6 +17,10 @@ struct dim3 {
     dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
 struct double2 { double x, y; };
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+inline float2 make_float2(float a, float b) { return float2{a, b}; }
+inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
 inline double2 make_double2(double a, double b) { return double2{a, b}; }
 
 #define __global__
@@ -26,6 +30,7 @@ inline double2 make_double2(double a, double b) { return double2{a, b}; }
 #define __launch_bounds__(...)
 #define __shared__
 #define __align__(x)
+#define __noinline__
 
 #include <cstdint>
 #include <cstdio>
@@ -40,10 +45,12 @@ struct Warp {
     double xch[32];
     Warp() : bar(32) {}
 };
+struct Cta;
 struct Cluster {
     std::barrier<> bar;
     int size;
-    Cluster(int ctas, int threads) : bar((std::ptrdiff_t)ctas * threads), size(ctas) {}
+    std::vector<Cta *> ctas;       // by rank
+    Cluster(int ctas_, int threads) : bar((std::ptrdiff_t)ctas_ * threads), size(ctas_) {}
 };
 struct Cta {
     std::barrier<> bar;
@@ -62,6 +69,11 @@ inline double *dyn_smem()
 {
     double *p = cta->smem.data();
     return (reinterpret_cast<std::uintptr_t>(p) & 15) ? p + 1 : p;     // 16-byte aligned like the GPU's
+}
+inline double *dyn_smem_of(Cta *c)
+{
+    double *p = c->smem.data();
+    return (reinterpret_cast<std::uintptr_t>(p) & 15) ? p + 1 : p;
 }
 inline int cluster_rank() { return cta->rank; }
 inline int cluster_size() { return cta->cluster ? cta->cluster->size : 1; }
@@ -86,6 +98,38 @@ inline double __shfl_xor_sync(unsigned m, double v, int o) { return __shfl_sync(
 using std::max;
 using std::min;
 
+// one correctly rounded IEEE operation each (compile the harness with -ffp-contract=off), like the intrinsics
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline double __dsub_rn(double a, double b) { return a - b; }
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __ddiv_rn(double a, double b) { return a / b; }
+inline double __dsqrt_rn(double a) { return std::sqrt(a); }
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __fsub_rn(float a, float b) { return a - b; }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fdiv_rn(float a, float b) { return a / b; }
+inline float __fsqrt_rn(float a) { return std::sqrt(a); }
+inline double rsqrt(double a) { return 1.0 / std::sqrt(a); }
+inline float rsqrtf(float a) { return 1.0f / std::sqrt(a); }
+template <typename T> inline T __ldg(const T *p) { return *p; }
+
+// cooperative_groups::this_cluster() for kernels that use the library interface directly
+namespace cooperative_groups {
+struct cluster_group {
+    unsigned num_blocks() const { return (unsigned)emu::cluster_size(); }
+    unsigned block_rank() const { return (unsigned)emu::cluster_rank(); }
+    void sync() const { emu::cluster_sync(); }
+    // the address of `p` (inside this CTA's dynamic shared memory) in the CTA of rank `r`
+    template <typename T> T *map_shared_rank(T *p, unsigned r) const
+    {
+        emu::Cta *me = emu::cta, *other = me->cluster ? me->cluster->ctas[r] : me;
+        const std::ptrdiff_t off = reinterpret_cast<unsigned char *>(p) - reinterpret_cast<unsigned char *>(emu::dyn_smem_of(me));
+        return reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(emu::dyn_smem_of(other)) + off);
+    }
+};
+inline cluster_group this_cluster() { return cluster_group(); }
+}  // namespace cooperative_groups
+
 namespace emu {
 // kernel<<<grid, threads>>>(args...): blocks run one after the other, the threads of a block concurrently
 // (threads must be a multiple of 32: every warp barrier expects 32 arrivals)
@@ -101,6 +145,7 @@ void launch(dim3 grid, int threads, F &&body, size_t smem_doubles = 0, int csize
                 ctas.emplace_back(new Cta(threads, smem_doubles));
                 ctas.back()->rank = r;
                 ctas.back()->cluster = csize > 1 ? &cl : nullptr;
+                cl.ctas.push_back(ctas.back().get());
             }
             std::vector<std::thread> ts;
             for (int r = 0; r < csize; ++r)
