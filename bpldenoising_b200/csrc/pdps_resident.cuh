@@ -18,7 +18,9 @@
 // The path is bounded by barrier latency + shared-memory bandwidth + fp64 issue, not
 // by HBM.  Same operation order as the other kernels: strict mode is bit-identical.
 #pragma once
+#ifndef BPLTV_EMU      // tests/emu/emu_cuda.h supplies cooperative_groups::this_cluster() on OS threads
 #include <cooperative_groups.h>
+#endif
 
 #include <algorithm>
 #include <cstdlib>
@@ -63,7 +65,11 @@ static __device__ __forceinline__ void st2(Real *p, Real a, Real b)
 template <typename Real, int KC, bool MAP, bool STRICT>
 __global__ void __launch_bounds__(RES_THREADS, 1) pdps_resident_kernel(const ResidentArgs<Real> a)
 {
+#ifdef BPLTV_EMU
+    unsigned char *smem_raw = reinterpret_cast<unsigned char *>(emu::dyn_smem());
+#else
     extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
     cg::cluster_group cluster = cg::this_cluster();
     const int CS = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
@@ -234,6 +240,7 @@ static inline bool resident_eligible(size_t smem_optin, int M, int N) { return r
 template <typename Real>
 static inline int resident_cluster_size(size_t smem_optin, int M, int N) { return resident_plan<Real>(smem_optin, M, N).CS; }
 
+#ifndef BPLTV_EMU      // host-side launch (CUDA runtime)
 template <typename Real, int KC>
 static inline cudaError_t launch_resident_kc(const ResidentArgs<Real> &a, const ResidentPlan &p, bool map, bool strict,
                                              cudaStream_t st)
@@ -296,5 +303,6 @@ static inline cudaError_t launch_resident(ResidentArgs<Real> a, size_t smem_opti
     if (p.KC == 2) return launch_resident_kc<Real, 2>(a, p, map, strict, st);
     return launch_resident_kc<Real, 4>(a, p, map, strict, st);
 }
+#endif  // BPLTV_EMU
 
 }  // namespace bpltv

@@ -8,6 +8,7 @@
 #include <barrier>
 #include <cmath>
 #include <cstddef>
+#include <cstring>
 #include <memory>
 #include <thread>
 #include <vector>
@@ -84,16 +85,37 @@ inline thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 inline void __syncthreads() { emu::cta->bar.arrive_and_wait(); }
 inline void __syncwarp() { emu::warp->bar.arrive_and_wait(); }
-inline double __shfl_sync(unsigned, double v, int src)
+// warp shuffles / votes through the per-warp exchange buffer (all 32 lanes take part, as on the GPU)
+template <typename T>
+inline T emu_shfl(T v, int src)
 {
+    static_assert(sizeof(T) <= sizeof(double), "exchange slot");
     emu::Warp &w = *emu::warp;
-    w.xch[threadIdx.x & 31] = v;
+    std::memcpy(&w.xch[threadIdx.x & 31], &v, sizeof(T));
     w.bar.arrive_and_wait();
-    const double r = w.xch[src & 31];
+    T r;
+    std::memcpy(&r, &w.xch[src & 31], sizeof(T));
     w.bar.arrive_and_wait();
     return r;
 }
-inline double __shfl_xor_sync(unsigned m, double v, int o) { return __shfl_sync(m, v, (int)(threadIdx.x & 31) ^ o); }
+template <typename T> inline T __shfl_sync(unsigned, T v, int src) { return emu_shfl(v, src); }
+template <typename T> inline T __shfl_xor_sync(unsigned, T v, int o) { return emu_shfl(v, (int)(threadIdx.x & 31) ^ o); }
+template <typename T> inline T __shfl_up_sync(unsigned, T v, unsigned d)
+{
+    const int lane = (int)(threadIdx.x & 31);
+    return emu_shfl(v, lane >= (int)d ? lane - (int)d : lane);
+}
+template <typename T> inline T __shfl_down_sync(unsigned, T v, unsigned d)
+{
+    const int lane = (int)(threadIdx.x & 31);
+    return emu_shfl(v, lane + (int)d < 32 ? lane + (int)d : lane);
+}
+inline int __any_sync(unsigned, int pred)
+{
+    int any = 0;
+    for (int l = 0; l < 32; ++l) any |= emu_shfl(pred ? 1 : 0, l);      // 32 exchanges: simple, and only used at set-up
+    return any;
+}
 
 using std::max;
 using std::min;
