@@ -40,7 +40,11 @@ struct MarchArgs {
 
 static __device__ __forceinline__ void prefetch_l2(const void *p)
 {
+#ifndef BPLTV_EMU      // a hint only; the thread emulation of tests/emu has no L2
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
 }
 
 template <typename Real, int VEC, bool MAP, bool STRICT, int MAXT, int MINB>

@@ -29,7 +29,9 @@ inline double2 make_double2(double a, double b) { return double2{a, b}; }
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
-#define __shared__
+// static shared arrays: one copy per kernel instantiation, shared by the OS threads of the CTA that is running
+// (non-cluster launches run their CTAs one after the other); dynamic shared memory goes through emu::dyn_smem()
+#define __shared__ static
 #define __align__(x)
 #define __noinline__
 
