@@ -161,6 +161,7 @@ namespace emu {
 template <typename F>
 void launch(dim3 grid, int threads, F &&body, size_t smem_doubles = 0, int csize = 1)
 {
+    for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
         for (unsigned bx0 = 0; bx0 < grid.x; bx0 += (unsigned)csize) {
             Cluster cl(csize, threads);
@@ -175,7 +176,7 @@ void launch(dim3 grid, int threads, F &&body, size_t smem_doubles = 0, int csize
             for (int r = 0; r < csize; ++r)
                 for (int t = 0; t < threads; ++t)
                     ts.emplace_back([&, r, t] {
-                        threadIdx = dim3((unsigned)t); blockIdx = dim3(bx0 + (unsigned)r, by);
+                        threadIdx = dim3((unsigned)t); blockIdx = dim3(bx0 + (unsigned)r, by, bz);
                         blockDim = dim3((unsigned)threads); gridDim = grid;
                         cta = ctas[r].get(); warp = cta->warps[t / 32].get();
                         body();
