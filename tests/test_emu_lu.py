@@ -45,7 +45,8 @@ def _case(n, seed):
     return np.asfortranarray(t), u
 
 
-def _run(lib, n, u, t, maps, alpha3, gamma, grid, vec_in_smem, want_band=False, nops=3, csize=1, use_pin=1):
+def _run(lib, n, u, t, maps, alpha3, gamma, grid, vec_in_smem, want_band=False, nops=3, csize=1, use_pin=1,
+         expect_pivot_failure=False):
     N = n * n
     bw = ((n if nops == 1 else 2 * n) + 1) & ~1          # lu_band_halfwidth (gradient_lu.cuh): even
     LD = 2 * (bw + 16) + 1
@@ -57,7 +58,7 @@ def _run(lib, n, u, t, maps, alpha3, gamma, grid, vec_in_smem, want_band=False, 
     rc = lib.emu_lu_gradient(use_pin, csize, nops, n, _ptr(u.flatten(order="F")), _ptr(t.flatten(order="F")), _ptr(am), _ptr(a3),
                              C.c_double(gamma), grid[0], grid[1], 3, int(vec_in_smem), _ptr(out), C.byref(rr),
                              C.byref(pf), _ptr(band), C.byref(ld))
-    assert rc == 0 and ld.value == LD and pf.value == 0
+    assert rc == 0 and ld.value == LD and (pf.value == 0 or expect_pivot_failure)
     got = out.reshape(nops, grid[1], grid[0]).transpose(2, 1, 0)      # [operator][patch] → (pi, pj, operator)
     return got, rr.value, (None if band is None else band[:N * LD].reshape(N, LD)), bw + 16
 
@@ -156,3 +157,19 @@ def test_band_lu_odd_sizes_clusters_and_staging_on_the_thread_emulation(threads,
         got, _, _, _ = _run(lib, n, u, t, [amap], None, 1e8, (2, 2), 1, nops=1, csize=cs, use_pin=pin)
         got, lit = got[:, :, 0], orc.gradient_reg_patch(amap, (2, 2), u, t, refine=3)
     assert np.all(np.abs(got - lit) <= 2e-9 * np.abs(lit).max()), (got, lit)
+
+
+def test_band_lu_poisons_the_output_when_a_pivot_vanishes():
+    """No silent wrong answer: on a flat image with γ = 2²⁰ and the (unphysical, API-rejected) parameter
+    α = −2⁻²¹ the first pivot 1 + 2αγ is exactly zero — the kernels must flag it and return NaN, which the API turns
+    into BPLTV_ERR_NUMERIC."""
+    lib = _build(64)
+    n = 8
+    u = np.asfortranarray(np.full((n, n), 0.5))
+    t = np.asfortranarray(np.full((n, n), 0.25))
+    out = np.zeros(1)
+    rr, pf, ld = C.c_double(), C.c_int(), C.c_int()
+    a3 = np.array([-2.0 ** -21, 0.0, 0.0])
+    rc = lib.emu_lu_gradient(1, 1, 1, n, _ptr(u.flatten(order="F")), _ptr(t.flatten(order="F")), None, _ptr(a3),
+                             C.c_double(2.0 ** 20), 1, 1, 3, 1, _ptr(out), C.byref(rr), C.byref(pf), None, C.byref(ld))
+    assert rc == 0 and pf.value == 1 and np.isnan(out[0])
