@@ -110,3 +110,14 @@ extern "C" double emu_cost(const double *u, const double *ubar, long long n)
     emu::launch(dim3(1), 256, [&] { sum_partials_kernel(partials.data(), blocks, 0.5, &out); });
     return out;
 }
+
+// PatchOp up-sampling (S7) and the per-image squared errors of the λ-sweeps, as bpltv_api.cu launches them
+extern "C" void emu_patch_upsample(const double *lam, int lm, int ln, double *map, int M, int N)
+{
+    emu::launch(dim3((unsigned)((M * N + 255) / 256)), 256, [&] { patch_upsample_kernel<double>(lam, lm, ln, map, M, N); });
+}
+
+extern "C" void emu_sqerr_images(const double *u, const double *ubar, int plane, int f_mod, int V, double *out)
+{
+    emu::launch(dim3((unsigned)V), 256, [&] { sqerr_image_kernel<double>(u, ubar, plane, f_mod, out); });
+}

@@ -67,3 +67,21 @@ def test_cost_reduction_on_the_thread_emulation(lib):
         got = lib.emu_cost(_ptr(u), _ptr(ub), C.c_longlong(n))
         ref = 0.5 * float(np.sum((u - ub) ** 2))
         assert abs(got - ref) <= 1e-14 * ref + 1e-300, n
+
+
+def test_patch_upsample_and_sweep_errors_on_the_thread_emulation(lib):
+    """PatchOp up-sampling (S7: block-constant, also for grids that do not divide the image) and the per-image squared
+    errors of a λ-sweep (virtual image v = set·O + image reads truth image v % O)."""
+    rng = np.random.default_rng(11)
+    for (M, N, lm, ln) in ((12, 10, 2, 2), (13, 7, 3, 2), (5, 5, 5, 5), (9, 4, 1, 3)):
+        x = np.asfortranarray(rng.uniform(0.01, 0.1, (lm, ln)))
+        out = np.zeros((M, N), order="F")
+        lib.emu_patch_upsample(_ptr(x), lm, ln, _ptr(out), M, N)
+        assert np.array_equal(out, orc.patch_upsample(x, M, N)), (M, N, lm, ln)
+    plane, O, L = 77, 3, 4
+    ub = np.asfortranarray(rng.uniform(0, 1, (plane, O)))
+    u = np.asfortranarray(rng.uniform(0, 1, (plane, O * L)))
+    out = np.zeros(O * L)
+    lib.emu_sqerr_images(_ptr(u), _ptr(ub), plane, O, O * L, _ptr(out))
+    ref = np.array([np.sum((u[:, v] - ub[:, v % O]) ** 2) for v in range(O * L)])
+    assert np.allclose(out, ref, rtol=1e-14, atol=0)
