@@ -84,3 +84,19 @@ def test_learning_function_shapes_and_branches(datasets):
     xp = 0.02 * np.ones((2, 2, 3))
     up, cp, gp = sr.sumregs_learning_function(xp, (t, f), 0.1, maxiter=200)
     assert gp.shape == (2, 2, 3) and np.allclose(up, u) and np.allclose(gp.sum(axis=(0, 1)), g, rtol=1e-5)
+
+
+def test_patch_regularised_system_reduces_to_the_scalar_one_for_uniform_maps(datasets):
+    """Pin for the row-scaled patch system (:195-262), which has no compliance form to be checked against: with three
+    UNIFORM maps its rows are scaled by constants, it is the scalar system (:112-167) at the same γ, and the patch
+    gradients must add up to the scalar gradient (PatchOp adjoint = block sums, S7)."""
+    t, f = datasets["faces_train_128_10"]
+    t, f = np.asfortranarray(t[40:60, 40:60, :1]), np.asfortranarray(f[40:60, 40:60, :1])
+    x = np.array([0.03, 0.02, 0.04])
+    u = sr.sumregs_pdps(f, list(x), maxiter=400)
+    maps = [np.full((20, 20), v) for v in x]
+    for gamma in (1e3, 1e8):
+        gp = sr.sumregs_gradient_reg(maps, u[:, :, 0], t[:, :, 0], grid_shape=(2, 2), gamma=gamma, refine=3)
+        gs = sr.sumregs_gradient_reg(x, u[:, :, 0], t[:, :, 0], gamma=gamma, refine=3)
+        assert gp.shape == (2, 2, 3)
+        assert np.all(np.abs(gp.sum(axis=(0, 1)) - gs) <= 1e-9 * np.abs(gs).max()), (gamma, gp.sum(axis=(0, 1)), gs)
