@@ -27,6 +27,7 @@
 #include "gradient.cuh"
 #include "gradient_sumregs.cuh"
 #include "gradient_lu.cuh"
+#include "gradient_nd.h"
 
 // the option structs are mirrored field by field in bpldenoising_b200/_lib.py (ctypes) and julia/BPLTV.jl
 static_assert(sizeof(bpltv_pdps_opts) == 72, "bpltv_pdps_opts layout");
@@ -112,6 +113,8 @@ struct Dev {
     DBuf x[2], y1[2], y2[2], fbuf, amap, steps, partials, scalars, stage, lam_dev, ubuf, sry;
     GradWork grad;            // gradient.cuh
     GradWork grad3;           // gradient_sumregs.cuh
+    NdWork *nd = nullptr;     // gradient_nd.cuh (nested-dissection adjoint solver), created on first use
+    bool grad_used_nd = false;
     StepKey steps_key;
     std::vector<unsigned char> steps_host;
     long long launches = 0;
@@ -852,9 +855,27 @@ static int set_dataset_impl(bpltv_ctx *ctx, const double *truth, const double *n
 // (10), 31.6 vs 37.0 (148), 25.5 vs 25.5 / 29.7 vs 35.1 (2×2 patch parameter, 1 / 10 images), 144 vs 337 (32 images
 // of 256², 4-CTA clusters), 253 vs 590 (BASELINE config 5's share of one GPU: 128 images of 256², 5000 inner
 // iterations).  Hence the LU whenever it takes the shape; BPLTV_GRAD_REG_LU=0/1 overrides.
+// Solver of the adjoint systems (bpltv_eval_opts.solver): 0 / 2 — nested-dissection multifrontal Cholesky
+// (gradient_nd.cuh: O(n³) operations, the whole GPU per image); 1 — the banded factorisations of round 1 (multiplier-
+// space Cholesky for `gradient`, node-space LU for `gradient_reg`), kept as an independent second implementation.
+// BPLTV_GRAD_SOLVER overrides option 0.
 template <typename Real>
 static int run_tv_gradient(Dev &d, const GradProblem<Real> &gp, cudaStream_t st, double *d_grad_out)
 {
+    int solver = gp.solver;
+    if (solver == 0) solver = env_int("BPLTV_GRAD_SOLVER", 0);
+    d.grad_used_nd = false;
+    if (solver != 1) {
+        if (!d.nd) d.nd = nd_work_create();
+        NdProblem np;
+        np.u = gp.u; np.ubar = gp.ubar; np.prec = (int)sizeof(Real) * 8; np.M = gp.M; np.N = gp.N; np.O = gp.O;
+        np.alpha_s = gp.alpha_s; np.alpha_map = gp.alpha_map; np.lm = gp.lm; np.ln = gp.ln; np.regularised = gp.regularised;
+        np.gamma = gp.gamma; np.act_tol = gp.act_tol; np.eps_act = gp.eps_act; np.tol = gp.tol; np.maxit = gp.maxit;
+        const int rc = nd_run_gradient(d.nd, np, d.sm_count, d.smem_optin, st, d_grad_out, &d.launches);
+        if (rc == 0) { d.grad_used_nd = true; return 0; }
+        if (rc != -1) { d.grad.err = nd_work_error(d.nd); return rc; }
+        // -1: fronts beyond shared memory for this image size — the band solver takes over
+    }
     const char *lu_env = getenv("BPLTV_GRAD_REG_LU");
     const bool lu = lu_env && *lu_env ? atoi(lu_env) != 0 : true;
     if (gp.regularised && lu && gp.M == gp.N && gp.M >= 4) {
@@ -911,15 +932,19 @@ static int learn_eval_impl(bpltv_ctx *ctx, const double *lam, int lm, int ln, do
     const size_t plane = (size_t)ctx->M * ctx->N;
     std::memset(&ctx->stats, 0, sizeof ctx->stats);
     std::vector<std::vector<double>> host(ndev, std::vector<double>(1 + ng, 0.0));
+    std::vector<double> relres(ndev, 0.0);
     for (int di = 0; di < ndev; ++di) {
         Dev &d = ctx->devs[di];
         CU_TRY(cudaSetDevice(d.id));
         d.launches = 0;
+        d.grad_used_nd = false;
         RC_TRY(d.scalars.ensure((1 + ng) * sizeof(double)));
         const Real *u = nullptr;
         RC_TRY(eval_on_device<Real>(ctx, d, lam, lm, ln, Delta, eo, d.stream, &u, d.scalars.as<double>()));
         CU_TRY(cudaMemcpyAsync(host[di].data(), d.scalars.p, (1 + ng) * sizeof(double), cudaMemcpyDeviceToHost,
                                d.stream));
+        if (d.grad_used_nd)
+            CU_TRY(cudaMemcpyAsync(&relres[di], nd_work_relres_max(d.nd), sizeof(double), cudaMemcpyDeviceToHost, d.stream));
         if (u_out && d.O > 0) RC_TRY(download_stack<Real>(d, u, plane * d.O, u_out + plane * d.o_begin, d.stream));
         CU_TRY(cudaEventRecord(d.ev[4], d.stream));
     }
@@ -938,14 +963,16 @@ static int learn_eval_impl(bpltv_ctx *ctx, const double *lam, int lm, int ln, do
         ctx->stats.ms_total = std::max<double>(ctx->stats.ms_total, ev_ms(d.ev[0], d.ev[4]));
         ctx->stats.kernel_launches += d.launches;
         ctx->stats.solver_iterations += d.grad.last_iterations;
-        ctx->stats.solver_max_relres = std::max(ctx->stats.solver_max_relres, d.grad.last_relres);
+        ctx->stats.solver_max_relres = std::max(ctx->stats.solver_max_relres, d.grad_used_nd ? relres[di] : d.grad.last_relres);
     }
     ctx->stats.pdps_iterations = eo.pdps.maxiter;
     ctx->stats.pixel_iterations = (long long)plane * ctx->O * eo.pdps.maxiter;
     ctx->stats.n_devices = ndev;
     if (!std::isfinite(cost)) return fail(BPLTV_ERR_NUMERIC, "non-finite cost");
     for (int k = 0; k < ng; ++k)
-        if (!std::isfinite(grad[k])) return fail(BPLTV_ERR_NUMERIC, "non-finite gradient entry %d", k);
+        if (!std::isfinite(grad[k]))
+            return fail(BPLTV_ERR_NUMERIC, "non-finite gradient entry %d (adjoint solve: worst backward error %.3g, tolerance %.3g)", k,
+                        ctx->stats.solver_max_relres, eo.solver_tol);
     *cost_out = cost;
     for (int k = 0; k < ng; ++k) grad_out[k] = grad[k];
     return 0;
@@ -1045,10 +1072,12 @@ static int gradient_impl(bpltv_ctx *ctx, const double *u_host, const double *lam
     const size_t plane = (size_t)ctx->M * ctx->N;
     std::memset(&ctx->stats, 0, sizeof ctx->stats);
     std::vector<std::vector<double>> host(ndev, std::vector<double>(ng, 0.0));
+    std::vector<double> relres(ndev, 0.0);
     for (int di = 0; di < ndev; ++di) {
         Dev &d = ctx->devs[di];
         CU_TRY(cudaSetDevice(d.id));
         d.launches = 0;
+        d.grad_used_nd = false;
         if (d.O == 0) continue;
         cudaStream_t st = d.stream;
         RC_TRY(d.scalars.ensure((1 + ng) * sizeof(double)));
@@ -1067,6 +1096,8 @@ static int gradient_impl(bpltv_ctx *ctx, const double *u_host, const double *lam
         if (rc != 0) return fail(rc, "gradient: %s", d.grad.err.c_str());
         CU_TRY(cudaEventRecord(d.ev[3], st));
         CU_TRY(cudaMemcpyAsync(host[di].data(), d.scalars.as<double>() + 1, ng * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (d.grad_used_nd)
+            CU_TRY(cudaMemcpyAsync(&relres[di], nd_work_relres_max(d.nd), sizeof(double), cudaMemcpyDeviceToHost, st));
     }
     std::vector<double> grad(ng, 0.0);
     for (int di = 0; di < ndev; ++di) {
@@ -1078,11 +1109,13 @@ static int gradient_impl(bpltv_ctx *ctx, const double *u_host, const double *lam
         ctx->stats.ms_gradient = std::max<double>(ctx->stats.ms_gradient, ev_ms(d.ev[2], d.ev[3]));
         ctx->stats.kernel_launches += d.launches;
         ctx->stats.solver_iterations += d.grad.last_iterations;
-        ctx->stats.solver_max_relres = std::max(ctx->stats.solver_max_relres, d.grad.last_relres);
+        ctx->stats.solver_max_relres = std::max(ctx->stats.solver_max_relres, d.grad_used_nd ? relres[di] : d.grad.last_relres);
     }
     ctx->stats.n_devices = ndev;
     for (int k = 0; k < ng; ++k) {
-        if (!std::isfinite(grad[k])) return fail(BPLTV_ERR_NUMERIC, "non-finite gradient entry %d", k);
+        if (!std::isfinite(grad[k]))
+            return fail(BPLTV_ERR_NUMERIC, "non-finite gradient entry %d (adjoint solve: worst backward error %.3g, tolerance %.3g)", k,
+                        ctx->stats.solver_max_relres, eo.solver_tol);
         grad_out[k] = grad[k];
     }
     return 0;
@@ -1164,8 +1197,8 @@ void bpltv_default_eval_opts(bpltv_eval_opts *o)
     o->gamma = 1e8;      // :142, :197
     o->act_tol = 1e-12;  // :109, :231
     o->eps_act = 0.0;    // → eps() scalar (:128) / sqrt(eps()) patch (:245)
-    o->solver_tol = 1e-13;
-    o->solver_maxit = 400000;
+    o->solver_tol = 1e-9;
+    o->solver_maxit = 0;
     o->solver = 0;
     o->force_branch = 0;
 }
@@ -1225,6 +1258,8 @@ int bpltv_destroy(bpltv_ctx *ctx)
         for (DBuf *b : bufs) b->release();
         d.grad.release();
         d.grad3.release();
+        nd_work_destroy(d.nd);
+        d.nd = nullptr;
         for (auto &ev : d.ev) if (ev) cudaEventDestroy(ev);
         if (d.stream) cudaStreamDestroy(d.stream);
     }

@@ -1047,7 +1047,7 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_solve_kernel(GradSlots ws, 
 __global__ void grad_reduce_kernel(const double *out_img, const double *relres_img, int O, int ng, double *grad,
                                    double *relres_max)
 {
-    const int g = threadIdx.x;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g < ng) {
         double s = 0.0;
         for (int o = 0; o < O; ++o) s += out_img[(size_t)o * ng + g];

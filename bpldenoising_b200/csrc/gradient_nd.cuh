@@ -1,0 +1,345 @@
+// gradient_nd.cuh — host driver of the nested-dissection adjoint solver (nd_symbolic.h, nd_solver.cuh, nd_tv.cuh).
+//
+// gradient (/root/reference/src/TVLearningFunctionVec.jl:98-135, :219-254) runs in multiplier space (MULT: 1-2
+// unknowns per pixel, sizes known only after the classification → one small device→host read per wave of images);
+// gradient_reg (:137-161, :192-215) in node space (NODE: one unknown per node, every size static).
+// Images are processed in waves of `slots`; inside a wave every kernel has a grid (work items, images), so one image
+// spreads over the SMs level by level and many images fill the GPU together.
+#pragma once
+#include <cstring>
+#include <string>
+
+#include "gradient_nd.h"
+#include "nd_tv.cuh"
+
+namespace bpltv {
+
+// grad[g] = Σ_o out_img[o][g] in image order (the reference's serial `for i = 1:O`, TVLearningFunctionVec.jl:76-81),
+// and the worst backward error over the images
+__global__ void nd_reduce_kernel(const double *out_img, const double *relres_img, int O, int ng, double *grad, double *relres_max)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < ng) {
+        double s = 0.0;
+        for (int o = 0; o < O; ++o) s += out_img[(size_t)o * ng + g];
+        grad[g] = s;
+    }
+    if (g == 0) {
+        double m = 0.0;
+        for (int o = 0; o < O; ++o) m = fmax(m, relres_img[o]);
+        relres_max[0] = m;
+    }
+}
+
+struct NdPlan {      // symbolic structure of one image size, on the device
+    NdSymbolic sym;
+    int n = 0;
+    void *d_fronts = nullptr, *d_pixlist = nullptr, *d_nbr = nullptr, *d_cmap = nullptr, *d_step_start = nullptr;
+    void *d_posg1 = nullptr, *d_foff1 = nullptr;       // static tables of the one-unknown-per-pixel case
+    long long tot1[4] = {0, 0, 0, 0};
+    size_t posg_len = 0;
+    void release()
+    {
+        void **all[] = {&d_fronts, &d_pixlist, &d_nbr, &d_cmap, &d_step_start, &d_posg1, &d_foff1};
+        for (void **p : all) { if (*p) cudaFree(*p); *p = nullptr; }
+        n = 0;
+    }
+};
+
+struct NdBuf {
+    void *p = nullptr; size_t bytes = 0;
+    cudaError_t ensure(size_t need)
+    {
+        if (need <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e == cudaSuccess) bytes = need; else cudaGetLastError();
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+struct NdWork {
+    std::string err;
+    NdPlan plan;
+    NdBuf pix, off, vec, posg, foff, totals, ast, L, U0, U1, UV0, UV1, info, out_img, relres, relres_max;
+    std::vector<long long> h_totals;
+    int attr_smem_factor = 0, attr_smem_solve = 0;
+    // what the last call saw (statistics)
+    double last_relres = 0.0;
+    long long last_guarded = 0;
+    size_t last_bytes_per_image = 0;
+    void release()
+    {
+        plan.release();
+        NdBuf *all[] = {&pix, &off, &vec, &posg, &foff, &totals, &ast, &L, &U0, &U1, &UV0, &UV1, &info, &out_img, &relres, &relres_max};
+        for (NdBuf *b : all) b->release();
+    }
+};
+
+constexpr int ND_LEAF = 4;
+
+static inline int nd_build_plan(NdPlan &pl, int n, cudaStream_t st, std::string &err)
+{
+    if (pl.n == n) return 0;
+    pl.release();
+    pl.sym.build(n, 1, ND_LEAF);
+    const NdSymbolic &s = pl.sym;
+    const int nf = (int)s.fronts.size();
+    pl.posg_len = s.pixlist.size() + nf;
+    std::vector<int> posg1(pl.posg_len);
+    std::vector<long long> foff1((size_t)4 * nf);
+    long long run[3] = {0, 0, 0}, lvl_max[2] = {0, 0};
+    for (int stp = 0; stp < s.nsteps(); ++stp) {
+        run[1] = run[2] = 0;
+        for (int t = s.step_start[stp]; t < s.step_start[stp + 1]; ++t) {
+            const NdFront &f = s.fronts[t];
+            for (int k = 0; k <= f.npiv + f.nring; ++k) posg1[(size_t)f.pix0 + t + k] = k;
+            long long sz[3];
+            nd_front_sizes(f.npiv, f.nring, sz);
+            for (int k = 0; k < 3; ++k) { foff1[4 * (size_t)t + k] = run[k]; run[k] += sz[k]; }
+        }
+        lvl_max[0] = std::max(lvl_max[0], run[1]); lvl_max[1] = std::max(lvl_max[1], run[2]);
+    }
+    pl.tot1[0] = run[0]; pl.tot1[1] = lvl_max[0]; pl.tot1[2] = lvl_max[1]; pl.tot1[3] = 0;
+    auto up = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, std::max<size_t>(bytes, 16));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, st);
+        return e;
+    };
+    cudaError_t e = up(&pl.d_fronts, s.fronts.data(), s.fronts.size() * sizeof(NdFront));
+    if (e == cudaSuccess) e = up(&pl.d_pixlist, s.pixlist.data(), s.pixlist.size() * sizeof(int));
+    if (e == cudaSuccess) e = up(&pl.d_nbr, s.nbr.data(), s.nbr.size() * sizeof(int));
+    if (e == cudaSuccess) e = up(&pl.d_cmap, s.cmap.data(), s.cmap.size() * sizeof(int));
+    if (e == cudaSuccess) e = up(&pl.d_step_start, s.step_start.data(), s.step_start.size() * sizeof(int));
+    if (e == cudaSuccess) e = up(&pl.d_posg1, posg1.data(), posg1.size() * sizeof(int));
+    if (e == cudaSuccess) e = up(&pl.d_foff1, foff1.data(), foff1.size() * sizeof(long long));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);     // the host vectors go out of scope
+    if (e != cudaSuccess) { cudaGetLastError(); pl.release(); err = std::string("nested-dissection plan upload: ") + cudaGetErrorString(e); return -6; }
+    pl.n = n;
+    return 0;
+}
+
+// threads of the per-front kernels of a level, from the (estimated) largest front of the level
+static inline int nd_factor_threads(int nF)
+{
+    const int nt = (nF + 31) / 32, ntiles = nt * (nt + 1) / 2;
+    return 32 * std::min(16, std::max(2, ntiles));
+}
+static inline int nd_solve_threads(int nF) { return std::min(512, std::max(64, (nF + 31) & ~31)); }
+
+static inline int nd_fail(NdWork &w, int code, const std::string &msg) { w.err = msg; return code; }
+
+template <typename Real>
+static int run_gradient_nd(NdWork &w, const NdProblem &gp, int sm_count, size_t smem_optin,
+                           cudaStream_t st, double *d_grad_out, long long *launches)
+{
+    NdWork &gw = w;
+    const Real *gp_u = static_cast<const Real *>(gp.u), *gp_ubar = static_cast<const Real *>(gp.ubar),
+               *gp_amap = static_cast<const Real *>(gp.alpha_map);
+    const int n = gp.M, N = gp.M * gp.N, ng = gp.lm * gp.ln;
+    if (gp.M != gp.N) return nd_fail(gw, -1, "square images required");
+    if (ng > 65536) return nd_fail(gw, -1, "lambda grid larger than 65536 entries is not supported");
+    const bool node = gp.regularised;
+    const int mb = node ? 1 : 2;
+    {
+        const int rc = nd_build_plan(w.plan, n, st, gw.err);
+        if (rc != 0) return rc;
+    }
+    const NdSymbolic &sym = w.plan.sym;
+    const int nf = (int)sym.fronts.size(), nsteps = sym.nsteps();
+    if (nsteps > 62) return nd_fail(gw, -1, "image too large for the nested-dissection level table");
+    // shared memory of the largest level (worst case: mb unknowns on every pixel)
+    size_t fsmem = 0, ssmem = 0;
+    for (int s = 0; s < nsteps; ++s) {
+        fsmem = std::max(fsmem, nd_factor_smem(mb * sym.step_max_front_pix[s], s > 0 ? mb * sym.step_max_ring_pix[s - 1] : 0));
+        ssmem = std::max(ssmem, nd_solve_smem(mb * sym.step_max_front_pix[s]));
+    }
+    if (fsmem > smem_optin || ssmem > smem_optin) return -1;      // the caller falls back to the band solver
+    if (w.attr_smem_factor < (int)fsmem) {
+        cudaError_t e = cudaFuncSetAttribute(nd_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+        if (e != cudaSuccess) { cudaGetLastError(); return nd_fail(gw, -2, std::string("nd_factor attributes: ") + cudaGetErrorString(e)); }
+        w.attr_smem_factor = (int)fsmem;
+    }
+    if (w.attr_smem_solve < (int)ssmem) {
+        cudaError_t e = cudaFuncSetAttribute(nd_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(nd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem);
+        if (e != cudaSuccess) { cudaGetLastError(); return nd_fail(gw, -2, std::string("nd_solve attributes: ") + cudaGetErrorString(e)); }
+        w.attr_smem_solve = (int)ssmem;
+    }
+
+    // ---- per-slot sizes.  Pools of the MULT form are estimated at 2.2× the one-unknown-per-pixel sizes (≈ 1.5
+    // unknowns per pixel) and grown when a wave needs more.
+    const long long *t1 = w.plan.tot1;
+    const double est = node ? 1.0 : 2.2;
+    const size_t fix_bytes = (size_t)NDTV_PLANES * N * 8 + (size_t)5 * mb * mb * N * 8 +
+                             (node ? 0 : ((size_t)N + 2) * 4 + (size_t)6 * N * 8 + w.plan.posg_len * 4 + (size_t)4 * nf * 8 + 32) + 16;
+    const size_t pool_bytes = (size_t)(est * (double)(t1[0] + 2 * t1[1] + 2 * t1[2])) * 8;
+    const size_t per_slot = fix_bytes + pool_bytes;
+    w.last_bytes_per_image = per_slot;
+    int slots = std::min(gp.O, 1024);
+    {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const size_t have = w.pix.bytes + w.ast.bytes + w.L.bytes + w.U0.bytes + w.U1.bytes + w.vec.bytes + w.posg.bytes + w.foff.bytes;
+        const size_t budget = (free_b + have) / 2;
+        slots = (int)std::min<size_t>((size_t)slots, std::max<size_t>(1, budget / per_slot));
+    }
+    auto need = [&](NdBuf &b, size_t bytes, const char *what) -> int {
+        cudaError_t e = b.ensure(bytes);
+        if (e != cudaSuccess) return nd_fail(gw, -6, std::string("nested-dissection workspace (") + what + "): " + cudaGetErrorString(e));
+        return 0;
+    };
+    int rc = 0;
+    NdTvSlots ws;
+    ws.n = n; ws.N = N;
+    ws.pix_stride = (size_t)NDTV_PLANES * N;
+    ws.off_stride = (size_t)N + 2;
+    ws.vec_stride = (size_t)6 * N;
+    const size_t ast_stride = (size_t)5 * mb * mb * N;
+    if ((rc = need(w.pix, ws.pix_stride * 8 * slots, "pixel planes"))) return rc;
+    if ((rc = need(w.ast, ast_stride * 8 * slots, "stencil matrix"))) return rc;
+    if ((rc = need(w.info, (size_t)16 * slots, "info"))) return rc;
+    if ((rc = need(w.out_img, (size_t)gp.O * ng * 8, "per-image gradients"))) return rc;
+    if ((rc = need(w.relres, (size_t)gp.O * 8, "residuals"))) return rc;
+    if ((rc = need(w.relres_max, 16, "residual maximum"))) return rc;
+    if (!node) {
+        if ((rc = need(w.off, ws.off_stride * 4 * slots, "mode offsets"))) return rc;
+        if ((rc = need(w.vec, ws.vec_stride * 8 * slots, "mode vectors"))) return rc;
+        if ((rc = need(w.posg, w.plan.posg_len * 4 * slots, "front offsets"))) return rc;
+        if ((rc = need(w.foff, (size_t)4 * nf * 8 * slots, "pool offsets"))) return rc;
+        if ((rc = need(w.totals, (size_t)32 * slots, "pool totals"))) return rc;
+    }
+    ws.pix = (double *)w.pix.p; ws.off = (int *)w.off.p; ws.vec = (double *)w.vec.p; ws.info = (int *)w.info.p;
+
+    NdDev nd;
+    nd.n = n; nd.N = N; nd.W = 1; nd.nnb = sym.nnb; nd.nh = nd_nh(1); nd.mb = mb;
+    nd.nfronts = nf; nd.nsteps = nsteps;
+    nd.fronts = (const NdFront *)w.plan.d_fronts; nd.pixlist = (const int *)w.plan.d_pixlist;
+    nd.nbr = (const int *)w.plan.d_nbr; nd.cmap = (const int *)w.plan.d_cmap; nd.step_start = (const int *)w.plan.d_step_start;
+    if (node) {
+        nd.off = nullptr; nd.off_stride = 0;
+        nd.posg = (int *)w.plan.d_posg1; nd.posg_stride = 0;
+        nd.foff = (long long *)w.plan.d_foff1; nd.foff_stride = 0;
+        nd.totals = nullptr;
+    } else {
+        nd.off = ws.off; nd.off_stride = ws.off_stride;
+        nd.posg = (int *)w.posg.p; nd.posg_stride = w.plan.posg_len;
+        nd.foff = (long long *)w.foff.p; nd.foff_stride = (size_t)4 * nf;
+        nd.totals = (long long *)w.totals.p;
+    }
+    nd.ast = (const double *)w.ast.p; nd.ast_stride = ast_stride;
+    nd.info = ws.info;
+
+    NdTvVariant gv;
+    gv.patch = gp.alpha_map != nullptr; gv.lm = gp.lm; gv.ln = gp.ln;
+    gv.alpha_s = gp.alpha_s; gv.gamma = gp.gamma; gv.act_tol = gp.act_tol; gv.eps_act = gp.eps_act;
+    gv.relres_tol = gp.tol > 0 ? gp.tol : 1e300;
+    const double guard = node ? 0.0 : 1e-13;
+    const int refine = gp.maxit > 0 ? std::min(gp.maxit, 8) : 1;
+    const int chunks = std::max(1, std::min(64, (N + 255) / 256));
+    const int pgroups = std::max(1, std::min(ng, 32));
+    const double fsz = node ? 1.0 : 1.25;        // typical unknowns per pixel, for the CTA sizes only
+
+    for (int img0 = 0; img0 < gp.O; img0 += slots) {
+        const int cnt = std::min(slots, gp.O - img0);
+        size_t Ls, Us, UVs;
+        if (node) {
+            ndtv_classify_node_kernel<Real><<<dim3(cnt, chunks), 256, 0, st>>>(ws, gv, gp_u, gp_ubar, gp_amap, img0);
+            ndtv_stencil_node_kernel<<<dim3(cnt, chunks), 256, 0, st>>>(ws, (double *)w.ast.p, ast_stride);
+            *launches += 2;
+            Ls = (size_t)t1[0]; Us = (size_t)t1[1]; UVs = (size_t)t1[2];
+        } else {
+            ndtv_classify_mult_kernel<Real><<<cnt, 512, 0, st>>>(ws, gv, gp_u, gp_ubar, gp_amap, img0);
+            nd_dims_kernel<<<dim3((nf + 7) / 8, cnt), 256, 0, st>>>(nd);
+            nd_scan_kernel<<<cnt, 256, 0, st>>>(nd);
+            ndtv_stencil_mult_kernel<<<dim3(cnt, chunks), 256, 0, st>>>(ws, (double *)w.ast.p, ast_stride);
+            *launches += 4;
+            w.h_totals.resize((size_t)4 * cnt);
+            cudaError_t e = cudaMemcpyAsync(w.h_totals.data(), w.totals.p, (size_t)32 * cnt, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { cudaGetLastError(); return nd_fail(gw, -2, std::string("nested-dissection sizes: ") + cudaGetErrorString(e)); }
+            long long m[4] = {0, 0, 0, 0};
+            for (int s = 0; s < cnt; ++s)
+                for (int k = 0; k < 4; ++k) m[k] = std::max(m[k], w.h_totals[4 * (size_t)s + k]);
+            Ls = (size_t)m[0]; Us = (size_t)m[1]; UVs = (size_t)m[2];
+        }
+        Ls = (Ls + 1) & ~(size_t)1; Us = (Us + 1) & ~(size_t)1; UVs = (UVs + 1) & ~(size_t)1;
+        if ((rc = need(w.L, Ls * 8 * cnt, "factors"))) return rc;
+        if ((rc = need(w.U0, Us * 8 * cnt, "update matrices"))) return rc;
+        if ((rc = need(w.U1, Us * 8 * cnt, "update matrices"))) return rc;
+        if ((rc = need(w.UV0, UVs * 8 * cnt, "update vectors"))) return rc;
+        if ((rc = need(w.UV1, UVs * 8 * cnt, "update vectors"))) return rc;
+        nd.L = (double *)w.L.p; nd.L_stride = Ls;
+        nd.U[0] = (double *)w.U0.p; nd.U[1] = (double *)w.U1.p; nd.U_stride = Us;
+        nd.UV[0] = (double *)w.UV0.p; nd.UV[1] = (double *)w.UV1.p; nd.UV_stride = UVs;
+        w.last_bytes_per_image = fix_bytes + (Ls + 2 * Us + 2 * UVs) * 8;
+
+        for (int s = 0; s < nsteps; ++s) {
+            const int t0 = sym.step_start[s], cntf = sym.step_start[s + 1] - t0;
+            const int nFw = mb * sym.step_max_front_pix[s];
+            const int T = nd_factor_threads((int)(fsz * sym.step_max_front_pix[s]));
+            const size_t sm = nd_factor_smem(nFw, s > 0 ? mb * sym.step_max_ring_pix[s - 1] : 0);
+            nd_factor_kernel<<<dim3(cntf, cnt), T, sm, st>>>(nd, t0, s & 1, guard, nFw);
+        }
+        *launches += nsteps;
+        auto solve = [&](double *vec, size_t stride) {
+            for (int s = 0; s < nsteps; ++s) {
+                const int t0 = sym.step_start[s], cntf = sym.step_start[s + 1] - t0;
+                const int T = nd_solve_threads((int)(fsz * sym.step_max_front_pix[s]));
+                nd_fwd_kernel<<<dim3(cntf, cnt), T, nd_solve_smem(mb * sym.step_max_front_pix[s]), st>>>(nd, t0, s & 1, vec, stride);
+            }
+            for (int s = nsteps - 1; s >= 0; --s) {
+                const int t0 = sym.step_start[s], cntf = sym.step_start[s + 1] - t0;
+                const int T = nd_solve_threads((int)(fsz * sym.step_max_front_pix[s]));
+                nd_bwd_kernel<<<dim3(cntf, cnt), T, nd_solve_smem(mb * sym.step_max_front_pix[s]), st>>>(nd, t0, vec, stride);
+            }
+            *launches += 2 * nsteps;
+        };
+        if (node) {
+            double *p = ws.pix + 7 * (size_t)N, *work = ws.pix + 8 * (size_t)N;
+            solve(p, ws.pix_stride);
+            ndtv_residual_node_kernel<<<cnt, 512, 0, st>>>(ws, (double *)w.relres.p, img0);
+            for (int it = 0; it < refine; ++it) {
+                solve(work, ws.pix_stride);
+                ndtv_axpy_node_kernel<<<dim3(cnt, chunks), 256, 0, st>>>(ws, 7, 8);
+                ndtv_residual_node_kernel<<<cnt, 512, 0, st>>>(ws, (double *)w.relres.p, img0);
+            }
+            ndtv_finish_node_kernel<<<dim3(cnt, pgroups), 512, 0, st>>>(ws, gv, (const double *)w.relres.p, (double *)w.out_img.p, img0);
+            *launches += 2 + 2 * refine;
+        } else {
+            double *zeta = ws.vec + 2 * (size_t)N, *work = ws.vec + 4 * (size_t)N;
+            ndtv_copy_mult_kernel<<<dim3(cnt, chunks), 256, 0, st>>>(ws, 1, 0);
+            solve(zeta, ws.vec_stride);
+            ndtv_residual_mult_kernel<<<cnt, 512, 0, st>>>(ws, (double *)w.relres.p, img0);
+            for (int it = 0; it < refine; ++it) {
+                solve(work, ws.vec_stride);
+                ndtv_axpy_mult_kernel<<<dim3(cnt, chunks), 256, 0, st>>>(ws, 1, 2);
+                ndtv_residual_mult_kernel<<<cnt, 512, 0, st>>>(ws, (double *)w.relres.p, img0);
+            }
+            ndtv_finish_mult_kernel<<<dim3(cnt, pgroups), 512, 0, st>>>(ws, gv, (const double *)w.relres.p, (double *)w.out_img.p, img0);
+            *launches += 3 + 2 * refine;
+        }
+    }
+    nd_reduce_kernel<<<(ng + 255) / 256, 256, 0, st>>>((double *)w.out_img.p, (double *)w.relres.p, gp.O, ng, d_grad_out,
+                                                         (double *)w.relres_max.p);
+    *launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return nd_fail(gw, -2, std::string("nested-dissection kernel launch failed: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+NdWork *nd_work_create() { return new NdWork(); }
+void nd_work_destroy(NdWork *w) { if (w) { w->release(); delete w; } }
+const char *nd_work_error(const NdWork *w) { return w->err.c_str(); }
+size_t nd_work_bytes_per_image(const NdWork *w) { return w->last_bytes_per_image; }
+const double *nd_work_relres_max(const NdWork *w) { return (const double *)w->relres_max.p; }
+int nd_run_gradient(NdWork *w, const NdProblem &gp, int sm_count, size_t smem_optin, cudaStream_t st, double *d_grad_out,
+                    long long *launches)
+{
+    return gp.prec == 64 ? run_gradient_nd<double>(*w, gp, sm_count, smem_optin, st, d_grad_out, launches)
+                         : run_gradient_nd<float>(*w, gp, sm_count, smem_optin, st, d_grad_out, launches);
+}
+
+}  // namespace bpltv

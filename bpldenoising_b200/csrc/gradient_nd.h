@@ -1,0 +1,35 @@
+// gradient_nd.h — interface of the nested-dissection adjoint solver's translation unit (gradient_nd.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+
+namespace bpltv {
+
+struct NdWork;      // plan, workspaces and pools of one device (gradient_nd.cuh)
+
+// gradient (regularised = false) / gradient_reg (true) of /root/reference/src/TVLearningFunctionVec.jl:72-254 for a
+// stack of O images on the device; u, ubar, alpha_map are device pointers of the context's precision (prec = 64 | 32)
+struct NdProblem {
+    const void *u, *ubar;
+    int prec;
+    int M, N, O;
+    double alpha_s;
+    const void *alpha_map;      // M·N map of the patch parameter, or nullptr
+    int lm, ln;
+    bool regularised;
+    double gamma, act_tol, eps_act;
+    double tol;                 // backward error above which the result is poisoned with NaN (≤ 0: never)
+    int maxit;                  // refinement steps (≤ 0: default)
+};
+
+NdWork *nd_work_create();
+void nd_work_destroy(NdWork *w);
+const char *nd_work_error(const NdWork *w);
+size_t nd_work_bytes_per_image(const NdWork *w);
+const double *nd_work_relres_max(const NdWork *w);      // device pointer: worst backward error of the last call
+// 0 ok; -1: the shape is not taken (fronts beyond shared memory) — use the band solver; other negatives: bpltv_status
+int nd_run_gradient(NdWork *w, const NdProblem &gp, int sm_count, size_t smem_optin, cudaStream_t st, double *d_grad_out,
+                    long long *launches);
+
+}  // namespace bpltv

@@ -84,9 +84,13 @@ typedef struct bpltv_eval_opts {
     double act_tol;   /* |∇u| < 1e-12 is "active" in gradient         (:109,:231) */
     double eps_act;   /* weight of the active rows: eps() scalar (:128),
                          sqrt(eps()) patch (:245); 0 → those defaults            */
-    double solver_tol;   /* relative residual target of the adjoint solve        */
-    int solver_maxit;    /* cap on Krylov iterations of the adjoint solve        */
-    int solver;          /* 0 auto; 1 PCG (Jacobi); 2 block-Cholesky + refinement */
+    double solver_tol;   /* backward error of the adjoint solve (matrix-free residual after
+                            refinement) above which the gradient is reported as
+                            BPLTV_ERR_NUMERIC instead of returned; 1e-9; <= 0: never   */
+    int solver_maxit;    /* steps of iterative refinement; 0 -> default (1)           */
+    int solver;          /* 0 auto = 2; 2 nested-dissection multifrontal Cholesky (the
+                            whole GPU per image); 1 the banded factorisations of round 1
+                            (one SM per image), kept as a second implementation          */
     int force_branch;    /* 0: by Δ (reference); 1: gradient; 2: gradient_reg;
                             3: cost only (grad_out left zero; λ-sweeps, validation)  */
     int reserved0;
@@ -100,9 +104,10 @@ typedef struct bpltv_stats {
     double ms_upload, ms_pdps, ms_cost, ms_gradient, ms_download, ms_total;
     long long pdps_iterations;   /* of the last call                           */
     long long pixel_iterations;  /* M·N·O·iterations of the last call          */
-    long long solver_iterations; /* Krylov iterations summed over images       */
+    long long solver_iterations; /* reserved (0)                               */
     long long kernel_launches;   /* CUDA kernels launched by the last call     */
-    double solver_max_relres;    /* worst final relative residual over images  */
+    double solver_max_relres;    /* worst backward error of the adjoint solve over the images
+                                    (host-pointer entry points, solver 0/2)    */
     int pdps_kernel_used;        /* enum bpltv_pdps_kernel actually dispatched */
     int n_devices;
     int tblock_depth;            /* PDPS iterations per HBM pass of that kernel (1 unless TBLOCK) */

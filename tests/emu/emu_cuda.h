@@ -136,6 +136,21 @@ inline float __fsqrt_rn(float a) { return std::sqrt(a); }
 inline double rsqrt(double a) { return 1.0 / std::sqrt(a); }
 inline float rsqrtf(float a) { return 1.0f / std::sqrt(a); }
 template <typename T> inline T __ldg(const T *p) { return *p; }
+inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline int atomicMin(int *p, int v)
+{
+    int old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
+inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v)
+{
+    unsigned long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (v > old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
+inline long long __double_as_longlong(double d) { long long r; std::memcpy(&r, &d, 8); return r; }
+inline double __longlong_as_double(long long l) { double r; std::memcpy(&r, &l, 8); return r; }
 
 // cooperative_groups::this_cluster() for kernels that use the library interface directly
 namespace cooperative_groups {

@@ -1,0 +1,162 @@
+"""CPU check of the nested-dissection adjoint solver (bpldenoising_b200/csrc/nd_symbolic.h, nd_solver.cuh,
+nd_tv.cuh) where no GPU exists: the device code is compiled with g++ against tests/emu/emu_cuda.h (one OS thread
+per CUDA thread, CTA / warp barriers, shuffles) and run for one image in the launch order of gradient_nd.cuh,
+then compared with the oracle — the compliance-form checker and the literal sparse systems of
+/root/reference/src/TVLearningFunctionVec.jl:98-161, :192-254.  The emulation checks the elimination tree, the
+index tables, the extend-add maps and the barrier placement, not performance; the GPU parity tests proper are
+tests/test_gpu_gradient.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, "emu")
+CSRC = os.path.join(HERE, "..", "bpldenoising_b200", "csrc")
+
+
+def _build():
+    out = os.path.join(EMU, "_build", "libemu_nd.so")
+    srcs = [os.path.join(EMU, "emu_nd.cpp"), os.path.join(EMU, "emu_cuda.h")] + \
+           [os.path.join(CSRC, f) for f in ("nd_symbolic.h", "nd_solver.cuh", "nd_tv.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-fPIC", "-shared", "-DBPLTV_EMU", "-ffp-contract=off",
+                        "-o", out, srcs[0]], check=True)
+    lib = C.CDLL(out)
+    lib.emu_nd_gradient.restype = C.c_int
+    lib.emu_nd_symbolic_check.restype = C.c_int
+    return lib
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return _build()
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _case(n, seed, flat=True):
+    """A denoised-looking image: smooth + edges, with an exactly flat block (|∇u| = 0: the two-mode pixels of the
+    multiplier form, the γ·I tensors of the regularised one)."""
+    rng = np.random.default_rng(seed)
+    ii, jj = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    t = 0.5 + 0.3 * np.sin(ii / 3.0) * np.cos(jj / 4.0) + 0.2 * (ii > n // 2)
+    u = t + 0.02 * rng.standard_normal((n, n))
+    if flat:
+        u[1:5, 2:6] = u[1, 2]
+        u[n - 4:, n - 3:] = u[n - 1, n - 1]
+    return np.asfortranarray(t), np.asfortranarray(u)
+
+
+def _run(lib, reg, u, t, alpha, grid=(1, 1), refine=None, leaf=4, gamma=1e8, eps_act=None, ast_out=None, off_out=None):
+    n = u.shape[0]
+    amap = None
+    a_s = 0.0
+    if np.ndim(alpha) == 2:
+        amap = np.ascontiguousarray(np.asarray(alpha, dtype=np.float64).flatten(order="F"))
+    else:
+        a_s = float(alpha)
+    if eps_act is None:
+        eps_act = np.sqrt(orc.EPS) if amap is not None else orc.EPS
+    if refine is None:
+        refine = 1
+    out = np.zeros(grid[0] * grid[1])
+    stats = np.zeros(8)
+    p = np.zeros(n * n)
+    rc = lib.emu_nd_gradient(int(reg), n, _ptr(u.flatten(order="F")), _ptr(t.flatten(order="F")), _ptr(amap),
+                             C.c_double(a_s), C.c_double(gamma), C.c_double(1e-12), C.c_double(eps_act),
+                             grid[0], grid[1], refine, leaf, _ptr(out), _ptr(stats), _ptr(p), _ptr(ast_out),
+                             None if off_out is None else off_out.ctypes.data_as(C.POINTER(C.c_int)))
+    assert rc == 0
+    return out.reshape(grid, order="F"), stats, p
+
+
+@pytest.mark.parametrize("n,W,leaf", [(1, 1, 4), (3, 1, 4), (7, 1, 4), (16, 1, 4), (33, 1, 4), (64, 1, 8), (50, 2, 5), (128, 1, 4)])
+def test_elimination_tree(lib, n, W, leaf):
+    nf, ns, mf = C.c_int(), C.c_int(), C.c_int()
+    rc = lib.emu_nd_symbolic_check(n, W, leaf, C.byref(nf), C.byref(ns), C.byref(mf))
+    assert rc == 0, f"tree check {rc}"
+    assert mf.value <= 3 * W * n + n + 8
+
+
+@pytest.mark.parametrize("n", [12, 24, 37])
+def test_gradient_reg_scalar(lib, n):
+    t, u = _case(n, 1 + n)
+    g, stats, p = _run(lib, True, u, t, 0.07)
+    ref, pref = orc.gradient_reg_scalar(0.07, u, t, refine=4, return_p=True)
+    assert stats[2] == 0 and stats[0] < 1e-15, stats
+    assert np.linalg.norm(p - pref) <= 1e-9 * np.linalg.norm(pref)
+    assert abs(g[0, 0] - ref) <= 1e-9 * abs(ref), (g, ref)
+    dual = orc.gradient_dual("reg", 0.07, u, t)
+    assert abs(g[0, 0] - dual) <= 1e-10 * abs(dual)
+
+
+def test_gradient_reg_patch(lib):
+    n = 24
+    t, u = _case(n, 5)
+    x = np.array([[0.05, 0.1, 0.02], [0.08, 0.03, 0.06]])
+    amap = orc.patch_upsample(x, n, n)
+    g, stats, _ = _run(lib, True, u, t, amap, grid=x.shape)
+    ref = orc.gradient_reg_patch(amap, x.shape, u, t, refine=4)
+    assert stats[2] == 0 and stats[0] < 1e-15, stats
+    assert np.linalg.norm(g - ref) <= 1e-9 * np.linalg.norm(ref), (g, ref)
+
+
+@pytest.mark.parametrize("n,leaf", [(12, 4), (24, 4), (24, 3), (37, 6)])
+def test_gradient_scalar(lib, n, leaf):
+    t, u = _case(n, 11 + n)
+    g, stats, _ = _run(lib, False, u, t, 0.07, leaf=leaf)
+    dual = orc.gradient_dual("nonreg", 0.07, u, t)
+    assert abs(g[0, 0] - dual) <= 1e-10 * abs(dual), (g, dual, stats)
+    ref = orc.gradient_scalar(0.07, u, t, refine=4)
+    assert abs(g[0, 0] - ref) <= 1e-6 * abs(ref), (g, ref)
+    assert stats[7] > n * n            # some pixels are flat: two modes
+
+
+def test_gradient_patch(lib):
+    n = 24
+    t, u = _case(n, 7)
+    x = np.array([[0.05, 0.1], [0.08, 0.02]])
+    amap = orc.patch_upsample(x, n, n)
+    g, stats, _ = _run(lib, False, u, t, amap, grid=x.shape)
+    dual = orc.gradient_dual("nonreg", amap, u, t, grid_shape=x.shape)
+    assert np.linalg.norm(g - dual) <= 1e-10 * np.linalg.norm(dual), (g, dual, stats)
+
+
+def test_no_flat_pixels_and_tiny_images(lib):
+    for n in (4, 5, 9):
+        t, u = _case(n, 3, flat=False)
+        g, stats, _ = _run(lib, False, u, t, 0.1)
+        dual = orc.gradient_dual("nonreg", 0.1, u, t)
+        assert abs(g[0, 0] - dual) <= 1e-10 * abs(dual)
+        g, stats, _ = _run(lib, True, u, t, 0.1)
+        ref = orc.gradient_reg_scalar(0.1, u, t, refine=4)
+        assert abs(g[0, 0] - ref) <= 1e-9 * abs(ref)
+
+
+def test_barely_sloped_region_does_not_break_the_factorisation(lib):
+    """tests/golden/nd_hard_crop.npz: a crop of a synthetic 256×256 image after 5000 PDPS iterations (BASELINE config 5's
+    generator) where |∇u| hovers around the 1e-12 threshold of TVLearningFunctionVec.jl:109 — flat pixels (compliance
+    eps()) next to barely sloped ones (compliance |∇u|/α ≈ 1e-11) with noise for a direction.  The system has 120 eigenvalues
+    below 1e-13 in 391 and is decided by rounding: a factorisation with explicit block inverses or a bare pivot floor
+    overflowed here (and so does the plain floor of oracle.gradient_dual's band Cholesky).  Required: finite, no breakdown
+    flag, and the 60-digit solution of the same system (mpmath, tools/nd_hard_crop_reference.py) to 1e-4 — the reference's
+    own literal system carries entries of 1e11 and 4.5e15 at such pixels and is reproducible to no better."""
+    z = np.load(os.path.join(HERE, "golden", "nd_hard_crop.npz"))
+    u, t = np.asfortranarray(z["u"]), np.asfortranarray(z["t"])
+    for refine in (1, 2):
+        g, stats, _ = _run(lib, False, u, t, 0.1, refine=refine)
+        assert np.isfinite(g[0, 0]) and stats[2] == 0, (g, stats)
+        assert abs(g[0, 0] - float(z["g16_mp60"])) <= 1e-4 * abs(float(z["g16_mp60"])), g
+    u, t = np.asfortranarray(z["u64"]), np.asfortranarray(z["t64"])
+    g, stats, _ = _run(lib, False, u, t, 0.1)
+    assert np.isfinite(g[0, 0]) and stats[2] == 0 and stats[0] < 1e-9, (g, stats)
+    g2, stats, _ = _run(lib, False, u, t, 0.1, leaf=6)            # another elimination tree: same answer to 1e-5
+    assert abs(g2[0, 0] - g[0, 0]) <= 1e-5 * abs(g[0, 0]), (g, g2)

@@ -181,3 +181,52 @@ def test_single_process_multi_device_context(bp, oracle, datasets):
         assert np.array_equal(u1, u2)
         assert abs(cost1 - cost2) <= 1e-13 * cost1 and abs(g1 - g2) <= 1e-12 * abs(g1)
         assert c2.stats()["n_devices"] == 2
+
+
+@pytest.mark.parametrize("variant", ["reg", "nonreg"])
+def test_nested_dissection_vs_band_solvers(bp, ctx, oracle, datasets, variant):
+    """Two independent implementations of every adjoint solve: the nested-dissection multifrontal Cholesky (default,
+    eval_opts.solver = 0/2) and round 1's banded factorisations (solver = 1).  Same formulation per branch, different
+    elimination order and kernels: they must agree far inside the oracle bars, scalar and patch, odd sizes included."""
+    reg = variant == "reg"
+    for n, O, name in ((128, 3, "faces_train_128_10"), (37, 2, "cameraman_128_5"), (64, 1, "circle_128_10")):
+        t, f = (a[:n, :n, :O].copy(order="F") for a in datasets[name])
+        if t.shape[2] < O:
+            t, f = (np.concatenate([a, a[::-1]], axis=2).copy(order="F") for a in (t, f))
+        x = np.array([[0.02, 0.05, 0.03], [0.04, 0.01, 0.06]])
+        am = oracle.patch_upsample(x, n, n)
+        us = oracle.pdps(f, 0.06, maxiter=1500)
+        up = oracle.pdps(f, am, maxiter=1500)
+        ctx.set_dataset((t, f))
+        nd, band = bp.eval_opts(solver=2), bp.eval_opts(solver=1)
+        gs_nd, gs_b = ctx.gradient(0.06, us, reg, nd), ctx.gradient(0.06, us, reg, band)
+        st = ctx.stats()
+        gp_nd, gp_b = ctx.gradient(x, up, reg, nd), ctx.gradient(x, up, reg, band)
+        assert _rel(gs_nd, gs_b) <= 1e-11, (n, gs_nd, gs_b)
+        assert _rel(gp_nd, gp_b) <= 1e-11, (n, gp_nd, gp_b)
+        dual = sum(oracle.gradient_dual(variant, 0.06, us[:, :, i], t[:, :, i]) for i in range(t.shape[2]))
+        assert _rel(gs_nd, dual) <= 1e-10
+    ctx.gradient(0.06, us, reg, nd)
+    assert 0 <= ctx.stats()["solver_max_relres"] <= 1e-9
+
+
+def test_adjoint_solver_reports_failure(bp, ctx, oracle, datasets):
+    """A backward error above eval_opts.solver_tol is an error, not a silently inaccurate gradient."""
+    t, f = (a[:48, :48, :1].copy(order="F") for a in datasets["cameraman_128_5"])
+    u = oracle.pdps(f, 0.1, maxiter=1000)
+    ctx.set_dataset((t, f))
+    with pytest.raises(bp.BpltvError) as ei:
+        ctx.gradient(0.1, u, False, bp.eval_opts(solver_tol=1e-30))
+    assert "backward error" in str(ei.value)
+    assert np.isfinite(ctx.gradient(0.1, u, False, bp.eval_opts(solver_tol=0.0)))
+
+
+def test_gradient_256_many_images_nested_dissection(bp, ctx, oracle):
+    """BASELINE config 5's image size in a wave of many images (one grid dimension of every kernel)."""
+    t, f = bp.synthetic_dataset(256, 256, 6, seed=20240602)
+    u = ctx.denoise(f, 0.1, bp.pdps_opts(maxiter=1000))
+    ctx.set_dataset((t, f))
+    for reg in (True, False):
+        g = ctx.gradient(0.1, u, regularised=reg)
+        parts = [oracle.gradient_dual("reg" if reg else "nonreg", 0.1, u[:, :, i], t[:, :, i]) for i in range(6)]
+        assert _rel(g, sum(parts)) <= 1e-10, (reg, g, sum(parts))
