@@ -160,3 +160,15 @@ def test_barely_sloped_region_does_not_break_the_factorisation(lib):
     assert np.isfinite(g[0, 0]) and stats[2] == 0 and stats[0] < 1e-9, (g, stats)
     g2, stats, _ = _run(lib, False, u, t, 0.1, leaf=6)            # another elimination tree: same answer to 1e-5
     assert abs(g2[0, 0] - g[0, 0]) <= 1e-5 * abs(g[0, 0]), (g, g2)
+
+
+def test_against_binary128(lib):
+    """the emulated CUDA path against the binary128 solves of oracle/quad_adjoint.c (tests/test_oracle_quad.py): 1e-12"""
+    from oracle import quad
+    t, u = _case(20, 9)
+    g, _, p = _run(lib, False, u, t, 0.07)
+    q, pq = quad.gradient_compliance(0.07, u, t, return_p=True)
+    assert abs(g[0, 0] - q) <= 1e-12 * abs(q) and np.linalg.norm(p - pq) <= 1e-12 * np.linalg.norm(pq)
+    g, _, p = _run(lib, True, u, t, 0.07)
+    q, pq = quad.gradient_reg(0.07, u, t, return_p=True)
+    assert abs(g[0, 0] - q) <= 1e-12 * abs(q) and np.linalg.norm(p - pq) <= 1e-12 * np.linalg.norm(pq)
