@@ -118,14 +118,21 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture."""
+def ncu_traffic(kernel_family, depth):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture — only if that capture is of the
+    kernel this run dispatched (same family, same temporal depth); otherwise None."""
     p = os.path.join(ROOT, "profiles", "ncu_top_kernel.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("dram_bytes_per_launch")
+            rec = json.load(open(p))
         except ValueError:
             return None
+        name = rec.get("kernel", "")
+        # pdps_tblock_kernel<double, VEC, T, ...>: the third template argument is the depth
+        args_ = [a.strip() for a in name[name.find("<") + 1:name.rfind(">")].split(",")] if "<" in name else []
+        if name.startswith(kernel_family) and args_[:1] == ["double"] and (kernel_family != "pdps_tblock_kernel" or
+                                                                            (len(args_) > 2 and args_[2] == str(depth))):
+            return rec.get("dram_bytes_per_launch")
     return None
 
 
@@ -136,40 +143,71 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_reference_step(orc, f_sample, iters, threads):
+def cpu_reference_step(orc, f_sample, iters, threads, fused=False):
     t0 = time.perf_counter()
-    orc.pdps(f_sample, LAM, maxiter=iters, nthreads=threads)
+    orc.pdps(f_sample, LAM, maxiter=iters, nthreads=threads, fused=fused)
     dt = time.perf_counter() - t0
     return f_sample.size * iters / dt / 1e9, dt
 
 
+def _leaf_datasets_module():
+    """bpldenoising_b200/datasets.py executed as a stand-alone module: the reference arm must not import the package
+    (its __init__ loads libbpltv.so — the library under test has no business in the baseline's process)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_bpltv_datasets_leaf", os.path.join(ROOT, "bpldenoising_b200", "datasets.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def run_reference(args):
+    """The reference algorithm on the host cores: the C port of the recursion (oracle/bpltv_oracle.c), all threads.
+    Each step is the FULL workload (64 images × 1000 iterations) when the whole run fits ~4 minutes, otherwise the full
+    batch for a proportionally reduced iteration count (the rate does not depend on the iteration count).  `value` is the
+    faster of two bit-identical variants: the faithful one (separate passes, like the reference's broadcasts) and a
+    fused single-sweep one (what a tuned CPU code would do)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     from oracle import oracle as orc
     orc.build()
-    from bpldenoising_b200.datasets import synthetic_dataset
+    assert "bpldenoising_b200" not in sys.modules
+    synthetic_dataset = _leaf_datasets_module().synthetic_dataset
     cores = host_threads()   # torchrun exports OMP_NUM_THREADS=1: ask for the cores explicitly
-    n_img = max(1, min(cores, O_PER_GPU))
-    iters = 100
-    _, f = synthetic_dataset(M, N, n_img, seed=20240601)
+    _, f = synthetic_dataset(M, N, O_PER_GPU, seed=20240601)
+    # probe both variants on a short run
+    probe = {}
+    for fused in (False, True):
+        cpu_reference_step(orc, f, 5, cores, fused)
+        probe[fused] = cpu_reference_step(orc, f, 25, cores, fused)[0]
+    fused = probe[True] >= probe[False]
+    n_steps = args.warmup + args.steps
+    full_s = f.size * ITERS / (probe[fused] * 1e9)
+    budget_s = 230.0
+    iters = ITERS if full_s * n_steps <= budget_s else max(50, int(ITERS * budget_s / (full_s * n_steps)))
     vals = []
-    for k in range(args.warmup + args.steps):
-        v, dt = cpu_reference_step(orc, f, iters, cores)
+    for k in range(n_steps):
+        v, dt = cpu_reference_step(orc, f, iters, cores, fused)
         if k >= args.warmup:
             vals.append((v, dt))
     value = statistics.mean(v for v, _ in vals)
     ms = statistics.mean(dt for _, dt in vals) * 1e3
-    sample = (f"{n_img} of the {O_PER_GPU} images (512x512) x {iters} of the {ITERS} iterations per step, "
-              f"OpenMP over images, {cores} threads; C port of the reference recursion (oracle/bpltv_oracle.c), "
-              "not Julia (not installed; its solver packages are un-vendored)")
+    full = iters == ITERS
+    sample = (f"all {O_PER_GPU} images (512x512) x {iters} of the {ITERS} iterations per step"
+              + (" = the full step" if full else " (rate extrapolates to the full step: per-iteration cost is constant)")
+              + f", OpenMP over images, {cores} threads; C port of the reference recursion (oracle/bpltv_oracle.c, gcc -O3), "
+              + ("fused single-sweep variant" if fused else "separate passes as in the reference's broadcasts")
+              + "; not Julia (not installed; its solver packages are un-vendored)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms if full else ms * ITERS / iters,
+        "ms_per_step_is": "measured" if full else f"extrapolated from {iters} iterations per step",
+        "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": _config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "variant": "fused" if fused else "unfused",
+                         "probe_unfused": probe[False], "probe_fused": probe[True]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -310,9 +348,9 @@ def main():
     # peak the launch actually uses (ncu dram bytes ÷ launch time).
     alg_bytes = ALG_BYTES_PER_PIXEL_ITER_F64 * float(M) * N * O_PER_GPU * depth
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
-    traffic = ncu_traffic()
     kname = {2: "pdps_march_kernel<double,VEC=2>", 4: "pdps_tblock_kernel<double,VEC=2,T=%d>" % depth}.get(
         kernel_used, "kernel id %d" % kernel_used)
+    traffic = ncu_traffic({2: "pdps_march_kernel", 4: "pdps_tblock_kernel"}.get(kernel_used, "?"), depth)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel": kname,
                 "iterations_per_launch": depth, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_ms,
@@ -349,6 +387,29 @@ def main():
            "ms_per_step": e2e_ms, "device_ms": {"upload": st["ms_upload"], "pdps": st["ms_pdps"],
                                                  "download": st["ms_download"]}}
 
+    # the same call with PAGEABLE host arrays (what a Julia caller passes: plain Array{Float64,3})
+    pg_in = np.asfortranarray(np.array(noisy, copy=True))
+    pg_out = np.zeros_like(pg_in, order="F")
+    for _ in range(2):
+        ctx.denoise(pg_in, LAM, popts, out=pg_out)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(max(2, K // 2)):
+        u = ctx.denoise(pg_in, LAM, popts, out=pg_out)
+        _ = float(u[0, 0, 0])
+    pg_ms = (time.perf_counter() - t0) * 1e3 / max(2, K // 2)
+    stp = ctx.stats()
+    t = torch.tensor([pg_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    pg_ms = float(t.item())
+    e2e["pageable"] = {"value": pix_iter_per_step * world / (pg_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": pg_ms,
+                       "device_ms": {"upload": stp["ms_upload"], "pdps": stp["ms_pdps"], "download": stp["ms_download"]},
+                       "note": "pageable numpy arrays as the caller's buffers; the headline e2e uses pinned ones"}
+    del pg_in, pg_out
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -362,6 +423,19 @@ def main():
         line["per_gpu_value_other_arith"] = {"arith": "fast" if arith == bp.STRICT else "strict", "value": value_other,
                                               "unit": UNIT, "frac_of_hbm_peak": value_other * 1e9 * ALG_BYTES_PER_PIXEL_ITER_F64 / 1e9 / peak}
 
+    # ---- BASELINE configs[4] ("config 5") at every N: one bilevel learning step on 1024 synthetic 256×256 images,
+    # sharded by image over the ranks, ONE all-reduce of [loss, gradient] per evaluation; strong scaling (total work fixed)
+    if not args.no_extras:
+        try:
+            line["config5"] = config5_extra(bp, torch, dist, dev, tstream, world, rank, local)
+        except Exception as e:
+            line["config5"] = {"error": f"{type(e).__name__}: {e}"}
+        if world == 1 and torch.cuda.device_count() > 1:
+            try:
+                line["multi_device_context"] = multi_device_extra(bp, torch.cuda.device_count())
+            except Exception as e:
+                line["multi_device_context"] = {"error": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
         line["clocks"] = clk.summary()
         # ---- CPU baseline: the oracle port on this box's host cores (bounded sample) ----
@@ -371,14 +445,16 @@ def main():
         n_img = max(1, min(cores, O_PER_GPU))
         f_s = np.asfortranarray(noisy[:, :, np.arange(n_img) % O_PER_GPU])
         iters_s = 200
-        v_all, dt_all = cpu_reference_step(orc, f_s, iters_s, cores)
+        v_unf, dt_unf = cpu_reference_step(orc, f_s, iters_s, cores)
+        v_fus, dt_fus = cpu_reference_step(orc, f_s, iters_s, cores, fused=True)
         v_one, dt_one = cpu_reference_step(orc, np.asfortranarray(noisy[:, :, :1]), iters_s, 1)
         line["cpu_baseline"] = {
-            "value": v_all, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n_img} images 512x512 x {iters_s} iterations, OpenMP over images ({dt_all:.1f} s); "
+            "value": max(v_unf, v_fus), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_img} images 512x512 x {iters_s} iterations, OpenMP over images, gcc -O3: faithful separate "
+                      f"passes {v_unf:.3f} ({dt_unf:.1f} s), fused single sweep {v_fus:.3f} ({dt_fus:.1f} s), bit-identical; "
                       f"1 thread / 1 image: {v_one:.4f} {UNIT} ({dt_one:.1f} s). C restatement of the reference "
                       "recursion (oracle/bpltv_oracle.c) — Julia is not installed",
-            "single_thread_value": v_one,
+            "unfused_value": v_unf, "fused_value": v_fus, "single_thread_value": v_one,
         }
         # ---- extras: learn_eval wall time on the reference-shaped configs (N=1 only) ------
         if world == 1 and not args.no_extras:
@@ -391,6 +467,65 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def config5_extra(bp, torch, dist, dev, tstream, world, rank, local, total=1024, n=256, iters=5000):
+    """BASELINE.json configs[4]: tv_op_learning_function on `total` synthetic n×n images, both gradient branches
+    (Δ = 0.1 → gradient, Δ = 1e-7 → gradient_reg) and the loss alone, images sharded `shard_range(total, world, rank)`.
+    Each evaluation = one learn_eval_device + one NCCL all-reduce of [loss, gradient]; CUDA-event time, max over ranks.
+    The gradient's share is the difference to the loss-only evaluation."""
+    from bpldenoising_b200.parallel import shard_range
+    b, c = shard_range(total, world, rank)
+    truth, noisy = bp.synthetic_dataset(n, n, c, seed=20240602 + 1000 * rank)
+    d_t = torch.from_numpy(np.ascontiguousarray(truth.transpose(2, 1, 0))).to(dev)
+    d_n = torch.from_numpy(np.ascontiguousarray(noisy.transpose(2, 1, 0))).to(dev)
+    cg = torch.zeros(2, dtype=torch.float64, device=dev)
+    out = {"images_total": total, "image": [n, n], "iterations": iters, "images_per_rank": c, "ranks": world,
+           "scaling": "strong", "lambda": LAM}
+    with bp.Context([local], 64) as c5:
+        c5.set_dataset_device(d_t.data_ptr(), d_n.data_ptr(), n, n, c, tstream.cuda_stream)
+        for name, Delta, branch in (("loss_only", 0.1, 3), ("gradient", 0.1, 0), ("gradient_reg", 1e-7, 0)):
+            eo = bp.eval_opts(bp.pdps_opts(maxiter=iters), force_branch=branch)
+            ms = None
+            for rep in range(2):     # the first evaluation allocates workspaces
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(tstream)
+                c5.learn_eval_device(LAM, Delta, cg.data_ptr(), eo, stream=tstream.cuda_stream)
+                if world > 1:
+                    dist.all_reduce(cg)
+                e1.record(tstream)
+                torch.cuda.synchronize()
+                t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            out[name] = {"seconds": ms * 1e-3, "loss": float(cg[0].item()), "grad": float(cg[1].item()),
+                         "kernel_launches": c5.stats()["kernel_launches"]}
+        for name in ("gradient", "gradient_reg"):
+            out[name]["gradient_share_seconds"] = out[name]["seconds"] - out["loss_only"]["seconds"]
+        out["gpixel_iter_per_s_loss_only"] = total * n * n * iters / out["loss_only"]["seconds"] / 1e9
+    del d_t, d_n
+    return out
+
+
+def multi_device_extra(bp, ndev):
+    """The in-library multi-device path (bpltv_create with several device ids: what a single Julia process uses) against
+    a one-device context on the same data: identical images, loss and gradient to rounding of the host-side sum."""
+    ds = _reference_datasets()
+    t, f = (a[:, :, :5].copy(order="F") for a in ds["faces_train_128_10"])
+    res = {"devices": ndev}
+    with bp.Context([0], 64) as c1, bp.Context(list(range(ndev)), 64) as cn:
+        c1.set_dataset((t, f)); cn.set_dataset((t, f))
+        eo = bp.eval_opts(bp.pdps_opts(maxiter=1000))
+        for name, Delta in (("gradient", 0.1), ("gradient_reg", 1e-7)):
+            u1, cost1, g1 = c1.learn_eval(0.07, Delta, eo)
+            un, costn, gn = cn.learn_eval(0.07, Delta, eo)
+            res[name] = {"max_abs_du": float(np.abs(u1 - un).max()), "rel_dcost": abs(cost1 - costn) / abs(cost1),
+                         "rel_dgrad": abs(g1 - gn) / abs(g1), "n_devices_used": cn.stats()["n_devices"]}
+    return res
 
 
 def _reference_datasets():

@@ -6,7 +6,7 @@ Only the hot path lives here: the CUDA kernels + C ABI (`csrc/`, `libbpltv.so`,
 the package loads the CUDA library and fails loudly when it has not been built.
 """
 from . import _lib
-from ._lib import (BpltvError, FAST, KERNEL_AUTO, KERNEL_GENERIC, KERNEL_MARCH, KERNEL_RESIDENT,
+from ._lib import (BpltvError, reload_env, FAST, KERNEL_AUTO, KERNEL_GENERIC, KERNEL_MARCH, KERNEL_RESIDENT,
                    KERNEL_TBLOCK, STRICT)
 
 _lib.load()  # no silent CPU path: ImportError if libbpltv.so is absent
@@ -22,7 +22,7 @@ from .parallel import shard_range  # noqa: E402
 from . import trbox  # noqa: E402,F401
 
 __all__ = [
-    "BpltvError", "Context", "L2CostFunction", "TVDenoise", "default_context", "denoise",
+    "BpltvError", "reload_env", "Context", "L2CostFunction", "TVDenoise", "default_context", "denoise",
     "eval_opts", "gradient", "gradient_reg", "pdps_opts", "tv_op_learning_function",
     "synthetic_dataset", "shard_range", "generate_cost", "generate_scalar_tv_cost", "generate_2d_tv_cost",
     "validate_tv_parameter", "sumregs_denoise", "sumregs_learning_function", "sumregs_eval_opts", "sumregs_pdps_opts", "load_dataset", "testdataset", "quality", "STRICT", "FAST", "KERNEL_AUTO", "KERNEL_GENERIC",

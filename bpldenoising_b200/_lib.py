@@ -44,7 +44,7 @@ EXPORTS = [
     "bpltv_set_dataset", "bpltv_denoise", "bpltv_learn_eval", "bpltv_gradient", "bpltv_sweep", "bpltv_default_sumregs_eval_opts",
     "bpltv_sumregs_denoise", "bpltv_sumregs_learn_eval", "bpltv_sumregs_gradient",
     "bpltv_denoise_device", "bpltv_set_dataset_device", "bpltv_learn_eval_device",
-    "bpltv_get_stats", "bpltv_last_error", "bpltv_version",
+    "bpltv_get_stats", "bpltv_last_error", "bpltv_version", "bpltv_reload_env",
 ]
 
 _lib = None
@@ -93,9 +93,11 @@ def load() -> C.CDLL:
     L.bpltv_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.bpltv_last_error.restype = C.c_char_p
     L.bpltv_version.restype = C.c_int
+    L.bpltv_reload_env.restype = None
+    L.bpltv_reload_env.argtypes = []
     for name in EXPORTS:
         if name not in ("bpltv_default_pdps_opts", "bpltv_default_eval_opts", "bpltv_default_sumregs_eval_opts",
-                        "bpltv_last_error"):
+                        "bpltv_last_error", "bpltv_reload_env"):
             getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -104,3 +106,8 @@ def load() -> C.CDLL:
 def check(rc: int):
     if rc != 0:
         raise BpltvError(rc, load().bpltv_last_error().decode("utf-8", "replace"))
+
+
+def reload_env():
+    """Re-read the BPLTV_* developer switches (the library snapshots them when the first context is created)."""
+    load().bpltv_reload_env()

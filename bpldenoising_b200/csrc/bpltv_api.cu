@@ -18,6 +18,7 @@
 #include <cstddef>
 
 #include "../../include/bpltv.h"
+#include "env_switches.h"
 #include "common.cuh"
 #include "pdps_generic.cuh"
 #include "pdps_march.cuh"
@@ -180,7 +181,7 @@ static int upload_steps(Dev &d, const bpltv_pdps_opts &o, cudaStream_t st)
 // ---------------------------------------------------------------------------
 static int env_int(const char *name, int dflt)
 {
-    const char *s = getenv(name);
+    const char *s = bpltv::env_get(name);
     return (s && *s) ? atoi(s) : dflt;
 }
 
@@ -876,7 +877,7 @@ static int run_tv_gradient(Dev &d, const GradProblem<Real> &gp, cudaStream_t st,
         if (rc != -1) { d.grad.err = nd_work_error(d.nd); return rc; }
         // -1: fronts beyond shared memory for this image size — the band solver takes over
     }
-    const char *lu_env = getenv("BPLTV_GRAD_REG_LU");
+    const char *lu_env = bpltv::env_get("BPLTV_GRAD_REG_LU");
     const bool lu = lu_env && *lu_env ? atoi(lu_env) != 0 : true;
     if (gp.regularised && lu && gp.M == gp.N && gp.M >= 4) {
         LuProblem<Real> lp;
@@ -1170,6 +1171,8 @@ extern "C" {
 
 int bpltv_version(void) { return BPLTV_VERSION; }
 
+void bpltv_reload_env(void) { bpltv::env_reload(); }
+
 const char *bpltv_last_error(void) { return g_last_error.c_str(); }
 
 void bpltv_default_pdps_opts(bpltv_pdps_opts *o)
@@ -1216,6 +1219,7 @@ int bpltv_create(const int *device_ids, int ndev, int precision, bpltv_ctx **out
         return fail(BPLTV_ERR_NODEVICE, "no CUDA device (%s); libbpltv has no CPU fallback",
                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
     }
+    bpltv::env_get("BPLTV_PDPS_KERNEL");      // takes the snapshot of the BPLTV_* switches if none exists yet
     bpltv_ctx *ctx = new bpltv_ctx();
     ctx->prec = precision;
     std::memset(&ctx->stats, 0, sizeof ctx->stats);
@@ -1309,12 +1313,16 @@ static int check_eval(bpltv_ctx *ctx, const double *lam, int lm, int ln, const b
     RC_TRY(check_lambda(lam, lm, ln));
     if (opts) eo = *opts; else bpltv_default_eval_opts(&eo);
     RC_TRY(check_pdps_opts(eo.pdps));
-    if (ctx->M != ctx->N)
+    // force_branch == 3 evaluates the loss alone (λ-sweeps, validation): no gradient is formed, so neither the
+    // reference's square-image precondition nor λ > 0 applies (like the sum-of-regularisers path)
+    const bool grad_needed = eo.force_branch != 3;
+    if (grad_needed && ctx->M != ctx->N)
         return fail(BPLTV_ERR_ARG, "the gradient assumes square images like the reference "
                                    "(TVLearningFunctionVec.jl:102); got %dx%d", ctx->M, ctx->N);
     if (lm > ctx->M || ln > ctx->N) return fail(BPLTV_ERR_ARG, "lambda grid larger than the image");
     for (int k = 0; k < lm * ln; ++k)
-        if (!(lam[k] > 0.0)) return fail(BPLTV_ERR_ARG, "lambda[%d] must be > 0 for the gradient", k);
+        if (grad_needed ? !(lam[k] > 0.0) : !(lam[k] >= 0.0))
+            return fail(BPLTV_ERR_ARG, grad_needed ? "lambda[%d] must be > 0 for the gradient" : "lambda[%d] must be >= 0", k);
     if (!(eo.gamma > 0) || !(eo.act_tol >= 0)) return fail(BPLTV_ERR_ARG, "bad gamma / act_tol");
     return 0;
 }

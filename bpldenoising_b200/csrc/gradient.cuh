@@ -20,6 +20,7 @@
 //
 // Mapping: one CTA per image "slot"; images are processed in waves of ≤ #SM slots.
 #pragma once
+#include "env_switches.h"
 #include <cooperative_groups.h>
 
 #include <cstdio>
@@ -1071,7 +1072,7 @@ static inline cudaError_t launch_factor(const GradSlots &ws, double guard, int u
         // shared look-ahead with the weighted tile distribution: A/B on B200 — 23.8 -> 22.1 ms (cameraman),
         // 27.7 -> 25.3 ms (10 faces), 20.6 -> 18.5 ms (circle, patch), 165 -> 140 ms (32 images of 256x256);
         // bit-identical results either way
-        const char *pla_env = getenv("BPLTV_GRAD_PLA");
+        const char *pla_env = bpltv::env_get("BPLTV_GRAD_PLA");
         const bool pla = pla_env && *pla_env ? atoi(pla_env) != 0 : true;
         if (pla) {
             cudaError_t e = cudaFuncSetAttribute(grad_factor_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1124,7 +1125,7 @@ static inline cudaError_t launch_factor(const GradSlots &ws, double guard, int u
 // look-ahead pivots → barrier), which a cluster barrier only lengthens (measured: 24 ms with 1 or 8 CTAs).
 static inline int factor_cluster_size(int images_in_wave, int sm_count, int max_band)
 {
-    const char *env = getenv("BPLTV_GRAD_CLUSTER");
+    const char *env = bpltv::env_get("BPLTV_GRAD_CLUSTER");
     if (env && *env) { const int c = atoi(env); if (c == 1 || c == 2 || c == 4 || c == 8 || c == 16) return c; }
     if (max_band < 600) return 1;
     int C = 1;
@@ -1245,7 +1246,7 @@ static int run_gradient(GradWork &w, const GradProblem<Real> &gp, int sm_count, 
     gv.lm = gp.lm; gv.ln = gp.ln;
     gv.alpha_s = gp.alpha_s; gv.gamma = gp.gamma; gv.act_tol = gp.act_tol; gv.eps_act = gp.eps_act;
     gv.guard_rel = 1e-13;
-    gv.refine = getenv("BPLTV_GRAD_REFINE") ? atoi(getenv("BPLTV_GRAD_REFINE")) : 1;
+    gv.refine = bpltv::env_get("BPLTV_GRAD_REFINE") ? atoi(bpltv::env_get("BPLTV_GRAD_REFINE")) : 1;
     // pivot floor relative to the scale of B C⁻¹ Bᵀ (C⁻¹ = λ for the patch-reg system, 1 otherwise)
     double cscale = 1.0;
     if (gv.regularised && gv.patch) cscale = 1.0;  // refined below from the map's max on the host side if needed
@@ -1263,7 +1264,7 @@ static int run_gradient(GradWork &w, const GradProblem<Real> &gp, int sm_count, 
         grad_classify_kernel<Real><<<cnt, GRAD_THREADS, 0, st>>>(ws, gv, gp.u, gp.ubar, gp.alpha_map, img0);
         grad_assemble_kernel<<<cnt, GRAD_THREADS, 0, st>>>(ws);
         {
-            cudaError_t fe = launch_factor(ws, guard, use_stage, getenv("BPLTV_GRAD_DBG") ? atoi(getenv("BPLTV_GRAD_DBG")) : 0, cnt,
+            cudaError_t fe = launch_factor(ws, guard, use_stage, bpltv::env_get("BPLTV_GRAD_DBG") ? atoi(bpltv::env_get("BPLTV_GRAD_DBG")) : 0, cnt,
                                            factor_cluster_size(cnt, sm_count, ws.LD), smem, st);
             if (fe != cudaSuccess) { cudaGetLastError(); return grad_fail(w, -2, std::string("factor launch failed: ") + cudaGetErrorString(fe)); }
         }

@@ -7,6 +7,7 @@
 //             and patch (:192-215, `α[:] .* Gᵀ(B−C)G`, row-scaled as written), forward differences only,
 //             half-bandwidth n.
 #pragma once
+#include "env_switches.h"
 #include "gradient.cuh"
 #include "lu_band.cuh"
 
@@ -33,7 +34,7 @@ struct LuProblem {
 // then its panel chain) as leave every image of the wave its own cluster; one when the trailing window has too few 32×32 tiles to share.  BPLTV_LU_CLUSTER overrides.
 static inline int lu_cluster_ctas(int images_in_wave, int sm_count, int bw)
 {
-    const char *env = getenv("BPLTV_LU_CLUSTER");
+    const char *env = bpltv::env_get("BPLTV_LU_CLUSTER");
     if (env && *env) { const int c = atoi(env); if (c == 1 || c == 2 || c == 4 || c == 8 || c == 16) return c; }
     if (bw < 200) return 1;
     int C = 1;

@@ -65,7 +65,7 @@ struct NdWork {
     NdPlan plan;
     NdBuf pix, off, vec, posg, foff, totals, ast, L, U0, U1, UV0, UV1, info, out_img, relres, relres_max;
     std::vector<long long> h_totals;
-    int attr_smem_factor = 0, attr_smem_solve = 0;
+    int attr_smem_factor = 0, attr_smem_solve = 0, attr_smem_factor_small = 0, attr_smem_solve_small = 0;
     // what the last call saw (statistics)
     double last_relres = 0.0;
     long long last_guarded = 0;
@@ -121,14 +121,6 @@ static inline int nd_build_plan(NdPlan &pl, int n, cudaStream_t st, std::string 
     return 0;
 }
 
-// threads of the per-front kernels of a level, from the (estimated) largest front of the level
-static inline int nd_factor_threads(int nF)
-{
-    const int nt = (nF + 31) / 32, ntiles = nt * (nt + 1) / 2;
-    return 32 * std::min(16, std::max(2, ntiles));
-}
-static inline int nd_solve_threads(int nF) { return std::min(512, std::max(64, (nF + 31) & ~31)); }
-
 static inline int nd_fail(NdWork &w, int code, const std::string &msg) { w.err = msg; return code; }
 
 template <typename Real>
@@ -150,23 +142,46 @@ static int run_gradient_nd(NdWork &w, const NdProblem &gp, int sm_count, size_t 
     const NdSymbolic &sym = w.plan.sym;
     const int nf = (int)sym.fronts.size(), nsteps = sym.nsteps();
     if (nsteps > 62) return nd_fail(gw, -1, "image too large for the nested-dissection level table");
-    // shared memory of the largest level (worst case: mb unknowns on every pixel)
-    size_t fsmem = 0, ssmem = 0;
+    // launch plan of every level; shared memory of the largest (worst case: mb unknowns on every pixel)
+    const double fsz = node ? 1.0 : 1.25;        // typical unknowns per pixel, for CTA sizes and arenas only
+    std::vector<NdLevelPlan> plan(nsteps);
+    std::vector<char> plan_small(nsteps);
+    size_t fsmem = 0, ssmem = 0, fsmem_small = 0, ssmem_small = 0;
     for (int s = 0; s < nsteps; ++s) {
-        fsmem = std::max(fsmem, nd_factor_smem(mb * sym.step_max_front_pix[s], s > 0 ? mb * sym.step_max_ring_pix[s - 1] : 0));
-        ssmem = std::max(ssmem, nd_solve_smem(mb * sym.step_max_front_pix[s]));
+        plan[s] = nd_level_plan(sym, s, mb, fsz);
+        plan_small[s] = plan[s].small;
+        if (plan[s].small) { fsmem_small = std::max(fsmem_small, plan[s].smem_f); ssmem_small = std::max(ssmem_small, plan[s].smem_s); }
+        // every level can also run on the generic kernels
+        fsmem = std::max(fsmem, nd_factor_smem(plan[s].nFw, s > 0 ? mb * sym.step_max_ring_pix[s - 1] : 0));
+        ssmem = std::max(ssmem, nd_solve_smem(plan[s].nFw));
     }
-    if (fsmem > smem_optin || ssmem > smem_optin) return -1;      // the caller falls back to the band solver
-    if (w.attr_smem_factor < (int)fsmem) {
-        cudaError_t e = cudaFuncSetAttribute(nd_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
-        if (e != cudaSuccess) { cudaGetLastError(); return nd_fail(gw, -2, std::string("nd_factor attributes: ") + cudaGetErrorString(e)); }
-        w.attr_smem_factor = (int)fsmem;
-    }
-    if (w.attr_smem_solve < (int)ssmem) {
-        cudaError_t e = cudaFuncSetAttribute(nd_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(nd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem);
-        if (e != cudaSuccess) { cudaGetLastError(); return nd_fail(gw, -2, std::string("nd_solve attributes: ") + cudaGetErrorString(e)); }
-        w.attr_smem_solve = (int)ssmem;
+    if (fsmem > smem_optin || ssmem > smem_optin || fsmem_small > smem_optin || ssmem_small > smem_optin)
+        return -1;      // the caller falls back to the band solver
+    {
+        cudaError_t e = cudaSuccess;
+        if (w.attr_smem_factor < (int)fsmem) {
+            e = cudaFuncSetAttribute(nd_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+            w.attr_smem_factor = (int)fsmem;
+        }
+        if (e == cudaSuccess && w.attr_smem_solve < (int)ssmem) {
+            e = cudaFuncSetAttribute(nd_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(nd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem);
+            w.attr_smem_solve = (int)ssmem;
+        }
+        if (e == cudaSuccess && w.attr_smem_factor_small < (int)fsmem_small) {
+            e = cudaFuncSetAttribute(nd_factor_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem_small);
+            w.attr_smem_factor_small = (int)fsmem_small;
+        }
+        if (e == cudaSuccess && w.attr_smem_solve_small < (int)ssmem_small) {
+            e = cudaFuncSetAttribute(nd_fwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem_small);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(nd_bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem_small);
+            w.attr_smem_solve_small = (int)ssmem_small;
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            w.attr_smem_factor = w.attr_smem_solve = w.attr_smem_factor_small = w.attr_smem_solve_small = 0;
+            return nd_fail(gw, -2, std::string("nested-dissection kernel attributes: ") + cudaGetErrorString(e));
+        }
     }
 
     // ---- per-slot sizes.  Pools of the MULT form are estimated at 2.2× the one-unknown-per-pixel sizes (≈ 1.5
@@ -178,7 +193,7 @@ static int run_gradient_nd(NdWork &w, const NdProblem &gp, int sm_count, size_t 
     const size_t pool_bytes = (size_t)(est * (double)(t1[0] + 2 * t1[1] + 2 * t1[2])) * 8;
     const size_t per_slot = fix_bytes + pool_bytes;
     w.last_bytes_per_image = per_slot;
-    int slots = std::min(gp.O, 1024);
+    int slots = std::min(gp.O, 256);      // 256 images already give every level thousands of fronts
     {
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
@@ -240,7 +255,6 @@ static int run_gradient_nd(NdWork &w, const NdProblem &gp, int sm_count, size_t 
     const int refine = gp.maxit > 0 ? std::min(gp.maxit, 8) : 1;
     const int chunks = std::max(1, std::min(64, (N + 255) / 256));
     const int pgroups = std::max(1, std::min(ng, 32));
-    const double fsz = node ? 1.0 : 1.25;        // typical unknowns per pixel, for the CTA sizes only
 
     for (int img0 = 0; img0 < gp.O; img0 += slots) {
         const int cnt = std::min(slots, gp.O - img0);
@@ -276,24 +290,34 @@ static int run_gradient_nd(NdWork &w, const NdProblem &gp, int sm_count, size_t 
         nd.UV[0] = (double *)w.UV0.p; nd.UV[1] = (double *)w.UV1.p; nd.UV_stride = UVs;
         w.last_bytes_per_image = fix_bytes + (Ls + 2 * Us + 2 * UVs) * 8;
 
+        // the warp-per-front kernels pay off when the level has warps for every scheduler of the GPU; with few fronts (the
+        // upper small levels of a single image) a CTA per front is faster (ncu, 1 image of 128²: 48 vs 117 µs at 256 fronts)
+        for (int s = 0; s < nsteps; ++s) plan[s].small = plan_small[s] && (long long)plan[s].nfr * cnt >= 4LL * sm_count;
         for (int s = 0; s < nsteps; ++s) {
-            const int t0 = sym.step_start[s], cntf = sym.step_start[s + 1] - t0;
-            const int nFw = mb * sym.step_max_front_pix[s];
-            const int T = nd_factor_threads((int)(fsz * sym.step_max_front_pix[s]));
-            const size_t sm = nd_factor_smem(nFw, s > 0 ? mb * sym.step_max_ring_pix[s - 1] : 0);
-            nd_factor_kernel<<<dim3(cntf, cnt), T, sm, st>>>(nd, t0, s & 1, guard, nFw);
+            const NdLevelPlan &lp = plan[s];
+            if (lp.small)
+                nd_factor_small_kernel<<<dim3((lp.nfr + ND_SMALL_WARPS - 1) / ND_SMALL_WARPS, cnt), 32 * ND_SMALL_WARPS, lp.smem_f, st>>>(
+                    nd, lp.t0, lp.nfr, s & 1, guard, lp.arena_f);
+            else
+                nd_factor_kernel<<<dim3(lp.nfr, cnt), lp.threads_f, nd_factor_smem(lp.nFw, s > 0 ? mb * sym.step_max_ring_pix[s - 1] : 0), st>>>(nd, lp.t0, s & 1, guard, lp.nFw);
         }
         *launches += nsteps;
         auto solve = [&](double *vec, size_t stride) {
             for (int s = 0; s < nsteps; ++s) {
-                const int t0 = sym.step_start[s], cntf = sym.step_start[s + 1] - t0;
-                const int T = nd_solve_threads((int)(fsz * sym.step_max_front_pix[s]));
-                nd_fwd_kernel<<<dim3(cntf, cnt), T, nd_solve_smem(mb * sym.step_max_front_pix[s]), st>>>(nd, t0, s & 1, vec, stride);
+                const NdLevelPlan &lp = plan[s];
+                if (lp.small)
+                    nd_fwd_small_kernel<<<dim3((lp.nfr + ND_SMALL_WARPS - 1) / ND_SMALL_WARPS, cnt), 32 * ND_SMALL_WARPS, lp.smem_s, st>>>(
+                        nd, lp.t0, lp.nfr, s & 1, vec, stride, lp.arena_s);
+                else
+                    nd_fwd_kernel<<<dim3(lp.nfr, cnt), lp.threads_s, nd_solve_smem(lp.nFw), st>>>(nd, lp.t0, s & 1, vec, stride);
             }
             for (int s = nsteps - 1; s >= 0; --s) {
-                const int t0 = sym.step_start[s], cntf = sym.step_start[s + 1] - t0;
-                const int T = nd_solve_threads((int)(fsz * sym.step_max_front_pix[s]));
-                nd_bwd_kernel<<<dim3(cntf, cnt), T, nd_solve_smem(mb * sym.step_max_front_pix[s]), st>>>(nd, t0, vec, stride);
+                const NdLevelPlan &lp = plan[s];
+                if (lp.small)
+                    nd_bwd_small_kernel<<<dim3((lp.nfr + ND_SMALL_WARPS - 1) / ND_SMALL_WARPS, cnt), 32 * ND_SMALL_WARPS, lp.smem_s, st>>>(
+                        nd, lp.t0, lp.nfr, vec, stride, lp.arena_s);
+                else
+                    nd_bwd_kernel<<<dim3(lp.nfr, cnt), lp.threads_s, nd_solve_smem(lp.nFw), st>>>(nd, lp.t0, vec, stride);
             }
             *launches += 2 * nsteps;
         };

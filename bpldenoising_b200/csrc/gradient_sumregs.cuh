@@ -20,6 +20,7 @@
 // cannot be symmetrised and so has no SPD compliance form: it is solved in node space by the band LU of
 // lu_band.cuh (run_gradient3_lu below).
 #pragma once
+#include "env_switches.h"
 #include "gradient.cuh"
 #include "sumregs_stencils.cuh"
 #include "gradient_lu.cuh"
@@ -386,7 +387,7 @@ static int run_gradient3(GradWork &w, const Grad3Problem<Real> &gp, int sm_count
     if (gp.regularised && gp.alpha_maps) return band_lu();   // row-scaled, non-symmetric (:246): node-space band LU
     {   // scalar sumregs_gradient_reg (:112-167, γ = 1e3): n² unknowns with half-bandwidth 2n in node space
         // instead of ≤ 6n² modes with half-bandwidth ≤ 6(2n+1) in multiplier space.  BPLTV_SUMREGS_REG_LU=0/1.
-        const char *lu_env = getenv("BPLTV_SUMREGS_REG_LU");
+        const char *lu_env = bpltv::env_get("BPLTV_SUMREGS_REG_LU");
         const bool lu = lu_env && *lu_env ? atoi(lu_env) != 0 : BPLTV_SUMREGS_REG_LU_DEFAULT;
         if (gp.regularised && lu) {
             const int rc = band_lu();
@@ -477,7 +478,7 @@ static int run_gradient3(GradWork &w, const Grad3Problem<Real> &gp, int sm_count
         grad3_classify_kernel<Real><<<cnt, GRAD_THREADS, 0, st>>>(ws, gv, gp.u, gp.ubar, gp.alpha_maps, img0);
         grad3_assemble_kernel<<<cnt, GRAD_THREADS, 0, st>>>(ws);
         {
-            cudaError_t fe = launch_factor(ws, guard, use_stage, getenv("BPLTV_GRAD_DBG") ? atoi(getenv("BPLTV_GRAD_DBG")) : 0, cnt, factor_cluster_size(cnt, sm_count, ws.LD), smem, st);
+            cudaError_t fe = launch_factor(ws, guard, use_stage, bpltv::env_get("BPLTV_GRAD_DBG") ? atoi(bpltv::env_get("BPLTV_GRAD_DBG")) : 0, cnt, factor_cluster_size(cnt, sm_count, ws.LD), smem, st);
             if (fe != cudaSuccess) { cudaGetLastError(); return grad_fail(w, -2, std::string("factor launch failed: ") + cudaGetErrorString(fe)); }
         }
         grad3_solve_kernel<<<cnt, GRAD_THREADS, zs_bytes, st>>>(ws, gv, (double *)w.out_img, (double *)w.relres, img0, zs_cap);

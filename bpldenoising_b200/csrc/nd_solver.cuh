@@ -607,4 +607,363 @@ __global__ void nd_bwd_kernel(NdDev nd, int t0, double *vec_all, size_t vec_stri
     }
 }
 
+
+// ===========================================================================
+// Small fronts (the bottom levels of the tree: thousands of fronts of 25-60 unknowns per image): ONE WARP per front,
+// several fronts per CTA, the whole front in shared memory, no CTA barrier inside the factorisation.  The generic
+// kernels above spend a 64-thread CTA, five CTA barriers per block step and a round trip through global memory on
+// each of them (ncu, 148 images of 128×128: 70 % of the factorisation time in the four bottom levels).
+// The CTA's shared-memory arena is packed greedily: the fronts of its warps are processed in as few rounds as fit
+// (one, except when a multiplier-form image is flat nearly everywhere).
+// ===========================================================================
+constexpr int ND_SMALL_WARPS = 8;
+constexpr int ND_SMALL_MAXF = 128;      // levels whose largest possible front is at most this (and whose typical front is at most
+constexpr int ND_SMALL_TYPF = 64;       // this) may go to the small kernels — when there are enough fronts to fill the GPU with warps
+
+// arena (doubles) of a level: room for the largest possible single front, and for ND_SMALL_WARPS typical ones
+static inline int nd_small_arena(int nF_worst, int nP_worst, int nF_typ, bool factor)
+{
+    const long long one = factor ? (long long)nF_worst * nF_worst + nF_worst + 2 : (long long)nF_worst * nP_worst + nF_worst + 2;
+    const long long typ = factor ? (long long)nF_typ * nF_typ + nF_typ + 2 : (long long)nF_typ * std::min(nP_worst, nF_typ) + nF_typ + 2;
+    long long a = std::max(one, (long long)ND_SMALL_WARPS * typ);
+    a = std::min(a, std::max(one, (long long)12 * 1024));      // ≤ 96 KB unless a single front needs more: ≥ 2 CTAs per SM
+    return (int)((a + 1) & ~1LL);
+}
+static inline size_t nd_small_smem(int arena) { return (size_t)arena * sizeof(double) + 2 * ND_SMALL_WARPS * sizeof(int); }
+
+// which warps of the CTA run in round `round`: warps [w0, w1) such that their needs fit the arena (greedy, in order).
+// Every thread evaluates this from the same shared table, so all agree without further communication.
+static __device__ __forceinline__ bool nd_small_round(const int *s_need, int nw, int arena, int round, int w, int &base)
+{
+    int w0 = 0;
+    for (int r = 0;; ++r) {
+        int w1 = w0, used = 0;
+        while (w1 < nw && (w1 == w0 || used + s_need[w1] <= arena)) { used += s_need[w1]; ++w1; }
+        if (r == round) {
+            if (w < w0 || w >= w1) return false;
+            base = 0;
+            for (int k = w0; k < w; ++k) base += s_need[k];
+            return true;
+        }
+        w0 = w1;
+        if (w0 >= nw) return false;
+    }
+}
+static __device__ __forceinline__ int nd_small_rounds(const int *s_need, int nw, int arena)
+{
+    int w0 = 0, rounds = 0;
+    while (w0 < nw) {
+        int w1 = w0, used = 0;
+        while (w1 < nw && (w1 == w0 || used + s_need[w1] <= arena)) { used += s_need[w1]; ++w1; }
+        w0 = w1; ++rounds;
+    }
+    return rounds;
+}
+
+static __device__ __forceinline__ double nd_warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+static __device__ __forceinline__ double nd_warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// grid (ceil(fronts of the level / ND_SMALL_WARPS), slots), block 32·ND_SMALL_WARPS
+__global__ void __launch_bounds__(32 * ND_SMALL_WARPS) nd_factor_small_kernel(NdDev nd, int t0, int nfr, int par, double guard, int arena)
+{
+    ND_DYN_SMEM(sm);
+    int *s_need = reinterpret_cast<int *>(sm + arena);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int slot = blockIdx.y;
+    const int t = t0 + blockIdx.x * nw + warp;
+    const bool live = t < t0 + nfr;
+    const NdFront f = nd.fronts[live ? t : t0];
+    const int *pos = nd.posg + nd.posg_stride * slot + f.pix0 + (live ? t : t0);
+    const long long *foff = nd.foff + nd.foff_stride * slot;
+    const int nP = live ? pos[f.npiv] : 0, nF = live ? pos[f.npiv + f.nring] : 0, nR = nF - nP;
+    if (lane == 0) s_need[warp] = live ? ((nF * nF + nF + 2) & ~1) : 0;
+    __syncthreads();
+    const int rounds = nd_small_rounds(s_need, nw, arena);
+    const double *ast = nd.ast + nd.ast_stride * slot;
+    const int MB = nd.mb, MB2 = MB * MB;
+    int guarded = 0, bad = 0;
+    for (int round = 0; round < rounds; ++round) {
+        int base = 0;
+        if (live && nd_small_round(s_need, nw, arena, round, warp, base)) {
+            double *F = sm + base;                              // column-major nF×nF, lower triangle
+            int *umap = reinterpret_cast<int *>(F + (size_t)nF * nF);
+            double *L = nd.L + nd.L_stride * slot + foff[4 * (size_t)t];
+            double *U = nd.U[par] + nd.U_stride * slot + foff[4 * (size_t)t + 1];
+            for (int k = lane; k < nF * nF; k += 32) F[k] = 0.0;
+            __syncwarp();
+            {
+                const int ne = nd.nnb + 1;
+                for (int idx = lane; idx < f.npiv * ne; idx += 32) {
+                    const int kp = idx / ne, e = idx - kp * ne;
+                    const int p = nd.pixlist[f.pix0 + kp];
+                    const int a0 = pos[kp], mp = pos[kp + 1] - a0;
+                    if (e == 0) {
+                        const double *blk = ast + (size_t)p * nd.nh * MB2;
+                        for (int al = 0; al < mp; ++al)
+                            for (int be = al; be < mp; ++be) F[(a0 + al) * nF + a0 + be] = blk[be * MB + al];
+                    } else {
+                        const int kq = nd.nbr[f.nbr0 + kp * nd.nnb + (e - 1)];
+                        if (kq <= kp) continue;
+                        const int q = nd.pixlist[f.pix0 + kq];
+                        const int b0 = pos[kq], mq = pos[kq + 1] - b0;
+                        const int h = 1 + ((e - 1) >> 1);
+                        const bool fwd = ((e - 1) & 1) == 0;
+                        const double *blk = ast + ((size_t)(fwd ? p : q) * nd.nh + h) * MB2;
+                        for (int al = 0; al < mp; ++al)
+                            for (int be = 0; be < mq; ++be)
+                                F[(a0 + al) * nF + b0 + be] = fwd ? blk[be * MB + al] : blk[al * MB + be];
+                    }
+                }
+            }
+            __syncwarp();
+            for (int ci = 0; ci < 2; ++ci) {
+                const int c = ci == 0 ? f.child0 : f.child1;
+                if (c < 0) continue;
+                const NdFront cf = nd.fronts[c];
+                const int *cpos = nd.posg + nd.posg_stride * slot + cf.pix0 + c + cf.npiv;
+                const int cnP = cpos[0], cnR = cpos[cf.nring] - cnP;
+                for (int k = lane; k < cf.nring; k += 32) {
+                    const int r0 = cpos[k] - cnP, m = cpos[k + 1] - cpos[k];
+                    const int R0 = pos[nd.cmap[cf.cmap0 + k]];
+                    for (int al = 0; al < m; ++al) umap[r0 + al] = R0 + al;
+                }
+                __syncwarp();
+                const double *cU = nd.U[par ^ 1] + nd.U_stride * slot + foff[4 * (size_t)c + 1];
+                for (int idx = lane; idx < cnR * cnR; idx += 32) {
+                    const int r = idx % cnR, cc = idx / cnR;
+                    if (r < cc) continue;
+                    int R = umap[r], C = umap[cc];
+                    if (R < C) { const int s = R; R = C; C = s; }
+                    F[C * nF + R] += cU[idx];
+                }
+                __syncwarp();
+            }
+            // right-looking Cholesky of the first nP columns; the pivot rule sees the whole column (see nd_diag_block)
+            for (int c = 0; c < nP; ++c) {
+                double *col = F + c * nF;
+                double d = col[c];
+                if (guard > 0.0) {
+                    double am = 0.0;
+                    for (int r = c + 1 + lane; r < nF; r += 32) am = fmax(am, fabs(col[r]));
+                    am = nd_warp_max(am);
+                    const double floor_ = fmax(guard, am * am * 0.0625);
+                    if (!(d >= floor_)) { d = floor_; if (lane == 0) ++guarded; }
+                } else if (!(d > 0.0)) {
+                    bad = 1; d = 1.0;
+                }
+                const double inv = rsqrt(d);
+                __syncwarp();
+                if (lane == 0) col[c] = d * inv;
+                for (int r = c + 1 + lane; r < nF; r += 32) {
+                    const double l = col[r] * inv;
+                    col[r] = l;
+                    if (!(fabs(l) <= ND_LMAX)) bad = 1;
+                }
+                __syncwarp();
+                // rank-one update of the trailing lower triangle: each lane keeps the multipliers of its rows
+                // (r = c+1+lane, +32, …) in registers and sweeps four columns at a time — loads, FMAs, stores grouped
+                // so that the shared-memory round trips of the four columns overlap
+                {
+                    double lr[ND_SMALL_MAXF / 32];
+#pragma unroll
+                    for (int k = 0; k < ND_SMALL_MAXF / 32; ++k) {
+                        const int r = c + 1 + lane + 32 * k;
+                        lr[k] = r < nF ? col[r] : 0.0;
+                    }
+                    for (int c2 = c + 1; c2 < nF; c2 += 4) {
+                        double lc[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) lc[j] = c2 + j < nF ? col[c2 + j] : 0.0;
+#pragma unroll
+                        for (int k = 0; k < ND_SMALL_MAXF / 32; ++k) {
+                            const int r = c + 1 + lane + 32 * k;
+                            if (r < c2 || r >= nF) continue;
+                            double tv[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) tv[j] = (c2 + j <= r) ? F[(c2 + j) * nF + r] : 0.0;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) tv[j] = fma(-lr[k], lc[j], tv[j]);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) if (c2 + j <= r) F[(c2 + j) * nF + r] = tv[j];
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            for (int idx = lane; idx < nF * nP; idx += 32) L[idx] = F[idx];
+            for (int idx = lane; idx < nR * nR; idx += 32) {
+                const int r = idx % nR, cc = idx / nR;
+                if (r >= cc) U[idx] = F[(nP + cc) * nF + nP + r];
+            }
+        }
+        __syncthreads();
+    }
+    if (guarded) atomicAdd(nd.info + 4 * slot, guarded);
+    if (bad) atomicAdd(nd.info + 4 * slot + 1, 1);
+}
+
+__global__ void __launch_bounds__(32 * ND_SMALL_WARPS) nd_fwd_small_kernel(NdDev nd, int t0, int nfr, int par, double *vec_all, size_t vec_stride, int arena)
+{
+    ND_DYN_SMEM(sm);
+    int *s_need = reinterpret_cast<int *>(sm + arena);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int slot = blockIdx.y;
+    const int t = t0 + blockIdx.x * nw + warp;
+    const bool live = t < t0 + nfr;
+    const NdFront f = nd.fronts[live ? t : t0];
+    const int *pos = nd.posg + nd.posg_stride * slot + f.pix0 + (live ? t : t0);
+    const long long *foff = nd.foff + nd.foff_stride * slot;
+    const int *off = nd.off ? nd.off + nd.off_stride * slot : nullptr;
+    const int nP = live ? pos[f.npiv] : 0, nF = live ? pos[f.npiv + f.nring] : 0, nR = nF - nP;
+    if (lane == 0) s_need[warp] = live ? ((nF * nP + nF + 2) & ~1) : 0;
+    __syncthreads();
+    const int rounds = nd_small_rounds(s_need, nw, arena);
+    double *vec = vec_all + vec_stride * slot;
+    for (int round = 0; round < rounds; ++round) {
+        int base = 0;
+        if (live && nd_small_round(s_need, nw, arena, round, warp, base)) {
+            double *Ls = sm + base, *v = Ls + (size_t)nF * nP;
+            const double *L = nd.L + nd.L_stride * slot + foff[4 * (size_t)t];
+            double *uv = nd.UV[par] + nd.UV_stride * slot + foff[4 * (size_t)t + 2];
+            for (int idx = lane; idx < nF * nP; idx += 32) Ls[idx] = L[idx];
+            for (int k = lane; k < f.npiv + f.nring; k += 32) {
+                const int a0 = pos[k], m = pos[k + 1] - a0;
+                if (k < f.npiv) {
+                    const int q = nd.pixlist[f.pix0 + k];
+                    const int g0 = off ? off[q] : q;
+                    for (int al = 0; al < m; ++al) v[a0 + al] = vec[g0 + al];
+                } else {
+                    for (int al = 0; al < m; ++al) v[a0 + al] = 0.0;
+                }
+            }
+            __syncwarp();
+            for (int ci = 0; ci < 2; ++ci) {
+                const int c = ci == 0 ? f.child0 : f.child1;
+                if (c < 0) continue;
+                const NdFront cf = nd.fronts[c];
+                const int *cpos = nd.posg + nd.posg_stride * slot + cf.pix0 + c + cf.npiv;
+                const int cnP = cpos[0];
+                const double *cuv = nd.UV[par ^ 1] + nd.UV_stride * slot + foff[4 * (size_t)c + 2];
+                for (int k = lane; k < cf.nring; k += 32) {
+                    const int r0 = cpos[k] - cnP, m = cpos[k + 1] - cpos[k];
+                    const int R0 = pos[nd.cmap[cf.cmap0 + k]];
+                    for (int al = 0; al < m; ++al) v[R0 + al] += cuv[r0 + al];
+                }
+                __syncwarp();
+            }
+            for (int c = 0; c < nP; ++c) {
+                const double *col = Ls + c * nF;
+                const double yc = v[c] / col[c];
+                __syncwarp();
+                if (lane == 0) v[c] = yc;
+                for (int r = c + 1 + lane; r < nF; r += 32) v[r] = fma(-col[r], yc, v[r]);
+                __syncwarp();
+            }
+            for (int k = lane; k < f.npiv; k += 32) {
+                const int a0 = pos[k], m = pos[k + 1] - a0;
+                const int q = nd.pixlist[f.pix0 + k];
+                const int g0 = off ? off[q] : q;
+                for (int al = 0; al < m; ++al) vec[g0 + al] = v[a0 + al];
+            }
+            for (int r = lane; r < nR; r += 32) uv[r] = v[nP + r];
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(32 * ND_SMALL_WARPS) nd_bwd_small_kernel(NdDev nd, int t0, int nfr, double *vec_all, size_t vec_stride, int arena)
+{
+    ND_DYN_SMEM(sm);
+    int *s_need = reinterpret_cast<int *>(sm + arena);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int slot = blockIdx.y;
+    const int t = t0 + blockIdx.x * nw + warp;
+    const bool live = t < t0 + nfr;
+    const NdFront f = nd.fronts[live ? t : t0];
+    const int *pos = nd.posg + nd.posg_stride * slot + f.pix0 + (live ? t : t0);
+    const long long *foff = nd.foff + nd.foff_stride * slot;
+    const int *off = nd.off ? nd.off + nd.off_stride * slot : nullptr;
+    const int nP = live ? pos[f.npiv] : 0, nF = live ? pos[f.npiv + f.nring] : 0;
+    if (lane == 0) s_need[warp] = live ? ((nF * nP + nF + 2) & ~1) : 0;
+    __syncthreads();
+    const int rounds = nd_small_rounds(s_need, nw, arena);
+    double *vec = vec_all + vec_stride * slot;
+    for (int round = 0; round < rounds; ++round) {
+        int base = 0;
+        if (live && nd_small_round(s_need, nw, arena, round, warp, base)) {
+            double *Ls = sm + base, *v = Ls + (size_t)nF * nP;
+            const double *L = nd.L + nd.L_stride * slot + foff[4 * (size_t)t];
+            for (int idx = lane; idx < nF * nP; idx += 32) Ls[idx] = L[idx];
+            for (int k = lane; k < f.npiv + f.nring; k += 32) {
+                const int a0 = pos[k], m = pos[k + 1] - a0;
+                const int q = nd.pixlist[f.pix0 + k];
+                const int g0 = off ? off[q] : q;
+                for (int al = 0; al < m; ++al) v[a0 + al] = vec[g0 + al];
+            }
+            __syncwarp();
+            for (int c = nP - 1; c >= 0; --c) {
+                const double *col = Ls + c * nF;
+                double s = 0.0;
+                for (int r = c + 1 + lane; r < nF; r += 32) s = fma(col[r], v[r], s);
+                s = nd_warp_sum(s);
+                const double xc = (v[c] - s) / col[c];
+                __syncwarp();
+                if (lane == 0) v[c] = xc;
+                __syncwarp();
+            }
+            for (int k = lane; k < f.npiv; k += 32) {
+                const int a0 = pos[k], m = pos[k + 1] - a0;
+                const int q = nd.pixlist[f.pix0 + k];
+                const int g0 = off ? off[q] : q;
+                for (int al = 0; al < m; ++al) vec[g0 + al] = v[a0 + al];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+
+// how one level of the tree is launched (shared by gradient_nd.cuh and the emulation harness)
+struct NdLevelPlan {
+    bool small;                 // warp-per-front kernels
+    int t0, nfr;                // fronts of the level
+    int nFw;                    // largest possible front (mb unknowns on every pixel)
+    int threads_f, threads_s;   // generic kernels: CTA sizes of the factorisation / of the solves
+    size_t smem_f, smem_s;      // dynamic shared memory of the factorisation / of the solves
+    int arena_f, arena_s;       // small kernels: arena (doubles)
+};
+static inline NdLevelPlan nd_level_plan(const NdSymbolic &sym, int s, int mb, double typ_per_pixel)
+{
+    NdLevelPlan lp;
+    lp.t0 = sym.step_start[s]; lp.nfr = sym.step_start[s + 1] - lp.t0;
+    lp.nFw = mb * sym.step_max_front_pix[s];
+    const int nPw = mb * sym.step_max_piv_pix[s];
+    const int nFt = std::min(lp.nFw, (int)(typ_per_pixel * sym.step_max_front_pix[s]) + 1);
+    lp.small = lp.nFw <= ND_SMALL_MAXF && nFt <= ND_SMALL_TYPF;
+    const int nt = (nFt + 31) / 32, ntiles = nt * (nt + 1) / 2;
+    lp.threads_f = 32 * std::min(16, std::max(2, ntiles));
+    lp.threads_s = std::min(512, std::max(64, (nFt + 31) & ~31));
+    lp.arena_f = lp.arena_s = 0;
+    if (lp.small) {
+        lp.arena_f = nd_small_arena(lp.nFw, nPw, nFt, true);
+        lp.arena_s = nd_small_arena(lp.nFw, nPw, nFt, false);
+        lp.smem_f = nd_small_smem(lp.arena_f);
+        lp.smem_s = nd_small_smem(lp.arena_s);
+    } else {
+        lp.smem_f = nd_factor_smem(lp.nFw, s > 0 ? mb * sym.step_max_ring_pix[s - 1] : 0);
+        lp.smem_s = nd_solve_smem(lp.nFw);
+    }
+    return lp;
+}
+
 }  // namespace bpltv

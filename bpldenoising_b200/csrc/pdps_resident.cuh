@@ -18,6 +18,7 @@
 // The path is bounded by barrier latency + shared-memory bandwidth + fp64 issue, not
 // by HBM.  Same operation order as the other kernels: strict mode is bit-identical.
 #pragma once
+#include "env_switches.h"
 #ifndef BPLTV_EMU      // tests/emu/emu_cuda.h supplies cooperative_groups::this_cluster() on OS threads
 #include <cooperative_groups.h>
 #endif
@@ -282,7 +283,7 @@ static inline cudaError_t launch_resident(ResidentArgs<Real> a, size_t smem_opti
     // Few images: 16-CTA clusters (non-portable size) halve the columns per CTA — 5000 iterations of one
     // 128×128 image in 8.0 ms instead of 11.9 ms; they fit about one per GPC, so larger batches (10 images:
     // 16.0 vs 11.9 ms) keep the 8-CTA plan.  BPLTV_RESIDENT_CS caps the cluster size.
-    const char *cs_env = getenv("BPLTV_RESIDENT_CS");
+    const char *cs_env = bpltv::env_get("BPLTV_RESIDENT_CS");
     const int cs_cap = cs_env && *cs_env ? atoi(cs_env) : 16;
     if (cs_cap >= 16) {
         const ResidentPlan p16 = resident_plan<Real>(smem_optin, a.M, a.N, 16);

@@ -12,6 +12,7 @@
 // One IEEE operation per operator of the reference expression in strict mode (bit-identical to
 // oracle/sumregs.py), FMA / rsqrt in fast mode.
 #pragma once
+#include "env_switches.h"
 #ifndef BPLTV_EMU      // tests/emu/emu_cuda.h supplies cooperative_groups::this_cluster() on OS threads
 #include <cooperative_groups.h>
 #endif
@@ -331,7 +332,7 @@ template <typename Real>
 static inline cudaError_t launch_sumregs_resident(SumRegsResArgs<Real> a, size_t smem_optin, bool map, bool strict,
                                                   cudaStream_t st)
 {
-    const char *cs_env = getenv("BPLTV_RESIDENT_CS");
+    const char *cs_env = bpltv::env_get("BPLTV_RESIDENT_CS");
     const int cs_cap = cs_env && *cs_env ? atoi(cs_env) : 16;
     const int caps[2] = {std::min(cs_cap, 16), std::min(cs_cap, 8)};
     cudaError_t last = cudaErrorInvalidValue;

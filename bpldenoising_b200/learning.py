@@ -305,7 +305,7 @@ class Context:
 # module-level functions with the reference's names
 # ------------------------------------------------------------------------------
 _default_ctx: Optional[Context] = None
-_resident_key = None
+_resident = None      # (context, truth array, noisy array) of the last upload — strong references, compared with `is`
 
 
 def default_context() -> Context:
@@ -317,12 +317,15 @@ def default_context() -> Context:
 
 def _ensure_resident(ctx: Context, data):
     """The dataset is constant across the ≤21 evaluations of a learn run
-    (/root/reference/src/TRBox.jl:210,227): upload it once per (truth, noisy) pair."""
-    global _resident_key
-    key = (id(ctx), id(data[0]), id(data[1]), np.asarray(data[1]).shape)
-    if key != _resident_key:
+    (/root/reference/src/TRBox.jl:210,227): upload it once per (truth, noisy) pair.  The pair is recognised by object
+    identity of arrays this module keeps alive (an `id()` of a freed temporary can be reused by the next one), so a new
+    array object — a slice, a copy — is always uploaded again.  In-place edits of an array already uploaded are NOT seen:
+    call `ctx.set_dataset(data)` after editing, like the Julia binding's `set_dataset!`."""
+    global _resident
+    if (_resident is None or _resident[0] is not ctx or _resident[1] is not data[0] or _resident[2] is not data[1]
+            or ctx.shape is None):
         ctx.set_dataset(data)
-        _resident_key = key
+        _resident = (ctx, data[0], data[1])
 
 
 def denoise(data, x, op=None, ctx: Optional[Context] = None, **kwargs) -> np.ndarray:

@@ -197,7 +197,15 @@ int bpltv_sumregs_gradient(bpltv_ctx *ctx, const double *u, const double *lam, i
 
 /* Device-resident variants (single-device contexts only): pointers are device
  * memory of the context's precision (double or float), `stream` a cudaStream_t
- * (NULL → the context's stream).  Asynchronous: nothing is synchronised.
+ * (NULL → the context's stream).  All work is enqueued on `stream` and the call
+ * returns without waiting for it, with these exceptions a caller overlapping
+ * other streams should know: (1) the first call with a given shape / option set
+ * allocates workspaces (cudaMalloc / cudaFree synchronise the device) and uploads
+ * the step-size table (one stream synchronisation); later calls reuse both;
+ * (2) the non-regularised gradient (Δ > Δt) synchronises `stream` once per wave of
+ * ≤ 256 images, after the pixel classification, to size its factor pools (the
+ * number of unknowns is data dependent; one 32-byte read per image).  The loss-only
+ * and the regularised evaluations have no such point.
  * d_costgrad: 1 + lm·ln doubles = [cost, grad...] (what one NCCL all-reduce sums
  * across ranks).  d_u_out may be NULL for learn_eval_device.        */
 int bpltv_denoise_device(bpltv_ctx *ctx, const void *d_noisy, int M, int N, int O,
@@ -210,6 +218,9 @@ int bpltv_learn_eval_device(bpltv_ctx *ctx, const double *lam, int lm, int ln,
                             double *d_costgrad, void *stream);
 
 int bpltv_get_stats(bpltv_ctx *ctx, bpltv_stats *out);
+/* The developer switches (environment variables BPLTV_*) are read once, when the first context is
+ * created; this re-reads them (the test-suite flips them between calls).  Not needed by a normal caller. */
+void bpltv_reload_env(void);
 const char *bpltv_last_error(void);
 int bpltv_version(void);
 

@@ -31,6 +31,8 @@ struct EvalOpts
 end
 
 lasterr() = unsafe_string(ccall((:bpltv_last_error, lib), Cstring, ()))
+# the BPLTV_* developer switches are snapshotted when the first context is created; re-read them after changing ENV
+reload_env() = ccall((:bpltv_reload_env, lib), Cvoid, ())
 check(rc) = rc == 0 ? nothing : (rc == -1 ? throw(ArgumentError(lasterr())) : error("libbpltv ($rc): " * lasterr()))
 
 function default_pdps()

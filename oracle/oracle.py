@@ -62,6 +62,11 @@ def lib() -> ctypes.CDLL:
             f.argtypes = [P, ctypes.c_int, ctypes.c_int, ctypes.c_int, P, ctypes.c_int,
                           ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                           ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, P]
+            ff = getattr(L, f"oracle_pdps_fused_{suf}")
+            ff.restype = ctypes.c_int
+            ff.argtypes = [P, ctypes.c_int, ctypes.c_int, ctypes.c_int, P, ctypes.c_int,
+                           ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                           ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, P]
             g = getattr(L, f"oracle_fwd_grad_{suf}")
             g.restype = None
             g.argtypes = [P, ctypes.c_int, ctypes.c_int, P, P]
@@ -125,10 +130,11 @@ def patch_adjoint(g, m, n):
 # Lower-level solve
 # --------------------------------------------------------------------------
 def pdps(f, alpha, *, maxiter=5000, tau0=5.0, sigma0=0.99 / 5, rho=0.0, accel=True,
-         opnorm=OPNORM, init_mode=0, dtype=np.float64, nthreads=0):
+         opnorm=OPNORM, init_mode=0, dtype=np.float64, nthreads=0, fused=False):
     """denoise(data, x, op): /root/reference/src/TVLearningFunctionVec.jl:45-70.
 
     ``alpha``: scalar, or M×N map (already up-sampled).  Returns M×N×O (Fortran).
+    ``fused``: the single-sweep variant of the same recursion (bit-identical; the stronger CPU baseline of bench.py).
     """
     f3 = _fortran3(f, dtype)
     M, N, O = f3.shape
@@ -140,9 +146,14 @@ def pdps(f, alpha, *, maxiter=5000, tau0=5.0, sigma0=0.99 / 5, rho=0.0, accel=Tr
     else:
         al = al.reshape(1)
     u = np.zeros_like(f3, order="F")
-    fn = getattr(lib(), "oracle_pdps_f64" if dtype == np.float64 else "oracle_pdps_f32")
-    rc = fn(_ptr(f3), M, N, O, _ptr(al), int(is_map), rho, tau0, sigma0, opnorm,
-            int(accel), maxiter, init_mode, nthreads, _ptr(u))
+    suf = "f64" if dtype == np.float64 else "f32"
+    if fused:
+        assert rho == 0.0
+        rc = getattr(lib(), "oracle_pdps_fused_" + suf)(_ptr(f3), M, N, O, _ptr(al), int(is_map), tau0, sigma0, opnorm,
+                                                        int(accel), maxiter, init_mode, nthreads, _ptr(u))
+    else:
+        rc = getattr(lib(), "oracle_pdps_" + suf)(_ptr(f3), M, N, O, _ptr(al), int(is_map), rho, tau0, sigma0, opnorm,
+                                                  int(accel), maxiter, init_mode, nthreads, _ptr(u))
     if rc != 0:
         raise RuntimeError(f"oracle_pdps failed: {rc}")
     return u

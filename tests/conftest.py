@@ -66,6 +66,15 @@ def bp():
     return b
 
 
+@pytest.fixture(autouse=True)
+def _fresh_env_switches():
+    """The library snapshots the BPLTV_* switches; tests that flip them call bp.reload_env() themselves, and the snapshot
+    is refreshed again after every test so that a restored environment is what the next test sees."""
+    yield
+    if "bpldenoising_b200" in sys.modules:
+        sys.modules["bpldenoising_b200"].reload_env()
+
+
 @pytest.fixture(scope="module")
 def ctx(bp):
     c = bp.Context([0], 64)

@@ -9,18 +9,11 @@
 
 using namespace bpltv;
 
-static int factor_threads(int nF)
-{
-    const int nt = (nF + 31) / 32, ntiles = nt * (nt + 1) / 2;
-    return 32 * std::min(16, std::max(2, ntiles));
-}
-static int solve_threads(int nF) { return std::min(512, std::max(64, (nF + 31) & ~31)); }
-
 // regularised != 0: NODE form (gradient_reg), else MULT form (gradient).  alpha_map: n·n doubles or NULL.
 // stats_out (8 doubles or NULL): relres, guarded pivots, vanished-pivot flag, L doubles, max U doubles, fronts, levels, unknowns
 extern "C" int emu_nd_gradient(int regularised, int n, const double *u, const double *ubar, const double *alpha_map,
                                double alpha_s, double gamma, double act_tol, double eps_act, int lm, int ln, int refine,
-                               int leaf, double *out, double *stats_out, double *p_out, double *ast_out, int *off_out)
+                               int leaf, double *out, double *stats_out, double *p_out, double *ast_out, int *off_out, int use_small)
 {
     const int N = n * n, ng = lm * ln;
     const bool node = regularised != 0;
@@ -70,22 +63,44 @@ extern "C" int emu_nd_gradient(int regularised, int n, const double *u, const do
     nd.L_stride = nd.U_stride = nd.UV_stride = 0;
 
     const double guard = node ? 0.0 : 1e-13;
+    std::vector<NdLevelPlan> plan(nsteps);
     for (int s = 0; s < nsteps; ++s) {
-        const int t0 = sym.step_start[s], cntf = sym.step_start[s + 1] - t0;
-        const int nFw = mb * sym.step_max_front_pix[s];
-        const size_t sm = nd_factor_smem(nFw, s > 0 ? mb * sym.step_max_ring_pix[s - 1] : 0);
-        emu::launch(dim3(cntf, 1), factor_threads(sym.step_max_front_pix[s]), [&] { nd_factor_kernel(nd, t0, s & 1, guard, nFw); }, sm / 8 + 2);
+        plan[s] = nd_level_plan(sym, s, mb, node ? 1.0 : 1.25);
+        if (!use_small && plan[s].small) {
+            plan[s].small = false;
+            plan[s].smem_f = nd_factor_smem(plan[s].nFw, s > 0 ? mb * sym.step_max_ring_pix[s - 1] : 0);
+            plan[s].smem_s = nd_solve_smem(plan[s].nFw);
+        }
+        if (use_small == 2 && plan[s].small) {      // test hook: a starved arena forces several rounds per CTA
+            plan[s].arena_f = nd_small_arena(plan[s].nFw, mb * sym.step_max_piv_pix[s], 1, true);
+            plan[s].arena_s = nd_small_arena(plan[s].nFw, mb * sym.step_max_piv_pix[s], 1, false);
+            plan[s].smem_f = nd_small_smem(plan[s].arena_f); plan[s].smem_s = nd_small_smem(plan[s].arena_s);
+        }
+    }
+    for (int s = 0; s < nsteps; ++s) {
+        const NdLevelPlan &lp = plan[s];
+        if (lp.small)
+            emu::launch(dim3((lp.nfr + ND_SMALL_WARPS - 1) / ND_SMALL_WARPS, 1), 32 * ND_SMALL_WARPS,
+                        [&] { nd_factor_small_kernel(nd, lp.t0, lp.nfr, s & 1, guard, lp.arena_f); }, lp.smem_f / 8 + 2);
+        else
+            emu::launch(dim3(lp.nfr, 1), lp.threads_f, [&] { nd_factor_kernel(nd, lp.t0, s & 1, guard, lp.nFw); }, lp.smem_f / 8 + 2);
     }
     auto solve = [&](double *v) {
         for (int s = 0; s < nsteps; ++s) {
-            const int t0 = sym.step_start[s], cntf = sym.step_start[s + 1] - t0;
-            emu::launch(dim3(cntf, 1), solve_threads(sym.step_max_front_pix[s]), [&] { nd_fwd_kernel(nd, t0, s & 1, v, 0); },
-                        nd_solve_smem(mb * sym.step_max_front_pix[s]) / 8 + 2);
+            const NdLevelPlan &lp = plan[s];
+            if (lp.small)
+                emu::launch(dim3((lp.nfr + ND_SMALL_WARPS - 1) / ND_SMALL_WARPS, 1), 32 * ND_SMALL_WARPS,
+                            [&] { nd_fwd_small_kernel(nd, lp.t0, lp.nfr, s & 1, v, 0, lp.arena_s); }, lp.smem_s / 8 + 2);
+            else
+                emu::launch(dim3(lp.nfr, 1), lp.threads_s, [&] { nd_fwd_kernel(nd, lp.t0, s & 1, v, 0); }, lp.smem_s / 8 + 2);
         }
         for (int s = nsteps - 1; s >= 0; --s) {
-            const int t0 = sym.step_start[s], cntf = sym.step_start[s + 1] - t0;
-            emu::launch(dim3(cntf, 1), solve_threads(sym.step_max_front_pix[s]), [&] { nd_bwd_kernel(nd, t0, v, 0); },
-                        nd_solve_smem(mb * sym.step_max_front_pix[s]) / 8 + 2);
+            const NdLevelPlan &lp = plan[s];
+            if (lp.small)
+                emu::launch(dim3((lp.nfr + ND_SMALL_WARPS - 1) / ND_SMALL_WARPS, 1), 32 * ND_SMALL_WARPS,
+                            [&] { nd_bwd_small_kernel(nd, lp.t0, lp.nfr, v, 0, lp.arena_s); }, lp.smem_s / 8 + 2);
+            else
+                emu::launch(dim3(lp.nfr, 1), lp.threads_s, [&] { nd_bwd_kernel(nd, lp.t0, v, 0); }, lp.smem_s / 8 + 2);
         }
     };
     double relres = -1.0;

@@ -55,7 +55,7 @@ def _case(n, seed, flat=True):
     return np.asfortranarray(t), np.asfortranarray(u)
 
 
-def _run(lib, reg, u, t, alpha, grid=(1, 1), refine=None, leaf=4, gamma=1e8, eps_act=None, ast_out=None, off_out=None):
+def _run(lib, reg, u, t, alpha, grid=(1, 1), refine=None, leaf=4, gamma=1e8, eps_act=None, ast_out=None, off_out=None, small=1):
     n = u.shape[0]
     amap = None
     a_s = 0.0
@@ -73,7 +73,7 @@ def _run(lib, reg, u, t, alpha, grid=(1, 1), refine=None, leaf=4, gamma=1e8, eps
     rc = lib.emu_nd_gradient(int(reg), n, _ptr(u.flatten(order="F")), _ptr(t.flatten(order="F")), _ptr(amap),
                              C.c_double(a_s), C.c_double(gamma), C.c_double(1e-12), C.c_double(eps_act),
                              grid[0], grid[1], refine, leaf, _ptr(out), _ptr(stats), _ptr(p), _ptr(ast_out),
-                             None if off_out is None else off_out.ctypes.data_as(C.POINTER(C.c_int)))
+                             None if off_out is None else off_out.ctypes.data_as(C.POINTER(C.c_int)), int(small))
     assert rc == 0
     return out.reshape(grid, order="F"), stats, p
 
@@ -172,3 +172,16 @@ def test_against_binary128(lib):
     g, _, p = _run(lib, True, u, t, 0.07)
     q, pq = quad.gradient_reg(0.07, u, t, return_p=True)
     assert abs(g[0, 0] - q) <= 1e-12 * abs(q) and np.linalg.norm(p - pq) <= 1e-12 * np.linalg.norm(pq)
+
+
+@pytest.mark.parametrize("reg", [False, True])
+def test_small_front_kernels_equal_the_generic_ones(lib, reg):
+    """the warp-per-front kernels of the bottom levels against the CTA-per-front kernels (same operations in another order:
+    1e-12), with a comfortable arena and with one so small that every CTA needs several rounds"""
+    t, u = _case(40, 21)
+    g0, s0, p0 = _run(lib, reg, u, t, 0.07, small=0)
+    for small in (1, 2):
+        g1, s1, p1 = _run(lib, reg, u, t, 0.07, small=small)
+        assert abs(g1[0, 0] - g0[0, 0]) <= 1e-12 * abs(g0[0, 0]), (small, g0, g1)
+        assert np.linalg.norm(p1 - p0) <= 1e-11 * np.linalg.norm(p0)
+        assert s1[2] == 0

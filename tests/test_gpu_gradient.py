@@ -72,6 +72,7 @@ def test_gradient_reg_by_both_solvers(bp, ctx, oracle, datasets, monkeypatch):
     got = {}
     for mode in ("0", "1"):
         monkeypatch.setenv("BPLTV_GRAD_REG_LU", mode)
+        bp.reload_env()
         gs = ctx.gradient(0.06, us, regularised=True)
         gp = ctx.gradient(x, up, regularised=True)
         assert _rel(gs, dual_s) <= 1e-10 and _rel(gp, dual_p) <= 1e-10, mode
@@ -84,10 +85,12 @@ def test_gradient_reg_by_both_solvers(bp, ctx, oracle, datasets, monkeypatch):
     u = oracle.pdps(f, 0.08, maxiter=800)
     ctx.set_dataset((t, f))
     monkeypatch.setenv("BPLTV_GRAD_REG_LU", "1")
+    bp.reload_env()
     g = ctx.gradient(0.08, u, regularised=True)
     dual = sum(oracle.gradient_dual("reg", 0.08, u[:, :, i], t[:, :, i]) for i in range(2))
     assert _rel(g, dual) <= 1e-10
     monkeypatch.setenv("BPLTV_GRAD_REG_LU", "0")
+    bp.reload_env()
     assert _rel(ctx.gradient(0.08, u, regularised=True), dual) <= 1e-10           # the Cholesky at the odd size
     dual_n = sum(oracle.gradient_dual("nonreg", 0.08, u[:, :, i], t[:, :, i]) for i in range(2))
     assert _rel(ctx.gradient(0.08, u, regularised=False), dual_n) <= 1e-10        # and the non-regularised branch

@@ -47,10 +47,12 @@ def test_ragged_shapes_all_kernels(bp, ctx, oracle, shape):
         if M % vec:
             continue
         os.environ["BPLTV_MARCH_VEC"] = str(vec)
+        bp.reload_env()
         try:
             u = ctx.denoise(f, 0.08, _opts(bp, maxiter=60, kernel=bp.KERNEL_MARCH))
         finally:
             del os.environ["BPLTV_MARCH_VEC"]
+            bp.reload_env()
         assert np.array_equal(u, ref), (shape, "march vec", vec)
 
 
@@ -91,10 +93,12 @@ def test_march_chunking_is_invisible(bp, ctx, oracle, datasets):
     ref = oracle.pdps(f, 0.1, maxiter=40)
     for chunk in (1, 3, 8, 127, 128):
         os.environ["BPLTV_MARCH_CHUNK"] = str(chunk)
+        bp.reload_env()
         try:
             u = ctx.denoise(f, 0.1, _opts(bp, maxiter=40, kernel=bp.KERNEL_MARCH))
         finally:
             del os.environ["BPLTV_MARCH_CHUNK"]
+            bp.reload_env()
         assert np.array_equal(u, ref), chunk
 
 
@@ -229,10 +233,12 @@ def test_tblock_range_ends_are_invisible(bp, ctx, oracle, datasets, depth):
     ref = oracle.pdps(f, 0.1, maxiter=12 + depth - 1)
     for chunk in (1, 2, 3, 4, 5, 9, 36, 37, 38, 50, 111):
         os.environ["BPLTV_MARCH_CHUNK"] = str(chunk)
+        bp.reload_env()
         try:
             u = ctx.denoise(f, 0.1, _opts(bp, maxiter=12 + depth - 1, kernel=bp.KERNEL_TBLOCK, tblock=depth))
         finally:
             del os.environ["BPLTV_MARCH_CHUNK"]
+            bp.reload_env()
         assert np.array_equal(u, ref), (depth, chunk, np.abs(u - ref).max())
 
 
@@ -250,6 +256,7 @@ def test_tblock_ragged_shapes_and_precisions(bp, ctx, ctx32, oracle, shape):
             if M % vec:
                 continue
             os.environ["BPLTV_MARCH_VEC"] = str(vec)
+            bp.reload_env()
             try:
                 if vec <= 2 and M // vec <= 256:
                     u = ctx.denoise(f, 0.08, _opts(bp, maxiter=30, kernel=bp.KERNEL_TBLOCK, tblock=depth))
@@ -259,6 +266,7 @@ def test_tblock_ragged_shapes_and_precisions(bp, ctx, ctx32, oracle, shape):
                     assert np.array_equal(u32.astype(np.float32), ref32), (shape, depth, vec, "fp32")
             finally:
                 del os.environ["BPLTV_MARCH_VEC"]
+                bp.reload_env()
 
 
 def test_tblock_fast_mode_and_switches(bp, ctx, oracle, datasets):

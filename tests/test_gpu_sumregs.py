@@ -54,6 +54,7 @@ def test_sumregs_resident_and_streaming_kernels_agree(bp, ctx, ctx32, sr, monkey
     assert np.array_equal(stream, ref) and ctx.stats()["kernel_launches"] == 2 * 50
     for cs in (1, 2, 4, 8, 16):
         monkeypatch.setenv("BPLTV_RESIDENT_CS", str(cs))
+        bp.reload_env()
         u = ctx.sumregs_denoise(f, x, bp.sumregs_pdps_opts(maxiter=50, kernel=bp.KERNEL_RESIDENT))
         assert np.array_equal(u, ref) and ctx.stats()["kernel_launches"] == 1, cs
         up = ctx.sumregs_denoise(f, xp, bp.sumregs_pdps_opts(maxiter=50, kernel=bp.KERNEL_RESIDENT))
@@ -251,11 +252,13 @@ def test_cluster_factorisation_is_invisible(bp, ctx, sr, datasets):
     ref = {}
     for C in ("1", "2", "4", "8", "16"):
         os.environ["BPLTV_GRAD_CLUSTER"] = C
+        bp.reload_env()
         try:
             got = (ctx.gradient(0.07, utv, False), ctx.gradient(0.07, utv, True),
                    ctx.sumregs_gradient(x3, u3, False), ctx.sumregs_gradient(x3, u3, True))
         finally:
             del os.environ["BPLTV_GRAD_CLUSTER"]
+            bp.reload_env()
         if C == "1":
             ref = got
         else:

@@ -186,3 +186,15 @@ def test_oracle_pins(oracle, datasets):
     assert abs(g - float(pins["grad_reg"])) <= 1e-9 * abs(float(pins["grad_reg"]))
     g = oracle.gradient_scalar(0.1, u[:, :, 0], t[:, :, 0])
     assert abs(g - float(pins["grad"])) <= 1e-4 * abs(float(pins["grad"]))  # LU-order noise, SURVEY §7.3-2
+
+
+def test_fused_cpu_variant_is_bit_identical(oracle):
+    """bench.py's stronger CPU baseline (one sweep per iteration instead of the reference's separate passes) performs the
+    same IEEE operations per pixel: identical bits, fp64 and fp32, scalar λ and λ-map, ragged shapes."""
+    rng = np.random.default_rng(5)
+    for shape in ((40, 33, 3), (1, 17, 1), (19, 1, 2), (64, 64, 2)):
+        f = np.asfortranarray(np.round(rng.random(shape) * 255) / 255)
+        am = 0.03 + 0.1 * rng.random(shape[:2])
+        for dt in (np.float64, np.float32):
+            assert np.array_equal(oracle.pdps(f, 0.08, maxiter=70, dtype=dt), oracle.pdps(f, 0.08, maxiter=70, dtype=dt, fused=True))
+            assert np.array_equal(oracle.pdps(f, am, maxiter=50, dtype=dt), oracle.pdps(f, am, maxiter=50, dtype=dt, fused=True))
