@@ -57,6 +57,49 @@ static int run(int M, int N, int O, int CS, int threads, int maxiter, int strict
     return 0;
 }
 
+// the temporally blocked variant (pdps_resident_tb_kernel): threads = tpc · ceil((NC+4)/KC) rounded up to a warp
+template <typename Real>
+static int run_tb(int M, int N, int O, int CS, int KC, int maxiter, int strict, const double *f_in, double alpha_s,
+                  const double *amap_in, double *u_out)
+{
+    if (M < 2 || (M & 1)) return -1;
+    const int NC = (N + CS - 1) / CS, E = NC + 4, tpc = M / 2;
+    if (NC < 2 || (CS - 1) * NC >= N) return -2;
+    const int threads = (tpc * ((E + KC - 1) / KC) + 31) & ~31;
+    const size_t n = (size_t)M * N * O, plane = (size_t)M * N;
+    std::vector<Real> f(n), u(n, (Real)0), amap;
+    for (size_t k = 0; k < n; ++k) f[k] = (Real)f_in[k];
+    if (amap_in) { amap.resize(plane); for (size_t k = 0; k < plane; ++k) amap[k] = (Real)amap_in[k]; }
+    const auto st = steps<Real>(maxiter, 5.0, 0.99 / 5, std::sqrt(8.0));
+    ResidentArgs<Real> a;
+    a.f = f.data(); a.u_out = u.data(); a.alpha_map = amap_in ? amap.data() : nullptr; a.steps = st.data();
+    a.maxiter = maxiter; a.M = M; a.N = N; a.O = O; a.init_mode = 0; a.NC = NC; a.alpha_s = (Real)alpha_s;
+    a.bm = BatchMap<Real>();
+    const size_t smem_doubles = ((size_t)(3 * E + 4) * M * sizeof(Real) + 7) / 8;
+    auto body = [&] {
+        if (KC == 1) {
+            if (amap_in) { if (strict) pdps_resident_tb_kernel<Real, 1, true, true>(a); else pdps_resident_tb_kernel<Real, 1, true, false>(a); }
+            else { if (strict) pdps_resident_tb_kernel<Real, 1, false, true>(a); else pdps_resident_tb_kernel<Real, 1, false, false>(a); }
+        } else if (KC == 2) {
+            if (amap_in) { if (strict) pdps_resident_tb_kernel<Real, 2, true, true>(a); else pdps_resident_tb_kernel<Real, 2, true, false>(a); }
+            else { if (strict) pdps_resident_tb_kernel<Real, 2, false, true>(a); else pdps_resident_tb_kernel<Real, 2, false, false>(a); }
+        } else {
+            if (amap_in) { if (strict) pdps_resident_tb_kernel<Real, 4, true, true>(a); else pdps_resident_tb_kernel<Real, 4, true, false>(a); }
+            else { if (strict) pdps_resident_tb_kernel<Real, 4, false, true>(a); else pdps_resident_tb_kernel<Real, 4, false, false>(a); }
+        }
+    };
+    emu::launch(dim3((unsigned)(O * CS)), threads, body, smem_doubles, CS);
+    for (size_t k = 0; k < n; ++k) u_out[k] = (double)u[k];
+    return 0;
+}
+
+extern "C" int emu_pdps_resident_tb(int prec, int M, int N, int O, int CS, int KC, int maxiter, int strict,
+                                    const double *f, double alpha_s, const double *amap, double *u_out)
+{
+    return prec == 32 ? run_tb<float>(M, N, O, CS, KC, maxiter, strict, f, alpha_s, amap, u_out)
+                      : run_tb<double>(M, N, O, CS, KC, maxiter, strict, f, alpha_s, amap, u_out);
+}
+
 extern "C" int emu_pdps_resident(int prec, int M, int N, int O, int CS, int threads, int maxiter, int strict,
                                  const double *f, double alpha_s, const double *amap, double *u_out)
 {

@@ -311,3 +311,27 @@ def test_config4_full_size_is_bit_identical_to_the_oracle_pins(bp, ctx, ctx32):
         assert got == pins[key]["u_sha256"], key
         # an fp32 context also holds ū in fp32 (k/255 rounded), so its loss differs from the fp64 one in the 8th digit
         assert abs(cost - pins[key]["cost"]) <= (1e-12 if key == "f64" else 1e-6) * cost, (key, cost)
+
+
+def test_temporally_blocked_resident_kernel_is_bit_identical(bp, ctx, ctx32, oracle, datasets):
+    """pdps_resident_tb_kernel (two iterations per halo exchange; default for fp32, BPLTV_RESIDENT_TB=1 forces it): the
+    same bits as the oracle in fp64 and fp32, odd and even iteration counts, scalar λ and λ-map, 1 and 10 images."""
+    import os
+    t, f = datasets["faces_train_128_10"]
+    x = np.array([[0.05, 0.1], [0.08, 0.02]])
+    am = oracle.patch_upsample(x, 128, 128)
+    os.environ["BPLTV_RESIDENT_TB"] = "1"
+    bp.reload_env()
+    try:
+        for O in (1, 10):
+            fo = np.asfortranarray(f[:, :, :O])
+            for its in (301, 600):
+                o = bp.pdps_opts(maxiter=its, kernel=bp.KERNEL_RESIDENT)
+                assert np.array_equal(ctx.denoise(fo, 0.08, o), oracle.pdps(fo, 0.08, maxiter=its)), (O, its)
+                u32 = ctx32.denoise(fo, 0.08, o)
+                assert np.array_equal(u32.astype(np.float32), oracle.pdps(fo, 0.08, maxiter=its, dtype=np.float32)), (O, its)
+            o = bp.pdps_opts(maxiter=400, kernel=bp.KERNEL_RESIDENT)
+            assert np.array_equal(ctx.denoise(fo, x, o), oracle.pdps(fo, am, maxiter=400)), O
+    finally:
+        del os.environ["BPLTV_RESIDENT_TB"]
+        bp.reload_env()
