@@ -44,7 +44,7 @@ EXPORTS = [
     "bpltv_set_dataset", "bpltv_denoise", "bpltv_learn_eval", "bpltv_gradient", "bpltv_sweep", "bpltv_default_sumregs_eval_opts",
     "bpltv_sumregs_denoise", "bpltv_sumregs_learn_eval", "bpltv_sumregs_gradient",
     "bpltv_denoise_device", "bpltv_set_dataset_device", "bpltv_learn_eval_device",
-    "bpltv_get_stats", "bpltv_last_error", "bpltv_version", "bpltv_reload_env",
+    "bpltv_get_stats", "bpltv_last_error", "bpltv_version", "bpltv_reload_env", "bpltv_selftest",
 ]
 
 _lib = None
@@ -91,6 +91,7 @@ def load() -> C.CDLL:
     L.bpltv_learn_eval_device.argtypes = [vp, dp, C.c_int, C.c_int, C.c_double,
                                           C.POINTER(EvalOpts), vp, vp, vp]
     L.bpltv_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.bpltv_selftest.argtypes = [vp, C.c_int, C.c_int, C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_ulonglong)]
     L.bpltv_last_error.restype = C.c_char_p
     L.bpltv_version.restype = C.c_int
     L.bpltv_reload_env.restype = None

@@ -29,6 +29,7 @@
 #include "gradient_sumregs.cuh"
 #include "gradient_lu.cuh"
 #include "gradient_nd.h"
+#include "selftest.cuh"
 
 // the option structs are mirrored field by field in bpldenoising_b200/_lib.py (ctypes) and julia/BPLTV.jl
 static_assert(sizeof(bpltv_pdps_opts) == 72, "bpltv_pdps_opts layout");
@@ -1503,6 +1504,29 @@ int bpltv_get_stats(bpltv_ctx *ctx, bpltv_stats *out)
 {
     if (!ctx || !out) return fail(BPLTV_ERR_ARG, "NULL argument");
     *out = ctx->stats;
+    return 0;
+}
+
+int bpltv_selftest(bpltv_ctx *ctx, int what, int mode, unsigned long long count, unsigned long long seed,
+                   unsigned long long *result)
+{
+    if (!ctx || !result) return fail(BPLTV_ERR_ARG, "NULL argument");
+    if (what != 0 || mode < 0 || mode > 3) return fail(BPLTV_ERR_ARG, "selftest: unknown test %d / mode %d", what, mode);
+    Dev &d = ctx->devs[0];
+    CU_TRY(cudaSetDevice(d.id));
+    unsigned long long *dres = nullptr;
+    CU_TRY(cudaMalloc(&dres, 4 * sizeof(unsigned long long)));
+    cudaError_t e = cudaMemsetAsync(dres, 0, 4 * sizeof(unsigned long long), d.stream);
+    if (e == cudaSuccess) {
+        const unsigned grid = (unsigned)(d.sm_count * 8);
+        if (ctx->prec == 64) selftest_ball_scale_kernel<double><<<grid, 256, 0, d.stream>>>(mode, count, seed, dres);
+        else selftest_ball_scale_kernel<float><<<grid, 256, 0, d.stream>>>(mode, count, seed, dres);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(result, dres, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+    cudaFree(dres);
+    if (e != cudaSuccess) return fail(BPLTV_ERR_CUDA, "selftest: %s", cudaGetErrorString(e));
     return 0;
 }
 

@@ -269,20 +269,45 @@ static __device__ __forceinline__ void tblock_step(const int c, const TBStage<Re
     // that left the ball are scaled in one block so that their √ and ÷ chains overlap (a
     // thread none of whose pixels left the ball skips it entirely)
     if (outside) {
+        if (STRICT) {
+            // α / sqrt(n²) with both operations correctly rounded, as branch-free chains (BallScale, common.cuh): the
+            // T·VEC chains of the thread interleave; a pixel outside the chain's operand range (never on image data)
+            // sends the thread's pixels through the IEEE operations instead
+            Real sc[T][VEC];
+            bool out[T][VEC], ok = true;
 #pragma unroll
-        for (int s = 0; s < T; ++s)
+            for (int s = 0; s < T; ++s)
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                if (STRICT) {
-                    const bool out = n2[s][v] > A::mul(al[s][v], al[s][v]);
-                    const Real sc = A::div(al[s][v], A::sqrt(out ? n2[s][v] : (Real)1));
-                    if (out) { v1[s][v] = A::mul(v1[s][v], sc); v2[s][v] = A::mul(v2[s][v], sc); }
-                } else {
+                for (int v = 0; v < VEC; ++v) {
+                    out[s][v] = n2[s][v] > A::mul(al[s][v], al[s][v]);
+                    if (!out[s][v]) n2[s][v] = (Real)1;
+                    ok &= BallScale<Real>::fast_ok(n2[s][v], al[s][v]);
+                }
+#pragma unroll
+            for (int s = 0; s < T; ++s)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) sc[s][v] = BallScale<Real>::eval(n2[s][v], al[s][v]);
+            if (!ok) {
+#pragma unroll
+                for (int s = 0; s < T; ++s)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) sc[s][v] = ball_scale_ieee<Real>(n2[s][v], al[s][v]);
+            }
+#pragma unroll
+            for (int s = 0; s < T; ++s)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+                    if (out[s][v]) { v1[s][v] = A::mul(v1[s][v], sc[s][v]); v2[s][v] = A::mul(v2[s][v], sc[s][v]); }
+        } else {
+#pragma unroll
+            for (int s = 0; s < T; ++s)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
                     const bool out = n2[s][v] > al[s][v] * al[s][v];
                     const Real sc = al[s][v] * rsqrt_(out ? n2[s][v] : (Real)1);
                     if (out) { v1[s][v] *= sc; v2[s][v] *= sc; }
                 }
-            }
+        }
     }
 #pragma unroll
     for (int s = 0; s < T; ++s) {

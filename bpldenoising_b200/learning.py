@@ -276,6 +276,14 @@ class Context:
         check(self._L.bpltv_get_stats(self._h, C.byref(s)))
         return s.asdict()
 
+    def selftest(self, mode: int, count: int, seed: int = 1, what: int = 0) -> dict:
+        """Arithmetic self-test (include/bpltv.h, bpltv_selftest): the strict kernels' projection scale against the IEEE
+        operations on `count` generated operand pairs of the context's precision."""
+        res = (C.c_ulonglong * 4)()
+        check(self._L.bpltv_selftest(self._h, what, mode, count, seed, res))
+        return {"took": int(res[0]), "mismatches": int(res[1]), "first_a_bits": int(res[2]) & ((1 << 63) - 1),
+                "first_alpha_bits": int(res[3])}
+
     # ---- device-pointer entry points (torch tensors; plumbing only) --------------
     def denoise_device(self, d_noisy_ptr: int, M: int, N: int, O: int, x, d_out_ptr: int,
                        opts: Optional[PdpsOpts] = None, stream: int = 0):

@@ -221,6 +221,16 @@ int bpltv_get_stats(bpltv_ctx *ctx, bpltv_stats *out);
 /* The developer switches (environment variables BPLTV_*) are read once, when the first context is
  * created; this re-reads them (the test-suite flips them between calls).  Not needed by a normal caller. */
 void bpltv_reload_env(void);
+/* Arithmetic self-test (test-suite entry point, not needed by a caller).  what = 0: the strict kernels form the
+ * projection scale `α / sqrt(n²)` of the reference's PDPS step by a branch-free chain instead of the compiler's IEEE
+ * sqrt / div expansions (csrc/common.cuh, BallScale); this runs `count` operand pairs of the context's precision
+ * through both.  mode 0: the operand range of image data, 1: the chain's whole range, 2: structured significands
+ * (rounding boundaries, perfect squares ± 1 ulp), 3: every `a` bit pattern in turn (exhaustive for a 32-bit context
+ * from count = 2^30).  result[0] = pairs the chain took (the others go through the IEEE operations in the kernels as
+ * well), result[1] = pairs whose bits differ (must be 0), result[2], result[3] = bit patterns of the first such
+ * (a | 2^63, α). */
+int bpltv_selftest(bpltv_ctx *ctx, int what, int mode, unsigned long long count, unsigned long long seed,
+                   unsigned long long *result);
 const char *bpltv_last_error(void);
 int bpltv_version(void);
 

@@ -33,6 +33,14 @@ end
 lasterr() = unsafe_string(ccall((:bpltv_last_error, lib), Cstring, ()))
 # the BPLTV_* developer switches are snapshotted when the first context is created; re-read them after changing ENV
 reload_env() = ccall((:bpltv_reload_env, lib), Cvoid, ())
+# arithmetic self-test of the strict kernels' projection scale (include/bpltv.h): (pairs taken, mismatches, a bits, α bits)
+function selftest(ctx::Ptr{Cvoid}, mode::Integer, count::Integer; seed::Integer = 1)
+    res = zeros(Culonglong, 4)
+    rc = ccall((:bpltv_selftest, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Culonglong, Culonglong, Ptr{Culonglong}),
+               ctx, 0, mode, count, seed, res)
+    rc == 0 || error(unsafe_string(ccall((:bpltv_last_error, lib), Cstring, ())))
+    return res
+end
 check(rc) = rc == 0 ? nothing : (rc == -1 ? throw(ArgumentError(lasterr())) : error("libbpltv ($rc): " * lasterr()))
 
 function default_pdps()

@@ -57,6 +57,42 @@ int oracle_max_threads(void)
 #endif
 }
 
+/* In-place lower banded Cholesky with a pivot floor — the factorisation of oracle.gradient_dual (the CPU checker of the
+ * multiplier-space adjoint systems, /root/reference/src/TVLearningFunctionVec.jl:98-161 after eliminating p).
+ * ab is LAPACK's lower band storage as numpy holds it, row-major (bw+1) × Nd: ab[r*Nd + j] = A[j+r, j].  The same
+ * right-looking column sweep, operation for operation, as the numpy loop it replaces (oracle.py: _chol_band_guard_py),
+ * on a column-contiguous copy; the columns a pivot column updates are independent and shared among the threads.
+ * Returns the number of pivots raised to `guard`. */
+long long oracle_chol_band_guard(double *ab, int bw, long long Nd, double guard)
+{
+    const long long ld = (long long)bw + 1;
+    double *c = (double *)malloc((size_t)(ld * Nd) * sizeof(double));
+    if (!c) return -1;
+    for (long long j = 0; j < Nd; ++j)
+        for (long long r = 0; r < ld; ++r) c[j * ld + r] = ab[r * Nd + j];
+    long long guarded = 0;
+    for (long long j = 0; j < Nd; ++j) {
+        double *l = c + j * ld;
+        double d = l[0];
+        if (!(d > guard)) { d = guard; ++guarded; }
+        d = sqrt(d);
+        l[0] = d;
+        const long long m = (long long)bw < Nd - 1 - j ? (long long)bw : Nd - 1 - j;
+        for (long long r = 1; r <= m; ++r) l[r] = l[r] / d;
+#pragma omp parallel for schedule(static) if (m >= 96)
+        for (long long b = 1; b <= m; ++b) {
+            const double lb = l[b];
+            if (lb == 0.0) continue;
+            double *t = c + (j + b) * ld;
+            for (long long r = 0; r <= m - b; ++r) t[r] -= l[b + r] * lb;
+        }
+    }
+    for (long long j = 0; j < Nd; ++j)
+        for (long long r = 0; r < ld; ++r) ab[r * Nd + j] = c[j * ld + r];
+    free(c);
+    return guarded;
+}
+
 #define REAL double
 #define SUF f64
 #define SQRT sqrt

@@ -133,6 +133,28 @@ inline float __fsub_rn(float a, float b) { return a - b; }
 inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __fdiv_rn(float a, float b) { return a / b; }
 inline float __fsqrt_rn(float a) { return std::sqrt(a); }
+inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
+inline float __fmaf_rn(float a, float b, float c) { return std::fma(a, b, c); }
+inline int __double2hiint(double a) { unsigned long long u; std::memcpy(&u, &a, 8); return (int)(u >> 32); }
+inline int __double2loint(double a) { unsigned long long u; std::memcpy(&u, &a, 8); return (int)(u & 0xffffffffu); }
+inline unsigned __float_as_uint(float a) { unsigned u; std::memcpy(&u, &a, 4); return u; }
+// stand-ins for the hardware's reciprocal-square-root seeds, so the emulated kernels run BallScale's chain for real.
+// fp64 (MUFU.RSQ64H writes the upper word only): the exact value cut down to its upper word, 20 significand bits —
+// the chain's own Newton step absorbs any seed of that accuracy.  fp32 (MUFU.RSQ, ≈ 1 ulp): the correctly rounded
+// value — the √ part of the fp32 chain is the vendor's fast path, which relies on the accuracy of its own seed (with 1-2
+// bits cut off it misrounds a few √ in 10⁸), so its seed cannot be modelled pessimistically; the fp32 chain with the
+// real seed is checked on the GPU over every operand `a` (tests/test_gpu_pdps.py).
+inline double emu_rsqrt_seed(double a)
+{
+    double y = 1.0 / std::sqrt(a);
+    unsigned long long u; std::memcpy(&u, &y, 8); u &= 0xffffffff00000000ull; std::memcpy(&y, &u, 8);
+    return y;
+}
+inline float emu_rsqrt_seed(float a)
+{
+    float y = (float)(1.0 / std::sqrt((double)a));
+    return y;
+}
 inline double rsqrt(double a) { return 1.0 / std::sqrt(a); }
 inline float rsqrtf(float a) { return 1.0f / std::sqrt(a); }
 template <typename T> inline T __ldg(const T *p) { return *p; }

@@ -335,3 +335,23 @@ def test_temporally_blocked_resident_kernel_is_bit_identical(bp, ctx, ctx32, ora
     finally:
         del os.environ["BPLTV_RESIDENT_TB"]
         bp.reload_env()
+
+
+@pytest.mark.parametrize("prec", [64, 32])
+def test_projection_scale_chain_equals_the_ieee_operations(bp, ctx, ctx32, prec):
+    """The strict kernels form the projection scale `α / sqrt(n²)` (two correctly rounded operations in the reference) by
+    BallScale's branch-free chain (csrc/common.cuh).  bpltv_selftest runs generated operand pairs through the chain and
+    through __ddiv_rn(α, __dsqrt_rn(a)) / __fdiv_rn(α, __fsqrt_rn(a)) on the device: not one pair may differ.  Modes: image
+    range, the chain's whole operand range, structured significands (rounding boundaries, perfect squares ± 1 ulp) and —
+    exhaustive in fp32 — every `a` bit pattern of the range."""
+    c = ctx if prec == 64 else ctx32
+    for mode, count in ((0, 1 << 32), (1, 1 << 32), (2, 1 << 32), (3, 1 << 32)):
+        r = c.selftest(mode, count, seed=2024 + mode)
+        assert r["took"] > 0.7 * count, (mode, r)
+        assert r["mismatches"] == 0, (prec, mode, r, hex(r["first_a_bits"]), hex(r["first_alpha_bits"]))
+    if prec == 32:
+        # every float a of the chain's range (119 binades × 2²³ significands), a fresh α for each, three times over
+        span = 119 << 23
+        for seed in (1, 2, 3):
+            r = c.selftest(3, span, seed=seed)
+            assert r["took"] >= span - 119 and r["mismatches"] == 0, (seed, r)

@@ -198,3 +198,29 @@ def test_fused_cpu_variant_is_bit_identical(oracle):
         for dt in (np.float64, np.float32):
             assert np.array_equal(oracle.pdps(f, 0.08, maxiter=70, dtype=dt), oracle.pdps(f, 0.08, maxiter=70, dtype=dt, fused=True))
             assert np.array_equal(oracle.pdps(f, am, maxiter=50, dtype=dt), oracle.pdps(f, am, maxiter=50, dtype=dt, fused=True))
+
+
+def test_band_cholesky_c_loop_equals_the_numpy_loop(oracle):
+    """oracle.gradient_dual factorises with liboracle's C loop (oracle_chol_band_guard); the numpy loop it replaced is
+    kept as its cross-check: identical bits, pivot floor included."""
+    rng = np.random.default_rng(3)
+    Nd, bw = 1500, 70
+    B = np.zeros((Nd, Nd))
+    for r in range(1, bw + 1):
+        if 5 <= r < 20:
+            continue                                     # structural zeros inside the band
+        v = rng.uniform(-1, 1, Nd - r)
+        B += np.diag(v, -r)
+    B[100, :] = 0.0
+    D = rng.uniform(0.5, 1.5, Nd)
+    D[100] = 1e-20                                       # a vanished pivot (an uncoupled unknown): the floor has to act
+    A = B @ B.T + np.diag(D)                             # SPD, half-bandwidth 2·bw
+    w = 2 * bw
+    ab = np.zeros((w + 1, Nd))
+    for r in range(w + 1):
+        ab[r, :Nd - r] = np.diag(A, -r)
+    a1, a2 = ab.copy(), ab.copy()
+    g1 = oracle._chol_band_guard(a1, 1e-3)
+    g2 = oracle._chol_band_guard_py(a2, 1e-3)
+    assert g1 == g2 >= 1
+    assert np.all(np.isfinite(a1)) and np.array_equal(a1, a2)
