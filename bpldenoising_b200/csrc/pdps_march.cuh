@@ -139,14 +139,18 @@ __global__ void __launch_bounds__(MAXT, MINB) pdps_march_kernel(const MarchArgs<
             }
             // ---- dual update of column c-1 (Δy2 = x̄(:,c) - x̄(:,c-1)) --------------
             if (c > c0) {
-                Real o1[VEC], o2[VEC];
+                Real o1[VEC], o2[VEC], d2[VEC], alv[VEC];
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) {
-                    const Real d2 = STRICT ? StrictOps<Real>::sub(xb_c[v], xb_p[v]) : xb_c[v] - xb_p[v];
+                    d2[v] = STRICT ? StrictOps<Real>::sub(xb_c[v], xb_p[v]) : xb_c[v] - xb_p[v];
                     o1[v] = y1_p[v]; o2[v] = y2_p[v];
-                    const Real al = MAP ? al_p[v] : alpha_s;
-                    if (has_rho) dual_update_rho<Real, STRICT>(o1[v], o2[v], d1_p[v], d2, al, a.rho, sc);
-                    else dual_update<Real, STRICT, false>(o1[v], o2[v], d1_p[v], d2, al, a.rho, sc);
+                    alv[v] = MAP ? al_p[v] : alpha_s;
+                }
+                if (has_rho) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) dual_update_rho<Real, STRICT>(o1[v], o2[v], d1_p[v], d2[v], alv[v], a.rho, sc);
+                } else {
+                    dual_update_n<Real, STRICT, VEC>(o1, o2, d1_p, d2, alv, sc);   // the rows' projection chains interleave
                 }
                 if (rows_ok) {
                     IO::st(y1out + (size_t)(c - 1) * M + r0, o1);
@@ -163,13 +167,17 @@ __global__ void __launch_bounds__(MAXT, MINB) pdps_march_kernel(const MarchArgs<
 
         // last image column: Δy2 = 0 there, nobody looks ahead
         if (c1 == N) {
-            Real o1[VEC], o2[VEC];
+            Real o1[VEC], o2[VEC], d2[VEC], alv[VEC];
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                o1[v] = y1_p[v]; o2[v] = y2_p[v];
-                const Real al = MAP ? al_p[v] : alpha_s;
-                if (has_rho) dual_update_rho<Real, STRICT>(o1[v], o2[v], d1_p[v], (Real)0, al, a.rho, sc);
-                else dual_update<Real, STRICT, false>(o1[v], o2[v], d1_p[v], (Real)0, al, a.rho, sc);
+                o1[v] = y1_p[v]; o2[v] = y2_p[v]; d2[v] = (Real)0;
+                alv[v] = MAP ? al_p[v] : alpha_s;
+            }
+            if (has_rho) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) dual_update_rho<Real, STRICT>(o1[v], o2[v], d1_p[v], (Real)0, alv[v], a.rho, sc);
+            } else {
+                dual_update_n<Real, STRICT, VEC>(o1, o2, d1_p, d2, alv, sc);
             }
             if (rows_ok) {
                 IO::st(y1out + (size_t)(N - 1) * M + r0, o1);

@@ -178,9 +178,13 @@ __global__ void __launch_bounds__(RES_THREADS, 1) pdps_resident_kernel(const Res
                 if (STRICT) { d2_0 = StrictOps<Real>::sub(rt0, xb[k][0]); d2_1 = StrictOps<Real>::sub(rt1, xb[k][1]); }
                 else { d2_0 = rt0 - xb[k][0]; d2_1 = rt1 - xb[k][1]; }
             }
-            Real v1 = y1o[k][0], v2 = y2o[k][0], w1 = y1o[k][1], w2 = y2o[k][1];
-            dual_update<Real, STRICT, false>(v1, v2, d1_0, d2_0, al[k][0], (Real)0, sc);
-            dual_update<Real, STRICT, false>(w1, w2, d1_1, d2_1, al[k][1], (Real)0, sc);
+            Real v1, v2, w1, w2;
+            {   // both rows of the thread in one block: their projection chains interleave
+                Real ya[2] = {y1o[k][0], y1o[k][1]}, yb[2] = {y2o[k][0], y2o[k][1]};
+                const Real da[2] = {d1_0, d1_1}, db[2] = {d2_0, d2_1}, aa[2] = {al[k][0], al[k][1]};
+                dual_update_n<Real, STRICT, 2>(ya, yb, da, db, aa, sc);
+                v1 = ya[0]; w1 = ya[1]; v2 = yb[0]; w2 = yb[1];
+            }
             Real *py1 = y1p + (size_t)c * M + r0;
             Real *py2 = y2p + (size_t)(c + 1) * M + r0;
             if (valid) {
@@ -347,9 +351,13 @@ __global__ void __launch_bounds__(res_tb_max_threads(KC), 1) pdps_resident_tb_ke
                 if (STRICT) { d2_0 = StrictOps<Real>::sub(rt0, xb[k][0]); d2_1 = StrictOps<Real>::sub(rt1, xb[k][1]); }
                 else { d2_0 = rt0 - xb[k][0]; d2_1 = rt1 - xb[k][1]; }
             }
-            Real v1 = y1o[k][0], v2 = y2o[k][0], w1 = y1o[k][1], w2 = y2o[k][1];
-            dual_update<Real, STRICT, false>(v1, v2, d1_0, d2_0, al[k][0], (Real)0, sc);
-            dual_update<Real, STRICT, false>(w1, w2, d1_1, d2_1, al[k][1], (Real)0, sc);
+            Real v1, v2, w1, w2;
+            {   // both rows of the thread in one block: their projection chains interleave
+                Real ya[2] = {y1o[k][0], y1o[k][1]}, yb[2] = {y2o[k][0], y2o[k][1]};
+                const Real da[2] = {d1_0, d1_1}, db[2] = {d2_0, d2_1}, aa[2] = {al[k][0], al[k][1]};
+                dual_update_n<Real, STRICT, 2>(ya, yb, da, db, aa, sc);
+                v1 = ya[0]; w1 = ya[1]; v2 = yb[0]; w2 = yb[1];
+            }
             st2(y1p + (size_t)e * M + r0, v1, w1);
             st2(y2p + (size_t)e * M + r0, v2, w2);
         }

@@ -98,14 +98,15 @@ __global__ void __launch_bounds__(256) sumregs_dual_kernel(const SumRegsArgs<Rea
     d2[1] = lf ? A::sub(c, xl) : z;
     d1[2] = (up && dn) ? A::mul(half, A::sub(xd, xu)) : z;        // ∇ᶜ (S11)
     d2[2] = (lf && rt) ? A::mul(half, A::sub(xr, xl)) : z;
+    Real v1[3], v2[3], al[3];
 #pragma unroll
     for (int op = 0; op < 3; ++op) {
-        Real *p1 = a.y + (size_t)(2 * op) * n + k, *p2 = a.y + (size_t)(2 * op + 1) * n + k;
-        Real v1 = *p1, v2 = *p2;
-        const Real al = MAP ? __ldg(a.amap + (size_t)op * plane + q) : a.alpha[op];
-        dual_update<Real, STRICT, false>(v1, v2, d1[op], d2[op], al, (Real)0, a.sc);
-        *p1 = v1; *p2 = v2;
+        v1[op] = a.y[(size_t)(2 * op) * n + k]; v2[op] = a.y[(size_t)(2 * op + 1) * n + k];
+        al[op] = MAP ? __ldg(a.amap + (size_t)op * plane + q) : a.alpha[op];
     }
+    dual_update_n<Real, STRICT, 3>(v1, v2, d1, d2, al, a.sc);     // the three operators' projection chains interleave
+#pragma unroll
+    for (int op = 0; op < 3; ++op) { a.y[(size_t)(2 * op) * n + k] = v1[op]; a.y[(size_t)(2 * op + 1) * n + k] = v2[op]; }
 }
 
 // ---------------------------------------------------------------------------
@@ -242,20 +243,16 @@ __global__ void __launch_bounds__(SRR_THREADS, 1) sumregs_resident_kernel(const 
             d2[1] = lf ? A::sub(cc, xl) : z;
             d1[2] = (up && dn) ? A::mul(half, A::sub(xd, xu)) : z;         // ∇ᶜ (S11)
             d2[2] = (lf && rt) ? A::mul(half, A::sub(xr, xl)) : z;
-            Real v1, v2;
-            v1 = y0[p0]; v2 = y1[p1];
-            dual_update<Real, STRICT, false>(v1, v2, d1[0], d2[0], al[k][0], (Real)0, sc);
-            y0[p0] = v1; y1[p1] = v2;
-            if (last && y1_r) y1_r[p0 - (nc - 1) * M] = v2;                       // forward, component 2: the right CTA reads column c0−1
-            v1 = y2[p0]; v2 = y3[p0];
-            dual_update<Real, STRICT, false>(v1, v2, d1[1], d2[1], al[k][1], (Real)0, sc);
-            y2[p0] = v1; y3[p0] = v2;
-            if (first && y3_l) y3_l[NC * M + p0] = v2;                   // backward, component 2: the left CTA reads column c0+NC
-            v1 = y4[p0]; v2 = y5[p1];
-            dual_update<Real, STRICT, false>(v1, v2, d1[2], d2[2], al[k][2], (Real)0, sc);
-            y4[p0] = v1; y5[p1] = v2;
-            if (first && y5_l) y5_l[(NC + 1) * M + p0] = v2;             // centred, component 2: both neighbours
-            if (last && y5_r) y5_r[p0 - (nc - 1) * M] = v2;
+            Real v1[3] = {y0[p0], y2[p0], y4[p0]}, v2[3] = {y1[p1], y3[p0], y5[p1]};
+            const Real alk[3] = {al[k][0], al[k][1], al[k][2]};
+            dual_update_n<Real, STRICT, 3>(v1, v2, d1, d2, alk, sc);    // the three operators' projection chains interleave
+            y0[p0] = v1[0]; y1[p1] = v2[0];
+            if (last && y1_r) y1_r[p0 - (nc - 1) * M] = v2[0];                    // forward, component 2: the right CTA reads column c0−1
+            y2[p0] = v1[1]; y3[p0] = v2[1];
+            if (first && y3_l) y3_l[NC * M + p0] = v2[1];                // backward, component 2: the left CTA reads column c0+NC
+            y4[p0] = v1[2]; y5[p1] = v2[2];
+            if (first && y5_l) y5_l[(NC + 1) * M + p0] = v2[2];          // centred, component 2: both neighbours
+            if (last && y5_r) y5_r[p0 - (nc - 1) * M] = v2[2];
         }
         cluster.sync();
     }
