@@ -49,7 +49,7 @@ def _config(n_gpus):
         "arith": "strict (one IEEE op per reference operator; bit-identical to the oracle) unless --arith fast",
         "kernel": "auto: temporally blocked streaming kernel, 2 iterations per HBM pass in strict arithmetic (4 in fast)",
         "l2": "working set 7 planes x 128 MiB = 896 MiB per GPU >> 126 MB L2 (no flush needed)",
-        "parallelism": f"images sharded over {n_gpus} GPU(s), one all-reduce of the loss per step",
+        "parallelism": f"images sharded over {n_gpus} GPU(s), one NCCL all-reduce of [loss, gradient] per step, issued by libbpltv itself (bpltv_comm_init)",
     }
 
 
@@ -264,10 +264,14 @@ def main():
     assert stream != 0
     ctx.set_dataset_device(d_truth.data_ptr(), d_noisy.data_ptr(), M, N, O_PER_GPU, stream)
 
+    # N > 1: the context joins the job's NCCL communicator INSIDE libbpltv (bpltv_comm_init; torch.distributed only carries
+    # the 128-byte id): every learn_eval then ends in the library's own ncclAllReduce of [loss, gradient] on `stream`
+    if world > 1:
+        from bpldenoising_b200.parallel import join_job
+        join_job(ctx)
+
     def step():
         ctx.learn_eval_device(LAM, 0.1, d_costgrad.data_ptr(), eopts, stream=stream)
-        if world > 1:
-            dist.all_reduce(d_costgrad)  # upper-level loss summed over ranks (NCCL)
 
     for _ in range(W):
         step()
@@ -472,7 +476,8 @@ def main():
 def config5_extra(bp, torch, dist, dev, tstream, world, rank, local, total=1024, n=256, iters=5000):
     """BASELINE.json configs[4]: tv_op_learning_function on `total` synthetic n×n images, both gradient branches
     (Δ = 0.1 → gradient, Δ = 1e-7 → gradient_reg) and the loss alone, images sharded `shard_range(total, world, rank)`.
-    Each evaluation = one learn_eval_device + one NCCL all-reduce of [loss, gradient]; CUDA-event time, max over ranks.
+    Each evaluation = one learn_eval_device, which ends in the library's NCCL all-reduce of [loss, gradient]; CUDA-event
+    time, max over ranks.
     The gradient's share is the difference to the loss-only evaluation."""
     from bpldenoising_b200.parallel import shard_range
     b, c = shard_range(total, world, rank)
@@ -483,6 +488,9 @@ def config5_extra(bp, torch, dist, dev, tstream, world, rank, local, total=1024,
     out = {"images_total": total, "image": [n, n], "iterations": iters, "images_per_rank": c, "ranks": world,
            "scaling": "strong", "lambda": LAM}
     with bp.Context([local], 64) as c5:
+        if world > 1:
+            from bpldenoising_b200.parallel import join_job
+            join_job(c5)              # [loss, gradient] summed by the library's own ncclAllReduce
         c5.set_dataset_device(d_t.data_ptr(), d_n.data_ptr(), n, n, c, tstream.cuda_stream)
         for name, Delta, branch in (("loss_only", 0.1, 3), ("gradient", 0.1, 0), ("gradient_reg", 1e-7, 0)):
             eo = bp.eval_opts(bp.pdps_opts(maxiter=iters), force_branch=branch)
@@ -494,8 +502,6 @@ def config5_extra(bp, torch, dist, dev, tstream, world, rank, local, total=1024,
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(tstream)
                 c5.learn_eval_device(LAM, Delta, cg.data_ptr(), eo, stream=tstream.cuda_stream)
-                if world > 1:
-                    dist.all_reduce(cg)
                 e1.record(tstream)
                 torch.cuda.synchronize()
                 t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)

@@ -45,6 +45,7 @@ EXPORTS = [
     "bpltv_sumregs_denoise", "bpltv_sumregs_learn_eval", "bpltv_sumregs_gradient",
     "bpltv_denoise_device", "bpltv_set_dataset_device", "bpltv_learn_eval_device",
     "bpltv_get_stats", "bpltv_last_error", "bpltv_version", "bpltv_reload_env", "bpltv_selftest",
+    "bpltv_comm_unique_id", "bpltv_comm_init", "bpltv_comm_destroy",
 ]
 
 _lib = None
@@ -92,6 +93,9 @@ def load() -> C.CDLL:
                                           C.POINTER(EvalOpts), vp, vp, vp]
     L.bpltv_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.bpltv_selftest.argtypes = [vp, C.c_int, C.c_int, C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_ulonglong)]
+    L.bpltv_comm_unique_id.argtypes = [C.POINTER(C.c_ubyte)]
+    L.bpltv_comm_init.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]
+    L.bpltv_comm_destroy.argtypes = [vp]
     L.bpltv_last_error.restype = C.c_char_p
     L.bpltv_version.restype = C.c_int
     L.bpltv_reload_env.restype = None

@@ -30,6 +30,7 @@
 #include "gradient_lu.cuh"
 #include "gradient_nd.h"
 #include "selftest.cuh"
+#include "nccl_dyn.h"
 
 // the option structs are mirrored field by field in bpldenoising_b200/_lib.py (ctypes) and julia/BPLTV.jl
 static_assert(sizeof(bpltv_pdps_opts) == 72, "bpltv_pdps_opts layout");
@@ -128,7 +129,21 @@ struct bpltv_ctx {
     int M = 0, N = 0, O = 0;  // resident dataset shape (global)
     bool have_dataset = false;
     bpltv_stats stats;
+    // one-process-per-GPU jobs: the communicator of bpltv_comm_init (nullptr: this process is the whole job)
+    void *comm = nullptr;
+    int comm_ranks = 1, comm_rank = 0;
 };
+
+// [cost, grad…] summed over the ranks of the job, in place, on `st` (one ncclAllReduce per evaluation); no-op without
+// a communicator.  Every rank receives the same bits.
+static int allreduce_costgrad(bpltv_ctx *ctx, double *d_costgrad, int count, cudaStream_t st)
+{
+    if (!ctx->comm) return 0;
+    NcclApi &api = nccl_api();
+    const int rc = api.AllReduce(d_costgrad, d_costgrad, (size_t)count, /*ncclDouble*/ 8, /*ncclSum*/ 0, ctx->comm, st);
+    if (rc != 0) return fail(BPLTV_ERR_CUDA, "ncclAllReduce of [cost, grad]: %s", api.what(rc));
+    return 0;
+}
 
 static void shard_range(int O, int ndev, int d, int &begin, int &count)
 {
@@ -793,6 +808,7 @@ static int sumregs_learn_eval_impl(bpltv_ctx *ctx, const double *lam, int lm, in
         }
         const Real *u = nullptr;
         RC_TRY(sumregs_eval_on_device<Real>(ctx, d, lam, lm, ln, Delta, eo, ug, d.stream, &u, d.scalars.as<double>()));
+        RC_TRY(allreduce_costgrad(ctx, d.scalars.as<double>(), 1 + ng, d.stream));
         CU_TRY(cudaMemcpyAsync(host[di].data(), d.scalars.p, (1 + ng) * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
         if (u_out && d.O > 0) RC_TRY(download_stack<Real>(d, u, plane * d.O, u_out + plane * d.o_begin, d.stream));
         CU_TRY(cudaEventRecord(d.ev[4], d.stream));
@@ -943,6 +959,7 @@ static int learn_eval_impl(bpltv_ctx *ctx, const double *lam, int lm, int ln, do
         RC_TRY(d.scalars.ensure((1 + ng) * sizeof(double)));
         const Real *u = nullptr;
         RC_TRY(eval_on_device<Real>(ctx, d, lam, lm, ln, Delta, eo, d.stream, &u, d.scalars.as<double>()));
+        RC_TRY(allreduce_costgrad(ctx, d.scalars.as<double>(), 1 + ng, d.stream));
         CU_TRY(cudaMemcpyAsync(host[di].data(), d.scalars.p, (1 + ng) * sizeof(double), cudaMemcpyDeviceToHost,
                                d.stream));
         if (d.grad_used_nd)
@@ -1156,6 +1173,7 @@ static int learn_eval_device_impl(bpltv_ctx *ctx, const double *lam, int lm, int
     std::memset(&ctx->stats, 0, sizeof ctx->stats);
     const Real *u = nullptr;
     RC_TRY(eval_on_device<Real>(ctx, d, lam, lm, ln, Delta, eo, st, &u, d_costgrad));
+    RC_TRY(allreduce_costgrad(ctx, d_costgrad, 1 + lm * ln, st));
     if (d_u_out && d.O > 0)
         CU_TRY(cudaMemcpyAsync(d_u_out, u, (size_t)d.M * d.N * d.O * sizeof(Real), cudaMemcpyDeviceToDevice, st));
     ctx->stats.kernel_launches = d.launches;
@@ -1252,9 +1270,55 @@ int bpltv_create(const int *device_ids, int ndev, int precision, bpltv_ctx **out
     return 0;
 }
 
+int bpltv_comm_unique_id(unsigned char *id_out)
+{
+    if (!id_out) return fail(BPLTV_ERR_ARG, "NULL argument");
+    NcclApi &api = nccl_api();
+    if (!api.load()) return fail(BPLTV_ERR_STATE, "NCCL library not available (%s); set BPLTV_NCCL_LIB", api.err.c_str());
+    NcclId id;
+    const int rc = api.GetUniqueId(&id);
+    if (rc != 0) return fail(BPLTV_ERR_CUDA, "ncclGetUniqueId: %s", api.what(rc));
+    std::memcpy(id_out, id.internal, BPLTV_COMM_ID_BYTES);
+    return 0;
+}
+
+int bpltv_comm_destroy(bpltv_ctx *ctx)
+{
+    if (!ctx) return fail(BPLTV_ERR_ARG, "NULL argument");
+    if (ctx->comm) {
+        cudaSetDevice(ctx->devs[0].id);
+        cudaStreamSynchronize(ctx->devs[0].stream);
+        nccl_api().CommDestroy(ctx->comm);
+        ctx->comm = nullptr;
+    }
+    ctx->comm_ranks = 1; ctx->comm_rank = 0;
+    return 0;
+}
+
+int bpltv_comm_init(bpltv_ctx *ctx, int nranks, int rank, const unsigned char *id)
+{
+    if (!ctx || !id) return fail(BPLTV_ERR_ARG, "NULL argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(BPLTV_ERR_ARG, "bad rank %d of %d", rank, nranks);
+    if (ctx->devs.size() != 1)
+        return fail(BPLTV_ERR_ARG, "a communicator joins single-device contexts (one process per GPU); this context shards over %d devices itself",
+                    (int)ctx->devs.size());
+    NcclApi &api = nccl_api();
+    if (!api.load()) return fail(BPLTV_ERR_STATE, "NCCL library not available (%s); set BPLTV_NCCL_LIB", api.err.c_str());
+    bpltv_comm_destroy(ctx);
+    CU_TRY(cudaSetDevice(ctx->devs[0].id));
+    NcclId nid;
+    std::memcpy(nid.internal, id, BPLTV_COMM_ID_BYTES);
+    void *comm = nullptr;
+    const int rc = api.CommInitRank(&comm, nranks, nid, rank);
+    if (rc != 0) return fail(BPLTV_ERR_CUDA, "ncclCommInitRank(%d of %d): %s", rank, nranks, api.what(rc));
+    ctx->comm = comm; ctx->comm_ranks = nranks; ctx->comm_rank = rank;
+    return 0;
+}
+
 int bpltv_destroy(bpltv_ctx *ctx)
 {
     if (!ctx) return 0;
+    bpltv_comm_destroy(ctx);
     for (Dev &d : ctx->devs) {
         cudaSetDevice(d.id);
         if (d.stream) cudaStreamSynchronize(d.stream);

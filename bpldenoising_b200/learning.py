@@ -12,6 +12,7 @@ the C ABI.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import numpy as np
@@ -107,6 +108,20 @@ def sumregs_pdps_opts(**kw) -> PdpsOpts:
             raise TypeError(f"unknown PDPS option {k!r}")
         setattr(o, k, type(getattr(o, k))(v))
     return o
+
+
+def _point_at_nccl():
+    """libbpltv binds NCCL at run time ($BPLTV_NCCL_LIB, else libnccl.so.2 by soname).  Where no system copy is on the
+    loader path, point it at the copy pip puts beside torch (nvidia/nccl/lib) — a path, not an import of torch."""
+    if os.environ.get("BPLTV_NCCL_LIB"):
+        return
+    import importlib.util
+    spec = importlib.util.find_spec("nvidia")
+    for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+        cand = os.path.join(base, "nccl", "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            os.environ["BPLTV_NCCL_LIB"] = cand
+            return
 
 
 class Context:
@@ -275,6 +290,27 @@ class Context:
         s = Stats()
         check(self._L.bpltv_get_stats(self._h, C.byref(s)))
         return s.asdict()
+
+    # ---- one process per GPU: the job's collective inside the library (include/bpltv.h, bpltv_comm_*) -------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """The 128-byte NCCL id rank 0 creates and ships to the other ranks (any transport)."""
+        _point_at_nccl()
+        buf = (C.c_ubyte * 128)()
+        check(_lib.load().bpltv_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        """Join the job's communicator (collective).  From then on learn_eval / learn_eval_device /
+        sumregs_learn_eval return the loss and gradient summed over all ranks (one ncclAllReduce per evaluation)."""
+        _point_at_nccl()
+        if len(unique_id) != 128:
+            raise ValueError("the NCCL id has 128 bytes")
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        check(self._L.bpltv_comm_init(self._h, nranks, rank, buf))
+
+    def comm_destroy(self):
+        check(self._L.bpltv_comm_destroy(self._h))
 
     def selftest(self, mode: int, count: int, seed: int = 1, what: int = 0) -> dict:
         """Arithmetic self-test (include/bpltv.h, bpltv_selftest): the strict kernels' projection scale against the IEEE

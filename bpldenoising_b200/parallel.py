@@ -28,3 +28,18 @@ def allreduce_costgrad(costgrad, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(costgrad, op=dist.ReduceOp.SUM, group=group)
     return costgrad
+
+
+def join_job(ctx, group=None):
+    """One process per GPU under torchrun: attach `ctx` (a single-device Context holding this rank's shard) to the job's
+    NCCL communicator INSIDE libbpltv (bpltv_comm_init).  torch.distributed is only the courier of the 128-byte id
+    (a broadcast from rank 0); afterwards every learn_eval of `ctx` returns the whole job's loss and gradient, summed by
+    the library's own ncclAllReduce, and `allreduce_costgrad` is not needed."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    box = [ctx.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    ctx.comm_init(world, rank, box[0])
+    return world, rank

@@ -217,6 +217,20 @@ int bpltv_learn_eval_device(bpltv_ctx *ctx, const double *lam, int lm, int ln,
                             double Delta, const bpltv_eval_opts *opts, void *d_u_out,
                             double *d_costgrad, void *stream);
 
+/* One process per GPU (MPI / Distributed.jl / torchrun): the job's single collective lives in the library.  Every rank
+ * owns a single-device context holding ITS shard of the images (contiguous blocks of ceil(O/nranks) images, the same
+ * split bpltv_create uses across the devices of one process) and joins one NCCL communicator; from then on
+ * bpltv_learn_eval, bpltv_learn_eval_device and bpltv_sumregs_learn_eval return the loss and the gradient of the WHOLE
+ * job on every rank — the per-image sums of /root/reference/src/TVLearningFunctionVec.jl:72-83, :163-175 completed by
+ * ONE ncclAllReduce (fp64 sum) of [cost, grad...] per evaluation on the context's stream; the denoised images stay
+ * per rank.  NCCL is bound at run time (dlopen of $BPLTV_NCCL_LIB, else libnccl.so.2): no communicator, no dependency.
+ *   rank 0:  bpltv_comm_unique_id(id);  ship the 128 bytes to the other ranks by any means;
+ *   all:     bpltv_comm_init(ctx, nranks, rank, id)   (collective: returns when every rank has joined).          */
+#define BPLTV_COMM_ID_BYTES 128
+int bpltv_comm_unique_id(unsigned char *id_out);
+int bpltv_comm_init(bpltv_ctx *ctx, int nranks, int rank, const unsigned char *id);
+int bpltv_comm_destroy(bpltv_ctx *ctx);
+
 int bpltv_get_stats(bpltv_ctx *ctx, bpltv_stats *out);
 /* The developer switches (environment variables BPLTV_*) are read once, when the first context is
  * created; this re-reads them (the test-suite flips them between calls).  Not needed by a normal caller. */

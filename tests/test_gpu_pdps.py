@@ -354,4 +354,4 @@ def test_projection_scale_chain_equals_the_ieee_operations(bp, ctx, ctx32, prec)
         span = 119 << 23
         for seed in (1, 2, 3):
             r = c.selftest(3, span, seed=seed)
-            assert r["took"] >= span - 119 and r["mismatches"] == 0, (seed, r)
+            assert r["took"] >= span - 2 * 119 and r["mismatches"] == 0, (seed, r)    # two guarded significands per binade

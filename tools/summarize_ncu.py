@@ -2,6 +2,7 @@
 
   python tools/summarize_ncu.py launches gpurun_out/launches_bench.csv profiles/r1_launches_bench.md
   python tools/summarize_ncu.py rep gpurun_out/prof_march.ncu-rep profiles/r1_ncu_march.md [top_kernel.json]
+  python tools/summarize_ncu.py rep gpurun_out/prof_x_raw.csv profiles/r2_ncu_x.md      (raw page exported on the box)
 """
 import csv
 import io
@@ -35,7 +36,12 @@ def to_bytes(v, unit):
 
 
 def rep(path, out, top_json=None):
-    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a .ncu-rep, or the `ncu -i … --page raw --csv` export of one made on the GPU box (reports of many launches exceed
+    # what travels back)
+    if path.endswith(".csv"):
+        txt = "".join(l for l in open(path, newline="") if not l.startswith("=="))
+    else:
+        txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
