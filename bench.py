@@ -47,7 +47,7 @@ def _config(n_gpus):
                     "1000 accelerated PDPS iterations (tau0=5, sigma0=0.99/5) + loss 0.5||u-u_true||^2",
         "images_per_gpu": O_PER_GPU, "image": [M, N], "iterations": ITERS, "lambda": LAM,
         "arith": "strict (one IEEE op per reference operator; bit-identical to the oracle) unless --arith fast",
-        "kernel": "auto: temporally blocked streaming kernel, 2 iterations per HBM pass in strict arithmetic (4 in fast)",
+        "kernel": "auto: temporally blocked streaming kernel, 4 iterations per HBM pass (fp64; strict fp32: 2)",
         "l2": "working set 7 planes x 128 MiB = 896 MiB per GPU >> 126 MB L2 (no flush needed)",
         "parallelism": f"images sharded over {n_gpus} GPU(s), one NCCL all-reduce of [loss, gradient] per step, issued by libbpltv itself (bpltv_comm_init)",
     }

@@ -366,7 +366,10 @@ static int run_pdps(Dev &d, const Real *f, int M, int N, int O, double alpha_s, 
         return fail(BPLTV_ERR_ARG, "march PDPS kernel does not take M=%d", M);
     int tdepth = 1;
     if (kernel == BPLTV_KERNEL_TBLOCK) {
-        tdepth = o.tblock > 0 ? o.tblock : env_int("BPLTV_TBLOCK_T", strict ? 2 : 4);
+        // depth when the caller leaves it open (measured, config 4, Gpixel-iter/s T = 2 / 3 / 4): fp64 strict 189 / 183 /
+        // 197 and — sustained, where T = 2's HBM traffic runs the chip into its power cap — 182 vs 196; fp64 fast 189 /
+        // 206 / 220; fp32 strict 370 / 346 / 331 (its four-pixel stages spill at depth 4); fp32 fast 370 / 444 / 486
+        tdepth = o.tblock > 0 ? o.tblock : env_int("BPLTV_TBLOCK_T", (strict && sizeof(Real) == 4) ? 2 : 4);
         if (tdepth < 1 || tdepth > 4) return fail(BPLTV_ERR_ARG, "temporal blocking depth must be 1..4 (got %d)", tdepth);
         if (!tblock_vec<Real>(M) || rho)
             return fail(BPLTV_ERR_ARG, "temporally blocked PDPS kernel does not take M=%d (rho=%g)", M, o.rho);

@@ -72,7 +72,7 @@ typedef struct bpltv_pdps_opts {
     int arith;      /* enum bpltv_arith                                     */
     int kernel;     /* enum bpltv_pdps_kernel                               */
     int tblock;     /* temporal blocking depth T of BPLTV_KERNEL_TBLOCK, 2..4
-                       (0 = auto: 2 in strict, 4 in fast arithmetic)          */
+                       (0 = auto: 4; 2 for strict arithmetic in fp32)          */
     int reserved[4];
 } bpltv_pdps_opts;
 

@@ -19,7 +19,7 @@ with bp.Context([0], int(os.environ.get("BPLTV_PREC", "64"))) as ctx:
     elif case == "tblock":  # same shape through the temporally blocked kernel (depth from BPLTV_TBLOCK_T)
         t, f = bp.synthetic_dataset(512, 512, 64, seed=20240601)
         u = ctx.denoise(f, 0.1, bp.pdps_opts(maxiter=iters, kernel=bp.KERNEL_TBLOCK, arith=arith,
-                                             tblock=int(os.environ.get("BPLTV_TBLOCK_T", "2"))))
+                                             tblock=int(os.environ.get("BPLTV_TBLOCK_T", "4"))))
         print("tblock ok", float(u.mean()), ctx.stats()["ms_pdps"])
     elif case == "resident":
         t, f = bp.synthetic_dataset(128, 128, 10, seed=7)
