@@ -12,7 +12,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cstddef>
@@ -92,6 +94,111 @@ struct DBuf {
     template <typename T> T *as() const { return static_cast<T *>(p); }
 };
 
+// ---------------------------------------------------------------------------
+// Pageable host buffers.  What a caller hands in is usually pageable memory (a Julia Array, a numpy array):
+// cudaMemcpyAsync then goes through the driver's single staging thread — measured 11 GB/s up and 18 GB/s down on the B200
+// box against 55 GB/s from pinned memory, i.e. 19 ms of copies beside a 95 ms solve at BASELINE config 4.  Registering the
+// caller's buffer for the duration of the call (cudaHostRegister) costs more than it saves (page pinning ≈ the copy).
+// Instead NT host threads move 4 MiB chunks through their own pinned slots: thread t owns chunks t, t+NT, … and two
+// slots, copies chunk k into a slot while the DMA of chunk k-1 drains the other (and the reverse for downloads).
+// The caller's buffers stay untouched and unpinned; the slots belong to the context (ownership rule of SURVEY §8b).
+// ---------------------------------------------------------------------------
+struct HostStage {
+    static constexpr int MAXT = 8, NSLOT = 2;
+    static constexpr size_t SLOT = (size_t)4 << 20;
+    static constexpr size_t MIN_BYTES = (size_t)8 << 20;     // below this the driver's path is as good
+    char *pin = nullptr;
+    cudaEvent_t ev[MAXT * NSLOT] = {nullptr};
+    bool used[MAXT * NSLOT] = {false};
+    int nt = 0;
+    bool init()
+    {
+        if (pin) return true;
+        const unsigned hc = std::thread::hardware_concurrency();
+        nt = (int)std::max(1u, std::min<unsigned>(MAXT, hc ? hc / 2 : 2));
+        if (cudaHostAlloc((void **)&pin, (size_t)nt * NSLOT * SLOT, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError(); pin = nullptr; return false;
+        }
+        for (int i = 0; i < nt * NSLOT; ++i)
+            if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); release(); return false; }
+        return true;
+    }
+    void release()
+    {
+        for (auto &e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
+        for (auto &u : used) u = false;
+        if (pin) cudaFreeHost(pin);
+        pin = nullptr;
+    }
+};
+
+static bool host_is_pageable(const void *h)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, h) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+// host ↔ device copy of `bytes` through the pinned slots, enqueued on `st`.  to_device: returns when the caller's
+// buffer has been read (the last DMAs may still be in flight on `st`); otherwise returns when the data is in `host`.
+static cudaError_t staged_copy(HostStage &hs, int device, char *dev, char *host, size_t bytes, cudaStream_t st, bool to_device)
+{
+    const size_t SLOT = HostStage::SLOT;
+    const size_t nchunks = (bytes + SLOT - 1) / SLOT;
+    const int nt = (int)std::min<size_t>((size_t)hs.nt, nchunks);
+    std::atomic<int> err{(int)cudaSuccess};
+    auto fail_with = [&](cudaError_t e) { int ok = (int)cudaSuccess; err.compare_exchange_strong(ok, (int)e); };
+    auto worker = [&](int t) {
+        cudaError_t e = cudaSetDevice(device);
+        if (e != cudaSuccess) { fail_with(e); return; }
+        auto span = [&](size_t c, size_t &off, size_t &len) { off = c * SLOT; len = std::min(SLOT, bytes - off); };
+        if (to_device) {
+            size_t k = 0;
+            for (size_t c = (size_t)t; c < nchunks; c += (size_t)nt, ++k) {
+                const int s = t * HostStage::NSLOT + (int)(k % HostStage::NSLOT);
+                char *slot = hs.pin + (size_t)s * SLOT;
+                if (hs.used[s] && (e = cudaEventSynchronize(hs.ev[s])) != cudaSuccess) { fail_with(e); return; }
+                size_t off, len;
+                span(c, off, len);
+                std::memcpy(slot, host + off, len);
+                if ((e = cudaMemcpyAsync(dev + off, slot, len, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+                    (e = cudaEventRecord(hs.ev[s], st)) != cudaSuccess) { fail_with(e); return; }
+                hs.used[s] = true;
+            }
+        } else {
+            // chunk k of this thread lands in slot k % NSLOT; keep NSLOT DMAs in flight ahead of the host copy
+            auto issue = [&](size_t k) -> cudaError_t {
+                const size_t c = (size_t)t + k * (size_t)nt;
+                const int s = t * HostStage::NSLOT + (int)(k % HostStage::NSLOT);
+                size_t off, len;
+                span(c, off, len);
+                if (hs.used[s]) { cudaError_t w = cudaEventSynchronize(hs.ev[s]); if (w != cudaSuccess) return w; }
+                cudaError_t r = cudaMemcpyAsync(hs.pin + (size_t)s * SLOT, dev + off, len, cudaMemcpyDeviceToHost, st);
+                if (r == cudaSuccess) r = cudaEventRecord(hs.ev[s], st);
+                hs.used[s] = true;
+                return r;
+            };
+            const size_t mine = nchunks > (size_t)t ? (nchunks - (size_t)t + (size_t)nt - 1) / (size_t)nt : 0;
+            for (size_t k = 0; k < std::min<size_t>(HostStage::NSLOT, mine); ++k)
+                if ((e = issue(k)) != cudaSuccess) { fail_with(e); return; }
+            for (size_t k = 0; k < mine; ++k) {
+                const int s = t * HostStage::NSLOT + (int)(k % HostStage::NSLOT);
+                if ((e = cudaEventSynchronize(hs.ev[s])) != cudaSuccess) { fail_with(e); return; }
+                size_t off, len;
+                span((size_t)t + k * (size_t)nt, off, len);
+                std::memcpy(host + off, hs.pin + (size_t)s * SLOT, len);
+                hs.used[s] = false;                                // consumed: the slot is free without a wait
+                if (k + HostStage::NSLOT < mine && (e = issue(k + HostStage::NSLOT)) != cudaSuccess) { fail_with(e); return; }
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(worker, t);
+    worker(0);
+    for (auto &x : th) x.join();
+    return (cudaError_t)err.load();
+}
+
 struct StepKey {
     double tau0 = -1, sigma0 = -1, opnorm = -1;
     int accel = -1, maxiter = -1, prec = 0;
@@ -121,6 +228,7 @@ struct Dev {
     StepKey steps_key;
     std::vector<unsigned char> steps_host;
     long long launches = 0;
+    HostStage hstage;         // pinned slots for pageable caller buffers
 };
 
 struct bpltv_ctx {
@@ -515,11 +623,12 @@ static int upload_stack(Dev &d, const double *h, size_t n, DBuf &dst, cudaStream
 {
     RC_TRY(dst.ensure(std::max<size_t>(n, 1) * sizeof(Real)));
     if (n == 0) return 0;
-    if (sizeof(Real) == 8) {
-        CU_TRY(cudaMemcpyAsync(dst.p, h, n * 8, cudaMemcpyHostToDevice, st));
-    } else {
-        RC_TRY(d.stage.ensure(n * 8));
-        CU_TRY(cudaMemcpyAsync(d.stage.p, h, n * 8, cudaMemcpyHostToDevice, st));
+    if (sizeof(Real) != 8) RC_TRY(d.stage.ensure(n * 8));
+    void *target = sizeof(Real) == 8 ? dst.p : d.stage.p;
+    const bool staged = n * 8 >= HostStage::MIN_BYTES && env_int("BPLTV_HOST_STAGING", 1) && host_is_pageable(h) && d.hstage.init();
+    if (staged) CU_TRY(staged_copy(d.hstage, d.id, static_cast<char *>(target), reinterpret_cast<char *>(const_cast<double *>(h)), n * 8, st, true));
+    else CU_TRY(cudaMemcpyAsync(target, h, n * 8, cudaMemcpyHostToDevice, st));
+    if (sizeof(Real) != 8) {
         const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
         convert_kernel<Real, double><<<blocks, 256, 0, st>>>(d.stage.as<double>(), dst.as<Real>(), n);
         d.launches += 1;
@@ -531,15 +640,19 @@ template <typename Real>
 static int download_stack(Dev &d, const Real *src, size_t n, double *h, cudaStream_t st)
 {
     if (n == 0) return 0;
-    if (sizeof(Real) == 8) {
-        CU_TRY(cudaMemcpyAsync(h, src, n * 8, cudaMemcpyDeviceToHost, st));
-    } else {
+    const void *source = src;
+    if (sizeof(Real) != 8) {
         RC_TRY(d.stage.ensure(n * 8));
         const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
         convert_kernel<double, Real><<<blocks, 256, 0, st>>>(src, d.stage.as<double>(), n);
         d.launches += 1;
-        CU_TRY(cudaMemcpyAsync(h, d.stage.p, n * 8, cudaMemcpyDeviceToHost, st));
+        source = d.stage.p;
     }
+    // a pageable destination: through the pinned slots (the call then returns with the data in `h`, which every
+    // host-pointer entry point guarantees at its end anyway)
+    const bool staged = n * 8 >= HostStage::MIN_BYTES && env_int("BPLTV_HOST_STAGING", 1) && host_is_pageable(h) && d.hstage.init();
+    if (staged) CU_TRY(staged_copy(d.hstage, d.id, static_cast<char *>(const_cast<void *>(source)), reinterpret_cast<char *>(h), n * 8, st, false));
+    else CU_TRY(cudaMemcpyAsync(h, source, n * 8, cudaMemcpyDeviceToHost, st));
     return 0;
 }
 
@@ -572,6 +685,10 @@ static int denoise_impl(bpltv_ctx *ctx, const double *noisy, int M, int N, int O
     const int ndev = (int)ctx->devs.size();
     const size_t plane = (size_t)M * N;
     std::memset(&ctx->stats, 0, sizeof ctx->stats);
+    // pass 1: every device gets its shard and its solve enqueued; pass 2: the downloads (a pageable destination makes
+    // download_stack wait for the device, which must not hold back the other devices' work)
+    std::vector<const Real *> us(ndev, nullptr);
+    std::vector<int> obs(ndev, 0), ocs(ndev, 0);
     for (int di = 0; di < ndev; ++di) {
         Dev &d = ctx->devs[di];
         CU_TRY(cudaSetDevice(d.id));
@@ -579,6 +696,7 @@ static int denoise_impl(bpltv_ctx *ctx, const double *noisy, int M, int N, int O
         int ob, oc;
         if (noisy) shard_range(O, ndev, di, ob, oc);
         else { ob = d.o_begin; oc = d.O; }
+        obs[di] = ob; ocs[di] = oc;
         cudaStream_t st = d.stream;
         CU_TRY(cudaEventRecord(d.ev[0], st));
         const Real *f;
@@ -591,13 +709,17 @@ static int denoise_impl(bpltv_ctx *ctx, const double *noisy, int M, int N, int O
         CU_TRY(cudaEventRecord(d.ev[1], st));
         double alpha_s; const Real *amap;
         RC_TRY(prepare_lambda<Real>(d, lam, lm, ln, M, N, st, &alpha_s, &amap));
-        const Real *u = nullptr; int used = 0, depth = 1;
-        RC_TRY(run_pdps<Real>(d, f, M, N, oc, alpha_s, amap, o, st, &u, &used, &depth));
+        int used = 0, depth = 1;
+        RC_TRY(run_pdps<Real>(d, f, M, N, oc, alpha_s, amap, o, st, &us[di], &used, &depth));
         ctx->stats.pdps_kernel_used = used;
         ctx->stats.tblock_depth = depth;
         CU_TRY(cudaEventRecord(d.ev[2], st));
-        if (oc > 0) RC_TRY(download_stack<Real>(d, u, plane * oc, u_out + plane * ob, st));
-        CU_TRY(cudaEventRecord(d.ev[3], st));
+    }
+    for (int di = 0; di < ndev; ++di) {
+        Dev &d = ctx->devs[di];
+        CU_TRY(cudaSetDevice(d.id));
+        if (ocs[di] > 0) RC_TRY(download_stack<Real>(d, us[di], plane * ocs[di], u_out + plane * obs[di], d.stream));
+        CU_TRY(cudaEventRecord(d.ev[3], d.stream));
     }
     for (int di = 0; di < ndev; ++di) {
         Dev &d = ctx->devs[di];
@@ -711,6 +833,8 @@ static int sumregs_denoise_impl(bpltv_ctx *ctx, const double *noisy, int M, int 
     const int ndev = (int)ctx->devs.size();
     const size_t plane = (size_t)M * N;
     std::memset(&ctx->stats, 0, sizeof ctx->stats);
+    std::vector<const Real *> us(ndev, nullptr);        // two passes, as in denoise_impl
+    std::vector<int> obs(ndev, 0), ocs(ndev, 0);
     for (int di = 0; di < ndev; ++di) {
         Dev &d = ctx->devs[di];
         CU_TRY(cudaSetDevice(d.id));
@@ -718,6 +842,7 @@ static int sumregs_denoise_impl(bpltv_ctx *ctx, const double *noisy, int M, int 
         int ob, oc;
         if (noisy) shard_range(O, ndev, di, ob, oc);
         else { ob = d.o_begin; oc = d.O; }
+        obs[di] = ob; ocs[di] = oc;
         cudaStream_t st = d.stream;
         CU_TRY(cudaEventRecord(d.ev[0], st));
         const Real *f;
@@ -730,11 +855,14 @@ static int sumregs_denoise_impl(bpltv_ctx *ctx, const double *noisy, int M, int 
         CU_TRY(cudaEventRecord(d.ev[1], st));
         Real alpha[3]; const Real *amap;
         RC_TRY(prepare_lambda3<Real>(d, lam, lm, ln, M, N, st, alpha, &amap));
-        const Real *u = nullptr;
-        RC_TRY(run_sumregs_pdps<Real>(d, f, M, N, oc, alpha, amap, o, st, &u));
+        RC_TRY(run_sumregs_pdps<Real>(d, f, M, N, oc, alpha, amap, o, st, &us[di]));
         CU_TRY(cudaEventRecord(d.ev[2], st));
-        if (oc > 0) RC_TRY(download_stack<Real>(d, u, plane * oc, u_out + plane * ob, st));
-        CU_TRY(cudaEventRecord(d.ev[3], st));
+    }
+    for (int di = 0; di < ndev; ++di) {
+        Dev &d = ctx->devs[di];
+        CU_TRY(cudaSetDevice(d.id));
+        if (ocs[di] > 0) RC_TRY(download_stack<Real>(d, us[di], plane * ocs[di], u_out + plane * obs[di], d.stream));
+        CU_TRY(cudaEventRecord(d.ev[3], d.stream));
     }
     for (int di = 0; di < ndev; ++di) {
         Dev &d = ctx->devs[di];
@@ -799,6 +927,7 @@ static int sumregs_learn_eval_impl(bpltv_ctx *ctx, const double *lam, int lm, in
     const size_t plane = (size_t)ctx->M * ctx->N;
     std::memset(&ctx->stats, 0, sizeof ctx->stats);
     std::vector<std::vector<double>> host(ndev, std::vector<double>(1 + ng, 0.0));
+    std::vector<const Real *> us(ndev, nullptr);
     for (int di = 0; di < ndev; ++di) {
         Dev &d = ctx->devs[di];
         CU_TRY(cudaSetDevice(d.id));
@@ -809,11 +938,14 @@ static int sumregs_learn_eval_impl(bpltv_ctx *ctx, const double *lam, int lm, in
             RC_TRY(upload_stack<Real>(d, u_host + plane * d.o_begin, plane * d.O, d.ubuf, d.stream));
             ug = d.ubuf.as<Real>();
         }
-        const Real *u = nullptr;
-        RC_TRY(sumregs_eval_on_device<Real>(ctx, d, lam, lm, ln, Delta, eo, ug, d.stream, &u, d.scalars.as<double>()));
+        RC_TRY(sumregs_eval_on_device<Real>(ctx, d, lam, lm, ln, Delta, eo, ug, d.stream, &us[di], d.scalars.as<double>()));
         RC_TRY(allreduce_costgrad(ctx, d.scalars.as<double>(), 1 + ng, d.stream));
         CU_TRY(cudaMemcpyAsync(host[di].data(), d.scalars.p, (1 + ng) * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
-        if (u_out && d.O > 0) RC_TRY(download_stack<Real>(d, u, plane * d.O, u_out + plane * d.o_begin, d.stream));
+    }
+    for (int di = 0; di < ndev; ++di) {      // second pass: see denoise_impl
+        Dev &d = ctx->devs[di];
+        CU_TRY(cudaSetDevice(d.id));
+        if (u_out && d.O > 0) RC_TRY(download_stack<Real>(d, us[di], plane * d.O, u_out + plane * d.o_begin, d.stream));
         CU_TRY(cudaEventRecord(d.ev[4], d.stream));
     }
     double cost = 0.0;
@@ -954,20 +1086,24 @@ static int learn_eval_impl(bpltv_ctx *ctx, const double *lam, int lm, int ln, do
     std::memset(&ctx->stats, 0, sizeof ctx->stats);
     std::vector<std::vector<double>> host(ndev, std::vector<double>(1 + ng, 0.0));
     std::vector<double> relres(ndev, 0.0);
+    std::vector<const Real *> us(ndev, nullptr);
     for (int di = 0; di < ndev; ++di) {
         Dev &d = ctx->devs[di];
         CU_TRY(cudaSetDevice(d.id));
         d.launches = 0;
         d.grad_used_nd = false;
         RC_TRY(d.scalars.ensure((1 + ng) * sizeof(double)));
-        const Real *u = nullptr;
-        RC_TRY(eval_on_device<Real>(ctx, d, lam, lm, ln, Delta, eo, d.stream, &u, d.scalars.as<double>()));
+        RC_TRY(eval_on_device<Real>(ctx, d, lam, lm, ln, Delta, eo, d.stream, &us[di], d.scalars.as<double>()));
         RC_TRY(allreduce_costgrad(ctx, d.scalars.as<double>(), 1 + ng, d.stream));
         CU_TRY(cudaMemcpyAsync(host[di].data(), d.scalars.p, (1 + ng) * sizeof(double), cudaMemcpyDeviceToHost,
                                d.stream));
         if (d.grad_used_nd)
             CU_TRY(cudaMemcpyAsync(&relres[di], nd_work_relres_max(d.nd), sizeof(double), cudaMemcpyDeviceToHost, d.stream));
-        if (u_out && d.O > 0) RC_TRY(download_stack<Real>(d, u, plane * d.O, u_out + plane * d.o_begin, d.stream));
+    }
+    for (int di = 0; di < ndev; ++di) {      // second pass: see denoise_impl
+        Dev &d = ctx->devs[di];
+        CU_TRY(cudaSetDevice(d.id));
+        if (u_out && d.O > 0) RC_TRY(download_stack<Real>(d, us[di], plane * d.O, u_out + plane * d.o_begin, d.stream));
         CU_TRY(cudaEventRecord(d.ev[4], d.stream));
     }
     double cost = 0.0;
@@ -1332,6 +1468,7 @@ int bpltv_destroy(bpltv_ctx *ctx)
         d.grad3.release();
         nd_work_destroy(d.nd);
         d.nd = nullptr;
+        d.hstage.release();
         for (auto &ev : d.ev) if (ev) cudaEventDestroy(ev);
         if (d.stream) cudaStreamDestroy(d.stream);
     }

@@ -305,7 +305,8 @@ def test_config4_full_size_is_bit_identical_to_the_oracle_pins(bp, ctx, ctx32):
     for c, key, dt in ((ctx, "f64", np.float64), (ctx32, "f32", np.float32)):
         c.set_dataset((truth, noisy))
         u, cost, _ = c.learn_eval(pins["lambda"], 0.1, bp.eval_opts(bp.pdps_opts(maxiter=pins["iterations"]), force_branch=3))
-        assert c.stats()["pdps_kernel_used"] == bp.KERNEL_TBLOCK and c.stats()["tblock_depth"] == 2
+        # AUTO: four iterations per HBM pass in fp64, two for strict arithmetic in fp32
+        assert c.stats()["pdps_kernel_used"] == bp.KERNEL_TBLOCK and c.stats()["tblock_depth"] == (4 if key == "f64" else 2)
         got = [hashlib.sha256(np.ascontiguousarray(u[:, :, o].astype(dt).T).tobytes()).hexdigest()
                for o in range(pins["O"])]
         assert got == pins[key]["u_sha256"], key
