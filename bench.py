@@ -266,12 +266,22 @@ def main():
 
     # N > 1: the context joins the job's NCCL communicator INSIDE libbpltv (bpltv_comm_init; torch.distributed only carries
     # the 128-byte id): every learn_eval then ends in the library's own ncclAllReduce of [loss, gradient] on `stream`
+    collective = "none (one rank)"
+    lib_comm = False
     if world > 1:
         from bpldenoising_b200.parallel import join_job
-        join_job(ctx)
+        try:
+            join_job(ctx)
+            lib_comm = True
+            collective = "ncclAllReduce issued by libbpltv (bpltv_comm_init)"
+        except Exception as e:      # noqa: BLE001 - keep the scaling run alive and say what happened
+            # every rank fails or succeeds together (the id broadcast is collective, the NCCL binding is the same file)
+            collective = f"torch.distributed all_reduce (library communicator unavailable: {type(e).__name__}: {e})"
 
     def step():
         ctx.learn_eval_device(LAM, 0.1, d_costgrad.data_ptr(), eopts, stream=stream)
+        if world > 1 and not lib_comm:
+            dist.all_reduce(d_costgrad)
 
     for _ in range(W):
         step()
@@ -417,7 +427,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": _config(world), "roofline": roofline, "e2e": e2e,
+        "dtype": "f64", "data": "synthetic", "config": dict(_config(world), collective=collective), "roofline": roofline, "e2e": e2e,
         "gpu_launches": int(launches_per_step * K), "loss": loss,
     }
     if value_f32 is not None:
@@ -488,9 +498,15 @@ def config5_extra(bp, torch, dist, dev, tstream, world, rank, local, total=1024,
     out = {"images_total": total, "image": [n, n], "iterations": iters, "images_per_rank": c, "ranks": world,
            "scaling": "strong", "lambda": LAM}
     with bp.Context([local], 64) as c5:
+        lib_comm = False
         if world > 1:
             from bpldenoising_b200.parallel import join_job
-            join_job(c5)              # [loss, gradient] summed by the library's own ncclAllReduce
+            try:
+                join_job(c5)          # [loss, gradient] summed by the library's own ncclAllReduce
+                lib_comm = True
+            except Exception:         # noqa: BLE001 - the headline leg has recorded why
+                pass
+        out["collective"] = "libbpltv ncclAllReduce" if lib_comm else ("torch.distributed all_reduce" if world > 1 else "none")
         c5.set_dataset_device(d_t.data_ptr(), d_n.data_ptr(), n, n, c, tstream.cuda_stream)
         for name, Delta, branch in (("loss_only", 0.1, 3), ("gradient", 0.1, 0), ("gradient_reg", 1e-7, 0)):
             eo = bp.eval_opts(bp.pdps_opts(maxiter=iters), force_branch=branch)
@@ -502,6 +518,8 @@ def config5_extra(bp, torch, dist, dev, tstream, world, rank, local, total=1024,
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(tstream)
                 c5.learn_eval_device(LAM, Delta, cg.data_ptr(), eo, stream=tstream.cuda_stream)
+                if world > 1 and not lib_comm:
+                    dist.all_reduce(cg)
                 e1.record(tstream)
                 torch.cuda.synchronize()
                 t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)

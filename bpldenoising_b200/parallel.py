@@ -39,7 +39,14 @@ def join_job(ctx, group=None):
     import torch.distributed as dist
 
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    box = [ctx.comm_unique_id() if rank == 0 else None]
+    box = [None]
+    if rank == 0:
+        try:
+            box[0] = ctx.comm_unique_id()
+        except Exception as e:      # noqa: BLE001 - the other ranks are waiting in the broadcast: tell them
+            box[0] = ("error", f"{type(e).__name__}: {e}")
     dist.broadcast_object_list(box, src=0, group=group)
-    ctx.comm_init(world, rank, box[0])
+    if not isinstance(box[0], (bytes, bytearray)):
+        raise RuntimeError(f"rank 0 could not create the NCCL id: {box[0]}")
+    ctx.comm_init(world, rank, bytes(box[0]))
     return world, rank
