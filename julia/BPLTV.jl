@@ -12,7 +12,8 @@
 # by the equivalent ctypes binding (bpldenoising_b200/_lib.py), which calls the same symbols.
 module BPLTV
 
-export tv_op_learning_function, sumregs_learning_function, sumregs_denoise, denoise, TVDenoise, generate_cost, bpltv_context, set_devices!
+export tv_op_learning_function, sumregs_learning_function, sumregs_denoise, denoise, TVDenoise, generate_cost, bpltv_context, set_devices!,
+       comm_unique_id, comm_init!, comm_destroy!, shard_range
 
 const lib = get(ENV, "BPLTV_LIB", joinpath(@__DIR__, "..", "bpldenoising_b200", "libbpltv.so"))
 
@@ -78,6 +79,26 @@ function bpltv_context()
         ctx[] = h[]
     end
     ctx[]
+end
+
+# ---- one process per GPU (MPI.jl, Distributed.jl): the job's single collective lives in the library (include/bpltv.h) ----
+# rank 0: id = comm_unique_id(); ship the 128 bytes to every rank by your own transport; all ranks: comm_init!(n, r, id).
+# Afterwards tv_op_learning_function / sumregs_learning_function called with THIS rank's block of the data
+# (shard_range) return the loss and gradient of the whole job on every rank (one ncclAllReduce per evaluation).
+function comm_unique_id()
+    id = zeros(UInt8, 128)
+    check(ccall((:bpltv_comm_unique_id, lib), Cint, (Ptr{UInt8},), id))
+    id
+end
+function comm_init!(nranks::Integer, rank::Integer, id::Vector{UInt8})
+    length(devices[]) == 1 || throw(ArgumentError("a communicator joins single-device contexts: set_devices!([gpu]) first"))
+    check(ccall((:bpltv_comm_init, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), bpltv_context(), nranks, rank, id))
+end
+comm_destroy!() = ctx[] == C_NULL ? nothing : check(ccall((:bpltv_comm_destroy, lib), Cint, (Ptr{Cvoid},), ctx[]))
+"first image (1-based) and count of `rank`'s contiguous block of O images: blocks of ceil(O/nranks), as inside the library"
+function shard_range(O::Integer, nranks::Integer, rank::Integer)
+    per = cld(O, nranks); b = min(O, rank * per)
+    (b + 1, min(O, b + per) - b)
 end
 
 lam(x::Real) = (Float64[x;;], 1, 1)
