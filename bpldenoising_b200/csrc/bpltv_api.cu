@@ -477,7 +477,16 @@ static int run_pdps(Dev &d, const Real *f, int M, int N, int O, double alpha_s, 
         // depth when the caller leaves it open (measured, config 4, Gpixel-iter/s T = 2 / 3 / 4): fp64 strict 189 / 183 /
         // 197 and — sustained, where T = 2's HBM traffic runs the chip into its power cap — 182 vs 196; fp64 fast 189 /
         // 206 / 220; fp32 strict 370 / 346 / 331 (its four-pixel stages spill at depth 4); fp32 fast 370 / 444 / 486
-        tdepth = o.tblock > 0 ? o.tblock : env_int("BPLTV_TBLOCK_T", (strict && sizeof(Real) == 4) ? 2 : 4);
+        // Strict fp64 stacks that leave a depth-4 CTA (255 registers: 256 threads per SM) fewer than 160 columns go at
+        // depth 2: 128 images of 256² (110 columns per CTA) 180.6 / 172.3 / 170.2 — the 2(T−1) halo columns and the
+        // pipeline fill weigh more on short ranges.
+        int auto_depth = (strict && sizeof(Real) == 4) ? 2 : 4;
+        if (strict && sizeof(Real) == 8 && tblock_vec<Real>(M)) {
+            const int nthreads = (M / tblock_vec<Real>(M) + 31) / 32 * 32;
+            const long long cols_per_cta = (long long)N * O * nthreads / ((long long)d.sm_count * 256);
+            if (cols_per_cta < 160) auto_depth = 2;
+        }
+        tdepth = o.tblock > 0 ? o.tblock : env_int("BPLTV_TBLOCK_T", auto_depth);
         if (tdepth < 1 || tdepth > 4) return fail(BPLTV_ERR_ARG, "temporal blocking depth must be 1..4 (got %d)", tdepth);
         if (!tblock_vec<Real>(M) || rho)
             return fail(BPLTV_ERR_ARG, "temporally blocked PDPS kernel does not take M=%d (rho=%g)", M, o.rho);

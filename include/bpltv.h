@@ -72,7 +72,8 @@ typedef struct bpltv_pdps_opts {
     int arith;      /* enum bpltv_arith                                     */
     int kernel;     /* enum bpltv_pdps_kernel                               */
     int tblock;     /* temporal blocking depth T of BPLTV_KERNEL_TBLOCK, 2..4
-                       (0 = auto: 4; 2 for strict arithmetic in fp32)          */
+                       (0 = auto: 4; 2 for strict arithmetic in fp32 and for
+                       strict fp64 stacks with few columns per CTA)             */
     int reserved[4];
 } bpltv_pdps_opts;
 
