@@ -225,6 +225,7 @@ struct Dev {
     GradWork grad3;           // gradient_sumregs.cuh
     NdWork *nd = nullptr;     // gradient_nd.cuh (nested-dissection adjoint solver), created on first use
     bool grad_used_nd = false;
+    bool grad_used_band = false; // a banded factorisation ran: its worst backward error is in grad.relres_max (device)
     StepKey steps_key;
     std::vector<unsigned char> steps_host;
     long long launches = 0;
@@ -937,6 +938,7 @@ static int sumregs_learn_eval_impl(bpltv_ctx *ctx, const double *lam, int lm, in
     std::memset(&ctx->stats, 0, sizeof ctx->stats);
     std::vector<std::vector<double>> host(ndev, std::vector<double>(1 + ng, 0.0));
     std::vector<const Real *> us(ndev, nullptr);
+    std::vector<double> relres(ndev, 0.0);
     for (int di = 0; di < ndev; ++di) {
         Dev &d = ctx->devs[di];
         CU_TRY(cudaSetDevice(d.id));
@@ -950,6 +952,9 @@ static int sumregs_learn_eval_impl(bpltv_ctx *ctx, const double *lam, int lm, in
         RC_TRY(sumregs_eval_on_device<Real>(ctx, d, lam, lm, ln, Delta, eo, ug, d.stream, &us[di], d.scalars.as<double>()));
         RC_TRY(allreduce_costgrad(ctx, d.scalars.as<double>(), 1 + ng, d.stream));
         CU_TRY(cudaMemcpyAsync(host[di].data(), d.scalars.p, (1 + ng) * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
+        // worst backward error of the banded adjoint solves (grad_reduce_kernel leaves it in the workspace)
+        if (d.O > 0 && eo.force_branch != 3 && d.grad3.relres_max)
+            CU_TRY(cudaMemcpyAsync(&relres[di], d.grad3.relres_max, sizeof(double), cudaMemcpyDeviceToHost, d.stream));
     }
     for (int di = 0; di < ndev; ++di) {      // second pass: see denoise_impl
         Dev &d = ctx->devs[di];
@@ -964,6 +969,7 @@ static int sumregs_learn_eval_impl(bpltv_ctx *ctx, const double *lam, int lm, in
         CU_TRY(cudaSetDevice(d.id));
         CU_TRY(cudaStreamSynchronize(d.stream));
         cost += host[di][0];
+        ctx->stats.solver_max_relres = std::max(ctx->stats.solver_max_relres, relres[di]);
         for (int k = 0; k < ng; ++k) grad[k] += host[di][1 + k];
         ctx->stats.ms_pdps = std::max<double>(ctx->stats.ms_pdps, ev_ms(d.ev[0], d.ev[1]));
         ctx->stats.ms_cost = std::max<double>(ctx->stats.ms_cost, ev_ms(d.ev[1], d.ev[2]));
@@ -979,6 +985,9 @@ static int sumregs_learn_eval_impl(bpltv_ctx *ctx, const double *lam, int lm, in
     if (!std::isfinite(cost)) return fail(BPLTV_ERR_NUMERIC, "non-finite cost");
     for (int k = 0; k < ng; ++k)
         if (!std::isfinite(grad[k])) return fail(BPLTV_ERR_NUMERIC, "non-finite gradient entry %d", k);
+    if (eo.solver_tol > 0 && !(ctx->stats.solver_max_relres <= eo.solver_tol))
+        return fail(BPLTV_ERR_NUMERIC, "adjoint solve: worst backward error %.3g above the tolerance %.3g", ctx->stats.solver_max_relres,
+                    eo.solver_tol);
     if (cost_out) *cost_out = cost;
     for (int k = 0; k < ng; ++k) grad_out[k] = grad[k];
     return 0;
@@ -1027,6 +1036,7 @@ static int run_tv_gradient(Dev &d, const GradProblem<Real> &gp, cudaStream_t st,
     int solver = gp.solver;
     if (solver == 0) solver = env_int("BPLTV_GRAD_SOLVER", 0);
     d.grad_used_nd = false;
+    d.grad_used_band = false;
     if (solver != 1) {
         if (!d.nd) d.nd = nd_work_create();
         NdProblem np;
@@ -1046,9 +1056,20 @@ static int run_tv_gradient(Dev &d, const GradProblem<Real> &gp, cudaStream_t st,
         lp.alpha[0] = gp.alpha_s; lp.alpha[1] = lp.alpha[2] = 0.0;
         lp.alpha_maps = gp.alpha_map; lp.lm = gp.lm; lp.ln = gp.ln; lp.gamma = gp.gamma; lp.nops = 1;
         const int rc = run_gradient_lu<Real>(d.grad, lp, d.sm_count, d.smem_optin, st, d_grad_out, &d.launches);
+        if (rc == 0) d.grad_used_band = true;
         if (rc != -1) return rc;      // -1: the LU does not take this shape (panels beyond shared memory): Cholesky
     }
-    return run_gradient<Real>(d.grad, gp, d.sm_count, d.smem_optin, st, d_grad_out, &d.launches);
+    const int rc = run_gradient<Real>(d.grad, gp, d.sm_count, d.smem_optin, st, d_grad_out, &d.launches);
+    if (rc == 0) d.grad_used_band = true;
+    return rc;
+}
+
+// worst backward error of the adjoint solves of the last gradient on this device (device pointer) or nullptr
+static const double *relres_of_last_gradient(const Dev &d)
+{
+    if (d.grad_used_nd) return nd_work_relres_max(d.nd);
+    if (d.grad_used_band) return static_cast<const double *>(d.grad.relres_max);
+    return nullptr;
 }
 
 template <typename Real>
@@ -1100,14 +1121,14 @@ static int learn_eval_impl(bpltv_ctx *ctx, const double *lam, int lm, int ln, do
         Dev &d = ctx->devs[di];
         CU_TRY(cudaSetDevice(d.id));
         d.launches = 0;
-        d.grad_used_nd = false;
+        d.grad_used_nd = d.grad_used_band = false;
         RC_TRY(d.scalars.ensure((1 + ng) * sizeof(double)));
         RC_TRY(eval_on_device<Real>(ctx, d, lam, lm, ln, Delta, eo, d.stream, &us[di], d.scalars.as<double>()));
         RC_TRY(allreduce_costgrad(ctx, d.scalars.as<double>(), 1 + ng, d.stream));
         CU_TRY(cudaMemcpyAsync(host[di].data(), d.scalars.p, (1 + ng) * sizeof(double), cudaMemcpyDeviceToHost,
                                d.stream));
-        if (d.grad_used_nd)
-            CU_TRY(cudaMemcpyAsync(&relres[di], nd_work_relres_max(d.nd), sizeof(double), cudaMemcpyDeviceToHost, d.stream));
+        if (relres_of_last_gradient(d))
+            CU_TRY(cudaMemcpyAsync(&relres[di], relres_of_last_gradient(d), sizeof(double), cudaMemcpyDeviceToHost, d.stream));
     }
     for (int di = 0; di < ndev; ++di) {      // second pass: see denoise_impl
         Dev &d = ctx->devs[di];
@@ -1130,7 +1151,7 @@ static int learn_eval_impl(bpltv_ctx *ctx, const double *lam, int lm, int ln, do
         ctx->stats.ms_total = std::max<double>(ctx->stats.ms_total, ev_ms(d.ev[0], d.ev[4]));
         ctx->stats.kernel_launches += d.launches;
         ctx->stats.solver_iterations += d.grad.last_iterations;
-        ctx->stats.solver_max_relres = std::max(ctx->stats.solver_max_relres, d.grad_used_nd ? relres[di] : d.grad.last_relres);
+        ctx->stats.solver_max_relres = std::max(ctx->stats.solver_max_relres, relres[di]);
     }
     ctx->stats.pdps_iterations = eo.pdps.maxiter;
     ctx->stats.pixel_iterations = (long long)plane * ctx->O * eo.pdps.maxiter;
@@ -1140,6 +1161,11 @@ static int learn_eval_impl(bpltv_ctx *ctx, const double *lam, int lm, int ln, do
         if (!std::isfinite(grad[k]))
             return fail(BPLTV_ERR_NUMERIC, "non-finite gradient entry %d (adjoint solve: worst backward error %.3g, tolerance %.3g)", k,
                         ctx->stats.solver_max_relres, eo.solver_tol);
+    // the banded factorisations report their backward error like the nested-dissection solver (which poisons the
+    // gradient on the device): the same tolerance, checked here
+    if (eo.solver_tol > 0 && !(ctx->stats.solver_max_relres <= eo.solver_tol))
+        return fail(BPLTV_ERR_NUMERIC, "adjoint solve: worst backward error %.3g above the tolerance %.3g", ctx->stats.solver_max_relres,
+                    eo.solver_tol);
     *cost_out = cost;
     for (int k = 0; k < ng; ++k) grad_out[k] = grad[k];
     return 0;
@@ -1244,7 +1270,7 @@ static int gradient_impl(bpltv_ctx *ctx, const double *u_host, const double *lam
         Dev &d = ctx->devs[di];
         CU_TRY(cudaSetDevice(d.id));
         d.launches = 0;
-        d.grad_used_nd = false;
+        d.grad_used_nd = d.grad_used_band = false;
         if (d.O == 0) continue;
         cudaStream_t st = d.stream;
         RC_TRY(d.scalars.ensure((1 + ng) * sizeof(double)));
@@ -1263,8 +1289,8 @@ static int gradient_impl(bpltv_ctx *ctx, const double *u_host, const double *lam
         if (rc != 0) return fail(rc, "gradient: %s", d.grad.err.c_str());
         CU_TRY(cudaEventRecord(d.ev[3], st));
         CU_TRY(cudaMemcpyAsync(host[di].data(), d.scalars.as<double>() + 1, ng * sizeof(double), cudaMemcpyDeviceToHost, st));
-        if (d.grad_used_nd)
-            CU_TRY(cudaMemcpyAsync(&relres[di], nd_work_relres_max(d.nd), sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (relres_of_last_gradient(d))
+            CU_TRY(cudaMemcpyAsync(&relres[di], relres_of_last_gradient(d), sizeof(double), cudaMemcpyDeviceToHost, st));
     }
     std::vector<double> grad(ng, 0.0);
     for (int di = 0; di < ndev; ++di) {
@@ -1276,7 +1302,7 @@ static int gradient_impl(bpltv_ctx *ctx, const double *u_host, const double *lam
         ctx->stats.ms_gradient = std::max<double>(ctx->stats.ms_gradient, ev_ms(d.ev[2], d.ev[3]));
         ctx->stats.kernel_launches += d.launches;
         ctx->stats.solver_iterations += d.grad.last_iterations;
-        ctx->stats.solver_max_relres = std::max(ctx->stats.solver_max_relres, d.grad_used_nd ? relres[di] : d.grad.last_relres);
+        ctx->stats.solver_max_relres = std::max(ctx->stats.solver_max_relres, relres[di]);
     }
     ctx->stats.n_devices = ndev;
     for (int k = 0; k < ng; ++k) {
@@ -1285,6 +1311,9 @@ static int gradient_impl(bpltv_ctx *ctx, const double *u_host, const double *lam
                         ctx->stats.solver_max_relres, eo.solver_tol);
         grad_out[k] = grad[k];
     }
+    if (eo.solver_tol > 0 && !(ctx->stats.solver_max_relres <= eo.solver_tol))
+        return fail(BPLTV_ERR_NUMERIC, "adjoint solve: worst backward error %.3g above the tolerance %.3g", ctx->stats.solver_max_relres,
+                    eo.solver_tol);
     return 0;
 }
 

@@ -107,8 +107,8 @@ typedef struct bpltv_stats {
     long long pixel_iterations;  /* M·N·O·iterations of the last call          */
     long long solver_iterations; /* reserved (0)                               */
     long long kernel_launches;   /* CUDA kernels launched by the last call     */
-    double solver_max_relres;    /* worst backward error of the adjoint solve over the images
-                                    (host-pointer entry points, solver 0/2)    */
+    double solver_max_relres;    /* worst backward error of the adjoint solves over the images
+                                    (host-pointer entry points, every solver)  */
     int pdps_kernel_used;        /* enum bpltv_pdps_kernel actually dispatched */
     int n_devices;
     int tblock_depth;            /* PDPS iterations per HBM pass of that kernel (1 unless TBLOCK) */
