@@ -94,3 +94,37 @@ def save_results(params: dict, b, b_data, x, opt_img, log, out_root: Optional[st
         written["png"].append(p)
     written["mean_ssim"], written["mean_psnr"] = mean_ssim, mean_psnr
     return written
+
+
+# ------------------------------------------------------------------------------
+# cost curves (/root/reference/src/BPLDenoising.jl:106-110, :153-157)
+# ------------------------------------------------------------------------------
+def save_cost_curve(dataset_name: str, parameter_range, costs, parameter_range_2=None, out_root: Optional[str] = None) -> dict:
+    """What `generate_cost` / `generate_2d_cost` `@save` (:110 `<name>_cost.jld2` with `parameter_range costs`; :157
+    `<name>_cost_2d.jld2` with `parameter_range_1 parameter_range_2 costs`), under `output/<name>/` like the reference.
+    JLD2 is Julia's own container (an HDF5 dialect written by JLD2.jl) and cannot be produced without Julia, so the
+    variables are written under the reference's names as `.npz` (for this mirror) and as raw little-endian Float64
+    `.bin` files with a `.json` index — the form `julia/cost_curves_to_jld2.jl` turns into the `.jld2` file
+    `generate_cost_plot` / `generate_2d_cost_plot` (:113-126, :160-174) `@load`.  In the Julia deployment the reference's
+    own `@save` line stays and none of this is needed."""
+    import json
+    root = os.path.join(out_root or default_save_prefix, dataset_name)
+    os.makedirs(root, exist_ok=True)
+    two_d = parameter_range_2 is not None
+    stem = os.path.join(root, dataset_name + ("_cost_2d" if two_d else "_cost"))
+    names = (("parameter_range_1", parameter_range), ("parameter_range_2", parameter_range_2), ("costs", costs)) if two_d \
+        else (("parameter_range", parameter_range), ("costs", costs))
+    arrays = {k: np.asarray(v, dtype=np.float64) for k, v in names}
+    if two_d:
+        assert arrays["costs"].shape == (arrays["parameter_range_1"].size, arrays["parameter_range_2"].size)
+    else:
+        assert arrays["costs"].shape == arrays["parameter_range"].shape
+    np.savez(stem + ".npz", **arrays)
+    index = {"jld2": os.path.basename(stem) + ".jld2", "variables": []}
+    for k, a in arrays.items():
+        fn = f"{os.path.basename(stem)}.{k}.bin"
+        a.ravel(order="F").astype("<f8").tofile(os.path.join(root, fn))      # column-major, as Julia reads it
+        index["variables"].append({"name": k, "file": fn, "shape": list(a.shape)})
+    with open(stem + ".json", "w") as fh:
+        json.dump(index, fh, indent=1)
+    return {"npz": stem + ".npz", "index": stem + ".json"}

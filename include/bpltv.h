@@ -107,8 +107,13 @@ typedef struct bpltv_stats {
     long long pixel_iterations;  /* M·N·O·iterations of the last call          */
     long long solver_iterations; /* reserved (0)                               */
     long long kernel_launches;   /* CUDA kernels launched by the last call     */
-    double solver_max_relres;    /* worst backward error of the adjoint solves over the images
-                                    (host-pointer entry points, every solver)  */
+    double solver_max_relres;    /* worst residual of the adjoint solves over the images (host-pointer
+                                    entry points).  Nested dissection (solver 0/2): the normwise
+                                    backward error that solver_tol bounds.  Banded solvers (solver 1,
+                                    sum of regularisers): the relative residual |r|/|b| after the
+                                    last refinement step — informational (with entries up to
+                                    alpha*gamma it is not a backward error); the band LU applies its
+                                    own backward-error test and poisons the gradient with NaN      */
     int pdps_kernel_used;        /* enum bpltv_pdps_kernel actually dispatched */
     int n_devices;
     int tblock_depth;            /* PDPS iterations per HBM pass of that kernel (1 unless TBLOCK) */

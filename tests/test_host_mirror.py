@@ -98,3 +98,26 @@ def test_save_results_writes_the_reference_artefacts(bp, datasets, tmp_path):
     pars = [np.asarray(Image.open(p)) for p in w3["png"] if "_par_" in p]
     assert len(pars) == 3 and pars[2][127, 127] == 255 and pars[1][0, 0] == 0 and pars[0][127, 127] < 255
     assert float(open(w3["quality"]).read().splitlines()[3].split()[1]) == 0.0 and w3["mean_psnr"] > 0
+
+
+def test_cost_curves_are_saved_under_the_reference_names(tmp_path):
+    """generate_cost / generate_2d_cost `@save` (/root/reference/src/BPLDenoising.jl:110, :157): the same variables under
+    the same names, as .npz plus the raw column-major Float64 files julia/cost_curves_to_jld2.jl converts to .jld2."""
+    import json
+    from bpldenoising_b200 import results
+    pr = np.geomspace(1e-3, 1.0, 7)
+    costs = 1.0 / pr
+    w = results.save_cost_curve("cameraman_128_5", pr, costs, out_root=str(tmp_path))
+    z = np.load(w["npz"])
+    assert sorted(z.files) == ["costs", "parameter_range"] and np.array_equal(z["costs"], costs)
+    idx = json.load(open(w["index"]))
+    assert idx["jld2"] == "cameraman_128_5_cost.jld2" and [v["name"] for v in idx["variables"]] == ["parameter_range", "costs"]
+    raw = np.fromfile(tmp_path / "cameraman_128_5" / idx["variables"][1]["file"], dtype="<f8")
+    assert np.array_equal(raw, costs)
+    p1, p2 = np.array([0.1, 0.2, 0.3]), np.array([1.0, 2.0])
+    c2 = np.arange(6.0).reshape(3, 2)
+    w2 = results.save_cost_curve("circle_128_10", p1, c2, parameter_range_2=p2, out_root=str(tmp_path))
+    idx2 = json.load(open(w2["index"]))
+    assert idx2["jld2"] == "circle_128_10_cost_2d.jld2"
+    raw2 = np.fromfile(tmp_path / "circle_128_10" / idx2["variables"][2]["file"], dtype="<f8")
+    assert np.array_equal(raw2.reshape((3, 2), order="F"), c2)          # column-major on disk

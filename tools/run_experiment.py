@@ -6,6 +6,8 @@
     python tools/run_experiment.py scalar_bilevel_sumregs_learn --dataset_name cameraman_128_5
     python tools/run_experiment.py patch_bilevel_sumregs_learn  --dataset_name cameraman_128_5
     python tools/run_experiment.py validate_tv_parameter --parameter 0.07 --dataset_name faces_val_128_10
+    python tools/run_experiment.py generate_scalar_tv_cost --dataset_name cameraman_128_5 --range 1e-3 1.0 64
+    python tools/run_experiment.py generate_2d_tv_cost     --dataset_name circle_128_10   --range 1e-3 1.0 16
 
 Each follows /root/reference/src/BPLDenoising.jl (:325-344, :359-376, :432-451, :464-481, :381-415): load the
 dataset (filelist.txt + PNG pairs, Datasets.jl:54-65), take `num_samples` images, run the trust-region
@@ -28,7 +30,9 @@ def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("experiment", choices=["scalar_bilevel_tv_learn", "patch_bilevel_tv_learn",
                                            "scalar_bilevel_sumregs_learn", "patch_bilevel_sumregs_learn",
-                                           "validate_tv_parameter"])
+                                           "validate_tv_parameter", "generate_scalar_tv_cost", "generate_2d_tv_cost"])
+    ap.add_argument("--range", nargs=3, type=float, default=[1e-3, 1.0, 64], metavar=("FIRST", "LAST", "COUNT"),
+                    help="cost curves: geometric parameter range (the reference's callers pass their own range)")
     ap.add_argument("--dataset_name", default="cameraman_128_5")          # default_params (:306-314)
     ap.add_argument("--datasets_dir", default="BPLDenoising/datasets/")   # Datasets.jl:9
     ap.add_argument("--num_samples", type=int, default=1)
@@ -50,6 +54,18 @@ def main(argv=None):
             return 0
         k = a.num_samples
         data = (np.asfortranarray(b[:, :, :k]), np.asfortranarray(b_noisy[:, :, :k]))
+        if a.experiment in ("generate_scalar_tv_cost", "generate_2d_tv_cost"):
+            # generate_cost / generate_2d_cost (:92-111, :136-158): the whole range as one batched launch, saved under the
+            # reference's variable names (results.save_cost_curve)
+            pr = np.geomspace(a.range[0], a.range[1], int(a.range[2]))
+            if a.experiment == "generate_scalar_tv_cost":
+                costs = bp.generate_scalar_tv_cost(data, pr, num_samples=k, ctx=ctx)
+                w = results.save_cost_curve(name, pr, costs, out_root=a.output)
+            else:
+                costs = bp.generate_2d_tv_cost(data, pr, pr, num_samples=k, ctx=ctx)
+                w = results.save_cost_curve(name, pr, costs, parameter_range_2=pr, out_root=a.output)
+            print(f"{costs.size} costs, minimum {float(np.min(costs)):.6f} → {w['npz']}")
+            return 0
         run = {"scalar_bilevel_tv_learn": (trbox.scalar_bilevel_tv_learn, "tv_optimal_parameter_scalar_"),
                "patch_bilevel_tv_learn": (trbox.patch_bilevel_tv_learn, "tv_optimal_parameter_(2, 2)_"),
                "scalar_bilevel_sumregs_learn": (trbox.scalar_bilevel_sumregs_learn, "sumregs_optimal_parameter_scalar_"),
