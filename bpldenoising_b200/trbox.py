@@ -18,9 +18,13 @@ no image arithmetic.  Quirks of the reference are kept, each marked QUIRK:
   predicted reduction is negative (:247-249), and the run stops only when a *logged*
   iteration sees Δ < tol (BilevelVisualise.jl:246-248).
 
-Not restated bit-for-bit (cannot be checked without Julia): `LinearOperators.LBFGSOperator`
-(here: standard forward L-BFGS, memory 5, Barzilai–Borwein initial scaling) and
-`Krylov.cg_lanczos` (here: an exact dense solve of the ≤ tens-of-unknowns operator).
+The two third-party pieces (un-vendored packages, `/root/reference/Project.toml`) are restated from their published
+algorithms, not bit for bit (nothing to check them against without Julia):
+* `LinearOperators.LBFGSOperator(n)` — forward (Hessian) L-BFGS, memory 5, initial matrix (yᵀy / yᵀs)·I of the newest
+  pair (`scaling = true`), pairs with yᵀs ≤ 1e-20 skipped: `LBFGSOperator` below (the same operator; the package keeps
+  the compact vectors a_k, b_k, this class unrolls the recursion);
+* `Krylov.cg_lanczos(B, b)` — the conjugate-gradient iterates with the package's default stopping rule
+  ‖r‖ ≤ √eps + √eps·‖b‖ and ≤ 2n products: `cg_solve` below.
 """
 from __future__ import annotations
 
@@ -104,6 +108,37 @@ class LBFGSOperator:
         return np.column_stack([self.mul(e) for e in np.eye(self.n)])
 
 
+def cg_solve(mul: Callable[[np.ndarray], np.ndarray], b: np.ndarray) -> np.ndarray:
+    """`pn, ks = Krylov.cg_lanczos(B, -gx[:])` (TRBox.jl:136).  CG-Lanczos produces the conjugate-gradient iterates (it is CG
+    written on the Lanczos basis) and stops, with Krylov.jl's defaults, at ‖r_k‖ ≤ atol + rtol·‖b‖, atol = rtol = √eps, after
+    at most 2n products — so the reference's Newton step is an INEXACT solve at the 1e-8 level, which an exact dense solve
+    would not reproduce.  Here: plain CG from x₀ = 0 with that stopping rule (the same iterates in exact arithmetic)."""
+    n = b.size
+    tol = math.sqrt(EPS)
+    x = np.zeros(n)
+    r = b.astype(np.float64).copy()
+    bnorm = float(np.linalg.norm(r))
+    if bnorm == 0.0:
+        return x
+    eps_stop = tol + tol * bnorm
+    pdir = r.copy()
+    rr = float(r @ r)
+    for _ in range(2 * n):
+        if math.sqrt(rr) <= eps_stop:
+            break
+        Ap = mul(pdir)
+        curv = float(pdir @ Ap)
+        if curv <= 0.0:                      # cg_lanczos stops on non-positive curvature; L-BFGS operators are SPD
+            break
+        a = rr / curv
+        x += a * pdir
+        r -= a * Ap
+        rr_new = float(r @ r)
+        pdir = r + (rr_new / rr) * pdir
+        rr = rr_new
+    return x
+
+
 # ---- auxiliary functions (TRBox.jl:59-186) ----------------------------------------
 def get_bounds(x, Delta):  # :160-164
     lb = np.maximum(-Delta, EPS - np.asarray(x, dtype=np.float64))
@@ -142,7 +177,7 @@ def dogleg_box(x, gx, B, Delta):
         return float(p + t * (pn - p))
     # array, :99-114
     g = np.ravel(gx, order="F")
-    pn = np.linalg.solve(B.dense(), -g).reshape(np.shape(gx), order="F")  # newton_step (:135-141)
+    pn = cg_solve(B.mul, -g).reshape(np.shape(gx), order="F")  # newton_step (:135-141)
     if in_bounds(lb, Delta, pn):
         return pn
     p = (-(np.linalg.norm(g) ** 2 / float(g @ B.mul(g))) * g).reshape(np.shape(gx), order="F")  # :143-146

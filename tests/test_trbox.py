@@ -108,3 +108,27 @@ def test_run_experiment_cli_reproduces_the_artefacts(tmp_path, datasets):
     assert f"{stem}.txt" in files and f"{stem}_quality.txt" in files and f"{stem}_reco_1.png" in files
     q = open(out / "cameraman_128_5" / f"{stem}_quality.txt").read().splitlines()
     assert len(q) == 3 and float(q[1].split()[4]) > float(q[1].split()[2])    # out_psnr > orig_psnr
+
+
+def test_cg_solve_is_the_inexact_newton_step_of_cg_lanczos():
+    """newton_step (TRBox.jl:135-141) solves B pn = −g with Krylov.cg_lanczos: CG iterates, stopped at
+    ‖r‖ ≤ √eps + √eps·‖b‖.  The restatement meets that bound, agrees with the exact solve to the same level and stops
+    within 2n products of an L-BFGS operator holding several pairs."""
+    from bpldenoising_b200 import trbox
+    rng = np.random.default_rng(4)
+    n = 12
+    B = trbox.LBFGSOperator(n)
+    H = rng.standard_normal((n, n)); H = H @ H.T + n * np.eye(n)
+    for _ in range(7):                                   # more pairs than the memory holds
+        s = rng.standard_normal(n)
+        B.push(s, H @ s)
+    D = B.dense()
+    assert np.allclose(D, D.T, rtol=1e-12, atol=1e-12) and np.all(np.linalg.eigvalsh(0.5 * (D + D.T)) > 0)
+    calls = []
+    g = rng.standard_normal(n)
+    x = trbox.cg_solve(lambda v: (calls.append(1), B.mul(v))[1], -g)
+    tol = np.sqrt(np.finfo(float).eps)
+    assert np.linalg.norm(D @ x + g) <= 1.01 * (tol + tol * np.linalg.norm(g)) and len(calls) <= 2 * n
+    exact = np.linalg.solve(D, -g)
+    assert np.linalg.norm(x - exact) <= 1e-6 * np.linalg.norm(exact)
+    assert np.array_equal(trbox.cg_solve(B.mul, np.zeros(n)), np.zeros(n))
