@@ -27,6 +27,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "halo_async.cuh"
 
 namespace bpltv {
 
@@ -62,8 +63,17 @@ static __device__ __forceinline__ void st2(Real *p, Real a, Real b)
     *reinterpret_cast<typename Vec2T<Real>::type *>(p) = v;
 }
 
+// bytes of the planes of one CTA, and of the two halo mbarriers behind them (ASYNC kernels)
+template <typename Real>
+static __host__ __device__ __forceinline__ size_t resident_plane_bytes(int NC, int M)
+{
+    return (((size_t)(3 * NC + 2) * M * sizeof(Real)) + 15) & ~(size_t)15;
+}
+
 // KC = column slots per thread (each slot = 2 consecutive rows of one column)
-template <typename Real, int KC, bool MAP, bool STRICT>
+// ASYNC: halo columns travel by st.async + mbarrier (above) and the two phases of an iteration are separated by
+// CTA barriers; otherwise by plain DSMEM stores and two cluster barriers per iteration (round 1).
+template <typename Real, int KC, bool MAP, bool STRICT, bool ASYNC>
 __global__ void __launch_bounds__(RES_THREADS, 1) pdps_resident_kernel(const ResidentArgs<Real> a)
 {
 #ifdef BPLTV_EMU
@@ -87,6 +97,12 @@ __global__ void __launch_bounds__(RES_THREADS, 1) pdps_resident_kernel(const Res
     // neighbours' planes through DSMEM
     Real *xb_left = rank > 0 ? cluster.map_shared_rank(xbp, rank - 1) : nullptr;        // their right halo
     Real *y2_right = rank + 1 < CS ? cluster.map_shared_rank(y2p, rank + 1) : nullptr;  // their left halo
+    // ASYNC: hbar[0] counts the x̄ halo column arriving from the right neighbour, hbar[1] the y2 halo column from the left
+    unsigned long long *hbar = reinterpret_cast<unsigned long long *>(smem_raw + resident_plane_bytes<Real>(NC, M));
+    unsigned long long *hbar_left = (ASYNC && rank > 0) ? cluster.map_shared_rank(hbar, rank - 1) : nullptr;       // its [0]
+    unsigned long long *hbar_right = (ASYNC && rank + 1 < CS) ? cluster.map_shared_rank(hbar, rank + 1) : nullptr;  // its [1]
+    const unsigned colbytes = (unsigned)(M * sizeof(Real));
+    if (ASYNC && threadIdx.x == 0) { halo_bar_init(hbar); halo_bar_init(hbar + 1); }
 
     const int tpc = M >> 1;                 // threads per column (2 rows each)
     const int CG = blockDim.x / tpc;        // column groups
@@ -119,11 +135,20 @@ __global__ void __launch_bounds__(RES_THREADS, 1) pdps_resident_kernel(const Res
             }
         }
     }
-    cluster.sync();  // planes zeroed everywhere before anyone pushes into a halo
+    cluster.sync();  // planes zeroed (and the halo mbarriers initialised) everywhere before anyone pushes into a halo
 
     for (int it = 0; it < a.maxiter; ++it) {
         const StepConsts<Real> sc = a.steps[it];
         Real xb[KC][2], y1o[KC][2], y2o[KC][2];
+        if (ASYNC) {
+            // y2 of the column left of this CTA, sent by the left neighbour in phase B of the previous iteration
+            if (hbar_left && it > 0) halo_wait(hbar + 1, it - 1, colbytes);
+            // this iteration's phases of both mbarriers (their previous phases are complete: thread 0 waited on them)
+            if (threadIdx.x == 0) {
+                if (hbar_right) halo_bar_arm(hbar, colbytes);
+                if (hbar_left) halo_bar_arm(hbar + 1, colbytes);
+            }
+        }
         // ---- phase A: x ← prox, x̄ ← over-relaxation ----------------------------------
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
@@ -148,11 +173,18 @@ __global__ void __launch_bounds__(RES_THREADS, 1) pdps_resident_kernel(const Res
             x[k][0] = xn0; x[k][1] = xn1;
             if (valid) {
                 st2(xbp + (size_t)c * M + r0, xb[k][0], xb[k][1]);
-                if (c == 0 && xb_left)    // first local column: the left CTA needs it as x̄(:, its NC)
-                    st2(xb_left + (size_t)NC * M + r0, xb[k][0], xb[k][1]);
+                if (c == 0 && xb_left) {  // first local column: the left CTA needs it as x̄(:, its NC)
+                    if (ASYNC) halo_push2(xb_left + (size_t)NC * M + r0, xb[k][0], xb[k][1], hbar_left);
+                    else st2(xb_left + (size_t)NC * M + r0, xb[k][0], xb[k][1]);
+                }
             }
         }
-        cluster.sync();
+        if (ASYNC) {
+            __syncthreads();                                      // x̄ of this CTA's own columns
+            if (hbar_right) halo_wait(hbar, it, colbytes);        // x̄ of the column right of it
+        } else {
+            cluster.sync();
+        }
         // ---- phase B: y ← P_λ(y + σ∇x̄) ---------------------------------------------------
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
@@ -190,12 +222,17 @@ __global__ void __launch_bounds__(RES_THREADS, 1) pdps_resident_kernel(const Res
             if (valid) {
                 st2(py1, v1, w1);
                 st2(py2, v2, w2);
-                if (c == NC - 1 && y2_right)    // last local column: the right CTA needs it as y2(:, c0-1)
-                    st2(y2_right + r0, v2, w2);
+                if (c == NC - 1 && y2_right) {  // last local column: the right CTA needs it as y2(:, c0-1)
+                    if (ASYNC) halo_push2(y2_right + r0, v2, w2, hbar_right + 1);
+                    else st2(y2_right + r0, v2, w2);
+                }
             }
         }
-        cluster.sync();
+        if (ASYNC) __syncthreads();                               // the duals of this CTA's own columns
+        else cluster.sync();
     }
+    // nothing may still be in flight towards this CTA's shared memory when it exits
+    if (ASYNC && hbar_left && a.maxiter > 0) halo_wait(hbar + 1, a.maxiter - 1, colbytes);
 
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
@@ -442,7 +479,7 @@ static inline ResidentPlan resident_plan(size_t smem_optin, int M, int N, int cs
         if ((CS - 1) * NC >= N) continue;              // every rank must own at least one column
         const int KC = (NC + CG - 1) / CG;
         if (KC > 4) continue;
-        const size_t smem = (size_t)(3 * NC + 2) * M * sizeof(Real);
+        const size_t smem = resident_plane_bytes<Real>(NC, M) + 16;      // planes + the two halo mbarriers
         if (smem > smem_optin) continue;
         p.ok = true; p.CS = CS; p.NC = NC; p.KC = KC <= 1 ? 1 : (KC <= 2 ? 2 : 4); p.smem = smem;
         return p;
@@ -550,8 +587,16 @@ static inline cudaError_t launch_resident_kc(const ResidentArgs<Real> &a, const 
                                              cudaStream_t st)
 {
     void (*fn)(const ResidentArgs<Real>);
-    if (map) fn = strict ? pdps_resident_kernel<Real, KC, true, true> : pdps_resident_kernel<Real, KC, true, false>;
-    else fn = strict ? pdps_resident_kernel<Real, KC, false, true> : pdps_resident_kernel<Real, KC, false, false>;
+    // halo exchange by st.async + mbarrier (default) or by DSMEM stores + two cluster barriers per iteration (BPLTV_RESIDENT_ASYNC=0)
+    const char *as_env = bpltv::env_get("BPLTV_RESIDENT_ASYNC");
+    const bool async = as_env && *as_env ? atoi(as_env) != 0 : true;
+    if (async) {
+        if (map) fn = strict ? pdps_resident_kernel<Real, KC, true, true, true> : pdps_resident_kernel<Real, KC, true, false, true>;
+        else fn = strict ? pdps_resident_kernel<Real, KC, false, true, true> : pdps_resident_kernel<Real, KC, false, false, true>;
+    } else {
+        if (map) fn = strict ? pdps_resident_kernel<Real, KC, true, true, false> : pdps_resident_kernel<Real, KC, true, false, false>;
+        else fn = strict ? pdps_resident_kernel<Real, KC, false, true, false> : pdps_resident_kernel<Real, KC, false, false, false>;
+    }
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return e;
     if (p.CS > 8) {
@@ -594,7 +639,10 @@ static inline cudaError_t launch_resident(ResidentArgs<Real> a, size_t smem_opti
     // cluster barriers give back, in fp32 the arithmetic is cheap enough to win.  Hence: fp32 single-wave batches by
     // default; BPLTV_RESIDENT_TB=1 forces it for every precision, =0 disables it.
     const char *tb_env = bpltv::env_get("BPLTV_RESIDENT_TB");
-    const bool tb_on = tb_env && *tb_env ? atoi(tb_env) != 0 : (sizeof(Real) == 4 && a.O <= 8);
+    // Round 2, later: with the halo exchange by st.async + mbarrier kernel B itself went 7.52 → 4.99 ms (fp64) and 6.24 →
+    // 3.32 ms (fp32) for one image and beats the blocked variant (8.21 / 5.44 ms) everywhere: the blocked kernel is
+    // opt-in only (BPLTV_RESIDENT_TB=1).
+    const bool tb_on = tb_env && *tb_env ? atoi(tb_env) != 0 : false;
     if (tb_on && a.maxiter >= 4) {
         const cudaError_t etb = launch_resident_tb<Real>(a, smem_optin, map, strict, cs_cap, st);
         if (etb == cudaSuccess) return etb;

@@ -21,6 +21,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "halo_async.cuh"
 
 namespace bpltv {
 
@@ -116,9 +117,13 @@ __global__ void __launch_bounds__(256) sumregs_dual_kernel(const SumRegsArgs<Rea
 // x and f (and the three λ values of a map) stay in registers, x̄ and the six dual planes in shared memory
 // with the halo columns their stencils need: x̄ ±1 column, y[1] (forward, component 2) one to the left,
 // y[3] (backward, component 2) one to the right, y[5] (centred, component 2) both.  Owners PUSH their
-// boundary columns into the neighbours' halo slots through distributed shared memory; two cluster
-// barriers per iteration order the pushes against the reads (primal phase reads y / writes x̄, dual phase
-// reads x̄ / writes y).  Same operations in the same order as the streaming kernels: bit-identical.
+// boundary columns into the neighbours' halo slots through distributed shared memory.  Round 2: the pushes are
+// `st.async` stores counted on mbarriers of the RECEIVER (halo_async.cuh) — four per CTA: what the left / the right
+// neighbour sends in the primal phase (one x̄ column each) and in the dual phase (two dual columns each) — and the two
+// phases of an iteration are separated by CTA barriers; round 1's two cluster barriers per iteration (a GPU-scope memory
+// fence each) are gone.  The readers of a halo column are the threads of this CTA's first / last column, and they are
+// the ones that send the columns the neighbour waits for before it overwrites that halo: no slot is double-buffered.
+// Same operations in the same order as the streaming kernels: bit-identical.
 // ---------------------------------------------------------------------------
 constexpr int SRR_THREADS = 512;
 
@@ -131,6 +136,13 @@ struct SumRegsResArgs {
     Real alpha[3];
     int maxiter, M, N, O, init_mode, NC;
 };
+
+// bytes of the planes of one CTA (the four halo mbarriers follow them)
+template <typename Real>
+static __host__ __device__ __forceinline__ size_t sumregs_resident_plane_bytes(int NC, int M)
+{
+    return (((size_t)(7 * NC + 6) * M * sizeof(Real)) + 15) & ~(size_t)15;
+}
 
 template <typename Real, int KP, bool MAP, bool STRICT>
 __global__ void __launch_bounds__(SRR_THREADS, 1) sumregs_resident_kernel(const SumRegsResArgs<Real> a)
@@ -167,6 +179,15 @@ __global__ void __launch_bounds__(SRR_THREADS, 1) sumregs_resident_kernel(const 
     Real *y3_l = rank > 0 ? cluster.map_shared_rank(y3, rank - 1) : nullptr;
     Real *y5_l = rank > 0 ? cluster.map_shared_rank(y5, rank - 1) : nullptr;
     Real *y5_r = rank + 1 < CS ? cluster.map_shared_rank(y5, rank + 1) : nullptr;
+    // mbarriers behind the planes: [0] primal-phase bytes from the left neighbour, [1] from the right, [2] dual-phase
+    // bytes from the left, [3] from the right
+    unsigned long long *hbar = reinterpret_cast<unsigned long long *>(srr_smem + sumregs_resident_plane_bytes<Real>(NC, M));
+    unsigned long long *hbar_l = rank > 0 ? cluster.map_shared_rank(hbar, rank - 1) : nullptr;        // I am its RIGHT neighbour: [1], [3]
+    unsigned long long *hbar_r = rank + 1 < CS ? cluster.map_shared_rank(hbar, rank + 1) : nullptr;   // I am its LEFT neighbour: [0], [2]
+    const bool has_l = rank > 0, has_r = rank + 1 < CS;
+    const unsigned colbytes = (unsigned)(M * sizeof(Real));
+    if (threadIdx.x == 0)
+        for (int b = 0; b < 4; ++b) halo_bar_init(hbar + b);
 
     const size_t plane = (size_t)M * N;
     const size_t img = (size_t)o * plane;
@@ -191,11 +212,20 @@ __global__ void __launch_bounds__(SRR_THREADS, 1) sumregs_resident_kernel(const 
             if (MAP) { al[k][0] = a.amap[q]; al[k][1] = a.amap[plane + q]; al[k][2] = a.amap[2 * plane + q]; }
         }
     }
-    cluster.sync();   // planes zeroed everywhere before anyone pushes into a halo
+    cluster.sync();   // planes zeroed and mbarriers initialised everywhere before anyone pushes into a halo
 
     const Real z = (Real)0, half = (Real)0.5;
     for (int it = 0; it < a.maxiter; ++it) {
         const StepConsts<Real> sc = a.steps[it];
+        // the neighbours' dual columns of the previous iteration; then this iteration's phases of the four mbarriers
+        if (it > 0) {
+            if (has_l) halo_wait(hbar + 2, it - 1, 2 * colbytes);
+            if (has_r) halo_wait(hbar + 3, it - 1, 2 * colbytes);
+        }
+        if (threadIdx.x == 0) {
+            if (has_l) { halo_bar_arm(hbar + 0, colbytes); halo_bar_arm(hbar + 2, 2 * colbytes); }
+            if (has_r) { halo_bar_arm(hbar + 1, colbytes); halo_bar_arm(hbar + 3, 2 * colbytes); }
+        }
         // ---- primal: x ← prox, x̄ ← over-relaxation (reads the duals, writes x̄) ----
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
@@ -222,10 +252,12 @@ __global__ void __launch_bounds__(SRR_THREADS, 1) sumregs_resident_kernel(const 
             }
             x[k] = xn;
             xb[p1] = xbar;
-            if (first && xb_l) xb_l[(NC + 1) * M + p0] = xbar;        // the left CTA's right halo (first column: p0 = row)
-            if (last && xb_r) xb_r[p0 - (nc - 1) * M] = xbar;         // the right CTA's left halo
+            if (first && xb_l) halo_push1(xb_l + (NC + 1) * M + p0, xbar, hbar_l + 1);        // the left CTA's right halo (first column: p0 = row)
+            if (last && xb_r) halo_push1(xb_r + (p0 - (nc - 1) * M), xbar, hbar_r + 0);        // the right CTA's left halo
         }
-        cluster.sync();
+        __syncthreads();                                      // x̄ of this CTA's own columns
+        if (has_l) halo_wait(hbar + 0, it, colbytes);         // x̄ of the columns next to them
+        if (has_r) halo_wait(hbar + 1, it, colbytes);
         // ---- dual: y_k ← P_{α_k}(y_k + σ∇_k x̄) (reads x̄, writes the duals) ----
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
@@ -247,14 +279,19 @@ __global__ void __launch_bounds__(SRR_THREADS, 1) sumregs_resident_kernel(const 
             const Real alk[3] = {al[k][0], al[k][1], al[k][2]};
             dual_update_n<Real, STRICT, 3>(v1, v2, d1, d2, alk, sc);    // the three operators' projection chains interleave
             y0[p0] = v1[0]; y1[p1] = v2[0];
-            if (last && y1_r) y1_r[p0 - (nc - 1) * M] = v2[0];                    // forward, component 2: the right CTA reads column c0−1
+            if (last && y1_r) halo_push1(y1_r + (p0 - (nc - 1) * M), v2[0], hbar_r + 2);      // forward, component 2: the right CTA reads column c0−1
             y2[p0] = v1[1]; y3[p0] = v2[1];
-            if (first && y3_l) y3_l[NC * M + p0] = v2[1];                // backward, component 2: the left CTA reads column c0+NC
+            if (first && y3_l) halo_push1(y3_l + NC * M + p0, v2[1], hbar_l + 3);            // backward, component 2: the left CTA reads column c0+NC
             y4[p0] = v1[2]; y5[p1] = v2[2];
-            if (first && y5_l) y5_l[(NC + 1) * M + p0] = v2[2];          // centred, component 2: both neighbours
-            if (last && y5_r) y5_r[p0 - (nc - 1) * M] = v2[2];
+            if (first && y5_l) halo_push1(y5_l + (NC + 1) * M + p0, v2[2], hbar_l + 3);      // centred, component 2: both neighbours
+            if (last && y5_r) halo_push1(y5_r + (p0 - (nc - 1) * M), v2[2], hbar_r + 2);
         }
-        cluster.sync();
+        __syncthreads();                                      // the duals of this CTA's own columns
+    }
+    // nothing may still be in flight towards this CTA's shared memory when it exits
+    if (a.maxiter > 0) {
+        if (has_l) halo_wait(hbar + 2, a.maxiter - 1, 2 * colbytes);
+        if (has_r) halo_wait(hbar + 3, a.maxiter - 1, 2 * colbytes);
     }
 #pragma unroll
     for (int k = 0; k < KP; ++k) {
@@ -281,7 +318,7 @@ static inline SumRegsResPlan sumregs_resident_plan(size_t smem_optin, int M, int
         if ((CS - 1) * NC >= N) continue;                 // every rank owns at least one column
         const int KP = (NC * M + SRR_THREADS - 1) / SRR_THREADS;
         if (KP > 8) continue;
-        const size_t smem = (size_t)(7 * NC + 6) * M * sizeof(Real);
+        const size_t smem = sumregs_resident_plane_bytes<Real>(NC, M) + 32;     // planes + four halo mbarriers
         if (smem > smem_optin) continue;
         p.ok = true; p.CS = CS; p.NC = NC; p.KP = KP <= 1 ? 1 : (KP <= 2 ? 2 : (KP <= 4 ? 4 : 8)); p.smem = smem;
         return p;

@@ -30,6 +30,9 @@ static std::vector<StepConsts<Real>> steps(int maxiter, double tau0, double sigm
     return h;
 }
 
+static int g_async = 1;
+extern "C" void emu_resident_set_async(int on) { g_async = on; }
+
 template <typename Real>
 static int run(int M, int N, int O, int CS, int threads, int maxiter, int strict, const double *f_in, double alpha_s,
                const double *amap_in, double *u_out)
@@ -48,11 +51,18 @@ static int run(int M, int N, int O, int CS, int threads, int maxiter, int strict
     a.f = f.data(); a.u_out = u.data(); a.alpha_map = amap_in ? amap.data() : nullptr; a.steps = st.data();
     a.maxiter = maxiter; a.M = M; a.N = N; a.O = O; a.init_mode = 0; a.NC = NC; a.alpha_s = (Real)alpha_s;
     a.bm = BatchMap<Real>();
-    const size_t smem_doubles = ((size_t)(3 * NC + 2) * M * sizeof(Real) + 7) / 8;
-    emu::launch(dim3((unsigned)(O * CS)), threads, [&] {
-        if (amap_in) { if (strict) pdps_resident_kernel<Real, 4, true, true>(a); else pdps_resident_kernel<Real, 4, true, false>(a); }
-        else { if (strict) pdps_resident_kernel<Real, 4, false, true>(a); else pdps_resident_kernel<Real, 4, false, false>(a); }
-    }, smem_doubles, CS);
+    const size_t smem_doubles = (resident_plane_bytes<Real>(NC, M) + 16 + 7) / 8;      // planes + the two halo mbarriers
+    if (g_async) {      // halo columns by (emulated) st.async + mbarrier, CTA barriers between the phases
+        emu::launch(dim3((unsigned)(O * CS)), threads, [&] {
+            if (amap_in) { if (strict) pdps_resident_kernel<Real, 4, true, true, true>(a); else pdps_resident_kernel<Real, 4, true, false, true>(a); }
+            else { if (strict) pdps_resident_kernel<Real, 4, false, true, true>(a); else pdps_resident_kernel<Real, 4, false, false, true>(a); }
+        }, smem_doubles, CS);
+    } else {            // plain DSMEM stores + two cluster barriers per iteration
+        emu::launch(dim3((unsigned)(O * CS)), threads, [&] {
+            if (amap_in) { if (strict) pdps_resident_kernel<Real, 4, true, true, false>(a); else pdps_resident_kernel<Real, 4, true, false, false>(a); }
+            else { if (strict) pdps_resident_kernel<Real, 4, false, true, false>(a); else pdps_resident_kernel<Real, 4, false, false, false>(a); }
+        }, smem_doubles, CS);
+    }
     for (size_t k = 0; k < n; ++k) u_out[k] = (double)u[k];
     return 0;
 }

@@ -47,7 +47,7 @@ static int run(int M, int N, int O, int CS, int threads, int maxiter, int strict
     a.f = f.data(); a.u_out = u.data(); a.amap = amap_in ? amap.data() : nullptr; a.steps = st.data();
     for (int k = 0; k < 3; ++k) a.alpha[k] = (Real)(alpha3 ? alpha3[k] : 0.0);
     a.maxiter = maxiter; a.M = M; a.N = N; a.O = O; a.init_mode = init_mode; a.NC = NC;
-    const size_t smem_doubles = ((size_t)(7 * NC + 6) * M * sizeof(Real) + 7) / 8;
+    const size_t smem_doubles = (sumregs_resident_plane_bytes<Real>(NC, M) + 32 + 7) / 8;      // planes + four halo mbarriers
     emu::launch(dim3((unsigned)(O * CS)), threads, [&] {
         if (amap_in) { if (strict) sumregs_resident_kernel<Real, 8, true, true>(a); else sumregs_resident_kernel<Real, 8, true, false>(a); }
         else { if (strict) sumregs_resident_kernel<Real, 8, false, true>(a); else sumregs_resident_kernel<Real, 8, false, false>(a); }

@@ -47,8 +47,13 @@ def _run(L, f, alpha, cs, prec=64, strict=1, maxiter=30, threads=64):
     return u
 
 
+@pytest.mark.parametrize("async_halo", [1, 0])
 @pytest.mark.parametrize("shape", [(16, 13, 2), (8, 21, 1), (32, 6, 1)])
-def test_kernel_b_is_bit_identical_for_every_cluster_size(lib, shape):
+def test_kernel_b_is_bit_identical_for_every_cluster_size(lib, shape, async_halo):
+    """Both halo schemes of kernel B: async_halo = 1 — boundary columns sent with (emulated) st.async, counted on an
+    mbarrier of the receiver, CTA barriers between the phases (the default on the GPU); 0 — plain DSMEM stores and two
+    cluster barriers per iteration."""
+    lib.emu_resident_set_async(async_halo)
     M, N, O = shape
     rng = np.random.default_rng(M * 17 + N)
     f = np.asfortranarray(np.round(rng.uniform(0, 1, shape) * 255) / 255)

@@ -315,7 +315,7 @@ def test_config4_full_size_is_bit_identical_to_the_oracle_pins(bp, ctx, ctx32):
 
 
 def test_temporally_blocked_resident_kernel_is_bit_identical(bp, ctx, ctx32, oracle, datasets):
-    """pdps_resident_tb_kernel (two iterations per halo exchange; default for fp32, BPLTV_RESIDENT_TB=1 forces it): the
+    """pdps_resident_tb_kernel (two iterations per halo exchange; opt-in, BPLTV_RESIDENT_TB=1): the
     same bits as the oracle in fp64 and fp32, odd and even iteration counts, scalar λ and λ-map, 1 and 10 images."""
     import os
     t, f = datasets["faces_train_128_10"]
@@ -356,3 +356,26 @@ def test_projection_scale_chain_equals_the_ieee_operations(bp, ctx, ctx32, prec)
         for seed in (1, 2, 3):
             r = c.selftest(3, span, seed=seed)
             assert r["took"] >= span - 2 * 119 and r["mismatches"] == 0, (seed, r)    # two guarded significands per binade
+
+
+def test_resident_kernel_halo_schemes_agree(bp, ctx, ctx32, oracle, datasets, monkeypatch):
+    """Kernel B exchanges its halo columns by st.async + mbarrier (default; csrc/halo_async.cuh) or, with
+    BPLTV_RESIDENT_ASYNC=0, by DSMEM stores and two cluster barriers per iteration (round 1): both bit-identical to the
+    oracle — 1, 4 and 10 images (16- and 8-CTA clusters), λ-map, fp32, and a ragged shape whose last rank owns fewer columns."""
+    t, f = datasets["faces_train_128_10"]
+    x = np.array([[0.05, 0.1], [0.08, 0.02]])
+    am = oracle.patch_upsample(x, 128, 128)
+    fr = np.asfortranarray(f[:64, :45, :3])
+    for mode in ("1", "0"):
+        monkeypatch.setenv("BPLTV_RESIDENT_ASYNC", mode)
+        bp.reload_env()
+        for O in (1, 4, 10):
+            fo = np.asfortranarray(f[:, :, :O])
+            o = bp.pdps_opts(maxiter=257, kernel=bp.KERNEL_RESIDENT)
+            assert np.array_equal(ctx.denoise(fo, 0.08, o), oracle.pdps(fo, 0.08, maxiter=257)), (mode, O)
+            assert np.array_equal(ctx32.denoise(fo, 0.08, o).astype(np.float32),
+                                  oracle.pdps(fo, 0.08, maxiter=257, dtype=np.float32)), (mode, O)
+        o = bp.pdps_opts(maxiter=200, kernel=bp.KERNEL_RESIDENT)
+        assert np.array_equal(ctx.denoise(np.asfortranarray(f[:, :, :2]), x, o), oracle.pdps(f[:, :, :2], am, maxiter=200)), mode
+        assert np.array_equal(ctx.denoise(fr, 0.1, o), oracle.pdps(fr, 0.1, maxiter=200)), mode
+        assert np.array_equal(ctx.denoise(fr, 0.1, bp.pdps_opts(maxiter=1, kernel=bp.KERNEL_RESIDENT)), oracle.pdps(fr, 0.1, maxiter=1)), mode
