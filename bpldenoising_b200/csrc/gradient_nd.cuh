@@ -9,6 +9,7 @@
 #include <cstring>
 #include <string>
 
+#include "env_switches.h"
 #include "gradient_nd.h"
 #include "nd_tv.cuh"
 
@@ -144,11 +145,18 @@ static int run_gradient_nd(NdWork &w, const NdProblem &gp, int sm_count, size_t 
     if (nsteps > 62) return nd_fail(gw, -1, "image too large for the nested-dissection level table");
     // launch plan of every level; shared memory of the largest (worst case: mb unknowns on every pixel)
     const double fsz = node ? 1.0 : 1.25;        // typical unknowns per pixel, for CTA sizes and arenas only
+    // CTA size of the generic front factorisation: a stack of many images has fronts for every SM several times over, and
+    // 4-warp CTAs (several per SM) beat 16-warp ones by 5–12 % (148 × 128²: 16.9 → 14.7 ms, 128 × 256²: 81.2 → 77.5 ms; the
+    // kernel is bound by the barriers of its block steps, not by threads); few images keep the wide CTAs.  The CTA size of
+    // the solves makes no measurable difference.  BPLTV_ND_WARPS_F / BPLTV_ND_THREADS_S override.
+    const char *e1 = bpltv::env_get("BPLTV_ND_WARPS_F"), *e2 = bpltv::env_get("BPLTV_ND_THREADS_S");
+    const int cta_warps_f = e1 && *e1 ? std::max(2, std::min(16, atoi(e1))) : (gp.O >= 32 ? 4 : 16);
+    const int cta_threads_s = e2 && *e2 ? std::max(64, std::min(512, atoi(e2))) : 512;
     std::vector<NdLevelPlan> plan(nsteps);
     std::vector<char> plan_small(nsteps);
     size_t fsmem = 0, ssmem = 0, fsmem_small = 0, ssmem_small = 0;
     for (int s = 0; s < nsteps; ++s) {
-        plan[s] = nd_level_plan(sym, s, mb, fsz);
+        plan[s] = nd_level_plan(sym, s, mb, fsz, cta_warps_f, cta_threads_s);
         plan_small[s] = plan[s].small;
         if (plan[s].small) { fsmem_small = std::max(fsmem_small, plan[s].smem_f); ssmem_small = std::max(ssmem_small, plan[s].smem_s); }
         // every level can also run on the generic kernels

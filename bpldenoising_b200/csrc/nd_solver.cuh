@@ -942,7 +942,8 @@ struct NdLevelPlan {
     size_t smem_f, smem_s;      // dynamic shared memory of the factorisation / of the solves
     int arena_f, arena_s;       // small kernels: arena (doubles)
 };
-static inline NdLevelPlan nd_level_plan(const NdSymbolic &sym, int s, int mb, double typ_per_pixel)
+static inline NdLevelPlan nd_level_plan(const NdSymbolic &sym, int s, int mb, double typ_per_pixel, int max_warps_f = 16,
+                                       int max_threads_s = 512)
 {
     NdLevelPlan lp;
     lp.t0 = sym.step_start[s]; lp.nfr = sym.step_start[s + 1] - lp.t0;
@@ -951,8 +952,8 @@ static inline NdLevelPlan nd_level_plan(const NdSymbolic &sym, int s, int mb, do
     const int nFt = std::min(lp.nFw, (int)(typ_per_pixel * sym.step_max_front_pix[s]) + 1);
     lp.small = lp.nFw <= ND_SMALL_MAXF && nFt <= ND_SMALL_TYPF;
     const int nt = (nFt + 31) / 32, ntiles = nt * (nt + 1) / 2;
-    lp.threads_f = 32 * std::min(16, std::max(2, ntiles));
-    lp.threads_s = std::min(512, std::max(64, (nFt + 31) & ~31));
+    lp.threads_f = 32 * std::min(max_warps_f, std::max(2, ntiles));
+    lp.threads_s = std::min(max_threads_s, std::max(64, (nFt + 31) & ~31));
     lp.arena_f = lp.arena_s = 0;
     if (lp.small) {
         lp.arena_f = nd_small_arena(lp.nFw, nPw, nFt, true);
