@@ -379,3 +379,27 @@ def test_resident_kernel_halo_schemes_agree(bp, ctx, ctx32, oracle, datasets, mo
         assert np.array_equal(ctx.denoise(np.asfortranarray(f[:, :, :2]), x, o), oracle.pdps(f[:, :, :2], am, maxiter=200)), mode
         assert np.array_equal(ctx.denoise(fr, 0.1, o), oracle.pdps(fr, 0.1, maxiter=200)), mode
         assert np.array_equal(ctx.denoise(fr, 0.1, bp.pdps_opts(maxiter=1, kernel=bp.KERNEL_RESIDENT)), oracle.pdps(fr, 0.1, maxiter=1)), mode
+
+
+def test_large_pageable_stacks_through_a_two_device_context(bp):
+    """Pageable caller buffers of 8 MiB or more travel through the context's pinned slots (several host threads, two
+    passes over the devices so that a blocking download does not hold back the other device): a two-device context returns
+    the bits of a one-device context for a 32 MiB stack, fp64 and fp32, denoise and learn_eval.  Needs ≥ 2 GPUs."""
+    import ctypes
+    cuda = ctypes.CDLL("libcuda.so.1")
+    n = ctypes.c_int(0)
+    cuda.cuInit(0); cuda.cuDeviceGetCount(ctypes.byref(n))
+    if n.value < 2:
+        pytest.skip("needs 2 GPUs")
+    truth, noisy = bp.synthetic_dataset(512, 512, 16, seed=11)          # 32 MiB per array, 16 MiB per device
+    for prec in (64, 32):
+        with bp.Context([0], prec) as c1, bp.Context([0, 1], prec) as c2:
+            o = bp.pdps_opts(maxiter=40)
+            u1, u2 = c1.denoise(noisy, 0.1, o), c2.denoise(noisy, 0.1, o)
+            assert np.array_equal(u1, u2), prec
+            c1.set_dataset((truth, noisy)); c2.set_dataset((truth, noisy))
+            eo = bp.eval_opts(o, force_branch=3)
+            v1, cost1, _ = c1.learn_eval(0.1, 0.1, eo)
+            v2, cost2, _ = c2.learn_eval(0.1, 0.1, eo)
+            assert np.array_equal(v1, v2) and np.array_equal(v1, u1) and abs(cost1 - cost2) <= 1e-13 * cost1, prec
+    # the one-device fp32 result itself is pinned to the oracle at this shape by the config-4 SHA-256 pins
