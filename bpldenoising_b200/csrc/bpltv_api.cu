@@ -192,9 +192,15 @@ static cudaError_t staged_copy(HostStage &hs, int device, char *dev, char *host,
             }
         }
     };
+    // chunks are dealt by thread index, so a thread that could not be started (std::system_error: no exception may cross
+    // the C ABI) has its chunks done by the caller's thread afterwards
     std::vector<std::thread> th;
-    for (int t = 1; t < nt; ++t) th.emplace_back(worker, t);
+    std::vector<int> orphan;
+    for (int t = 1; t < nt; ++t) {
+        try { th.emplace_back(worker, t); } catch (...) { orphan.push_back(t); }
+    }
     worker(0);
+    for (int t : orphan) worker(t);
     for (auto &x : th) x.join();
     return (cudaError_t)err.load();
 }
