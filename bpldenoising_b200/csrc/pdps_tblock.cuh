@@ -37,6 +37,11 @@
 // The arithmetic is common.cuh's primal_update / dual ascent / projection in the same order
 // per pixel and iteration, so strict mode stays bit-identical to the oracle.
 #pragma once
+#ifdef BPLTV_EMU
+#include <cstdint>
+#include <cstdio>
+#include <thread>
+#endif
 #include "common.cuh"
 
 namespace bpltv {
@@ -47,16 +52,46 @@ constexpr int TB_PF = TB_R - 1;      // columns in flight ahead of the march fro
 // ring slots of f: later stages read f of column c-2s (power of two ≥ TB_R + 2(T-1))
 template <int T> struct TBRingF { static constexpr int value = (TB_R + 2 * (T - 1)) <= 8 ? 8 : 16; };
 
-static __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-static __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+#ifdef BPLTV_EMU
+// Thread emulation (tests/emu): shared-window addresses are plain pointers, a bulk copy is a memcpy by the issuing thread,
+// and an mbarrier is a 64-bit word — low half: bytes the current phase still expects, high half: completed phases.
+typedef std::uintptr_t tb_addr;
+static inline tb_addr smem_u32(const void *p) { return reinterpret_cast<tb_addr>(p); }
+static inline void mbar_init(tb_addr bar, unsigned) { __atomic_store_n(reinterpret_cast<unsigned long long *>(bar), 0ULL, __ATOMIC_RELEASE); }
+static inline void mbar_fence_init() {}
+static inline void mbar_expect_tx(tb_addr bar, unsigned bytes)
+{
+    __atomic_fetch_add(reinterpret_cast<unsigned long long *>(bar), (unsigned long long)bytes, __ATOMIC_RELAXED);
+}
+static inline void mbar_wait(tb_addr bar, unsigned parity)
+{
+    while (((__atomic_load_n(reinterpret_cast<unsigned long long *>(bar), __ATOMIC_ACQUIRE) >> 32) & 1ULL) == parity) std::this_thread::yield();
+}
+static inline void tma_load_1d(tb_addr dst, const void *src, unsigned bytes, tb_addr bar)
+{
+    if ((dst & 15) || (reinterpret_cast<std::uintptr_t>(src) & 15) || (bytes & 15)) { std::fprintf(stderr, "emu: misaligned bulk copy\n"); std::abort(); }
+    std::memcpy(reinterpret_cast<void *>(dst), src, bytes);
+    unsigned long long *b = reinterpret_cast<unsigned long long *>(bar);
+    const unsigned long long before = __atomic_fetch_sub(b, (unsigned long long)bytes, __ATOMIC_ACQ_REL);
+    if ((unsigned)(before & 0xffffffffULL) == bytes) __atomic_fetch_add(b, 1ULL << 32, __ATOMIC_RELEASE);   // the phase completes
+}
+template <typename Real, int VEC>
+static inline void lds16(tb_addr addr, Real (&v)[VEC]) { std::memcpy(v, reinterpret_cast<const void *>(addr), sizeof(Real) * VEC); }
+template <typename Real>
+static inline Real lds1(tb_addr addr, Real) { Real v; std::memcpy(&v, reinterpret_cast<const void *>(addr), sizeof(Real)); return v; }
+#else
+typedef unsigned tb_addr;
+static __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+static __device__ __forceinline__ tb_addr smem_u32(const void *p) { return (tb_addr)__cvta_generic_to_shared(p); }
+static __device__ __forceinline__ void mbar_init(tb_addr bar, unsigned count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-static __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+static __device__ __forceinline__ void mbar_expect_tx(tb_addr bar, unsigned bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-static __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+static __device__ __forceinline__ void mbar_wait(tb_addr bar, unsigned parity)
 {
     asm volatile(
         "{\n"
@@ -70,31 +105,32 @@ static __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 }
 // global → shared copy of `bytes` (multiple of 16, both addresses 16-byte aligned) by the TMA
 // engine; completion is counted in bytes on the mbarrier `bar`
-static __device__ __forceinline__ void tma_load_1d(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+static __device__ __forceinline__ void tma_load_1d(tb_addr dst, const void *src, unsigned bytes, tb_addr bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
 // 16-byte shared-memory load of VEC Reals
-static __device__ __forceinline__ void lds16(unsigned addr, double (&v)[2])
+static __device__ __forceinline__ void lds16(tb_addr addr, double (&v)[2])
 {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(addr));
 }
-static __device__ __forceinline__ void lds16(unsigned addr, float (&v)[4])
+static __device__ __forceinline__ void lds16(tb_addr addr, float (&v)[4])
 {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
 }
 template <typename Real, int VEC>
-static __device__ __forceinline__ void lds16(unsigned, Real (&)[VEC]) {}  // never called (RING ⇒ 16-byte vectors)
-static __device__ __forceinline__ double lds1(unsigned addr, double)
+static __device__ __forceinline__ void lds16(tb_addr, Real (&)[VEC]) {}  // never called (RING ⇒ 16-byte vectors)
+static __device__ __forceinline__ double lds1(tb_addr addr, double)
 {
     double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr)); return v;
 }
-static __device__ __forceinline__ float lds1(unsigned addr, float)
+static __device__ __forceinline__ float lds1(tb_addr addr, float)
 {
     float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v;
 }
+#endif
 
 template <typename Real, int T>
 struct TBlockArgs {
@@ -129,7 +165,8 @@ struct TBSeg {
     // column prefetch ring (RING kernels), shared-window byte addresses of this thread's rows:
     // slot i of {x,y1,y2} at ring_t + i·3·colb (planes colb apart), slot j of f at fring_t + j·colb;
     // image column c of the segment is load number k0 + (c - cs)
-    unsigned ring_t, fring_t, ring0, fring0, bars, colb;
+    tb_addr ring_t, fring_t, ring0, fring0, bars;
+    unsigned colb;
     int k0;
 };
 
@@ -137,8 +174,8 @@ struct TBSeg {
 template <typename Real, int T>
 static __device__ __forceinline__ void tb_issue(const TBSeg<Real> &g, int kk, int col)
 {
-    const unsigned bar = g.bars + 8u * (unsigned)(kk & (TB_R - 1));
-    const unsigned sx = g.ring0 + (unsigned)(kk & (TB_R - 1)) * 3u * g.colb;
+    const tb_addr bar = g.bars + 8u * (unsigned)(kk & (TB_R - 1));
+    const tb_addr sx = g.ring0 + (unsigned)(kk & (TB_R - 1)) * 3u * g.colb;
     const size_t off = (size_t)col * g.M;
     mbar_expect_tx(bar, 4 * g.colb);
     tma_load_1d(sx, g.xin + off, g.colb, bar);
@@ -182,7 +219,7 @@ static __device__ __forceinline__ void tblock_step(const int c, const TBStage<Re
             if (RING) {
                 if (threadIdx.x == 0 && p + TB_PF <= g.cl) tb_issue<Real, T>(g, k + TB_PF, p + TB_PF);
                 mbar_wait(g.bars + 8u * (unsigned)(k & (TB_R - 1)), ((unsigned)k / TB_R) & 1u);
-                const unsigned sx = g.ring_t + (unsigned)(k & (TB_R - 1)) * 3u * g.colb;
+                const tb_addr sx = g.ring_t + (unsigned)(k & (TB_R - 1)) * 3u * g.colb;
                 lds16(sx, x_c);
                 lds16(sx + g.colb, y1_c[0]);
                 lds16(sx + 2 * g.colb, y2_c[0]);
@@ -348,7 +385,11 @@ template <typename Real, int VEC, int T, bool MAP, bool STRICT, bool RING, bool 
 __global__ void __launch_bounds__(MAXT, MINB) pdps_tblock_kernel(const TBlockArgs<Real, T> a)
 {
     typedef VecIO<Real, VEC> IO;
+#ifdef BPLTV_EMU
+    unsigned char *tb_smem = reinterpret_cast<unsigned char *>(emu::dyn_smem());
+#else
     extern __shared__ __align__(128) unsigned char tb_smem[];
+#endif
     __shared__ unsigned long long s_bars[TB_R];
     // slot [warp] of s_dn: x̄ of the warp's first row (read by the warp above it);
     // slot [warp+1] of s_up: the finished y1 of the warp's last row (read by the warp below)
@@ -373,7 +414,7 @@ __global__ void __launch_bounds__(MAXT, MINB) pdps_tblock_kernel(const TBlockArg
         if (threadIdx.x == 0) {
 #pragma unroll
             for (int i = 0; i < TB_R; ++i) mbar_init(g.bars + 8u * i, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_fence_init();
         }
         __syncthreads();
     }
