@@ -580,6 +580,7 @@ def learn_eval_extras(bp):
         with bp.Context([0], 64) as c:
             c.set_dataset(data)
             c.learn_eval(x, Delta)  # warm-up (allocations)
+            c.learn_eval(x, 1e-9)   # … of the regularised branch too (Δ ≤ Δt): the learn run below reaches it
             ts = []
             for _ in range(3):
                 t0 = time.perf_counter()
