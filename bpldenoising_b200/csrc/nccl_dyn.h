@@ -9,6 +9,7 @@
 #include <dlfcn.h>
 
 #include <cstdlib>
+#include <mutex>
 #include <string>
 
 namespace bpltv {
@@ -24,11 +25,13 @@ struct NcclApi {
     const char *(*GetErrorString)(int) = nullptr;
     int (*GetVersion)(int *) = nullptr;
     std::string err;
+    std::mutex mu;
 
     // BPLTV_NCCL_LIB names the library; otherwise the soname (a process that already loaded NCCL — e.g. through
     // torch — gets that copy), then the unversioned name
     bool load()
     {
+        std::lock_guard<std::mutex> lock(mu);      // ranks of one process (host threads) may arrive together
         if (handle) return true;
         const char *names[3] = {std::getenv("BPLTV_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
         for (const char *n : names) {
