@@ -71,8 +71,11 @@ struct NdWork {
     double last_relres = 0.0;
     long long last_guarded = 0;
     size_t last_bytes_per_image = 0;
+    // images per wave decided for (image size, form, images wanted): asked of the driver once
+    int slots_key_n = -1, slots_key_node = -1, slots_key_want = -1, slots_cached = 0;
     void release()
     {
+        slots_key_n = slots_key_node = slots_key_want = -1;
         plan.release();
         NdBuf *all[] = {&pix, &off, &vec, &posg, &foff, &totals, &ast, &L, &U0, &U1, &UV0, &UV1, &info, &out_img, &relres, &relres_max};
         for (NdBuf *b : all) b->release();
@@ -202,16 +205,23 @@ static int run_gradient_nd(NdWork &w, const NdProblem &gp, int sm_count, size_t 
     const size_t per_slot = fix_bytes + pool_bytes;
     w.last_bytes_per_image = per_slot;
     int slots = std::min(gp.O, 256);      // 256 images already give every level thousands of fronts
-    {
+    if (w.slots_key_n == n && w.slots_key_node == (int)node && w.slots_key_want == slots) {
+        slots = w.slots_cached;           // the same question as last time: no free-memory query on the evaluation path
+    } else {
+        const int want = slots;
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
         const size_t have = w.pix.bytes + w.ast.bytes + w.L.bytes + w.U0.bytes + w.U1.bytes + w.vec.bytes + w.posg.bytes + w.foff.bytes;
         const size_t budget = (free_b + have) / 2;
         slots = (int)std::min<size_t>((size_t)slots, std::max<size_t>(1, budget / per_slot));
+        w.slots_key_n = n; w.slots_key_node = (int)node; w.slots_key_want = want; w.slots_cached = slots;
     }
     auto need = [&](NdBuf &b, size_t bytes, const char *what) -> int {
         cudaError_t e = b.ensure(bytes);
-        if (e != cudaSuccess) return nd_fail(gw, -6, std::string("nested-dissection workspace (") + what + "): " + cudaGetErrorString(e));
+        if (e != cudaSuccess) {
+            w.slots_key_n = -1;      // memory got tighter since the wave size was decided: ask again next time
+            return nd_fail(gw, -6, std::string("nested-dissection workspace (") + what + "): " + cudaGetErrorString(e));
+        }
         return 0;
     };
     int rc = 0;
