@@ -49,12 +49,18 @@ struct NdPlan {      // symbolic structure of one image size, on the device
 
 struct NdBuf {
     void *p = nullptr; size_t bytes = 0;
+    // grows by at least half of what it had: the pools of the multiplier form follow the data (unknowns per pixel change
+    // with λ from one evaluation of a learn run to the next), and a cudaFree + cudaMalloc per evaluation synchronises
     cudaError_t ensure(size_t need)
     {
         if (need <= bytes) return cudaSuccess;
+        const size_t want = std::max(need, bytes + bytes / 2);
         if (p) cudaFree(p);
         p = nullptr; bytes = 0;
-        cudaError_t e = cudaMalloc(&p, need);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) { bytes = want; return e; }
+        cudaGetLastError();
+        e = cudaMalloc(&p, need);
         if (e == cudaSuccess) bytes = need; else cudaGetLastError();
         return e;
     }
