@@ -589,9 +589,12 @@ def learn_eval_extras(bp):
             st = c.stats()
             out[name] = {"images": int(data[0].shape[2]), "ms": min(ts), "ms_pdps": st["ms_pdps"],
                          "ms_gradient": st["ms_gradient"], "cost": cost, "grad": np.asarray(g).ravel().tolist()}
-            res = trbox.bilevel_learn(data, lambda xx, d_, D: bp.tv_op_learning_function(xx, d_, D, ctx=c), x,
-                                      dict(Delta0=Delta))
-            out[name]["learn_run"] = {"seconds": res.seconds, "evaluations": res.evaluations,
+            # best of two runs: the first one still pays for buffers that grow with the data (the number of adjoint
+            # unknowns follows λ); a warmed context repeats the run to within 1 % (tools/dbg_learn_run.py)
+            runs = [trbox.bilevel_learn(data, lambda xx, d_, D: bp.tv_op_learning_function(xx, d_, D, ctx=c), x,
+                                        dict(Delta0=Delta)) for _ in range(2)]
+            res = min(runs, key=lambda r: r.seconds)
+            out[name]["learn_run"] = {"seconds": res.seconds, "seconds_first_run": runs[0].seconds, "evaluations": res.evaluations,
                                       "final_cost": res.log[-1].function_value,
                                       "x": np.asarray(res.x).ravel().tolist()}
             if dsname == "faces_train_128_10":   # "validated on faces_val_128_10": TVDenoise = 10000 iterations
