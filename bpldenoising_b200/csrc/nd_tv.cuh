@@ -78,50 +78,53 @@ __global__ void __launch_bounds__(512) ndtv_classify_mult_kernel(NdTvSlots ws, N
            *rc = pix + 6 * (size_t)N;
     int *off = ws.off + ws.off_stride * slot;
     if (threadIdx.x < 4) ws.info[4 * slot + threadIdx.x] = 0;
-    const int per = (N + blockDim.x - 1) / blockDim.x;
-    const int q0 = min(N, (int)threadIdx.x * per), q1 = min(N, q0 + per);
-    int cnt = 0;
-    for (int q = q0; q < q1; ++q) {
-        const int i = q % n, j = q / n;
-        const double uq = (double)u[q];
-        const double g1 = (i + 1 < n) ? (double)u[q + 1] - uq : 0.0;
-        const double g2 = (j + 1 < n) ? (double)u[q + n] - uq : 0.0;
-        const double nrm = sqrt(g1 * g1 + g2 * g2);
-        const double a = gv.patch ? (double)alpha_map[q] : gv.alpha_s;
-        const bool iso = nrm < gv.act_tol;                      // "active" (:109, :231)
-        ea[q] = iso ? 1.0 : -g2 / nrm;
-        eb[q] = iso ? 0.0 : g1 / nrm;
-        E[q] = iso ? gv.eps_act : nrm / a;
-        w1[q] = iso ? 0.0 : g1 / nrm;
-        w2[q] = iso ? 0.0 : g2 / nrm;
-        rc[q] = uq - (double)ub[q];                             // u − ū (:130, :247)
-        off[q] = iso ? 2 : 1;
-        cnt += iso ? 2 : 1;
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        const int nw = (blockDim.x + 31) >> 5;
-        int v = lane < nw ? s_warp[lane] : 0, iv = v;
+    // tiles of blockDim.x consecutive pixels (coalesced), a CTA-wide exclusive scan of the mode counts per tile and a
+    // running total carried from tile to tile (threads beyond the image take part in the scan with a count of 0)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    int base = 0;
+    for (int q0 = 0; q0 < N; q0 += blockDim.x) {
+        const int q = q0 + (int)threadIdx.x;
+        int cnt = 0;
+        if (q < N) {
+            const int i = q % n, j = q / n;
+            const double uq = (double)u[q];
+            const double g1 = (i + 1 < n) ? (double)u[q + 1] - uq : 0.0;
+            const double g2 = (j + 1 < n) ? (double)u[q + n] - uq : 0.0;
+            const double nrm = sqrt(g1 * g1 + g2 * g2);
+            const double a = gv.patch ? (double)alpha_map[q] : gv.alpha_s;
+            const bool iso = nrm < gv.act_tol;                      // "active" (:109, :231)
+            ea[q] = iso ? 1.0 : -g2 / nrm;
+            eb[q] = iso ? 0.0 : g1 / nrm;
+            E[q] = iso ? gv.eps_act : nrm / a;
+            w1[q] = iso ? 0.0 : g1 / nrm;
+            w2[q] = iso ? 0.0 : g2 / nrm;
+            rc[q] = uq - (double)ub[q];                             // u − ū (:130, :247)
+            cnt = iso ? 2 : 1;
+        }
+        int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, iv, o);
-            if (lane >= o) iv += t;
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
-        s_warp[lane] = iv - v;
-        if (lane == 31) s_warp[32] = iv;
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int v = lane < nw ? s_warp[lane] : 0, iv = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, iv, o);
+                if (lane >= o) iv += t;
+            }
+            s_warp[lane] = iv - v;
+            if (lane == 31) s_warp[32] = iv;
+        }
+        __syncthreads();
+        if (q < N) off[q] = base + s_warp[warp] + incl - cnt;
+        base += s_warp[32];
+        __syncthreads();                                            // s_warp is rewritten by the next tile
     }
-    __syncthreads();
-    int run = s_warp[warp] + incl - cnt;
-    for (int q = q0; q < q1; ++q) { const int c = off[q]; off[q] = run; run += c; }
-    if (threadIdx.x == 0) off[N] = s_warp[32];
+    if (threadIdx.x == 0) off[N] = base;
 }
 
 // node coefficients of a mode of pixel (i,j) with direction (e1,e2): β0 at q, β1 at q+1, β2 at q+n
