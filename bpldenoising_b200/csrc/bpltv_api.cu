@@ -230,7 +230,9 @@ struct Dev {
     GradWork grad;            // gradient.cuh
     GradWork grad3;           // gradient_sumregs.cuh
     NdWork *nd = nullptr;     // gradient_nd.cuh (nested-dissection adjoint solver), created on first use
+    NdWork *nd3 = nullptr;    // the same solver at coupling radius 2 (scalar sumregs_gradient_reg); a plan of its own
     bool grad_used_nd = false;
+    bool grad3_used_nd = false;
     bool grad_used_band = false; // a banded factorisation ran: its worst backward error is in grad.relres_max (device)
     StepKey steps_key;
     std::vector<unsigned char> steps_host;
@@ -924,7 +926,24 @@ static int sumregs_eval_on_device(bpltv_ctx *ctx, Dev &d, const double *lam, int
         gp.gamma = (gp.regularised && amap && eo.gamma_patch > 0) ? eo.gamma_patch : eo.gamma;   // :200 vs :117
         gp.act_tol = eo.act_tol;
         gp.eps_act = eo.eps_act > 0 ? eo.eps_act : 2.220446049250313e-16;   // eps() in both variants (:318-320, :387-389)
-        int rc = run_gradient3<Real>(d.grad3, gp, d.sm_count, d.smem_optin, st, d_costgrad + 1, &d.launches);
+        // scalar sumregs_gradient_reg (:112-167) is symmetric positive definite in node space with coupling radius 2:
+        // nested-dissection multifrontal Cholesky (eval_opts.solver 0 / 2, BPLTV_GRAD_SOLVER); solver 1 or a shape the
+        // fronts do not take: the node-space band LU / compliance form of run_gradient3
+        int solver = eo.solver;
+        if (solver == 0) solver = env_int("BPLTV_GRAD_SOLVER", 0);
+        d.grad3_used_nd = false;
+        int rc = -1;
+        if (gp.regularised && !amap && solver != 1 && M == N) {
+            if (!d.nd3) d.nd3 = nd_work_create();
+            Nd3Problem np;
+            np.u = u; np.ubar = d.truth.as<Real>(); np.prec = (int)sizeof(Real) * 8; np.M = M; np.N = N; np.O = O;
+            for (int k = 0; k < 3; ++k) np.alpha[k] = lam[k];
+            np.gamma = gp.gamma; np.tol = 0.0; np.maxit = eo.solver_maxit;
+            rc = nd_run_gradient3_reg(d.nd3, np, d.sm_count, d.smem_optin, st, d_costgrad + 1, &d.launches);
+            if (rc == 0) d.grad3_used_nd = true;
+            else if (rc != -1) return fail(rc, "sumregs gradient: %s", nd_work_error(d.nd3));
+        }
+        if (rc == -1) rc = run_gradient3<Real>(d.grad3, gp, d.sm_count, d.smem_optin, st, d_costgrad + 1, &d.launches);
         if (rc != 0) return fail(rc == -1 ? BPLTV_ERR_ARG : rc, "sumregs gradient: %s", d.grad3.err.c_str());
     }
     CU_TRY(cudaEventRecord(d.ev[3], st));
@@ -959,8 +978,9 @@ static int sumregs_learn_eval_impl(bpltv_ctx *ctx, const double *lam, int lm, in
         RC_TRY(allreduce_costgrad(ctx, d.scalars.as<double>(), 1 + ng, d.stream));
         CU_TRY(cudaMemcpyAsync(host[di].data(), d.scalars.p, (1 + ng) * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
         // worst backward error of the banded adjoint solves (grad_reduce_kernel leaves it in the workspace)
-        if (d.O > 0 && eo.force_branch != 3 && d.grad3.relres_max)
-            CU_TRY(cudaMemcpyAsync(&relres[di], d.grad3.relres_max, sizeof(double), cudaMemcpyDeviceToHost, d.stream));
+        const void *rr = d.grad3_used_nd ? (const void *)nd_work_relres_max(d.nd3) : (const void *)d.grad3.relres_max;
+        if (d.O > 0 && eo.force_branch != 3 && rr)
+            CU_TRY(cudaMemcpyAsync(&relres[di], rr, sizeof(double), cudaMemcpyDeviceToHost, d.stream));
     }
     for (int di = 0; di < ndev; ++di) {      // second pass: see denoise_impl
         Dev &d = ctx->devs[di];
@@ -1500,6 +1520,7 @@ int bpltv_destroy(bpltv_ctx *ctx)
         d.grad.release();
         d.grad3.release();
         nd_work_destroy(d.nd);
+        nd_work_destroy(d.nd3);
         d.nd = nullptr;
         d.hstage.release();
         for (auto &ev : d.ev) if (ev) cudaEventDestroy(ev);

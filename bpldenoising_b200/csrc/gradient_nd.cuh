@@ -7,10 +7,13 @@
 // spreads over the SMs level by level and many images fill the GPU together.
 #pragma once
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <vector>
 
 #include "env_switches.h"
 #include "gradient_nd.h"
+#include "nd_sumregs.cuh"
 #include "nd_tv.cuh"
 
 namespace bpltv {
@@ -72,7 +75,6 @@ struct NdWork {
     NdPlan plan;
     NdBuf pix, off, vec, posg, foff, totals, ast, L, U0, U1, UV0, UV1, info, out_img, relres, relres_max;
     std::vector<long long> h_totals;
-    int attr_smem_factor = 0, attr_smem_solve = 0, attr_smem_factor_small = 0, attr_smem_solve_small = 0;
     // what the last call saw (statistics)
     double last_relres = 0.0;
     long long last_guarded = 0;
@@ -90,11 +92,11 @@ struct NdWork {
 
 constexpr int ND_LEAF = 4;
 
-static inline int nd_build_plan(NdPlan &pl, int n, cudaStream_t st, std::string &err)
+static inline int nd_build_plan(NdPlan &pl, int n, int W, cudaStream_t st, std::string &err)
 {
-    if (pl.n == n) return 0;
+    if (pl.n == n && pl.sym.W == W) return 0;
     pl.release();
-    pl.sym.build(n, 1, ND_LEAF);
+    pl.sym.build(n, W, ND_LEAF);
     const NdSymbolic &s = pl.sym;
     const int nf = (int)s.fronts.size();
     pl.posg_len = s.pixlist.size() + nf;
@@ -133,6 +135,112 @@ static inline int nd_build_plan(NdPlan &pl, int n, cudaStream_t st, std::string 
 
 static inline int nd_fail(NdWork &w, int code, const std::string &msg) { w.err = msg; return code; }
 
+// Launch plan of every level of the tree for `mb` unknowns per pixel at most (`fsz` typical): CTA sizes, shared memory of
+// the largest front (worst case: mb unknowns on every pixel), kernel attributes.  -1: a front does not fit in shared
+// memory (the caller falls back to a band solver).
+static int nd_prepare_levels(NdWork &w, const NdSymbolic &sym, int mb, double fsz, int O, size_t smem_optin,
+                             std::vector<NdLevelPlan> &plan, std::vector<char> &plan_small)
+{
+    const int nsteps = sym.nsteps();
+    // CTA size of the generic front factorisation: a stack of many images has fronts for every SM several times over, and
+    // 4-warp CTAs (several per SM) beat 16-warp ones by 5–12 % (148 × 128²: 16.9 → 14.7 ms, 128 × 256²: 81.2 → 77.5 ms; the
+    // kernel is bound by the barriers of its block steps, not by threads); few images keep the wide CTAs.  The CTA size of
+    // the solves makes no measurable difference.  BPLTV_ND_WARPS_F / BPLTV_ND_THREADS_S override.
+    const char *e1 = bpltv::env_get("BPLTV_ND_WARPS_F"), *e2 = bpltv::env_get("BPLTV_ND_THREADS_S");
+    const int cta_warps_f = e1 && *e1 ? std::max(2, std::min(16, atoi(e1))) : (O >= 32 ? 4 : 16);
+    const int cta_threads_s = e2 && *e2 ? std::max(64, std::min(512, atoi(e2))) : 512;
+    plan.assign(nsteps, NdLevelPlan());
+    plan_small.assign(nsteps, 0);
+    size_t fsmem = 0, ssmem = 0, fsmem_small = 0, ssmem_small = 0;
+    for (int s = 0; s < nsteps; ++s) {
+        plan[s] = nd_level_plan(sym, s, mb, fsz, cta_warps_f, cta_threads_s);
+        plan_small[s] = plan[s].small;
+        if (plan[s].small) { fsmem_small = std::max(fsmem_small, plan[s].smem_f); ssmem_small = std::max(ssmem_small, plan[s].smem_s); }
+        // every level can also run on the generic kernels
+        fsmem = std::max(fsmem, nd_factor_smem(plan[s].nFw, s > 0 ? mb * sym.step_max_ring_pix[s - 1] : 0));
+        ssmem = std::max(ssmem, nd_solve_smem(plan[s].nFw));
+    }
+    if (fsmem > smem_optin || ssmem > smem_optin || fsmem_small > smem_optin || ssmem_small > smem_optin)
+        return -1;      // the caller falls back to the band solver
+    {
+        // the opt-in shared-memory size is an attribute of the KERNEL on the current device, shared by every workspace
+        // that launches it (the TV solver and the sum-of-regularisers one): raised to the largest any of them asked for
+        static std::mutex mu;
+        static int have[64][4] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        dev = std::max(0, std::min(63, dev));
+        std::lock_guard<std::mutex> lock(mu);
+        cudaError_t e = cudaSuccess;
+        if (have[dev][0] < (int)fsmem) {
+            e = cudaFuncSetAttribute(nd_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+            if (e == cudaSuccess) have[dev][0] = (int)fsmem;
+        }
+        if (e == cudaSuccess && have[dev][1] < (int)ssmem) {
+            e = cudaFuncSetAttribute(nd_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(nd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem);
+            if (e == cudaSuccess) have[dev][1] = (int)ssmem;
+        }
+        if (e == cudaSuccess && have[dev][2] < (int)fsmem_small) {
+            e = cudaFuncSetAttribute(nd_factor_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem_small);
+            if (e == cudaSuccess) have[dev][2] = (int)fsmem_small;
+        }
+        if (e == cudaSuccess && have[dev][3] < (int)ssmem_small) {
+            e = cudaFuncSetAttribute(nd_fwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem_small);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(nd_bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem_small);
+            if (e == cudaSuccess) have[dev][3] = (int)ssmem_small;
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return nd_fail(w, -2, std::string("nested-dissection kernel attributes: ") + cudaGetErrorString(e));
+        }
+    }
+    return 0;
+}
+
+// one launch per level: assemble + partial Cholesky of every front of the wave's `cnt` images
+static void nd_launch_factor(const NdDev &nd, std::vector<NdLevelPlan> &plan, const std::vector<char> &plan_small,
+                             const NdSymbolic &sym, int mb, int cnt, int sm_count, double guard, cudaStream_t st, long long *launches)
+{
+    const int nsteps = sym.nsteps();
+    // the warp-per-front kernels pay off when the level has warps for every scheduler of the GPU; with few fronts (the
+    // upper small levels of a single image) a CTA per front is faster (ncu, 1 image of 128²: 48 vs 117 µs at 256 fronts)
+    for (int s = 0; s < nsteps; ++s) plan[s].small = plan_small[s] && (long long)plan[s].nfr * cnt >= 4LL * sm_count;
+    for (int s = 0; s < nsteps; ++s) {
+        const NdLevelPlan &lp = plan[s];
+        if (lp.small)
+            nd_factor_small_kernel<<<dim3((lp.nfr + ND_SMALL_WARPS - 1) / ND_SMALL_WARPS, cnt), 32 * ND_SMALL_WARPS, lp.smem_f, st>>>(
+                nd, lp.t0, lp.nfr, s & 1, guard, lp.arena_f);
+        else
+            nd_factor_kernel<<<dim3(lp.nfr, cnt), lp.threads_f, nd_factor_smem(lp.nFw, s > 0 ? mb * sym.step_max_ring_pix[s - 1] : 0), st>>>(nd, lp.t0, s & 1, guard, lp.nFw);
+    }
+    *launches += nsteps;
+}
+
+// L y = b up the tree, Lᵀ x = y down: `vec` (per image, `stride` doubles apart) is overwritten by the solution
+static void nd_launch_solve(const NdDev &nd, const std::vector<NdLevelPlan> &plan, int cnt, double *vec, size_t stride,
+                            cudaStream_t st, long long *launches)
+{
+    const int nsteps = (int)plan.size();
+    for (int s = 0; s < nsteps; ++s) {
+        const NdLevelPlan &lp = plan[s];
+        if (lp.small)
+            nd_fwd_small_kernel<<<dim3((lp.nfr + ND_SMALL_WARPS - 1) / ND_SMALL_WARPS, cnt), 32 * ND_SMALL_WARPS, lp.smem_s, st>>>(
+                nd, lp.t0, lp.nfr, s & 1, vec, stride, lp.arena_s);
+        else
+            nd_fwd_kernel<<<dim3(lp.nfr, cnt), lp.threads_s, nd_solve_smem(lp.nFw), st>>>(nd, lp.t0, s & 1, vec, stride);
+    }
+    for (int s = nsteps - 1; s >= 0; --s) {
+        const NdLevelPlan &lp = plan[s];
+        if (lp.small)
+            nd_bwd_small_kernel<<<dim3((lp.nfr + ND_SMALL_WARPS - 1) / ND_SMALL_WARPS, cnt), 32 * ND_SMALL_WARPS, lp.smem_s, st>>>(
+                nd, lp.t0, lp.nfr, vec, stride, lp.arena_s);
+        else
+            nd_bwd_kernel<<<dim3(lp.nfr, cnt), lp.threads_s, nd_solve_smem(lp.nFw), st>>>(nd, lp.t0, vec, stride);
+    }
+    *launches += 2 * nsteps;
+}
+
 template <typename Real>
 static int run_gradient_nd(NdWork &w, const NdProblem &gp, int sm_count, size_t smem_optin,
                            cudaStream_t st, double *d_grad_out, long long *launches)
@@ -146,59 +254,19 @@ static int run_gradient_nd(NdWork &w, const NdProblem &gp, int sm_count, size_t 
     const bool node = gp.regularised;
     const int mb = node ? 1 : 2;
     {
-        const int rc = nd_build_plan(w.plan, n, st, gw.err);
+        const int rc = nd_build_plan(w.plan, n, 1, st, gw.err);
         if (rc != 0) return rc;
     }
     const NdSymbolic &sym = w.plan.sym;
     const int nf = (int)sym.fronts.size(), nsteps = sym.nsteps();
     if (nsteps > 62) return nd_fail(gw, -1, "image too large for the nested-dissection level table");
-    // launch plan of every level; shared memory of the largest (worst case: mb unknowns on every pixel)
+    // launch plan of every level (CTA sizes, shared memory, kernel attributes)
     const double fsz = node ? 1.0 : 1.25;        // typical unknowns per pixel, for CTA sizes and arenas only
-    // CTA size of the generic front factorisation: a stack of many images has fronts for every SM several times over, and
-    // 4-warp CTAs (several per SM) beat 16-warp ones by 5–12 % (148 × 128²: 16.9 → 14.7 ms, 128 × 256²: 81.2 → 77.5 ms; the
-    // kernel is bound by the barriers of its block steps, not by threads); few images keep the wide CTAs.  The CTA size of
-    // the solves makes no measurable difference.  BPLTV_ND_WARPS_F / BPLTV_ND_THREADS_S override.
-    const char *e1 = bpltv::env_get("BPLTV_ND_WARPS_F"), *e2 = bpltv::env_get("BPLTV_ND_THREADS_S");
-    const int cta_warps_f = e1 && *e1 ? std::max(2, std::min(16, atoi(e1))) : (gp.O >= 32 ? 4 : 16);
-    const int cta_threads_s = e2 && *e2 ? std::max(64, std::min(512, atoi(e2))) : 512;
-    std::vector<NdLevelPlan> plan(nsteps);
-    std::vector<char> plan_small(nsteps);
-    size_t fsmem = 0, ssmem = 0, fsmem_small = 0, ssmem_small = 0;
-    for (int s = 0; s < nsteps; ++s) {
-        plan[s] = nd_level_plan(sym, s, mb, fsz, cta_warps_f, cta_threads_s);
-        plan_small[s] = plan[s].small;
-        if (plan[s].small) { fsmem_small = std::max(fsmem_small, plan[s].smem_f); ssmem_small = std::max(ssmem_small, plan[s].smem_s); }
-        // every level can also run on the generic kernels
-        fsmem = std::max(fsmem, nd_factor_smem(plan[s].nFw, s > 0 ? mb * sym.step_max_ring_pix[s - 1] : 0));
-        ssmem = std::max(ssmem, nd_solve_smem(plan[s].nFw));
-    }
-    if (fsmem > smem_optin || ssmem > smem_optin || fsmem_small > smem_optin || ssmem_small > smem_optin)
-        return -1;      // the caller falls back to the band solver
+    std::vector<NdLevelPlan> plan;
+    std::vector<char> plan_small;
     {
-        cudaError_t e = cudaSuccess;
-        if (w.attr_smem_factor < (int)fsmem) {
-            e = cudaFuncSetAttribute(nd_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
-            w.attr_smem_factor = (int)fsmem;
-        }
-        if (e == cudaSuccess && w.attr_smem_solve < (int)ssmem) {
-            e = cudaFuncSetAttribute(nd_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(nd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem);
-            w.attr_smem_solve = (int)ssmem;
-        }
-        if (e == cudaSuccess && w.attr_smem_factor_small < (int)fsmem_small) {
-            e = cudaFuncSetAttribute(nd_factor_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem_small);
-            w.attr_smem_factor_small = (int)fsmem_small;
-        }
-        if (e == cudaSuccess && w.attr_smem_solve_small < (int)ssmem_small) {
-            e = cudaFuncSetAttribute(nd_fwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem_small);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(nd_bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem_small);
-            w.attr_smem_solve_small = (int)ssmem_small;
-        }
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            w.attr_smem_factor = w.attr_smem_solve = w.attr_smem_factor_small = w.attr_smem_solve_small = 0;
-            return nd_fail(gw, -2, std::string("nested-dissection kernel attributes: ") + cudaGetErrorString(e));
-        }
+        const int rc = nd_prepare_levels(w, sym, mb, fsz, gp.O, smem_optin, plan, plan_small);
+        if (rc != 0) return rc;
     }
 
     // ---- per-slot sizes.  Pools of the MULT form are estimated at 2.2× the one-unknown-per-pixel sizes (≈ 1.5
@@ -314,37 +382,8 @@ static int run_gradient_nd(NdWork &w, const NdProblem &gp, int sm_count, size_t 
         nd.UV[0] = (double *)w.UV0.p; nd.UV[1] = (double *)w.UV1.p; nd.UV_stride = UVs;
         w.last_bytes_per_image = fix_bytes + (Ls + 2 * Us + 2 * UVs) * 8;
 
-        // the warp-per-front kernels pay off when the level has warps for every scheduler of the GPU; with few fronts (the
-        // upper small levels of a single image) a CTA per front is faster (ncu, 1 image of 128²: 48 vs 117 µs at 256 fronts)
-        for (int s = 0; s < nsteps; ++s) plan[s].small = plan_small[s] && (long long)plan[s].nfr * cnt >= 4LL * sm_count;
-        for (int s = 0; s < nsteps; ++s) {
-            const NdLevelPlan &lp = plan[s];
-            if (lp.small)
-                nd_factor_small_kernel<<<dim3((lp.nfr + ND_SMALL_WARPS - 1) / ND_SMALL_WARPS, cnt), 32 * ND_SMALL_WARPS, lp.smem_f, st>>>(
-                    nd, lp.t0, lp.nfr, s & 1, guard, lp.arena_f);
-            else
-                nd_factor_kernel<<<dim3(lp.nfr, cnt), lp.threads_f, nd_factor_smem(lp.nFw, s > 0 ? mb * sym.step_max_ring_pix[s - 1] : 0), st>>>(nd, lp.t0, s & 1, guard, lp.nFw);
-        }
-        *launches += nsteps;
-        auto solve = [&](double *vec, size_t stride) {
-            for (int s = 0; s < nsteps; ++s) {
-                const NdLevelPlan &lp = plan[s];
-                if (lp.small)
-                    nd_fwd_small_kernel<<<dim3((lp.nfr + ND_SMALL_WARPS - 1) / ND_SMALL_WARPS, cnt), 32 * ND_SMALL_WARPS, lp.smem_s, st>>>(
-                        nd, lp.t0, lp.nfr, s & 1, vec, stride, lp.arena_s);
-                else
-                    nd_fwd_kernel<<<dim3(lp.nfr, cnt), lp.threads_s, nd_solve_smem(lp.nFw), st>>>(nd, lp.t0, s & 1, vec, stride);
-            }
-            for (int s = nsteps - 1; s >= 0; --s) {
-                const NdLevelPlan &lp = plan[s];
-                if (lp.small)
-                    nd_bwd_small_kernel<<<dim3((lp.nfr + ND_SMALL_WARPS - 1) / ND_SMALL_WARPS, cnt), 32 * ND_SMALL_WARPS, lp.smem_s, st>>>(
-                        nd, lp.t0, lp.nfr, vec, stride, lp.arena_s);
-                else
-                    nd_bwd_kernel<<<dim3(lp.nfr, cnt), lp.threads_s, nd_solve_smem(lp.nFw), st>>>(nd, lp.t0, vec, stride);
-            }
-            *launches += 2 * nsteps;
-        };
+        nd_launch_factor(nd, plan, plan_small, sym, mb, cnt, sm_count, guard, st, launches);
+        auto solve = [&](double *vec, size_t stride) { nd_launch_solve(nd, plan, cnt, vec, stride, st, launches); };
         if (node) {
             double *p = ws.pix + 7 * (size_t)N, *work = ws.pix + 8 * (size_t)N;
             solve(p, ws.pix_stride);
@@ -378,6 +417,120 @@ static int run_gradient_nd(NdWork &w, const NdProblem &gp, int sm_count, size_t 
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// scalar sumregs_gradient_reg on the same solver (nd_sumregs.cuh): node space, one unknown per node, W = 2
+// ---------------------------------------------------------------------------
+template <typename Real>
+static int run_gradient3_nd_reg(NdWork &w, const Nd3Problem &gp, int sm_count, size_t smem_optin, cudaStream_t st,
+                                double *d_grad_out, long long *launches)
+{
+    const Real *gp_u = static_cast<const Real *>(gp.u), *gp_ubar = static_cast<const Real *>(gp.ubar);
+    const int n = gp.M, N = gp.M * gp.N, nops = 3, ng = 1;
+    if (gp.M != gp.N) return nd_fail(w, -1, "square images required");
+    if (n < 8) return -1;                                   // tiny images: the band LU
+    {
+        const int rc = nd_build_plan(w.plan, n, ND3_W, st, w.err);
+        if (rc != 0) return rc;
+    }
+    const NdSymbolic &sym = w.plan.sym;
+    const int nf = (int)sym.fronts.size(), nsteps = sym.nsteps();
+    if (nsteps > 62) return nd_fail(w, -1, "image too large for the nested-dissection level table");
+    std::vector<NdLevelPlan> plan;
+    std::vector<char> plan_small;
+    {
+        const int rc = nd_prepare_levels(w, sym, 1, 1.0, gp.O, smem_optin, plan, plan_small);
+        if (rc != 0) return rc;
+    }
+    const long long *t1 = w.plan.tot1;
+    const size_t pix_stride = (size_t)LU_PLANES * N, ast_stride = (size_t)ND3_NH * N;
+    const size_t Ls = ((size_t)t1[0] + 1) & ~(size_t)1, Us = ((size_t)t1[1] + 1) & ~(size_t)1, UVs = ((size_t)t1[2] + 1) & ~(size_t)1;
+    const size_t per_slot = (pix_stride + ast_stride + Ls + 2 * Us + 2 * UVs) * 8 + 16;
+    w.last_bytes_per_image = per_slot;
+    int slots = std::min(gp.O, 256);
+    if (w.slots_key_n == n && w.slots_key_node == 3 && w.slots_key_want == slots) {
+        slots = w.slots_cached;
+    } else {
+        const int want = slots;
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const size_t have = w.pix.bytes + w.ast.bytes + w.L.bytes + w.U0.bytes + w.U1.bytes;
+        const size_t budget = (free_b + have) / 2;
+        slots = (int)std::min<size_t>((size_t)slots, std::max<size_t>(1, budget / per_slot));
+        w.slots_key_n = n; w.slots_key_node = 3; w.slots_key_want = want; w.slots_cached = slots;
+    }
+    auto need = [&](NdBuf &b, size_t bytes, const char *what) -> int {
+        cudaError_t e = b.ensure(bytes);
+        if (e != cudaSuccess) {
+            w.slots_key_n = -1;
+            return nd_fail(w, -6, std::string("nested-dissection workspace (") + what + "): " + cudaGetErrorString(e));
+        }
+        return 0;
+    };
+    int rc = 0;
+    if ((rc = need(w.pix, pix_stride * 8 * slots, "pixel planes"))) return rc;
+    if ((rc = need(w.ast, ast_stride * 8 * slots, "stencil matrix"))) return rc;
+    if ((rc = need(w.info, (size_t)16 * slots, "info"))) return rc;
+    if ((rc = need(w.out_img, (size_t)gp.O * nops * ng * 8, "per-image gradients"))) return rc;
+    if ((rc = need(w.relres, (size_t)gp.O * 8, "residuals"))) return rc;
+    if ((rc = need(w.relres_max, 16, "residual maximum"))) return rc;
+    if ((rc = need(w.L, Ls * 8 * slots, "factors"))) return rc;
+    if ((rc = need(w.U0, Us * 8 * slots, "update matrices"))) return rc;
+    if ((rc = need(w.U1, Us * 8 * slots, "update matrices"))) return rc;
+    if ((rc = need(w.UV0, UVs * 8 * slots, "update vectors"))) return rc;
+    if ((rc = need(w.UV1, UVs * 8 * slots, "update vectors"))) return rc;
+
+    LuSlots ws;
+    ws.ab = nullptr; ws.ab_stride = 0; ws.pix = (double *)w.pix.p; ws.pix_stride = pix_stride; ws.info = (int *)w.info.p;
+    ws.n = n; ws.N = N; ws.bw = 0; ws.bwx = 0; ws.LD = 0; ws.use_pin = 0; ws.nops = nops;
+    Lu3Params pr;
+    for (int k = 0; k < 3; ++k) pr.alpha[k] = gp.alpha[k];
+    pr.gamma = gp.gamma; pr.lm = 1; pr.ln = 1; pr.refine = 0;
+
+    NdDev nd;
+    nd.n = n; nd.N = N; nd.W = ND3_W; nd.nnb = sym.nnb; nd.nh = nd_nh(ND3_W); nd.mb = 1;
+    nd.nfronts = nf; nd.nsteps = nsteps;
+    nd.fronts = (const NdFront *)w.plan.d_fronts; nd.pixlist = (const int *)w.plan.d_pixlist;
+    nd.nbr = (const int *)w.plan.d_nbr; nd.cmap = (const int *)w.plan.d_cmap; nd.step_start = (const int *)w.plan.d_step_start;
+    nd.off = nullptr; nd.off_stride = 0;
+    nd.posg = (int *)w.plan.d_posg1; nd.posg_stride = 0;
+    nd.foff = (long long *)w.plan.d_foff1; nd.foff_stride = 0;
+    nd.totals = nullptr;
+    nd.L = (double *)w.L.p; nd.L_stride = Ls;
+    nd.U[0] = (double *)w.U0.p; nd.U[1] = (double *)w.U1.p; nd.U_stride = Us;
+    nd.UV[0] = (double *)w.UV0.p; nd.UV[1] = (double *)w.UV1.p; nd.UV_stride = UVs;
+    nd.ast = (const double *)w.ast.p; nd.ast_stride = ast_stride;
+    nd.info = (int *)w.info.p;
+
+    const double tol = gp.tol > 0 ? gp.tol : 1e300;
+    const int refine = gp.maxit > 0 ? std::min(gp.maxit, 8) : 1;
+    const int chunks = std::max(1, std::min(64, (N + 255) / 256));
+    for (int img0 = 0; img0 < gp.O; img0 += slots) {
+        const int cnt = std::min(slots, gp.O - img0);
+        cudaMemsetAsync(w.ast.p, 0, ast_stride * 8 * cnt, st);
+        cudaMemsetAsync(w.info.p, 0, (size_t)16 * cnt, st);
+        lu3_classify_kernel<Real><<<dim3(cnt, chunks), 256, 0, st>>>(ws, pr.gamma, gp_u, gp_ubar, img0);
+        nd3_stencil_kernel<<<dim3(cnt, chunks), 256, 0, st>>>(ws, pr, (double *)w.ast.p, ast_stride);
+        *launches += 2;
+        nd_launch_factor(nd, plan, plan_small, sym, 1, cnt, sm_count, 0.0, st, launches);
+        double *p = ws.pix + (size_t)LU_PL_P * N, *work = ws.pix + (size_t)LU_PL_WORK * N;
+        nd_launch_solve(nd, plan, cnt, p, pix_stride, st, launches);
+        nd3_residual_kernel<Real><<<cnt, 512, 0, st>>>(ws, pr, (double *)w.relres.p, img0);
+        for (int it = 0; it < refine; ++it) {
+            nd_launch_solve(nd, plan, cnt, work, pix_stride, st, launches);
+            nd3_axpy_kernel<<<dim3(cnt, chunks), 256, 0, st>>>(ws);
+            nd3_residual_kernel<Real><<<cnt, 512, 0, st>>>(ws, pr, (double *)w.relres.p, img0);
+        }
+        nd3_finish_kernel<<<cnt, 512, 0, st>>>(ws, pr, (const int *)w.info.p, tol, (double *)w.out_img.p, (double *)w.relres.p, img0);
+        *launches += 2 + 2 * refine;
+    }
+    nd_reduce_kernel<<<1, 32, 0, st>>>((double *)w.out_img.p, (double *)w.relres.p, gp.O, nops * ng, d_grad_out,
+                                       (double *)w.relres_max.p);
+    *launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return nd_fail(w, -2, std::string("nested-dissection kernel launch failed: ") + cudaGetErrorString(e));
+    return 0;
+}
+
 NdWork *nd_work_create() { return new NdWork(); }
 void nd_work_destroy(NdWork *w) { if (w) { w->release(); delete w; } }
 const char *nd_work_error(const NdWork *w) { return w->err.c_str(); }
@@ -388,6 +541,12 @@ int nd_run_gradient(NdWork *w, const NdProblem &gp, int sm_count, size_t smem_op
 {
     return gp.prec == 64 ? run_gradient_nd<double>(*w, gp, sm_count, smem_optin, st, d_grad_out, launches)
                          : run_gradient_nd<float>(*w, gp, sm_count, smem_optin, st, d_grad_out, launches);
+}
+int nd_run_gradient3_reg(NdWork *w, const Nd3Problem &gp, int sm_count, size_t smem_optin, cudaStream_t st, double *d_grad_out,
+                         long long *launches)
+{
+    return gp.prec == 64 ? run_gradient3_nd_reg<double>(*w, gp, sm_count, smem_optin, st, d_grad_out, launches)
+                         : run_gradient3_nd_reg<float>(*w, gp, sm_count, smem_optin, st, d_grad_out, launches);
 }
 
 }  // namespace bpltv

@@ -23,6 +23,18 @@ struct NdProblem {
     int maxit;                  // refinement steps (≤ 0: default)
 };
 
+// scalar sumregs_gradient_reg of /root/reference/src/SumRegsLearningFunction.jl:112-167 (three difference operators,
+// symmetric node-space system, coupling radius 2) for a stack of O images on the device
+struct Nd3Problem {
+    const void *u, *ubar;
+    int prec;
+    int M, N, O;
+    double alpha[3];
+    double gamma;
+    double tol;                 // backward error above which the result is poisoned with NaN (≤ 0: never)
+    int maxit;                  // refinement steps (≤ 0: default)
+};
+
 NdWork *nd_work_create();
 void nd_work_destroy(NdWork *w);
 const char *nd_work_error(const NdWork *w);
@@ -31,5 +43,8 @@ const double *nd_work_relres_max(const NdWork *w);      // device pointer: worst
 // 0 ok; -1: the shape is not taken (fronts beyond shared memory) — use the band solver; other negatives: bpltv_status
 int nd_run_gradient(NdWork *w, const NdProblem &gp, int sm_count, size_t smem_optin, cudaStream_t st, double *d_grad_out,
                     long long *launches);
+// d_grad_out: 3 doubles (one per operator).  Use a workspace of its own (the plan is keyed by the coupling radius).
+int nd_run_gradient3_reg(NdWork *w, const Nd3Problem &gp, int sm_count, size_t smem_optin, cudaStream_t st, double *d_grad_out,
+                         long long *launches);
 
 }  // namespace bpltv

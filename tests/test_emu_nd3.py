@@ -1,0 +1,119 @@
+"""CPU check of the scalar `sumregs_gradient_reg` on the nested-dissection solver (bpldenoising_b200/csrc/
+nd_sumregs.cuh + nd_solver.cuh at coupling radius 2) where no GPU exists: the device code is compiled with g++
+against tests/emu/emu_cuda.h and run for one image in the launch order of gradient_nd.cuh's run_gradient3_nd_reg,
+then compared with the oracle's literal system (/root/reference/src/SumRegsLearningFunction.jl:112-167, γ = 1e3).
+The GPU parity test proper is tests/test_gpu_sumregs.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import sumregs as sr
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, "emu")
+CSRC = os.path.join(HERE, "..", "bpldenoising_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    out = os.path.join(EMU, "_build", "libemu_nd3.so")
+    srcs = [os.path.join(EMU, "emu_nd3.cpp"), os.path.join(EMU, "emu_cuda.h")] + \
+           [os.path.join(CSRC, f) for f in ("nd_symbolic.h", "nd_solver.cuh", "nd_sumregs.cuh", "lu_band.cuh",
+                                            "sumregs_stencils.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-fPIC", "-shared", "-DBPLTV_EMU", "-ffp-contract=off",
+                        "-o", out, srcs[0]], check=True)
+    lib = C.CDLL(out)
+    lib.emu_nd3_gradient_reg.restype = C.c_int
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _case(n, seed):
+    rng = np.random.default_rng(seed)
+    t = np.round(rng.random((n, n)) * 255) / 255
+    u = np.asfortranarray(t + 0.05 * rng.standard_normal((n, n)))
+    u[:3, :3] = u[0, 0]                      # an exactly flat block: |∇_k u| = 0, the γ·I tensors
+    u[n - 4:, n - 5:] = u[n - 1, n - 1]
+    return np.asfortranarray(t), u
+
+
+def _run(lib, u, t, x, gamma=1e3, refine=1, leaf=4, small=1, want_ast=False):
+    n = u.shape[0]
+    out, stats, p = np.zeros(3), np.zeros(6), np.zeros(n * n)
+    ast = np.zeros(13 * n * n) if want_ast else None
+    rc = lib.emu_nd3_gradient_reg(n, _ptr(u.flatten(order="F")), _ptr(t.flatten(order="F")),
+                                  _ptr(np.asarray(x, dtype=np.float64)), C.c_double(gamma), refine, leaf, int(small),
+                                  _ptr(out), _ptr(stats), _ptr(p), _ptr(ast))
+    assert rc == 0
+    return out, stats, p, (None if ast is None else ast.reshape(n * n, 13))
+
+
+def _literal_matrix(x, u, gamma):
+    n = u.shape[0]
+    uf = u.flatten(order="F")
+    A = sp.identity(n * n, format="csr")
+    for k, kind in enumerate(sr.KINDS):
+        G = sr.op_matrix(kind, n)
+        BmC, _ = sr._sets_reg(G, uf, gamma)
+        A = A + x[k] * (G.T @ BmC @ G)
+    return A.toarray()
+
+
+def test_stencil_form_is_the_literal_matrix(lib):
+    """nd3_stencil_kernel's 13 forward offsets per node = the lower triangle of I + Σ α_k G_kᵀ(B_k − C_k)G_k (:160)"""
+    n = 11
+    t, u = _case(n, 3)
+    x = np.array([0.05, 0.04, 0.06])
+    _, _, _, ast = _run(lib, u, t, x, want_ast=True)
+    A = _literal_matrix(x, u, 1e3)
+    S = np.zeros_like(A)
+    h = 0
+    offs = [(0, 0), (1, 0), (2, 0)] + [(di, dj) for dj in (1, 2) for di in (-2, -1, 0, 1, 2)]
+    for h, (di, dj) in enumerate(offs):
+        for v in range(n * n):
+            i, j = v % n, v // n
+            if 0 <= i + di < n and 0 <= j + dj < n:
+                w = (i + di) + n * (j + dj)
+                S[w, v] = ast[v, h]
+                S[v, w] = ast[v, h]
+            else:
+                assert ast[v, h] == 0.0
+    assert np.abs(S - A).max() <= 1e-15 * np.abs(A).max()
+    assert np.abs(A - A.T).max() <= 1e-13 * np.abs(A).max()         # symmetric: why the Cholesky applies
+
+
+@pytest.mark.parametrize("n,leaf", [(8, 4), (13, 4), (24, 4), (24, 6), (37, 5)])
+def test_scalar_reg_gradient(lib, n, leaf):
+    t, u = _case(n, 40 + n)
+    x = np.array([0.05, 0.04, 0.06])
+    got, stats, p, _ = _run(lib, u, t, x, leaf=leaf)
+    lit = sr.sumregs_gradient_reg(x, u, t, refine=3)
+    assert stats[1] == 0 and stats[0] <= 1e-15, stats
+    assert np.all(np.abs(got - lit) <= 1e-11 * np.abs(lit).max()), (got, lit)
+
+
+def test_small_front_kernels_equal_the_generic_ones(lib):
+    t, u = _case(30, 9)
+    x = np.array([0.1, 0.02, 0.07])
+    g0, s0, p0, _ = _run(lib, u, t, x, small=0)
+    g1, s1, p1, _ = _run(lib, u, t, x, small=1)
+    assert np.all(np.abs(g1 - g0) <= 1e-12 * np.abs(g0).max())
+    assert np.linalg.norm(p1 - p0) <= 1e-12 * np.linalg.norm(p0)
+
+
+def test_one_operator_switched_off(lib):
+    """α_k = 0 for two operators: the TV gradient_reg system with γ = 1e3 (forward differences only)"""
+    t, u = _case(16, 5)
+    x = np.array([0.08, 0.0, 0.0])
+    got, stats, _, _ = _run(lib, u, t, x)
+    lit = sr.sumregs_gradient_reg(x, u, t, refine=3)
+    assert np.all(np.abs(got - lit) <= 1e-11 * np.abs(lit).max()), (got, lit)

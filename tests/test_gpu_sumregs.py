@@ -242,6 +242,44 @@ def test_scalar_bilevel_sumregs_learn_run(bp, ctx, datasets):
     assert res.log[-1].function_value <= c0
 
 
+def test_scalar_sumregs_gradient_reg_nested_dissection_vs_band_lu(bp, ctx, ctx32, sr, datasets):
+    """Scalar sumregs_gradient_reg (:112-167, γ = 1e3) takes the nested-dissection multifrontal Cholesky at coupling
+    radius 2 (nd_sumregs.cuh; eval_opts.solver 0) — against the node-space band LU (solver 1), an independent second
+    implementation, and against the refined literal sparse solve: 1e-9 (the bar of the regularised variants); the
+    solver's backward error is reported.  Several images, an odd size, the reference's 128², an fp32 context."""
+    import os
+    x = np.array([0.03, 0.02, 0.04])
+    for n, k, off in ((37, 3, 30), (128, 2, 0)):
+        t, f = _crop(datasets, "faces_train_128_10", n, k=k, off=off)
+        u = np.asfortranarray(ctx.sumregs_denoise(f, x, bp.sumregs_pdps_opts(maxiter=300)))
+        u[2:9, 3:8, 0] = u[2, 3, 0]                     # exactly flat pixels: the γ·I tensors
+        ctx.set_dataset((t, f))
+        g_nd = ctx.sumregs_gradient(x, u, regularised=True)
+        st = ctx.stats()
+        assert st["solver_max_relres"] <= 1e-14, st
+        launches_nd = st["kernel_launches"]
+        os.environ["BPLTV_GRAD_SOLVER"] = "1"
+        bp.reload_env()
+        try:
+            g_lu = ctx.sumregs_gradient(x, u, regularised=True)
+            launches_lu = ctx.stats()["kernel_launches"]
+        finally:
+            del os.environ["BPLTV_GRAD_SOLVER"]
+            bp.reload_env()
+        assert launches_nd != launches_lu                # two different paths did run
+        assert np.all(np.abs(g_nd - g_lu) <= 1e-10 * np.abs(g_lu).max()), (n, g_nd, g_lu)
+        if n <= 48:
+            lit = sum(sr.sumregs_gradient_reg(x, u[:, :, i], t[:, :, i], refine=3) for i in range(k))
+            assert np.all(np.abs(g_nd - lit) <= 1e-9 * np.abs(lit).max()), (g_nd, lit)
+        # fp32 context: the fp32 u, adjoint system in fp64 — north_star's 1e-5 on the same u
+        ctx32.set_dataset((t, f))
+        g32 = ctx32.sumregs_gradient(x, u.astype(np.float32).astype(np.float64), regularised=True)
+        u32 = np.asfortranarray(u.astype(np.float32).astype(np.float64))
+        ctx.set_dataset((t.astype(np.float32).astype(np.float64), f))
+        g64 = ctx.sumregs_gradient(x, u32, regularised=True)
+        assert np.all(np.abs(g32 - g64) <= 1e-5 * np.abs(g64).max()), (g32, g64)
+
+
 def test_cluster_factorisation_is_invisible(bp, ctx, sr, datasets):
     """The banded Cholesky shared by a thread-block cluster (2, 4, 8 CTAs per image) gives bit-identical
     gradients to the single-CTA factorisation, for the TV and the sum-of-regularisers systems."""

@@ -30,13 +30,22 @@ for name, k in (("cameraman_128_5", 1), ("faces_train_128_10", 10)):
         xp = 0.001 * np.ones((2, 2, 3)); xp[1, 0, :] *= 1.5
         us = c.sumregs_denoise(None, xs, bp.sumregs_pdps_opts(maxiter=2000))
         up = c.sumregs_denoise(None, xp, bp.sumregs_pdps_opts(maxiter=2000))
+        os.environ["BPLTV_GRAD_SOLVER"] = "1"            # the banded solvers of round 1
         os.environ["BPLTV_SUMREGS_REG_LU"] = "0"
+        bp.reload_env()
         ms_c, g_c = timed(c, xs, True, us)
         os.environ["BPLTV_SUMREGS_REG_LU"] = "1"
+        bp.reload_env()
         ms_l, g_l = timed(c, xs, True, us)
+        os.environ.pop("BPLTV_GRAD_SOLVER")
         os.environ.pop("BPLTV_SUMREGS_REG_LU")
+        bp.reload_env()
         print("%s x%d scalar reg: Cholesky %.1f ms, band LU %.1f ms, rel diff %.2e" %
               (name, k, ms_c, ms_l, np.abs(g_c - g_l).max() / np.abs(g_c).max()), flush=True)
+        ms_nd, g_nd = timed(c, xs, True, us)
+        print("%s x%d scalar reg: nested dissection (W=2) %.2f ms, rel diff to band LU %.2e, relres %.1e, %d launches" %
+              (name, k, ms_nd, np.abs(g_nd - g_l).max() / np.abs(g_l).max(), c.stats()["solver_max_relres"],
+               c.stats()["kernel_launches"]), flush=True)
         ms_p, g_p = timed(c, xp, True, up)
         print("%s x%d patch reg (band LU): %.1f ms" % (name, k, ms_p), flush=True)
         ms_n, _ = timed(c, xs, False, us)
@@ -49,3 +58,23 @@ with bp.Context([0], 64) as c:
     up = c.sumregs_denoise(None, xp, bp.sumregs_pdps_opts(maxiter=500))
     ms_p, g_p = timed(c, xp, True, up, reps=2)
     print("synthetic 256x256 x2 patch reg (band LU): %.1f ms, finite %s" % (ms_p, bool(np.all(np.isfinite(g_p)))), flush=True)
+# many images: scalar sumregs_gradient_reg on the nested-dissection solver vs the band LU
+for n, k in ((128, 148), (256, 32)):
+    t, f = bp.synthetic_dataset(n, n, k, seed=20240602)
+    with bp.Context([0], 64) as c:
+        c.set_dataset((t, f))
+        xs = np.array([0.01, 0.01, 0.01])
+        us = c.sumregs_denoise(None, xs, bp.sumregs_pdps_opts(maxiter=300))
+        ms_nd, g_nd = timed(c, xs, True, us, reps=3)
+        rr = c.stats()["solver_max_relres"]
+        os.environ["BPLTV_GRAD_SOLVER"] = "1"
+        bp.reload_env()
+        try:
+            ms_l, g_l = timed(c, xs, True, us, reps=2)
+        except bp.BpltvError as e:
+            ms_l, g_l = float("nan"), g_nd
+            print("band LU refused:", e)
+        os.environ.pop("BPLTV_GRAD_SOLVER")
+        bp.reload_env()
+        print("synthetic %dx%d x%d scalar reg: nested dissection %.1f ms (relres %.1e), band LU %.1f ms, rel diff %.2e" %
+              (n, n, k, ms_nd, rr, ms_l, np.abs(g_nd - g_l).max() / np.abs(g_l).max()), flush=True)
