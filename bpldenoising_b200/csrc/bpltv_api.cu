@@ -943,6 +943,19 @@ static int sumregs_eval_on_device(bpltv_ctx *ctx, Dev &d, const double *lam, int
             if (rc == 0) d.grad3_used_nd = true;
             else if (rc != -1) return fail(rc, "sumregs gradient: %s", nd_work_error(d.nd3));
         }
+        // sumregs_gradient (non-regularised, scalar :264-327 and patch :330-407): the same solver in multiplier space
+        // (3-6 unknowns per pixel); fronts beyond shared memory (-1) go to the band Cholesky
+        if (!gp.regularised && solver != 1 && M == N) {
+            if (!d.nd3) d.nd3 = nd_work_create();
+            Nd3mProblem np;
+            np.u = u; np.ubar = d.truth.as<Real>(); np.alpha_maps = amap; np.prec = (int)sizeof(Real) * 8;
+            np.M = M; np.N = N; np.O = O; np.lm = lm; np.ln = ln;
+            for (int k = 0; k < 3; ++k) np.alpha[k] = gp.alpha[k];
+            np.act_tol = gp.act_tol; np.eps_act = gp.eps_act; np.tol = 0.0; np.maxit = eo.solver_maxit;
+            rc = nd_run_gradient3(d.nd3, np, d.sm_count, d.smem_optin, st, d_costgrad + 1, &d.launches);
+            if (rc == 0) d.grad3_used_nd = true;
+            else if (rc != -1) return fail(rc, "sumregs gradient: %s", nd_work_error(d.nd3));
+        }
         if (rc == -1) rc = run_gradient3<Real>(d.grad3, gp, d.sm_count, d.smem_optin, st, d_costgrad + 1, &d.launches);
         if (rc != 0) return fail(rc == -1 ? BPLTV_ERR_ARG : rc, "sumregs gradient: %s", d.grad3.err.c_str());
     }

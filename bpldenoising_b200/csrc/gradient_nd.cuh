@@ -9,6 +9,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "env_switches.h"
@@ -73,8 +74,9 @@ struct NdBuf {
 struct NdWork {
     std::string err;
     NdPlan plan;
-    NdBuf pix, off, vec, posg, foff, totals, ast, L, U0, U1, UV0, UV1, info, out_img, relres, relres_max;
+    NdBuf pix, off, off3, lvl, vec, posg, foff, totals, ast, L, U0, U1, UV0, UV1, info, out_img, relres, relres_max;
     std::vector<long long> h_totals;
+    size_t budget_cached = 0;
     // what the last call saw (statistics)
     double last_relres = 0.0;
     long long last_guarded = 0;
@@ -85,7 +87,7 @@ struct NdWork {
     {
         slots_key_n = slots_key_node = slots_key_want = -1;
         plan.release();
-        NdBuf *all[] = {&pix, &off, &vec, &posg, &foff, &totals, &ast, &L, &U0, &U1, &UV0, &UV1, &info, &out_img, &relres, &relres_max};
+        NdBuf *all[] = {&pix, &off, &off3, &lvl, &vec, &posg, &foff, &totals, &ast, &L, &U0, &U1, &UV0, &UV1, &info, &out_img, &relres, &relres_max};
         for (NdBuf *b : all) b->release();
     }
 };
@@ -135,6 +137,52 @@ static inline int nd_build_plan(NdPlan &pl, int n, int W, cudaStream_t st, std::
 
 static inline int nd_fail(NdWork &w, int code, const std::string &msg) { w.err = msg; return code; }
 
+// Opt-in shared memory of the front kernels.  -1: a front does not fit (the caller falls back to a band solver).
+static int nd_kernel_attributes(NdWork &w, size_t fsmem, size_t ssmem, size_t fsmem_small, size_t ssmem_small, size_t smem_optin)
+{
+    if (fsmem > smem_optin || ssmem > smem_optin || fsmem_small > smem_optin || ssmem_small > smem_optin)
+        return -1;      // the caller falls back to the band solver
+    {
+        // the opt-in shared-memory size is an attribute of the KERNEL on the current device, shared by every workspace
+        // that launches it (the TV solver and the sum-of-regularisers one): raised to the largest any of them asked for
+        static std::mutex mu;
+        static int have[64][5] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        dev = std::max(0, std::min(63, dev));
+        std::lock_guard<std::mutex> lock(mu);
+        cudaError_t e = cudaSuccess;
+        if (have[dev][0] < (int)fsmem) {
+            e = cudaFuncSetAttribute(nd_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+            if (e == cudaSuccess) have[dev][0] = (int)fsmem;
+        }
+        if (e == cudaSuccess && have[dev][4] < (int)fsmem) {
+            e = cudaFuncSetAttribute(nd_factor_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(nd_factor_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e == cudaSuccess) have[dev][4] = (int)fsmem;
+        }
+        if (e == cudaSuccess && have[dev][1] < (int)ssmem) {
+            e = cudaFuncSetAttribute(nd_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(nd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem);
+            if (e == cudaSuccess) have[dev][1] = (int)ssmem;
+        }
+        if (e == cudaSuccess && have[dev][2] < (int)fsmem_small) {
+            e = cudaFuncSetAttribute(nd_factor_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem_small);
+            if (e == cudaSuccess) have[dev][2] = (int)fsmem_small;
+        }
+        if (e == cudaSuccess && have[dev][3] < (int)ssmem_small) {
+            e = cudaFuncSetAttribute(nd_fwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem_small);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(nd_bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem_small);
+            if (e == cudaSuccess) have[dev][3] = (int)ssmem_small;
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return nd_fail(w, -2, std::string("nested-dissection kernel attributes: ") + cudaGetErrorString(e));
+        }
+    }
+    return 0;
+}
+
 // Launch plan of every level of the tree for `mb` unknowns per pixel at most (`fsz` typical): CTA sizes, shared memory of
 // the largest front (worst case: mb unknowns on every pixel), kernel attributes.  -1: a front does not fit in shared
 // memory (the caller falls back to a band solver).
@@ -160,42 +208,70 @@ static int nd_prepare_levels(NdWork &w, const NdSymbolic &sym, int mb, double fs
         fsmem = std::max(fsmem, nd_factor_smem(plan[s].nFw, s > 0 ? mb * sym.step_max_ring_pix[s - 1] : 0));
         ssmem = std::max(ssmem, nd_solve_smem(plan[s].nFw));
     }
-    if (fsmem > smem_optin || ssmem > smem_optin || fsmem_small > smem_optin || ssmem_small > smem_optin)
-        return -1;      // the caller falls back to the band solver
-    {
-        // the opt-in shared-memory size is an attribute of the KERNEL on the current device, shared by every workspace
-        // that launches it (the TV solver and the sum-of-regularisers one): raised to the largest any of them asked for
-        static std::mutex mu;
-        static int have[64][4] = {};
-        int dev = 0;
-        cudaGetDevice(&dev);
-        dev = std::max(0, std::min(63, dev));
-        std::lock_guard<std::mutex> lock(mu);
-        cudaError_t e = cudaSuccess;
-        if (have[dev][0] < (int)fsmem) {
-            e = cudaFuncSetAttribute(nd_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
-            if (e == cudaSuccess) have[dev][0] = (int)fsmem;
-        }
-        if (e == cudaSuccess && have[dev][1] < (int)ssmem) {
-            e = cudaFuncSetAttribute(nd_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(nd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem);
-            if (e == cudaSuccess) have[dev][1] = (int)ssmem;
-        }
-        if (e == cudaSuccess && have[dev][2] < (int)fsmem_small) {
-            e = cudaFuncSetAttribute(nd_factor_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem_small);
-            if (e == cudaSuccess) have[dev][2] = (int)fsmem_small;
-        }
-        if (e == cudaSuccess && have[dev][3] < (int)ssmem_small) {
-            e = cudaFuncSetAttribute(nd_fwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem_small);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(nd_bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem_small);
-            if (e == cudaSuccess) have[dev][3] = (int)ssmem_small;
-        }
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            return nd_fail(w, -2, std::string("nested-dissection kernel attributes: ") + cudaGetErrorString(e));
-        }
+    return nd_kernel_attributes(w, fsmem, ssmem, fsmem_small, ssmem_small, smem_optin);
+}
+
+// CTAs per front of a level (a thread-block cluster shares the front: nd_factor_body<true>): the top levels of the tree
+// have fewer fronts than the GPU has SMs, and their fronts are the large ones.  As many as leave every front of the
+// wave its own cluster, while every warp of the cluster still has a tile of the trailing update.  BPLTV_ND_CLUSTER = 1
+// switches it off, 2 / 4 / 8 / 16 caps the size; BPLTV_ND_CLUSTER_MINF: smallest front (unknowns) that is shared.
+static int nd_cluster_size(const NdLevelPlan &lp, int cnt, int sm_count)
+{
+    const char *e1 = bpltv::env_get("BPLTV_ND_CLUSTER"), *e2 = bpltv::env_get("BPLTV_ND_CLUSTER_MINF");
+    const int cap = e1 && *e1 ? std::max(1, std::min(16, atoi(e1))) : 16;
+    const int minf = e2 && *e2 ? atoi(e2) : 256;
+    if (lp.small || lp.nFw < minf || cap < 2) return 1;
+    const long long fronts = (long long)lp.nfr * cnt;
+    const int nt = (lp.nFw + 31) / 32, ntiles = nt * (nt + 1) / 2, warps = lp.threads_f / 32;
+    long long C = std::min<long long>(cap, sm_count / std::max<long long>(1, fronts));
+    C = std::min<long long>(C, ntiles / (2 * warps));       // two tiles per warp of the cluster at least
+    return (int)std::max<long long>(1, C);
+}
+
+// how many clusters of C CTAs (threads, dynamic shared memory) the device runs at once: asked of the driver once per shape
+static int nd_active_clusters(int C, int threads, size_t smem)
+{
+    static std::mutex mu;
+    static std::unordered_map<unsigned long long, int> memo;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long key = ((unsigned long long)dev << 48) ^ ((unsigned long long)C << 40) ^ ((unsigned long long)threads << 24) ^
+                                   (unsigned long long)(smem >> 8);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = memo.find(key);
+    if (it != memo.end()) return it->second;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)C); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, nd_factor_cluster_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); nclusters = 0; }
+    memo[key] = nclusters;
+    return nclusters;
+}
+
+// launch of the cluster-shared front factorisation; the cluster shrinks until the device runs all fronts of the level at once
+static cudaError_t nd_launch_factor_cluster(const NdDev &nd, const NdLevelPlan &lp, int s, int cnt, int C, double guard, cudaStream_t st)
+{
+    const size_t smem = nd_factor_smem(lp.nFw, lp.nRc);
+    const long long fronts = (long long)lp.nfr * cnt;
+    while (C > 1 && nd_active_clusters(C, lp.threads_f, smem) < fronts) --C;
+    if (C > 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(lp.nfr * C), (unsigned)cnt);
+        cfg.blockDim = dim3((unsigned)lp.threads_f);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, nd_factor_cluster_kernel, nd, lp.t0, s & 1, guard, lp.nFw);
     }
-    return 0;
+    nd_factor_kernel<<<dim3(lp.nfr, cnt), lp.threads_f, smem, st>>>(nd, lp.t0, s & 1, guard, lp.nFw);
+    return cudaGetLastError();
 }
 
 // one launch per level: assemble + partial Cholesky of every front of the wave's `cnt` images
@@ -211,8 +287,11 @@ static void nd_launch_factor(const NdDev &nd, std::vector<NdLevelPlan> &plan, co
         if (lp.small)
             nd_factor_small_kernel<<<dim3((lp.nfr + ND_SMALL_WARPS - 1) / ND_SMALL_WARPS, cnt), 32 * ND_SMALL_WARPS, lp.smem_f, st>>>(
                 nd, lp.t0, lp.nfr, s & 1, guard, lp.arena_f);
-        else
-            nd_factor_kernel<<<dim3(lp.nfr, cnt), lp.threads_f, nd_factor_smem(lp.nFw, s > 0 ? mb * sym.step_max_ring_pix[s - 1] : 0), st>>>(nd, lp.t0, s & 1, guard, lp.nFw);
+        else {
+            const int C = nd_cluster_size(lp, cnt, sm_count);
+            if (C > 1) nd_launch_factor_cluster(nd, lp, s, cnt, C, guard, st);
+            else nd_factor_kernel<<<dim3(lp.nfr, cnt), lp.threads_f, nd_factor_smem(lp.nFw, lp.nRc), st>>>(nd, lp.t0, s & 1, guard, lp.nFw);
+        }
     }
     *launches += nsteps;
 }
@@ -531,6 +610,164 @@ static int run_gradient3_nd_reg(NdWork &w, const Nd3Problem &gp, int sm_count, s
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// sumregs_gradient (non-regularised) on the same solver: multiplier space, 3-6 unknowns per pixel, W = 2.  Front sizes
+// are data: measured per level on the device (nd_level_sizes_kernel) and read back with the pool totals, one
+// synchronisation per wave; a front beyond shared memory sends the call back to the band Cholesky (-1).
+// ---------------------------------------------------------------------------
+template <typename Real>
+static int run_gradient3_nd_mult(NdWork &w, const Nd3mProblem &gp, int sm_count, size_t smem_optin, cudaStream_t st,
+                                 double *d_grad_out, long long *launches)
+{
+    const Real *gp_u = static_cast<const Real *>(gp.u), *gp_ubar = static_cast<const Real *>(gp.ubar),
+               *gp_amaps = static_cast<const Real *>(gp.alpha_maps);
+    const int n = gp.M, N = gp.M * gp.N, ng = gp.lm * gp.ln, mb = ND3M_MB;
+    if (gp.M != gp.N) return nd_fail(w, -1, "square images required");
+    if (n < 8) return -1;
+    if (3 * ng > 65536) return nd_fail(w, -1, "lambda grid too large");
+    {
+        const int rc = nd_build_plan(w.plan, n, ND3_W, st, w.err);
+        if (rc != 0) return rc;
+    }
+    const NdSymbolic &sym = w.plan.sym;
+    const int nf = (int)sym.fronts.size(), nsteps = sym.nsteps();
+    if (nsteps > 62) return nd_fail(w, -1, "image too large for the nested-dissection level table");
+    const char *e1 = bpltv::env_get("BPLTV_ND_WARPS_F");
+    const int cta_warps_f = e1 && *e1 ? std::max(2, std::min(16, atoi(e1))) : 16;
+
+    const long long *t1 = w.plan.tot1;
+    const size_t pix_stride = (size_t)ND3M_PLANES * N, ast_stride = (size_t)ND3_NH * mb * mb * N;
+    const size_t off3_stride = (size_t)3 * N + 1, poff_stride = (size_t)N + 2, vec_stride = (size_t)3 * mb * N;
+    const size_t fix_bytes = (pix_stride + ast_stride + vec_stride) * 8 + (off3_stride + poff_stride + w.plan.posg_len) * 4 +
+                             (size_t)4 * nf * 8 + 32 + 16;
+    // pools grow with the square of the unknowns per pixel: estimated at 4 per pixel, checked against the measured sizes
+    const size_t pool_est = (size_t)(16.0 * (double)(t1[0] + 2 * t1[1]) + 4.0 * (double)(2 * t1[2])) * 8;
+    int slots = std::min(gp.O, 64);
+    if (w.slots_key_n == n && w.slots_key_node == 4 && w.slots_key_want == slots) {
+        slots = w.slots_cached;
+    } else {
+        const int want = slots;
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const size_t have = w.pix.bytes + w.ast.bytes + w.L.bytes + w.U0.bytes + w.U1.bytes + w.vec.bytes + w.posg.bytes + w.foff.bytes;
+        w.budget_cached = (free_b + have) / 2;
+        slots = (int)std::min<size_t>((size_t)slots, std::max<size_t>(1, w.budget_cached / (fix_bytes + pool_est)));
+        w.slots_key_n = n; w.slots_key_node = 4; w.slots_key_want = want; w.slots_cached = slots;
+    }
+    auto need = [&](NdBuf &b, size_t bytes, const char *what) -> int {
+        cudaError_t e = b.ensure(bytes);
+        if (e != cudaSuccess) {
+            w.slots_key_n = -1;
+            return nd_fail(w, -6, std::string("nested-dissection workspace (") + what + "): " + cudaGetErrorString(e));
+        }
+        return 0;
+    };
+    int rc = 0;
+    if ((rc = need(w.out_img, (size_t)gp.O * 3 * ng * 8, "per-image gradients"))) return rc;
+    if ((rc = need(w.relres, (size_t)gp.O * 8, "residuals"))) return rc;
+    if ((rc = need(w.relres_max, 16, "residual maximum"))) return rc;
+    if ((rc = need(w.lvl, 512, "level sizes"))) return rc;
+
+    Nd3mVariant gv;
+    gv.patch = gp.alpha_maps != nullptr; gv.lm = gp.lm; gv.ln = gp.ln;
+    for (int k = 0; k < 3; ++k) gv.alpha[k] = gp.alpha[k];
+    gv.act_tol = gp.act_tol; gv.eps_act = gp.eps_act; gv.relres_tol = gp.tol > 0 ? gp.tol : 1e300;
+    const double guard = 1e-13;
+    const int refine = gp.maxit > 0 ? std::min(gp.maxit, 8) : 1;
+    const int chunks = std::max(1, std::min(64, (N + 255) / 256));
+    const int chunks_st = std::max(1, std::min(512, (int)(((long long)N * ND3_NH + 255) / 256)));
+    std::vector<NdLevelPlan> plan(nsteps);
+    const std::vector<char> plan_small(nsteps, 0);
+    int h_lvl[128];
+
+    for (int img0 = 0; img0 < gp.O;) {
+        const int cnt = std::min(slots, gp.O - img0);
+        if ((rc = need(w.pix, pix_stride * 8 * slots, "pixel planes"))) return rc;
+        if ((rc = need(w.ast, ast_stride * 8 * slots, "stencil matrix"))) return rc;
+        if ((rc = need(w.info, (size_t)16 * slots, "info"))) return rc;
+        if ((rc = need(w.off, poff_stride * 4 * slots, "mode offsets"))) return rc;
+        if ((rc = need(w.off3, off3_stride * 4 * slots, "mode offsets"))) return rc;
+        if ((rc = need(w.vec, vec_stride * 8 * slots, "mode vectors"))) return rc;
+        if ((rc = need(w.posg, w.plan.posg_len * 4 * slots, "front offsets"))) return rc;
+        if ((rc = need(w.foff, (size_t)4 * nf * 8 * slots, "pool offsets"))) return rc;
+        if ((rc = need(w.totals, (size_t)32 * slots, "pool totals"))) return rc;
+        Nd3mSlots ws;
+        ws.n = n; ws.N = N; ws.pix = (double *)w.pix.p; ws.pix_stride = pix_stride;
+        ws.off3 = (int *)w.off3.p; ws.off3_stride = off3_stride; ws.poff = (int *)w.off.p; ws.poff_stride = poff_stride;
+        ws.vec = (double *)w.vec.p; ws.vec_stride = vec_stride; ws.info = (int *)w.info.p;
+        NdDev nd;
+        nd.n = n; nd.N = N; nd.W = ND3_W; nd.nnb = sym.nnb; nd.nh = nd_nh(ND3_W); nd.mb = mb;
+        nd.nfronts = nf; nd.nsteps = nsteps;
+        nd.fronts = (const NdFront *)w.plan.d_fronts; nd.pixlist = (const int *)w.plan.d_pixlist;
+        nd.nbr = (const int *)w.plan.d_nbr; nd.cmap = (const int *)w.plan.d_cmap; nd.step_start = (const int *)w.plan.d_step_start;
+        nd.off = ws.poff; nd.off_stride = poff_stride;
+        nd.posg = (int *)w.posg.p; nd.posg_stride = w.plan.posg_len;
+        nd.foff = (long long *)w.foff.p; nd.foff_stride = (size_t)4 * nf;
+        nd.totals = (long long *)w.totals.p;
+        nd.ast = (const double *)w.ast.p; nd.ast_stride = ast_stride;
+        nd.info = ws.info;
+
+        cudaMemsetAsync(w.lvl.p, 0, 512, st);
+        nd3m_classify_kernel<Real><<<cnt, 512, 0, st>>>(ws, gv, gp_u, gp_ubar, gp_amaps, img0);
+        nd_dims_kernel<<<dim3((nf + 7) / 8, cnt), 256, 0, st>>>(nd);
+        nd_scan_kernel<<<cnt, 256, 0, st>>>(nd);
+        nd_level_sizes_kernel<<<dim3((nf + 255) / 256, cnt), 256, 0, st>>>(nd, (int *)w.lvl.p);
+        nd3m_stencil_kernel<<<dim3(cnt, chunks_st), 256, 0, st>>>(ws, (double *)w.ast.p, ast_stride);
+        *launches += 5;
+        w.h_totals.resize((size_t)4 * cnt);
+        cudaError_t e = cudaMemcpyAsync(w.h_totals.data(), w.totals.p, (size_t)32 * cnt, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_lvl, w.lvl.p, 512, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { cudaGetLastError(); return nd_fail(w, -2, std::string("nested-dissection sizes: ") + cudaGetErrorString(e)); }
+        long long m[4] = {0, 0, 0, 0};
+        for (int s = 0; s < cnt; ++s)
+            for (int k = 0; k < 4; ++k) m[k] = std::max(m[k], w.h_totals[4 * (size_t)s + k]);
+        const size_t Ls = ((size_t)m[0] + 1) & ~(size_t)1, Us = ((size_t)m[1] + 1) & ~(size_t)1, UVs = ((size_t)m[2] + 1) & ~(size_t)1;
+        const size_t pool_bytes = (Ls + 2 * Us + 2 * UVs) * 8;
+        w.last_bytes_per_image = fix_bytes + pool_bytes;
+        if (cnt > 1 && (fix_bytes + pool_bytes) * cnt > w.budget_cached && w.budget_cached > 0) {
+            // the images carry more unknowns than estimated: a smaller wave, classified again
+            slots = (int)std::max<size_t>(1, std::min<size_t>((size_t)cnt - 1, w.budget_cached / (fix_bytes + pool_bytes)));
+            w.slots_cached = slots;
+            continue;
+        }
+        size_t fsmem = 0, ssmem = 0;
+        for (int s = 0; s < nsteps; ++s) {
+            plan[s] = nd_level_plan_sized(sym, s, h_lvl[2 * s], s > 0 ? h_lvl[2 * (s - 1) + 1] : 0, cta_warps_f, 512);
+            fsmem = std::max(fsmem, plan[s].smem_f); ssmem = std::max(ssmem, plan[s].smem_s);
+        }
+        if ((rc = nd_kernel_attributes(w, fsmem, ssmem, 0, 0, smem_optin))) return rc;      // -1: the band Cholesky
+        if ((rc = need(w.L, Ls * 8 * cnt, "factors"))) return rc;
+        if ((rc = need(w.U0, Us * 8 * cnt, "update matrices"))) return rc;
+        if ((rc = need(w.U1, Us * 8 * cnt, "update matrices"))) return rc;
+        if ((rc = need(w.UV0, UVs * 8 * cnt, "update vectors"))) return rc;
+        if ((rc = need(w.UV1, UVs * 8 * cnt, "update vectors"))) return rc;
+        nd.L = (double *)w.L.p; nd.L_stride = Ls;
+        nd.U[0] = (double *)w.U0.p; nd.U[1] = (double *)w.U1.p; nd.U_stride = Us;
+        nd.UV[0] = (double *)w.UV0.p; nd.UV[1] = (double *)w.UV1.p; nd.UV_stride = UVs;
+
+        nd_launch_factor(nd, plan, plan_small, sym, mb, cnt, sm_count, guard, st, launches);
+        double *zeta = ws.vec + (size_t)mb * N, *work = ws.vec + (size_t)2 * mb * N;
+        nd3m_axpy_kernel<<<dim3(cnt, chunks), 256, 0, st>>>(ws, 1, 0, 0);
+        nd_launch_solve(nd, plan, cnt, zeta, vec_stride, st, launches);
+        nd3m_residual_kernel<<<cnt, 512, 0, st>>>(ws, (double *)w.relres.p, img0);
+        for (int it = 0; it < refine; ++it) {
+            nd_launch_solve(nd, plan, cnt, work, vec_stride, st, launches);
+            nd3m_axpy_kernel<<<dim3(cnt, chunks), 256, 0, st>>>(ws, 1, 2, 1);
+            nd3m_residual_kernel<<<cnt, 512, 0, st>>>(ws, (double *)w.relres.p, img0);
+        }
+        nd3m_finish_kernel<<<cnt, 512, 0, st>>>(ws, gv, (const double *)w.relres.p, (double *)w.out_img.p, img0);
+        *launches += 3 + 2 * refine;
+        img0 += cnt;
+    }
+    nd_reduce_kernel<<<(3 * ng + 255) / 256, 256, 0, st>>>((double *)w.out_img.p, (double *)w.relres.p, gp.O, 3 * ng, d_grad_out,
+                                                           (double *)w.relres_max.p);
+    *launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return nd_fail(w, -2, std::string("nested-dissection kernel launch failed: ") + cudaGetErrorString(e));
+    return 0;
+}
+
 NdWork *nd_work_create() { return new NdWork(); }
 void nd_work_destroy(NdWork *w) { if (w) { w->release(); delete w; } }
 const char *nd_work_error(const NdWork *w) { return w->err.c_str(); }
@@ -547,6 +784,12 @@ int nd_run_gradient3_reg(NdWork *w, const Nd3Problem &gp, int sm_count, size_t s
 {
     return gp.prec == 64 ? run_gradient3_nd_reg<double>(*w, gp, sm_count, smem_optin, st, d_grad_out, launches)
                          : run_gradient3_nd_reg<float>(*w, gp, sm_count, smem_optin, st, d_grad_out, launches);
+}
+int nd_run_gradient3(NdWork *w, const Nd3mProblem &gp, int sm_count, size_t smem_optin, cudaStream_t st, double *d_grad_out,
+                     long long *launches)
+{
+    return gp.prec == 64 ? run_gradient3_nd_mult<double>(*w, gp, sm_count, smem_optin, st, d_grad_out, launches)
+                         : run_gradient3_nd_mult<float>(*w, gp, sm_count, smem_optin, st, d_grad_out, launches);
 }
 
 }  // namespace bpltv

@@ -35,6 +35,19 @@ struct Nd3Problem {
     int maxit;                  // refinement steps (≤ 0: default)
 };
 
+// sumregs_gradient (non-regularised; scalar :264-327, patch :330-407) in multiplier space: 3-6 unknowns per pixel,
+// coupling radius 2.  alpha_maps: 3 maps of M·N (patch) or nullptr (scalar: alpha[3]).
+struct Nd3mProblem {
+    const void *u, *ubar, *alpha_maps;
+    int prec;
+    int M, N, O;
+    double alpha[3];
+    int lm, ln;
+    double act_tol, eps_act;
+    double tol;                 // relative residual above which the result is poisoned with NaN (≤ 0: never)
+    int maxit;                  // refinement steps (≤ 0: default)
+};
+
 NdWork *nd_work_create();
 void nd_work_destroy(NdWork *w);
 const char *nd_work_error(const NdWork *w);
@@ -46,5 +59,9 @@ int nd_run_gradient(NdWork *w, const NdProblem &gp, int sm_count, size_t smem_op
 // d_grad_out: 3 doubles (one per operator).  Use a workspace of its own (the plan is keyed by the coupling radius).
 int nd_run_gradient3_reg(NdWork *w, const Nd3Problem &gp, int sm_count, size_t smem_optin, cudaStream_t st, double *d_grad_out,
                          long long *launches);
+
+// d_grad_out: 3·lm·ln doubles, [operator][patch].  Shares the workspace of nd_run_gradient3_reg (same tree).
+int nd_run_gradient3(NdWork *w, const Nd3mProblem &gp, int sm_count, size_t smem_optin, cudaStream_t st, double *d_grad_out,
+                     long long *launches);
 
 }  // namespace bpltv

@@ -26,6 +26,7 @@
 #pragma once
 #ifndef BPLTV_EMU
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #endif
 #include "nd_symbolic.h"
 
@@ -272,7 +273,13 @@ static inline size_t nd_factor_smem(int nFmax, int nRchild_max)
 // ---------------------------------------------------------------------------
 // assemble + partial Cholesky of the fronts of one level.  grid (fronts of the level, slots)
 // ---------------------------------------------------------------------------
-__global__ void nd_factor_kernel(NdDev nd, int t0, int par, double guard, int nFmax)
+// CL: the front is shared by the CTAs of a thread-block cluster (the top levels of the tree, where a level has fewer
+// fronts than the GPU has SMs): assembly and write-back are dealt over all threads of the cluster, the diagonal block and
+// the panel are formed redundantly by every CTA in its own shared memory (same operations in the same order: the same
+// pivots and the same bits), the tiles of the trailing update are dealt over all warps of the cluster, and one cluster
+// barrier per phase / block step publishes them through global memory.  Results do not depend on the cluster size.
+template <bool CL>
+static __device__ __forceinline__ void nd_factor_body(const NdDev &nd, int t0, int par, double guard, int nFmax)
 {
     ND_DYN_SMEM(sm);
     constexpr int NB = ND_NB;
@@ -282,7 +289,14 @@ __global__ void nd_factor_kernel(NdDev nd, int t0, int par, double guard, int nF
     const int PR = nd_panel_pitch(nFmax);
     int *umap = reinterpret_cast<int *>(P + (size_t)NB * PR);
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
-    const int t = t0 + blockIdx.x, slot = blockIdx.y;
+    int crank = 0, csize = 1;
+    if (CL) {
+        cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+        crank = (int)cluster.block_rank(); csize = (int)cluster.num_blocks();
+    }
+    auto csync = [&]() { if (CL) cooperative_groups::this_cluster().sync(); else __syncthreads(); };
+    const int gtid = crank * T + tid, GT = csize * T;       // thread index / count over the cluster
+    const int t = t0 + blockIdx.x / csize, slot = blockIdx.y;
     const NdFront f = nd.fronts[t];
     const int *pos = nd.posg + nd.posg_stride * slot + f.pix0 + t;
     const long long *foff = nd.foff + nd.foff_stride * slot;
@@ -293,13 +307,13 @@ __global__ void nd_factor_kernel(NdDev nd, int t0, int par, double guard, int nF
     const int MB = nd.mb, MB2 = MB * MB;
 
     // ---- zero
-    for (size_t k = tid; k < (size_t)nF * nP; k += T) L[k] = 0.0;
-    for (size_t k = tid; k < (size_t)nR * nR; k += T) U[k] = 0.0;
-    __syncthreads();
+    for (size_t k = gtid; k < (size_t)nF * nP; k += GT) L[k] = 0.0;
+    for (size_t k = gtid; k < (size_t)nR * nR; k += GT) U[k] = 0.0;
+    csync();
     // ---- original entries of the pivot columns (each pixel pair once: by the earlier pixel of the front)
     {
         const int ne = nd.nnb + 1;
-        for (int idx = tid; idx < f.npiv * ne; idx += T) {
+        for (int idx = gtid; idx < f.npiv * ne; idx += GT) {
             const int kp = idx / ne, e = idx - kp * ne;
             const int p = nd.pixlist[f.pix0 + kp];
             const int a0 = pos[kp], mp = pos[kp + 1] - a0;
@@ -321,7 +335,7 @@ __global__ void nd_factor_kernel(NdDev nd, int t0, int par, double guard, int nF
             }
         }
     }
-    __syncthreads();
+    csync();
     // ---- extend-add: the children's update matrices, one child after the other (fixed order)
     for (int ci = 0; ci < 2; ++ci) {
         const int c = ci == 0 ? f.child0 : f.child1;
@@ -337,14 +351,14 @@ __global__ void nd_factor_kernel(NdDev nd, int t0, int par, double guard, int nF
         __syncthreads();
         const double *cU = nd.U[par ^ 1] + nd.U_stride * slot + foff[4 * (size_t)c + 1];
         const size_t tot = (size_t)cnR * cnR;
-        for (size_t idx = tid; idx < tot; idx += T) {
+        for (size_t idx = gtid; idx < tot; idx += GT) {
             const int r = (int)(idx % cnR), cc = (int)(idx / cnR);
             if (r < cc) continue;
             int R = umap[r], C = umap[cc];
             if (R < C) { const int s = R; R = C; C = s; }
             nd_col(L, U, nP, nF, nR, C)[R] += cU[idx];
         }
-        __syncthreads();
+        csync();
     }
     // ---- blocked partial Cholesky of the first nP columns
     int guarded = 0, bad = 0;
@@ -407,11 +421,13 @@ __global__ void nd_factor_kernel(NdDev nd, int t0, int par, double guard, int nF
             }
         }
         guarded += blk_guarded;
-        for (int idx = tid; idx < NB * NB; idx += T) {
-            const int r = idx / NB, c = idx - r * NB;
-            if (r < nb && c <= r) L[(size_t)(kb + c) * nF + kb + r] = S[idx];
-        }
-        for (int idx = tid; idx < ntr * nb; idx += T) {
+        if (CL) csync();        // every CTA has read the block's columns (its own S0 and panel) before they are overwritten
+        if (crank == 0)
+            for (int idx = tid; idx < NB * NB; idx += T) {
+                const int r = idx / NB, c = idx - r * NB;
+                if (r < nb && c <= r) L[(size_t)(kb + c) * nF + kb + r] = S[idx];
+            }
+        for (int idx = gtid; idx < ntr * nb; idx += GT) {
             const int c = idx / ntr, rr = idx - c * ntr;
             const double v = P[c * PR + rr];
             L[(size_t)(kb + c) * nF + k1 + rr] = v;
@@ -420,7 +436,7 @@ __global__ void nd_factor_kernel(NdDev nd, int t0, int par, double guard, int nF
         // trailing update F22 -= P Pᵀ (lower triangle) in 32×32 warp tiles, 4 rows × 8 columns per thread
         const int nt = ntr32 >> 5, ntiles = nt * (nt + 1) / 2;
         const int li = lane & 7, lj = lane >> 3;
-        for (int wt = warp; wt < ntiles; wt += nwarps) {
+        for (int wt = crank * nwarps + warp; wt < ntiles; wt += csize * nwarps) {
             // wt = ti(ti+1)/2 + tj, tj ≤ ti
             int ti = (int)((sqrt(8.0 * wt + 1.0) - 1.0) * 0.5);
             while ((ti + 1) * (ti + 2) / 2 <= wt) ++ti;
@@ -461,11 +477,15 @@ __global__ void nd_factor_kernel(NdDev nd, int t0, int par, double guard, int nF
                 }
             }
         }
-        __syncthreads();
+        csync();
     }
-    if (guarded) atomicAdd(nd.info + 4 * slot, guarded);
+    if (guarded && crank == 0) atomicAdd(nd.info + 4 * slot, guarded);
     if (bad) atomicAdd(nd.info + 4 * slot + 1, 1);
 }
+
+__global__ void nd_factor_kernel(NdDev nd, int t0, int par, double guard, int nFmax) { nd_factor_body<false>(nd, t0, par, guard, nFmax); }
+// grid (fronts of the level × cluster size, slots), launched with the cluster dimension
+__global__ void __launch_bounds__(512) nd_factor_cluster_kernel(NdDev nd, int t0, int par, double guard, int nFmax) { nd_factor_body<true>(nd, t0, par, guard, nFmax); }
 
 // dynamic shared memory of the solve kernels (bytes): the front's vector, the diagonal block, NB scratch
 static inline size_t nd_solve_smem(int nFmax) { return (size_t)(nFmax + ND_NB * ND_NB + 2 * ND_NB + 2) * sizeof(double); }
@@ -938,6 +958,7 @@ struct NdLevelPlan {
     bool small;                 // warp-per-front kernels
     int t0, nfr;                // fronts of the level
     int nFw;                    // largest possible front (mb unknowns on every pixel)
+    int nRc;                    // largest possible ring of a child (unknowns): the extend-add map of the generic kernel
     int threads_f, threads_s;   // generic kernels: CTA sizes of the factorisation / of the solves
     size_t smem_f, smem_s;      // dynamic shared memory of the factorisation / of the solves
     int arena_f, arena_s;       // small kernels: arena (doubles)
@@ -948,6 +969,7 @@ static inline NdLevelPlan nd_level_plan(const NdSymbolic &sym, int s, int mb, do
     NdLevelPlan lp;
     lp.t0 = sym.step_start[s]; lp.nfr = sym.step_start[s + 1] - lp.t0;
     lp.nFw = mb * sym.step_max_front_pix[s];
+    lp.nRc = s > 0 ? mb * sym.step_max_ring_pix[s - 1] : 0;
     const int nPw = mb * sym.step_max_piv_pix[s];
     const int nFt = std::min(lp.nFw, (int)(typ_per_pixel * sym.step_max_front_pix[s]) + 1);
     lp.small = lp.nFw <= ND_SMALL_MAXF && nFt <= ND_SMALL_TYPF;
@@ -961,10 +983,45 @@ static inline NdLevelPlan nd_level_plan(const NdSymbolic &sym, int s, int mb, do
         lp.smem_f = nd_small_smem(lp.arena_f);
         lp.smem_s = nd_small_smem(lp.arena_s);
     } else {
-        lp.smem_f = nd_factor_smem(lp.nFw, s > 0 ? mb * sym.step_max_ring_pix[s - 1] : 0);
+        lp.smem_f = nd_factor_smem(lp.nFw, lp.nRc);
         lp.smem_s = nd_solve_smem(lp.nFw);
     }
     return lp;
+}
+
+// The same for a level whose sizes were MEASURED on the device (nd_level_sizes_kernel): the forms with many unknowns per
+// pixel (sum-of-regularisers multipliers: 3-6) cannot afford worst-case shared memory.  Generic kernels only.
+static inline NdLevelPlan nd_level_plan_sized(const NdSymbolic &sym, int s, int nF, int nRchild, int max_warps_f = 16,
+                                             int max_threads_s = 512)
+{
+    NdLevelPlan lp;
+    lp.t0 = sym.step_start[s]; lp.nfr = sym.step_start[s + 1] - lp.t0;
+    lp.nFw = std::max(nF, 1);
+    lp.nRc = nRchild;
+    lp.small = false;
+    const int nt = (lp.nFw + 31) / 32, ntiles = nt * (nt + 1) / 2;
+    lp.threads_f = 32 * std::min(max_warps_f, std::max(2, ntiles));
+    lp.threads_s = std::min(max_threads_s, std::max(64, (lp.nFw + 31) & ~31));
+    lp.arena_f = lp.arena_s = 0;
+    lp.smem_f = nd_factor_smem(lp.nFw, lp.nRc);
+    lp.smem_s = nd_solve_smem(lp.nFw);
+    return lp;
+}
+
+// largest front and largest ring (unknowns) of every level over the images of the wave → lvl[2s], lvl[2s+1] (zeroed by
+// the caller).  grid (ceil(fronts / 256), slots)
+__global__ void __launch_bounds__(256) nd_level_sizes_kernel(NdDev nd, int *lvl)
+{
+    const int slot = blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nd.nfronts) {
+        const NdFront f = nd.fronts[t];
+        const int *pos = nd.posg + nd.posg_stride * slot + f.pix0 + t;
+        const int nP = pos[f.npiv], nF = pos[f.npiv + f.nring];
+        const int s = nd.nsteps - 1 - f.depth;
+        atomicMax(lvl + 2 * s, nF);
+        atomicMax(lvl + 2 * s + 1, nF - nP);
+    }
 }
 
 }  // namespace bpltv

@@ -117,3 +117,57 @@ def test_one_operator_switched_off(lib):
     got, stats, _, _ = _run(lib, u, t, x)
     lit = sr.sumregs_gradient_reg(x, u, t, refine=3)
     assert np.all(np.abs(got - lit) <= 1e-11 * np.abs(lit).max()), (got, lit)
+
+
+# ---------------------------------------------------------------------------
+# sumregs_gradient (non-regularised) in multiplier space: 3-6 unknowns per pixel on the same tree
+# ---------------------------------------------------------------------------
+def _run_mult(lib, u, t, x=None, maps=None, grid=(1, 1), refine=1, leaf=4, csize=1):
+    n = u.shape[0]
+    ng = grid[0] * grid[1]
+    out, stats, p = np.zeros(3 * ng), np.zeros(6), np.zeros(n * n)
+    am = None if maps is None else np.concatenate([np.asarray(m).flatten(order="F") for m in maps])
+    a3 = None if x is None else np.asarray(x, dtype=np.float64)
+    lib.emu_nd3_gradient_mult.restype = C.c_int
+    rc = lib.emu_nd3_gradient_mult(n, _ptr(u.flatten(order="F")), _ptr(t.flatten(order="F")), _ptr(a3), _ptr(am),
+                                   grid[0], grid[1], C.c_double(1e-12), C.c_double(sr.EPS), refine, leaf, csize, _ptr(out),
+                                   _ptr(stats), _ptr(p))
+    assert rc == 0
+    return out.reshape(3, grid[1], grid[0]).transpose(2, 1, 0), stats, p      # [operator][patch] → (pi, pj, operator)
+
+
+@pytest.mark.parametrize("n,leaf", [(8, 4), (13, 4), (20, 4), (20, 5)])
+def test_scalar_nonreg_gradient_multiplier_form(lib, n, leaf):
+    """≤ 1e-10 against the compliance-form CPU checker (the same formulation), ≤ 1e-6 against the refined literal
+    saddle-point system (:264-327) — the bars of tests/test_gpu_sumregs.py"""
+    t, u = _case(n, 70 + n)
+    x = np.array([0.05, 0.04, 0.06])
+    got, stats, _ = _run_mult(lib, u, t, x=x, leaf=leaf)
+    assert stats[2] == 0 and stats[3] > 3 * n * n, stats          # flat pixels carry two modes per operator
+    du = sr.sumregs_gradient_dual("nonreg", x, u, t)
+    assert np.all(np.abs(got[0, 0] - du) <= 1e-10 * np.abs(du).max()), (got, du, stats)
+    lit = sr.sumregs_gradient(x, u, t, refine=3)
+    assert np.all(np.abs(got[0, 0] - lit) <= 1e-6 * np.abs(lit).max()), (got, lit)
+
+
+def test_patch_nonreg_gradient_multiplier_form(lib):
+    from oracle import oracle as orc
+    n = 16
+    t, u = _case(n, 12)
+    xp = np.stack([np.array([[0.03, 0.05], [0.02, 0.04]]) * s for s in (1.0, 0.7, 1.3)], axis=2)
+    maps = [np.asfortranarray(orc.patch_upsample(xp[:, :, k], n, n)) for k in range(3)]
+    got, stats, _ = _run_mult(lib, u, t, maps=maps, grid=(2, 2))
+    dp = sr.sumregs_gradient_dual("nonreg", maps, u, t, grid_shape=(2, 2))
+    assert stats[2] == 0
+    assert got.shape == dp.shape and np.all(np.abs(got - dp) <= 1e-10 * np.abs(dp).max()), (got, dp)
+
+
+def test_cluster_shared_front_factorisation_is_invisible(lib):
+    """nd_factor_cluster_kernel: the front dealt over the CTAs of a cluster (assembly, write-back and trailing tiles shared,
+    diagonal block and panel redundant) gives the bits of the single-CTA kernel, for 2 and 3 CTAs per front"""
+    t, u = _case(14, 31)
+    x = np.array([0.05, 0.04, 0.06])
+    g1, s1, p1 = _run_mult(lib, u, t, x=x)
+    for cs in (2, 3):
+        g, s, p = _run_mult(lib, u, t, x=x, csize=cs)
+        assert np.array_equal(g, g1) and np.array_equal(p, p1) and s[0] == s1[0] and s[1] == s1[1], cs

@@ -219,7 +219,9 @@ def test_sumregs_learning_function_end_to_end(bp, ctx, sr, datasets):
     assert np.array_equal(u, ref) and abs(cost - orc.cost(ref, t)) <= 1e-12 * cost
     assert g.shape == (3,) and np.all(np.isfinite(g))
     st = ctx.stats()
-    assert st["ms_gradient"] > 0 and st["kernel_launches"] == 1 + 2 + 5      # resident solve, cost, gradient
+    # resident solve, cost, gradient (nested dissection: classification, sizes, stencil, one launch per tree level for
+    # the factorisation and two per solve, residuals, functional)
+    assert st["ms_gradient"] > 0 and 1 + 2 + 5 < st["kernel_launches"] <= 120
     assert 0 < st["solver_max_relres"] < 1.0                                 # |r|/|b| of the banded adjoint solve (informational)
     u2, cost2, g2 = bp.sumregs_learning_function(x0, (t, f), 1e-4, ctx=ctx, maxiter=300)  # Δ ≤ Δt: regularised
     assert np.array_equal(u2, u) and cost2 == cost and not np.allclose(g, g2)
@@ -278,6 +280,43 @@ def test_scalar_sumregs_gradient_reg_nested_dissection_vs_band_lu(bp, ctx, ctx32
         ctx.set_dataset((t.astype(np.float32).astype(np.float64), f))
         g64 = ctx.sumregs_gradient(x, u32, regularised=True)
         assert np.all(np.abs(g32 - g64) <= 1e-5 * np.abs(g64).max()), (g32, g64)
+
+
+def test_sumregs_gradient_nested_dissection_vs_band_cholesky(bp, ctx, sr, datasets):
+    """sumregs_gradient (non-regularised: scalar :264-327, patch :330-407) takes the nested-dissection solver in
+    multiplier space (3-6 unknowns per pixel, nd_sumregs.cuh MULT3; eval_opts.solver 0) — against the band Cholesky of
+    round 1 (solver 1): 1e-9, both being ≤ 1e-10 from the CPU compliance-form checker at the sizes it finishes."""
+    import os
+    from oracle import oracle as orc
+    x = np.array([0.03, 0.02, 0.04])
+    xp = np.stack([np.array([[0.03, 0.05], [0.02, 0.04]]) * s for s in (1.0, 0.7, 1.3)], axis=2)
+    for n, k, off in ((37, 3, 30), (128, 2, 0)):
+        t, f = _crop(datasets, "faces_train_128_10", n, k=k, off=off)
+        u = np.asfortranarray(ctx.sumregs_denoise(f, x, bp.sumregs_pdps_opts(maxiter=500)))
+        u[2:9, 3:8, 0] = u[2, 3, 0]                     # exactly flat pixels: two modes per operator
+        ctx.set_dataset((t, f))
+        g_nd = ctx.sumregs_gradient(x, u, regularised=False)
+        st = ctx.stats()
+        gp_nd = ctx.sumregs_gradient(xp, u, regularised=False)
+        os.environ["BPLTV_GRAD_SOLVER"] = "1"
+        bp.reload_env()
+        try:
+            g_b = ctx.sumregs_gradient(x, u, regularised=False)
+            stb = ctx.stats()
+            gp_b = ctx.sumregs_gradient(xp, u, regularised=False)
+        finally:
+            del os.environ["BPLTV_GRAD_SOLVER"]
+            bp.reload_env()
+        assert st["kernel_launches"] != stb["kernel_launches"]          # two different paths did run
+        assert st["solver_max_relres"] <= 1e-9, st
+        assert np.all(np.abs(g_nd - g_b) <= 1e-9 * np.abs(g_b).max()), (n, g_nd, g_b)
+        assert gp_nd.shape == (2, 2, 3) and np.all(np.abs(gp_nd - gp_b) <= 1e-9 * np.abs(gp_b).max()), (n, gp_nd, gp_b)
+        if n <= 48:
+            du = sum(sr.sumregs_gradient_dual("nonreg", x, u[:, :, i], t[:, :, i]) for i in range(k))
+            assert np.all(np.abs(g_nd - du) <= 1e-10 * np.abs(du).max()), (g_nd, du)
+            maps = [orc.patch_upsample(xp[:, :, kk], n, n) for kk in range(3)]
+            dp = sum(sr.sumregs_gradient_dual("nonreg", maps, u[:, :, i], t[:, :, i], grid_shape=(2, 2)) for i in range(k))
+            assert np.all(np.abs(gp_nd - dp) <= 1e-10 * np.abs(dp).max()), (gp_nd, dp)
 
 
 def test_cluster_factorisation_is_invisible(bp, ctx, sr, datasets):

@@ -48,9 +48,20 @@ for name, k in (("cameraman_128_5", 1), ("faces_train_128_10", 10)):
                c.stats()["kernel_launches"]), flush=True)
         ms_p, g_p = timed(c, xp, True, up)
         print("%s x%d patch reg (band LU): %.1f ms" % (name, k, ms_p), flush=True)
-        ms_n, _ = timed(c, xs, False, us)
-        ms_pn, _ = timed(c, xp, False, up)
-        print("%s x%d non-reg: scalar %.1f ms, patch %.1f ms" % (name, k, ms_n, ms_pn), flush=True)
+        ms_n, g_n = timed(c, xs, False, us)
+        st_n = c.stats()
+        ms_pn, g_pn = timed(c, xp, False, up)
+        os.environ["BPLTV_GRAD_SOLVER"] = "1"
+        bp.reload_env()
+        ms_nb, g_nb = timed(c, xs, False, us, reps=2)
+        ms_pnb, g_pnb = timed(c, xp, False, up, reps=2)
+        os.environ.pop("BPLTV_GRAD_SOLVER")
+        bp.reload_env()
+        print("%s x%d non-reg: nested dissection scalar %.1f ms (relres %.1e, %d launches, %.0f MB per image), patch %.1f ms; "
+              "band Cholesky %.1f / %.1f ms; rel diff %.1e / %.1e" %
+              (name, k, ms_n, st_n["solver_max_relres"], st_n["kernel_launches"], st_n.get("grad_bytes_per_image", 0) / 1e6,
+               ms_pn, ms_nb, ms_pnb, np.abs(g_n - g_nb).max() / np.abs(g_nb).max(),
+               np.abs(g_pn - g_pnb).max() / np.abs(g_pnb).max()), flush=True)
 t, f = bp.synthetic_dataset(256, 256, 2, seed=20240602)
 with bp.Context([0], 64) as c:
     c.set_dataset((t, f))
