@@ -91,7 +91,10 @@ typedef struct bpltv_eval_opts {
     int solver_maxit;    /* steps of iterative refinement; 0 -> default (1)           */
     int solver;          /* 0 auto = 2; 2 nested-dissection multifrontal Cholesky (the
                             whole GPU per image); 1 the banded factorisations of round 1
-                            (one SM per image), kept as a second implementation          */
+                            (one SM per image), kept as a second implementation.  Sum of
+                            regularisers: the symmetric variants (sumregs_gradient scalar
+                            and patch, scalar sumregs_gradient_reg) follow this switch; the
+                            row-scaled patch sumregs_gradient_reg is always the band LU   */
     int force_branch;    /* 0: by Δ (reference); 1: gradient; 2: gradient_reg;
                             3: cost only (grad_out left zero; λ-sweeps, validation)  */
     int reserved0;
@@ -109,8 +112,10 @@ typedef struct bpltv_stats {
     long long kernel_launches;   /* CUDA kernels launched by the last call     */
     double solver_max_relres;    /* worst residual of the adjoint solves over the images (host-pointer
                                     entry points).  Nested dissection (solver 0/2): the normwise
-                                    backward error that solver_tol bounds.  Banded solvers (solver 1,
-                                    sum of regularisers): the relative residual |r|/|b| after the
+                                    backward error that solver_tol bounds (TV, scalar
+                                    sumregs_gradient_reg) or the relative residual |r|/|b| of the
+                                    multiplier system (sumregs_gradient).  Banded solvers (solver 1,
+                                    patch sumregs_gradient_reg): the relative residual |r|/|b| after the
                                     last refinement step — informational (with entries up to
                                     alpha*gamma it is not a backward error); the band LU applies its
                                     own backward-error test and poisons the gradient with NaN      */
