@@ -518,12 +518,41 @@ __global__ void nd_factor_kernel(NdDev nd, int t0, int par, double guard, int nF
 // grid (fronts of the level × cluster size, slots), launched with the cluster dimension
 __global__ void __launch_bounds__(512) nd_factor_cluster_kernel(NdDev nd, int t0, int par, double guard, int nFmax) { nd_factor_body<true>(nd, t0, par, guard, nFmax); }
 
-// dynamic shared memory of the solve kernels (bytes): the front's vector, the diagonal block, NB scratch
-static inline size_t nd_solve_smem(int nFmax) { return (size_t)(nFmax + ND_NB * ND_NB + 2 * ND_NB + 2) * sizeof(double); }
+// dynamic shared memory of the solve kernels (bytes): the front's vector, the ring sums of the backward sweep, two
+// diagonal blocks (the next one is fetched while the current one is used), NB scratch
+static inline size_t nd_solve_smem(int nFmax) { return (size_t)(2 * ((nFmax + 1) & ~1) + 2 * ND_NB * ND_NB + 2 * ND_NB + 2) * sizeof(double); }
+
+// diagonal block kb of the factor → registers (≤ 4 per thread, CTAs of ≥ 64 threads) → shared memory, so that the global
+// latency of the NEXT block hides behind the substitution of the current one
+static __device__ __forceinline__ void nd_diag_fetch(const double *L, int nF, int nP, int kb, int tid, int T, double sreg[4])
+{
+    constexpr int NB = ND_NB;
+    const int nb = min(NB, nP - kb);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int idx = tid + k * T;
+        sreg[k] = 0.0;
+        if (idx < NB * NB) {
+            const int r = idx / NB, c = idx - r * NB;
+            sreg[k] = (r < nb && c <= r) ? L[(size_t)(kb + c) * nF + kb + r] : (r == c ? 1.0 : 0.0);
+        }
+    }
+}
+static __device__ __forceinline__ void nd_diag_store(double *S, int tid, int T, const double sreg[4])
+{
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int idx = tid + k * T;
+        if (idx < ND_NB * ND_NB) S[idx] = sreg[k];
+    }
+}
 
 // ---------------------------------------------------------------------------
 // forward substitution, one level: y_P = L11⁻¹(b_P + children), update vector = children − L21 y_P
 // vec: per slot, unknowns in pixel order (b on entry; the pivot entries become y)
+// Only the PIVOT rows are updated inside the serial block loop; the ring rows (the bulk of a front) take all their
+// blocks in one parallel pass afterwards, block by block in the same order — the same sums, the same bits as a loop that
+// updates every row at every step, with a chain of nP/16 short steps instead of nP/16 passes over the whole front.
 // ---------------------------------------------------------------------------
 __global__ void nd_fwd_kernel(NdDev nd, int t0, int par, double *vec_all, size_t vec_stride)
 {
@@ -539,8 +568,11 @@ __global__ void nd_fwd_kernel(NdDev nd, int t0, int par, double *vec_all, size_t
     const double *L = nd.L + nd.L_stride * slot + foff[4 * (size_t)t];
     double *uv = nd.UV[par] + nd.UV_stride * slot + foff[4 * (size_t)t + 2];
     double *vec = vec_all + vec_stride * slot;
-    double *v = sm, *S = sm + ((nF + 1) & ~1), *ys = S + NB * NB;
+    const int nFe = (nF + 1) & ~1;
+    double *v = sm, *Sb = sm + 2 * nFe, *ys = Sb + 2 * NB * NB;
+    double sreg[4];
 
+    if (nP > 0) nd_diag_fetch(L, nF, nP, 0, tid, T, sreg);
     for (int k = tid; k < f.npiv + f.nring; k += T) {
         const int a0 = pos[k], m = pos[k + 1] - a0;
         if (k < f.npiv) {
@@ -551,6 +583,7 @@ __global__ void nd_fwd_kernel(NdDev nd, int t0, int par, double *vec_all, size_t
             for (int al = 0; al < m; ++al) v[a0 + al] = 0.0;
         }
     }
+    nd_diag_store(Sb, tid, T, sreg);
     __syncthreads();
     for (int ci = 0; ci < 2; ++ci) {
         const int c = ci == 0 ? f.child0 : f.child1;
@@ -566,18 +599,17 @@ __global__ void nd_fwd_kernel(NdDev nd, int t0, int par, double *vec_all, size_t
         }
         __syncthreads();
     }
-    for (int kb = 0; kb < nP; kb += NB) {
+    for (int kb = 0, b = 0; kb < nP; kb += NB, ++b) {
         const int nb = min(NB, nP - kb), k1 = kb + nb;
-        for (int idx = tid; idx < NB * NB; idx += T) {
-            const int r = idx / NB, c = idx - r * NB;
-            S[idx] = (r < nb && c <= r) ? L[(size_t)(kb + c) * nF + kb + r] : (r == c ? 1.0 : 0.0);
-        }
+        double *S = Sb + (b & 1) * NB * NB;
+        if (k1 < nP) nd_diag_fetch(L, nF, nP, k1, tid, T, sreg);
         if (tid < NB) ys[tid] = tid < nb ? v[kb + tid] : 0.0;
         __syncthreads();
         if (warp == 0) nd_block_subst(S, ys, false, lane);
         __syncthreads();
+        if (k1 < nP) nd_diag_store(Sb + ((b + 1) & 1) * NB * NB, tid, T, sreg);
         if (tid < nb) v[kb + tid] = ys[tid];
-        for (int r = k1 + tid; r < nF; r += T) {
+        for (int r = k1 + tid; r < nP; r += T) {
             double s0 = 0.0, s1 = 0.0;
 #pragma unroll 4
             for (int c = 0; c < nb; c += 2) {
@@ -587,6 +619,32 @@ __global__ void nd_fwd_kernel(NdDev nd, int t0, int par, double *vec_all, size_t
             v[r] -= s0 + s1;
         }
         __syncthreads();
+    }
+    // ring rows: every block of pivot columns in turn (16 independent loads per block and row)
+    for (int r = nP + tid; r < nF; r += T) {
+        double acc = v[r];
+        for (int kb = 0; kb < nP; kb += NB) {
+            const int nb = min(NB, nP - kb);
+            const double *col = L + (size_t)kb * nF + r;
+            double s0 = 0.0, s1 = 0.0;
+            if (nb == NB) {
+                double l[NB];
+#pragma unroll
+                for (int c = 0; c < NB; ++c) l[c] = col[(size_t)c * nF];
+#pragma unroll
+                for (int c = 0; c < NB; c += 2) {
+                    s0 = fma(l[c], v[kb + c], s0);
+                    s1 = fma(l[c + 1], v[kb + c + 1], s1);
+                }
+            } else {
+                for (int c = 0; c < nb; c += 2) {
+                    s0 = fma(col[(size_t)c * nF], v[kb + c], s0);
+                    if (c + 1 < nb) s1 = fma(col[(size_t)(c + 1) * nF], v[kb + c + 1], s1);
+                }
+            }
+            acc -= s0 + s1;
+        }
+        v[r] = acc;
     }
     for (int k = tid; k < f.npiv; k += T) {
         const int a0 = pos[k], m = pos[k + 1] - a0;
@@ -598,7 +656,9 @@ __global__ void nd_fwd_kernel(NdDev nd, int t0, int par, double *vec_all, size_t
 }
 
 // ---------------------------------------------------------------------------
-// backward substitution, one level: x_P = L11⁻ᵀ(y_P − L21ᵀ x_ring); the ring's x comes from the ancestors
+// backward substitution, one level: x_P = L11⁻ᵀ(y_P − L21ᵀ x_ring); the ring's x comes from the ancestors.
+// The ring part of every pivot column's dot product is formed up front, in parallel (a warp per column); the serial
+// block loop adds the part over the pivot rows below the block.
 // ---------------------------------------------------------------------------
 __global__ void nd_bwd_kernel(NdDev nd, int t0, double *vec_all, size_t vec_stride)
 {
@@ -613,37 +673,58 @@ __global__ void nd_bwd_kernel(NdDev nd, int t0, double *vec_all, size_t vec_stri
     const int nP = pos[f.npiv], nF = pos[f.npiv + f.nring];
     const double *L = nd.L + nd.L_stride * slot + foff[4 * (size_t)t];
     double *vec = vec_all + vec_stride * slot;
-    double *v = sm, *S = sm + ((nF + 1) & ~1), *ts = S + NB * NB;
+    const int nFe = (nF + 1) & ~1;
+    double *v = sm, *tR = sm + nFe, *Sb = sm + 2 * nFe, *ts = Sb + 2 * NB * NB;
+    double sreg[4];
+    const int nblk = (nP + NB - 1) / NB;
 
+    if (nblk > 0) nd_diag_fetch(L, nF, nP, (nblk - 1) * NB, tid, T, sreg);
     for (int k = tid; k < f.npiv + f.nring; k += T) {
         const int a0 = pos[k], m = pos[k + 1] - a0;
         const int q = nd.pixlist[f.pix0 + k];
         const int g0 = off ? off[q] : q;
         for (int al = 0; al < m; ++al) v[a0 + al] = vec[g0 + al];
     }
+    if (nblk > 0) nd_diag_store(Sb + ((nblk - 1) & 1) * NB * NB, tid, T, sreg);
     __syncthreads();
-    const int nblk = (nP + NB - 1) / NB;
+    for (int c = warp; c < nP; c += nwarps) {
+        const double *col = L + (size_t)c * nF;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        for (int r = nP + lane; r < nF; r += 128) {
+            const double l0 = col[r], l1 = r + 32 < nF ? col[r + 32] : 0.0, l2 = r + 64 < nF ? col[r + 64] : 0.0,
+                         l3 = r + 96 < nF ? col[r + 96] : 0.0;
+            s0 = fma(l0, v[r], s0);
+            if (r + 32 < nF) s1 = fma(l1, v[r + 32], s1);
+            if (r + 64 < nF) s2 = fma(l2, v[r + 64], s2);
+            if (r + 96 < nF) s3 = fma(l3, v[r + 96], s3);
+        }
+        double s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) tR[c] = s;
+    }
+    __syncthreads();
     for (int blk = nblk - 1; blk >= 0; --blk) {
         const int kb = blk * NB, nb = min(NB, nP - kb), k1 = kb + nb;
-        for (int idx = tid; idx < NB * NB; idx += T) {
-            const int r = idx / NB, c = idx - r * NB;
-            S[idx] = (r < nb && c <= r) ? L[(size_t)(kb + c) * nF + kb + r] : (r == c ? 1.0 : 0.0);
-        }
+        double *S = Sb + (blk & 1) * NB * NB;
+        if (blk > 0) nd_diag_fetch(L, nF, nP, kb - NB, tid, T, sreg);
         for (int c = warp; c < NB; c += nwarps) {
             double s = 0.0;
             if (c < nb) {
                 const double *col = L + (size_t)(kb + c) * nF;
                 double s0 = 0.0, s1 = 0.0;
-                for (int r = k1 + lane; r < nF; r += 64) {
-                    s0 = fma(col[r], v[r], s0);
-                    if (r + 32 < nF) s1 = fma(col[r + 32], v[r + 32], s1);
+                for (int r = k1 + lane; r < nP; r += 64) {
+                    const double l0 = col[r], l1 = r + 32 < nP ? col[r + 32] : 0.0;
+                    s0 = fma(l0, v[r], s0);
+                    if (r + 32 < nP) s1 = fma(l1, v[r + 32], s1);
                 }
                 s = s0 + s1;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             }
-            if (lane == 0) ts[c] = c < nb ? v[kb + c] - s : 0.0;
+            if (lane == 0) ts[c] = c < nb ? v[kb + c] - (tR[kb + c] + s) : 0.0;
         }
+        if (blk > 0) nd_diag_store(Sb + ((blk - 1) & 1) * NB * NB, tid, T, sreg);
         __syncthreads();
         if (warp == 0) nd_block_subst(S, ts, true, lane);
         __syncthreads();
