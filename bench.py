@@ -644,6 +644,13 @@ def learn_eval_extras(bp):
         # SumRegsLearningFunction.jl:246 (node-space band LU)
         rec["patch_sumregs_gradient"] = best_of_3(xp, 0.1)
         rec["patch_sumregs_gradient_reg"] = best_of_3(xp, 1e-4)
+        # the reference's two sum-of-regularisers experiments (BPLDenoising.jl:432-481: cameraman_128_5, one sample,
+        # 20 trust-region iterations) through the host restatement of the driver; best of two runs (warmed context)
+        for key, fn in (("learn_run_scalar", trbox.scalar_bilevel_sumregs_learn), ("learn_run_patch", trbox.patch_bilevel_sumregs_learn)):
+            runs = [fn(data, ctx=c) for _ in range(2)]
+            res = min(runs, key=lambda r: r.seconds)
+            rec[key] = {"seconds": res.seconds, "seconds_first_run": runs[0].seconds, "evaluations": res.evaluations,
+                        "final_cost": res.log[-1].function_value, "x": np.asarray(res.x).ravel().tolist()}
         out["sumregs_cameraman_128_5"] = rec
 
     # λ-sweep (generate_scalar_tv_cost, /root/reference/src/BPLDenoising.jl:92-130): 64 parameters ×

@@ -651,6 +651,10 @@ static int run_gradient3_nd_mult(NdWork &w, const Nd3mProblem &gp, int sm_count,
         cudaMemGetInfo(&free_b, &total_b);
         const size_t have = w.pix.bytes + w.ast.bytes + w.L.bytes + w.U0.bytes + w.U1.bytes + w.vec.bytes + w.posg.bytes + w.foff.bytes;
         w.budget_cached = (free_b + have) / 2;
+        {   // test hook: BPLTV_ND3_BUDGET_MB replaces the memory budget of a wave (exercises the smaller-wave retry)
+            const char *bm = bpltv::env_get("BPLTV_ND3_BUDGET_MB");
+            if (bm && *bm) w.budget_cached = (size_t)atoll(bm) << 20;
+        }
         slots = (int)std::min<size_t>((size_t)slots, std::max<size_t>(1, w.budget_cached / (fix_bytes + pool_est)));
         w.slots_key_n = n; w.slots_key_node = 4; w.slots_key_want = want; w.slots_cached = slots;
     }
@@ -735,6 +739,12 @@ static int run_gradient3_nd_mult(NdWork &w, const Nd3mProblem &gp, int sm_count,
         for (int s = 0; s < nsteps; ++s) {
             plan[s] = nd_level_plan_sized(sym, s, h_lvl[2 * s], s > 0 ? h_lvl[2 * (s - 1) + 1] : 0, cta_warps_f, 512);
             fsmem = std::max(fsmem, plan[s].smem_f); ssmem = std::max(ssmem, plan[s].smem_s);
+        }
+        {   // test hook: BPLTV_ND3_MAXF caps the front size this path takes (exercises the fall-back below)
+            const char *mf = bpltv::env_get("BPLTV_ND3_MAXF");
+            if (mf && *mf)
+                for (int s = 0; s < nsteps; ++s)
+                    if (h_lvl[2 * s] > atoi(mf)) return -1;
         }
         if ((rc = nd_kernel_attributes(w, fsmem, ssmem, 0, 0, smem_optin))) return rc;      // -1: the band Cholesky
         if ((rc = need(w.L, Ls * 8 * cnt, "factors"))) return rc;

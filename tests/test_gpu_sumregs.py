@@ -319,6 +319,43 @@ def test_sumregs_gradient_nested_dissection_vs_band_cholesky(bp, ctx, sr, datase
             assert np.all(np.abs(gp_nd - dp) <= 1e-10 * np.abs(dp).max()), (gp_nd, dp)
 
 
+def test_sumregs_gradient_fallback_and_wave_retry(bp, sr, datasets):
+    """Two data-dependent branches of the multiplier-form driver (gradient_nd.cuh, run_gradient3_nd_mult): a front beyond
+    what the path takes sends the call to the band Cholesky (BPLTV_ND3_MAXF forces it), and a wave whose measured pools
+    exceed the memory budget is repeated with fewer images (BPLTV_ND3_BUDGET_MB forces it) — same gradients either way."""
+    import os
+    x = np.array([0.03, 0.02, 0.04])
+    t, f = _crop(datasets, "faces_train_128_10", 40, k=5, off=20)
+    with bp.Context([0], 64) as c:
+        c.set_dataset((t, f))
+        u = np.asfortranarray(c.sumregs_denoise(f, x, bp.sumregs_pdps_opts(maxiter=300)))
+        ref = c.sumregs_gradient(x, u, regularised=False)
+        launches = c.stats()["kernel_launches"]
+        os.environ["BPLTV_GRAD_SOLVER"] = "1"
+        bp.reload_env()
+        band = c.sumregs_gradient(x, u, regularised=False)
+        del os.environ["BPLTV_GRAD_SOLVER"]
+        os.environ["BPLTV_ND3_MAXF"] = "100"
+        bp.reload_env()
+        try:
+            fb = c.sumregs_gradient(x, u, regularised=False)
+            assert np.array_equal(fb, band) and c.stats()["kernel_launches"] < launches
+        finally:
+            del os.environ["BPLTV_ND3_MAXF"]
+            bp.reload_env()
+    os.environ["BPLTV_ND3_BUDGET_MB"] = "40"       # room for one or two 40×40 images per wave, not five
+    bp.reload_env()
+    try:
+        with bp.Context([0], 64) as c:
+            c.set_dataset((t, f))
+            small = c.sumregs_gradient(x, u, regularised=False)
+            assert c.stats()["kernel_launches"] > launches          # several waves
+    finally:
+        del os.environ["BPLTV_ND3_BUDGET_MB"]
+        bp.reload_env()
+    assert np.all(np.abs(small - ref) <= 1e-12 * np.abs(ref).max()), (small, ref)
+
+
 def test_cluster_factorisation_is_invisible(bp, ctx, sr, datasets):
     """The banded Cholesky shared by a thread-block cluster (2, 4, 8 CTAs per image) gives bit-identical
     gradients to the single-CTA factorisation, for the TV and the sum-of-regularisers systems."""
