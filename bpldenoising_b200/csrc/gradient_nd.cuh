@@ -195,7 +195,9 @@ static int nd_prepare_levels(NdWork &w, const NdSymbolic &sym, int mb, double fs
     // kernel is bound by the barriers of its block steps, not by threads); few images keep the wide CTAs.  The CTA size of
     // the solves makes no measurable difference.  BPLTV_ND_WARPS_F / BPLTV_ND_THREADS_S override.
     const char *e1 = bpltv::env_get("BPLTV_ND_WARPS_F"), *e2 = bpltv::env_get("BPLTV_ND_THREADS_S");
-    const int cta_warps_f = e1 && *e1 ? std::max(2, std::min(16, atoi(e1))) : (O >= 32 ? 4 : 16);
+    // (the width is now decided per level at launch time, nd_factor_cta_threads: the plan carries the widest CTA)
+    const int cta_warps_f = e1 && *e1 ? std::max(2, std::min(16, atoi(e1))) : 16;
+    (void)O;
     const int cta_threads_s = e2 && *e2 ? std::max(64, std::min(512, atoi(e2))) : 512;
     plan.assign(nsteps, NdLevelPlan());
     plan_small.assign(nsteps, 0);
@@ -274,6 +276,18 @@ static cudaError_t nd_launch_factor_cluster(const NdDev &nd, const NdLevelPlan &
     return cudaGetLastError();
 }
 
+// CTA width of the generic front factorisation of one level.  A level with several fronts per SM runs narrow CTAs (4
+// warps, four CTAs per SM: more independent fronts in flight hide the latency chain of a block step), a level with about
+// one front per SM gives each front the whole SM (16 warps).  Measured as a global choice in round 2 (4 warps won by
+// 5-12 % on stacks); per level the top of the tree no longer pays for it (ncu, 128 × 256²: the root level ran 128 CTAs of
+// 4 warps, 43 tile rounds per block step).
+static int nd_factor_cta_threads(const NdLevelPlan &lp, int cnt, int sm_count)
+{
+    const long long fronts = (long long)lp.nfr * cnt;
+    const int cap = 2 * fronts <= 3LL * sm_count ? 16 : (fronts <= 3LL * sm_count ? 8 : 4);
+    return std::min(lp.threads_f, 32 * cap);
+}
+
 // one launch per level: assemble + partial Cholesky of every front of the wave's `cnt` images
 static void nd_launch_factor(const NdDev &nd, std::vector<NdLevelPlan> &plan, const std::vector<char> &plan_small,
                              const NdSymbolic &sym, int mb, int cnt, int sm_count, double guard, cudaStream_t st, long long *launches)
@@ -290,7 +304,7 @@ static void nd_launch_factor(const NdDev &nd, std::vector<NdLevelPlan> &plan, co
         else {
             const int C = nd_cluster_size(lp, cnt, sm_count);
             if (C > 1) nd_launch_factor_cluster(nd, lp, s, cnt, C, guard, st);
-            else nd_factor_kernel<<<dim3(lp.nfr, cnt), lp.threads_f, nd_factor_smem(lp.nFw, lp.nRc), st>>>(nd, lp.t0, s & 1, guard, lp.nFw);
+            else nd_factor_kernel<<<dim3(lp.nfr, cnt), nd_factor_cta_threads(lp, cnt, sm_count), nd_factor_smem(lp.nFw, lp.nRc), st>>>(nd, lp.t0, s & 1, guard, lp.nFw);
         }
     }
     *launches += nsteps;
