@@ -238,6 +238,20 @@ struct Dev {
     std::vector<unsigned char> steps_host;
     long long launches = 0;
     HostStage hstage;         // pinned slots for pageable caller buffers
+    // denoise with pinned host buffers: the copies of image chunks run on a second stream under the first and the last
+    // passes of the streaming solve (PipeIO below)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t pipe_ev[2 * 8 + 2] = {nullptr};
+};
+
+// Host↔device copies of a denoise call overlapped with its solve.  The stack is cut into `chunks` groups of images; the
+// first `q` passes of the temporally blocked kernel run chunk by chunk as the uploads arrive, the middle passes on the
+// whole stack, the last `q` passes chunk by chunk again with each chunk's download following it on the copy stream.
+// Images are independent and every range cut of the kernel is bit-identical, so the result does not change.
+struct PipeIO {
+    const double *h_in = nullptr;     // this device's shard of the caller's noisy stack (pinned)
+    double *h_out = nullptr;          // … of the caller's result (pinned)
+    int chunks = 3, q = 6;           // measured on config 4 (e2e Gpixel-iter/s): K×q = 3×6 190.1, 4×6 189.1, 6×4 189.4, 8×3 188.5; serial 185.2
 };
 
 struct bpltv_ctx {
@@ -410,8 +424,11 @@ static int tblock_vec(int M)
 // of iterations done (the caller finishes the remainder with kernel A).
 template <typename Real, int T>
 static int run_tblock_passes(Dev &d, const Real *f, int M, int N, int O, Real alpha_s, const Real *alpha_map,
-                             bool strict, int it0, int iters, cudaStream_t st, int *buf, const BatchMap<Real> &bm)
+                             bool strict, int it0, int iters, cudaStream_t st, int *buf, const BatchMap<Real> &bm,
+                             int o0 = 0, int oc = -1)      // images [o0, o0 + oc) of the stack only (oc < 0: all)
 {
+    const size_t img_off = (size_t)o0 * M * N;
+    if (oc >= 0) { f += img_off; O = oc; }
     const int vec = tblock_vec<Real>(M);
     const int nthreads = (M / vec + 31) / 32 * 32;
     const bool batch = bm.alpha_vec != nullptr || bm.f_mod != 0 || bm.lam_div != 0;
@@ -436,8 +453,8 @@ static int run_tblock_passes(Dev &d, const Real *f, int M, int N, int O, Real al
     int done = 0;
     for (int it = it0; it + T <= it0 + iters; it += T) {
         const int bi = *buf, bo = bi ^ 1;
-        a.x_in = d.x[bi].as<Real>(); a.y1_in = d.y1[bi].as<Real>(); a.y2_in = d.y2[bi].as<Real>();
-        a.x_out = d.x[bo].as<Real>(); a.y1_out = d.y1[bo].as<Real>(); a.y2_out = d.y2[bo].as<Real>();
+        a.x_in = d.x[bi].as<Real>() + img_off; a.y1_in = d.y1[bi].as<Real>() + img_off; a.y2_in = d.y2[bi].as<Real>() + img_off;
+        a.x_out = d.x[bo].as<Real>() + img_off; a.y1_out = d.y1[bo].as<Real>() + img_off; a.y2_out = d.y2[bo].as<Real>() + img_off;
         for (int s = 0; s < T; ++s) a.sc[s] = hsteps[it + s];
         fn<<<(unsigned)grid, nthreads, smem, st>>>(a);
         *buf = bo;
@@ -447,25 +464,13 @@ static int run_tblock_passes(Dev &d, const Real *f, int M, int N, int O, Real al
     return done;
 }
 
-// Runs opts.maxiter iterations on `f` (device, M×N×O Reals).  On return (stream
-// order) the denoised stack is in *u_result (one of the ping-pong buffers).
+// Which lower-level kernel a solve of O images of M×N takes (bpltv_pdps_opts.kernel, AUTO rules) and, for the
+// temporally blocked one, its depth.
 template <typename Real>
-static int run_pdps(Dev &d, const Real *f, int M, int N, int O, double alpha_s, const Real *alpha_map,
-                    const bpltv_pdps_opts &o, cudaStream_t st, const Real **u_result, int *kernel_used,
-                    int *depth_used = nullptr, const BatchMap<Real> *bmap = nullptr)
+static int choose_pdps_kernel(Dev &d, int M, int N, int O, const bpltv_pdps_opts &o, int *kernel_out, int *tdepth_out)
 {
-    if (O == 0) { *u_result = nullptr; return 0; }
-    const size_t n = (size_t)M * N * O;
-    for (int b = 0; b < 2; ++b) {
-        RC_TRY(d.x[b].ensure(n * sizeof(Real)));
-        RC_TRY(d.y1[b].ensure(n * sizeof(Real)));
-        RC_TRY(d.y2[b].ensure(n * sizeof(Real)));
-    }
     const bool strict = o.arith == BPLTV_ARITH_STRICT;
     const bool rho = o.rho != 0.0;
-    const bool map = alpha_map != nullptr;
-    const BatchMap<Real> bm = bmap ? *bmap : BatchMap<Real>();
-
     int kernel = o.kernel;
     if (kernel == BPLTV_KERNEL_AUTO) kernel = env_int("BPLTV_PDPS_KERNEL", 0);
     if (kernel == BPLTV_KERNEL_AUTO) {
@@ -500,6 +505,104 @@ static int run_pdps(Dev &d, const Real *f, int M, int N, int O, double alpha_s, 
         if (!tblock_vec<Real>(M) || rho)
             return fail(BPLTV_ERR_ARG, "temporally blocked PDPS kernel does not take M=%d (rho=%g)", M, o.rho);
     }
+    *kernel_out = kernel; *tdepth_out = tdepth;
+    return 0;
+}
+
+// The pipelined form of a denoise call with host buffers (PipeIO): decided before the upload.  fp64 contexts, pinned
+// caller buffers (pageable ones go through the staging threads), the temporally blocked kernel with a whole number of
+// passes, a stack large enough for the copies to matter.  BPLTV_PIPE_IO=0 switches it off; BPLTV_PIPE_MIN_MB,
+// BPLTV_PIPE_CHUNKS, BPLTV_PIPE_PASSES tune it (tests).
+template <typename Real>
+static bool pipe_eligible(Dev &d, int M, int N, int O, const bpltv_pdps_opts &o, int kernel, int tdepth, const double *h_in,
+                          double *h_out, PipeIO *pio)
+{
+    if (sizeof(Real) != 8 || !h_in || !h_out || !env_int("BPLTV_PIPE_IO", 1)) return false;
+    if (kernel != BPLTV_KERNEL_TBLOCK || tdepth < 2 || o.maxiter % tdepth != 0) return false;
+    const int K = std::max(2, std::min(8, env_int("BPLTV_PIPE_CHUNKS", 3)));
+    const int q = std::max(1, env_int("BPLTV_PIPE_PASSES", 6));
+    if (o.maxiter / tdepth < 4 * q || O < 2 * K) return false;
+    if ((size_t)M * N * O * 8 < ((size_t)env_int("BPLTV_PIPE_MIN_MB", 32) << 20)) return false;
+    if (host_is_pageable(h_in) || host_is_pageable(h_out)) return false;
+    if (!d.copy_stream && cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return false; }
+    for (auto &e : d.pipe_ev)
+        if (!e && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
+    pio->h_in = h_in; pio->h_out = h_out; pio->chunks = K; pio->q = q;
+    return true;
+}
+
+// All passes of a pipelined denoise call (see PipeIO).  f = d.fbuf (filled here, chunk by chunk, on the copy stream).
+template <typename Real, int T>
+static int run_tblock_pipelined(Dev &d, Real *f, int M, int N, int O, Real alpha_s, const Real *alpha_map, bool strict,
+                                int maxiter, int init_mode, cudaStream_t st, int *buf, const BatchMap<Real> &bm, const PipeIO &pio)
+{
+    const int K = pio.chunks, q = pio.q, P = maxiter / T;
+    const size_t plane = (size_t)M * N;
+    cudaStream_t cs = d.copy_stream;
+    cudaEvent_t ev_start = d.pipe_ev[16], ev_end = d.pipe_ev[17];
+    // the copy stream joins: nothing enqueued earlier on `st` may still read the buffers the uploads overwrite
+    if (cudaEventRecord(ev_start, st) != cudaSuccess || cudaStreamWaitEvent(cs, ev_start, 0) != cudaSuccess) return -1;
+    for (int k = 0; k < K; ++k) {
+        const int o0 = (int)((long long)O * k / K), o1 = (int)((long long)O * (k + 1) / K);
+        const size_t off = plane * o0, cnt = plane * (o1 - o0);
+        if (cudaMemcpyAsync(reinterpret_cast<double *>(f) + off, pio.h_in + off, cnt * 8, cudaMemcpyHostToDevice, cs) != cudaSuccess) return -1;
+        if (cudaEventRecord(d.pipe_ev[k], cs) != cudaSuccess) return -1;
+    }
+    const int b0 = *buf;
+    int b_end = b0;
+    for (int k = 0; k < K; ++k) {
+        const int o0 = (int)((long long)O * k / K), o1 = (int)((long long)O * (k + 1) / K);
+        const size_t off = plane * o0, cnt = plane * (o1 - o0);
+        if (cudaStreamWaitEvent(st, d.pipe_ev[k], 0) != cudaSuccess) return -1;
+        if (init_mode && cudaMemcpyAsync(d.x[b0].as<Real>() + off, f + off, cnt * sizeof(Real), cudaMemcpyDeviceToDevice, st) != cudaSuccess) return -1;
+        int b = b0;
+        const int rc = run_tblock_passes<Real, T>(d, f, M, N, O, alpha_s, alpha_map, strict, 0, q * T, st, &b, bm, o0, o1 - o0);
+        if (rc < 0) return rc;
+        b_end = b;
+    }
+    *buf = b_end;
+    {
+        const int rc = run_tblock_passes<Real, T>(d, f, M, N, O, alpha_s, alpha_map, strict, q * T, (P - 2 * q) * T, st, buf, bm);
+        if (rc < 0) return rc;
+    }
+    const int b1 = *buf;
+    for (int k = 0; k < K; ++k) {
+        const int o0 = (int)((long long)O * k / K), o1 = (int)((long long)O * (k + 1) / K);
+        const size_t off = plane * o0, cnt = plane * (o1 - o0);
+        int b = b1;
+        const int rc = run_tblock_passes<Real, T>(d, f, M, N, O, alpha_s, alpha_map, strict, (P - q) * T, q * T, st, &b, bm, o0, o1 - o0);
+        if (rc < 0) return rc;
+        b_end = b;
+        if (cudaEventRecord(d.pipe_ev[8 + k], st) != cudaSuccess || cudaStreamWaitEvent(cs, d.pipe_ev[8 + k], 0) != cudaSuccess) return -1;
+        if (cudaMemcpyAsync(pio.h_out + off, reinterpret_cast<const double *>(d.x[b].as<Real>()) + off, cnt * 8, cudaMemcpyDeviceToHost, cs) != cudaSuccess) return -1;
+    }
+    *buf = b_end;
+    // `st` ends behind the last download: whoever synchronises the context's stream has the result in the caller's buffer
+    if (cudaEventRecord(ev_end, cs) != cudaSuccess || cudaStreamWaitEvent(st, ev_end, 0) != cudaSuccess) return -1;
+    return P * T;
+}
+
+// Runs opts.maxiter iterations on `f` (device, M×N×O Reals).  On return (stream
+// order) the denoised stack is in *u_result (one of the ping-pong buffers).
+template <typename Real>
+static int run_pdps(Dev &d, const Real *f, int M, int N, int O, double alpha_s, const Real *alpha_map,
+                    const bpltv_pdps_opts &o, cudaStream_t st, const Real **u_result, int *kernel_used,
+                    int *depth_used = nullptr, const BatchMap<Real> *bmap = nullptr, const PipeIO *pipe = nullptr)
+{
+    if (O == 0) { *u_result = nullptr; return 0; }
+    const size_t n = (size_t)M * N * O;
+    for (int b = 0; b < 2; ++b) {
+        RC_TRY(d.x[b].ensure(n * sizeof(Real)));
+        RC_TRY(d.y1[b].ensure(n * sizeof(Real)));
+        RC_TRY(d.y2[b].ensure(n * sizeof(Real)));
+    }
+    const bool strict = o.arith == BPLTV_ARITH_STRICT;
+    const bool rho = o.rho != 0.0;
+    const bool map = alpha_map != nullptr;
+    const BatchMap<Real> bm = bmap ? *bmap : BatchMap<Real>();
+
+    int kernel = 0, tdepth = 1;
+    RC_TRY(choose_pdps_kernel<Real>(d, M, N, O, o, &kernel, &tdepth));
     *kernel_used = kernel;
     if (depth_used) *depth_used = tdepth;
 
@@ -523,7 +626,9 @@ static int run_pdps(Dev &d, const Real *f, int M, int N, int O, double alpha_s, 
     }
 
     // x⁰ = 0 | f (S3), y⁰ = 0
-    if (o.init_mode) {
+    if (o.init_mode && pipe) {
+        // x⁰ = f chunk by chunk, as the uploads arrive (run_tblock_pipelined)
+    } else if (o.init_mode) {
         const int Of = bm.f_mod ? bm.f_mod : O;   // a sweep's virtual stack repeats the Of images of f
         for (int v0 = 0; v0 < O; v0 += Of)
             CU_TRY(cudaMemcpyAsync(d.x[0].as<Real>() + (size_t)v0 * M * N, f,
@@ -536,7 +641,13 @@ static int run_pdps(Dev &d, const Real *f, int M, int N, int O, double alpha_s, 
     int it_begin = 0;  // iterations already done
     if (kernel == BPLTV_KERNEL_TBLOCK && tdepth > 1) {
         int done = 0;
-        if (tdepth == 2) done = run_tblock_passes<Real, 2>(d, f, M, N, O, (Real)alpha_s, alpha_map, strict, 0, o.maxiter, st, &buf, bm);
+        if (pipe) {
+            Real *fw = const_cast<Real *>(f);
+            if (tdepth == 2) done = run_tblock_pipelined<Real, 2>(d, fw, M, N, O, (Real)alpha_s, alpha_map, strict, o.maxiter, o.init_mode, st, &buf, bm, *pipe);
+            else if (tdepth == 3) done = run_tblock_pipelined<Real, 3>(d, fw, M, N, O, (Real)alpha_s, alpha_map, strict, o.maxiter, o.init_mode, st, &buf, bm, *pipe);
+            else done = run_tblock_pipelined<Real, 4>(d, fw, M, N, O, (Real)alpha_s, alpha_map, strict, o.maxiter, o.init_mode, st, &buf, bm, *pipe);
+        }
+        else if (tdepth == 2) done = run_tblock_passes<Real, 2>(d, f, M, N, O, (Real)alpha_s, alpha_map, strict, 0, o.maxiter, st, &buf, bm);
         else if (tdepth == 3) done = run_tblock_passes<Real, 3>(d, f, M, N, O, (Real)alpha_s, alpha_map, strict, 0, o.maxiter, st, &buf, bm);
         else done = run_tblock_passes<Real, 4>(d, f, M, N, O, (Real)alpha_s, alpha_map, strict, 0, o.maxiter, st, &buf, bm);
         if (done == -2) return fail(BPLTV_ERR_ARG, "λ-sweeps through the temporally blocked kernel are built for depths 2 and 4 only");
@@ -707,6 +818,7 @@ static int denoise_impl(bpltv_ctx *ctx, const double *noisy, int M, int N, int O
     // download_stack wait for the device, which must not hold back the other devices' work)
     std::vector<const Real *> us(ndev, nullptr);
     std::vector<int> obs(ndev, 0), ocs(ndev, 0);
+    std::vector<char> piped_dev(ndev, 0);      // the solve carried its own copies (PipeIO)
     for (int di = 0; di < ndev; ++di) {
         Dev &d = ctx->devs[di];
         CU_TRY(cudaSetDevice(d.id));
@@ -718,7 +830,18 @@ static int denoise_impl(bpltv_ctx *ctx, const double *noisy, int M, int N, int O
         cudaStream_t st = d.stream;
         CU_TRY(cudaEventRecord(d.ev[0], st));
         const Real *f;
-        if (noisy) {
+        PipeIO pio;
+        bool piped = false;
+        if (noisy && oc > 0) {
+            int k_ = 0, t_ = 1;
+            RC_TRY(choose_pdps_kernel<Real>(d, M, N, oc, o, &k_, &t_));
+            piped = pipe_eligible<Real>(d, M, N, oc, o, k_, t_, noisy + plane * ob, u_out + plane * ob, &pio);
+        }
+        piped_dev[di] = piped;
+        if (noisy && piped) {
+            RC_TRY(d.fbuf.ensure(plane * oc * sizeof(Real)));      // filled chunk by chunk under the first passes
+            f = d.fbuf.as<Real>();
+        } else if (noisy) {
             RC_TRY(upload_stack<Real>(d, noisy + plane * ob, plane * oc, d.fbuf, st));
             f = d.fbuf.as<Real>();
         } else {
@@ -728,7 +851,7 @@ static int denoise_impl(bpltv_ctx *ctx, const double *noisy, int M, int N, int O
         double alpha_s; const Real *amap;
         RC_TRY(prepare_lambda<Real>(d, lam, lm, ln, M, N, st, &alpha_s, &amap));
         int used = 0, depth = 1;
-        RC_TRY(run_pdps<Real>(d, f, M, N, oc, alpha_s, amap, o, st, &us[di], &used, &depth));
+        RC_TRY(run_pdps<Real>(d, f, M, N, oc, alpha_s, amap, o, st, &us[di], &used, &depth, nullptr, piped ? &pio : nullptr));
         ctx->stats.pdps_kernel_used = used;
         ctx->stats.tblock_depth = depth;
         CU_TRY(cudaEventRecord(d.ev[2], st));
@@ -736,7 +859,7 @@ static int denoise_impl(bpltv_ctx *ctx, const double *noisy, int M, int N, int O
     for (int di = 0; di < ndev; ++di) {
         Dev &d = ctx->devs[di];
         CU_TRY(cudaSetDevice(d.id));
-        if (ocs[di] > 0) RC_TRY(download_stack<Real>(d, us[di], plane * ocs[di], u_out + plane * obs[di], d.stream));
+        if (ocs[di] > 0 && !piped_dev[di]) RC_TRY(download_stack<Real>(d, us[di], plane * ocs[di], u_out + plane * obs[di], d.stream));
         CU_TRY(cudaEventRecord(d.ev[3], d.stream));
     }
     for (int di = 0; di < ndev; ++di) {
@@ -1537,6 +1660,8 @@ int bpltv_destroy(bpltv_ctx *ctx)
         d.nd = nullptr;
         d.hstage.release();
         for (auto &ev : d.ev) if (ev) cudaEventDestroy(ev);
+        for (auto &ev : d.pipe_ev) if (ev) cudaEventDestroy(ev);
+        if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
     delete ctx;

@@ -403,3 +403,52 @@ def test_large_pageable_stacks_through_a_two_device_context(bp):
             v2, cost2, _ = c2.learn_eval(0.1, 0.1, eo)
             assert np.array_equal(v1, v2) and np.array_equal(v1, u1) and abs(cost1 - cost2) <= 1e-13 * cost1, prec
     # the one-device fp32 result itself is pinned to the oracle at this shape by the config-4 SHA-256 pins
+
+
+def test_pipelined_host_copies_do_not_change_the_result(bp):
+    """denoise(data, x) with PINNED host buffers: the uploads and downloads of image chunks run on a second stream under
+    the first and the last passes of the temporally blocked kernel (PipeIO, bpltv_api.cu).  Same bits as the serial
+    upload → solve → download, for x⁰ = 0 and x⁰ = f, and the launch count shows that the chunked passes ran."""
+    import os
+    torch = pytest.importorskip("torch")
+    M = N = 64
+    O = 16
+    _, f = bp.synthetic_dataset(M, N, O, seed=11)
+    h_in = torch.empty((O, N, M), dtype=torch.float64).pin_memory()
+    h_out = torch.empty((O, N, M), dtype=torch.float64).pin_memory()
+    np_in = h_in.numpy().transpose(2, 1, 0)      # Fortran-ordered M×N×O views of the pinned buffers
+    np_out = h_out.numpy().transpose(2, 1, 0)
+    np_in[...] = f
+    for init_mode in (0, 1):
+        o = bp.pdps_opts(maxiter=120, kernel=bp.KERNEL_TBLOCK, init_mode=init_mode)
+        res = {}
+        for pipe in ("1", "0"):
+            os.environ["BPLTV_PIPE_IO"] = pipe
+            os.environ["BPLTV_PIPE_MIN_MB"] = "0"
+            os.environ["BPLTV_PIPE_CHUNKS"] = "4"
+            bp.reload_env()
+            try:
+                with bp.Context([0], 64) as c:
+                    np_out[...] = -1.0
+                    c.denoise(np_in, 0.1, o, out=np_out)
+                    res[pipe] = (np_out.copy(), c.stats()["kernel_launches"], c.stats()["tblock_depth"])
+            finally:
+                del os.environ["BPLTV_PIPE_IO"], os.environ["BPLTV_PIPE_MIN_MB"], os.environ["BPLTV_PIPE_CHUNKS"]
+                bp.reload_env()
+        depth = res["0"][2]
+        passes = 120 // depth
+        assert res["0"][1] == passes
+        assert res["1"][1] == passes + 2 * 6 * (4 - 1), res       # 4 chunks × 6 passes at either end instead of 6 whole ones
+        assert np.array_equal(res["1"][0], res["0"][0]), init_mode
+    # a pageable destination keeps the serial path
+    os.environ["BPLTV_PIPE_MIN_MB"] = "0"
+    bp.reload_env()
+    try:
+        with bp.Context([0], 64) as c:
+            u = c.denoise(np_in, 0.1, bp.pdps_opts(maxiter=120, kernel=bp.KERNEL_TBLOCK))
+            assert c.stats()["kernel_launches"] == 120 // c.stats()["tblock_depth"]
+            o0 = bp.pdps_opts(maxiter=120, kernel=bp.KERNEL_TBLOCK)
+            assert o0.init_mode == 0 or np.array_equal(u, res["0"][0])      # (the loop's last result is init_mode = 1)
+    finally:
+        del os.environ["BPLTV_PIPE_MIN_MB"]
+        bp.reload_env()
