@@ -251,6 +251,7 @@ struct Dev {
 struct PipeIO {
     const double *h_in = nullptr;     // this device's shard of the caller's noisy stack (pinned)
     double *h_out = nullptr;          // … of the caller's result (pinned)
+    bool stage_in = false, stage_out = false;   // pageable buffers: through the context's pinned slots
     int chunks = 3, q = 6;           // measured on config 4 (e2e Gpixel-iter/s): K×q = 3×6 190.1, 4×6 189.1, 6×4 189.4, 8×3 188.5; serial 185.2
 };
 
@@ -523,7 +524,14 @@ static bool pipe_eligible(Dev &d, int M, int N, int O, const bpltv_pdps_opts &o,
     const int q = std::max(1, env_int("BPLTV_PIPE_PASSES", 6));
     if (o.maxiter / tdepth < 4 * q || O < 2 * K) return false;
     if ((size_t)M * N * O * 8 < ((size_t)env_int("BPLTV_PIPE_MIN_MB", 32) << 20)) return false;
-    if (host_is_pageable(h_in) || host_is_pageable(h_out)) return false;
+    // Pageable caller buffers keep the serial path unless BPLTV_PIPE_PAGEABLE=1: their chunks can travel through the
+    // pinned slots (HostStage) on the copy stream, but the staging threads are the bottleneck there and the measured
+    // gain was nil (95.6 vs 95.5 ms per step at config 4), so the simpler order stays the default.
+    const bool pg_in = host_is_pageable(h_in), pg_out = host_is_pageable(h_out);
+    if ((pg_in || pg_out) && !env_int("BPLTV_PIPE_PAGEABLE", 0)) return false;
+    pio->stage_in = pg_in && env_int("BPLTV_HOST_STAGING", 1) && d.hstage.init();
+    pio->stage_out = pg_out && env_int("BPLTV_HOST_STAGING", 1) && d.hstage.init();
+    if ((pg_in && !pio->stage_in) || (pg_out && !pio->stage_out)) return false;
     if (!d.copy_stream && cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return false; }
     for (auto &e : d.pipe_ev)
         if (!e && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -542,17 +550,27 @@ static int run_tblock_pipelined(Dev &d, Real *f, int M, int N, int O, Real alpha
     cudaEvent_t ev_start = d.pipe_ev[16], ev_end = d.pipe_ev[17];
     // the copy stream joins: nothing enqueued earlier on `st` may still read the buffers the uploads overwrite
     if (cudaEventRecord(ev_start, st) != cudaSuccess || cudaStreamWaitEvent(cs, ev_start, 0) != cudaSuccess) return -1;
-    for (int k = 0; k < K; ++k) {
-        const int o0 = (int)((long long)O * k / K), o1 = (int)((long long)O * (k + 1) / K);
-        const size_t off = plane * o0, cnt = plane * (o1 - o0);
-        if (cudaMemcpyAsync(reinterpret_cast<double *>(f) + off, pio.h_in + off, cnt * 8, cudaMemcpyHostToDevice, cs) != cudaSuccess) return -1;
-        if (cudaEventRecord(d.pipe_ev[k], cs) != cudaSuccess) return -1;
-    }
+    // (a staged upload occupies the calling thread until the caller's chunk has been read: the passes of the chunks that
+    // are already on the device were enqueued before and run meanwhile)
+    auto upload = [&](size_t off, size_t cnt) -> cudaError_t {
+        char *dst = reinterpret_cast<char *>(reinterpret_cast<double *>(f) + off);
+        char *src = reinterpret_cast<char *>(const_cast<double *>(pio.h_in + off));
+        if (pio.stage_in && cnt * 8 >= HostStage::MIN_BYTES) return staged_copy(d.hstage, d.id, dst, src, cnt * 8, cs, true);
+        return cudaMemcpyAsync(dst, src, cnt * 8, cudaMemcpyHostToDevice, cs);
+    };
+    auto download = [&](size_t off, size_t cnt, const Real *u) -> cudaError_t {
+        char *src = reinterpret_cast<char *>(const_cast<double *>(reinterpret_cast<const double *>(u) + off));
+        char *dst = reinterpret_cast<char *>(pio.h_out + off);
+        if (pio.stage_out && cnt * 8 >= HostStage::MIN_BYTES) return staged_copy(d.hstage, d.id, src, dst, cnt * 8, cs, false);
+        return cudaMemcpyAsync(dst, src, cnt * 8, cudaMemcpyDeviceToHost, cs);
+    };
     const int b0 = *buf;
     int b_end = b0;
     for (int k = 0; k < K; ++k) {
         const int o0 = (int)((long long)O * k / K), o1 = (int)((long long)O * (k + 1) / K);
         const size_t off = plane * o0, cnt = plane * (o1 - o0);
+        if (upload(off, cnt) != cudaSuccess) return -1;
+        if (cudaEventRecord(d.pipe_ev[k], cs) != cudaSuccess) return -1;
         if (cudaStreamWaitEvent(st, d.pipe_ev[k], 0) != cudaSuccess) return -1;
         if (init_mode && cudaMemcpyAsync(d.x[b0].as<Real>() + off, f + off, cnt * sizeof(Real), cudaMemcpyDeviceToDevice, st) != cudaSuccess) return -1;
         int b = b0;
@@ -573,10 +591,16 @@ static int run_tblock_pipelined(Dev &d, Real *f, int M, int N, int O, Real alpha
         const int rc = run_tblock_passes<Real, T>(d, f, M, N, O, alpha_s, alpha_map, strict, (P - q) * T, q * T, st, &b, bm, o0, o1 - o0);
         if (rc < 0) return rc;
         b_end = b;
-        if (cudaEventRecord(d.pipe_ev[8 + k], st) != cudaSuccess || cudaStreamWaitEvent(cs, d.pipe_ev[8 + k], 0) != cudaSuccess) return -1;
-        if (cudaMemcpyAsync(pio.h_out + off, reinterpret_cast<const double *>(d.x[b].as<Real>()) + off, cnt * 8, cudaMemcpyDeviceToHost, cs) != cudaSuccess) return -1;
+        if (cudaEventRecord(d.pipe_ev[8 + k], st) != cudaSuccess) return -1;
     }
     *buf = b_end;
+    // the downloads follow their chunks (all passes are enqueued by now: a staged download may occupy this thread)
+    for (int k = 0; k < K; ++k) {
+        const int o0 = (int)((long long)O * k / K), o1 = (int)((long long)O * (k + 1) / K);
+        const size_t off = plane * o0, cnt = plane * (o1 - o0);
+        if (cudaStreamWaitEvent(cs, d.pipe_ev[8 + k], 0) != cudaSuccess) return -1;
+        if (download(off, cnt, d.x[b_end].as<Real>()) != cudaSuccess) return -1;
+    }
     // `st` ends behind the last download: whoever synchronises the context's stream has the result in the caller's buffer
     if (cudaEventRecord(ev_end, cs) != cudaSuccess || cudaStreamWaitEvent(st, ev_end, 0) != cudaSuccess) return -1;
     return P * T;

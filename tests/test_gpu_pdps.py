@@ -440,15 +440,39 @@ def test_pipelined_host_copies_do_not_change_the_result(bp):
         assert res["0"][1] == passes
         assert res["1"][1] == passes + 2 * 6 * (4 - 1), res       # 4 chunks × 6 passes at either end instead of 6 whole ones
         assert np.array_equal(res["1"][0], res["0"][0]), init_mode
-    # a pageable destination keeps the serial path
+    # pageable caller buffers (what a Julia Array is): the same pipeline, the chunks through the context's pinned slots
+    # when they are large enough for the staging threads (here they are not: the driver's own pageable path)
     os.environ["BPLTV_PIPE_MIN_MB"] = "0"
+    os.environ["BPLTV_PIPE_CHUNKS"] = "4"
+    os.environ["BPLTV_PIPE_PAGEABLE"] = "1"          # opt-in (no measured gain: the staging threads bind that path)
     bp.reload_env()
     try:
         with bp.Context([0], 64) as c:
-            u = c.denoise(np_in, 0.1, bp.pdps_opts(maxiter=120, kernel=bp.KERNEL_TBLOCK))
-            assert c.stats()["kernel_launches"] == 120 // c.stats()["tblock_depth"]
-            o0 = bp.pdps_opts(maxiter=120, kernel=bp.KERNEL_TBLOCK)
-            assert o0.init_mode == 0 or np.array_equal(u, res["0"][0])      # (the loop's last result is init_mode = 1)
+            u = c.denoise(np.asfortranarray(f), 0.1, bp.pdps_opts(maxiter=120, kernel=bp.KERNEL_TBLOCK, init_mode=1))
+            assert c.stats()["kernel_launches"] == 120 // c.stats()["tblock_depth"] + 2 * 6 * 3
+            assert np.array_equal(u, res["0"][0])            # (the loop's last result is init_mode = 1)
     finally:
-        del os.environ["BPLTV_PIPE_MIN_MB"]
+        del os.environ["BPLTV_PIPE_MIN_MB"], os.environ["BPLTV_PIPE_CHUNKS"], os.environ["BPLTV_PIPE_PAGEABLE"]
         bp.reload_env()
+
+
+def test_pipelined_copies_of_a_large_pageable_stack(bp):
+    """64 MiB of pageable input and output: the chunks of the pipelined denoise call travel through the staging threads
+    (HostStage) on the copy stream when BPLTV_PIPE_PAGEABLE=1 (off by default: no measured gain) — same bits as the serial path."""
+    import os
+    _, f = bp.synthetic_dataset(256, 256, 128, seed=5)
+    f = np.asfortranarray(f)
+    o = bp.pdps_opts(maxiter=96)
+    res = {}
+    for pipe in ("1", "0"):
+        os.environ["BPLTV_PIPE_PAGEABLE"] = pipe
+        bp.reload_env()
+        try:
+            with bp.Context([0], 64) as c:
+                u = c.denoise(f, 0.1, o)
+                res[pipe] = (u, c.stats()["kernel_launches"], c.stats()["pdps_kernel_used"])
+        finally:
+            del os.environ["BPLTV_PIPE_PAGEABLE"]
+            bp.reload_env()
+    assert res["0"][2] == bp.KERNEL_TBLOCK and res["1"][1] > res["0"][1]
+    assert np.array_equal(res["1"][0], res["0"][0])
