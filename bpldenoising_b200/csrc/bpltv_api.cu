@@ -520,15 +520,17 @@ static bool pipe_eligible(Dev &d, int M, int N, int O, const bpltv_pdps_opts &o,
 {
     if (sizeof(Real) != 8 || !h_in || !h_out || !env_int("BPLTV_PIPE_IO", 1)) return false;
     if (kernel != BPLTV_KERNEL_TBLOCK || tdepth < 2 || o.maxiter % tdepth != 0) return false;
+    // Pageable caller buffers (a Julia Array) travel through the pinned slots (HostStage) chunk by chunk on the copy
+    // stream.  There the staging threads bind the copies (≈ 1.5-1.9 ms per third of config 4's stack against 0.8 ms of
+    // DMA), so a chunk phase has to be longer to cover them: 14 passes per chunk instead of 6.  Measured at config 4
+    // (e2e Gpixel-iter/s): pageable K×q = 3×6 175.5 (= serial), 3×14 181.7, 3×18 179.1, 4×12 180.0, 6×8 172.9; pinned 3×6
+    // 190.1, 3×14 186.5.  BPLTV_PIPE_PAGEABLE=0 keeps pageable buffers on the serial path.
+    const bool pg_in = host_is_pageable(h_in), pg_out = host_is_pageable(h_out);
+    if ((pg_in || pg_out) && !env_int("BPLTV_PIPE_PAGEABLE", 1)) return false;
     const int K = std::max(2, std::min(8, env_int("BPLTV_PIPE_CHUNKS", 3)));
-    const int q = std::max(1, env_int("BPLTV_PIPE_PASSES", 6));
+    const int q = std::max(1, env_int("BPLTV_PIPE_PASSES", (pg_in || pg_out) ? 14 : 6));
     if (o.maxiter / tdepth < 4 * q || O < 2 * K) return false;
     if ((size_t)M * N * O * 8 < ((size_t)env_int("BPLTV_PIPE_MIN_MB", 32) << 20)) return false;
-    // Pageable caller buffers keep the serial path unless BPLTV_PIPE_PAGEABLE=1: their chunks can travel through the
-    // pinned slots (HostStage) on the copy stream, but the staging threads are the bottleneck there and the measured
-    // gain was nil (95.6 vs 95.5 ms per step at config 4), so the simpler order stays the default.
-    const bool pg_in = host_is_pageable(h_in), pg_out = host_is_pageable(h_out);
-    if ((pg_in || pg_out) && !env_int("BPLTV_PIPE_PAGEABLE", 0)) return false;
     pio->stage_in = pg_in && env_int("BPLTV_HOST_STAGING", 1) && d.hstage.init();
     pio->stage_out = pg_out && env_int("BPLTV_HOST_STAGING", 1) && d.hstage.init();
     if ((pg_in && !pio->stage_in) || (pg_out && !pio->stage_out)) return false;
