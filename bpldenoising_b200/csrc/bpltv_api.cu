@@ -1090,6 +1090,7 @@ static int sumregs_eval_on_device(bpltv_ctx *ctx, Dev &d, const double *lam, int
             np.gamma = gp.gamma; np.tol = 0.0; np.maxit = eo.solver_maxit;
             rc = nd_run_gradient3_reg(d.nd3, np, d.sm_count, d.smem_optin, st, d_costgrad + 1, &d.launches);
             if (rc == 0) d.grad3_used_nd = true;
+            else if (rc == BPLTV_ERR_ALLOC) rc = -1;      // the band solver needs less memory per image
             else if (rc != -1) return fail(rc, "sumregs gradient: %s", nd_work_error(d.nd3));
         }
         // sumregs_gradient (non-regularised, scalar :264-327 and patch :330-407): the same solver in multiplier space
@@ -1103,6 +1104,7 @@ static int sumregs_eval_on_device(bpltv_ctx *ctx, Dev &d, const double *lam, int
             np.act_tol = gp.act_tol; np.eps_act = gp.eps_act; np.tol = 0.0; np.maxit = eo.solver_maxit;
             rc = nd_run_gradient3(d.nd3, np, d.sm_count, d.smem_optin, st, d_costgrad + 1, &d.launches);
             if (rc == 0) d.grad3_used_nd = true;
+            else if (rc == BPLTV_ERR_ALLOC) rc = -1;      // the band Cholesky needs less memory per image
             else if (rc != -1) return fail(rc, "sumregs gradient: %s", nd_work_error(d.nd3));
         }
         if (rc == -1) rc = run_gradient3<Real>(d.grad3, gp, d.sm_count, d.smem_optin, st, d_costgrad + 1, &d.launches);
