@@ -461,11 +461,20 @@ static __device__ __forceinline__ void nd_factor_body(const NdDev &nd, int t0, i
             const int tj = wt - ti * (ti + 1) / 2;
             const int i0 = 32 * ti + 4 * li, j0 = 32 * tj + 8 * lj;
             if (j0 > i0 + 3 || j0 >= ntr || i0 >= ntr) continue;      // nothing of this thread's patch in the lower triangle
+            // The tile's old entries are the initial values of the accumulators: their loads are issued before the
+            // rank-16 loop and fly under it (an update after the loop — load, subtract, store per element, or in batches
+            // — exposes L2 round trips the block step's chain has to wait for: ncu, 20 % of the kernel's stall samples).
             double acc[4][8];
 #pragma unroll
-            for (int x = 0; x < 4; ++x)
+            for (int y = 0; y < 8; ++y) {
+                const int cc = j0 + y;
+                const double *col = nd_col(L, U, nP, nF, nR, k1 + (cc < ntr ? cc : 0)) + k1;
 #pragma unroll
-                for (int y = 0; y < 8; ++y) acc[x][y] = 0.0;
+                for (int x = 0; x < 4; ++x) {
+                    const int r = i0 + x;
+                    acc[x][y] = (cc < ntr && r >= cc && r < ntr) ? col[r] : 0.0;
+                }
+            }
 #pragma unroll 4
             for (int c = 0; c < NB; ++c) {
                 const double *pc = P + c * PR;
@@ -475,37 +484,22 @@ static __device__ __forceinline__ void nd_factor_body(const NdDev &nd, int t0, i
                 const double2 b1 = *reinterpret_cast<const double2 *>(pc + j0 + 2);
                 const double2 b2 = *reinterpret_cast<const double2 *>(pc + j0 + 4);
                 const double2 b3 = *reinterpret_cast<const double2 *>(pc + j0 + 6);
-                const double pi[4] = {a0.x, a0.y, a1.x, a1.y};
+                const double pi[4] = {-a0.x, -a0.y, -a1.x, -a1.y};
                 const double pj[8] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, b3.x, b3.y};
 #pragma unroll
                 for (int x = 0; x < 4; ++x)
 #pragma unroll
                     for (int y = 0; y < 8; ++y) acc[x][y] = fma(pi[x], pj[y], acc[x][y]);
             }
-            // read-modify-write of the tile, two columns at a time: the 8 loads of a pair are issued together (the compiler
-            // cannot move a load above the store before it — possible aliasing — so an element-by-element update would
-            // expose one L2 round trip per element: 20 % of the kernel's stall samples, ncu)
 #pragma unroll
-            for (int y = 0; y < 8; y += 2) {
-                double *col[2];
-                double v[2][4];
-                bool ok[2][4];
+            for (int y = 0; y < 8; ++y) {
+                const int cc = j0 + y;
+                double *col = nd_col(L, U, nP, nF, nR, k1 + (cc < ntr ? cc : 0)) + k1;
 #pragma unroll
-                for (int yy = 0; yy < 2; ++yy) {
-                    const int cc = j0 + y + yy;
-                    col[yy] = nd_col(L, U, nP, nF, nR, k1 + (cc < ntr ? cc : 0)) + k1;
-#pragma unroll
-                    for (int x = 0; x < 4; ++x) {
-                        const int r = i0 + x;
-                        ok[yy][x] = cc < ntr && r >= cc && r < ntr;
-                        v[yy][x] = ok[yy][x] ? col[yy][r] : 0.0;
-                    }
+                for (int x = 0; x < 4; ++x) {
+                    const int r = i0 + x;
+                    if (cc < ntr && r >= cc && r < ntr) col[r] = acc[x][y];
                 }
-#pragma unroll
-                for (int yy = 0; yy < 2; ++yy)
-#pragma unroll
-                    for (int x = 0; x < 4; ++x)
-                        if (ok[yy][x]) col[yy][i0 + x] = v[yy][x] - acc[x][y + yy];
             }
         }
         csync();
@@ -514,7 +508,7 @@ static __device__ __forceinline__ void nd_factor_body(const NdDev &nd, int t0, i
     if (bad) atomicAdd(nd.info + 4 * slot + 1, 1);
 }
 
-__global__ void nd_factor_kernel(NdDev nd, int t0, int par, double guard, int nFmax) { nd_factor_body<false>(nd, t0, par, guard, nFmax); }
+__global__ void __launch_bounds__(512) nd_factor_kernel(NdDev nd, int t0, int par, double guard, int nFmax) { nd_factor_body<false>(nd, t0, par, guard, nFmax); }
 // grid (fronts of the level × cluster size, slots), launched with the cluster dimension
 __global__ void __launch_bounds__(512) nd_factor_cluster_kernel(NdDev nd, int t0, int par, double guard, int nFmax) { nd_factor_body<true>(nd, t0, par, guard, nFmax); }
 
