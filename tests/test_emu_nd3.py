@@ -91,7 +91,7 @@ def test_stencil_form_is_the_literal_matrix(lib):
     assert np.abs(A - A.T).max() <= 1e-13 * np.abs(A).max()         # symmetric: why the Cholesky applies
 
 
-@pytest.mark.parametrize("n,leaf", [(8, 4), (13, 4), (24, 4), (24, 6), (37, 5)])
+@pytest.mark.parametrize("n,leaf", [(8, 4), (13, 4), (24, 6)])
 def test_scalar_reg_gradient(lib, n, leaf):
     t, u = _case(n, 40 + n)
     x = np.array([0.05, 0.04, 0.06])
@@ -102,7 +102,7 @@ def test_scalar_reg_gradient(lib, n, leaf):
 
 
 def test_small_front_kernels_equal_the_generic_ones(lib):
-    t, u = _case(30, 9)
+    t, u = _case(20, 9)
     x = np.array([0.1, 0.02, 0.07])
     g0, s0, p0, _ = _run(lib, u, t, x, small=0)
     g1, s1, p1, _ = _run(lib, u, t, x, small=1)
@@ -136,7 +136,7 @@ def _run_mult(lib, u, t, x=None, maps=None, grid=(1, 1), refine=1, leaf=4, csize
     return out.reshape(3, grid[1], grid[0]).transpose(2, 1, 0), stats, p      # [operator][patch] → (pi, pj, operator)
 
 
-@pytest.mark.parametrize("n,leaf", [(8, 4), (13, 4), (20, 4), (20, 5)])
+@pytest.mark.parametrize("n,leaf", [(8, 4), (13, 4), (20, 5)])
 def test_scalar_nonreg_gradient_multiplier_form(lib, n, leaf):
     """≤ 1e-10 against the compliance-form CPU checker (the same formulation), ≤ 1e-6 against the refined literal
     saddle-point system (:264-327) — the bars of tests/test_gpu_sumregs.py"""
@@ -165,7 +165,7 @@ def test_patch_nonreg_gradient_multiplier_form(lib):
 def test_cluster_shared_front_factorisation_is_invisible(lib):
     """nd_factor_cluster_kernel: the front dealt over the CTAs of a cluster (assembly, write-back and trailing tiles shared,
     diagonal block and panel redundant) gives the bits of the single-CTA kernel, for 2 and 3 CTAs per front"""
-    t, u = _case(14, 31)
+    t, u = _case(12, 31)
     x = np.array([0.05, 0.04, 0.06])
     g1, s1, p1 = _run_mult(lib, u, t, x=x)
     for cs in (2, 3):
