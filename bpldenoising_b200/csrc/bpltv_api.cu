@@ -516,7 +516,7 @@ static int choose_pdps_kernel(Dev &d, int M, int N, int O, const bpltv_pdps_opts
 // BPLTV_PIPE_CHUNKS, BPLTV_PIPE_PASSES tune it (tests).
 template <typename Real>
 static bool pipe_eligible(Dev &d, int M, int N, int O, const bpltv_pdps_opts &o, int kernel, int tdepth, const double *h_in,
-                          double *h_out, PipeIO *pio)
+                          double *h_out, bool allow_pageable, PipeIO *pio)
 {
     if (sizeof(Real) != 8 || !h_in || !h_out || !env_int("BPLTV_PIPE_IO", 1)) return false;
     if (kernel != BPLTV_KERNEL_TBLOCK || tdepth < 2 || o.maxiter % tdepth != 0) return false;
@@ -526,7 +526,9 @@ static bool pipe_eligible(Dev &d, int M, int N, int O, const bpltv_pdps_opts &o,
     // (e2e Gpixel-iter/s): pageable K×q = 3×6 175.5 (= serial), 3×14 181.7, 3×18 179.1, 4×12 180.0, 6×8 172.9; pinned 3×6
     // 190.1, 3×14 186.5.  BPLTV_PIPE_PAGEABLE=0 keeps pageable buffers on the serial path.
     const bool pg_in = host_is_pageable(h_in), pg_out = host_is_pageable(h_out);
-    if ((pg_in || pg_out) && !env_int("BPLTV_PIPE_PAGEABLE", 1)) return false;
+    // (a staged copy occupies the calling thread: in a context of several devices it would hold back the other devices'
+    // work, so pageable buffers are pipelined in single-device contexts only)
+    if ((pg_in || pg_out) && (!allow_pageable || !env_int("BPLTV_PIPE_PAGEABLE", 1))) return false;
     const int K = std::max(2, std::min(8, env_int("BPLTV_PIPE_CHUNKS", 3)));
     const int q = std::max(1, env_int("BPLTV_PIPE_PASSES", (pg_in || pg_out) ? 14 : 6));
     if (o.maxiter / tdepth < 4 * q || O < 2 * K) return false;
@@ -861,7 +863,7 @@ static int denoise_impl(bpltv_ctx *ctx, const double *noisy, int M, int N, int O
         if (noisy && oc > 0) {
             int k_ = 0, t_ = 1;
             RC_TRY(choose_pdps_kernel<Real>(d, M, N, oc, o, &k_, &t_));
-            piped = pipe_eligible<Real>(d, M, N, oc, o, k_, t_, noisy + plane * ob, u_out + plane * ob, &pio);
+            piped = pipe_eligible<Real>(d, M, N, oc, o, k_, t_, noisy + plane * ob, u_out + plane * ob, ndev == 1, &pio);
         }
         piped_dev[di] = piped;
         if (noisy && piped) {
