@@ -138,15 +138,16 @@ static inline int nd_build_plan(NdPlan &pl, int n, int W, cudaStream_t st, std::
 static inline int nd_fail(NdWork &w, int code, const std::string &msg) { w.err = msg; return code; }
 
 // Opt-in shared memory of the front kernels.  -1: a front does not fit (the caller falls back to a band solver).
-static int nd_kernel_attributes(NdWork &w, size_t fsmem, size_t ssmem, size_t fsmem_small, size_t ssmem_small, size_t smem_optin)
+static int nd_kernel_attributes(NdWork &w, size_t fsmem, size_t ssmem, size_t fsmem_small, size_t ssmem_small, size_t smem_optin,
+                                size_t fsmem8 = 0)      // fsmem8: of the levels that take 8-column block steps
 {
-    if (fsmem > smem_optin || ssmem > smem_optin || fsmem_small > smem_optin || ssmem_small > smem_optin)
+    if (fsmem > smem_optin || ssmem > smem_optin || fsmem_small > smem_optin || ssmem_small > smem_optin || fsmem8 > smem_optin)
         return -1;      // the caller falls back to the band solver
     {
         // the opt-in shared-memory size is an attribute of the KERNEL on the current device, shared by every workspace
         // that launches it (the TV solver and the sum-of-regularisers one): raised to the largest any of them asked for
         static std::mutex mu;
-        static int have[64][5] = {};
+        static int have[64][6] = {};
         int dev = 0;
         cudaGetDevice(&dev);
         dev = std::max(0, std::min(63, dev));
@@ -160,6 +161,12 @@ static int nd_kernel_attributes(NdWork &w, size_t fsmem, size_t ssmem, size_t fs
             e = cudaFuncSetAttribute(nd_factor_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(nd_factor_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
             if (e == cudaSuccess) have[dev][4] = (int)fsmem;
+        }
+        if (e == cudaSuccess && fsmem8 > 0 && have[dev][5] < (int)fsmem8) {
+            e = cudaFuncSetAttribute(nd_factor8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem8);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(nd_factor8_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem8);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(nd_factor8_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e == cudaSuccess) have[dev][5] = (int)fsmem8;
         }
         if (e == cudaSuccess && have[dev][1] < (int)ssmem) {
             e = cudaFuncSetAttribute(nd_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem);
@@ -231,14 +238,14 @@ static int nd_cluster_size(const NdLevelPlan &lp, int cnt, int sm_count)
 }
 
 // how many clusters of C CTAs (threads, dynamic shared memory) the device runs at once: asked of the driver once per shape
-static int nd_active_clusters(int C, int threads, size_t smem)
+static int nd_active_clusters(int C, int threads, size_t smem, int nb = ND_NB)
 {
     static std::mutex mu;
     static std::unordered_map<unsigned long long, int> memo;
     int dev = 0;
     cudaGetDevice(&dev);
     const unsigned long long key = ((unsigned long long)dev << 48) ^ ((unsigned long long)C << 40) ^ ((unsigned long long)threads << 24) ^
-                                   (unsigned long long)(smem >> 8);
+                                   ((unsigned long long)(nb == ND_NB ? 0 : 1) << 63) ^ (unsigned long long)(smem >> 8);
     std::lock_guard<std::mutex> lock(mu);
     auto it = memo.find(key);
     if (it != memo.end()) return it->second;
@@ -249,7 +256,9 @@ static int nd_active_clusters(int C, int threads, size_t smem)
     attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     int nclusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&nclusters, nd_factor_cluster_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); nclusters = 0; }
+    const cudaError_t qe = nb == ND_NB ? cudaOccupancyMaxActiveClusters(&nclusters, nd_factor_cluster_kernel, &cfg)
+                                       : cudaOccupancyMaxActiveClusters(&nclusters, nd_factor8_cluster_kernel, &cfg);
+    if (qe != cudaSuccess) { cudaGetLastError(); nclusters = 0; }
     memo[key] = nclusters;
     return nclusters;
 }
@@ -257,9 +266,9 @@ static int nd_active_clusters(int C, int threads, size_t smem)
 // launch of the cluster-shared front factorisation; the cluster shrinks until the device runs all fronts of the level at once
 static cudaError_t nd_launch_factor_cluster(const NdDev &nd, const NdLevelPlan &lp, int s, int cnt, int C, double guard, cudaStream_t st)
 {
-    const size_t smem = nd_factor_smem(lp.nFw, lp.nRc);
+    const size_t smem = nd_factor_smem(lp.nFw, lp.nRc, lp.nb);
     const long long fronts = (long long)lp.nfr * cnt;
-    while (C > 1 && nd_active_clusters(C, lp.threads_f, smem) < fronts) --C;
+    while (C > 1 && nd_active_clusters(C, lp.threads_f, smem, lp.nb) < fronts) --C;
     if (C > 1) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(lp.nfr * C), (unsigned)cnt);
@@ -270,9 +279,11 @@ static cudaError_t nd_launch_factor_cluster(const NdDev &nd, const NdLevelPlan &
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
+        if (lp.nb != ND_NB) return cudaLaunchKernelEx(&cfg, nd_factor8_cluster_kernel, nd, lp.t0, s & 1, guard, lp.nFw);
         return cudaLaunchKernelEx(&cfg, nd_factor_cluster_kernel, nd, lp.t0, s & 1, guard, lp.nFw);
     }
-    nd_factor_kernel<<<dim3(lp.nfr, cnt), lp.threads_f, smem, st>>>(nd, lp.t0, s & 1, guard, lp.nFw);
+    if (lp.nb != ND_NB) nd_factor8_kernel<<<dim3(lp.nfr, cnt), lp.threads_f, smem, st>>>(nd, lp.t0, s & 1, guard, lp.nFw);
+    else nd_factor_kernel<<<dim3(lp.nfr, cnt), lp.threads_f, smem, st>>>(nd, lp.t0, s & 1, guard, lp.nFw);
     return cudaGetLastError();
 }
 
@@ -304,6 +315,8 @@ static void nd_launch_factor(const NdDev &nd, std::vector<NdLevelPlan> &plan, co
         else {
             const int C = nd_cluster_size(lp, cnt, sm_count);
             if (C > 1) nd_launch_factor_cluster(nd, lp, s, cnt, C, guard, st);
+            else if (lp.nb != ND_NB)
+                nd_factor8_kernel<<<dim3(lp.nfr, cnt), nd_factor_cta_threads(lp, cnt, sm_count), nd_factor_smem(lp.nFw, lp.nRc, lp.nb), st>>>(nd, lp.t0, s & 1, guard, lp.nFw);
             else nd_factor_kernel<<<dim3(lp.nfr, cnt), nd_factor_cta_threads(lp, cnt, sm_count), nd_factor_smem(lp.nFw, lp.nRc), st>>>(nd, lp.t0, s & 1, guard, lp.nFw);
         }
     }
@@ -749,10 +762,14 @@ static int run_gradient3_nd_mult(NdWork &w, const Nd3mProblem &gp, int sm_count,
             w.slots_cached = slots;
             continue;
         }
-        size_t fsmem = 0, ssmem = 0;
+        size_t fsmem = 0, fsmem8 = 0, ssmem = 0;
+        // test hook: BPLTV_ND3_SMEM_KB lowers the shared memory the 16-column panel may take (sends fronts to the 8-column kernels)
+        const char *skb = bpltv::env_get("BPLTV_ND3_SMEM_KB");
+        const size_t smem_plan = skb && *skb ? std::min<size_t>(smem_optin, (size_t)atoi(skb) << 10) : smem_optin;
         for (int s = 0; s < nsteps; ++s) {
-            plan[s] = nd_level_plan_sized(sym, s, h_lvl[2 * s], s > 0 ? h_lvl[2 * (s - 1) + 1] : 0, cta_warps_f, 512);
-            fsmem = std::max(fsmem, plan[s].smem_f); ssmem = std::max(ssmem, plan[s].smem_s);
+            plan[s] = nd_level_plan_sized(sym, s, h_lvl[2 * s], s > 0 ? h_lvl[2 * (s - 1) + 1] : 0, smem_plan, cta_warps_f, 512);
+            if (plan[s].nb == ND_NB) fsmem = std::max(fsmem, plan[s].smem_f); else fsmem8 = std::max(fsmem8, plan[s].smem_f);
+            ssmem = std::max(ssmem, plan[s].smem_s);
         }
         {   // test hook: BPLTV_ND3_MAXF caps the front size this path takes (exercises the fall-back below)
             const char *mf = bpltv::env_get("BPLTV_ND3_MAXF");
@@ -760,7 +777,7 @@ static int run_gradient3_nd_mult(NdWork &w, const Nd3mProblem &gp, int sm_count,
                 for (int s = 0; s < nsteps; ++s)
                     if (h_lvl[2 * s] > atoi(mf)) return -1;
         }
-        if ((rc = nd_kernel_attributes(w, fsmem, ssmem, 0, 0, smem_optin))) return rc;      // -1: the band Cholesky
+        if ((rc = nd_kernel_attributes(w, fsmem, ssmem, 0, 0, smem_optin, fsmem8))) return rc;      // -1: the band Cholesky
         if ((rc = need(w.L, Ls * 8 * cnt, "factors"))) return rc;
         if ((rc = need(w.U0, Us * 8 * cnt, "update matrices"))) return rc;
         if ((rc = need(w.U1, Us * 8 * cnt, "update matrices"))) return rc;

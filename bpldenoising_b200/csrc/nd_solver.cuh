@@ -187,10 +187,10 @@ __global__ void __launch_bounds__(256) nd_scan_kernel(NdDev nd)
 // No explicit inverse of L11 anywhere: with pivots from 1 down to √guard the block has a condition number of 1e6 and
 // multiplying by its inverse loses what substitution keeps (measured: Schur complements of barely sloped regions
 // turned indefinite).
+template <int NB>
 static __device__ void nd_diag_block(const double *S0, double *S, double *dinv, const double *dfl, int nb, double guard, int lane,
                                      int &guarded, int &bad)
 {
-    constexpr int NB = ND_NB;
     double row[NB];
     const int lr = lane < NB ? lane : NB - 1;
 #pragma unroll
@@ -265,9 +265,9 @@ static __device__ __forceinline__ double *nd_col(double *L, double *U, int nP, i
 static __host__ __device__ __forceinline__ int nd_panel_pitch(int nFmax) { return (nFmax + 31) & ~31; }
 // dynamic shared memory of nd_factor_kernel (bytes): S0, S, reciprocal diagonal, column floors, panel P (NB × pitch),
 // the child map (ints)
-static inline size_t nd_factor_smem(int nFmax, int nRchild_max)
+static inline size_t nd_factor_smem(int nFmax, int nRchild_max, int nb = ND_NB)
 {
-    return (size_t)(2 * ND_NB * ND_NB + 2 * ND_NB + ND_NB * nd_panel_pitch(nFmax)) * sizeof(double) + (((size_t)nRchild_max * sizeof(int) + 15) & ~(size_t)15);
+    return (size_t)(2 * nb * nb + 2 * nb + nb * nd_panel_pitch(nFmax)) * sizeof(double) + (((size_t)nRchild_max * sizeof(int) + 15) & ~(size_t)15);
 }
 
 // ---------------------------------------------------------------------------
@@ -278,11 +278,13 @@ static inline size_t nd_factor_smem(int nFmax, int nRchild_max)
 // the panel are formed redundantly by every CTA in its own shared memory (same operations in the same order: the same
 // pivots and the same bits), the tiles of the trailing update are dealt over all warps of the cluster, and one cluster
 // barrier per phase / block step publishes them through global memory.  Results do not depend on the cluster size.
-template <bool CL>
+// NB: columns per block step.  16 everywhere, except for fronts whose 16-column panel exceeds shared memory (the
+// sum-of-regularisers multiplier form of a large or mostly flat image: > ≈ 1700 unknowns), which take 8 — twice the steps
+// for half the panel.  (The factor does not depend on NB beyond the order of the updates; the solves use blocks of 16.)
+template <bool CL, int NB>
 static __device__ __forceinline__ void nd_factor_body(const NdDev &nd, int t0, int par, double guard, int nFmax)
 {
     ND_DYN_SMEM(sm);
-    constexpr int NB = ND_NB;
     double *S0 = sm, *S = sm + NB * NB, *dinv = sm + 2 * NB * NB, *dfl = dinv + NB, *P = dfl + NB;
     __shared__ int s_cbad;
     __shared__ unsigned long long s_amax2;
@@ -391,7 +393,7 @@ static __device__ __forceinline__ void nd_factor_body(const NdDev &nd, int t0, i
         int blk_guarded = 0;
         for (int attempt = 0;; ++attempt) {
             __syncthreads();
-            if (warp == 0) nd_diag_block(S0, S, dinv, dfl, nb, guard, lane, blk_guarded, bad);
+            if (warp == 0) nd_diag_block<NB>(S0, S, dinv, dfl, nb, guard, lane, blk_guarded, bad);
             __syncthreads();
             // panel: L21 = A21 · L11⁻ᵀ by forward substitution, one thread per row, into P; rows up to the next
             // multiple of 32 are zero
@@ -508,9 +510,12 @@ static __device__ __forceinline__ void nd_factor_body(const NdDev &nd, int t0, i
     if (bad) atomicAdd(nd.info + 4 * slot + 1, 1);
 }
 
-__global__ void __launch_bounds__(512) nd_factor_kernel(NdDev nd, int t0, int par, double guard, int nFmax) { nd_factor_body<false>(nd, t0, par, guard, nFmax); }
+__global__ void __launch_bounds__(512) nd_factor_kernel(NdDev nd, int t0, int par, double guard, int nFmax) { nd_factor_body<false, ND_NB>(nd, t0, par, guard, nFmax); }
 // grid (fronts of the level × cluster size, slots), launched with the cluster dimension
-__global__ void __launch_bounds__(512) nd_factor_cluster_kernel(NdDev nd, int t0, int par, double guard, int nFmax) { nd_factor_body<true>(nd, t0, par, guard, nFmax); }
+__global__ void __launch_bounds__(512) nd_factor_cluster_kernel(NdDev nd, int t0, int par, double guard, int nFmax) { nd_factor_body<true, ND_NB>(nd, t0, par, guard, nFmax); }
+// the same with 8-column block steps (fronts whose 16-column panel does not fit in shared memory)
+__global__ void __launch_bounds__(512) nd_factor8_kernel(NdDev nd, int t0, int par, double guard, int nFmax) { nd_factor_body<false, 8>(nd, t0, par, guard, nFmax); }
+__global__ void __launch_bounds__(512) nd_factor8_cluster_kernel(NdDev nd, int t0, int par, double guard, int nFmax) { nd_factor_body<true, 8>(nd, t0, par, guard, nFmax); }
 
 // dynamic shared memory of the solve kernels (bytes): the front's vector, the ring sums of the backward sweep, two
 // diagonal blocks (the next one is fetched while the current one is used), NB scratch
@@ -1065,6 +1070,7 @@ struct NdLevelPlan {
     int t0, nfr;                // fronts of the level
     int nFw;                    // largest possible front (mb unknowns on every pixel)
     int nRc;                    // largest possible ring of a child (unknowns): the extend-add map of the generic kernel
+    int nb;                     // columns per block step of the generic factorisation (16; 8 for fronts beyond its panel)
     int threads_f, threads_s;   // generic kernels: CTA sizes of the factorisation / of the solves
     size_t smem_f, smem_s;      // dynamic shared memory of the factorisation / of the solves
     int arena_f, arena_s;       // small kernels: arena (doubles)
@@ -1076,6 +1082,7 @@ static inline NdLevelPlan nd_level_plan(const NdSymbolic &sym, int s, int mb, do
     lp.t0 = sym.step_start[s]; lp.nfr = sym.step_start[s + 1] - lp.t0;
     lp.nFw = mb * sym.step_max_front_pix[s];
     lp.nRc = s > 0 ? mb * sym.step_max_ring_pix[s - 1] : 0;
+    lp.nb = ND_NB;
     const int nPw = mb * sym.step_max_piv_pix[s];
     const int nFt = std::min(lp.nFw, (int)(typ_per_pixel * sym.step_max_front_pix[s]) + 1);
     lp.small = lp.nFw <= ND_SMALL_MAXF && nFt <= ND_SMALL_TYPF;
@@ -1097,8 +1104,8 @@ static inline NdLevelPlan nd_level_plan(const NdSymbolic &sym, int s, int mb, do
 
 // The same for a level whose sizes were MEASURED on the device (nd_level_sizes_kernel): the forms with many unknowns per
 // pixel (sum-of-regularisers multipliers: 3-6) cannot afford worst-case shared memory.  Generic kernels only.
-static inline NdLevelPlan nd_level_plan_sized(const NdSymbolic &sym, int s, int nF, int nRchild, int max_warps_f = 16,
-                                             int max_threads_s = 512)
+static inline NdLevelPlan nd_level_plan_sized(const NdSymbolic &sym, int s, int nF, int nRchild, size_t smem_optin,
+                                             int max_warps_f = 16, int max_threads_s = 512)
 {
     NdLevelPlan lp;
     lp.t0 = sym.step_start[s]; lp.nfr = sym.step_start[s + 1] - lp.t0;
@@ -1109,7 +1116,8 @@ static inline NdLevelPlan nd_level_plan_sized(const NdSymbolic &sym, int s, int 
     lp.threads_f = 32 * std::min(max_warps_f, std::max(2, ntiles));
     lp.threads_s = std::min(max_threads_s, std::max(64, (lp.nFw + 31) & ~31));
     lp.arena_f = lp.arena_s = 0;
-    lp.smem_f = nd_factor_smem(lp.nFw, lp.nRc);
+    lp.nb = nd_factor_smem(lp.nFw, lp.nRc, ND_NB) <= smem_optin ? ND_NB : 8;
+    lp.smem_f = nd_factor_smem(lp.nFw, lp.nRc, lp.nb);
     lp.smem_s = nd_solve_smem(lp.nFw);
     return lp;
 }

@@ -108,10 +108,10 @@ extern "C" int emu_nd3_gradient_reg(int n, const double *u, const double *ubar, 
 }
 
 // sumregs_gradient (non-regularised) in multiplier space, the launch order of run_gradient3_nd_mult.  alpha_maps: 3·n·n or NULL.
-// stats_out (6 doubles or NULL): relres, guarded pivots, breakdown flag, modes, largest front (unknowns), L doubles
+// stats_out (6 doubles or NULL): relres, guarded pivots, breakdown flag, modes, largest front (unknowns), levels on 8-column steps
 extern "C" int emu_nd3_gradient_mult(int n, const double *u, const double *ubar, const double *alpha3, const double *alpha_maps,
                                      int lm, int ln, double act_tol, double eps_act, int refine, int leaf, int csize,
-                                     double *out, double *stats_out, double *p_out)
+                                     long long smem_limit, double *out, double *stats_out, double *p_out)
 {
     const int N = n * n, mb = ND3M_MB, ng = lm * ln;
     NdSymbolic sym;
@@ -149,16 +149,25 @@ extern "C" int emu_nd3_gradient_mult(int n, const double *u, const double *ubar,
     nd.L = al16(Lp); nd.U[0] = al16(U0); nd.U[1] = al16(U1); nd.UV[0] = al16(UV0); nd.UV[1] = al16(UV1);
     nd.L_stride = nd.U_stride = nd.UV_stride = 0;
     std::vector<NdLevelPlan> plan(nsteps);
-    int maxF = 0;
+    int maxF = 0, levels8 = 0;
     for (int s = 0; s < nsteps; ++s) {
-        plan[s] = nd_level_plan_sized(sym, s, lvl[2 * s], s > 0 ? lvl[2 * (s - 1) + 1] : 0, 4, 128);
+        // smem_limit: bytes of shared memory the plan may use for the 16-column panel (a small value sends fronts to the
+        // 8-column kernels)
+        plan[s] = nd_level_plan_sized(sym, s, lvl[2 * s], s > 0 ? lvl[2 * (s - 1) + 1] : 0, (size_t)smem_limit, 4, 128);
         maxF = std::max(maxF, lvl[2 * s]);
     }
     for (int s = 0; s < nsteps; ++s) {
         const NdLevelPlan &lp = plan[s];
-        if (csize > 1 && lp.nFw >= 64)
-            emu::launch(dim3(lp.nfr * csize, 1), lp.threads_f, [&] { nd_factor_cluster_kernel(nd, lp.t0, s & 1, 1e-13, lp.nFw); },
-                        lp.smem_f / 8 + 2, csize);
+        if (lp.nb != ND_NB) ++levels8;
+        if (csize > 1 && lp.nFw >= 64) {
+            if (lp.nb != ND_NB)
+                emu::launch(dim3(lp.nfr * csize, 1), lp.threads_f, [&] { nd_factor8_cluster_kernel(nd, lp.t0, s & 1, 1e-13, lp.nFw); },
+                            lp.smem_f / 8 + 2, csize);
+            else
+                emu::launch(dim3(lp.nfr * csize, 1), lp.threads_f, [&] { nd_factor_cluster_kernel(nd, lp.t0, s & 1, 1e-13, lp.nFw); },
+                            lp.smem_f / 8 + 2, csize);
+        } else if (lp.nb != ND_NB)
+            emu::launch(dim3(lp.nfr, 1), lp.threads_f, [&] { nd_factor8_kernel(nd, lp.t0, s & 1, 1e-13, lp.nFw); }, lp.smem_f / 8 + 2);
         else
             emu::launch(dim3(lp.nfr, 1), lp.threads_f, [&] { nd_factor_kernel(nd, lp.t0, s & 1, 1e-13, lp.nFw); }, lp.smem_f / 8 + 2);
     }
@@ -188,7 +197,7 @@ extern "C" int emu_nd3_gradient_mult(int n, const double *u, const double *ubar,
     if (p_out) std::memcpy(p_out, pix.data() + (size_t)16 * N, N * sizeof(double));
     if (stats_out) {
         stats_out[0] = relres; stats_out[1] = info[0]; stats_out[2] = info[1]; stats_out[3] = off3[3 * N]; stats_out[4] = maxF;
-        stats_out[5] = (double)totals[0];
+        stats_out[5] = levels8;
     }
     return 0;
 }

@@ -122,7 +122,7 @@ def test_one_operator_switched_off(lib):
 # ---------------------------------------------------------------------------
 # sumregs_gradient (non-regularised) in multiplier space: 3-6 unknowns per pixel on the same tree
 # ---------------------------------------------------------------------------
-def _run_mult(lib, u, t, x=None, maps=None, grid=(1, 1), refine=1, leaf=4, csize=1):
+def _run_mult(lib, u, t, x=None, maps=None, grid=(1, 1), refine=1, leaf=4, csize=1, smem_limit=1 << 30):
     n = u.shape[0]
     ng = grid[0] * grid[1]
     out, stats, p = np.zeros(3 * ng), np.zeros(6), np.zeros(n * n)
@@ -130,7 +130,7 @@ def _run_mult(lib, u, t, x=None, maps=None, grid=(1, 1), refine=1, leaf=4, csize
     a3 = None if x is None else np.asarray(x, dtype=np.float64)
     lib.emu_nd3_gradient_mult.restype = C.c_int
     rc = lib.emu_nd3_gradient_mult(n, _ptr(u.flatten(order="F")), _ptr(t.flatten(order="F")), _ptr(a3), _ptr(am),
-                                   grid[0], grid[1], C.c_double(1e-12), C.c_double(sr.EPS), refine, leaf, csize, _ptr(out),
+                                   grid[0], grid[1], C.c_double(1e-12), C.c_double(sr.EPS), refine, leaf, csize, C.c_longlong(smem_limit), _ptr(out),
                                    _ptr(stats), _ptr(p))
     assert rc == 0
     return out.reshape(3, grid[1], grid[0]).transpose(2, 1, 0), stats, p      # [operator][patch] → (pi, pj, operator)
@@ -171,3 +171,18 @@ def test_cluster_shared_front_factorisation_is_invisible(lib):
     for cs in (2, 3):
         g, s, p = _run_mult(lib, u, t, x=x, csize=cs)
         assert np.array_equal(g, g1) and np.array_equal(p, p1) and s[0] == s1[0] and s[1] == s1[1], cs
+
+
+def test_eight_column_block_steps_for_fronts_beyond_the_panel(lib):
+    """fronts whose 16-column panel would not fit in shared memory take the 8-column kernels (nd_factor8_*): here the limit
+    is set so low that the upper levels do — the gradient agrees with the 16-column factorisation to rounding, alone and
+    shared by a cluster"""
+    t, u = _case(13, 17)
+    x = np.array([0.05, 0.04, 0.06])
+    g16, s16, p16 = _run_mult(lib, u, t, x=x)
+    assert s16[5] == 0
+    g8, s8, p8 = _run_mult(lib, u, t, x=x, smem_limit=20000)
+    assert s8[5] > 0 and s8[2] == 0
+    assert np.all(np.abs(g8 - g16) <= 1e-11 * np.abs(g16).max()) and np.linalg.norm(p8 - p16) <= 1e-11 * np.linalg.norm(p16)
+    g8c, s8c, p8c = _run_mult(lib, u, t, x=x, smem_limit=20000, csize=2)
+    assert np.array_equal(g8c, g8) and np.array_equal(p8c, p8)

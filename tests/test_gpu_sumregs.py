@@ -356,6 +356,36 @@ def test_sumregs_gradient_fallback_and_wave_retry(bp, sr, datasets):
     assert np.all(np.abs(small - ref) <= 1e-12 * np.abs(ref).max()), (small, ref)
 
 
+def test_sumregs_gradient_beyond_the_sixteen_column_panel(bp, sr, datasets):
+    """Fronts whose 16-column panel does not fit in shared memory take 8-column block steps (nd_factor8_*): forced on a 48²
+    crop (BPLTV_ND3_SMEM_KB) — the default factorisation's gradient to 1e-10 — and met for real on a 256×256 image, which the
+    banded solver refuses (n ≤ 136): finite, backward error at rounding level, the nested-dissection launch count."""
+    import os
+    x = np.array([0.03, 0.02, 0.04])
+    t, f = _crop(datasets, "faces_train_128_10", 48, k=2, off=20)
+    with bp.Context([0], 64) as c:
+        c.set_dataset((t, f))
+        u = np.asfortranarray(c.sumregs_denoise(f, x, bp.sumregs_pdps_opts(maxiter=300)))
+        ref = c.sumregs_gradient(x, u, regularised=False)
+        os.environ["BPLTV_ND3_SMEM_KB"] = "40"
+        bp.reload_env()
+        try:
+            g8 = c.sumregs_gradient(x, u, regularised=False)
+        finally:
+            del os.environ["BPLTV_ND3_SMEM_KB"]
+            bp.reload_env()
+        assert np.all(np.abs(g8 - ref) <= 1e-10 * np.abs(ref).max()), (g8, ref)
+    t, f = bp.synthetic_dataset(256, 256, 1, seed=3)
+    with bp.Context([0], 64) as c:
+        c.set_dataset((t, f))
+        u = np.asfortranarray(c.sumregs_denoise(f, x, bp.sumregs_pdps_opts(maxiter=500)))
+        g = c.sumregs_gradient(x, u, regularised=False)
+        st = c.stats()
+        assert np.all(np.isfinite(g)) and st["solver_max_relres"] <= 1e-9 and st["kernel_launches"] > 40, (g, st)
+        gr = c.sumregs_gradient(x, u, regularised=True)
+        assert np.all(np.isfinite(gr)) and np.all(np.sign(gr) == np.sign(g))
+
+
 def test_cluster_factorisation_is_invisible(bp, ctx, sr, datasets):
     """The banded Cholesky shared by a thread-block cluster (2, 4, 8 CTAs per image) gives bit-identical
     gradients to the single-CTA factorisation, for the TV and the sum-of-regularisers systems."""
