@@ -463,7 +463,7 @@ static int run_gradient_nd(NdWork &w, const NdProblem &gp, int sm_count, size_t 
             *launches += 2;
             Ls = (size_t)t1[0]; Us = (size_t)t1[1]; UVs = (size_t)t1[2];
         } else {
-            ndtv_classify_mult_kernel<Real><<<cnt, 512, 0, st>>>(ws, gv, gp_u, gp_ubar, gp_amap, img0);
+            ndtv_classify_mult_kernel<Real><<<cnt, 1024, 0, st>>>(ws, gv, gp_u, gp_ubar, gp_amap, img0);
             nd_dims_kernel<<<dim3((nf + 7) / 8, cnt), 256, 0, st>>>(nd);
             nd_scan_kernel<<<cnt, 256, 0, st>>>(nd);
             ndtv_stencil_mult_kernel<<<dim3(cnt, chunks), 256, 0, st>>>(ws, (double *)w.ast.p, ast_stride);
@@ -493,11 +493,11 @@ static int run_gradient_nd(NdWork &w, const NdProblem &gp, int sm_count, size_t 
         if (node) {
             double *p = ws.pix + 7 * (size_t)N, *work = ws.pix + 8 * (size_t)N;
             solve(p, ws.pix_stride);
-            ndtv_residual_node_kernel<<<cnt, 512, 0, st>>>(ws, (double *)w.relres.p, img0);
+            ndtv_residual_node_kernel<<<cnt, 1024, 0, st>>>(ws, (double *)w.relres.p, img0);
             for (int it = 0; it < refine; ++it) {
                 solve(work, ws.pix_stride);
                 ndtv_axpy_node_kernel<<<dim3(cnt, chunks), 256, 0, st>>>(ws, 7, 8);
-                ndtv_residual_node_kernel<<<cnt, 512, 0, st>>>(ws, (double *)w.relres.p, img0);
+                ndtv_residual_node_kernel<<<cnt, 1024, 0, st>>>(ws, (double *)w.relres.p, img0);
             }
             ndtv_finish_node_kernel<<<dim3(cnt, pgroups), 512, 0, st>>>(ws, gv, (const double *)w.relres.p, (double *)w.out_img.p, img0);
             *launches += 2 + 2 * refine;
@@ -505,11 +505,11 @@ static int run_gradient_nd(NdWork &w, const NdProblem &gp, int sm_count, size_t 
             double *zeta = ws.vec + 2 * (size_t)N, *work = ws.vec + 4 * (size_t)N;
             ndtv_copy_mult_kernel<<<dim3(cnt, chunks), 256, 0, st>>>(ws, 1, 0);
             solve(zeta, ws.vec_stride);
-            ndtv_residual_mult_kernel<<<cnt, 512, 0, st>>>(ws, (double *)w.relres.p, img0);
+            ndtv_residual_mult_kernel<<<cnt, 1024, 0, st>>>(ws, (double *)w.relres.p, img0);
             for (int it = 0; it < refine; ++it) {
                 solve(work, ws.vec_stride);
                 ndtv_axpy_mult_kernel<<<dim3(cnt, chunks), 256, 0, st>>>(ws, 1, 2);
-                ndtv_residual_mult_kernel<<<cnt, 512, 0, st>>>(ws, (double *)w.relres.p, img0);
+                ndtv_residual_mult_kernel<<<cnt, 1024, 0, st>>>(ws, (double *)w.relres.p, img0);
             }
             ndtv_finish_mult_kernel<<<dim3(cnt, pgroups), 512, 0, st>>>(ws, gv, (const double *)w.relres.p, (double *)w.out_img.p, img0);
             *launches += 3 + 2 * refine;
@@ -620,13 +620,13 @@ static int run_gradient3_nd_reg(NdWork &w, const Nd3Problem &gp, int sm_count, s
         nd_launch_factor(nd, plan, plan_small, sym, 1, cnt, sm_count, 0.0, st, launches);
         double *p = ws.pix + (size_t)LU_PL_P * N, *work = ws.pix + (size_t)LU_PL_WORK * N;
         nd_launch_solve(nd, plan, cnt, p, pix_stride, st, launches);
-        nd3_residual_kernel<Real><<<cnt, 512, 0, st>>>(ws, pr, (double *)w.relres.p, img0);
+        nd3_residual_kernel<Real><<<cnt, 1024, 0, st>>>(ws, pr, (double *)w.relres.p, img0);
         for (int it = 0; it < refine; ++it) {
             nd_launch_solve(nd, plan, cnt, work, pix_stride, st, launches);
             nd3_axpy_kernel<<<dim3(cnt, chunks), 256, 0, st>>>(ws);
-            nd3_residual_kernel<Real><<<cnt, 512, 0, st>>>(ws, pr, (double *)w.relres.p, img0);
+            nd3_residual_kernel<Real><<<cnt, 1024, 0, st>>>(ws, pr, (double *)w.relres.p, img0);
         }
-        nd3_finish_kernel<<<cnt, 512, 0, st>>>(ws, pr, (const int *)w.info.p, tol, (double *)w.out_img.p, (double *)w.relres.p, img0);
+        nd3_finish_kernel<<<cnt, 1024, 0, st>>>(ws, pr, (const int *)w.info.p, tol, (double *)w.out_img.p, (double *)w.relres.p, img0);
         *launches += 2 + 2 * refine;
     }
     nd_reduce_kernel<<<1, 32, 0, st>>>((double *)w.out_img.p, (double *)w.relres.p, gp.O, nops * ng, d_grad_out,
@@ -739,7 +739,7 @@ static int run_gradient3_nd_mult(NdWork &w, const Nd3mProblem &gp, int sm_count,
         nd.info = ws.info;
 
         cudaMemsetAsync(w.lvl.p, 0, 512, st);
-        nd3m_classify_kernel<Real><<<cnt, 512, 0, st>>>(ws, gv, gp_u, gp_ubar, gp_amaps, img0);
+        nd3m_classify_kernel<Real><<<cnt, 1024, 0, st>>>(ws, gv, gp_u, gp_ubar, gp_amaps, img0);
         nd_dims_kernel<<<dim3((nf + 7) / 8, cnt), 256, 0, st>>>(nd);
         nd_scan_kernel<<<cnt, 256, 0, st>>>(nd);
         nd_level_sizes_kernel<<<dim3((nf + 255) / 256, cnt), 256, 0, st>>>(nd, (int *)w.lvl.p);
@@ -791,13 +791,13 @@ static int run_gradient3_nd_mult(NdWork &w, const Nd3mProblem &gp, int sm_count,
         double *zeta = ws.vec + (size_t)mb * N, *work = ws.vec + (size_t)2 * mb * N;
         nd3m_axpy_kernel<<<dim3(cnt, chunks), 256, 0, st>>>(ws, 1, 0, 0);
         nd_launch_solve(nd, plan, cnt, zeta, vec_stride, st, launches);
-        nd3m_residual_kernel<<<cnt, 512, 0, st>>>(ws, (double *)w.relres.p, img0);
+        nd3m_residual_kernel<<<cnt, 1024, 0, st>>>(ws, (double *)w.relres.p, img0);
         for (int it = 0; it < refine; ++it) {
             nd_launch_solve(nd, plan, cnt, work, vec_stride, st, launches);
             nd3m_axpy_kernel<<<dim3(cnt, chunks), 256, 0, st>>>(ws, 1, 2, 1);
-            nd3m_residual_kernel<<<cnt, 512, 0, st>>>(ws, (double *)w.relres.p, img0);
+            nd3m_residual_kernel<<<cnt, 1024, 0, st>>>(ws, (double *)w.relres.p, img0);
         }
-        nd3m_finish_kernel<<<cnt, 512, 0, st>>>(ws, gv, (const double *)w.relres.p, (double *)w.out_img.p, img0);
+        nd3m_finish_kernel<<<cnt, 1024, 0, st>>>(ws, gv, (const double *)w.relres.p, (double *)w.out_img.p, img0);
         *launches += 3 + 2 * refine;
         img0 += cnt;
     }

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) nd3_stencil_kernel(LuSlots ws, Lu3Params 
 
 // work = r − M p (matrix-free), relres = ‖work‖ / ‖r‖.  One CTA per image.
 template <typename Real>
-__global__ void __launch_bounds__(512) nd3_residual_kernel(LuSlots ws, Lu3Params pr, double *relres_img, int img0)
+__global__ void __launch_bounds__(1024) nd3_residual_kernel(LuSlots ws, Lu3Params pr, double *relres_img, int img0)
 {
     __shared__ double red[40];
     const int slot = blockIdx.x, tid = threadIdx.x;
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256) nd3_axpy_kernel(LuSlots ws)
 // factorisation that broke down or an error above `tol` poisons the result with NaN (→ BPLTV_ERR_NUMERIC).
 // g_k = Σ_v p_v (G_kᵀ w_k)_v per operator (:166), summed per patch of the lm×ln grid (1×1 for the scalar parameter).
 // `work` must hold the residual of the final p.  One CTA per image.
-__global__ void __launch_bounds__(512) nd3_finish_kernel(LuSlots ws, Lu3Params pr, const int *nd_info, double tol, double *out_img,
+__global__ void __launch_bounds__(1024) nd3_finish_kernel(LuSlots ws, Lu3Params pr, const int *nd_info, double tol, double *out_img,
                                                          double *relres_img, int img0)
 {
     __shared__ double red[40];
@@ -183,7 +183,7 @@ static __device__ __forceinline__ double nd3m_beta(const double *pix, int N, int
 
 // per (pixel, operator) modes + exclusive scan of the mode counts.  One CTA per image.
 template <typename Real>
-__global__ void __launch_bounds__(512) nd3m_classify_kernel(Nd3mSlots ws, Nd3mVariant gv, const Real *u_all, const Real *ubar_all,
+__global__ void __launch_bounds__(1024) nd3m_classify_kernel(Nd3mSlots ws, Nd3mVariant gv, const Real *u_all, const Real *ubar_all,
                                                             const Real *alpha_maps, int img0)
 {
     __shared__ int s_warp[33];
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(256) nd3m_stencil_kernel(Nd3mSlots ws, double 
 }
 
 // p = r − Bᵀζ; res = B p − E ζ (through the stencils) → work; relres = ‖res‖/‖b‖.  One CTA per image.
-__global__ void __launch_bounds__(512) nd3m_residual_kernel(Nd3mSlots ws, double *relres_img, int img0)
+__global__ void __launch_bounds__(1024) nd3m_residual_kernel(Nd3mSlots ws, double *relres_img, int img0)
 {
     __shared__ double red[40];
     const int slot = blockIdx.x, tid = threadIdx.x;
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(256) nd3m_axpy_kernel(Nd3mSlots ws, int dst, i
 
 // functional per operator: scalar −Σ_q ⟨(G_k p)_q, w_kq⟩ (:326); patch −p_ν (G_kᵀ w_k)_ν summed over each patch (:395-405).
 // out_img: 3·lm·ln per image, [operator][patch].  A broken factorisation or a residual above the tolerance poisons with NaN.
-__global__ void __launch_bounds__(512) nd3m_finish_kernel(Nd3mSlots ws, Nd3mVariant gv, const double *relres_img, double *out_img, int img0)
+__global__ void __launch_bounds__(1024) nd3m_finish_kernel(Nd3mSlots ws, Nd3mVariant gv, const double *relres_img, double *out_img, int img0)
 {
     __shared__ double red[40];
     const int slot = blockIdx.x, tid = threadIdx.x;

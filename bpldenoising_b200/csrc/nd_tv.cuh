@@ -65,7 +65,7 @@ static __device__ double ndtv_block_sum(double v, double *red)
 // ===========================================================================
 // per-pixel modes + exclusive scan of the mode counts (one CTA per image)
 template <typename Real>
-__global__ void __launch_bounds__(512) ndtv_classify_mult_kernel(NdTvSlots ws, NdTvVariant gv, const Real *u_all,
+__global__ void __launch_bounds__(1024) ndtv_classify_mult_kernel(NdTvSlots ws, NdTvVariant gv, const Real *u_all,
                                                                  const Real *ubar_all, const Real *alpha_map, int img0)
 {
     __shared__ int s_warp[33];
@@ -223,7 +223,7 @@ static __device__ void ndtv_dual_primal(const NdTvSlots &ws, int slot, const dou
 }
 
 // p = r − Bᵀζ; res = B p − E ζ (through the stencils) → work; relres = ‖res‖/‖b‖.  One CTA per image.
-__global__ void __launch_bounds__(512) ndtv_residual_mult_kernel(NdTvSlots ws, double *relres_img, int img0)
+__global__ void __launch_bounds__(1024) ndtv_residual_mult_kernel(NdTvSlots ws, double *relres_img, int img0)
 {
     __shared__ double red[33];
     const int slot = blockIdx.x, tid = threadIdx.x;
@@ -446,7 +446,7 @@ static __device__ __forceinline__ double ndtv_node_apply(const double *pix, int 
 
 // work = rhs − A p (matrix-free); backward error η = ‖work‖ / (‖rhs‖ + ‖|A||p|‖) → relres_img.  One CTA per image.
 // (‖work‖/‖rhs‖ alone cannot fall below eps·‖A‖‖p‖/‖rhs‖ ≈ 1e-9 here: the entries of A reach αγ.)
-__global__ void __launch_bounds__(512) ndtv_residual_node_kernel(NdTvSlots ws, double *relres_img, int img0)
+__global__ void __launch_bounds__(1024) ndtv_residual_node_kernel(NdTvSlots ws, double *relres_img, int img0)
 {
     __shared__ double red[33];
     const int slot = blockIdx.x, tid = threadIdx.x;
