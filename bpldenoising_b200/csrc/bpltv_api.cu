@@ -104,7 +104,7 @@ struct DBuf {
 // The caller's buffers stay untouched and unpinned; the slots belong to the context (ownership rule of SURVEY §8b).
 // ---------------------------------------------------------------------------
 struct HostStage {
-    static constexpr int MAXT = 8, NSLOT = 2;
+    static constexpr int MAXT = 16, NSLOT = 2;
     static constexpr size_t SLOT = (size_t)4 << 20;
     static constexpr size_t MIN_BYTES = (size_t)8 << 20;     // below this the driver's path is as good
     char *pin = nullptr;
@@ -115,7 +115,11 @@ struct HostStage {
     {
         if (pin) return true;
         const unsigned hc = std::thread::hardware_concurrency();
-        nt = (int)std::max(1u, std::min<unsigned>(MAXT, hc ? hc / 2 : 2));
+        nt = (int)std::max(1u, std::min<unsigned>(8, hc ? hc / 2 : 2));
+        {   // BPLTV_STAGE_THREADS overrides (1..16); read here, once per context and device
+            const char *e = bpltv::env_get("BPLTV_STAGE_THREADS");
+            if (e && *e) nt = std::max(1, std::min((int)MAXT, atoi(e)));
+        }
         if (cudaHostAlloc((void **)&pin, (size_t)nt * NSLOT * SLOT, cudaHostAllocDefault) != cudaSuccess) {
             cudaGetLastError(); pin = nullptr; return false;
         }
