@@ -399,7 +399,10 @@ def main():
     nbytes = M * N * O_PER_GPU * 8
     e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
            "ms_per_step": e2e_ms, "device_ms": {"upload": st["ms_upload"], "pdps": st["ms_pdps"],
-                                                 "download": st["ms_download"]}}
+                                                 "download": st["ms_download"]},
+           "copies": "inside the timed call: H2D and D2H of image chunks run on a second stream under the first and the last "
+                     "passes of the solve (libbpltv PipeIO), so device_ms.pdps contains them and upload/download read ~0; "
+                     "BPLTV_PIPE_IO=0 gives the serial upload -> solve -> download"}
 
     # the same call with PAGEABLE host arrays (what a Julia caller passes: plain Array{Float64,3})
     pg_in = np.asfortranarray(np.array(noisy, copy=True))
