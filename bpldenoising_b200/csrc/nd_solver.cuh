@@ -609,11 +609,22 @@ __global__ void nd_fwd_kernel(NdDev nd, int t0, int par, double *vec_all, size_t
         if (k1 < nP) nd_diag_store(Sb + ((b + 1) & 1) * NB * NB, tid, T, sreg);
         if (tid < nb) v[kb + tid] = ys[tid];
         for (int r = k1 + tid; r < nP; r += T) {
+            const double *col = L + (size_t)kb * nF + r;
             double s0 = 0.0, s1 = 0.0;
-#pragma unroll 4
-            for (int c = 0; c < nb; c += 2) {
-                s0 = fma(L[(size_t)(kb + c) * nF + r], ys[c], s0);
-                if (c + 1 < nb) s1 = fma(L[(size_t)(kb + c + 1) * nF + r], ys[c + 1], s1);
+            if (nb == NB) {         // all 16 loads of the row in flight together (one L2 round trip on the serial chain)
+                double l[NB];
+#pragma unroll
+                for (int c = 0; c < NB; ++c) l[c] = col[(size_t)c * nF];
+#pragma unroll
+                for (int c = 0; c < NB; c += 2) {
+                    s0 = fma(l[c], ys[c], s0);
+                    s1 = fma(l[c + 1], ys[c + 1], s1);
+                }
+            } else {
+                for (int c = 0; c < nb; c += 2) {
+                    s0 = fma(col[(size_t)c * nF], ys[c], s0);
+                    if (c + 1 < nb) s1 = fma(col[(size_t)(c + 1) * nF], ys[c + 1], s1);
+                }
             }
             v[r] -= s0 + s1;
         }
@@ -712,10 +723,13 @@ __global__ void nd_bwd_kernel(NdDev nd, int t0, double *vec_all, size_t vec_stri
             if (c < nb) {
                 const double *col = L + (size_t)(kb + c) * nF;
                 double s0 = 0.0, s1 = 0.0;
-                for (int r = k1 + lane; r < nP; r += 64) {
-                    const double l0 = col[r], l1 = r + 32 < nP ? col[r + 32] : 0.0;
+                for (int r = k1 + lane; r < nP; r += 128) {      // four loads in flight; the sums keep their order
+                    const double l0 = col[r], l1 = r + 32 < nP ? col[r + 32] : 0.0, l2 = r + 64 < nP ? col[r + 64] : 0.0,
+                                 l3 = r + 96 < nP ? col[r + 96] : 0.0;
                     s0 = fma(l0, v[r], s0);
                     if (r + 32 < nP) s1 = fma(l1, v[r + 32], s1);
+                    if (r + 64 < nP) s0 = fma(l2, v[r + 64], s0);
+                    if (r + 96 < nP) s1 = fma(l3, v[r + 96], s1);
                 }
                 s = s0 + s1;
 #pragma unroll
