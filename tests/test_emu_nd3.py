@@ -165,7 +165,7 @@ def test_patch_nonreg_gradient_multiplier_form(lib):
 def test_cluster_shared_front_factorisation_is_invisible(lib):
     """nd_factor_cluster_kernel: the front dealt over the CTAs of a cluster (assembly, write-back and trailing tiles shared,
     diagonal block and panel redundant) gives the bits of the single-CTA kernel, for 2 and 3 CTAs per front"""
-    t, u = _case(12, 31)
+    t, u = _case(10, 31)
     x = np.array([0.05, 0.04, 0.06])
     g1, s1, p1 = _run_mult(lib, u, t, x=x)
     for cs in (2, 3):
