@@ -28,3 +28,13 @@ ncu -i /tmp/prof_nd_factor.ncu-rep --page raw --csv > gpurun_out/prof_nd_factor_
 timeout 900 ncu --set full --clock-control none -k regex:nd_factor -c 24 -f -o /tmp/prof_nd_factor1 python tools/prof_grad_nd.py 128 1 5000 >> gpurun_out/ncu_nd.log 2>&1
 ncu -i /tmp/prof_nd_factor1.ncu-rep --page raw --csv > gpurun_out/prof_nd_factor_1x128_raw.csv 2>> gpurun_out/ncu_nd.log
 du -sh gpurun_out
+# sum-of-regularisers gradients on the nested-dissection solver (late round 2): timings, launch list, full capture of the
+# cluster-shared front factorisation, solve share, learn runs, the 256x256 case
+timeout 300 python tools/time_sumregs_grad.py 2>&1 | tee gpurun_out/time_sumregs_grad_nd.txt
+timeout 300 python tools/time_nd_solve_share.py 2>&1 | tee gpurun_out/time_nd_solve_share.txt
+timeout 600 python tools/time_sumregs_learn.py 2>&1 | tee gpurun_out/time_sumregs_learn.txt
+timeout 300 python tools/time_sumregs_grad_256.py 2>&1 | tee gpurun_out/time_sumregs_grad_256.txt
+timeout 200 python tools/prof_sumregs_grad_nd.py > gpurun_out/plain_nd3m.log 2>&1 && \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name regex:nd --csv --log-file gpurun_out/nd3m_launches_1x128.csv python tools/prof_sumregs_grad_nd.py > gpurun_out/ncu_nd3m.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:nd_factor_cluster -s 12 -c 2 -f -o gpurun_out/prof_nd3m_cluster python tools/prof_sumregs_grad_nd.py > gpurun_out/ncu_nd3m_full.log 2>&1
+du -sh gpurun_out
